@@ -1,0 +1,185 @@
+"""ctypes front end of the CPU oracle (TEST INFRASTRUCTURE).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this
+module; nothing under serenity_b200/ does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force: bool = False) -> str:
+    path = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle_functionals.c", "oracle.h", "harmonics_table.h")]
+    if force or not os.path.exists(path) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
+    return path
+
+
+class _Basis(C.Structure):
+    _fields_ = [("nshell", C.c_int), ("nbf", C.c_int), ("l", C.c_void_p), ("pure", C.c_void_p),
+                ("nprim", C.c_void_p), ("prim_off", C.c_void_p), ("first_bf", C.c_void_p), ("centre", C.c_void_p),
+                ("alpha", C.c_void_p), ("coeff", C.c_void_p), ("normfac", C.c_void_p)]
+
+
+class _Grid(C.Structure):
+    _fields_ = [("npts", C.c_long), ("xyz", C.c_void_p), ("w", C.c_void_p), ("blocksize", C.c_int)]
+
+
+class _Func(C.Structure):
+    _fields_ = [("ncomp", C.c_int), ("id", C.c_void_p), ("mix", C.c_void_p)]
+
+
+class Timings(C.Structure):
+    _fields_ = [("basis_on_grid", C.c_double), ("density_on_grid", C.c_double), ("functional", C.c_double),
+                ("grid_to_matrix", C.c_double), ("total", C.c_double)]
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        _LIB = C.CDLL(path)
+        _LIB.orc_functional_on_grid.restype = C.c_double
+        _LIB.orc_nblocks.restype = C.c_int
+        _LIB.orc_max_threads.restype = C.c_int
+    return _LIB
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Basis:
+    def __init__(self, tab):
+        self.tab = tab
+        self._keep = [np.ascontiguousarray(x) for x in (tab.l, tab.pure, tab.nprim, tab.prim_off, tab.first_bf,
+                                                        tab.centre, tab.alpha, tab.coeff, tab.normfac)]
+        k = self._keep
+        self.c = _Basis(tab.nshell, tab.nbf, _p(k[0]), _p(k[1]), _p(k[2]), _p(k[3]), _p(k[4]), _p(k[5]), _p(k[6]),
+                        _p(k[7]), _p(k[8]))
+        self.nbf = tab.nbf
+
+
+class Grid:
+    def __init__(self, xyz, w, blocksize=128):
+        self.xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+        self.w = np.ascontiguousarray(w, dtype=np.float64)
+        self.c = _Grid(self.w.shape[0], _p(self.xyz), _p(self.w), blocksize)
+        self.npts = self.w.shape[0]
+        self.blocksize = blocksize
+
+    @property
+    def nblocks(self):
+        return (self.npts + self.blocksize - 1) // self.blocksize
+
+
+class Functional:
+    def __init__(self, ids, mix):
+        self.ids = np.asarray(ids, dtype=np.int32)
+        self.mix = np.asarray(mix, dtype=np.float64)
+        self.c = _Func(len(self.ids), _p(self.ids), _p(self.mix))
+
+    @property
+    def is_gga(self):
+        return bool(lib().orc_functional_is_gga(C.byref(self.c)))
+
+
+def max_threads():
+    return lib().orc_max_threads()
+
+
+def set_threads(n):
+    lib().orc_set_threads(int(n))
+
+
+def basis_block(basis: Basis, grid: Grid, radial_thr: float, deriv: int, block: int):
+    n = min(grid.blocksize, grid.npts - block * grid.blocksize)
+    nb = basis.nbf
+    arrs = [np.zeros((nb, n)) for _ in range(1 + (3 if deriv >= 1 else 0) + (6 if deriv >= 2 else 0))]
+    ptrs = [_p(a) for a in arrs] + [None] * (10 - len(arrs))
+    neg = np.zeros(nb, dtype=np.int32)
+    cen = np.zeros(3)
+    got = lib().orc_basis_block(C.byref(basis.c), C.byref(grid.c), C.c_double(radial_thr), deriv, block, *ptrs,
+                                _p(neg), _p(cen))
+    assert got == n
+    # arrays are [nbf][n] (function-major == n x nbf column-major); return as [n, nbf] views
+    return [a.T for a in arrs], neg, cen
+
+
+def density_on_grid(basis: Basis, grid: Grid, radial_thr: float, P, deriv: int = 1):
+    N = grid.npts
+    P = np.asfortranarray(P, dtype=np.float64)
+    rho = np.zeros(N)
+    g = [np.zeros(N) for _ in range(3)] if deriv >= 1 else [None] * 3
+    h = np.zeros((6, N)) if deriv >= 2 else None
+    nonneg = np.zeros(grid.nblocks, dtype=np.int32)
+    lib().orc_density_on_grid(C.byref(basis.c), C.byref(grid.c), C.c_double(radial_thr), _p(P), _p(rho), _p(g[0]),
+                              _p(g[1]), _p(g[2]), _p(h), _p(nonneg))
+    return rho, g, h, nonneg
+
+
+def functional_on_grid(func: Functional, w, rho, gx=None, gy=None, gz=None):
+    N = rho.shape[0]
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    out = [np.zeros(N) for _ in range(5)]
+    gga = gx is not None
+    e = lib().orc_functional_on_grid(C.byref(func.c), C.c_long(N), _p(w), _p(np.ascontiguousarray(rho)),
+                                     _p(gx), _p(gy), _p(gz), _p(out[0]), _p(out[1]),
+                                     _p(out[2]) if gga else None, _p(out[3]) if gga else None,
+                                     _p(out[4]) if gga else None)
+    return float(e), out
+
+
+def basic_functional(fid: int, rho: float, sigma: float):
+    F, a, s = C.c_double(), C.c_double(), C.c_double()
+    rc = lib().orc_basic_functional(int(fid), C.c_double(rho), C.c_double(sigma), C.byref(F), C.byref(a), C.byref(s))
+    if rc != 0:
+        raise ValueError("unsupported functional id %d" % fid)
+    return F.value, a.value, s.value
+
+
+def scalar_to_matrix(basis: Basis, grid: Grid, radial_thr: float, block_ave_thr: float, v, gx=None, gy=None, gz=None):
+    V = np.zeros((basis.nbf, basis.nbf), order="F")
+    c = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (v, gx, gy, gz)]
+    lib().orc_scalar_to_matrix(C.byref(basis.c), C.byref(grid.c), C.c_double(radial_thr), C.c_double(block_ave_thr),
+                               _p(c[0]), _p(c[1]), _p(c[2]), _p(c[3]), _p(V))
+    return V
+
+
+def build_xc(basis: Basis, grid: Grid, func: Functional, P, radial_thr=1e-9, block_ave_thr=1e-11):
+    P = np.asfortranarray(P, dtype=np.float64)
+    V = np.zeros((basis.nbf, basis.nbf), order="F")
+    E, ne = C.c_double(), C.c_double()
+    t = Timings()
+    rc = lib().orc_build_xc(C.byref(basis.c), C.byref(grid.c), C.byref(func.c), C.c_double(radial_thr),
+                            C.c_double(block_ave_thr), _p(P), _p(V), C.byref(E), C.byref(ne), C.byref(t))
+    if rc != 0:
+        raise MemoryError("orc_build_xc failed")
+    return V, E.value, ne.value, t
+
+
+def build_nadd(basis_a: Basis, P_a, env, grid: Grid, func: Functional, radial_thr=1e-9, block_ave_thr=1e-11):
+    """env: list of (Basis, P)."""
+    P_a = np.asfortranarray(P_a, dtype=np.float64)
+    Pe = [np.asfortranarray(p, dtype=np.float64) for _, p in env]
+    nenv = len(env)
+    barr = (C.POINTER(_Basis) * max(nenv, 1))(*[C.pointer(b.c) for b, _ in env])
+    parr = (C.c_void_p * max(nenv, 1))(*[p.ctypes.data for p in Pe])
+    V = np.zeros((basis_a.nbf, basis_a.nbf), order="F")
+    E = C.c_double()
+    parts = np.zeros(2 + nenv)
+    rc = lib().orc_build_nadd(C.byref(basis_a.c), _p(P_a), nenv, barr, parr, C.byref(grid.c), C.byref(func.c),
+                              C.c_double(radial_thr), C.c_double(block_ave_thr), _p(V), C.byref(E), _p(parts))
+    if rc != 0:
+        raise MemoryError("orc_build_nadd failed")
+    return V, E.value, parts

@@ -1,0 +1,184 @@
+"""Atom-centred integration grids (input producer of the hot path).
+
+Restates the construction of the reference so that the synthetic configs have the reference's point counts,
+weights and block structure:
+  * src/grid/construction/AtomGridFactory.cpp:78-198   radial counts, Ahlrichs M3 radial map (:236-255),
+    pruned Lebedev shells (zones :170-190); Lebedev rules come from scipy.integrate.lebedev_rule
+    (the reference ships Burkardt's table, sphere_lebedev_rule.cpp - same rules, different point order)
+  * src/grid/construction/GridFactory.cpp:52-321        SSF / Becke partition weights, weight cut 1e-14
+  * src/grid/HilbertRTreeSorting.cpp:46-214             locality sort (here: 3-D Hilbert index, 10 bits/axis;
+    same purpose, curve orientation differs from the reference's lookup tables)
+Blocks are runs of `blocksize` consecutive points of the returned order.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+
+import numpy as np
+from scipy.integrate import lebedev_rule
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+# AtomGridFactory.cpp:39-52 (H..Ne shown; enough for the BASELINE configs) and :54-63
+_AHLRICHS_ALPHA = {1: 0.8, 2: 0.9, 3: 1.8, 4: 1.4, 5: 1.3, 6: 1.1, 7: 0.9, 8: 0.9, 9: 0.9, 10: 0.9}
+_CLEMENTI = {1: 1.00, 2: 0.59, 3: 3.16, 4: 2.12, 5: 1.64, 6: 1.27, 7: 1.06, 8: 0.91, 9: 0.79, 10: 0.72}
+# Bragg-Slater radii in Angstrom (Slater 1964) for the BECKE flavour's size adjustment
+_BRAGG_SLATER = {1: 0.25, 6: 0.70, 7: 0.65, 8: 0.60}
+_RAD_ACC = [13, 13, 13, 14, 15, 16, 17]
+# index -> Lebedev degree; point counts 6,14,26,38,50,74,86,110,146,170,194,230,266,302,350,434,590,770,...
+_LEB_DEGREE = [3, 5, 7, 9, 11, 13, 15, 17, 19, 21, 23, 25, 27, 29, 31, 35, 41, 47, 53, 59, 65]
+_LDVAL = [[4, 4, 4, 4, 4], [4, 4, 4, 7, 4], [4, 4, 7, 10, 7], [4, 7, 10, 13, 10], [7, 10, 13, 15, 13],
+          [10, 13, 15, 16, 15], [13, 15, 16, 17, 16]]
+_RANGES = [[0.25, 0.5, 1.0, 4.5], [0.1667, 0.5, 0.9, 3.5], [0.1, 0.4, 0.8, 2.5]]
+
+_LEB_CACHE: dict = {}
+
+
+def _lebedev(index: int):
+    if index not in _LEB_CACHE:
+        x, w = lebedev_rule(_LEB_DEGREE[index])
+        _LEB_CACHE[index] = (np.ascontiguousarray(x.T), w / (4.0 * math.pi))  # weights normalised to 1
+    return _LEB_CACHE[index]
+
+
+def _row(z: int) -> int:
+    return 1 if z <= 2 else 2 if z <= 10 else 3
+
+
+def ahlrichs_radial(alpha: float, n: int):
+    """AtomGridFactory.cpp:236-255 (M3 map with exponent 0.6, Chebyshev 2nd kind)."""
+    i = np.arange(1, n + 1, dtype=np.float64)
+    tmp = alpha / math.log(2.0)
+    xi = np.cos(i * math.pi / (n + 1.0))
+    ri = tmp * (xi + 1.0) ** 0.6 * np.log(2.0 / (1.0 - xi))
+    ln = np.log((1.0 - xi) / 2.0)
+    sq = np.sqrt((1.0 + xi) / (1.0 - xi))
+    wi = (math.pi / (n + 1.0)) * (1.0 + xi) ** 1.8 * tmp ** 3 * (sq * ln * ln - 0.6 * ln ** 3 / sq)
+    return ri[::-1].copy(), wi[::-1].copy()  # radPoints[nRadial - i]
+
+
+def becke_radial(alpha: float, n: int):
+    """AtomGridFactory.cpp:203-212."""
+    i = np.arange(1, n + 1, dtype=np.float64)
+    xi = np.cos(i * math.pi / (n + 1))
+    w = np.sqrt((1.0 + xi) ** 5 / (1.0 - xi) ** 7) * (2.0 * math.pi) * alpha ** 3 / (n + 1)
+    r = alpha * (1.0 + xi) / (1.0 - xi)
+    return r[::-1].copy(), w[::-1].copy()
+
+
+def atom_grid(z: int, acc: int, radial: str = "AHLRICHS"):
+    """One atom's reference grid (points relative to the nucleus, weights incl. 4 pi r-quadrature)."""
+    row = _row(z)
+    n_rad = int(5.0 * (_RAD_ACC[acc - 1] + row - 8))
+    if radial == "AHLRICHS":
+        rp, rw = ahlrichs_radial(_AHLRICHS_ALPHA[z], n_rad)
+    else:  # BECKE radial grid: alpha = Bragg-Slater radius (H) or half of it, in bohr
+        from .geometry import ANGSTROM_TO_BOHR
+        bs = _BRAGG_SLATER[z] * ANGSTROM_TO_BOHR
+        rp, rw = becke_radial(bs if z == 1 else 0.5 * bs, n_rad)
+    zone_row = 2 if row > 3 else row - 1
+    redp1 = 2 if (row == 1 and acc > 1) else 1
+    zones = [r * _CLEMENTI[z] for r in _RANGES[zone_row]]
+    pts, wts = [], []
+    sph_acc = 0
+    for i in range(n_rad):
+        if sph_acc < 4 and rp[i] > zones[sph_acc]:
+            sph_acc += 1
+        x, w = _lebedev(_LDVAL[acc - redp1][sph_acc])
+        pts.append(x * rp[i])
+        wts.append(w * rw[i] * 4.0 * math.pi)
+    return np.concatenate(pts, axis=0), np.concatenate(wts)
+
+
+def _load_helper():
+    path = os.path.join(_HERE, "libsxc_inputs.so")
+    if not os.path.exists(path):
+        raise RuntimeError("serenity_b200/inputs/libsxc_inputs.so missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = ctypes.CDLL(path)
+    lib.sxc_partition_weights.restype = None
+    lib.sxc_partition_weights.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_void_p,
+                                          ctypes.c_void_p]
+    return lib
+
+
+_HELPER = None
+
+
+def hilbert_index(ipts: np.ndarray, bits: int = 10) -> np.ndarray:
+    """3-D Hilbert-curve index (Skilling's transpose algorithm, vectorised). ipts: [n,3] ints in [0, 2^bits)."""
+    X = [ipts[:, 0].astype(np.uint32).copy(), ipts[:, 1].astype(np.uint32).copy(), ipts[:, 2].astype(np.uint32).copy()]
+    M = np.uint32(1 << (bits - 1))
+    Q = M
+    while Q > 1:  # inverse undo excess work
+        P = np.uint32(Q - 1)
+        for i in range(3):
+            hit = (X[i] & Q) != 0
+            X[0] = np.where(hit, X[0] ^ P, X[0])
+            t = np.where(hit, np.uint32(0), (X[0] ^ X[i]) & P)
+            X[0] ^= t
+            X[i] ^= t
+        Q = np.uint32(Q >> 1)
+    for i in range(1, 3):  # Gray encode
+        X[i] ^= X[i - 1]
+    t = np.zeros_like(X[0])
+    Q = M
+    while Q > 1:
+        t = np.where((X[2] & Q) != 0, t ^ np.uint32(Q - 1), t)
+        Q = np.uint32(Q >> 1)
+    for i in range(3):
+        X[i] ^= t
+    idx = np.zeros(ipts.shape[0], dtype=np.uint64)
+    for b in range(bits - 1, -1, -1):  # interleave, x most significant
+        for i in range(3):
+            idx = (idx << np.uint64(1)) | ((X[i] >> np.uint32(b)) & np.uint32(1)).astype(np.uint64)
+    return idx
+
+
+def molecular_grid(symbols, coords_bohr, acc: int = 4, flavour: str = "SSF", radial: str = "AHLRICHS",
+                   weight_threshold: float = 1e-14, sort: bool = True):
+    """Returns (xyz [N,3] float64 C-contiguous == Matrix3Xd column-major interleaved, w [N])."""
+    global _HELPER
+    if _HELPER is None:
+        _HELPER = _load_helper()
+    from .geometry import atomic_numbers, ANGSTROM_TO_BOHR
+    zs = atomic_numbers(symbols)
+    coords = np.ascontiguousarray(coords_bohr, dtype=np.float64)
+    nat = len(zs)
+    adist = np.ascontiguousarray(np.linalg.norm(coords[:, None, :] - coords[None, :, :], axis=2))
+    aij = None
+    if flavour == "BECKE":  # GridFactory.cpp:95-113
+        bs = np.asarray([_BRAGG_SLATER[z] for z in zs]) * ANGSTROM_TO_BOHR
+        aij = np.zeros((nat, nat))
+        for i in range(nat):
+            for j in range(nat):
+                q = math.sqrt(bs[j] / bs[i])
+                u = (q - 1.0) / (q + 1.0)
+                a = u / (u * u - 1.0)
+                aij[i, j] = min(0.5, max(-0.5, a))  # aOfAtomPair(j, i) stored at data()[j + nAtoms*i]
+        aij = np.ascontiguousarray(aij)
+    cache = {}
+    all_p, all_w = [], []
+    for k in range(nat):
+        if zs[k] not in cache:
+            cache[zs[k]] = atom_grid(zs[k], acc, radial)
+        p0, w0 = cache[zs[k]]
+        pts = np.ascontiguousarray(p0 + coords[k])
+        w = w0.copy()
+        _HELPER.sxc_partition_weights(0 if flavour == "BECKE" else 1, nat, coords.ctypes.data, adist.ctypes.data,
+                                      aij.ctypes.data if aij is not None else None, k, pts.shape[0],
+                                      pts.ctypes.data, w.ctypes.data)
+        keep = w > weight_threshold  # GridFactory.cpp:264
+        all_p.append(pts[keep])
+        all_w.append(w[keep])
+    xyz = np.concatenate(all_p, axis=0)
+    w = np.concatenate(all_w)
+    if sort:
+        lo = xyz.min(axis=0)
+        span = np.maximum(xyz.max(axis=0) - lo, 1e-300)
+        ip = np.minimum(((xyz - lo) / span * 1024.0).astype(np.int64), 1023)
+        order = np.argsort(hilbert_index(ip, 10), kind="stable")
+        xyz, w = xyz[order], w[order]
+    return np.ascontiguousarray(xyz), np.ascontiguousarray(w)
