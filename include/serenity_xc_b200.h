@@ -1,0 +1,164 @@
+/*
+ * serenity_xc_b200.h - C ABI of libserenity_xc_b200.so: the B200 (sm_100a) XC / embedding-potential build.
+ *
+ * Drop-in boundary directly underneath Serenity's unchanged Potential interface
+ * (src/potentials/Potential.h:43-86).  An adapter replaces the bodies of
+ *   FuncPotential<SCFMode>::getMatrix / getEnergy          src/potentials/FuncPotential.cpp:67-111
+ *   NAddFuncPotential<SCFMode>::getMatrix / getEnergy      src/potentials/NAddFuncPotential.cpp:192-326
+ * with calls to this library (see INTEGRATION.md and serenity_b200/host/).  All pointers are plain host
+ * (or, for the *_device entry points, CUDA device) pointers owned by the caller and only touched during the
+ * call; device state (grid, shell tables, screening plan, work buffers) persists in the context across SCF
+ * iterations.  Functions return 0 or a negative sxc_status and never throw; sxc_last_error() gives the text
+ * the adapter puts into SerenityError (src/misc/SerenityError.h:36).
+ *
+ * Conventions (identical to the reference):
+ *   - grid points 3 x N column-major = xyz interleaved, as Eigen::Matrix3Xd (src/grid/Grid.h:39-81); weights [N];
+ *     a block = `blocksize` consecutive points (BasisFunctionOnGridController.cpp:170-179)
+ *   - matrices nb x nb column-major FP64 (Eigen::MatrixXd; src/data/matrices/MatrixInBasis.h:57)
+ *   - RESTRICTED P is the total density matrix (occupation 2)
+ *   - functional components are BASIC_FUNCTIONALS enum values (src/dft/functionals/BasicFunctionals.h:39-...)
+ *     with mixing factors, as Functional::getBasicFunctionals()/getMixingFactors() return them
+ *     (src/dft/functionals/wrappers/XCFun.cpp:721-745)
+ * There is no CPU fallback: every entry point that computes fails with SXC_ERR_CUDA without a usable device.
+ */
+#ifndef SERENITY_XC_B200_H
+#define SERENITY_XC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sxc_ctx sxc_ctx;
+
+typedef enum {
+  SXC_OK = 0,
+  SXC_ERR_INVALID = -1,     /* bad argument / handle */
+  SXC_ERR_CUDA = -2,        /* CUDA runtime error (text in sxc_last_error) */
+  SXC_ERR_NOMEM = -3,       /* device or host allocation failed */
+  SXC_ERR_UNSUPPORTED = -4  /* valid in the reference, not implemented here (e.g. nspin = 2, l > 6) */
+} sxc_status;
+
+/* supported BASIC_FUNCTIONALS (XCFun aliases: BasicFunctionals.cpp:1663-1790) */
+enum {
+  SXC_NONE = 0,
+  SXC_X_SLATER = 2,     /* slaterx     */
+  SXC_C_VWN = 45,       /* vwn5c       */
+  SXC_K_TF = 66,        /* tfk         */
+  SXC_X_B88 = 80,       /* beckex      */
+  SXC_X_B88_CORR = 81,  /* beckecorrx  */
+  SXC_X_PBE = 135,      /* pbex        */
+  SXC_C_LYP = 184,      /* lypc        */
+  SXC_C_P86 = 193,      /* p86c        */
+  SXC_C_PBE = 197,      /* pbec        */
+  SXC_K_PW91 = 283,     /* pw91k (Lembarki-Chermette) */
+  SXC_K_LLP = 286       /* llp91k      */
+};
+
+/* work/timing counters of the last build on this context (for roofline reporting) */
+typedef struct {
+  int64_t npts;           /* grid points owned by this context (its shard) */
+  int64_t nblocks;        /* blocks owned */
+  int64_t sum_s;          /* sum_b s_b       (significant functions) */
+  int64_t sum_ns;         /* sum_b n_b s_b   */
+  int64_t sum_ns2;        /* sum_b n_b s_b^2 -> F_gemm = 4 * sum_ns2 */
+  int64_t sum_ns2_padded; /* same with the padded tile sizes the kernels execute */
+  int64_t sum_s2;         /* sum_b s_b^2     -> gather/accumulate bytes 16 * sum_s2 */
+  int64_t s_max;
+  int64_t nbf;
+  int64_t workspace_bytes; /* device bytes of the phi / grad phi tile buffer */
+  int32_t nchunks;         /* block chunks the build was pipelined in */
+  int32_t kernel_launches; /* kernels launched by the last build */
+  float ms_basis;          /* CUDA-event times of the last build, per phase, summed over chunks */
+  float ms_density;
+  float ms_functional;
+  float ms_scatter;
+  float ms_total;
+} sxc_stats;
+
+/* ---- context ------------------------------------------------------------------------------------------- */
+/* One context per process and GPU (one process per GPU; calls are serialised by the caller, matching the
+ * reference's single SCF driver thread).  device = CUDA ordinal. */
+int sxc_create(sxc_ctx** ctx, int device);
+void sxc_destroy(sxc_ctx* ctx);
+const char* sxc_last_error(const sxc_ctx* ctx);
+/* run on the caller's stream (cudaStream_t passed as void*); NULL = the context's own stream */
+int sxc_set_stream(sxc_ctx* ctx, void* cuda_stream);
+/* cap of the phi/grad-phi tile buffer in bytes (default: 40 % of free device memory at plan time) */
+int sxc_set_workspace_limit(sxc_ctx* ctx, int64_t bytes);
+
+/* ---- inputs -------------------------------------------------------------------------------------------- */
+/* replaces GridController::getGridPoints()/getWeights() (src/grid/GridController.cpp:31-50); re-upload only
+ * on a Grid notify.  blocksize = settings grid.blocksize (128; 1..128 supported). */
+int sxc_set_grid(sxc_ctx* ctx, int64_t npts, const double* xyz, const double* w, int blocksize, int* grid);
+/* Multi-GPU: this context evaluates only the blocks of shard `rank` out of `world` (contiguous, cost-balanced
+ * ranges of the block order, decided when the first basis is paired with the grid).  Partial V / E / N of all
+ * ranks are summed by the caller (one all-reduce).  Requires blocksize == 128.  Default rank 0 of 1. */
+int sxc_set_grid_shard(sxc_ctx* ctx, int grid, int rank, int world);
+
+/* replaces the shell data BasisFunctionOnGridController reads from BasisController
+ * (src/data/grid/BasisFunctionOnGridController.cpp:216-222,274-287): per shell l, spherical flag, primitives,
+ * extendedIndex; coeff = libint-renormalised contr[0].coeff (src/basis/Shell.h:179-181); normfac [nbf] =
+ * Shell::getNormFactors() for Cartesian shells (1.0 for spherical).  radial_threshold =
+ * settings grid.basFuncRadialThreshold (1e-9). */
+int sxc_add_basis(sxc_ctx* ctx, int nshell, const int* l, const int* pure, const int* nprim, const int* first_bf,
+                  const double* centre /*3*nshell*/, const double* alpha, const double* coeff,
+                  const double* normfac, double radial_threshold, int* basis);
+
+/* replaces XCFun::getFunctional (src/dft/functionals/wrappers/XCFun.cpp:721-745) */
+int sxc_set_functional(sxc_ctx* ctx, int ncomp, const int* basic_id, const double* mix, int* func);
+
+/* ---- the hot path -------------------------------------------------------------------------------------- */
+/* FuncPotential::getMatrix + getEnergy (src/potentials/FuncPotential.cpp:67-111): V (nb x nb per spin,
+ * overwritten), E = sum_p w_p F_p, nelec = sum_p w_p rho_p.  block_ave_threshold = settings
+ * grid.blockAveThreshold (1e-11).  With a shard set, V/E/nelec are this rank's partial sums. */
+int sxc_build_xc(sxc_ctx* ctx, int grid, int basis, int func, int nspin, const double* P,
+                 double block_ave_threshold, double* V, double* E, double* nelec);
+/* same with device-resident P and result: d_VEN holds nb*nb doubles of V followed by E and nelec
+ * (the buffer of the single all-reduce).  Asynchronous on the context's stream. */
+int sxc_build_xc_device(sxc_ctx* ctx, int grid, int basis, int func, int nspin, const double* d_P,
+                        double block_ave_threshold, double* d_VEN);
+
+/* NAddFuncPotential::getMatrix + getEnergy (src/potentials/NAddFuncPotential.cpp:192-326) with the supersystem
+ * density of SupersystemDensityOnGridController::updateData (SupersystemDensityOnGridController.cpp:95-193):
+ * V_A = scatter of v[rho_A + sum rho_env] - v[rho_A] in the active basis; E[0] = E[rho_tot], E[1] = E[rho_A],
+ * E[2+i] = E[rho_env_i]  (E_nadd = E[0] - E[1] - sum E[2+i]).  env_frozen != 0: environment densities on the
+ * grid and their energies are kept from the previous call with the same handles (they are frozen during one
+ * FDE SCF, DensityOnGridFactory.cpp:41-48). */
+int sxc_build_nadd(sxc_ctx* ctx, int grid, int func, int nspin, int basis_act, const double* P_act, int nenv,
+                   const int* basis_env, const double* const* P_env, int env_frozen, double block_ave_threshold,
+                   double* V_act, double* E /*[2+nenv]*/);
+int sxc_build_nadd_device(sxc_ctx* ctx, int grid, int func, int nspin, int basis_act, const double* d_P_act,
+                          int nenv, const int* basis_env, const double* const* d_P_env, int env_frozen,
+                          double block_ave_threshold, double* d_VE /* nbA*nbA + 2 + nenv */);
+
+/* ---- stage-level entry points (the reference classes one level below the Potentials) -------------------- */
+/* DensityOnGridCalculator::calcDensityAndGradientOnGrid (DensityOnGridCalculator.cpp:55-65): host outputs [N];
+ * gx/gy/gz may be NULL.  With a shard set only the owned points are filled (others 0). */
+int sxc_density_on_grid(sxc_ctx* ctx, int grid, int basis, const double* P, double* rho, double* gx, double* gy,
+                        double* gz);
+/* BasisFunctionOnGridController::getBlockOnGridData (BasisFunctionOnGridController.cpp:122-131), derivative
+ * level 1: n x nbf column-major values (index mu*n + p) and the negligible flags; returns n through *n_out. */
+int sxc_basis_on_grid(sxc_ctx* ctx, int grid, int basis, int block, double* val, double* dx, double* dy,
+                      double* dz, int* negligible, int* n_out);
+/* FunctionalLibrary::calcData(GRADIENTS) (FunctionalLibrary.cpp:39-72 -> XCFun.cpp:39-159), RESTRICTED, on host
+ * arrays of length npts; gx..gz and dFdG* may be NULL for LDA functionals. */
+int sxc_functional_on_grid(sxc_ctx* ctx, int func, int64_t npts, const double* w, const double* rho,
+                           const double* gx, const double* gy, const double* gz, double* epuv, double* dFdRho,
+                           double* dFdGx, double* dFdGy, double* dFdGz, double* energy);
+/* ScalarOperatorToMatrixAdder::addScalarOperatorToMatrix (ScalarOperatorToMatrixAdder.cpp:52-116); gx == NULL
+ * selects the LDA variant; the result is ADDED to V as in the reference. */
+int sxc_scalar_to_matrix(sxc_ctx* ctx, int grid, int basis, double block_ave_threshold, const double* v,
+                         const double* gx, const double* gy, const double* gz, double* V);
+
+int sxc_get_stats(const sxc_ctx* ctx, sxc_stats* out);
+/* host-only helper behind sxc_set_grid_shard: splits n blocks into `world` contiguous ranges of nearly equal summed
+ * cost; bounds[world + 1] receives the range starts (bounds[0] = 0, bounds[world] = n). */
+int sxc_balance_ranges(int n, const double* cost, int world, int* bounds);
+int sxc_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SERENITY_XC_B200_H */

@@ -1,0 +1,72 @@
+"""ctypes binding of libserenity_xc_b200.so (the C ABI of include/serenity_xc_b200.h).
+
+The product path has no CPU fallback: a missing library or a missing CUDA device raises SerenityError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libserenity_xc_b200.so")
+
+# every symbol include/serenity_xc_b200.h declares
+SYMBOLS = [
+    "sxc_create", "sxc_destroy", "sxc_last_error", "sxc_set_stream", "sxc_set_workspace_limit", "sxc_set_grid",
+    "sxc_set_grid_shard", "sxc_add_basis", "sxc_set_functional", "sxc_build_xc", "sxc_build_xc_device",
+    "sxc_build_nadd", "sxc_build_nadd_device", "sxc_density_on_grid", "sxc_basis_on_grid",
+    "sxc_functional_on_grid", "sxc_scalar_to_matrix", "sxc_get_stats", "sxc_balance_ranges", "sxc_abi_version",
+]
+
+
+class SerenityError(RuntimeError):
+    """Mirror of src/misc/SerenityError.h:36 - what the adapter throws when the C ABI returns an error."""
+
+
+class Stats(C.Structure):
+    _fields_ = [("npts", C.c_int64), ("nblocks", C.c_int64), ("sum_s", C.c_int64), ("sum_ns", C.c_int64),
+                ("sum_ns2", C.c_int64), ("sum_ns2_padded", C.c_int64), ("sum_s2", C.c_int64), ("s_max", C.c_int64),
+                ("nbf", C.c_int64), ("workspace_bytes", C.c_int64), ("nchunks", C.c_int32),
+                ("kernel_launches", C.c_int32), ("ms_basis", C.c_float), ("ms_density", C.c_float),
+                ("ms_functional", C.c_float), ("ms_scatter", C.c_float), ("ms_total", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_LIB = None
+
+
+def load():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise SerenityError("libserenity_xc_b200.so is not built (run __graft_entry__.build()); "
+                            "there is no CPU fallback for the XC build")
+    lib = C.CDLL(LIB_PATH)
+    vp, i, d, i64 = C.c_void_p, C.c_int, C.c_double, C.c_int64
+    ip = C.POINTER(C.c_int)
+    lib.sxc_create.argtypes = [C.POINTER(vp), i]
+    lib.sxc_destroy.argtypes = [vp]
+    lib.sxc_destroy.restype = None
+    lib.sxc_last_error.argtypes = [vp]
+    lib.sxc_last_error.restype = C.c_char_p
+    lib.sxc_set_stream.argtypes = [vp, vp]
+    lib.sxc_set_workspace_limit.argtypes = [vp, i64]
+    lib.sxc_set_grid.argtypes = [vp, i64, vp, vp, i, ip]
+    lib.sxc_set_grid_shard.argtypes = [vp, i, i, i]
+    lib.sxc_add_basis.argtypes = [vp, i, vp, vp, vp, vp, vp, vp, vp, vp, d, ip]
+    lib.sxc_set_functional.argtypes = [vp, i, vp, vp, ip]
+    lib.sxc_build_xc.argtypes = [vp, i, i, i, i, vp, d, vp, C.POINTER(d), C.POINTER(d)]
+    lib.sxc_build_xc_device.argtypes = [vp, i, i, i, i, vp, d, vp]
+    lib.sxc_build_nadd.argtypes = [vp, i, i, i, i, vp, i, vp, vp, i, d, vp, vp]
+    lib.sxc_build_nadd_device.argtypes = [vp, i, i, i, i, vp, i, vp, vp, i, d, vp]
+    lib.sxc_density_on_grid.argtypes = [vp, i, i, vp, vp, vp, vp, vp]
+    lib.sxc_basis_on_grid.argtypes = [vp, i, i, i, vp, vp, vp, vp, vp, ip]
+    lib.sxc_functional_on_grid.argtypes = [vp, i, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(d)]
+    lib.sxc_scalar_to_matrix.argtypes = [vp, i, i, d, vp, vp, vp, vp, vp]
+    lib.sxc_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    lib.sxc_balance_ranges.argtypes = [i, vp, i, vp]
+    _LIB = lib
+    return lib

@@ -1,0 +1,52 @@
+"""In-tree build of the native pieces (the built .so files travel to the GPU box with the repo snapshot).
+
+  libserenity_xc_b200.so   CUDA kernels + C ABI, sm_100a only  (serenity_b200/csrc/sxc_api.cu)
+  inputs/libsxc_inputs.so  host helper of the synthetic-input producer (partition weights)
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
+              "-shared"]
+
+
+def _newer(target, sources):
+    return (not os.path.exists(target)) or any(os.path.getmtime(s) > os.path.getmtime(target) for s in sources)
+
+
+def build_cuda(force=False, verbose=False):
+    csrc = os.path.join(HERE, "csrc")
+    gen = os.path.join(csrc, "harmonics_gen.cuh")
+    if not os.path.exists(gen):
+        subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "gen_harmonics.py")])
+    out = os.path.join(HERE, "libserenity_xc_b200.so")
+    srcs = [os.path.join(csrc, f) for f in os.listdir(csrc)] + [os.path.join(ROOT, "include", "serenity_xc_b200.h")]
+    if force or _newer(out, srcs):
+        nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-ccbin", "/usr/bin/g++", "-o", out,
+                                                                              os.path.join(csrc, "sxc_api.cu")]
+        subprocess.check_call(cmd)
+    return out
+
+
+def build_inputs_helper(force=False):
+    src = os.path.join(HERE, "inputs", "gridweights.c")
+    out = os.path.join(HERE, "inputs", "libsxc_inputs.so")
+    if force or _newer(out, [src]):
+        subprocess.check_call(["/usr/bin/gcc", "-O3", "-march=x86-64-v3", "-fopenmp", "-fPIC", "-shared", "-o", out, src,
+                               "-lm"])
+    return out
+
+
+def build_all(force=False, verbose=False):
+    return [build_cuda(force, verbose), build_inputs_helper(force)]
+
+
+if __name__ == "__main__":
+    print("\n".join(build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)))

@@ -1,0 +1,199 @@
+// density_kernel.cuh - rho and grad rho on a block: B = phi_s P_s on the FP64 tensor cores, fused row sums.
+//
+// Row 8a-2 of SURVEY.md: MatrixOperatorToGridTransformer::transform
+// (src/data/grid/MatrixOperatorToGridTransformer.cpp:103-165):
+//     phi_s = phi Proj,  P_s = Proj^T P Proj,  B = phi_s P_s,
+//     rho_p = sum_mu B_pmu phi_pmu,   grad rho_p = 2 sum_mu B_pmu grad phi_pmu.
+// B200 design: one CTA (16 warps, 4 x 4 warp tiles of 32 points x 32 functions) per 128-point block. The product
+// runs as DMMA m8n8k4 tiles (mma.sync ... f64, the only FP64 tensor path on sm_100a): per j-tile of 128 functions
+// the K loop streams 16-function chunks of the phi tile (cp.async, 16 B) and the matching gathered P_s chunk
+// (cp.async, 8 B, straight from the L2-resident nb x nb matrix through the block's compact->function map) through a
+// 4-stage shared-memory ring; B never leaves registers - the epilogue multiplies the accumulator fragments with
+// phi / grad phi read in fragment layout (full 32-byte sectors) and reduces over functions with warp shuffles.
+#pragma once
+
+#include "sxc_common.cuh"
+
+namespace sxc {
+
+namespace dens {
+constexpr int THREADS = 512;
+constexpr int TJ = 128;       // functions per j-tile
+constexpr int TK = 16;        // functions per K chunk
+constexpr int A_STRIDE = BP + 4;   // 132: conflict-free fragment loads (stride = 4 mod 16 doubles)
+constexpr int B_STRIDE = TK + 4;   // 20
+constexpr int STAGES = 4;
+constexpr int A_ELEMS = TK * A_STRIDE;   // 2112 doubles
+constexpr int B_ELEMS = TJ * B_STRIDE;   // 1280 doubles
+constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
+constexpr size_t smem_bytes(int s_pad_max) {
+  return (size_t)STAGES * STAGE_ELEMS * sizeof(double) + (size_t)4 * BP * 4 * sizeof(double) +
+         (size_t)(s_pad_max + TJ) * sizeof(int);
+}
+}  // namespace dens
+
+__global__ void __launch_bounds__(dens::THREADS, 1)
+k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, const int* __restrict__ order,
+          const double* __restrict__ phi_buf, double* __restrict__ rho, double* __restrict__ gx,
+          double* __restrict__ gy, double* __restrict__ gz, int* __restrict__ nonneg) {
+  using namespace dens;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* stage_base = reinterpret_cast<double*>(smem_raw);
+  double* red = stage_base + STAGES * STAGE_ELEMS;          // [4][128][4]
+  int* sig = reinterpret_cast<int*>(red + 4 * BP * 4);      // [s_pad + TJ]
+
+  const int q = order[blockIdx.x];
+  const int blk = plan.block_id[q];
+  const long first = (long)blk * g.blocksize;
+  const int n = (int)min((long)g.blocksize, g.npts - first);
+  const int s = plan.s[q];
+  const int sp = plan.s_pad[q];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (nonneg && tid == 0) nonneg[blk] = s > 0;
+  if (s == 0) {  // MatrixOperatorToGridTransformer.cpp:117-126: outputs stay zero
+    if (tid < n) {
+      rho[first + tid] = 0.0;
+      if (gx) {
+        gx[first + tid] = 0.0;
+        gy[first + tid] = 0.0;
+        gz[first + tid] = 0.0;
+      }
+    }
+    return;
+  }
+  const double* __restrict__ tile = phi_buf + plan.phi_off[q];
+  const size_t comp_stride = (size_t)sp * BP;
+  const int* __restrict__ sig_g = plan.sig_bf + (size_t)q * plan.nbf_pad;
+  for (int c = tid; c < sp + TJ; c += THREADS) sig[c] = c < sp ? sig_g[c] : 0;
+  __syncthreads();
+
+  const int nk = sp / TK;                 // K chunks per j-tile
+  const int n32 = sp / 32;                // 32-function column groups
+  const int njt = (n32 + 3) / 4;          // j-tiles of 128
+  const int total = njt * nk;
+  const int pw = warp & 3, jw = warp >> 2;
+  const int lr = lane >> 2, lc = lane & 3;
+
+  auto issue = [&](int gi) {
+    if (gi < total) {
+      const int jt = gi / nk, kc = gi - jt * nk;
+      double* As = stage_base + (gi % STAGES) * STAGE_ELEMS;
+      double* Bs = As + A_ELEMS;
+      const double* src = tile + (size_t)kc * TK * BP;
+#pragma unroll
+      for (int i = 0; i < (TK * BP / 2) / THREADS; ++i) {  // 1024 x 16 B
+        const int idx = tid + i * THREADS;
+        const int row = idx >> 6, c16 = idx & 63;
+        cp_async16(As + row * A_STRIDE + c16 * 2, src + (size_t)row * BP + c16 * 2);
+      }
+      const int j0 = jt * TJ, k0 = kc * TK;
+#pragma unroll
+      for (int i = 0; i < (TJ * TK) / THREADS; ++i) {  // 2048 x 8 B gathers: B[j][k] = P[sig[k], sig[j]]
+        const int idx = tid + i * THREADS;
+        const int k = idx & (TK - 1), j = idx >> 4;
+        cp_async8(Bs + j * B_STRIDE + k, P + (size_t)sig[k0 + k] + (size_t)sig[j0 + j] * nbf);
+      }
+    }
+    cp_async_commit();
+  };
+
+  double acc[4][4][2];
+  for (int i = tid; i < 4 * BP * 4; i += THREADS) red[i] = 0.0;
+
+  issue(0);
+  issue(1);
+  issue(2);
+  int gi = 0;
+  for (int jt = 0; jt < njt; ++jt) {
+    const bool active = (jt * 4 + jw) < n32;  // the last j-tile may hold fewer than four 32-column groups
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+      for (int nn = 0; nn < 4; ++nn) acc[m][nn][0] = acc[m][nn][1] = 0.0;
+    for (int kc = 0; kc < nk; ++kc, ++gi) {
+      cp_async_wait<STAGES - 2>();
+      __syncthreads();
+      issue(gi + 3);
+      if (active) {
+        const double* As = stage_base + (gi % STAGES) * STAGE_ELEMS;
+        const double* Bs = As + A_ELEMS;
+#pragma unroll
+        for (int ks = 0; ks < TK / 4; ++ks) {
+          double a[4], bfrag[4];
+#pragma unroll
+          for (int m = 0; m < 4; ++m) a[m] = As[(ks * 4 + lc) * A_STRIDE + pw * 32 + m * 8 + lr];
+#pragma unroll
+          for (int nn = 0; nn < 4; ++nn) bfrag[nn] = Bs[(jw * 32 + nn * 8 + lr) * B_STRIDE + ks * 4 + lc];
+#pragma unroll
+          for (int m = 0; m < 4; ++m)
+#pragma unroll
+            for (int nn = 0; nn < 4; ++nn) dmma884(acc[m][nn][0], acc[m][nn][1], a[m], bfrag[nn]);
+        }
+      }
+    }
+    if (active) {
+      // epilogue: rho += B o phi, grad rho += B o grad phi   (MatrixOperatorToGridTransformer.cpp:158-163)
+      const int jbase = jt * TJ + jw * 32 + 2 * lc;
+      double r_rho[4], r_x[4], r_y[4], r_z[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) r_rho[m] = r_x[m] = r_y[m] = r_z[m] = 0.0;
+#pragma unroll
+      for (int nn = 0; nn < 4; ++nn) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const size_t row = (size_t)(jbase + nn * 8 + e) * BP;
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const int p = pw * 32 + m * 8 + lr;
+            const double c = acc[m][nn][e];
+            r_rho[m] += c * tile[row + p];
+            if (gx) {
+              r_x[m] += c * tile[comp_stride + row + p];
+              r_y[m] += c * tile[2 * comp_stride + row + p];
+              r_z[m] += c * tile[3 * comp_stride + row + p];
+            }
+          }
+        }
+      }
+      // reduce over the 4 lanes of a fragment row; lane lc == 0 owns the (jw, point) slot of the CTA scratch
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+          r_rho[m] += __shfl_xor_sync(0xffffffffu, r_rho[m], o);
+          r_x[m] += __shfl_xor_sync(0xffffffffu, r_x[m], o);
+          r_y[m] += __shfl_xor_sync(0xffffffffu, r_y[m], o);
+          r_z[m] += __shfl_xor_sync(0xffffffffu, r_z[m], o);
+        }
+        if (lc == 0) {
+          double* dst = red + ((size_t)jw * BP + pw * 32 + m * 8 + lr) * 4;
+          dst[0] += r_rho[m];
+          dst[1] += r_x[m];
+          dst[2] += r_y[m];
+          dst[3] += r_z[m];
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  if (tid < n) {
+    double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {  // fixed order over the four j-warp groups
+      const double* a = red + ((size_t)jj * BP + tid) * 4;
+      r0 += a[0];
+      r1 += a[1];
+      r2 += a[2];
+      r3 += a[3];
+    }
+    rho[first + tid] = r0;
+    if (gx) {
+      gx[first + tid] = 2.0 * r1;
+      gy[first + tid] = 2.0 * r2;
+      gz[first + tid] = 2.0 * r3;
+    }
+  }
+}
+
+}  // namespace sxc

@@ -1,0 +1,1090 @@
+// sxc_api.cu - context, screening plans, chunked pipeline and the C ABI of libserenity_xc_b200.so.
+//
+// Orchestrates rows 8a-1 ... 8a-7 of SURVEY.md on one B200:
+//   k_screen -> k_basis -> k_density -> k_functional -> k_form_g -> k_scatter (-> k_mirror, k_reduce_partials)
+// over chunks of 128-point blocks whose phi / grad phi tiles fit the workspace (default 40 % of free HBM), phi being
+// evaluated ONCE per build (the reference evaluates it twice, MatrixOperatorToGridTransformer.cpp:103 and
+// ScalarOperatorToMatrixAdder.cpp:69-70).  Host side is plain C++17; no torch types cross this boundary.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <numeric>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/serenity_xc_b200.h"
+#include "basis_kernels.cuh"
+#include "density_kernel.cuh"
+#include "functionals.cuh"
+#include "scatter_kernel.cuh"
+#include "sxc_common.cuh"
+
+using namespace sxc;
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------- device memory
+struct DevMem {
+  void* p = nullptr;
+  size_t bytes = 0;
+  DevMem() = default;
+  DevMem(const DevMem&) = delete;
+  DevMem& operator=(const DevMem&) = delete;
+  ~DevMem() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  cudaError_t ensure(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    release();
+    cudaError_t e = cudaMalloc(&p, need);
+    if (e == cudaSuccess) bytes = need;
+    return e;
+  }
+  template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct Grid {
+  long npts = 0;
+  int blocksize = 128;
+  int nblocks = 0;
+  int nlit = 0;  // literal 128-point blocks of the functional evaluation
+  DevMem xyzw;   // x[N] y[N] z[N] w[N]
+  int rank = 0, world = 1;
+  bool owner_fixed = false;
+  int own_first = 0, own_count = 0;  // owned contiguous block range
+  DevMem dens;     // rho, gx, gy, gz            [4][N]
+  DevMem pot;      // v_rho, v_gx, v_gy, v_gz    [4][N]
+  DevMem tot;      // supersystem density        [4][N]   (NAdd)
+  DevMem envsum;   // sum of environment densities [4][N] (NAdd, cached while frozen)
+  DevMem parts;    // e_part, n_part, e_part2 [3][nlit]
+  std::vector<int> env_key;       // basis handles the cached envsum belongs to
+  std::vector<double> env_energy; // cached E[rho_env_i] (this rank's partial sums)
+  bool env_valid = false;
+  GridView view() const {
+    GridView v;
+    v.npts = npts;
+    v.blocksize = blocksize;
+    v.nblocks = nblocks;
+    v.x = xyzw.as<double>();
+    v.y = v.x + npts;
+    v.z = v.y + npts;
+    v.w = v.z + npts;
+    return v;
+  }
+};
+
+struct Basis {
+  int nshell = 0, nbf = 0;
+  double radial_thr = 1e-9;
+  DevMem ints;  // l, pure, nprim, prim_off, first_bf, nfunc  [6][nshell]
+  DevMem dbl;   // centre[3 nshell], alpha, coeff, normfac
+  size_t nprim_total = 0;
+  int lmax = 0;
+  ShellView view() const {
+    ShellView v;
+    v.nshell = nshell;
+    v.nbf = nbf;
+    const int* i = ints.as<int>();
+    v.l = i;
+    v.pure = i + nshell;
+    v.nprim = i + 2 * nshell;
+    v.prim_off = i + 3 * nshell;
+    v.first_bf = i + 4 * nshell;
+    v.nfunc = i + 5 * nshell;
+    const double* d = dbl.as<double>();
+    v.centre = d;
+    v.alpha = d + 3 * (size_t)nshell;
+    v.coeff = v.alpha + nprim_total;
+    v.normfac = v.coeff + nprim_total;
+    v.radial_thr = radial_thr;
+    v.exp_thr = -std::log(radial_thr);
+    return v;
+  }
+};
+
+struct Chunk {
+  int slot0 = 0, nslots = 0;
+  size_t doubles = 0;     // tile buffer size of the chunk
+  int order_off = 0;      // offset into Plan::order (sorted slots of this chunk)
+  int item_off = 0, nitems = 0;  // scatter work items
+};
+
+struct Plan {
+  int grid = -1, basis = -1;
+  int nown = 0;
+  int nbf_pad = 0;
+  int s_pad_max = 0;
+  DevMem block_id, nsig_shell, s, sig_shell, sig_c0, sig_bf, s_pad, phi_off, order, items, skip;
+  std::vector<int> h_s, h_s_pad;
+  std::vector<Chunk> chunks;
+  sxc_stats stats{};
+  PlanView view() const {
+    PlanView v;
+    v.nown = nown;
+    v.block_id = block_id.as<int>();
+    v.nsig_shell = nsig_shell.as<int>();
+    v.s = s.as<int>();
+    v.sig_shell = sig_shell.as<int>();
+    v.sig_c0 = sig_c0.as<int>();
+    v.sig_bf = sig_bf.as<int>();
+    v.nbf_pad = nbf_pad;
+    v.s_pad = s_pad.as<int>();
+    v.phi_off = phi_off.as<long long>();
+    return v;
+  }
+};
+
+}  // namespace
+
+struct sxc_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
+  std::string err;
+  std::vector<std::unique_ptr<Grid>> grids;
+  std::vector<std::unique_ptr<Basis>> bases;
+  std::vector<FuncView> funcs;
+  std::map<std::pair<int, int>, std::unique_ptr<Plan>> plans;
+  DevMem phi;     // tile workspace (one chunk)
+  DevMem dP;      // staged density matrices (host API)
+  DevMem dOut;    // staged V | E | N (host API)
+  DevMem scratch; // small device scalars
+  int64_t ws_limit = 0;
+  sxc_stats stats{};
+  int launches = 0;
+  bool attrs_set = false;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  float ms[5] = {0, 0, 0, 0, 0};
+  bool timing = false;
+};
+
+namespace {
+
+int fail(sxc_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+
+#define CU(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess)                                                                            \
+      return fail(ctx, e_ == cudaErrorMemoryAllocation ? SXC_ERR_NOMEM : SXC_ERR_CUDA, "%s: %s (%s:%d)", #call, \
+                  cudaGetErrorString(e_), __FILE__, __LINE__);                                        \
+  } while (0)
+
+#define LAUNCH_CHECK()                                                                                      \
+  do {                                                                                                      \
+    ++ctx->launches;                                                                                        \
+    cudaError_t e_ = cudaGetLastError();                                                                    \
+    if (e_ != cudaSuccess)                                                                                  \
+      return fail(ctx, SXC_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+#define TRY(call)          \
+  do {                     \
+    int rc_ = (call);      \
+    if (rc_ != SXC_OK) return rc_; \
+  } while (0)
+
+Grid* get_grid(sxc_ctx* ctx, int h) { return (h >= 0 && h < (int)ctx->grids.size()) ? ctx->grids[h].get() : nullptr; }
+Basis* get_basis(sxc_ctx* ctx, int h) { return (h >= 0 && h < (int)ctx->bases.size()) ? ctx->bases[h].get() : nullptr; }
+
+int set_kernel_attrs(sxc_ctx* ctx) {
+  if (ctx->attrs_set) return SXC_OK;
+  CU(cudaFuncSetAttribute(k_density, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CU(cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  ctx->attrs_set = true;
+  return SXC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- plan
+int run_screen(sxc_ctx* ctx, const Grid& g, const Basis& b, const Plan& p) {
+  if (p.nown == 0) return SXC_OK;
+  k_screen<<<p.nown, 128, 0, ctx->stream>>>(g.view(), b.view(), p.view());
+  LAUNCH_CHECK();
+  return SXC_OK;
+}
+
+int alloc_plan_arrays(sxc_ctx* ctx, Plan& p, const Basis& b, const std::vector<int>& block_ids) {
+  p.nown = (int)block_ids.size();
+  p.nbf_pad = ((b.nbf + SPAD - 1) / SPAD) * SPAD;
+  const size_t n = std::max<size_t>(p.nown, 1);
+  CU(p.block_id.ensure(n * sizeof(int)));
+  CU(p.nsig_shell.ensure(n * sizeof(int)));
+  CU(p.s.ensure(n * sizeof(int)));
+  CU(p.sig_shell.ensure(n * b.nshell * sizeof(int)));
+  CU(p.sig_c0.ensure(n * b.nshell * sizeof(int)));
+  CU(p.sig_bf.ensure(n * p.nbf_pad * sizeof(int)));
+  CU(p.s_pad.ensure(n * sizeof(int)));
+  CU(p.phi_off.ensure(n * sizeof(long long)));
+  CU(p.skip.ensure(n * sizeof(int)));
+  if (p.nown)
+    CU(cudaMemcpyAsync(p.block_id.p, block_ids.data(), p.nown * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  return SXC_OK;
+}
+
+int64_t workspace_limit(sxc_ctx* ctx) {
+  if (ctx->ws_limit > 0) return ctx->ws_limit;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return (int64_t)4 << 30;
+  // keep what is already reserved for the workspace in the balance
+  return (int64_t)((free_b + ctx->phi.bytes) * 0.4);
+}
+
+int get_plan(sxc_ctx* ctx, int gh, int bh, Plan** out) {
+  Grid* g = get_grid(ctx, gh);
+  Basis* b = get_basis(ctx, bh);
+  if (!g || !b) return fail(ctx, SXC_ERR_INVALID, "invalid grid (%d) or basis (%d) handle", gh, bh);
+  auto key = std::make_pair(gh, bh);
+  auto it = ctx->plans.find(key);
+  if (it != ctx->plans.end()) {
+    *out = it->second.get();
+    return SXC_OK;
+  }
+  TRY(set_kernel_attrs(ctx));
+  // 1. ownership: contiguous block ranges balanced on n_b s_b^2, fixed by the first basis
+  if (!g->owner_fixed) {
+    if (g->world == 1) {
+      g->own_first = 0;
+      g->own_count = g->nblocks;
+    } else {
+      Plan tmp;
+      std::vector<int> all(g->nblocks);
+      std::iota(all.begin(), all.end(), 0);
+      TRY(alloc_plan_arrays(ctx, tmp, *b, all));
+      TRY(run_screen(ctx, *g, *b, tmp));
+      std::vector<int> s(g->nblocks);
+      CU(cudaMemcpyAsync(s.data(), tmp.s.p, s.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+      std::vector<double> cost(g->nblocks);
+      for (int i = 0; i < g->nblocks; ++i) {
+        const double sp = std::ceil(std::max(s[i], 1) / (double)SPAD) * SPAD;
+        cost[i] = 128.0 * sp * sp + 3.0e4 * sp + 1.0e5;  // GEMMs + basis evaluation + fixed per-block work
+      }
+      std::vector<int> bound(g->world + 1);
+      sxc_balance_ranges(g->nblocks, cost.data(), g->world, bound.data());
+      g->own_first = bound[g->rank];
+      g->own_count = bound[g->rank + 1] - bound[g->rank];
+    }
+    g->owner_fixed = true;
+  }
+  // 2. screening of the owned blocks
+  auto plan = std::make_unique<Plan>();
+  Plan& p = *plan;
+  p.grid = gh;
+  p.basis = bh;
+  std::vector<int> ids(g->own_count);
+  std::iota(ids.begin(), ids.end(), g->own_first);
+  TRY(alloc_plan_arrays(ctx, p, *b, ids));
+  TRY(run_screen(ctx, *g, *b, p));
+  p.h_s.resize(p.nown);
+  if (p.nown) CU(cudaMemcpyAsync(p.h_s.data(), p.s.p, p.nown * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  // 3. padded sizes, chunking, work orders
+  p.h_s_pad.resize(p.nown);
+  std::vector<long long> off(p.nown);
+  const int64_t limit = workspace_limit(ctx);
+  sxc_stats& st = p.stats;
+  st = sxc_stats{};
+  st.nbf = b->nbf;
+  st.nblocks = p.nown;
+  Chunk cur;
+  cur.slot0 = 0;
+  for (int q = 0; q < p.nown; ++q) {
+    const int s = p.h_s[q];
+    const int sp = std::max(SPAD, ((s + SPAD - 1) / SPAD) * SPAD);
+    p.h_s_pad[q] = sp;
+    p.s_pad_max = std::max(p.s_pad_max, sp);
+    const size_t tile = (size_t)4 * sp * BP;
+    if (cur.nslots > 0 && (int64_t)((cur.doubles + tile) * sizeof(double)) > limit) {
+      p.chunks.push_back(cur);
+      cur = Chunk();
+      cur.slot0 = q;
+    }
+    off[q] = (long long)cur.doubles;
+    cur.doubles += tile;
+    cur.nslots++;
+    const long first = (long)ids[q] * g->blocksize;
+    const long n = std::min<long>(g->blocksize, g->npts - first);
+    st.npts += n;
+    st.sum_s += s;
+    st.sum_ns += n * s;
+    st.sum_ns2 += n * (int64_t)s * s;
+    st.sum_ns2_padded += (int64_t)BP * sp * sp;
+    st.sum_s2 += (int64_t)s * s;
+    st.s_max = std::max<int64_t>(st.s_max, s);
+  }
+  if (cur.nslots > 0) p.chunks.push_back(cur);
+  if (g->blocksize != FUNC_BLOCK && p.chunks.size() > 1)
+    return fail(ctx, SXC_ERR_UNSUPPORTED, "grid.blocksize != 128 needs the whole grid in one workspace chunk");
+  st.nchunks = (int)p.chunks.size();
+  std::vector<int> order(std::max(p.nown, 1));
+  std::vector<ScatterItem> items;
+  for (Chunk& c : p.chunks) {
+    c.order_off = c.slot0;
+    std::iota(order.begin() + c.slot0, order.begin() + c.slot0 + c.nslots, c.slot0);
+    std::stable_sort(order.begin() + c.slot0, order.begin() + c.slot0 + c.nslots,
+                     [&](int a, int bq) { return p.h_s_pad[a] > p.h_s_pad[bq]; });
+    c.item_off = (int)items.size();
+    std::vector<std::pair<long, ScatterItem>> tmp;
+    for (int k = 0; k < c.nslots; ++k) {
+      const int q = c.slot0 + k;
+      if (p.h_s[q] == 0) continue;
+      const int nt = (p.h_s_pad[q] + scat::TI - 1) / scat::TI;
+      for (int it = 0; it < nt; ++it) tmp.push_back({(long)(nt - it) * 1, ScatterItem{q, it}});
+    }
+    std::stable_sort(tmp.begin(), tmp.end(), [](const auto& a, const auto& bq) { return a.first > bq.first; });
+    for (auto& t : tmp) items.push_back(t.second);
+    c.nitems = (int)items.size() - c.item_off;
+    st.workspace_bytes = std::max<int64_t>(st.workspace_bytes, (int64_t)(c.doubles * sizeof(double)));
+  }
+  CU(p.order.ensure(order.size() * sizeof(int)));
+  CU(p.items.ensure(std::max<size_t>(items.size(), 1) * sizeof(ScatterItem)));
+  if (p.nown) {
+    CU(cudaMemcpyAsync(p.s_pad.p, p.h_s_pad.data(), p.nown * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(p.phi_off.p, off.data(), p.nown * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(p.order.p, order.data(), p.nown * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (!items.empty())
+    CU(cudaMemcpyAsync(p.items.p, items.data(), items.size() * sizeof(ScatterItem), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (dens::smem_bytes(p.s_pad_max) > 227 * 1024 || scat::smem_bytes(p.s_pad_max) > 227 * 1024)
+    return fail(ctx, SXC_ERR_UNSUPPORTED, "more than %d significant functions in one block", p.s_pad_max);
+  *out = plan.get();
+  ctx->plans[key] = std::move(plan);
+  return SXC_OK;
+}
+
+int ensure_point_arrays(sxc_ctx* ctx, Grid& g, bool nadd) {
+  const size_t n4 = (size_t)4 * std::max<long>(g.npts, 1) * sizeof(double);
+  if (g.dens.bytes < n4) {
+    CU(g.dens.ensure(n4));
+    CU(cudaMemsetAsync(g.dens.p, 0, n4, ctx->stream));
+  }
+  if (g.pot.bytes < n4) {
+    CU(g.pot.ensure(n4));
+    CU(cudaMemsetAsync(g.pot.p, 0, n4, ctx->stream));
+  }
+  CU(g.parts.ensure((size_t)3 * std::max(g.nlit, 1) * sizeof(double)));
+  if (nadd) {
+    if (g.tot.bytes < n4) {
+      CU(g.tot.ensure(n4));
+      CU(cudaMemsetAsync(g.tot.p, 0, n4, ctx->stream));
+    }
+    if (g.envsum.bytes < n4) {
+      CU(g.envsum.ensure(n4));
+      g.env_valid = false;
+    }
+  }
+  return SXC_OK;
+}
+
+// phases of one chunk ------------------------------------------------------------------------------------------
+int phase_basis(sxc_ctx* ctx, const Grid& g, const Basis& b, const Plan& p, const Chunk& c) {
+  CU(ctx->phi.ensure(c.doubles * sizeof(double)));
+  k_basis<<<c.nslots, BASIS_GROUPS * BP, 0, ctx->stream>>>(g.view(), b.view(), p.view(), c.slot0,
+                                                            p.order.as<int>() + c.order_off, ctx->phi.as<double>());
+  LAUNCH_CHECK();
+  return SXC_OK;
+}
+
+int phase_density(sxc_ctx* ctx, const Grid& g, const Basis& b, const Plan& p, const Chunk& c, const double* dP,
+                  double* dens4, bool with_grad, int* nonneg) {
+  const long N = g.npts;
+  k_density<<<c.nslots, dens::THREADS, dens::smem_bytes(p.s_pad_max), ctx->stream>>>(
+      g.view(), p.view(), b.nbf, dP, p.order.as<int>() + c.order_off, ctx->phi.as<double>(), dens4,
+      with_grad ? dens4 + N : nullptr, with_grad ? dens4 + 2 * N : nullptr, with_grad ? dens4 + 3 * N : nullptr, nonneg);
+  LAUNCH_CHECK();
+  return SXC_OK;
+}
+
+// functional on the literal blocks covered by the chunk (or on all of them when blocksize != 128)
+int phase_functional(sxc_ctx* ctx, const Grid& g, const Plan& p, const Chunk& c, const FuncView& f, const double* dens4,
+                     double sign, int accumulate, double* pot4, double* e_part, double* n_part) {
+  const long N = g.npts;
+  const GridView gv = g.view();
+  const bool lit_is_block = g.blocksize == FUNC_BLOCK;
+  const int nb = lit_is_block ? c.nslots : g.nlit;
+  if (nb == 0) return SXC_OK;
+  const int* list = lit_is_block ? p.block_id.as<int>() + c.slot0 : nullptr;
+  k_functional<<<nb, FUNC_BLOCK, 0, ctx->stream>>>(f, N, list, gv.w, dens4, dens4 + N, dens4 + 2 * N, dens4 + 3 * N,
+                                                   sign, accumulate, nullptr, pot4, f.gga ? pot4 + N : nullptr,
+                                                   f.gga ? pot4 + 2 * N : nullptr, f.gga ? pot4 + 3 * N : nullptr,
+                                                   e_part, n_part);
+  LAUNCH_CHECK();
+  return SXC_OK;
+}
+
+int phase_scatter(sxc_ctx* ctx, const Grid& g, const Basis& b, const Plan& p, const Chunk& c, bool gga,
+                  double block_ave_thr, const double* pot4, double* dW) {
+  const long N = g.npts;
+  k_form_g<<<c.nslots, 256, 0, ctx->stream>>>(g.view(), p.view(), p.order.as<int>() + c.order_off, block_ave_thr, pot4,
+                                              gga ? pot4 + N : nullptr, gga ? pot4 + 2 * N : nullptr,
+                                              gga ? pot4 + 3 * N : nullptr, ctx->phi.as<double>(), p.skip.as<int>());
+  LAUNCH_CHECK();
+  if (c.nitems > 0) {
+    k_scatter<<<c.nitems, scat::THREADS, scat::smem_bytes(p.s_pad_max), ctx->stream>>>(
+        p.view(), b.nbf, p.items.as<ScatterItem>() + c.item_off, p.skip.as<int>(), ctx->phi.as<double>(), dW);
+    LAUNCH_CHECK();
+  }
+  return SXC_OK;
+}
+
+int finish_matrix(sxc_ctx* ctx, int nbf, double* dW) {
+  dim3 blk(32, 8), grd((nbf + 31) / 32, (nbf + 7) / 8);
+  k_mirror<<<grd, blk, 0, ctx->stream>>>(nbf, dW);
+  LAUNCH_CHECK();
+  return SXC_OK;
+}
+
+int reduce_to(sxc_ctx* ctx, const double* part, int n, double* out) {
+  k_reduce_partials<<<1, 256, 0, ctx->stream>>>(part, n, 1.0, 0, out);
+  LAUNCH_CHECK();
+  return SXC_OK;
+}
+
+struct PhaseTimer {
+  sxc_ctx* ctx;
+  int slot;
+  cudaEvent_t a = nullptr, b = nullptr;
+  PhaseTimer(sxc_ctx* c, int s) : ctx(c), slot(s) {
+    if (ctx->timing) {
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      cudaEventRecord(a, ctx->stream);
+    }
+  }
+  void stop(std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>>& sink) {
+    if (ctx->timing) {
+      cudaEventRecord(b, ctx->stream);
+      sink.push_back({slot, {a, b}});
+    }
+  }
+};
+using TimerSink = std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>>;
+
+void collect_timers(sxc_ctx* ctx, TimerSink& sink) {
+  for (int i = 0; i < 5; ++i) ctx->ms[i] = 0.f;
+  for (auto& t : sink) {
+    float ms = 0.f;
+    cudaEventSynchronize(t.second.second);
+    cudaEventElapsedTime(&ms, t.second.first, t.second.second);
+    ctx->ms[t.first] += ms;
+    cudaEventDestroy(t.second.first);
+    cudaEventDestroy(t.second.second);
+  }
+  sink.clear();
+}
+
+// ---------------------------------------------------------------------------------------------- builds
+int build_xc_device(sxc_ctx* ctx, int gh, int bh, int fh, int nspin, const double* dP, double thr, double* dVEN,
+                    TimerSink* sink) {
+  if (nspin != 1) return fail(ctx, SXC_ERR_UNSUPPORTED, "UNRESTRICTED (nspin = 2) is not implemented yet");
+  if (fh < 0 || fh >= (int)ctx->funcs.size()) return fail(ctx, SXC_ERR_INVALID, "invalid functional handle %d", fh);
+  Plan* pp = nullptr;
+  TRY(get_plan(ctx, gh, bh, &pp));
+  Plan& p = *pp;
+  Grid& g = *get_grid(ctx, gh);
+  Basis& b = *get_basis(ctx, bh);
+  const FuncView f = ctx->funcs[fh];
+  TRY(ensure_point_arrays(ctx, g, false));
+  const int launches0 = ctx->launches;
+  const size_t nb2 = (size_t)b.nbf * b.nbf;
+  double* parts = g.parts.as<double>();
+  CU(cudaMemsetAsync(dVEN, 0, (nb2 + 2) * sizeof(double), ctx->stream));
+  CU(cudaMemsetAsync(parts, 0, (size_t)3 * std::max(g.nlit, 1) * sizeof(double), ctx->stream));
+  PhaseTimer t_all(ctx, 4);
+  {  // the screening is part of every build in the reference (calculateBasisFunctionData :211-255)
+    PhaseTimer t(ctx, 0);
+    TRY(run_screen(ctx, g, b, p));
+    if (sink) t.stop(*sink);
+  }
+  for (const Chunk& c : p.chunks) {
+    {
+      PhaseTimer t(ctx, 0);
+      TRY(phase_basis(ctx, g, b, p, c));
+      if (sink) t.stop(*sink);
+    }
+    {
+      PhaseTimer t(ctx, 1);
+      TRY(phase_density(ctx, g, b, p, c, dP, g.dens.as<double>(), true, nullptr));
+      if (sink) t.stop(*sink);
+    }
+    {
+      PhaseTimer t(ctx, 2);
+      TRY(phase_functional(ctx, g, p, c, f, g.dens.as<double>(), 1.0, 0, g.pot.as<double>(), parts, parts + g.nlit));
+      if (sink) t.stop(*sink);
+    }
+    if (f.ncomp > 0) {
+      PhaseTimer t(ctx, 3);
+      TRY(phase_scatter(ctx, g, b, p, c, f.gga != 0, thr, g.pot.as<double>(), dVEN));
+      if (sink) t.stop(*sink);
+    }
+  }
+  TRY(finish_matrix(ctx, b.nbf, dVEN));
+  TRY(reduce_to(ctx, parts, g.nlit, dVEN + nb2));
+  TRY(reduce_to(ctx, parts + g.nlit, g.nlit, dVEN + nb2 + 1));
+  if (sink) t_all.stop(*sink);
+  ctx->stats = p.stats;
+  ctx->stats.kernel_launches = ctx->launches - launches0;
+  return SXC_OK;
+}
+
+__global__ void k_add4(long N, int blocksize, const int* __restrict__ block_id, const double* __restrict__ a,
+                       const double* __restrict__ b, double* __restrict__ out) {
+  const long first = (long)block_id[blockIdx.x] * blocksize;
+  const long n = min((long)blocksize, N - first);
+  for (int c = 0; c < 4; ++c)
+    for (long i = threadIdx.x; i < n; i += blockDim.x) {
+      const size_t k = (size_t)c * N + first + i;
+      out[k] = a[k] + (b ? b[k] : 0.0);
+    }
+}
+
+int build_nadd_device(sxc_ctx* ctx, int gh, int fh, int nspin, int bA, const double* dPA, int nenv, const int* bE,
+                      const double* const* dPE, int frozen, double thr, double* dVE, TimerSink* sink) {
+  if (nspin != 1) return fail(ctx, SXC_ERR_UNSUPPORTED, "UNRESTRICTED (nspin = 2) is not implemented yet");
+  if (fh < 0 || fh >= (int)ctx->funcs.size()) return fail(ctx, SXC_ERR_INVALID, "invalid functional handle %d", fh);
+  if (nenv < 0) return fail(ctx, SXC_ERR_INVALID, "nenv < 0");
+  Grid* gp = get_grid(ctx, gh);
+  Basis* ba = get_basis(ctx, bA);
+  if (!gp || !ba) return fail(ctx, SXC_ERR_INVALID, "invalid grid or active basis handle");
+  Grid& g = *gp;
+  const FuncView f = ctx->funcs[fh];
+  Plan* pa = nullptr;
+  TRY(get_plan(ctx, gh, bA, &pa));  // the active system fixes the block ownership
+  TRY(ensure_point_arrays(ctx, g, true));
+  const long N = g.npts;
+  const int launches0 = ctx->launches;
+  const size_t nb2 = (size_t)ba->nbf * ba->nbf;
+  double* parts = g.parts.as<double>();
+  PhaseTimer t_all(ctx, 4);
+  CU(cudaMemsetAsync(dVE, 0, (nb2 + 2 + nenv) * sizeof(double), ctx->stream));
+  CU(ctx->scratch.ensure(64 * sizeof(double)));
+
+  // environment: rho_env on the supersystem grid, summed; E[rho_env_i] (NAddEnergyHelper, NAddFuncPotential.cpp:502-516)
+  std::vector<int> key(bE, bE + nenv);
+  key.push_back(fh);
+  const bool reuse = frozen && g.env_valid && g.env_key == key;
+  if (!reuse) {
+    CU(cudaMemsetAsync(g.envsum.p, 0, (size_t)4 * N * sizeof(double), ctx->stream));
+    g.env_energy.assign(nenv, 0.0);
+    for (int i = 0; i < nenv; ++i) {
+      Basis* be = get_basis(ctx, bE[i]);
+      if (!be) return fail(ctx, SXC_ERR_INVALID, "invalid environment basis handle %d", bE[i]);
+      Plan* pe = nullptr;
+      TRY(get_plan(ctx, gh, bE[i], &pe));
+      CU(cudaMemsetAsync(parts, 0, (size_t)3 * std::max(g.nlit, 1) * sizeof(double), ctx->stream));
+      TRY(run_screen(ctx, g, *be, *pe));
+      for (const Chunk& c : pe->chunks) {
+        PhaseTimer t0(ctx, 0);
+        TRY(phase_basis(ctx, g, *be, *pe, c));
+        if (sink) t0.stop(*sink);
+        PhaseTimer t1(ctx, 1);
+        TRY(phase_density(ctx, g, *be, *pe, c, dPE[i], g.dens.as<double>(), true, nullptr));
+        if (pe->nown) {
+          k_add4<<<c.nslots, 128, 0, ctx->stream>>>(N, g.blocksize, pe->block_id.as<int>() + c.slot0, g.envsum.as<double>(),
+                                                    g.dens.as<double>(), g.envsum.as<double>());
+          LAUNCH_CHECK();
+        }
+        if (sink) t1.stop(*sink);
+        PhaseTimer t2(ctx, 2);
+        // energy only: the potential goes to g.pot and is overwritten later
+        TRY(phase_functional(ctx, g, *pe, c, f, g.dens.as<double>(), 1.0, 0, g.pot.as<double>(), parts, nullptr));
+        if (sink) t2.stop(*sink);
+      }
+      TRY(reduce_to(ctx, parts, g.nlit, ctx->scratch.as<double>() + i));
+    }
+    if (nenv > 0) {
+      CU(cudaMemcpyAsync(g.env_energy.data(), ctx->scratch.p, nenv * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+    }
+    g.env_key = key;
+    g.env_valid = true;
+  }
+  if (nenv > 0)
+    CU(cudaMemcpyAsync(dVE + nb2 + 2, g.env_energy.data(), nenv * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+
+  // active system: rho_A, rho_tot = rho_A + sum_env, v = v[rho_tot] - v[rho_A]  (NAddFuncPotential.cpp:197-225)
+  Plan& p = *pa;
+  CU(cudaMemsetAsync(parts, 0, (size_t)3 * std::max(g.nlit, 1) * sizeof(double), ctx->stream));
+  TRY(run_screen(ctx, g, *ba, p));
+  for (const Chunk& c : p.chunks) {
+    PhaseTimer t0(ctx, 0);
+    TRY(phase_basis(ctx, g, *ba, p, c));
+    if (sink) t0.stop(*sink);
+    PhaseTimer t1(ctx, 1);
+    TRY(phase_density(ctx, g, *ba, p, c, dPA, g.dens.as<double>(), true, nullptr));
+    if (p.nown) {
+      k_add4<<<c.nslots, 128, 0, ctx->stream>>>(N, g.blocksize, p.block_id.as<int>() + c.slot0, g.dens.as<double>(),
+                                                g.envsum.as<double>(), g.tot.as<double>());
+      LAUNCH_CHECK();
+    }
+    if (sink) t1.stop(*sink);
+    PhaseTimer t2(ctx, 2);
+    TRY(phase_functional(ctx, g, p, c, f, g.tot.as<double>(), 1.0, 0, g.pot.as<double>(), parts, nullptr));
+    TRY(phase_functional(ctx, g, p, c, f, g.dens.as<double>(), -1.0, 1, g.pot.as<double>(), parts + g.nlit, nullptr));
+    if (sink) t2.stop(*sink);
+    if (f.ncomp > 0) {
+      PhaseTimer t3(ctx, 3);
+      TRY(phase_scatter(ctx, g, *ba, p, c, f.gga != 0, thr, g.pot.as<double>(), dVE));
+      if (sink) t3.stop(*sink);
+    }
+  }
+  TRY(finish_matrix(ctx, ba->nbf, dVE));
+  TRY(reduce_to(ctx, parts, g.nlit, dVE + nb2));
+  TRY(reduce_to(ctx, parts + g.nlit, g.nlit, dVE + nb2 + 1));
+  if (sink) t_all.stop(*sink);
+  ctx->stats = p.stats;
+  ctx->stats.kernel_launches = ctx->launches - launches0;
+  return SXC_OK;
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+int sxc_abi_version(void) { return 1; }
+
+// host-only: contiguous ranges [bounds[r], bounds[r+1]) of nearly equal summed cost
+int sxc_balance_ranges(int n, const double* cost, int world, int* bounds) {
+  if (n < 0 || world < 1 || !bounds || (n > 0 && !cost)) return SXC_ERR_INVALID;
+  double total = 0.0;
+  for (int i = 0; i < n; ++i) total += cost[i];
+  for (int r = 0; r <= world; ++r) bounds[r] = n;
+  bounds[0] = 0;
+  double acc = 0.0;
+  int r = 1;
+  for (int i = 0; i < n && r < world; ++i) {
+    acc += cost[i];
+    while (r < world && acc >= total * r / world) bounds[r++] = i + 1;
+  }
+  return SXC_OK;
+}
+
+int sxc_create(sxc_ctx** out, int device) {
+  if (!out) return SXC_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return SXC_ERR_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return SXC_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SXC_ERR_CUDA;
+  if (prop.major < 10) return SXC_ERR_UNSUPPORTED;  // sm_100a code only
+  auto* ctx = new sxc_ctx();
+  ctx->device = device;
+  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return SXC_ERR_CUDA;
+  }
+  ctx->stream = ctx->own_stream;
+  *out = ctx;
+  return SXC_OK;
+}
+
+void sxc_destroy(sxc_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  ctx->plans.clear();
+  ctx->grids.clear();
+  ctx->bases.clear();
+  ctx->phi.release();
+  ctx->dP.release();
+  ctx->dOut.release();
+  ctx->scratch.release();
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+const char* sxc_last_error(const sxc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int sxc_set_stream(sxc_ctx* ctx, void* s) {
+  if (!ctx) return SXC_ERR_INVALID;
+  ctx->stream = s ? static_cast<cudaStream_t>(s) : ctx->own_stream;
+  return SXC_OK;
+}
+
+int sxc_set_workspace_limit(sxc_ctx* ctx, int64_t bytes) {
+  if (!ctx) return SXC_ERR_INVALID;
+  ctx->ws_limit = bytes;
+  ctx->plans.clear();  // chunking depends on the limit
+  return SXC_OK;
+}
+
+int sxc_set_grid(sxc_ctx* ctx, int64_t npts, const double* xyz, const double* w, int blocksize, int* grid) {
+  if (!ctx || !grid || npts <= 0 || !xyz || !w) return fail(ctx, SXC_ERR_INVALID, "sxc_set_grid: bad arguments");
+  if (blocksize < 1 || blocksize > BP)
+    return fail(ctx, SXC_ERR_UNSUPPORTED, "grid.blocksize %d outside 1..128", blocksize);
+  CU(cudaSetDevice(ctx->device));
+  auto g = std::make_unique<Grid>();
+  g->npts = npts;
+  g->blocksize = blocksize;
+  g->nblocks = (int)((npts + blocksize - 1) / blocksize);
+  g->nlit = (int)((npts + FUNC_BLOCK - 1) / FUNC_BLOCK);
+  std::vector<double> soa((size_t)4 * npts);
+  for (int64_t i = 0; i < npts; ++i) {  // Matrix3Xd interleaved -> SoA for coalesced loads
+    soa[i] = xyz[3 * i];
+    soa[npts + i] = xyz[3 * i + 1];
+    soa[2 * npts + i] = xyz[3 * i + 2];
+    soa[3 * npts + i] = w[i];
+  }
+  CU(g->xyzw.ensure(soa.size() * sizeof(double)));
+  CU(cudaMemcpyAsync(g->xyzw.p, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->grids.push_back(std::move(g));
+  *grid = (int)ctx->grids.size() - 1;
+  return SXC_OK;
+}
+
+int sxc_set_grid_shard(sxc_ctx* ctx, int grid, int rank, int world) {
+  Grid* g = ctx ? get_grid(ctx, grid) : nullptr;
+  if (!g || world < 1 || rank < 0 || rank >= world) return fail(ctx, SXC_ERR_INVALID, "sxc_set_grid_shard: bad arguments");
+  if (world > 1 && g->blocksize != FUNC_BLOCK)
+    return fail(ctx, SXC_ERR_UNSUPPORTED, "sharding needs grid.blocksize == 128");
+  g->rank = rank;
+  g->world = world;
+  g->owner_fixed = false;
+  g->env_valid = false;
+  for (auto it = ctx->plans.begin(); it != ctx->plans.end();)
+    it = (it->first.first == grid) ? ctx->plans.erase(it) : std::next(it);
+  return SXC_OK;
+}
+
+int sxc_add_basis(sxc_ctx* ctx, int nshell, const int* l, const int* pure, const int* nprim, const int* first_bf,
+                  const double* centre, const double* alpha, const double* coeff, const double* normfac,
+                  double radial_threshold, int* basis) {
+  if (!ctx || !basis || nshell <= 0 || !l || !pure || !nprim || !first_bf || !centre || !alpha || !coeff || !normfac)
+    return fail(ctx, SXC_ERR_INVALID, "sxc_add_basis: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  auto b = std::make_unique<Basis>();
+  b->nshell = nshell;
+  b->radial_thr = radial_threshold;
+  std::vector<int> ints((size_t)6 * nshell);
+  size_t np = 0;
+  int nbf = 0;
+  for (int s = 0; s < nshell; ++s) {
+    if (l[s] < 0 || l[s] > LMAX) return fail(ctx, SXC_ERR_UNSUPPORTED, "shell %d: angular momentum %d > %d", s, l[s], LMAX);
+    const int nf = pure[s] ? 2 * l[s] + 1 : (l[s] + 1) * (l[s] + 2) / 2;
+    ints[s] = l[s];
+    ints[nshell + s] = pure[s] ? 1 : 0;
+    ints[2 * nshell + s] = nprim[s];
+    ints[3 * nshell + s] = (int)np;
+    ints[4 * nshell + s] = first_bf[s];
+    ints[5 * nshell + s] = nf;
+    np += nprim[s];
+    nbf = std::max(nbf, first_bf[s] + nf);
+    b->lmax = std::max(b->lmax, l[s]);
+  }
+  b->nbf = nbf;
+  b->nprim_total = np;
+  std::vector<double> d((size_t)3 * nshell + 2 * np + nbf);
+  std::memcpy(d.data(), centre, sizeof(double) * 3 * nshell);
+  std::memcpy(d.data() + 3 * nshell, alpha, sizeof(double) * np);
+  std::memcpy(d.data() + 3 * nshell + np, coeff, sizeof(double) * np);
+  std::memcpy(d.data() + 3 * nshell + 2 * np, normfac, sizeof(double) * nbf);
+  CU(b->ints.ensure(ints.size() * sizeof(int)));
+  CU(b->dbl.ensure(d.size() * sizeof(double)));
+  CU(cudaMemcpyAsync(b->ints.p, ints.data(), ints.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(b->dbl.p, d.data(), d.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->bases.push_back(std::move(b));
+  *basis = (int)ctx->bases.size() - 1;
+  return SXC_OK;
+}
+
+int sxc_set_functional(sxc_ctx* ctx, int ncomp, const int* ids, const double* mix, int* func) {
+  if (!ctx || !func || ncomp < 0 || (ncomp > 0 && (!ids || !mix)))
+    return fail(ctx, SXC_ERR_INVALID, "sxc_set_functional: bad arguments");
+  FuncView f{};
+  for (int i = 0; i < ncomp; ++i) {
+    if (ids[i] == 0) continue;  // BASIC_FUNCTIONALS::NONE is skipped, XCFun.cpp:729-730
+    if (!functional_id_supported(ids[i]))
+      return fail(ctx, SXC_ERR_UNSUPPORTED, "basic functional %d is not implemented", ids[i]);
+    if (f.ncomp == MAX_COMP) return fail(ctx, SXC_ERR_UNSUPPORTED, "more than %d functional components", MAX_COMP);
+    f.id[f.ncomp] = ids[i];
+    f.mix[f.ncomp] = mix[i];
+    f.gga |= functional_id_is_gga(ids[i]) ? 1 : 0;
+    ++f.ncomp;
+  }
+  ctx->funcs.push_back(f);
+  *func = (int)ctx->funcs.size() - 1;
+  return SXC_OK;
+}
+
+int sxc_build_xc_device(sxc_ctx* ctx, int grid, int basis, int func, int nspin, const double* d_P, double thr,
+                        double* d_VEN) {
+  if (!ctx || !d_P || !d_VEN) return fail(ctx, SXC_ERR_INVALID, "sxc_build_xc_device: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  return build_xc_device(ctx, grid, basis, func, nspin, d_P, thr, d_VEN, nullptr);
+}
+
+int sxc_build_xc(sxc_ctx* ctx, int grid, int basis, int func, int nspin, const double* P, double thr, double* V,
+                 double* E, double* nelec) {
+  if (!ctx || !P || !V || !E) return fail(ctx, SXC_ERR_INVALID, "sxc_build_xc: bad arguments");
+  Basis* b = get_basis(ctx, basis);
+  if (!b) return fail(ctx, SXC_ERR_INVALID, "invalid basis handle %d", basis);
+  CU(cudaSetDevice(ctx->device));
+  const size_t nb2 = (size_t)b->nbf * b->nbf;
+  CU(ctx->dP.ensure(nb2 * sizeof(double)));
+  CU(ctx->dOut.ensure((nb2 + 2) * sizeof(double)));
+  CU(cudaMemcpyAsync(ctx->dP.p, P, nb2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  TimerSink sink;
+  ctx->timing = true;
+  int rc = build_xc_device(ctx, grid, basis, func, nspin, ctx->dP.as<double>(), thr, ctx->dOut.as<double>(), &sink);
+  ctx->timing = false;
+  if (rc != SXC_OK) {
+    collect_timers(ctx, sink);
+    return rc;
+  }
+  std::vector<double> tail(2);
+  CU(cudaMemcpyAsync(V, ctx->dOut.p, nb2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(tail.data(), ctx->dOut.as<double>() + nb2, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  collect_timers(ctx, sink);
+  ctx->stats.ms_basis = ctx->ms[0];
+  ctx->stats.ms_density = ctx->ms[1];
+  ctx->stats.ms_functional = ctx->ms[2];
+  ctx->stats.ms_scatter = ctx->ms[3];
+  ctx->stats.ms_total = ctx->ms[4];
+  *E = tail[0];
+  if (nelec) *nelec = tail[1];
+  return SXC_OK;
+}
+
+int sxc_build_nadd_device(sxc_ctx* ctx, int grid, int func, int nspin, int basis_act, const double* d_P_act, int nenv,
+                          const int* basis_env, const double* const* d_P_env, int env_frozen, double thr, double* d_VE) {
+  if (!ctx || !d_P_act || !d_VE || (nenv > 0 && (!basis_env || !d_P_env)))
+    return fail(ctx, SXC_ERR_INVALID, "sxc_build_nadd_device: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  return build_nadd_device(ctx, grid, func, nspin, basis_act, d_P_act, nenv, basis_env, d_P_env, env_frozen, thr, d_VE,
+                           nullptr);
+}
+
+int sxc_build_nadd(sxc_ctx* ctx, int grid, int func, int nspin, int basis_act, const double* P_act, int nenv,
+                   const int* basis_env, const double* const* P_env, int env_frozen, double thr, double* V_act, double* E) {
+  if (!ctx || !P_act || !V_act || !E || nenv < 0 || (nenv > 0 && (!basis_env || !P_env)))
+    return fail(ctx, SXC_ERR_INVALID, "sxc_build_nadd: bad arguments");
+  Basis* ba = get_basis(ctx, basis_act);
+  if (!ba) return fail(ctx, SXC_ERR_INVALID, "invalid active basis handle %d", basis_act);
+  CU(cudaSetDevice(ctx->device));
+  const size_t nbA2 = (size_t)ba->nbf * ba->nbf;
+  size_t total = nbA2;
+  std::vector<size_t> offs(nenv);
+  for (int i = 0; i < nenv; ++i) {
+    Basis* be = get_basis(ctx, basis_env[i]);
+    if (!be) return fail(ctx, SXC_ERR_INVALID, "invalid environment basis handle %d", basis_env[i]);
+    offs[i] = total;
+    total += (size_t)be->nbf * be->nbf;
+  }
+  CU(ctx->dP.ensure(total * sizeof(double)));
+  CU(ctx->dOut.ensure((nbA2 + 2 + nenv) * sizeof(double)));
+  CU(cudaMemcpyAsync(ctx->dP.p, P_act, nbA2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  std::vector<const double*> dpe(nenv);
+  for (int i = 0; i < nenv; ++i) {
+    Basis* be = get_basis(ctx, basis_env[i]);
+    dpe[i] = ctx->dP.as<double>() + offs[i];
+    CU(cudaMemcpyAsync(ctx->dP.as<double>() + offs[i], P_env[i], (size_t)be->nbf * be->nbf * sizeof(double),
+                       cudaMemcpyHostToDevice, ctx->stream));
+  }
+  TimerSink sink;
+  ctx->timing = true;
+  int rc = build_nadd_device(ctx, grid, func, nspin, basis_act, ctx->dP.as<double>(), nenv, basis_env, dpe.data(),
+                             env_frozen, thr, ctx->dOut.as<double>(), &sink);
+  ctx->timing = false;
+  if (rc != SXC_OK) {
+    collect_timers(ctx, sink);
+    return rc;
+  }
+  CU(cudaMemcpyAsync(V_act, ctx->dOut.p, nbA2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(E, ctx->dOut.as<double>() + nbA2, (2 + nenv) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  collect_timers(ctx, sink);
+  ctx->stats.ms_basis = ctx->ms[0];
+  ctx->stats.ms_density = ctx->ms[1];
+  ctx->stats.ms_functional = ctx->ms[2];
+  ctx->stats.ms_scatter = ctx->ms[3];
+  ctx->stats.ms_total = ctx->ms[4];
+  return SXC_OK;
+}
+
+int sxc_density_on_grid(sxc_ctx* ctx, int grid, int basis, const double* P, double* rho, double* gx, double* gy,
+                        double* gz) {
+  if (!ctx || !P || !rho) return fail(ctx, SXC_ERR_INVALID, "sxc_density_on_grid: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  Plan* pp = nullptr;
+  TRY(get_plan(ctx, grid, basis, &pp));
+  Grid& g = *get_grid(ctx, grid);
+  Basis& b = *get_basis(ctx, basis);
+  TRY(ensure_point_arrays(ctx, g, false));
+  const size_t nb2 = (size_t)b.nbf * b.nbf;
+  const long N = g.npts;
+  CU(ctx->dP.ensure(nb2 * sizeof(double)));
+  CU(cudaMemcpyAsync(ctx->dP.p, P, nb2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemsetAsync(g.dens.p, 0, (size_t)4 * N * sizeof(double), ctx->stream));
+  TRY(run_screen(ctx, g, b, *pp));
+  for (const Chunk& c : pp->chunks) {
+    TRY(phase_basis(ctx, g, b, *pp, c));
+    TRY(phase_density(ctx, g, b, *pp, c, ctx->dP.as<double>(), g.dens.as<double>(), gx != nullptr, nullptr));
+  }
+  const double* d = g.dens.as<double>();
+  CU(cudaMemcpyAsync(rho, d, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (gx) {
+    CU(cudaMemcpyAsync(gx, d + N, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(gy, d + 2 * N, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(gz, d + 3 * N, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SXC_OK;
+}
+
+int sxc_basis_on_grid(sxc_ctx* ctx, int grid, int basis, int block, double* val, double* dx, double* dy, double* dz,
+                      int* negligible, int* n_out) {
+  if (!ctx || !val || !negligible) return fail(ctx, SXC_ERR_INVALID, "sxc_basis_on_grid: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  Plan* pp = nullptr;
+  TRY(get_plan(ctx, grid, basis, &pp));
+  Plan& p = *pp;
+  Grid& g = *get_grid(ctx, grid);
+  Basis& b = *get_basis(ctx, basis);
+  const int q = block - g.own_first;
+  if (q < 0 || q >= p.nown) return fail(ctx, SXC_ERR_INVALID, "block %d is not owned by this context", block);
+  const Chunk* ch = nullptr;
+  for (const Chunk& c : p.chunks)
+    if (q >= c.slot0 && q < c.slot0 + c.nslots) ch = &c;
+  TRY(run_screen(ctx, g, b, p));
+  CU(ctx->phi.ensure(ch->doubles * sizeof(double)));
+  k_basis<<<1, BASIS_GROUPS * BP, 0, ctx->stream>>>(g.view(), b.view(), p.view(), q, nullptr, ctx->phi.as<double>());
+  LAUNCH_CHECK();
+  const int s = p.h_s[q], sp = p.h_s_pad[q];
+  std::vector<double> tile((size_t)4 * sp * BP);
+  std::vector<int> sig(std::max(s, 1));
+  std::vector<long long> off(1);
+  CU(cudaMemcpyAsync(off.data(), p.phi_off.as<long long>() + q, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaMemcpyAsync(tile.data(), ctx->phi.as<double>() + off[0], tile.size() * sizeof(double), cudaMemcpyDeviceToHost,
+                     ctx->stream));
+  if (s) CU(cudaMemcpyAsync(sig.data(), p.sig_bf.as<int>() + (size_t)q * p.nbf_pad, s * sizeof(int), cudaMemcpyDeviceToHost,
+                            ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  const long first = (long)block * g.blocksize;
+  const int n = (int)std::min<long>(g.blocksize, g.npts - first);
+  if (n_out) *n_out = n;
+  double* outs[4] = {val, dx, dy, dz};
+  for (int c = 0; c < 4; ++c)
+    if (outs[c]) std::fill(outs[c], outs[c] + (size_t)n * b.nbf, 0.0);
+  for (int i = 0; i < b.nbf; ++i) negligible[i] = 1;
+  for (int c = 0; c < s; ++c) {
+    negligible[sig[c]] = 0;
+    for (int comp = 0; comp < 4; ++comp) {
+      if (!outs[comp]) continue;
+      const double* src = tile.data() + ((size_t)comp * sp + c) * BP;
+      std::copy(src, src + n, outs[comp] + (size_t)sig[c] * n);
+    }
+  }
+  return SXC_OK;
+}
+
+int sxc_functional_on_grid(sxc_ctx* ctx, int func, int64_t npts, const double* w, const double* rho, const double* gx,
+                           const double* gy, const double* gz, double* epuv, double* dFdRho, double* dFdGx, double* dFdGy,
+                           double* dFdGz, double* energy) {
+  if (!ctx || npts <= 0 || !w || !rho || !epuv || !dFdRho)
+    return fail(ctx, SXC_ERR_INVALID, "sxc_functional_on_grid: bad arguments");
+  if (func < 0 || func >= (int)ctx->funcs.size()) return fail(ctx, SXC_ERR_INVALID, "invalid functional handle %d", func);
+  CU(cudaSetDevice(ctx->device));
+  FuncView f = ctx->funcs[func];
+  if (f.gga && !(gx && gy && gz)) return fail(ctx, SXC_ERR_INVALID, "GGA functional needs the density gradient");
+  const bool want_g = f.gga && dFdGx && dFdGy && dFdGz;
+  const int nlit = (int)((npts + FUNC_BLOCK - 1) / FUNC_BLOCK);
+  DevMem buf;
+  const size_t N = (size_t)npts;
+  CU(buf.ensure((10 * N + nlit + 1) * sizeof(double)));
+  double* d = buf.as<double>();
+  double *d_w = d, *d_rho = d + N, *d_gx = d + 2 * N, *d_gy = d + 3 * N, *d_gz = d + 4 * N, *d_ep = d + 5 * N,
+         *d_v = d + 6 * N, *d_part = d + 10 * N;
+  CU(cudaMemcpyAsync(d_w, w, N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_rho, rho, N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (f.gga) {
+    CU(cudaMemcpyAsync(d_gx, gx, N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_gy, gy, N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_gz, gz, N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  k_functional<<<nlit, FUNC_BLOCK, 0, ctx->stream>>>(f, npts, nullptr, d_w, d_rho, d_gx, d_gy, d_gz, 1.0, 0, d_ep, d_v,
+                                                     f.gga ? d_v + N : nullptr, f.gga ? d_v + 2 * N : nullptr,
+                                                     f.gga ? d_v + 3 * N : nullptr, d_part, nullptr);
+  LAUNCH_CHECK();
+  k_reduce_partials<<<1, 256, 0, ctx->stream>>>(d_part, nlit, 1.0, 0, d_part + nlit);
+  LAUNCH_CHECK();
+  CU(cudaMemcpyAsync(epuv, d_ep, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(dFdRho, d_v, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (want_g) {
+    CU(cudaMemcpyAsync(dFdGx, d_v + N, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(dFdGy, d_v + 2 * N, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(dFdGz, d_v + 3 * N, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  double e = 0.0;
+  CU(cudaMemcpyAsync(&e, d_part + nlit, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (energy) *energy = e;
+  return SXC_OK;
+}
+
+int sxc_scalar_to_matrix(sxc_ctx* ctx, int grid, int basis, double thr, const double* v, const double* gx,
+                         const double* gy, const double* gz, double* V) {
+  if (!ctx || !v || !V) return fail(ctx, SXC_ERR_INVALID, "sxc_scalar_to_matrix: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  Plan* pp = nullptr;
+  TRY(get_plan(ctx, grid, basis, &pp));
+  Grid& g = *get_grid(ctx, grid);
+  Basis& b = *get_basis(ctx, basis);
+  TRY(ensure_point_arrays(ctx, g, false));
+  const size_t nb2 = (size_t)b.nbf * b.nbf;
+  const long N = g.npts;
+  const bool gga = gx != nullptr;
+  if (gga && !(gy && gz)) return fail(ctx, SXC_ERR_INVALID, "gradient operator needs all three components");
+  CU(ctx->dOut.ensure((nb2 + 2) * sizeof(double)));
+  double* pot = g.pot.as<double>();
+  CU(cudaMemcpyAsync(pot, v, N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (gga) {
+    CU(cudaMemcpyAsync(pot + N, gx, N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(pot + 2 * N, gy, N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(pot + 3 * N, gz, N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CU(cudaMemsetAsync(ctx->dOut.p, 0, nb2 * sizeof(double), ctx->stream));
+  TRY(run_screen(ctx, g, b, *pp));
+  for (const Chunk& c : pp->chunks) {
+    TRY(phase_basis(ctx, g, b, *pp, c));
+    TRY(phase_scatter(ctx, g, b, *pp, c, gga, thr, pot, ctx->dOut.as<double>()));
+  }
+  TRY(finish_matrix(ctx, b.nbf, ctx->dOut.as<double>()));
+  std::vector<double> h(nb2);
+  CU(cudaMemcpyAsync(h.data(), ctx->dOut.p, nb2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (size_t i = 0; i < nb2; ++i) V[i] += h[i];  // the reference adds into the caller's matrix
+  return SXC_OK;
+}
+
+int sxc_get_stats(const sxc_ctx* ctx, sxc_stats* out) {
+  if (!ctx || !out) return SXC_ERR_INVALID;
+  *out = ctx->stats;
+  return SXC_OK;
+}
+
+}  // extern "C"

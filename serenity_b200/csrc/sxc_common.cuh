@@ -1,0 +1,112 @@
+// sxc_common.cuh - shared device helpers (sm_100a): FP64 tensor-core MMA, cp.async, reductions.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sxc {
+
+constexpr int BP = 128;       // points per tile (blocks are padded to this; reference default blocksize)
+constexpr int SPAD = 32;      // significant-function count is padded to a multiple of this
+constexpr int LMAX = 6;       // AM_MAX, src/parameters/Constants.h:31
+constexpr int FUNC_BLOCK = 128;  // the literal block size of the functional evaluation (FuncPotential.cpp:85)
+
+// D(8x8) += A(8x4, row) * B(4x8, col) in FP64 on the tensor cores (SASS: DMMA.8x8x4).
+// lane holds A[lane/4][lane%4], B[lane%4][lane/4], D[lane/4][2*(lane%4) + {0,1}].
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// block-wide sum for blockDim.x <= 1024 (all threads must call); result valid in all threads
+__device__ __forceinline__ double block_sum(double v, double* scratch /* >= 32 doubles */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  double r = 0.0;
+  for (int i = 0; i < nw; ++i) r += scratch[i];  // fixed order: deterministic
+  return r;
+}
+__device__ __forceinline__ double block_max(double v, double* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  double r = scratch[0];
+  for (int i = 1; i < nw; ++i) r = fmax(r, scratch[i]);
+  return r;
+}
+
+// Device view of a shell table (structure of arrays), see sxc_add_basis.
+struct ShellView {
+  int nshell;
+  int nbf;
+  const int* l;
+  const int* pure;
+  const int* nprim;
+  const int* prim_off;
+  const int* first_bf;
+  const int* nfunc;
+  const double* centre;  // [3*nshell]
+  const double* alpha;
+  const double* coeff;
+  const double* normfac;  // [nbf]
+  double radial_thr;
+  double exp_thr;  // -log(radial_thr)
+};
+
+// Device view of a grid (SoA) and of the blocks this context owns.
+struct GridView {
+  long npts;
+  int blocksize;
+  int nblocks;  // all blocks of the grid
+  const double* x;
+  const double* y;
+  const double* z;
+  const double* w;
+};
+
+// Per (grid, basis) screening plan, slot q = position in the owned-block list.
+struct PlanView {
+  int nown;                // owned blocks
+  const int* block_id;     // [nown] grid block index of slot q
+  int* nsig_shell;         // [nown]
+  int* s;                  // [nown] significant functions
+  int* sig_shell;          // [nown * nshell]
+  int* sig_c0;             // [nown * nshell] first compact index of each significant shell
+  int* sig_bf;             // [nown * nbf_pad] compact index -> basis function
+  int nbf_pad;             // row stride of sig_bf
+  const int* s_pad;        // [nown] padded s (multiple of SPAD), valid after plan creation
+  const long long* phi_off;  // [nown] offset (doubles) of the block's tile inside the current chunk buffer
+};
+
+}  // namespace sxc

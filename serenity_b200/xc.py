@@ -1,0 +1,261 @@
+"""Python host side over the C ABI: XCContext (handle owner) and mirrors of the reference's Potential classes.
+
+Plumbing only - every number is produced by the CUDA library (serenity_b200/csrc).  The class and method names
+follow the reference (src/potentials/FuncPotential.h:47-147, src/potentials/NAddFuncPotential.h:118-155) so that
+the parity tests read like the reference's own tests.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import SerenityError, Stats
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class XCContext:
+    """One context per process and GPU (sxc_create)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        rc = self._lib.sxc_create(C.byref(h), int(device))
+        if rc != 0:
+            raise SerenityError("sxc_create failed (status %d): no usable CUDA device %d - the XC build has no CPU "
+                                "fallback" % (rc, device))
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.sxc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise SerenityError("serenity_xc_b200 status %d: %s" % (rc, self._lib.sxc_last_error(self._h).decode()))
+
+    # ---- inputs
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self._lib.sxc_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def set_workspace_limit(self, nbytes: int):
+        self._check(self._lib.sxc_set_workspace_limit(self._h, int(nbytes)))
+
+    def set_grid(self, xyz, w, blocksize: int = 128) -> int:
+        xyz = _f64(xyz).reshape(-1, 3)
+        w = _f64(w)
+        g = C.c_int(-1)
+        self._check(self._lib.sxc_set_grid(self._h, w.shape[0], _ptr(xyz), _ptr(w), blocksize, C.byref(g)))
+        return g.value
+
+    def set_grid_shard(self, grid: int, rank: int, world: int):
+        self._check(self._lib.sxc_set_grid_shard(self._h, grid, rank, world))
+
+    def add_basis(self, tab, radial_threshold: float = 1e-9) -> int:
+        arrs = [np.ascontiguousarray(a) for a in (tab.l, tab.pure, tab.nprim, tab.first_bf, tab.centre, tab.alpha,
+                                                  tab.coeff, tab.normfac)]
+        b = C.c_int(-1)
+        self._check(self._lib.sxc_add_basis(self._h, tab.nshell, *[_ptr(a) for a in arrs], radial_threshold, C.byref(b)))
+        return b.value
+
+    def set_functional(self, ids, mix) -> int:
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        mix = _f64(mix)
+        f = C.c_int(-1)
+        self._check(self._lib.sxc_set_functional(self._h, len(ids), _ptr(ids), _ptr(mix), C.byref(f)))
+        return f.value
+
+    # ---- hot path
+    def build_xc(self, grid, basis, func, P, block_ave_threshold: float = 1e-11, nspin: int = 1):
+        P = np.asfortranarray(P, dtype=np.float64)
+        V = np.zeros(P.shape, order="F")
+        E, ne = C.c_double(), C.c_double()
+        self._check(self._lib.sxc_build_xc(self._h, grid, basis, func, nspin, _ptr(P), block_ave_threshold, _ptr(V),
+                                           C.byref(E), C.byref(ne)))
+        return V, E.value, ne.value
+
+    def build_xc_device(self, grid, basis, func, d_P_ptr: int, d_VEN_ptr: int, block_ave_threshold: float = 1e-11,
+                        nspin: int = 1):
+        self._check(self._lib.sxc_build_xc_device(self._h, grid, basis, func, nspin, C.c_void_p(d_P_ptr),
+                                                  block_ave_threshold, C.c_void_p(d_VEN_ptr)))
+
+    def build_nadd(self, grid, func, basis_act, P_act, basis_env, P_env, env_frozen: bool = False,
+                   block_ave_threshold: float = 1e-11, nspin: int = 1):
+        P_act = np.asfortranarray(P_act, dtype=np.float64)
+        P_env = [np.asfortranarray(p, dtype=np.float64) for p in P_env]
+        nenv = len(P_env)
+        be = np.ascontiguousarray(basis_env, dtype=np.int32)
+        pp = (C.c_void_p * max(nenv, 1))(*[p.ctypes.data for p in P_env])
+        V = np.zeros(P_act.shape, order="F")
+        E = np.zeros(2 + nenv)
+        self._check(self._lib.sxc_build_nadd(self._h, grid, func, nspin, basis_act, _ptr(P_act), nenv, _ptr(be), pp,
+                                             1 if env_frozen else 0, block_ave_threshold, _ptr(V), _ptr(E)))
+        return V, E
+
+    def build_nadd_device(self, grid, func, basis_act, d_P_act: int, basis_env, d_P_env, d_VE: int,
+                          env_frozen: bool = False, block_ave_threshold: float = 1e-11, nspin: int = 1):
+        nenv = len(d_P_env)
+        be = np.ascontiguousarray(basis_env, dtype=np.int32)
+        pp = (C.c_void_p * max(nenv, 1))(*d_P_env)
+        self._check(self._lib.sxc_build_nadd_device(self._h, grid, func, nspin, basis_act, C.c_void_p(d_P_act), nenv,
+                                                    _ptr(be), pp, 1 if env_frozen else 0, block_ave_threshold,
+                                                    C.c_void_p(d_VE)))
+
+    # ---- stage level
+    def density_on_grid(self, grid, basis, P, npts: int, gradient: bool = True):
+        P = np.asfortranarray(P, dtype=np.float64)
+        rho = np.zeros(npts)
+        g = [np.zeros(npts) for _ in range(3)] if gradient else [None, None, None]
+        self._check(self._lib.sxc_density_on_grid(self._h, grid, basis, _ptr(P), _ptr(rho), _ptr(g[0]), _ptr(g[1]),
+                                                  _ptr(g[2])))
+        return rho, g
+
+    def basis_on_grid(self, grid, basis, block: int, nbf: int, blocksize: int = 128):
+        arrs = [np.zeros((nbf, blocksize)) for _ in range(4)]
+        neg = np.zeros(nbf, dtype=np.int32)
+        n = C.c_int(0)
+        self._check(self._lib.sxc_basis_on_grid(self._h, grid, basis, block, *[_ptr(a) for a in arrs], _ptr(neg),
+                                                C.byref(n)))
+        n = n.value
+        # library layout: n x nbf column-major (index mu*n + p)
+        return [a.reshape(-1)[: n * nbf].reshape(nbf, n).T for a in arrs], neg, n
+
+    def functional_on_grid(self, func, w, rho, gx=None, gy=None, gz=None):
+        N = rho.shape[0]
+        out = [np.zeros(N) for _ in range(5)]
+        e = C.c_double()
+        gga = gx is not None
+        self._check(self._lib.sxc_functional_on_grid(
+            self._h, func, N, _ptr(_f64(w)), _ptr(_f64(rho)), _ptr(_f64(gx)) if gga else None,
+            _ptr(_f64(gy)) if gga else None, _ptr(_f64(gz)) if gga else None, _ptr(out[0]), _ptr(out[1]),
+            _ptr(out[2]) if gga else None, _ptr(out[3]) if gga else None, _ptr(out[4]) if gga else None, C.byref(e)))
+        return e.value, out
+
+    def scalar_to_matrix(self, grid, basis, nbf, v, gx=None, gy=None, gz=None, block_ave_threshold: float = 1e-11,
+                         V=None):
+        if V is None:
+            V = np.zeros((nbf, nbf), order="F")
+        gga = gx is not None
+        self._check(self._lib.sxc_scalar_to_matrix(self._h, grid, basis, block_ave_threshold, _ptr(_f64(v)),
+                                                   _ptr(_f64(gx)) if gga else None, _ptr(_f64(gy)) if gga else None,
+                                                   _ptr(_f64(gz)) if gga else None, _ptr(V)))
+        return V
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._check(self._lib.sxc_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Mirrors of the reference's controllers / potentials (host logic only: lazy evaluation + notification)
+# ------------------------------------------------------------------------------------------------------------------
+class DensityMatrixController:
+    """src/data/matrices/DensityMatrixController: owns P and notifies dependants when it changes."""
+
+    def __init__(self, P):
+        self._P = np.asfortranarray(P, dtype=np.float64)
+        self._sensitive = []
+
+    def addSensitiveObject(self, obj):
+        self._sensitive.append(obj)
+
+    def getDensityMatrix(self):
+        return self._P
+
+    def setDensityMatrix(self, P):
+        self._P = np.asfortranarray(P, dtype=np.float64)
+        for o in self._sensitive:
+            o.notify()
+
+
+class FuncPotential:
+    """Drop-in body of FuncPotential<RESTRICTED> (src/potentials/FuncPotential.cpp:40-111).
+
+    getMatrix() is lazy: recomputed only after notify() (density or grid changed, FuncPotential.h:107-109);
+    getEnergy(P) returns the cached E_xc irrespective of P (FuncPotential.cpp:67-71).
+    """
+
+    def __init__(self, ctx: XCContext, grid: int, basis: int, dmat: DensityMatrixController, functional: int,
+                 block_ave_threshold: float = 1e-11):
+        self._ctx, self._grid, self._basis, self._dmat, self._func = ctx, grid, basis, dmat, functional
+        self._thr = block_ave_threshold
+        self._potential = None
+        self._energy = 0.0
+        self.n_electrons_on_grid = None
+        dmat.addSensitiveObject(self)
+
+    def notify(self):
+        self._potential = None
+
+    def getMatrix(self):
+        if self._potential is None:
+            V, E, ne = self._ctx.build_xc(self._grid, self._basis, self._func, self._dmat.getDensityMatrix(), self._thr)
+            self._potential, self._energy, self.n_electrons_on_grid = V, E, ne
+        return self._potential
+
+    def getEnergy(self, P=None):
+        if self._potential is None:
+            self.getMatrix()
+        return self._energy
+
+
+class NAddFuncPotential:
+    """Drop-in body of NAddFuncPotential<RESTRICTED> (src/potentials/NAddFuncPotential.cpp:192-326)."""
+
+    def __init__(self, ctx: XCContext, grid: int, basis_act: int, act_dmat: DensityMatrixController, basis_env,
+                 env_dmats, functional: int, block_ave_threshold: float = 1e-11):
+        self._ctx, self._grid, self._func, self._thr = ctx, grid, functional, block_ave_threshold
+        self._bA, self._dA, self._bE, self._dE = basis_act, act_dmat, list(basis_env), list(env_dmats)
+        self._potential = None
+        self._energy = 0.0
+        self._env_frozen = False
+        act_dmat.addSensitiveObject(self)
+        for d in self._dE:
+            d.addSensitiveObject(_EnvWatcher(self))
+
+    def notify(self):
+        self._potential = None
+
+    def _env_changed(self):
+        self._potential = None
+        self._env_frozen = False
+
+    def getMatrix(self):
+        if self._potential is None:
+            V, E = self._ctx.build_nadd(self._grid, self._func, self._bA, self._dA.getDensityMatrix(), self._bE,
+                                        [d.getDensityMatrix() for d in self._dE], self._env_frozen, self._thr)
+            self._potential = V
+            self.energy_parts = E
+            self._energy = E[0] - E[1] - E[2:].sum()  # NAddFuncPotential.cpp:249, :282-286
+            self._env_frozen = True  # environment densities stay cached until one of them changes
+        return self._potential
+
+    def getEnergy(self, P=None):
+        if self._potential is None:
+            self.getMatrix()
+        return self._energy
+
+
+class _EnvWatcher:
+    def __init__(self, owner):
+        self._o = owner
+
+    def notify(self):
+        self._o._env_changed()
