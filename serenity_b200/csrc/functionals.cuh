@@ -115,7 +115,7 @@ constexpr double CBRT_3_OVER_PI = 0.98474502184269654115;      // (3/pi)^(1/3)
 constexpr double CBRT_6_OVER_PI = 1.2407009817988000333;       // (6/pi)^(1/3)
 constexpr double CF = 2.8712340001881918160;                   // (3/10)(3 pi^2)^(2/3)
 constexpr double CBRT_3PI2 = 3.0936677262801359310;            // (3 pi^2)^(1/3)
-constexpr double CBRT_6PI2 = 3.8977729270614684983;            // (6 pi^2)^(1/3)
+constexpr double CBRT_6PI2 = 3.8977770897207539590;            // (6 pi^2)^(1/3)
 constexpr double TWO_23 = 1.5874010519681994748;               // 2^(2/3)
 constexpr double TWO_13 = 1.2599210498948731648;               // 2^(1/3)
 constexpr double TWO_43 = 2.5198420997897463295;               // 2^(4/3)
