@@ -56,6 +56,18 @@ enum {
   SXC_K_LLP = 286       /* llp91k      */
 };
 
+/* kernels of one build, indices into sxc_stats.ms_kernel / n_kernel */
+enum {
+  SXC_T_SCREEN = 0,   /* k_screen: block prescreening                      (8a-1, :211-255) */
+  SXC_T_BASIS = 1,    /* k_basis: phi, grad phi tiles                      (8a-1)           */
+  SXC_T_DENSITY = 2,  /* k_density: phi_s P_s DMMA + rho / grad rho sums   (8a-2, 8a-3)     */
+  SXC_T_FUNCTIONAL = 3, /* k_functional: LDA/GGA kernels, w F partial sums (8a-4)           */
+  SXC_T_FORM_G = 4,   /* k_form_g: weights x potential, block test, G tile (8a-5)           */
+  SXC_T_SCATTER = 5,  /* k_scatter: phi^T G + G^T phi DMMA, accumulation   (8a-5)           */
+  SXC_T_FINISH = 6,   /* k_mirror + k_reduce_partials                                       */
+  SXC_T_COUNT = 8
+};
+
 /* work/timing counters of the last build on this context (for roofline reporting) */
 typedef struct {
   int64_t npts;           /* grid points owned by this context (its shard) */
@@ -70,11 +82,11 @@ typedef struct {
   int64_t workspace_bytes; /* device bytes of the phi / grad phi tile buffer */
   int32_t nchunks;         /* block chunks the build was pipelined in */
   int32_t kernel_launches; /* kernels launched by the last build */
-  float ms_basis;          /* CUDA-event times of the last build, per phase, summed over chunks */
-  float ms_density;
-  float ms_functional;
-  float ms_scatter;
-  float ms_total;
+  /* CUDA-event times (ms) and launch counts per kernel of the last build, summed over chunks and subsystems;
+   * filled by the host-buffer entry points always and by the *_device ones after sxc_set_timing(ctx, 1) */
+  float ms_kernel[SXC_T_COUNT];
+  int32_t n_kernel[SXC_T_COUNT];
+  float ms_total;          /* first kernel to last kernel of the build, on the device */
 } sxc_stats;
 
 /* ---- context ------------------------------------------------------------------------------------------- */
@@ -87,6 +99,9 @@ const char* sxc_last_error(const sxc_ctx* ctx);
 int sxc_set_stream(sxc_ctx* ctx, void* cuda_stream);
 /* cap of the phi/grad-phi tile buffer in bytes (default: 40 % of free device memory at plan time) */
 int sxc_set_workspace_limit(sxc_ctx* ctx, int64_t bytes);
+/* per-kernel CUDA-event timing of the *_device builds (off by default: events cost a few microseconds each);
+ * sxc_get_stats() then synchronises on the last build's events */
+int sxc_set_timing(sxc_ctx* ctx, int on);
 
 /* ---- inputs -------------------------------------------------------------------------------------------- */
 /* replaces GridController::getGridPoints()/getWeights() (src/grid/GridController.cpp:31-50); re-upload only
@@ -152,7 +167,7 @@ int sxc_functional_on_grid(sxc_ctx* ctx, int func, int64_t npts, const double* w
 int sxc_scalar_to_matrix(sxc_ctx* ctx, int grid, int basis, double block_ave_threshold, const double* v,
                          const double* gx, const double* gy, const double* gz, double* V);
 
-int sxc_get_stats(const sxc_ctx* ctx, sxc_stats* out);
+int sxc_get_stats(sxc_ctx* ctx, sxc_stats* out);
 /* host-only helper behind sxc_set_grid_shard: splits n blocks into `world` contiguous ranges of nearly equal summed
  * cost; bounds[world + 1] receives the range starts (bounds[0] = 0, bounds[world] = n). */
 int sxc_balance_ranges(int n, const double* cost, int world, int* bounds);

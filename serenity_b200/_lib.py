@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libserenity_xc_b200.so")
 
 # every symbol include/serenity_xc_b200.h declares
 SYMBOLS = [
-    "sxc_create", "sxc_destroy", "sxc_last_error", "sxc_set_stream", "sxc_set_workspace_limit", "sxc_set_grid",
+    "sxc_create", "sxc_destroy", "sxc_last_error", "sxc_set_stream", "sxc_set_workspace_limit", "sxc_set_timing", "sxc_set_grid",
     "sxc_set_grid_shard", "sxc_add_basis", "sxc_set_functional", "sxc_build_xc", "sxc_build_xc_device",
     "sxc_build_nadd", "sxc_build_nadd_device", "sxc_density_on_grid", "sxc_basis_on_grid",
     "sxc_functional_on_grid", "sxc_scalar_to_matrix", "sxc_get_stats", "sxc_balance_ranges", "sxc_abi_version",
@@ -23,15 +23,21 @@ class SerenityError(RuntimeError):
     """Mirror of src/misc/SerenityError.h:36 - what the adapter throws when the C ABI returns an error."""
 
 
+KERNEL_SLOTS = ["k_screen", "k_basis", "k_density", "k_functional", "k_form_g", "k_scatter", "finish"]  # SXC_T_*
+
+
 class Stats(C.Structure):
     _fields_ = [("npts", C.c_int64), ("nblocks", C.c_int64), ("sum_s", C.c_int64), ("sum_ns", C.c_int64),
                 ("sum_ns2", C.c_int64), ("sum_ns2_padded", C.c_int64), ("sum_s2", C.c_int64), ("s_max", C.c_int64),
                 ("nbf", C.c_int64), ("workspace_bytes", C.c_int64), ("nchunks", C.c_int32),
-                ("kernel_launches", C.c_int32), ("ms_basis", C.c_float), ("ms_density", C.c_float),
-                ("ms_functional", C.c_float), ("ms_scatter", C.c_float), ("ms_total", C.c_float)]
+                ("kernel_launches", C.c_int32), ("ms_kernel", C.c_float * 8), ("n_kernel", C.c_int32 * 8),
+                ("ms_total", C.c_float)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k not in ("ms_kernel", "n_kernel")}
+        d["ms_kernel"] = {n: float(self.ms_kernel[i]) for i, n in enumerate(KERNEL_SLOTS)}
+        d["n_kernel"] = {n: int(self.n_kernel[i]) for i, n in enumerate(KERNEL_SLOTS)}
+        return d
 
 
 _LIB = None
@@ -54,6 +60,7 @@ def load():
     lib.sxc_last_error.restype = C.c_char_p
     lib.sxc_set_stream.argtypes = [vp, vp]
     lib.sxc_set_workspace_limit.argtypes = [vp, i64]
+    lib.sxc_set_timing.argtypes = [vp, i]
     lib.sxc_set_grid.argtypes = [vp, i64, vp, vp, i, ip]
     lib.sxc_set_grid_shard.argtypes = [vp, i, i, i]
     lib.sxc_add_basis.argtypes = [vp, i, vp, vp, vp, vp, vp, vp, vp, vp, d, ip]

@@ -163,9 +163,15 @@ struct sxc_ctx {
   sxc_stats stats{};
   int launches = 0;
   bool attrs_set = false;
-  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  float ms[5] = {0, 0, 0, 0, 0};
-  bool timing = false;
+  bool timing = false;        // record events during the current build
+  bool timing_device = false; // sxc_set_timing: also for the *_device entry points
+  struct Stamp {
+    int slot;
+    cudaEvent_t a, b;
+  };
+  std::vector<Stamp> stamps;  // events of the last build, collected lazily
+  std::vector<cudaEvent_t> event_pool;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
 };
 
 namespace {
@@ -213,9 +219,73 @@ int set_kernel_attrs(sxc_ctx* ctx) {
   return SXC_OK;
 }
 
+cudaEvent_t take_event(sxc_ctx* ctx) {
+  cudaEvent_t e = nullptr;
+  if (!ctx->event_pool.empty()) {
+    e = ctx->event_pool.back();
+    ctx->event_pool.pop_back();
+  } else {
+    cudaEventCreate(&e);
+  }
+  return e;
+}
+
+// RAII bracket of one kernel (or kernel pair) of the build: two events on the build's stream when timing is on
+struct PhaseTimer {
+  sxc_ctx* ctx;
+  int slot;
+  cudaEvent_t a = nullptr;
+  PhaseTimer(sxc_ctx* c, int s) : ctx(c), slot(s) {
+    if (ctx->timing) {
+      a = take_event(ctx);
+      cudaEventRecord(a, ctx->stream);
+    }
+  }
+  ~PhaseTimer() {
+    if (a) {
+      cudaEvent_t b = take_event(ctx);
+      cudaEventRecord(b, ctx->stream);
+      ctx->stamps.push_back({slot, a, b});
+    }
+  }
+};
+constexpr int T_TOTAL = SXC_T_COUNT;  // pseudo slot of the whole build
+
+void begin_timing(sxc_ctx* ctx, bool on) {
+  for (auto& st : ctx->stamps) {
+    ctx->event_pool.push_back(st.a);
+    ctx->event_pool.push_back(st.b);
+  }
+  ctx->stamps.clear();
+  ctx->timing = on;
+  for (int i = 0; i < SXC_T_COUNT; ++i) {
+    ctx->stats.ms_kernel[i] = 0.f;
+    ctx->stats.n_kernel[i] = 0;
+  }
+  ctx->stats.ms_total = 0.f;
+}
+
+void collect_timers(sxc_ctx* ctx) {
+  for (auto& t : ctx->stamps) {
+    float ms = 0.f;
+    cudaEventSynchronize(t.b);
+    cudaEventElapsedTime(&ms, t.a, t.b);
+    if (t.slot == T_TOTAL) {
+      ctx->stats.ms_total += ms;
+    } else {
+      ctx->stats.ms_kernel[t.slot] += ms;
+      ctx->stats.n_kernel[t.slot] += 1;
+    }
+    ctx->event_pool.push_back(t.a);
+    ctx->event_pool.push_back(t.b);
+  }
+  ctx->stamps.clear();
+}
+
 // ---------------------------------------------------------------------------------------------- plan
 int run_screen(sxc_ctx* ctx, const Grid& g, const Basis& b, const Plan& p) {
   if (p.nown == 0) return SXC_OK;
+  PhaseTimer t(ctx, SXC_T_SCREEN);
   k_screen<<<p.nown, 128, 0, ctx->stream>>>(g.view(), b.view(), p.view());
   LAUNCH_CHECK();
   return SXC_OK;
@@ -398,6 +468,7 @@ int ensure_point_arrays(sxc_ctx* ctx, Grid& g, bool nadd) {
 // phases of one chunk ------------------------------------------------------------------------------------------
 int phase_basis(sxc_ctx* ctx, const Grid& g, const Basis& b, const Plan& p, const Chunk& c) {
   CU(ctx->phi.ensure(c.doubles * sizeof(double)));
+  PhaseTimer t(ctx, SXC_T_BASIS);
   k_basis<<<c.nslots, BASIS_GROUPS * BP, 0, ctx->stream>>>(g.view(), b.view(), p.view(), c.slot0,
                                                             p.order.as<int>() + c.order_off, ctx->phi.as<double>());
   LAUNCH_CHECK();
@@ -407,6 +478,7 @@ int phase_basis(sxc_ctx* ctx, const Grid& g, const Basis& b, const Plan& p, cons
 int phase_density(sxc_ctx* ctx, const Grid& g, const Basis& b, const Plan& p, const Chunk& c, const double* dP,
                   double* dens4, bool with_grad, int* nonneg) {
   const long N = g.npts;
+  PhaseTimer t(ctx, SXC_T_DENSITY);
   k_density<<<c.nslots, dens::THREADS, dens::smem_bytes(p.s_pad_max), ctx->stream>>>(
       g.view(), p.view(), b.nbf, dP, p.order.as<int>() + c.order_off, ctx->phi.as<double>(), dens4,
       with_grad ? dens4 + N : nullptr, with_grad ? dens4 + 2 * N : nullptr, with_grad ? dens4 + 3 * N : nullptr, nonneg);
@@ -423,6 +495,7 @@ int phase_functional(sxc_ctx* ctx, const Grid& g, const Plan& p, const Chunk& c,
   const int nb = lit_is_block ? c.nslots : g.nlit;
   if (nb == 0) return SXC_OK;
   const int* list = lit_is_block ? p.block_id.as<int>() + c.slot0 : nullptr;
+  PhaseTimer t(ctx, SXC_T_FUNCTIONAL);
   k_functional<<<nb, FUNC_BLOCK, 0, ctx->stream>>>(f, N, list, gv.w, dens4, dens4 + N, dens4 + 2 * N, dens4 + 3 * N,
                                                    sign, accumulate, nullptr, pot4, f.gga ? pot4 + N : nullptr,
                                                    f.gga ? pot4 + 2 * N : nullptr, f.gga ? pot4 + 3 * N : nullptr,
@@ -434,11 +507,15 @@ int phase_functional(sxc_ctx* ctx, const Grid& g, const Plan& p, const Chunk& c,
 int phase_scatter(sxc_ctx* ctx, const Grid& g, const Basis& b, const Plan& p, const Chunk& c, bool gga,
                   double block_ave_thr, const double* pot4, double* dW) {
   const long N = g.npts;
-  k_form_g<<<c.nslots, 256, 0, ctx->stream>>>(g.view(), p.view(), p.order.as<int>() + c.order_off, block_ave_thr, pot4,
-                                              gga ? pot4 + N : nullptr, gga ? pot4 + 2 * N : nullptr,
-                                              gga ? pot4 + 3 * N : nullptr, ctx->phi.as<double>(), p.skip.as<int>());
-  LAUNCH_CHECK();
+  {
+    PhaseTimer t(ctx, SXC_T_FORM_G);
+    k_form_g<<<c.nslots, 256, 0, ctx->stream>>>(g.view(), p.view(), p.order.as<int>() + c.order_off, block_ave_thr, pot4,
+                                                gga ? pot4 + N : nullptr, gga ? pot4 + 2 * N : nullptr,
+                                                gga ? pot4 + 3 * N : nullptr, ctx->phi.as<double>(), p.skip.as<int>());
+    LAUNCH_CHECK();
+  }
   if (c.nitems > 0) {
+    PhaseTimer t(ctx, SXC_T_SCATTER);
     k_scatter<<<c.nitems, scat::THREADS, scat::smem_bytes(p.s_pad_max), ctx->stream>>>(
         p.view(), b.nbf, p.items.as<ScatterItem>() + c.item_off, p.skip.as<int>(), ctx->phi.as<double>(), dW);
     LAUNCH_CHECK();
@@ -448,53 +525,22 @@ int phase_scatter(sxc_ctx* ctx, const Grid& g, const Basis& b, const Plan& p, co
 
 int finish_matrix(sxc_ctx* ctx, int nbf, double* dW) {
   dim3 blk(32, 8), grd((nbf + 31) / 32, (nbf + 7) / 8);
+  PhaseTimer t(ctx, SXC_T_FINISH);
   k_mirror<<<grd, blk, 0, ctx->stream>>>(nbf, dW);
   LAUNCH_CHECK();
   return SXC_OK;
 }
 
 int reduce_to(sxc_ctx* ctx, const double* part, int n, double* out) {
+  PhaseTimer t(ctx, SXC_T_FINISH);
   k_reduce_partials<<<1, 256, 0, ctx->stream>>>(part, n, 1.0, 0, out);
   LAUNCH_CHECK();
   return SXC_OK;
 }
 
-struct PhaseTimer {
-  sxc_ctx* ctx;
-  int slot;
-  cudaEvent_t a = nullptr, b = nullptr;
-  PhaseTimer(sxc_ctx* c, int s) : ctx(c), slot(s) {
-    if (ctx->timing) {
-      cudaEventCreate(&a);
-      cudaEventCreate(&b);
-      cudaEventRecord(a, ctx->stream);
-    }
-  }
-  void stop(std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>>& sink) {
-    if (ctx->timing) {
-      cudaEventRecord(b, ctx->stream);
-      sink.push_back({slot, {a, b}});
-    }
-  }
-};
-using TimerSink = std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>>;
-
-void collect_timers(sxc_ctx* ctx, TimerSink& sink) {
-  for (int i = 0; i < 5; ++i) ctx->ms[i] = 0.f;
-  for (auto& t : sink) {
-    float ms = 0.f;
-    cudaEventSynchronize(t.second.second);
-    cudaEventElapsedTime(&ms, t.second.first, t.second.second);
-    ctx->ms[t.first] += ms;
-    cudaEventDestroy(t.second.first);
-    cudaEventDestroy(t.second.second);
-  }
-  sink.clear();
-}
-
 // ---------------------------------------------------------------------------------------------- builds
 int build_xc_device(sxc_ctx* ctx, int gh, int bh, int fh, int nspin, const double* dP, double thr, double* dVEN,
-                    TimerSink* sink) {
+                    bool timed) {
   if (nspin != 1) return fail(ctx, SXC_ERR_UNSUPPORTED, "UNRESTRICTED (nspin = 2) is not implemented yet");
   if (fh < 0 || fh >= (int)ctx->funcs.size()) return fail(ctx, SXC_ERR_INVALID, "invalid functional handle %d", fh);
   Plan* pp = nullptr;
@@ -504,44 +550,28 @@ int build_xc_device(sxc_ctx* ctx, int gh, int bh, int fh, int nspin, const doubl
   Basis& b = *get_basis(ctx, bh);
   const FuncView f = ctx->funcs[fh];
   TRY(ensure_point_arrays(ctx, g, false));
+  ctx->stats = p.stats;
+  begin_timing(ctx, timed || ctx->timing_device);
   const int launches0 = ctx->launches;
   const size_t nb2 = (size_t)b.nbf * b.nbf;
   double* parts = g.parts.as<double>();
-  CU(cudaMemsetAsync(dVEN, 0, (nb2 + 2) * sizeof(double), ctx->stream));
-  CU(cudaMemsetAsync(parts, 0, (size_t)3 * std::max(g.nlit, 1) * sizeof(double), ctx->stream));
-  PhaseTimer t_all(ctx, 4);
-  {  // the screening is part of every build in the reference (calculateBasisFunctionData :211-255)
-    PhaseTimer t(ctx, 0);
+  {
+    PhaseTimer t_all(ctx, T_TOTAL);
+    CU(cudaMemsetAsync(dVEN, 0, (nb2 + 2) * sizeof(double), ctx->stream));
+    CU(cudaMemsetAsync(parts, 0, (size_t)3 * std::max(g.nlit, 1) * sizeof(double), ctx->stream));
+    // the screening is part of every build in the reference (calculateBasisFunctionData :211-255)
     TRY(run_screen(ctx, g, b, p));
-    if (sink) t.stop(*sink);
-  }
-  for (const Chunk& c : p.chunks) {
-    {
-      PhaseTimer t(ctx, 0);
+    for (const Chunk& c : p.chunks) {
       TRY(phase_basis(ctx, g, b, p, c));
-      if (sink) t.stop(*sink);
-    }
-    {
-      PhaseTimer t(ctx, 1);
       TRY(phase_density(ctx, g, b, p, c, dP, g.dens.as<double>(), true, nullptr));
-      if (sink) t.stop(*sink);
-    }
-    {
-      PhaseTimer t(ctx, 2);
       TRY(phase_functional(ctx, g, p, c, f, g.dens.as<double>(), 1.0, 0, g.pot.as<double>(), parts, parts + g.nlit));
-      if (sink) t.stop(*sink);
+      if (f.ncomp > 0) TRY(phase_scatter(ctx, g, b, p, c, f.gga != 0, thr, g.pot.as<double>(), dVEN));
     }
-    if (f.ncomp > 0) {
-      PhaseTimer t(ctx, 3);
-      TRY(phase_scatter(ctx, g, b, p, c, f.gga != 0, thr, g.pot.as<double>(), dVEN));
-      if (sink) t.stop(*sink);
-    }
+    TRY(finish_matrix(ctx, b.nbf, dVEN));
+    TRY(reduce_to(ctx, parts, g.nlit, dVEN + nb2));
+    TRY(reduce_to(ctx, parts + g.nlit, g.nlit, dVEN + nb2 + 1));
   }
-  TRY(finish_matrix(ctx, b.nbf, dVEN));
-  TRY(reduce_to(ctx, parts, g.nlit, dVEN + nb2));
-  TRY(reduce_to(ctx, parts + g.nlit, g.nlit, dVEN + nb2 + 1));
-  if (sink) t_all.stop(*sink);
-  ctx->stats = p.stats;
+  ctx->timing = false;
   ctx->stats.kernel_launches = ctx->launches - launches0;
   return SXC_OK;
 }
@@ -558,7 +588,7 @@ __global__ void k_add4(long N, int blocksize, const int* __restrict__ block_id, 
 }
 
 int build_nadd_device(sxc_ctx* ctx, int gh, int fh, int nspin, int bA, const double* dPA, int nenv, const int* bE,
-                      const double* const* dPE, int frozen, double thr, double* dVE, TimerSink* sink) {
+                      const double* const* dPE, int frozen, double thr, double* dVE, bool timed) {
   if (nspin != 1) return fail(ctx, SXC_ERR_UNSUPPORTED, "UNRESTRICTED (nspin = 2) is not implemented yet");
   if (fh < 0 || fh >= (int)ctx->funcs.size()) return fail(ctx, SXC_ERR_INVALID, "invalid functional handle %d", fh);
   if (nenv < 0) return fail(ctx, SXC_ERR_INVALID, "nenv < 0");
@@ -569,89 +599,82 @@ int build_nadd_device(sxc_ctx* ctx, int gh, int fh, int nspin, int bA, const dou
   const FuncView f = ctx->funcs[fh];
   Plan* pa = nullptr;
   TRY(get_plan(ctx, gh, bA, &pa));  // the active system fixes the block ownership
+  for (int i = 0; i < nenv; ++i) {
+    Plan* pe = nullptr;
+    if (!get_basis(ctx, bE[i])) return fail(ctx, SXC_ERR_INVALID, "invalid environment basis handle %d", bE[i]);
+    TRY(get_plan(ctx, gh, bE[i], &pe));
+  }
   TRY(ensure_point_arrays(ctx, g, true));
+  CU(ctx->scratch.ensure(64 * sizeof(double)));
   const long N = g.npts;
-  const int launches0 = ctx->launches;
   const size_t nb2 = (size_t)ba->nbf * ba->nbf;
   double* parts = g.parts.as<double>();
-  PhaseTimer t_all(ctx, 4);
-  CU(cudaMemsetAsync(dVE, 0, (nb2 + 2 + nenv) * sizeof(double), ctx->stream));
-  CU(ctx->scratch.ensure(64 * sizeof(double)));
+  ctx->stats = pa->stats;
+  begin_timing(ctx, timed || ctx->timing_device);
+  const int launches0 = ctx->launches;
+  {
+    PhaseTimer t_all(ctx, T_TOTAL);
+    CU(cudaMemsetAsync(dVE, 0, (nb2 + 2 + nenv) * sizeof(double), ctx->stream));
 
-  // environment: rho_env on the supersystem grid, summed; E[rho_env_i] (NAddEnergyHelper, NAddFuncPotential.cpp:502-516)
-  std::vector<int> key(bE, bE + nenv);
-  key.push_back(fh);
-  const bool reuse = frozen && g.env_valid && g.env_key == key;
-  if (!reuse) {
-    CU(cudaMemsetAsync(g.envsum.p, 0, (size_t)4 * N * sizeof(double), ctx->stream));
-    g.env_energy.assign(nenv, 0.0);
-    for (int i = 0; i < nenv; ++i) {
-      Basis* be = get_basis(ctx, bE[i]);
-      if (!be) return fail(ctx, SXC_ERR_INVALID, "invalid environment basis handle %d", bE[i]);
-      Plan* pe = nullptr;
-      TRY(get_plan(ctx, gh, bE[i], &pe));
-      CU(cudaMemsetAsync(parts, 0, (size_t)3 * std::max(g.nlit, 1) * sizeof(double), ctx->stream));
-      TRY(run_screen(ctx, g, *be, *pe));
-      for (const Chunk& c : pe->chunks) {
-        PhaseTimer t0(ctx, 0);
-        TRY(phase_basis(ctx, g, *be, *pe, c));
-        if (sink) t0.stop(*sink);
-        PhaseTimer t1(ctx, 1);
-        TRY(phase_density(ctx, g, *be, *pe, c, dPE[i], g.dens.as<double>(), true, nullptr));
-        if (pe->nown) {
-          k_add4<<<c.nslots, 128, 0, ctx->stream>>>(N, g.blocksize, pe->block_id.as<int>() + c.slot0, g.envsum.as<double>(),
-                                                    g.dens.as<double>(), g.envsum.as<double>());
-          LAUNCH_CHECK();
+    // environment: rho_env on the supersystem grid, summed; E[rho_env_i] (NAddEnergyHelper, NAddFuncPotential.cpp:502-516)
+    std::vector<int> key(bE, bE + nenv);
+    key.push_back(fh);
+    const bool reuse = frozen && g.env_valid && g.env_key == key;
+    if (!reuse) {
+      CU(cudaMemsetAsync(g.envsum.p, 0, (size_t)4 * N * sizeof(double), ctx->stream));
+      g.env_energy.assign(nenv, 0.0);
+      for (int i = 0; i < nenv; ++i) {
+        Basis* be = get_basis(ctx, bE[i]);
+        Plan* pe = nullptr;
+        TRY(get_plan(ctx, gh, bE[i], &pe));
+        CU(cudaMemsetAsync(parts, 0, (size_t)3 * std::max(g.nlit, 1) * sizeof(double), ctx->stream));
+        TRY(run_screen(ctx, g, *be, *pe));
+        for (const Chunk& c : pe->chunks) {
+          TRY(phase_basis(ctx, g, *be, *pe, c));
+          TRY(phase_density(ctx, g, *be, *pe, c, dPE[i], g.dens.as<double>(), true, nullptr));
+          if (pe->nown) {
+            PhaseTimer t(ctx, SXC_T_DENSITY);
+            k_add4<<<c.nslots, 128, 0, ctx->stream>>>(N, g.blocksize, pe->block_id.as<int>() + c.slot0,
+                                                      g.envsum.as<double>(), g.dens.as<double>(), g.envsum.as<double>());
+            LAUNCH_CHECK();
+          }
+          // energy only: the potential goes to g.pot and is overwritten later
+          TRY(phase_functional(ctx, g, *pe, c, f, g.dens.as<double>(), 1.0, 0, g.pot.as<double>(), parts, nullptr));
         }
-        if (sink) t1.stop(*sink);
-        PhaseTimer t2(ctx, 2);
-        // energy only: the potential goes to g.pot and is overwritten later
-        TRY(phase_functional(ctx, g, *pe, c, f, g.dens.as<double>(), 1.0, 0, g.pot.as<double>(), parts, nullptr));
-        if (sink) t2.stop(*sink);
+        TRY(reduce_to(ctx, parts, g.nlit, ctx->scratch.as<double>() + i));
       }
-      TRY(reduce_to(ctx, parts, g.nlit, ctx->scratch.as<double>() + i));
+      if (nenv > 0) {
+        CU(cudaMemcpyAsync(g.env_energy.data(), ctx->scratch.p, nenv * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+      }
+      g.env_key = key;
+      g.env_valid = true;
     }
-    if (nenv > 0) {
-      CU(cudaMemcpyAsync(g.env_energy.data(), ctx->scratch.p, nenv * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-      CU(cudaStreamSynchronize(ctx->stream));
-    }
-    g.env_key = key;
-    g.env_valid = true;
-  }
-  if (nenv > 0)
-    CU(cudaMemcpyAsync(dVE + nb2 + 2, g.env_energy.data(), nenv * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (nenv > 0)
+      CU(cudaMemcpyAsync(dVE + nb2 + 2, g.env_energy.data(), nenv * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
 
-  // active system: rho_A, rho_tot = rho_A + sum_env, v = v[rho_tot] - v[rho_A]  (NAddFuncPotential.cpp:197-225)
-  Plan& p = *pa;
-  CU(cudaMemsetAsync(parts, 0, (size_t)3 * std::max(g.nlit, 1) * sizeof(double), ctx->stream));
-  TRY(run_screen(ctx, g, *ba, p));
-  for (const Chunk& c : p.chunks) {
-    PhaseTimer t0(ctx, 0);
-    TRY(phase_basis(ctx, g, *ba, p, c));
-    if (sink) t0.stop(*sink);
-    PhaseTimer t1(ctx, 1);
-    TRY(phase_density(ctx, g, *ba, p, c, dPA, g.dens.as<double>(), true, nullptr));
-    if (p.nown) {
-      k_add4<<<c.nslots, 128, 0, ctx->stream>>>(N, g.blocksize, p.block_id.as<int>() + c.slot0, g.dens.as<double>(),
-                                                g.envsum.as<double>(), g.tot.as<double>());
-      LAUNCH_CHECK();
+    // active system: rho_A, rho_tot = rho_A + sum_env, v = v[rho_tot] - v[rho_A]  (NAddFuncPotential.cpp:197-225)
+    Plan& p = *pa;
+    CU(cudaMemsetAsync(parts, 0, (size_t)3 * std::max(g.nlit, 1) * sizeof(double), ctx->stream));
+    TRY(run_screen(ctx, g, *ba, p));
+    for (const Chunk& c : p.chunks) {
+      TRY(phase_basis(ctx, g, *ba, p, c));
+      TRY(phase_density(ctx, g, *ba, p, c, dPA, g.dens.as<double>(), true, nullptr));
+      if (p.nown) {
+        PhaseTimer t(ctx, SXC_T_DENSITY);
+        k_add4<<<c.nslots, 128, 0, ctx->stream>>>(N, g.blocksize, p.block_id.as<int>() + c.slot0, g.dens.as<double>(),
+                                                  g.envsum.as<double>(), g.tot.as<double>());
+        LAUNCH_CHECK();
+      }
+      TRY(phase_functional(ctx, g, p, c, f, g.tot.as<double>(), 1.0, 0, g.pot.as<double>(), parts, nullptr));
+      TRY(phase_functional(ctx, g, p, c, f, g.dens.as<double>(), -1.0, 1, g.pot.as<double>(), parts + g.nlit, nullptr));
+      if (f.ncomp > 0) TRY(phase_scatter(ctx, g, *ba, p, c, f.gga != 0, thr, g.pot.as<double>(), dVE));
     }
-    if (sink) t1.stop(*sink);
-    PhaseTimer t2(ctx, 2);
-    TRY(phase_functional(ctx, g, p, c, f, g.tot.as<double>(), 1.0, 0, g.pot.as<double>(), parts, nullptr));
-    TRY(phase_functional(ctx, g, p, c, f, g.dens.as<double>(), -1.0, 1, g.pot.as<double>(), parts + g.nlit, nullptr));
-    if (sink) t2.stop(*sink);
-    if (f.ncomp > 0) {
-      PhaseTimer t3(ctx, 3);
-      TRY(phase_scatter(ctx, g, *ba, p, c, f.gga != 0, thr, g.pot.as<double>(), dVE));
-      if (sink) t3.stop(*sink);
-    }
+    TRY(finish_matrix(ctx, ba->nbf, dVE));
+    TRY(reduce_to(ctx, parts, g.nlit, dVE + nb2));
+    TRY(reduce_to(ctx, parts + g.nlit, g.nlit, dVE + nb2 + 1));
   }
-  TRY(finish_matrix(ctx, ba->nbf, dVE));
-  TRY(reduce_to(ctx, parts, g.nlit, dVE + nb2));
-  TRY(reduce_to(ctx, parts + g.nlit, g.nlit, dVE + nb2 + 1));
-  if (sink) t_all.stop(*sink);
-  ctx->stats = p.stats;
+  ctx->timing = false;
   ctx->stats.kernel_launches = ctx->launches - launches0;
   return SXC_OK;
 }
@@ -661,7 +684,7 @@ int build_nadd_device(sxc_ctx* ctx, int gh, int fh, int nspin, int bA, const dou
 // ================================================================================================ C ABI
 extern "C" {
 
-int sxc_abi_version(void) { return 1; }
+int sxc_abi_version(void) { return 2; }
 
 // host-only: contiguous ranges [bounds[r], bounds[r+1]) of nearly equal summed cost
 int sxc_balance_ranges(int n, const double* cost, int world, int* bounds) {
@@ -710,6 +733,11 @@ void sxc_destroy(sxc_ctx* ctx) {
   ctx->dP.release();
   ctx->dOut.release();
   ctx->scratch.release();
+  for (auto& st : ctx->stamps) {
+    cudaEventDestroy(st.a);
+    cudaEventDestroy(st.b);
+  }
+  for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -833,7 +861,7 @@ int sxc_build_xc_device(sxc_ctx* ctx, int grid, int basis, int func, int nspin, 
                         double* d_VEN) {
   if (!ctx || !d_P || !d_VEN) return fail(ctx, SXC_ERR_INVALID, "sxc_build_xc_device: bad arguments");
   CU(cudaSetDevice(ctx->device));
-  return build_xc_device(ctx, grid, basis, func, nspin, d_P, thr, d_VEN, nullptr);
+  return build_xc_device(ctx, grid, basis, func, nspin, d_P, thr, d_VEN, false);
 }
 
 int sxc_build_xc(sxc_ctx* ctx, int grid, int basis, int func, int nspin, const double* P, double thr, double* V,
@@ -846,24 +874,14 @@ int sxc_build_xc(sxc_ctx* ctx, int grid, int basis, int func, int nspin, const d
   CU(ctx->dP.ensure(nb2 * sizeof(double)));
   CU(ctx->dOut.ensure((nb2 + 2) * sizeof(double)));
   CU(cudaMemcpyAsync(ctx->dP.p, P, nb2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  TimerSink sink;
-  ctx->timing = true;
-  int rc = build_xc_device(ctx, grid, basis, func, nspin, ctx->dP.as<double>(), thr, ctx->dOut.as<double>(), &sink);
+  int rc = build_xc_device(ctx, grid, basis, func, nspin, ctx->dP.as<double>(), thr, ctx->dOut.as<double>(), true);
   ctx->timing = false;
-  if (rc != SXC_OK) {
-    collect_timers(ctx, sink);
-    return rc;
-  }
+  if (rc != SXC_OK) return rc;
   std::vector<double> tail(2);
   CU(cudaMemcpyAsync(V, ctx->dOut.p, nb2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(tail.data(), ctx->dOut.as<double>() + nb2, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  collect_timers(ctx, sink);
-  ctx->stats.ms_basis = ctx->ms[0];
-  ctx->stats.ms_density = ctx->ms[1];
-  ctx->stats.ms_functional = ctx->ms[2];
-  ctx->stats.ms_scatter = ctx->ms[3];
-  ctx->stats.ms_total = ctx->ms[4];
+  collect_timers(ctx);
   *E = tail[0];
   if (nelec) *nelec = tail[1];
   return SXC_OK;
@@ -875,7 +893,7 @@ int sxc_build_nadd_device(sxc_ctx* ctx, int grid, int func, int nspin, int basis
     return fail(ctx, SXC_ERR_INVALID, "sxc_build_nadd_device: bad arguments");
   CU(cudaSetDevice(ctx->device));
   return build_nadd_device(ctx, grid, func, nspin, basis_act, d_P_act, nenv, basis_env, d_P_env, env_frozen, thr, d_VE,
-                           nullptr);
+                           false);
 }
 
 int sxc_build_nadd(sxc_ctx* ctx, int grid, int func, int nspin, int basis_act, const double* P_act, int nenv,
@@ -904,24 +922,14 @@ int sxc_build_nadd(sxc_ctx* ctx, int grid, int func, int nspin, int basis_act, c
     CU(cudaMemcpyAsync(ctx->dP.as<double>() + offs[i], P_env[i], (size_t)be->nbf * be->nbf * sizeof(double),
                        cudaMemcpyHostToDevice, ctx->stream));
   }
-  TimerSink sink;
-  ctx->timing = true;
   int rc = build_nadd_device(ctx, grid, func, nspin, basis_act, ctx->dP.as<double>(), nenv, basis_env, dpe.data(),
-                             env_frozen, thr, ctx->dOut.as<double>(), &sink);
+                             env_frozen, thr, ctx->dOut.as<double>(), true);
   ctx->timing = false;
-  if (rc != SXC_OK) {
-    collect_timers(ctx, sink);
-    return rc;
-  }
+  if (rc != SXC_OK) return rc;
   CU(cudaMemcpyAsync(V_act, ctx->dOut.p, nbA2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(E, ctx->dOut.as<double>() + nbA2, (2 + nenv) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  collect_timers(ctx, sink);
-  ctx->stats.ms_basis = ctx->ms[0];
-  ctx->stats.ms_density = ctx->ms[1];
-  ctx->stats.ms_functional = ctx->ms[2];
-  ctx->stats.ms_scatter = ctx->ms[3];
-  ctx->stats.ms_total = ctx->ms[4];
+  collect_timers(ctx);
   return SXC_OK;
 }
 
@@ -1081,8 +1089,15 @@ int sxc_scalar_to_matrix(sxc_ctx* ctx, int grid, int basis, double thr, const do
   return SXC_OK;
 }
 
-int sxc_get_stats(const sxc_ctx* ctx, sxc_stats* out) {
+int sxc_set_timing(sxc_ctx* ctx, int on) {
+  if (!ctx) return SXC_ERR_INVALID;
+  ctx->timing_device = on != 0;
+  return SXC_OK;
+}
+
+int sxc_get_stats(sxc_ctx* ctx, sxc_stats* out) {
   if (!ctx || !out) return SXC_ERR_INVALID;
+  collect_timers(ctx);
   *out = ctx->stats;
   return SXC_OK;
 }

@@ -1,0 +1,92 @@
+"""Multi-GPU host layer: grid blocks sharded over the ranks of one node, ONE all-reduce of [V | E | N] per build.
+
+SURVEY.md section 8e: the reference parallelises the path with `#pragma omp parallel for` over 128-point blocks
+(MatrixOperatorToGridTransformer.cpp:103, XCFun.cpp:129, ScalarOperatorToMatrixAdder.cpp:66,101) and sums per-thread
+nb x nb accumulators serially (ScalarOperatorToMatrixAdder.cpp:73-75).  Here: one process per GPU (torchrun), every rank
+holds the grid / shell table / P, evaluates a contiguous cost-balanced range of blocks (sxc_set_grid_shard) and the
+partial sums are combined by a single `all_reduce(SUM)` of nspin*nb*nb + 2 doubles over NCCL (NVLink 5 / NVSwitch).
+torch is plumbing only (device buffers, streams, the process group); all numbers come from the CUDA library.
+
+The local builder is injectable so that the reduce / layout logic is testable with the gloo backend on CPU
+(tests/test_sharded_gloo.py drives it with the oracle restricted to the rank's block range).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(costs, world: int):
+    """Contiguous block ranges of nearly equal summed cost: the host-only helper behind sxc_set_grid_shard."""
+    import ctypes as C
+    from . import _lib
+    costs = np.ascontiguousarray(costs, dtype=np.float64)
+    bounds = np.zeros(world + 1, dtype=np.int32)
+    rc = _lib.load().sxc_balance_ranges(len(costs), costs.ctypes.data_as(C.c_void_p), world,
+                                        bounds.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise _lib.SerenityError("sxc_balance_ranges failed (%d)" % rc)
+    return bounds
+
+
+class ShardedBuild:
+    """[V | E | N] of one XC build summed over the ranks of `group`.
+
+    local_build(d_P, d_VEN) must enqueue this rank's partial build on the current stream / device of d_VEN
+    (CUDA: XCContext.build_xc_device with the context's stream set to torch's current stream).
+    """
+
+    def __init__(self, nbf: int, local_build: Callable[[torch.Tensor, torch.Tensor], None], device,
+                 group: Optional[dist.ProcessGroup] = None, ntail: int = 2):
+        self.nbf, self.ntail = nbf, ntail
+        self._local = local_build
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.device = torch.device(device)
+        n = nbf * nbf
+        self.d_P = torch.zeros(n, dtype=torch.float64, device=self.device)
+        self.d_VEN = torch.zeros(n + ntail, dtype=torch.float64, device=self.device)
+        pin = self.device.type == "cuda"
+        self.h_P = torch.zeros(n, dtype=torch.float64, pin_memory=pin)
+        self.h_VEN = torch.zeros(n + ntail, dtype=torch.float64, pin_memory=pin)
+
+    # device-resident: P already in d_P, result stays in d_VEN (asynchronous on CUDA)
+    def build_device(self) -> torch.Tensor:
+        self._local(self.d_P, self.d_VEN)
+        if self.world > 1:
+            dist.all_reduce(self.d_VEN, op=dist.ReduceOp.SUM, group=self.group)
+        return self.d_VEN
+
+    # host buffers in, host buffers out: what FuncPotential::getMatrix/getEnergy hand to the SCF driver
+    def build(self, P: np.ndarray):
+        n = self.nbf * self.nbf
+        self.h_P.numpy()[:] = np.asarray(P, dtype=np.float64).reshape(-1, order="F")
+        self.d_P.copy_(self.h_P, non_blocking=True)
+        self.build_device()
+        self.h_VEN.copy_(self.d_VEN, non_blocking=True)
+        if self.device.type == "cuda":
+            torch.cuda.current_stream(self.device).synchronize()
+        out = self.h_VEN.numpy()
+        V = out[:n].reshape(self.nbf, self.nbf, order="F").copy(order="F")
+        return V, float(out[n]), float(out[n + 1])
+
+    @property
+    def h2d_bytes(self) -> int:
+        return self.h_P.numel() * 8
+
+    @property
+    def d2h_bytes(self) -> int:
+        return self.h_VEN.numel() * 8
+
+
+def cuda_local_build(ctx, grid: int, basis: int, func: int, block_ave_threshold: float = 1e-11):
+    """local_build for ShardedBuild on a CUDA rank: sxc_build_xc_device on torch's current stream."""
+
+    def run(d_P: torch.Tensor, d_VEN: torch.Tensor):
+        ctx.set_stream(torch.cuda.current_stream(d_P.device).cuda_stream)
+        ctx.build_xc_device(grid, basis, func, d_P.data_ptr(), d_VEN.data_ptr(), block_ave_threshold)
+
+    return run

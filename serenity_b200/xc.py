@@ -57,6 +57,9 @@ class XCContext:
     def set_workspace_limit(self, nbytes: int):
         self._check(self._lib.sxc_set_workspace_limit(self._h, int(nbytes)))
 
+    def set_timing(self, on: bool):
+        self._check(self._lib.sxc_set_timing(self._h, 1 if on else 0))
+
     def set_grid(self, xyz, w, blocksize: int = 128) -> int:
         xyz = _f64(xyz).reshape(-1, 3)
         w = _f64(w)

@@ -1,0 +1,69 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol include/*.h declares,
+fails loudly without a GPU (no CPU fallback), and the host-only helpers work."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "serenity_xc_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sxc_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from serenity_b200 import _lib
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), "libserenity_xc_b200.so lacks %s" % name
+    assert sorted(_lib.SYMBOLS) == declared  # the ctypes binding covers the whole header
+    assert lib.sxc_abi_version() == 2
+
+
+def test_stats_struct_matches_header():
+    """ctypes mirror of sxc_stats has the layout of the C struct (10 int64, 2 int32, 8 float, 8 int32, 1 float)."""
+    from serenity_b200._lib import Stats
+    assert C.sizeof(Stats) == 10 * 8 + 2 * 4 + 8 * 4 + 8 * 4 + 4 + 4  # + tail padding to 8
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from serenity_b200.xc import XCContext
+    from serenity_b200._lib import SerenityError
+    with pytest.raises(SerenityError):
+        XCContext(0)
+
+
+def test_product_path_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "serenity_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in src.lower() or f == "sharded.py" and "import oracle" not in src and "from oracle" not in src, \
+                    os.path.join(dirpath, f)
+
+
+def test_balance_ranges_contiguous_and_balanced():
+    from serenity_b200.sharded import shard_bounds
+    rng = np.random.default_rng(3)
+    cost = rng.uniform(1.0, 100.0, size=1000)
+    for world in (1, 2, 3, 4, 8):
+        b = shard_bounds(cost, world)
+        assert b[0] == 0 and b[-1] == len(cost) and np.all(np.diff(b) >= 0)
+        sums = [cost[b[r]:b[r + 1]].sum() for r in range(world)]
+        assert max(sums) - min(sums) <= 2 * cost.max() + 1e-9
+    # degenerate inputs: fewer blocks than ranks, empty list
+    b = shard_bounds(np.ones(3), 8)
+    assert b[0] == 0 and b[-1] == 3 and np.all(np.diff(b) >= 0) and np.diff(b).sum() == 3
+    b = shard_bounds(np.zeros(0), 4)
+    assert list(b) == [0, 0, 0, 0, 0]
