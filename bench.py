@@ -224,7 +224,6 @@ def run_b200(args):
     sub = cfg.subsystems[0]
     nbf = sub.basis.nbf
     ctx = XCContext(local)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     g = ctx.set_grid(cfg.xyz, cfg.w, 128)
     if world > 1:
         ctx.set_grid_shard(g, rank, world)
@@ -340,7 +339,7 @@ def run_b200(args):
                 "config": config_dict(cfg, world, {
                     "l2": "no flush: one build streams %.2f GB of phi/grad-phi tiles (>> 126 MB L2) between uses of any "
                           "input" % (tile_bytes / 1e9),
-                    "sum_n_s2": st["sum_ns2"], "s_max": st["s_max"], "s_mean": st["sum_s"] / max(1, st["nblocks"]),
+                    "sum_n_s2": st["sum_ns2"], "sum_n_s2_padded": st["sum_ns2_padded"], "s_max": st["s_max"], "s_mean": st["sum_s"] / max(1, st["nblocks"]),
                     "chunks": st["nchunks"], "shard_points": [s_["npts"] for s_ in stats_all]}),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_build * args.steps * world,
                 "kernels_ms_per_build": per_build_ms, "roofline": roof,

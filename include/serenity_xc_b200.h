@@ -95,7 +95,8 @@ typedef struct {
 int sxc_create(sxc_ctx** ctx, int device);
 void sxc_destroy(sxc_ctx* ctx);
 const char* sxc_last_error(const sxc_ctx* ctx);
-/* run on the caller's stream (cudaStream_t passed as void*); NULL = the context's own stream */
+/* run on the caller's stream (cudaStream_t passed as void*); NULL = the context's own (non-blocking) stream;
+ * pass cudaStreamLegacy ((void*)0x1) to name the legacy default stream */
 int sxc_set_stream(sxc_ctx* ctx, void* cuda_stream);
 /* cap of the phi/grad-phi tile buffer in bytes (default: 40 % of free device memory at plan time) */
 int sxc_set_workspace_limit(sxc_ctx* ctx, int64_t bytes);

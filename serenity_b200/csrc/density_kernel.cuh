@@ -4,12 +4,14 @@
 // (src/data/grid/MatrixOperatorToGridTransformer.cpp:103-165):
 //     phi_s = phi Proj,  P_s = Proj^T P Proj,  B = phi_s P_s,
 //     rho_p = sum_mu B_pmu phi_pmu,   grad rho_p = 2 sum_mu B_pmu grad phi_pmu.
-// B200 design: one CTA (16 warps, 4 x 4 warp tiles of 32 points x 32 functions) per 128-point block. The product
-// runs as DMMA m8n8k4 tiles (mma.sync ... f64, the only FP64 tensor path on sm_100a): per j-tile of 128 functions
-// the K loop streams 16-function chunks of the phi tile (cp.async, 16 B) and the matching gathered P_s chunk
-// (cp.async, 8 B, straight from the L2-resident nb x nb matrix through the block's compact->function map) through a
-// 4-stage shared-memory ring; B never leaves registers - the epilogue multiplies the accumulator fragments with
-// phi / grad phi read in fragment layout (full 32-byte sectors) and reduces over functions with warp shuffles.
+// B200 design: one CTA (8 warps = 4 point groups x 2 function groups, warp tile 32 points x 32 functions; two CTAs
+// per SM) per 128-point block.  The product runs as DMMA m8n8k4 tiles (mma.sync ... f64, the only FP64 tensor path on
+// sm_100a): per j-tile of 64 functions the K loop streams 16-function chunks of the phi tile (cp.async, 16 B) and the
+// matching gathered P_s chunk (cp.async, 8 B, straight from the L2-resident nb x nb matrix through the block's
+// compact->function map) through a 3-stage shared-memory ring; B never leaves registers - the epilogue multiplies the
+// accumulator fragments with phi / grad phi read in fragment layout (full 32-byte sectors) and reduces over functions
+// with warp shuffles.  s_pad is a multiple of 32, so the last j-tile may hold a single 32-function group: its K range
+// is then split over the two function-group warps (rho is linear in B, so the halves need no extra reduction).
 #pragma once
 
 #include "sxc_common.cuh"
@@ -17,30 +19,31 @@
 namespace sxc {
 
 namespace dens {
-constexpr int THREADS = 512;
-constexpr int TJ = 128;       // functions per j-tile
+constexpr int THREADS = 256;
+constexpr int TJ = 64;        // functions per j-tile
 constexpr int TK = 16;        // functions per K chunk
 constexpr int A_STRIDE = BP + 4;   // 132: conflict-free fragment loads (stride = 4 mod 16 doubles)
 constexpr int B_STRIDE = TK + 4;   // 20
-constexpr int STAGES = 4;
+constexpr int STAGES = 3;
 constexpr int A_ELEMS = TK * A_STRIDE;   // 2112 doubles
 constexpr int B_ELEMS = TJ * B_STRIDE;   // 1280 doubles
 constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
+constexpr int NJW = 2;
 constexpr size_t smem_bytes(int s_pad_max) {
-  return (size_t)STAGES * STAGE_ELEMS * sizeof(double) + (size_t)4 * BP * 4 * sizeof(double) +
+  return (size_t)STAGES * STAGE_ELEMS * sizeof(double) + (size_t)NJW * BP * 4 * sizeof(double) +
          (size_t)(s_pad_max + TJ) * sizeof(int);
 }
 }  // namespace dens
 
-__global__ void __launch_bounds__(dens::THREADS, 1)
+__global__ void __launch_bounds__(dens::THREADS, 2)
 k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, const int* __restrict__ order,
           const double* __restrict__ phi_buf, double* __restrict__ rho, double* __restrict__ gx,
           double* __restrict__ gy, double* __restrict__ gz, int* __restrict__ nonneg) {
   using namespace dens;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* stage_base = reinterpret_cast<double*>(smem_raw);
-  double* red = stage_base + STAGES * STAGE_ELEMS;          // [4][128][4]
-  int* sig = reinterpret_cast<int*>(red + 4 * BP * 4);      // [s_pad + TJ]
+  double* red = stage_base + STAGES * STAGE_ELEMS;          // [NJW][128][4]
+  int* sig = reinterpret_cast<int*>(red + NJW * BP * 4);    // [s_pad + TJ]
 
   const int q = order[blockIdx.x];
   const int blk = plan.block_id[q];
@@ -69,7 +72,7 @@ k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, cons
 
   const int nk = sp / TK;                 // K chunks per j-tile
   const int n32 = sp / 32;                // 32-function column groups
-  const int njt = (n32 + 3) / 4;          // j-tiles of 128
+  const int njt = (n32 + NJW - 1) / NJW;  // j-tiles of 64
   const int total = njt * nk;
   const int pw = warp & 3, jw = warp >> 2;
   const int lr = lane >> 2, lc = lane & 3;
@@ -87,25 +90,27 @@ k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, cons
         cp_async16(As + row * A_STRIDE + c16 * 2, src + (size_t)row * BP + c16 * 2);
       }
       const int j0 = jt * TJ, k0 = kc * TK;
+      const int ncol = min(TJ, sp - j0);
 #pragma unroll
-      for (int i = 0; i < (TJ * TK) / THREADS; ++i) {  // 2048 x 8 B gathers: B[j][k] = P[sig[k], sig[j]]
+      for (int i = 0; i < (TJ * TK) / THREADS; ++i) {  // <= 1024 x 8 B gathers: B[j][k] = P[sig[k], sig[j]]
         const int idx = tid + i * THREADS;
         const int k = idx & (TK - 1), j = idx >> 4;
-        cp_async8(Bs + j * B_STRIDE + k, P + (size_t)sig[k0 + k] + (size_t)sig[j0 + j] * nbf);
+        if (j < ncol) cp_async8(Bs + j * B_STRIDE + k, P + (size_t)sig[k0 + k] + (size_t)sig[j0 + j] * nbf);
       }
     }
     cp_async_commit();
   };
 
   double acc[4][4][2];
-  for (int i = tid; i < 4 * BP * 4; i += THREADS) red[i] = 0.0;
+  for (int i = tid; i < NJW * BP * 4; i += THREADS) red[i] = 0.0;
 
   issue(0);
   issue(1);
-  issue(2);
   int gi = 0;
   for (int jt = 0; jt < njt; ++jt) {
-    const bool active = (jt * 4 + jw) < n32;  // the last j-tile may hold fewer than four 32-column groups
+    // a last j-tile with one 32-function group: both function-group warps work on it, on alternating k-steps
+    const bool split = (n32 - jt * NJW) == 1;
+    const int cg = split ? 0 : jw;
 #pragma unroll
     for (int m = 0; m < 4; ++m)
 #pragma unroll
@@ -113,27 +118,26 @@ k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, cons
     for (int kc = 0; kc < nk; ++kc, ++gi) {
       cp_async_wait<STAGES - 2>();
       __syncthreads();
-      issue(gi + 3);
-      if (active) {
-        const double* As = stage_base + (gi % STAGES) * STAGE_ELEMS;
-        const double* Bs = As + A_ELEMS;
+      issue(gi + STAGES - 1);
+      const double* As = stage_base + (gi % STAGES) * STAGE_ELEMS;
+      const double* Bs = As + A_ELEMS;
 #pragma unroll
-        for (int ks = 0; ks < TK / 4; ++ks) {
-          double a[4], bfrag[4];
+      for (int ks = 0; ks < TK / 4; ++ks) {
+        if (split && (ks & 1) != jw) continue;
+        double a[4], bfrag[4];
 #pragma unroll
-          for (int m = 0; m < 4; ++m) a[m] = As[(ks * 4 + lc) * A_STRIDE + pw * 32 + m * 8 + lr];
+        for (int m = 0; m < 4; ++m) a[m] = As[(ks * 4 + lc) * A_STRIDE + pw * 32 + m * 8 + lr];
 #pragma unroll
-          for (int nn = 0; nn < 4; ++nn) bfrag[nn] = Bs[(jw * 32 + nn * 8 + lr) * B_STRIDE + ks * 4 + lc];
+        for (int nn = 0; nn < 4; ++nn) bfrag[nn] = Bs[(cg * 32 + nn * 8 + lr) * B_STRIDE + ks * 4 + lc];
 #pragma unroll
-          for (int m = 0; m < 4; ++m)
+        for (int m = 0; m < 4; ++m)
 #pragma unroll
-            for (int nn = 0; nn < 4; ++nn) dmma884(acc[m][nn][0], acc[m][nn][1], a[m], bfrag[nn]);
-        }
+          for (int nn = 0; nn < 4; ++nn) dmma884(acc[m][nn][0], acc[m][nn][1], a[m], bfrag[nn]);
       }
     }
-    if (active) {
+    {
       // epilogue: rho += B o phi, grad rho += B o grad phi   (MatrixOperatorToGridTransformer.cpp:158-163)
-      const int jbase = jt * TJ + jw * 32 + 2 * lc;
+      const int jbase = jt * TJ + cg * 32 + 2 * lc;
       double r_rho[4], r_x[4], r_y[4], r_z[4];
 #pragma unroll
       for (int m = 0; m < 4; ++m) r_rho[m] = r_x[m] = r_y[m] = r_z[m] = 0.0;
@@ -180,7 +184,7 @@ k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, cons
   if (tid < n) {
     double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {  // fixed order over the four j-warp groups
+    for (int jj = 0; jj < NJW; ++jj) {  // fixed order over the function-group warps
       const double* a = red + ((size_t)jj * BP + tid) * 4;
       r0 += a[0];
       r1 += a[1];

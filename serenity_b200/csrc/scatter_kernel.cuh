@@ -6,11 +6,14 @@
 //     T = phi_s^T G;  V_s = T + T^T;  V += Proj V_s Proj^T.
 // The LDA variant (:179-223, V_s = phi_s^T diag(a) phi_s) is the same expression with b = 0.
 // B200 design: k_form_g builds G in place of the d_x phi tile (bandwidth-bound, fused with the block-average
-// test); k_scatter computes only the upper triangle of V_s as stacked-K DMMA tiles
-//     U[I,J] = [phi_I | G_I] . [G_J | phi_J]^T      (K = 2 x 128 points)
-// with 128 x 128 output tiles (16 warps, 4 x 4 warp tiles of 32 x 32), a 4-stage cp.async ring over 8-point K chunks,
-// and accumulates into the GPU-resident
-// upper triangle with FP64 red.global (RED.E.ADD.F64); k_mirror copies the strict upper triangle down once per build.
+// test); k_scatter computes only the upper triangle of V_s, cut into 32 x 32 warp tiles
+//     U[I,J] = [phi_I | G_I] . [G_J | phi_J]^T      (stacked K = 2 x 128 points, DMMA m8n8k4)
+// A work item ("round") is a host-scheduled set of <= 8 warp tiles of one block that touch <= 6 distinct 32-row groups
+// (sxc_api.cu: scatter_schedule): the CTA (8 warps, two CTAs per SM) stages phi and G rows of those groups through a
+// 3-stage cp.async ring over 8-point K chunks, every warp owns one tile (rounds with <= 4 tiles split the two k-steps of
+// a chunk over two warps), and the accumulators go straight into the GPU-resident upper triangle with FP64
+// red.global (RED.E.ADD.F64); k_mirror copies the strict upper triangle down once per build.  Scheduling at warp-tile
+// granularity keeps > 90 % of the DMMA slots busy for any s (128 x 128 CTA tiles left half of them idle at s ~ 280).
 #pragma once
 
 #include "sxc_common.cuh"
@@ -67,155 +70,125 @@ k_form_g(GridView g, PlanView plan, const int* __restrict__ order, double block_
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// K4: U = phi_I G_J^T + G_I phi_J^T on 128 x 128 tiles, upper triangle only, atomically accumulated into W.
-// Work item = (slot q, row tile I); the CTA loops over the column tiles J >= I.
+// K4: U = phi_I G_J^T + G_I phi_J^T on 32 x 32 warp tiles of the upper triangle, atomically accumulated into W.
 // ------------------------------------------------------------------------------------------------------------
 namespace scat {
-constexpr int THREADS = 512;
-constexpr int TI = 128, TJ = 128;
+constexpr int WARPS = 8;
+constexpr int THREADS = WARPS * 32;
+constexpr int MAXG = 6;              // distinct 32-row groups staged per round
 constexpr int TKP = 8;               // points per K chunk
 constexpr int STRIDE = TKP + 4;      // 12 doubles: conflict-free fragment loads
-constexpr int ROWS = 2 * TI + 2 * TJ;  // phi_I, G_I, G_J, phi_J
-constexpr int STAGE_ELEMS = ROWS * STRIDE;
-constexpr int STAGES = 4;
-constexpr size_t smem_bytes(int s_pad_max) {
-  return (size_t)STAGES * STAGE_ELEMS * sizeof(double) + (size_t)(s_pad_max + TI) * sizeof(int);
-}
+constexpr int GROUP_ELEMS = 64 * STRIDE;        // 32 phi rows then 32 G rows of one group
+constexpr int STAGE_ELEMS = MAXG * GROUP_ELEMS;  // 4608 doubles
+constexpr int STAGES = 3;
+constexpr size_t smem_bytes() { return (size_t)STAGES * STAGE_ELEMS * sizeof(double); }
 }  // namespace scat
 
-struct ScatterItem {
-  int q;   // plan slot
-  int it;  // row tile index (128 rows)
+// one round of one block: which 32-row groups to stage and which tile each warp owns
+struct ScatterRound {
+  int q;                       // plan slot
+  unsigned char ngroups;       // staged groups (<= MAXG)
+  unsigned char pad[3];
+  unsigned char group[8];      // 32-row group index inside the block, [0, s_pad / 32)
+  unsigned char ta[8];         // per warp: staged slot of the row group I (0xff: idle warp)
+  unsigned char tb[8];         // per warp: staged slot of the column group J >= I
+  unsigned char kmask[8];      // per warp: k-steps of a chunk it multiplies (bit 0 / bit 1)
 };
+static_assert(sizeof(ScatterRound) == 40, "ScatterRound layout");
 
-__global__ void __launch_bounds__(scat::THREADS, 1)
-k_scatter(PlanView plan, int nbf, const ScatterItem* __restrict__ items, const int* __restrict__ skip_flag,
+__global__ void __launch_bounds__(scat::THREADS, 2)
+k_scatter(PlanView plan, int nbf, const ScatterRound* __restrict__ rounds, const int* __restrict__ skip_flag,
           const double* __restrict__ phi_buf, double* __restrict__ W) {
   using namespace scat;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* stage_base = reinterpret_cast<double*>(smem_raw);
-  int* sig = reinterpret_cast<int*>(stage_base + STAGES * STAGE_ELEMS);
+  __shared__ ScatterRound rd;
 
-  const ScatterItem item = items[blockIdx.x];
-  const int q = item.q;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < (int)(sizeof(ScatterRound) / sizeof(int)))
+    reinterpret_cast<int*>(&rd)[tid] = reinterpret_cast<const int*>(rounds + blockIdx.x)[tid];
+  __syncthreads();
+  const int q = rd.q;
   if (skip_flag[q]) return;
   const int s = plan.s[q];
   const int sp = plan.s_pad[q];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double* __restrict__ phi = phi_buf + plan.phi_off[q];
   const double* __restrict__ G = phi + (size_t)sp * BP;  // G lives in the d_x phi slot
-  const int* __restrict__ sig_g = plan.sig_bf + (size_t)q * plan.nbf_pad;
-  for (int c = tid; c < sp; c += THREADS) sig[c] = sig_g[c];
-
-  const int i0 = item.it * TI;
-  const int nj = sp / TJ + ((sp % TJ) ? 1 : 0);
-  const int jt0 = (i0 / TJ);  // first column tile that reaches the diagonal
-  const int npairs = nj - jt0;
-  constexpr int NKC = BP / TKP;  // 16 chunks per tile pair
-  const int total = npairs * NKC;
-  const int pw = warp & 3, jw = warp >> 2;
+  const int* __restrict__ sig = plan.sig_bf + (size_t)q * plan.nbf_pad;
+  const int nload = rd.ngroups * 64 * 4;  // 16-byte pieces per stage
+  constexpr int NKC = BP / TKP;           // 16 chunks
   const int lr = lane >> 2, lc = lane & 3;
 
-  auto issue = [&](int gi) {
-    if (gi < total) {
-      const int jp = gi / NKC, kc = gi - jp * NKC;
-      const int j0 = (jt0 + jp) * TJ;
-      double* st = stage_base + (gi % STAGES) * STAGE_ELEMS;
-      // 512 rows x 64 B = 2048 x 16 B
-#pragma unroll
-      for (int i = 0; i < (ROWS * 4) / THREADS; ++i) {
-        const int idx = tid + i * THREADS;
+  auto issue = [&](int kc) {
+    if (kc < NKC) {
+      double* st = stage_base + (kc % STAGES) * STAGE_ELEMS;
+      for (int idx = tid; idx < nload; idx += THREADS) {
         const int row = idx >> 2, c16 = idx & 3;
-        int r;
-        const double* src;
-        if (row < TI) {
-          r = i0 + row;
-          src = phi;
-        } else if (row < 2 * TI) {
-          r = i0 + row - TI;
-          src = G;
-        } else if (row < 2 * TI + TJ) {
-          r = j0 + row - 2 * TI;
-          src = G;
-        } else {
-          r = j0 + row - 2 * TI - TJ;
-          src = phi;
-        }
-        r = min(r, sp - 1);  // rows past s_pad are masked at the atomics stage
-        cp_async16(st + row * STRIDE + c16 * 2, src + (size_t)r * BP + kc * TKP + c16 * 2);
+        const int grp = row >> 6, r = row & 63;
+        const double* src = ((r & 32) ? G : phi) + (size_t)(rd.group[grp] * 32 + (r & 31)) * BP + kc * TKP + c16 * 2;
+        cp_async16(st + row * STRIDE + c16 * 2, src);
       }
     }
     cp_async_commit();
   };
 
+  const int sa = rd.ta[warp], sb = rd.tb[warp], kmask = rd.kmask[warp];
+  const bool active = sa != 0xff;
   double acc[4][4][2];
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+#pragma unroll
+    for (int nn = 0; nn < 4; ++nn) acc[m][nn][0] = acc[m][nn][1] = 0.0;
   issue(0);
   issue(1);
-  issue(2);
-  __syncthreads();  // sig[] visible
-  int gi = 0;
-  for (int jp = 0; jp < npairs; ++jp) {
-    const int j0 = (jt0 + jp) * TJ;
-    // warp tiles entirely below the diagonal or outside the matrix contribute nothing
-    const int wi0 = i0 + pw * 32, wj0 = j0 + jw * 32;
-    const bool active = (wi0 < sp) && (wj0 < sp) && (wj0 + 31 >= wi0);
+  for (int kc = 0; kc < NKC; ++kc) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    issue(kc + STAGES - 1);
+    if (active) {
+      const double* st = stage_base + (kc % STAGES) * STAGE_ELEMS;
+      const double* sI = st + sa * GROUP_ELEMS;  // phi_I rows 0..31, G_I rows 32..63
+      const double* sJ = st + sb * GROUP_ELEMS;
 #pragma unroll
-    for (int m = 0; m < 4; ++m)
+      for (int ks = 0; ks < TKP / 4; ++ks) {
+        if (!((kmask >> ks) & 1)) continue;
+        double a1[4], a2[4], b1[4], b2[4];
 #pragma unroll
-      for (int nn = 0; nn < 4; ++nn) acc[m][nn][0] = acc[m][nn][1] = 0.0;
-    for (int kc = 0; kc < NKC; ++kc, ++gi) {
-      cp_async_wait<STAGES - 2>();
-      __syncthreads();
-      issue(gi + 3);
-      if (active) {
-        const double* st = stage_base + (gi % STAGES) * STAGE_ELEMS;
-        const double* sPhiI = st;
-        const double* sGI = st + TI * STRIDE;
-        const double* sGJ = st + 2 * TI * STRIDE;
-        const double* sPhiJ = sGJ + TJ * STRIDE;
+        for (int m = 0; m < 4; ++m) {
+          const int o = (m * 8 + lr) * STRIDE + ks * 4 + lc;
+          a1[m] = sI[o];
+          a2[m] = sI[o + 32 * STRIDE];
+          b2[m] = sJ[o];
+          b1[m] = sJ[o + 32 * STRIDE];
+        }
 #pragma unroll
-        for (int ks = 0; ks < TKP / 4; ++ks) {
-          double a1[4], a2[4], b1[4], b2[4];
-#pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            const int o = (pw * 32 + m * 8 + lr) * STRIDE + ks * 4 + lc;
-            a1[m] = sPhiI[o];
-            a2[m] = sGI[o];
-          }
+        for (int m = 0; m < 4; ++m)
 #pragma unroll
           for (int nn = 0; nn < 4; ++nn) {
-            const int o = (jw * 32 + nn * 8 + lr) * STRIDE + ks * 4 + lc;
-            b1[nn] = sGJ[o];
-            b2[nn] = sPhiJ[o];
+            dmma884(acc[m][nn][0], acc[m][nn][1], a1[m], b1[nn]);
+            dmma884(acc[m][nn][0], acc[m][nn][1], a2[m], b2[nn]);
           }
-#pragma unroll
-          for (int m = 0; m < 4; ++m)
-#pragma unroll
-            for (int nn = 0; nn < 4; ++nn) {
-              dmma884(acc[m][nn][0], acc[m][nn][1], a1[m], b1[nn]);
-              dmma884(acc[m][nn][0], acc[m][nn][1], a2[m], b2[nn]);
-            }
-        }
       }
-    }
-    if (active) {
-      // V += Proj V_s Proj^T (:301), upper triangle (compact i <= j <=> global sig[i] <= sig[j])
-#pragma unroll
-      for (int nn = 0; nn < 4; ++nn)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int j = wj0 + nn * 8 + 2 * lc + e;
-          if (j >= s) continue;
-          const size_t col = (size_t)sig[j] * nbf;
-#pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            const int i = wi0 + m * 8 + lr;
-            if (i <= j) atomicAdd(W + col + sig[i], acc[m][nn][e]);
-          }
-        }
     }
   }
   cp_async_wait<0>();
+  if (active) {
+    // V += Proj V_s Proj^T (:301), upper triangle (compact i <= j <=> global sig[i] <= sig[j])
+    const int i0 = rd.group[sa] * 32, j0 = rd.group[sb] * 32;
+#pragma unroll
+    for (int nn = 0; nn < 4; ++nn)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = j0 + nn * 8 + 2 * lc + e;
+        if (j >= s) continue;
+        const size_t col = (size_t)sig[j] * nbf;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const int i = i0 + m * 8 + lr;
+          if (i <= j) atomicAdd(W + col + sig[i], acc[m][nn][e]);
+        }
+      }
+  }
 }
 
 // V[j,i] = V[i,j] for i < j (column-major, upper triangle holds the sums)

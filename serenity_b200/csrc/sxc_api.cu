@@ -155,6 +155,7 @@ struct sxc_ctx {
   std::vector<std::unique_ptr<Basis>> bases;
   std::vector<FuncView> funcs;
   std::map<std::pair<int, int>, std::unique_ptr<Plan>> plans;
+  std::map<int, std::vector<ScatterRound>> scatter_tpl;  // round templates per s_pad / 32
   DevMem phi;     // tile workspace (one chunk)
   DevMem dP;      // staged density matrices (host API)
   DevMem dOut;    // staged V | E | N (host API)
@@ -214,7 +215,7 @@ Basis* get_basis(sxc_ctx* ctx, int h) { return (h >= 0 && h < (int)ctx->bases.si
 int set_kernel_attrs(sxc_ctx* ctx) {
   if (ctx->attrs_set) return SXC_OK;
   CU(cudaFuncSetAttribute(k_density, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  CU(cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CU(cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scat::smem_bytes()));
   ctx->attrs_set = true;
   return SXC_OK;
 }
@@ -317,6 +318,66 @@ int64_t workspace_limit(sxc_ctx* ctx) {
   return (int64_t)((free_b + ctx->phi.bytes) * 0.4);
 }
 
+// Scatter schedule of a block with n32 = s_pad / 32 row groups: the n32 (n32 + 1) / 2 upper-triangle warp tiles are
+// walked in bands of two row groups (column-major inside a band) and cut into rounds of <= WARPS tiles that touch
+// <= MAXG distinct groups; rounds of <= WARPS / 2 tiles give every tile to two warps (one k-step of each chunk each).
+const std::vector<ScatterRound>& scatter_schedule(sxc_ctx* ctx, int n32) {
+  auto it = ctx->scatter_tpl.find(n32);
+  if (it != ctx->scatter_tpl.end()) return it->second;
+  std::vector<std::pair<int, int>> tiles;
+  for (int b0 = 0; b0 < n32; b0 += 2)
+    for (int j = b0; j < n32; ++j)
+      for (int i = b0; i < std::min(b0 + 2, n32); ++i)
+        if (i <= j) tiles.push_back({i, j});
+  const int T = (int)tiles.size();
+  const int R = (T + scat::WARPS - 1) / scat::WARPS;
+  const int per = (T + R - 1) / R;
+  std::vector<ScatterRound> out;
+  std::vector<std::pair<int, int>> cur;
+  std::vector<int> groups;
+  auto flush = [&]() {
+    if (cur.empty()) return;
+    ScatterRound r;
+    std::memset(&r, 0, sizeof(r));
+    std::memset(r.ta, 0xff, sizeof(r.ta));
+    std::memset(r.tb, 0xff, sizeof(r.tb));
+    std::sort(groups.begin(), groups.end());
+    r.ngroups = (unsigned char)groups.size();
+    for (size_t k = 0; k < groups.size(); ++k) r.group[k] = (unsigned char)groups[k];
+    auto slot = [&](int gidx) { return (unsigned char)(std::find(groups.begin(), groups.end(), gidx) - groups.begin()); };
+    const int nt = (int)cur.size();
+    const bool split = nt * 2 <= scat::WARPS;
+    for (int w = 0; w < nt; ++w) {
+      r.ta[w] = slot(cur[w].first);
+      r.tb[w] = slot(cur[w].second);
+      r.kmask[w] = split ? 1 : 3;
+      if (split) {
+        r.ta[nt + w] = r.ta[w];
+        r.tb[nt + w] = r.tb[w];
+        r.kmask[nt + w] = 2;
+      }
+    }
+    out.push_back(r);
+    cur.clear();
+    groups.clear();
+  };
+  for (const auto& t : tiles) {
+    std::vector<int> g2 = groups;
+    if (std::find(g2.begin(), g2.end(), t.first) == g2.end()) g2.push_back(t.first);
+    if (std::find(g2.begin(), g2.end(), t.second) == g2.end()) g2.push_back(t.second);
+    if ((int)cur.size() >= per || (int)g2.size() > scat::MAXG) {
+      flush();
+      g2.clear();
+      g2.push_back(t.first);
+      if (t.second != t.first) g2.push_back(t.second);
+    }
+    cur.push_back(t);
+    groups = g2;
+  }
+  flush();
+  return ctx->scatter_tpl[n32] = out;
+}
+
 int get_plan(sxc_ctx* ctx, int gh, int bh, Plan** out) {
   Grid* g = get_grid(ctx, gh);
   Basis* b = get_basis(ctx, bh);
@@ -405,36 +466,35 @@ int get_plan(sxc_ctx* ctx, int gh, int bh, Plan** out) {
     return fail(ctx, SXC_ERR_UNSUPPORTED, "grid.blocksize != 128 needs the whole grid in one workspace chunk");
   st.nchunks = (int)p.chunks.size();
   std::vector<int> order(std::max(p.nown, 1));
-  std::vector<ScatterItem> items;
+  std::vector<ScatterRound> items;
   for (Chunk& c : p.chunks) {
     c.order_off = c.slot0;
     std::iota(order.begin() + c.slot0, order.begin() + c.slot0 + c.nslots, c.slot0);
     std::stable_sort(order.begin() + c.slot0, order.begin() + c.slot0 + c.nslots,
                      [&](int a, int bq) { return p.h_s_pad[a] > p.h_s_pad[bq]; });
     c.item_off = (int)items.size();
-    std::vector<std::pair<long, ScatterItem>> tmp;
-    for (int k = 0; k < c.nslots; ++k) {
-      const int q = c.slot0 + k;
+    for (int k = 0; k < c.nslots; ++k) {  // largest blocks first; the rounds of a block stay adjacent (L2 reuse)
+      const int q = order[c.slot0 + k];
       if (p.h_s[q] == 0) continue;
-      const int nt = (p.h_s_pad[q] + scat::TI - 1) / scat::TI;
-      for (int it = 0; it < nt; ++it) tmp.push_back({(long)(nt - it) * 1, ScatterItem{q, it}});
+      for (ScatterRound r : scatter_schedule(ctx, p.h_s_pad[q] / 32)) {
+        r.q = q;
+        items.push_back(r);
+      }
     }
-    std::stable_sort(tmp.begin(), tmp.end(), [](const auto& a, const auto& bq) { return a.first > bq.first; });
-    for (auto& t : tmp) items.push_back(t.second);
     c.nitems = (int)items.size() - c.item_off;
     st.workspace_bytes = std::max<int64_t>(st.workspace_bytes, (int64_t)(c.doubles * sizeof(double)));
   }
   CU(p.order.ensure(order.size() * sizeof(int)));
-  CU(p.items.ensure(std::max<size_t>(items.size(), 1) * sizeof(ScatterItem)));
+  CU(p.items.ensure(std::max<size_t>(items.size(), 1) * sizeof(ScatterRound)));
   if (p.nown) {
     CU(cudaMemcpyAsync(p.s_pad.p, p.h_s_pad.data(), p.nown * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(p.phi_off.p, off.data(), p.nown * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(p.order.p, order.data(), p.nown * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   }
   if (!items.empty())
-    CU(cudaMemcpyAsync(p.items.p, items.data(), items.size() * sizeof(ScatterItem), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(p.items.p, items.data(), items.size() * sizeof(ScatterRound), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  if (dens::smem_bytes(p.s_pad_max) > 227 * 1024 || scat::smem_bytes(p.s_pad_max) > 227 * 1024)
+  if (dens::smem_bytes(p.s_pad_max) > 227 * 1024 || p.s_pad_max / 32 > 255)
     return fail(ctx, SXC_ERR_UNSUPPORTED, "more than %d significant functions in one block", p.s_pad_max);
   *out = plan.get();
   ctx->plans[key] = std::move(plan);
@@ -516,8 +576,8 @@ int phase_scatter(sxc_ctx* ctx, const Grid& g, const Basis& b, const Plan& p, co
   }
   if (c.nitems > 0) {
     PhaseTimer t(ctx, SXC_T_SCATTER);
-    k_scatter<<<c.nitems, scat::THREADS, scat::smem_bytes(p.s_pad_max), ctx->stream>>>(
-        p.view(), b.nbf, p.items.as<ScatterItem>() + c.item_off, p.skip.as<int>(), ctx->phi.as<double>(), dW);
+    k_scatter<<<c.nitems, scat::THREADS, scat::smem_bytes(), ctx->stream>>>(
+        p.view(), b.nbf, p.items.as<ScatterRound>() + c.item_off, p.skip.as<int>(), ctx->phi.as<double>(), dW);
     LAUNCH_CHECK();
   }
   return SXC_OK;

@@ -86,7 +86,9 @@ def cuda_local_build(ctx, grid: int, basis: int, func: int, block_ave_threshold:
     """local_build for ShardedBuild on a CUDA rank: sxc_build_xc_device on torch's current stream."""
 
     def run(d_P: torch.Tensor, d_VEN: torch.Tensor):
-        ctx.set_stream(torch.cuda.current_stream(d_P.device).cuda_stream)
+        # torch's default stream is the legacy NULL stream (handle 0); the C ABI reads NULL as "the context's own
+        # stream", so name the legacy stream explicitly (cudaStreamLegacy == (cudaStream_t)0x1)
+        ctx.set_stream(torch.cuda.current_stream(d_P.device).cuda_stream or 1)
         ctx.build_xc_device(grid, basis, func, d_P.data_ptr(), d_VEN.data_ptr(), block_ave_threshold)
 
     return run
