@@ -5,15 +5,18 @@
 //     G = diag(b_x) d_x phi_s + diag(b_y) d_y phi_s + diag(b_z) d_z phi_s + 1/2 diag(a) phi_s;
 //     T = phi_s^T G;  V_s = T + T^T;  V += Proj V_s Proj^T.
 // The LDA variant (:179-223, V_s = phi_s^T diag(a) phi_s) is the same expression with b = 0.
-// B200 design: k_form_g builds G in place of the d_x phi tile (bandwidth-bound, fused with the block-average
-// test); k_scatter computes only the upper triangle of V_s, cut into 32 x 32 warp tiles
-//     U[I,J] = [phi_I | G_I] . [G_J | phi_J]^T      (stacked K = 2 x 128 points, DMMA m8n8k4)
-// A work item ("round") is a host-scheduled set of <= 8 warp tiles of one block that touch <= 6 distinct 32-row groups
-// (sxc_api.cu: scatter_schedule): the CTA (8 warps, two CTAs per SM) stages phi and G rows of those groups through a
-// 3-stage cp.async ring over 8-point K chunks, every warp owns one tile (rounds with <= 4 tiles split the two k-steps of
-// a chunk over two warps), and the accumulators go straight into the GPU-resident upper triangle with FP64
-// red.global (RED.E.ADD.F64); k_mirror copies the strict upper triangle down once per build.  Scheduling at warp-tile
-// granularity keeps > 90 % of the DMMA slots busy for any s (128 x 128 CTA tiles left half of them idle at s ~ 280).
+// B200 design: k_form_g builds G in place of the d_x phi tile (bandwidth-bound: reads 4 tiles, writes 1; fused with
+// the block-average test).  k_vmat is a persistent kernel (8 warps, two CTAs per SM) that pulls blocks from a device
+// work queue (largest first) and computes only the upper triangle of V_s, cut into 32 x 32 warp tiles
+//          U[I,J] = [phi_I | G_I] . [G_J | phi_J]^T      (stacked K = 2 x 128 points, DMMA m8n8k4)
+// in host-scheduled "rounds" (sxc_api.cu: scatter_schedule): <= 8 warp tiles that touch <= 6 distinct 32-row groups.
+// The CTA stages phi and G rows of those groups through a 3-stage cp.async ring over 8-point K chunks (the ring runs
+// across round boundaries, so only the first round of a block pays the fill latency); every warp owns one tile
+// (rounds with <= 4 tiles split the two k-steps of a chunk over two warps), and the accumulators go straight into
+// the GPU-resident upper triangle with FP64 red.global (RED.E.ADD.F64).  k_mirror copies the strict upper triangle
+// down once per build.  Scheduling at warp-tile granularity keeps > 90 % of the DMMA slots busy for any s (128 x 128
+// CTA tiles left half of them idle at s ~ 280).  (Forming G inside k_vmat was tried and lost: with 256 threads per CTA
+// the streaming phase cannot keep enough loads in flight, 4.3 ms against 0.74 + 2.9 ms.)
 #pragma once
 
 #include "sxc_common.cuh"
@@ -69,14 +72,12 @@ k_form_g(GridView g, PlanView plan, const int* __restrict__ order, double block_
   }
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// K4: U = phi_I G_J^T + G_I phi_J^T on 32 x 32 warp tiles of the upper triangle, atomically accumulated into W.
-// ------------------------------------------------------------------------------------------------------------
 namespace scat {
 constexpr int WARPS = 8;
 constexpr int THREADS = WARPS * 32;
 constexpr int MAXG = 6;              // distinct 32-row groups staged per round
 constexpr int TKP = 8;               // points per K chunk
+constexpr int NKC = BP / TKP;        // 16 chunks per round
 constexpr int STRIDE = TKP + 4;      // 12 doubles: conflict-free fragment loads
 constexpr int GROUP_ELEMS = 64 * STRIDE;        // 32 phi rows then 32 G rows of one group
 constexpr int STAGE_ELEMS = MAXG * GROUP_ELEMS;  // 4608 doubles
@@ -84,9 +85,8 @@ constexpr int STAGES = 3;
 constexpr size_t smem_bytes() { return (size_t)STAGES * STAGE_ELEMS * sizeof(double); }
 }  // namespace scat
 
-// one round of one block: which 32-row groups to stage and which tile each warp owns
+// one round of the schedule of a block with s_pad / 32 row groups: which groups to stage, which tile each warp owns
 struct ScatterRound {
-  int q;                       // plan slot
   unsigned char ngroups;       // staged groups (<= MAXG)
   unsigned char pad[3];
   unsigned char group[8];      // 32-row group index inside the block, [0, s_pad / 32)
@@ -94,100 +94,122 @@ struct ScatterRound {
   unsigned char tb[8];         // per warp: staged slot of the column group J >= I
   unsigned char kmask[8];      // per warp: k-steps of a chunk it multiplies (bit 0 / bit 1)
 };
-static_assert(sizeof(ScatterRound) == 40, "ScatterRound layout");
+static_assert(sizeof(ScatterRound) == 36, "ScatterRound layout");
 
+// ------------------------------------------------------------------------------------------------------------
+// K4: persistent scatter.  grid <= 2 x SMs; blocks are taken from `order` through the atomic `counter`.
+// ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(scat::THREADS, 2)
-k_scatter(PlanView plan, int nbf, const ScatterRound* __restrict__ rounds, const int* __restrict__ skip_flag,
-          const double* __restrict__ phi_buf, double* __restrict__ W) {
+k_vmat(PlanView plan, int nbf, const int* __restrict__ order, int nblk, int* __restrict__ counter,
+       const int* __restrict__ skip_flag, const ScatterRound* __restrict__ tpl, const int* __restrict__ tpl_off,
+       const double* __restrict__ phi_buf, double* __restrict__ W) {
   using namespace scat;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* stage_base = reinterpret_cast<double*>(smem_raw);
-  __shared__ ScatterRound rd;
+  __shared__ int s_next;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid < (int)(sizeof(ScatterRound) / sizeof(int)))
-    reinterpret_cast<int*>(&rd)[tid] = reinterpret_cast<const int*>(rounds + blockIdx.x)[tid];
-  __syncthreads();
-  const int q = rd.q;
-  if (skip_flag[q]) return;
-  const int s = plan.s[q];
-  const int sp = plan.s_pad[q];
-  const double* __restrict__ phi = phi_buf + plan.phi_off[q];
-  const double* __restrict__ G = phi + (size_t)sp * BP;  // G lives in the d_x phi slot
-  const int* __restrict__ sig = plan.sig_bf + (size_t)q * plan.nbf_pad;
-  const int nload = rd.ngroups * 64 * 4;  // 16-byte pieces per stage
-  constexpr int NKC = BP / TKP;           // 16 chunks
   const int lr = lane >> 2, lc = lane & 3;
 
-  auto issue = [&](int kc) {
-    if (kc < NKC) {
-      double* st = stage_base + (kc % STAGES) * STAGE_ELEMS;
-      for (int idx = tid; idx < nload; idx += THREADS) {
-        const int row = idx >> 2, c16 = idx & 3;
-        const int grp = row >> 6, r = row & 63;
-        const double* src = ((r & 32) ? G : phi) + (size_t)(rd.group[grp] * 32 + (r & 31)) * BP + kc * TKP + c16 * 2;
-        cp_async16(st + row * STRIDE + c16 * 2, src);
-      }
-    }
-    cp_async_commit();
-  };
-
-  const int sa = rd.ta[warp], sb = rd.tb[warp], kmask = rd.kmask[warp];
-  const bool active = sa != 0xff;
-  double acc[4][4][2];
-#pragma unroll
-  for (int m = 0; m < 4; ++m)
-#pragma unroll
-    for (int nn = 0; nn < 4; ++nn) acc[m][nn][0] = acc[m][nn][1] = 0.0;
-  issue(0);
-  issue(1);
-  for (int kc = 0; kc < NKC; ++kc) {
-    cp_async_wait<STAGES - 2>();
+  for (;;) {
+    __syncthreads();  // the ring of the previous block is no longer read
+    if (tid == 0) s_next = atomicAdd(counter, 1);
     __syncthreads();
-    issue(kc + STAGES - 1);
-    if (active) {
-      const double* st = stage_base + (kc % STAGES) * STAGE_ELEMS;
-      const double* sI = st + sa * GROUP_ELEMS;  // phi_I rows 0..31, G_I rows 32..63
-      const double* sJ = st + sb * GROUP_ELEMS;
-#pragma unroll
-      for (int ks = 0; ks < TKP / 4; ++ks) {
-        if (!((kmask >> ks) & 1)) continue;
-        double a1[4], a2[4], b1[4], b2[4];
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          const int o = (m * 8 + lr) * STRIDE + ks * 4 + lc;
-          a1[m] = sI[o];
-          a2[m] = sI[o + 32 * STRIDE];
-          b2[m] = sJ[o];
-          b1[m] = sJ[o + 32 * STRIDE];
+    const int qi = s_next;
+    if (qi >= nblk) break;
+    const int q = order[qi];
+    if (skip_flag[q]) continue;
+    const int s = plan.s[q];
+    const int sp = plan.s_pad[q];
+    const size_t comp_stride = (size_t)sp * BP;
+    const double* __restrict__ tile = phi_buf + plan.phi_off[q];
+
+    // ---- 2. rounds of warp tiles
+    const double* __restrict__ phi = tile;
+    const double* __restrict__ G = tile + comp_stride;  // G lives in the d_x phi slot
+    const int* __restrict__ sig = plan.sig_bf + (size_t)q * plan.nbf_pad;
+    const int n32 = sp >> 5;
+    const ScatterRound* __restrict__ rounds = tpl + tpl_off[n32];
+    const int nr = tpl_off[n32 + 1] - tpl_off[n32];
+    const int total = nr * NKC;
+
+    auto issue = [&](int gi) {
+      if (gi < total) {
+        const int r = gi / NKC, kc = gi - r * NKC;
+        const ScatterRound* rd = rounds + r;
+        const int nload = rd->ngroups * 64 * 4;  // 16-byte pieces per stage
+        double* st = stage_base + (gi % STAGES) * STAGE_ELEMS;
+        for (int idx = tid; idx < nload; idx += THREADS) {
+          const int row = idx >> 2, c16 = idx & 3;
+          const int grp = row >> 6, rr = row & 63;
+          const double* src = ((rr & 32) ? G : phi) + (size_t)(rd->group[grp] * 32 + (rr & 31)) * BP + kc * TKP + c16 * 2;
+          cp_async16(st + row * STRIDE + c16 * 2, src);
         }
+      }
+      cp_async_commit();
+    };
+
+    double acc[4][4][2];
+    issue(0);
+    issue(1);
+    int gi = 0;
+    for (int r = 0; r < nr; ++r) {
+      const ScatterRound* rd = rounds + r;
+      const int slot_a = rd->ta[warp], slot_b = rd->tb[warp], kmask = rd->kmask[warp];
+      const bool active = slot_a != 0xff;
 #pragma unroll
-        for (int m = 0; m < 4; ++m)
+      for (int m = 0; m < 4; ++m)
 #pragma unroll
-          for (int nn = 0; nn < 4; ++nn) {
-            dmma884(acc[m][nn][0], acc[m][nn][1], a1[m], b1[nn]);
-            dmma884(acc[m][nn][0], acc[m][nn][1], a2[m], b2[nn]);
+        for (int nn = 0; nn < 4; ++nn) acc[m][nn][0] = acc[m][nn][1] = 0.0;
+      for (int kc = 0; kc < NKC; ++kc, ++gi) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        issue(gi + STAGES - 1);
+        if (active) {
+          const double* st = stage_base + (gi % STAGES) * STAGE_ELEMS;
+          const double* sI = st + slot_a * GROUP_ELEMS;  // phi_I rows 0..31, G_I rows 32..63
+          const double* sJ = st + slot_b * GROUP_ELEMS;
+#pragma unroll
+          for (int ks = 0; ks < TKP / 4; ++ks) {
+            if (!((kmask >> ks) & 1)) continue;
+            double a1[4], a2[4], b1[4], b2[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              const int o = (m * 8 + lr) * STRIDE + ks * 4 + lc;
+              a1[m] = sI[o];
+              a2[m] = sI[o + 32 * STRIDE];
+              b2[m] = sJ[o];
+              b1[m] = sJ[o + 32 * STRIDE];
+            }
+#pragma unroll
+            for (int m = 0; m < 4; ++m)
+#pragma unroll
+              for (int nn = 0; nn < 4; ++nn) {
+                dmma884(acc[m][nn][0], acc[m][nn][1], a1[m], b1[nn]);
+                dmma884(acc[m][nn][0], acc[m][nn][1], a2[m], b2[nn]);
+              }
+          }
+        }
+      }
+      if (active) {
+        // V += Proj V_s Proj^T (:301), upper triangle (compact i <= j <=> global sig[i] <= sig[j])
+        const int i0 = rd->group[slot_a] * 32, j0 = rd->group[slot_b] * 32;
+#pragma unroll
+        for (int nn = 0; nn < 4; ++nn)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int j = j0 + nn * 8 + 2 * lc + e;
+            if (j >= s) continue;
+            const size_t col = (size_t)sig[j] * nbf;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              const int i = i0 + m * 8 + lr;
+              if (i <= j) atomicAdd(W + col + sig[i], acc[m][nn][e]);
+            }
           }
       }
     }
-  }
-  cp_async_wait<0>();
-  if (active) {
-    // V += Proj V_s Proj^T (:301), upper triangle (compact i <= j <=> global sig[i] <= sig[j])
-    const int i0 = rd.group[sa] * 32, j0 = rd.group[sb] * 32;
-#pragma unroll
-    for (int nn = 0; nn < 4; ++nn)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int j = j0 + nn * 8 + 2 * lc + e;
-        if (j >= s) continue;
-        const size_t col = (size_t)sig[j] * nbf;
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          const int i = i0 + m * 8 + lr;
-          if (i <= j) atomicAdd(W + col + sig[i], acc[m][nn][e]);
-        }
-      }
+    cp_async_wait<0>();
   }
 }
 

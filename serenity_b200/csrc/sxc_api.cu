@@ -116,7 +116,6 @@ struct Chunk {
   int slot0 = 0, nslots = 0;
   size_t doubles = 0;     // tile buffer size of the chunk
   int order_off = 0;      // offset into Plan::order (sorted slots of this chunk)
-  int item_off = 0, nitems = 0;  // scatter work items
 };
 
 struct Plan {
@@ -124,7 +123,7 @@ struct Plan {
   int nown = 0;
   int nbf_pad = 0;
   int s_pad_max = 0;
-  DevMem block_id, nsig_shell, s, sig_shell, sig_c0, sig_bf, s_pad, phi_off, order, items, skip;
+  DevMem block_id, nsig_shell, s, sig_shell, sig_c0, sig_bf, s_pad, phi_off, order, tpl, tpl_off, skip;
   std::vector<int> h_s, h_s_pad;
   std::vector<Chunk> chunks;
   sxc_stats stats{};
@@ -160,6 +159,10 @@ struct sxc_ctx {
   DevMem dP;      // staged density matrices (host API)
   DevMem dOut;    // staged V | E | N (host API)
   DevMem scratch; // small device scalars
+  DevMem counters; // work-queue heads of the persistent kernels
+  static constexpr int NCOUNTERS = 1024;
+  int counter_next = NCOUNTERS;
+  int num_sms = 148;
   int64_t ws_limit = 0;
   sxc_stats stats{};
   int launches = 0;
@@ -215,7 +218,7 @@ Basis* get_basis(sxc_ctx* ctx, int h) { return (h >= 0 && h < (int)ctx->bases.si
 int set_kernel_attrs(sxc_ctx* ctx) {
   if (ctx->attrs_set) return SXC_OK;
   CU(cudaFuncSetAttribute(k_density, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  CU(cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scat::smem_bytes()));
+  CU(cudaFuncSetAttribute(k_vmat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scat::smem_bytes()));
   ctx->attrs_set = true;
   return SXC_OK;
 }
@@ -466,33 +469,35 @@ int get_plan(sxc_ctx* ctx, int gh, int bh, Plan** out) {
     return fail(ctx, SXC_ERR_UNSUPPORTED, "grid.blocksize != 128 needs the whole grid in one workspace chunk");
   st.nchunks = (int)p.chunks.size();
   std::vector<int> order(std::max(p.nown, 1));
-  std::vector<ScatterRound> items;
-  for (Chunk& c : p.chunks) {
+  for (Chunk& c : p.chunks) {  // work order of a chunk: largest blocks first
     c.order_off = c.slot0;
     std::iota(order.begin() + c.slot0, order.begin() + c.slot0 + c.nslots, c.slot0);
     std::stable_sort(order.begin() + c.slot0, order.begin() + c.slot0 + c.nslots,
                      [&](int a, int bq) { return p.h_s_pad[a] > p.h_s_pad[bq]; });
-    c.item_off = (int)items.size();
-    for (int k = 0; k < c.nslots; ++k) {  // largest blocks first; the rounds of a block stay adjacent (L2 reuse)
-      const int q = order[c.slot0 + k];
-      if (p.h_s[q] == 0) continue;
-      for (ScatterRound r : scatter_schedule(ctx, p.h_s_pad[q] / 32)) {
-        r.q = q;
-        items.push_back(r);
-      }
-    }
-    c.nitems = (int)items.size() - c.item_off;
     st.workspace_bytes = std::max<int64_t>(st.workspace_bytes, (int64_t)(c.doubles * sizeof(double)));
   }
+  // scatter round templates for every s_pad / 32 up to the largest block
+  const int n32max = p.s_pad_max / 32;
+  std::vector<int> tpl_off(n32max + 2, 0);
+  std::vector<ScatterRound> tpl;
+  for (int n32 = 1; n32 <= n32max; ++n32) {
+    tpl_off[n32] = (int)tpl.size();
+    const auto& rs = scatter_schedule(ctx, n32);
+    tpl.insert(tpl.end(), rs.begin(), rs.end());
+  }
+  tpl_off[n32max + 1] = (int)tpl.size();
+  tpl_off[0] = 0;
   CU(p.order.ensure(order.size() * sizeof(int)));
-  CU(p.items.ensure(std::max<size_t>(items.size(), 1) * sizeof(ScatterRound)));
+  CU(p.tpl.ensure(std::max<size_t>(tpl.size(), 1) * sizeof(ScatterRound)));
+  CU(p.tpl_off.ensure(tpl_off.size() * sizeof(int)));
   if (p.nown) {
     CU(cudaMemcpyAsync(p.s_pad.p, p.h_s_pad.data(), p.nown * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(p.phi_off.p, off.data(), p.nown * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(p.order.p, order.data(), p.nown * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   }
-  if (!items.empty())
-    CU(cudaMemcpyAsync(p.items.p, items.data(), items.size() * sizeof(ScatterRound), cudaMemcpyHostToDevice, ctx->stream));
+  if (!tpl.empty())
+    CU(cudaMemcpyAsync(p.tpl.p, tpl.data(), tpl.size() * sizeof(ScatterRound), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(p.tpl_off.p, tpl_off.data(), tpl_off.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   if (dens::smem_bytes(p.s_pad_max) > 227 * 1024 || p.s_pad_max / 32 > 255)
     return fail(ctx, SXC_ERR_UNSUPPORTED, "more than %d significant functions in one block", p.s_pad_max);
@@ -564,9 +569,19 @@ int phase_functional(sxc_ctx* ctx, const Grid& g, const Plan& p, const Chunk& c,
   return SXC_OK;
 }
 
+int next_counter(sxc_ctx* ctx, int** out) {
+  if (ctx->counter_next >= sxc_ctx::NCOUNTERS) {  // recycle the slots (one per persistent launch)
+    CU(cudaMemsetAsync(ctx->counters.p, 0, sxc_ctx::NCOUNTERS * sizeof(int), ctx->stream));
+    ctx->counter_next = 0;
+  }
+  *out = ctx->counters.as<int>() + ctx->counter_next++;
+  return SXC_OK;
+}
+
 int phase_scatter(sxc_ctx* ctx, const Grid& g, const Basis& b, const Plan& p, const Chunk& c, bool gga,
                   double block_ave_thr, const double* pot4, double* dW) {
   const long N = g.npts;
+  if (c.nslots == 0) return SXC_OK;
   {
     PhaseTimer t(ctx, SXC_T_FORM_G);
     k_form_g<<<c.nslots, 256, 0, ctx->stream>>>(g.view(), p.view(), p.order.as<int>() + c.order_off, block_ave_thr, pot4,
@@ -574,12 +589,14 @@ int phase_scatter(sxc_ctx* ctx, const Grid& g, const Basis& b, const Plan& p, co
                                                 gga ? pot4 + 3 * N : nullptr, ctx->phi.as<double>(), p.skip.as<int>());
     LAUNCH_CHECK();
   }
-  if (c.nitems > 0) {
-    PhaseTimer t(ctx, SXC_T_SCATTER);
-    k_scatter<<<c.nitems, scat::THREADS, scat::smem_bytes(), ctx->stream>>>(
-        p.view(), b.nbf, p.items.as<ScatterRound>() + c.item_off, p.skip.as<int>(), ctx->phi.as<double>(), dW);
-    LAUNCH_CHECK();
-  }
+  int* counter = nullptr;
+  TRY(next_counter(ctx, &counter));
+  PhaseTimer t(ctx, SXC_T_SCATTER);
+  const int grid = std::min(c.nslots, 2 * ctx->num_sms);
+  k_vmat<<<grid, scat::THREADS, scat::smem_bytes(), ctx->stream>>>(
+      p.view(), b.nbf, p.order.as<int>() + c.order_off, c.nslots, counter, p.skip.as<int>(), p.tpl.as<ScatterRound>(),
+      p.tpl_off.as<int>(), ctx->phi.as<double>(), dW);
+  LAUNCH_CHECK();
   return SXC_OK;
 }
 
@@ -773,6 +790,11 @@ int sxc_create(sxc_ctx** out, int device) {
   if (prop.major < 10) return SXC_ERR_UNSUPPORTED;  // sm_100a code only
   auto* ctx = new sxc_ctx();
   ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  if (ctx->counters.ensure(sxc_ctx::NCOUNTERS * sizeof(int)) != cudaSuccess) {
+    delete ctx;
+    return SXC_ERR_NOMEM;
+  }
   if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
     return SXC_ERR_CUDA;
@@ -793,6 +815,7 @@ void sxc_destroy(sxc_ctx* ctx) {
   ctx->dP.release();
   ctx->dOut.release();
   ctx->scratch.release();
+  ctx->counters.release();
   for (auto& st : ctx->stamps) {
     cudaEventDestroy(st.a);
     cudaEventDestroy(st.b);
