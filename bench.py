@@ -218,6 +218,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL writes its version / debug lines to stdout; keep stdout for the ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug.%h.%p")
         dist.init_process_group("nccl", device_id=dev)
 
     cfg, ids, mix = workload(args.workload)

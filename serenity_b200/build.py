@@ -44,8 +44,20 @@ def build_inputs_helper(force=False):
     return out
 
 
+def build_host_test(force=False):
+    """C++ adapter (serenity_b200/host) + its driver, linked against the C-ABI library."""
+    src = os.path.join(ROOT, "tests", "cpp", "host_adapter_test.cpp")
+    hdr = os.path.join(HERE, "host", "serenity_xc_adapter.h")
+    out = os.path.join(ROOT, "tests", "cpp", "host_adapter_test")
+    lib = os.path.join(HERE, "libserenity_xc_b200.so")
+    if force or _newer(out, [src, hdr, lib]):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++14", "-Wall", "-Wextra", "-o", out, src, "-L" + HERE,
+                               "-lserenity_xc_b200", "-Wl,-rpath,$ORIGIN/../../serenity_b200"])
+    return out
+
+
 def build_all(force=False, verbose=False):
-    return [build_cuda(force, verbose), build_inputs_helper(force)]
+    return [build_cuda(force, verbose), build_inputs_helper(force), build_host_test(force)]
 
 
 if __name__ == "__main__":

@@ -1,0 +1,311 @@
+// serenity_xc_adapter.h - C++ host side above the C ABI: drop-in bodies for Serenity's FuncPotential and
+// NAddFuncPotential with the reference's class names, constructor arguments, lazy-evaluation and error behaviour.
+//
+// Reference interfaces mirrored (paths relative to /root/reference/src):
+//   Potential<SCFMode>            potentials/Potential.h:43-86        getMatrix / getEnergy / getGeomGradients
+//   FuncPotential<SCFMode>        potentials/FuncPotential.h:47-147   (getMatrix: FuncPotential.cpp:74-111)
+//   NAddFuncPotential<SCFMode>    potentials/NAddFuncPotential.h:118-155 (getMatrix: NAddFuncPotential.cpp:192-300)
+//   NotifyingClass / ObjectSensitiveClass   notification/ (lazy invalidation: notify() drops the cached potential)
+//   SerenityError                 misc/SerenityError.h:36
+// Inside Serenity the light stand-ins below (Matrix, GridController, BasisController, DensityMatrixController,
+// Functional) are the program's own classes; INTEGRATION.md shows the five call sites that change.  Header-only,
+// C++14, no dependency besides include/serenity_xc_b200.h and the shared library.
+#ifndef SERENITY_XC_ADAPTER_H
+#define SERENITY_XC_ADAPTER_H
+
+#include <algorithm>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/serenity_xc_b200.h"
+
+namespace Serenity {
+
+class SerenityError : public std::runtime_error {
+ public:
+  explicit SerenityError(const std::string& msg) : std::runtime_error(msg) {}
+};
+
+namespace Options {
+enum class SCF_MODES { RESTRICTED = 0, UNRESTRICTED = 1 };
+}
+
+// Column-major dense matrix with Eigen::MatrixXd's memory layout (data()[row + rows * col]).
+struct Matrix {
+  int nrows = 0, ncols = 0;
+  std::vector<double> values;
+  Matrix() = default;
+  Matrix(int r, int c) : nrows(r), ncols(c), values((size_t)r * c, 0.0) {}
+  int rows() const { return nrows; }
+  int cols() const { return ncols; }
+  double* data() { return values.data(); }
+  const double* data() const { return values.data(); }
+  double& operator()(int i, int j) { return values[(size_t)i + (size_t)nrows * j]; }
+  double operator()(int i, int j) const { return values[(size_t)i + (size_t)nrows * j]; }
+};
+using FockMatrix = Matrix;     // data/matrices/FockMatrix.h
+using DensityMatrix = Matrix;  // data/matrices/DensityMatrix.h (RESTRICTED: total density, occupation 2)
+
+// notification/ObjectSensitiveClass.h, NotifyingClass.h
+class ObjectSensitive {
+ public:
+  virtual ~ObjectSensitive() = default;
+  virtual void notify() = 0;
+};
+class Notifying {
+ public:
+  void addSensitiveObject(std::weak_ptr<ObjectSensitive> o) { _sensitive.push_back(std::move(o)); }
+
+ protected:
+  void notifyObjects() {
+    for (auto& w : _sensitive)
+      if (auto s = w.lock()) s->notify();
+  }
+
+ private:
+  std::vector<std::weak_ptr<ObjectSensitive>> _sensitive;
+};
+
+namespace B200 {
+
+// One device context per process and GPU (sxc_create); shared by all potentials of the process.
+class XCDevice {
+ public:
+  explicit XCDevice(int device = 0) {
+    const int rc = sxc_create(&_ctx, device);
+    if (rc != SXC_OK)
+      throw SerenityError("serenity_xc_b200: no usable CUDA device " + std::to_string(device) + " (status " +
+                          std::to_string(rc) + "); the XC build has no CPU fallback");
+  }
+  ~XCDevice() { sxc_destroy(_ctx); }
+  XCDevice(const XCDevice&) = delete;
+  XCDevice& operator=(const XCDevice&) = delete;
+  sxc_ctx* get() const { return _ctx; }
+  void check(int rc) const {
+    if (rc != SXC_OK) throw SerenityError(std::string("serenity_xc_b200: ") + sxc_last_error(_ctx));
+  }
+
+ private:
+  sxc_ctx* _ctx = nullptr;
+};
+
+}  // namespace B200
+
+// grid/GridController.h: 3 x N points (Eigen::Matrix3Xd, xyz interleaved) + N weights; uploads once per device.
+class GridController : public Notifying {
+ public:
+  GridController(std::vector<double> xyz, std::vector<double> weights, int blocksize = 128)
+    : _xyz(std::move(xyz)), _w(std::move(weights)), _blocksize(blocksize) {}
+  const std::vector<double>& getGridPoints() const { return _xyz; }
+  const std::vector<double>& getWeights() const { return _w; }
+  unsigned int getNGridPoints() const { return (unsigned int)_w.size(); }
+  int handle(const B200::XCDevice& dev) {  // lazily uploaded (RememberingFactory-style key: this object)
+    if (_handle < 0) dev.check(sxc_set_grid(dev.get(), (int64_t)_w.size(), _xyz.data(), _w.data(), _blocksize, &_handle));
+    return _handle;
+  }
+
+ private:
+  std::vector<double> _xyz, _w;
+  int _blocksize;
+  int _handle = -1;
+};
+
+// basis/BasisController.h + basis/Shell.h: what BasisFunctionOnGridController reads from the shells.
+struct ShellTable {
+  std::vector<int> l, pure, nprim, firstBf;          // per shell (firstBf = extendedIndex)
+  std::vector<double> centre, alpha, coeff, normfac;  // 3 per shell | per primitive (renormalised) | per function
+};
+class BasisController {
+ public:
+  BasisController(ShellTable t, int nBasisFunctions, double radialThreshold = 1e-9)
+    : _t(std::move(t)), _nbf(nBasisFunctions), _thr(radialThreshold) {}
+  unsigned int getNBasisFunctions() const { return (unsigned int)_nbf; }
+  int handle(const B200::XCDevice& dev) {
+    if (_handle < 0)
+      dev.check(sxc_add_basis(dev.get(), (int)_t.l.size(), _t.l.data(), _t.pure.data(), _t.nprim.data(), _t.firstBf.data(),
+                              _t.centre.data(), _t.alpha.data(), _t.coeff.data(), _t.normfac.data(), _thr, &_handle));
+    return _handle;
+  }
+
+ private:
+  ShellTable _t;
+  int _nbf;
+  double _thr;
+  int _handle = -1;
+};
+
+// data/matrices/DensityMatrixController.h: owns P, notifies dependants when it changes.
+template<Options::SCF_MODES SCFMode>
+class DensityMatrixController : public Notifying {
+ public:
+  DensityMatrixController(std::shared_ptr<BasisController> basis, DensityMatrix P) : _basis(std::move(basis)), _P(std::move(P)) {}
+  const DensityMatrix& getDensityMatrix() const { return _P; }
+  void setDensityMatrix(DensityMatrix P) {
+    _P = std::move(P);
+    notifyObjects();
+  }
+  std::shared_ptr<BasisController> getBasisController() const { return _basis; }
+
+ private:
+  std::shared_ptr<BasisController> _basis;
+  DensityMatrix _P;
+};
+
+// dft/Functional.h: basic functionals (BASIC_FUNCTIONALS enum values) and mixing factors
+struct Functional {
+  std::vector<int> basicFunctionals;
+  std::vector<double> mixingFactors;
+};
+
+// potentials/Potential.h:43-86
+template<Options::SCF_MODES SCFMode>
+class Potential {
+ public:
+  virtual ~Potential() = default;
+  virtual FockMatrix& getMatrix() = 0;
+  virtual double getEnergy(const DensityMatrix& P) = 0;
+  virtual Matrix getGeomGradients() = 0;
+};
+
+namespace detail {
+inline int functionalHandle(const B200::XCDevice& dev, const Functional& f) {
+  int h = -1;
+  dev.check(sxc_set_functional(dev.get(), (int)f.basicFunctionals.size(), f.basicFunctionals.data(), f.mixingFactors.data(), &h));
+  return h;
+}
+template<Options::SCF_MODES SCFMode>
+constexpr int nspin() {
+  return SCFMode == Options::SCF_MODES::RESTRICTED ? 1 : 2;
+}
+}  // namespace detail
+
+// potentials/FuncPotential.h:47-147.  The `system` argument of the reference only supplies settings
+// (grid.blockAveThreshold); it is passed here as that number.
+template<Options::SCF_MODES SCFMode>
+class FuncPotential : public Potential<SCFMode>, public ObjectSensitive {
+ public:
+  FuncPotential(std::shared_ptr<B200::XCDevice> device, std::shared_ptr<DensityMatrixController<SCFMode>> dMat,
+                std::shared_ptr<GridController> grid, Functional functional, double blockAveThreshold = 1e-11)
+    : _dev(std::move(device)), _dMatController(std::move(dMat)), _grid(std::move(grid)), _functional(std::move(functional)),
+      _thr(blockAveThreshold), _func(detail::functionalHandle(*_dev, _functional)) {}
+
+  // call once after make_shared: registers for lazy invalidation (FuncPotential.cpp:56-63)
+  void registerSensitivity(const std::shared_ptr<FuncPotential>& self) {
+    _dMatController->addSensitiveObject(self);
+    _grid->addSensitiveObject(self);
+  }
+
+  FockMatrix& getMatrix() override final {  // FuncPotential.cpp:74-111
+    if (!_potential) {
+      const int nb = (int)_dMatController->getBasisController()->getNBasisFunctions();
+      auto V = std::make_unique<FockMatrix>(nb, nb * detail::nspin<SCFMode>());
+      double nel = 0.0;
+      _dev->check(sxc_build_xc(_dev->get(), _grid->handle(*_dev), _dMatController->getBasisController()->handle(*_dev), _func,
+                               detail::nspin<SCFMode>(), _dMatController->getDensityMatrix().data(), _thr, V->data(), &_energy,
+                               &nel));
+      _nElectronsOnGrid = nel;
+      _potential = std::move(V);
+    }
+    return *_potential;
+  }
+  double getEnergy(const DensityMatrix& /*P*/) override final {  // FuncPotential.cpp:67-71: cached, P is ignored
+    if (!_potential) getMatrix();
+    return _energy;
+  }
+  Matrix getGeomGradients() override final {
+    throw SerenityError("FuncPotential::getGeomGradients is not part of the B200 hot path (SURVEY.md row f-3)");
+  }
+  void notify() override final { _potential = nullptr; }  // FuncPotential.h:107-109
+  Functional getFunctional() { return _functional; }
+  std::shared_ptr<GridController> getGridController() { return _grid; }
+  double getNElectronsOnGrid() const { return _nElectronsOnGrid; }
+
+ private:
+  std::shared_ptr<B200::XCDevice> _dev;
+  std::shared_ptr<DensityMatrixController<SCFMode>> _dMatController;
+  std::shared_ptr<GridController> _grid;
+  Functional _functional;
+  double _thr;
+  int _func;
+  std::unique_ptr<FockMatrix> _potential;
+  double _energy = 0.0;
+  double _nElectronsOnGrid = 0.0;
+};
+
+// potentials/NAddFuncPotential.h:118-155 (first constructor; exact-exchange and solvation parts are ERI work and stay
+// with the reference's ExchangeInteractionPotential).
+template<Options::SCF_MODES SCFMode>
+class NAddFuncPotential : public Potential<SCFMode>, public ObjectSensitive {
+ public:
+  NAddFuncPotential(std::shared_ptr<B200::XCDevice> device, std::shared_ptr<DensityMatrixController<SCFMode>> activeDMat,
+                    std::vector<std::shared_ptr<DensityMatrixController<SCFMode>>> envDMats,
+                    std::shared_ptr<GridController> grid, Functional functional, double blockAveThreshold = 1e-11)
+    : _dev(std::move(device)), _act(std::move(activeDMat)), _env(std::move(envDMats)), _grid(std::move(grid)),
+      _functional(std::move(functional)), _thr(blockAveThreshold), _func(detail::functionalHandle(*_dev, _functional)) {}
+
+  struct EnvWatcher : ObjectSensitive {  // a changed environment density invalidates the cached rho_env on the grid
+    explicit EnvWatcher(NAddFuncPotential* o) : owner(o) {}
+    void notify() override {
+      owner->_potential = nullptr;
+      owner->_envFrozen = false;
+    }
+    NAddFuncPotential* owner;
+  };
+  void registerSensitivity(const std::shared_ptr<NAddFuncPotential>& self) {
+    _act->addSensitiveObject(self);
+    _grid->addSensitiveObject(self);
+    _watcher = std::make_shared<EnvWatcher>(this);
+    for (auto& e : _env) e->addSensitiveObject(_watcher);
+  }
+
+  FockMatrix& getMatrix() override final {  // NAddFuncPotential.cpp:192-300
+    if (!_potential) {
+      const int nb = (int)_act->getBasisController()->getNBasisFunctions();
+      auto V = std::make_unique<FockMatrix>(nb, nb * detail::nspin<SCFMode>());
+      std::vector<int> be;
+      std::vector<const double*> pe;
+      for (auto& e : _env) {
+        be.push_back(e->getBasisController()->handle(*_dev));
+        pe.push_back(e->getDensityMatrix().data());
+      }
+      _energyParts.assign(2 + _env.size(), 0.0);
+      _dev->check(sxc_build_nadd(_dev->get(), _grid->handle(*_dev), _func, detail::nspin<SCFMode>(),
+                                 _act->getBasisController()->handle(*_dev), _act->getDensityMatrix().data(), (int)_env.size(),
+                                 be.data(), pe.data(), _envFrozen ? 1 : 0, _thr, V->data(), _energyParts.data()));
+      _energy = _energyParts[0] - _energyParts[1];  // E[rho_tot] - E[rho_act] - sum_env E[rho_env], :249, :282-286
+      for (size_t i = 2; i < _energyParts.size(); ++i) _energy -= _energyParts[i];
+      _envFrozen = true;
+      _potential = std::move(V);
+    }
+    return *_potential;
+  }
+  double getEnergy(const DensityMatrix& /*P*/) override final {
+    if (!_potential) getMatrix();
+    return _energy;
+  }
+  Matrix getGeomGradients() override final {
+    throw SerenityError("NAddFuncPotential::getGeomGradients is not part of the B200 hot path (SURVEY.md row f-3)");
+  }
+  void notify() override final { _potential = nullptr; }
+  const std::vector<double>& getEnergyParts() const { return _energyParts; }
+
+ private:
+  std::shared_ptr<B200::XCDevice> _dev;
+  std::shared_ptr<DensityMatrixController<SCFMode>> _act;
+  std::vector<std::shared_ptr<DensityMatrixController<SCFMode>>> _env;
+  std::shared_ptr<GridController> _grid;
+  Functional _functional;
+  double _thr;
+  int _func;
+  std::shared_ptr<EnvWatcher> _watcher;
+  std::unique_ptr<FockMatrix> _potential;
+  std::vector<double> _energyParts;
+  double _energy = 0.0;
+  bool _envFrozen = false;
+};
+
+}  // namespace Serenity
+#endif

@@ -1,0 +1,115 @@
+// Drives the C++ adapter (serenity_b200/host/serenity_xc_adapter.h) like Serenity's potential tests drive the reference
+// classes (potentials/FuncPotential_test.cpp, NAddFuncPotential_test.cpp): build, cached second call, density change ->
+// notify -> rebuild.  Inputs come from a flat binary file written by tests/test_cpp_host.py; results go back the same way.
+//   host_adapter_test --expect-no-device          exit 0 iff constructing the device throws SerenityError
+//   host_adapter_test <in.bin> <out.bin>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+
+#include "../../serenity_b200/host/serenity_xc_adapter.h"
+
+using namespace Serenity;
+using R = Options::SCF_MODES;
+
+template <class T>
+static std::vector<T> rd(std::ifstream& f) {
+  int64_t n = 0;
+  f.read(reinterpret_cast<char*>(&n), 8);
+  std::vector<T> v((size_t)n);
+  f.read(reinterpret_cast<char*>(v.data()), n * sizeof(T));
+  return v;
+}
+static void wr(std::ofstream& f, const double* p, int64_t n) {
+  f.write(reinterpret_cast<const char*>(&n), 8);
+  f.write(reinterpret_cast<const char*>(p), n * 8);
+}
+static std::shared_ptr<BasisController> readBasis(std::ifstream& f) {
+  ShellTable t;
+  t.l = rd<int>(f);
+  t.pure = rd<int>(f);
+  t.nprim = rd<int>(f);
+  t.firstBf = rd<int>(f);
+  t.centre = rd<double>(f);
+  t.alpha = rd<double>(f);
+  t.coeff = rd<double>(f);
+  t.normfac = rd<double>(f);
+  const int nbf = (int)t.normfac.size();
+  return std::make_shared<BasisController>(std::move(t), nbf);
+}
+static DensityMatrix readMatrix(std::ifstream& f, int nb) {
+  DensityMatrix P(nb, nb);
+  P.values = rd<double>(f);
+  return P;
+}
+
+int main(int argc, char** argv) {
+  if (argc == 2 && std::strcmp(argv[1], "--expect-no-device") == 0) {
+    try {
+      B200::XCDevice dev(0);
+    } catch (const SerenityError& e) {
+      std::cout << "SerenityError: " << e.what() << "\n";
+      return 0;
+    }
+    return 1;
+  }
+  if (argc != 3) return 2;
+  try {
+    std::ifstream in(argv[1], std::ios::binary);
+    std::ofstream out(argv[2], std::ios::binary);
+    auto dev = std::make_shared<B200::XCDevice>(0);
+    auto grid = std::make_shared<GridController>(rd<double>(in), rd<double>(in));
+    Functional xc{rd<int>(in), rd<double>(in)};
+    Functional kin{rd<int>(in), rd<double>(in)};
+    auto basisA = readBasis(in);
+    auto basisB = readBasis(in);
+    const int nA = (int)basisA->getNBasisFunctions(), nB = (int)basisB->getNBasisFunctions();
+    auto dA = std::make_shared<DensityMatrixController<R::RESTRICTED>>(basisA, readMatrix(in, nA));
+    auto dB = std::make_shared<DensityMatrixController<R::RESTRICTED>>(basisB, readMatrix(in, nB));
+    DensityMatrix PA2 = readMatrix(in, nA);
+
+    // KS-DFT potential of subsystem A on the common grid
+    auto pot = std::make_shared<FuncPotential<R::RESTRICTED>>(dev, dA, grid, xc);
+    pot->registerSensitivity(pot);
+    FockMatrix& V1 = pot->getMatrix();
+    if (&pot->getMatrix() != &V1) throw SerenityError("getMatrix() must return the cached matrix until notify()");
+    wr(out, V1.data(), (int64_t)nA * nA);
+    const double E1 = pot->getEnergy(dA->getDensityMatrix());
+    wr(out, &E1, 1);
+    // non-additive potentials (freeze-and-thaw: XC and kinetic objects, NAddFuncPotential.cpp:192)
+    auto naddXC = std::make_shared<NAddFuncPotential<R::RESTRICTED>>(
+        dev, dA, std::vector<std::shared_ptr<DensityMatrixController<R::RESTRICTED>>>{dB}, grid, xc);
+    naddXC->registerSensitivity(naddXC);
+    auto naddKin = std::make_shared<NAddFuncPotential<R::RESTRICTED>>(
+        dev, dA, std::vector<std::shared_ptr<DensityMatrixController<R::RESTRICTED>>>{dB}, grid, kin);
+    naddKin->registerSensitivity(naddKin);
+    wr(out, naddXC->getMatrix().data(), (int64_t)nA * nA);
+    double e = naddXC->getEnergy(dA->getDensityMatrix());
+    wr(out, &e, 1);
+    wr(out, naddKin->getMatrix().data(), (int64_t)nA * nA);
+    e = naddKin->getEnergy(dA->getDensityMatrix());
+    wr(out, &e, 1);
+    // new active density: every potential that depends on it is invalidated and rebuilt (environment stays frozen)
+    dA->setDensityMatrix(PA2);
+    wr(out, pot->getMatrix().data(), (int64_t)nA * nA);
+    e = pot->getEnergy(PA2);
+    wr(out, &e, 1);
+    wr(out, naddXC->getMatrix().data(), (int64_t)nA * nA);
+    e = naddXC->getEnergy(PA2);
+    wr(out, &e, 1);
+    // error convention: SerenityError, as the reference throws
+    bool threw = false;
+    try {
+      pot->getGeomGradients();
+    } catch (const SerenityError&) {
+      threw = true;
+    }
+    if (!threw) throw SerenityError("getGeomGradients must throw");
+  } catch (const std::exception& e) {
+    std::cerr << "host_adapter_test failed: " << e.what() << "\n";
+    return 1;
+  }
+  return 0;
+}

@@ -1,0 +1,86 @@
+"""The C++ host adapter (serenity_b200/host/serenity_xc_adapter.h) driven like the reference's potential tests
+(potentials/FuncPotential_test.cpp, NAddFuncPotential_test.cpp), checked against the CPU oracle."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "cpp", "host_adapter_test")
+
+
+def _exe():
+    if not os.path.exists(EXE):
+        from serenity_b200 import build
+        build.build_host_test()
+    return EXE
+
+
+def test_adapter_fails_loudly_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    r = subprocess.run([_exe(), "--expect-no-device"], capture_output=True, text=True)
+    assert r.returncode == 0 and "SerenityError" in r.stdout and "no CPU fallback" in r.stdout
+
+
+def _w(f, a, dtype):
+    a = np.ascontiguousarray(a, dtype=dtype).reshape(-1)
+    f.write(struct.pack("<q", a.size))
+    f.write(a.tobytes())
+
+
+def _basis(f, t):
+    for a, dt in ((t.l, np.int32), (t.pure, np.int32), (t.nprim, np.int32), (t.first_bf, np.int32), (t.centre, np.float64),
+                  (t.alpha, np.float64), (t.coeff, np.float64), (t.normfac, np.float64)):
+        _w(f, a, dt)
+
+
+def _r(f, shape=None):
+    n = struct.unpack("<q", f.read(8))[0]
+    a = np.frombuffer(f.read(8 * n), dtype=np.float64)
+    return a.reshape(shape, order="F") if shape else float(a[0])
+
+
+@pytest.mark.gpu
+def test_cpp_potentials_match_oracle(tmp_path):
+    from oracle import pyoracle as orc
+    from serenity_b200.inputs import make_config
+    from serenity_b200.inputs.configs import FUNCTIONALS
+    cfg = make_config("fde_dimer", 2)
+    act, env = cfg.subsystems
+    xc, kin = FUNCTIONALS["PBE"], FUNCTIONALS["PW91K"]
+    PA2 = np.asfortranarray(act.P * 1.05)
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(fin, "wb") as f:
+        _w(f, cfg.xyz, np.float64)
+        _w(f, cfg.w, np.float64)
+        for ids, mix in (xc, kin):
+            _w(f, ids, np.int32)
+            _w(f, mix, np.float64)
+        _basis(f, act.basis)
+        _basis(f, env.basis)
+        _w(f, act.P.reshape(-1, order="F"), np.float64)
+        _w(f, env.P.reshape(-1, order="F"), np.float64)
+        _w(f, PA2.reshape(-1, order="F"), np.float64)
+    r = subprocess.run([_exe(), fin, fout], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    nA = act.basis.nbf
+    with open(fout, "rb") as f:
+        got = [(_r(f, (nA, nA)), _r(f)) for _ in range(5)]
+    og = orc.Grid(cfg.xyz, cfg.w, 128)
+    bA, bE = orc.Basis(act.basis), orc.Basis(env.basis)
+
+    def ks(P):
+        V, E, _, _ = orc.build_xc(bA, og, orc.Functional(*xc), P)
+        return V, E
+
+    def nadd(P, fn):
+        V, E, _ = orc.build_nadd(bA, P, [(bE, env.P)], og, orc.Functional(*fn))
+        return V, E
+
+    want = [ks(act.P), nadd(act.P, xc), nadd(act.P, kin), ks(PA2), nadd(PA2, xc)]
+    for (V, E), (Vr, Er) in zip(got, want):
+        assert np.abs(V - Vr).max() <= 1e-8 and abs(E - Er) <= 1e-9
