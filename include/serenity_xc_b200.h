@@ -37,7 +37,7 @@ typedef enum {
   SXC_ERR_INVALID = -1,     /* bad argument / handle */
   SXC_ERR_CUDA = -2,        /* CUDA runtime error (text in sxc_last_error) */
   SXC_ERR_NOMEM = -3,       /* device or host allocation failed */
-  SXC_ERR_UNSUPPORTED = -4  /* valid in the reference, not implemented here (e.g. nspin = 2, l > 6) */
+  SXC_ERR_UNSUPPORTED = -4  /* valid in the reference, not implemented here (e.g. l > 6, meta-GGA ids) */
 } sxc_status;
 
 /* supported BASIC_FUNCTIONALS (XCFun aliases: BasicFunctionals.cpp:1663-1790) */
@@ -126,12 +126,15 @@ int sxc_add_basis(sxc_ctx* ctx, int nshell, const int* l, const int* pure, const
 int sxc_set_functional(sxc_ctx* ctx, int ncomp, const int* basic_id, const double* mix, int* func);
 
 /* ---- the hot path -------------------------------------------------------------------------------------- */
-/* FuncPotential::getMatrix + getEnergy (src/potentials/FuncPotential.cpp:67-111): V (nb x nb per spin,
- * overwritten), E = sum_p w_p F_p, nelec = sum_p w_p rho_p.  block_ave_threshold = settings
- * grid.blockAveThreshold (1e-11).  With a shard set, V/E/nelec are this rank's partial sums. */
+/* FuncPotential<SCFMode>::getMatrix + getEnergy (src/potentials/FuncPotential.cpp:67-111).
+ * nspin = 1 (RESTRICTED): P, V nb x nb.  nspin = 2 (UNRESTRICTED): P = {P_alpha, P_beta} and V = {V_alpha, V_beta}
+ * stored back to back (2 nb^2 doubles each, the alpha/beta pair of src/data/SpinPolarizedData.h).
+ * V is overwritten, E = sum_p w_p F_p, nelec = sum_p w_p (rho_alpha + rho_beta).  block_ave_threshold = settings
+ * grid.blockAveThreshold (1e-11), applied per spin as in the reference.  With a shard set, V/E/nelec are this
+ * rank's partial sums. */
 int sxc_build_xc(sxc_ctx* ctx, int grid, int basis, int func, int nspin, const double* P,
                  double block_ave_threshold, double* V, double* E, double* nelec);
-/* same with device-resident P and result: d_VEN holds nb*nb doubles of V followed by E and nelec
+/* same with device-resident P and result: d_VEN holds nspin*nb*nb doubles of V followed by E and nelec
  * (the buffer of the single all-reduce).  Asynchronous on the context's stream. */
 int sxc_build_xc_device(sxc_ctx* ctx, int grid, int basis, int func, int nspin, const double* d_P,
                         double block_ave_threshold, double* d_VEN);
@@ -139,7 +142,8 @@ int sxc_build_xc_device(sxc_ctx* ctx, int grid, int basis, int func, int nspin, 
 /* NAddFuncPotential::getMatrix + getEnergy (src/potentials/NAddFuncPotential.cpp:192-326) with the supersystem
  * density of SupersystemDensityOnGridController::updateData (SupersystemDensityOnGridController.cpp:95-193):
  * V_A = scatter of v[rho_A + sum rho_env] - v[rho_A] in the active basis; E[0] = E[rho_tot], E[1] = E[rho_A],
- * E[2+i] = E[rho_env_i]  (E_nadd = E[0] - E[1] - sum E[2+i]).  env_frozen != 0: environment densities on the
+ * E[2+i] = E[rho_env_i]  (E_nadd = E[0] - E[1] - sum E[2+i]).  nspin = 2: every P / V is an {alpha, beta} pair
+ * stored back to back.  env_frozen != 0: environment densities on the
  * grid and their energies are kept from the previous call with the same handles (they are frozen during one
  * FDE SCF, DensityOnGridFactory.cpp:41-48). */
 int sxc_build_nadd(sxc_ctx* ctx, int grid, int func, int nspin, int basis_act, const double* P_act, int nenv,
@@ -147,7 +151,7 @@ int sxc_build_nadd(sxc_ctx* ctx, int grid, int func, int nspin, int basis_act, c
                    double* V_act, double* E /*[2+nenv]*/);
 int sxc_build_nadd_device(sxc_ctx* ctx, int grid, int func, int nspin, int basis_act, const double* d_P_act,
                           int nenv, const int* basis_env, const double* const* d_P_env, int env_frozen,
-                          double block_ave_threshold, double* d_VE /* nbA*nbA + 2 + nenv */);
+                          double block_ave_threshold, double* d_VE /* nspin*nbA*nbA + 2 + nenv */);
 
 /* ---- stage-level entry points (the reference classes one level below the Potentials) -------------------- */
 /* DensityOnGridCalculator::calcDensityAndGradientOnGrid (DensityOnGridCalculator.cpp:55-65): host outputs [N];
@@ -163,6 +167,11 @@ int sxc_basis_on_grid(sxc_ctx* ctx, int grid, int basis, int block, double* val,
 int sxc_functional_on_grid(sxc_ctx* ctx, int func, int64_t npts, const double* w, const double* rho,
                            const double* gx, const double* gy, const double* gz, double* epuv, double* dFdRho,
                            double* dFdGx, double* dFdGy, double* dFdGz, double* energy);
+/* same, UNRESTRICTED (XCFun.cpp:100-112, XC_A_B_AX_AY_AZ_BX_BY_BZ): dens8 / out8 are [8][npts] with rows
+ * rho_a, grad_a x y z, rho_b, grad_b x y z  ->  dF/drho_a, dF/dgrad_a x y z, dF/drho_b, dF/dgrad_b x y z.
+ * has_grad = 0: the gradient rows are ignored (LDA). */
+int sxc_functional_on_grid_u(sxc_ctx* ctx, int func, int64_t npts, const double* w, const double* dens8, int has_grad,
+                             double* epuv, double* out8, double* energy);
 /* ScalarOperatorToMatrixAdder::addScalarOperatorToMatrix (ScalarOperatorToMatrixAdder.cpp:52-116); gx == NULL
  * selects the LDA variant; the result is ADDED to V as in the reference. */
 int sxc_scalar_to_matrix(sxc_ctx* ctx, int grid, int basis, double block_ave_threshold, const double* v,

@@ -705,3 +705,97 @@ int orc_build_nadd(const orc_basis* bA, const double* PA, int nenv, const orc_ba
   free(nonneg);
   return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * UNRESTRICTED variants: the reference instantiates the same templates with SCFMode = UNRESTRICTED; every
+ * per-spin quantity is a {alpha, beta} pair looped with for_spin (data/SpinPolarizedData.h:1880).
+ * ------------------------------------------------------------------------------------------------ */
+int orc_build_xc_u(const orc_basis* b, const orc_grid* g, const orc_functional* f, double radial_thr,
+                   double block_ave_thr, const double* Pa, const double* Pb, double* Va, double* Vb, double* E,
+                   double* nelec) {
+  const long N = g->npts;
+  const int gga = orc_functional_is_gga(f);
+  double* buf = (double*)malloc(sizeof(double) * 17 * (size_t)N);
+  if (!buf) return -1;
+  double *rho = buf, *grad = rho + 2 * N, *ep = grad + 6 * N, *vr = ep + N, *vg = vr + 2 * N;
+  /* MatrixOperatorToGridTransformer.h:128-146: the same block data is contracted with P_alpha and P_beta */
+  orc_density_on_grid(b, g, radial_thr, Pa, rho, grad, grad + N, grad + 2 * N, NULL, NULL);
+  orc_density_on_grid(b, g, radial_thr, Pb, rho + N, grad + 3 * N, grad + 4 * N, grad + 5 * N, NULL, NULL);
+  *E = orc_functional_on_grid_u(f, N, g->w, rho, gga ? grad : NULL, ep, vr, gga ? vg : NULL);
+  memset(Va, 0, sizeof(double) * (size_t)b->nbf * b->nbf);
+  memset(Vb, 0, sizeof(double) * (size_t)b->nbf * b->nbf);
+  if (f->ncomp > 0) {
+    orc_scalar_to_matrix(b, g, radial_thr, block_ave_thr, vr, gga ? vg : NULL, vg + N, vg + 2 * N, Va);
+    orc_scalar_to_matrix(b, g, radial_thr, block_ave_thr, vr + N, gga ? vg + 3 * N : NULL, vg + 4 * N, vg + 5 * N, Vb);
+  }
+  if (nelec) {
+    double ne = 0.0;
+    for (long p = 0; p < N; ++p) ne += (rho[p] + rho[N + p]) * g->w[p];
+    *nelec = ne;
+  }
+  free(buf);
+  return 0;
+}
+
+int orc_build_nadd_u(const orc_basis* bA, const double* PAa, const double* PAb, int nenv, const orc_basis* const* bE,
+                     const double* const* PEa, const double* const* PEb, const orc_grid* g, const orc_functional* f,
+                     double radial_thr, double block_ave_thr, double* VAa, double* VAb, double* E_nadd, double* E_parts) {
+  const long N = g->npts;
+  const int nblocks = orc_nblocks(g);
+  const int gga = orc_functional_is_gga(f);
+  const int nsub = 1 + nenv;
+  /* per subsystem: rho[2][N] then grad[2][3][N] */
+  double* dens = (double*)malloc(sizeof(double) * 8 * (size_t)N * (size_t)nsub);
+  double* tot = (double*)calloc(8 * (size_t)N, sizeof(double));
+  double* fd = (double*)malloc(sizeof(double) * 18 * (size_t)N);
+  int* nonneg = (int*)malloc(sizeof(int) * (size_t)nblocks * (size_t)nsub);
+  if (!dens || !tot || !fd || !nonneg) return -1;
+  for (int i = 0; i < nsub; ++i) {
+    double* d = dens + 8 * (size_t)N * i;
+    const orc_basis* bb = i == 0 ? bA : bE[i - 1];
+    orc_density_on_grid(bb, g, radial_thr, i == 0 ? PAa : PEa[i - 1], d, d + 2 * N, d + 3 * N, d + 4 * N, NULL,
+                        nonneg + (size_t)nblocks * i);
+    orc_density_on_grid(bb, g, radial_thr, i == 0 ? PAb : PEb[i - 1], d + N, d + 5 * N, d + 6 * N, d + 7 * N, NULL,
+                        nonneg + (size_t)nblocks * i); /* same flags: they depend on the basis only */
+  }
+#pragma omp parallel for schedule(dynamic)
+  for (int blk = 0; blk < nblocks; ++blk) { /* SupersystemDensityOnGridController.cpp:196-307 */
+    const long first = (long)blk * g->blocksize;
+    const int n = block_size(g, blk);
+    for (int i = 0; i < nsub; ++i) {
+      if (!nonneg[(size_t)nblocks * i + blk]) continue;
+      const double* d = dens + 8 * (size_t)N * i;
+      for (int c = 0; c < 8; ++c)
+        for (int p = 0; p < n; ++p) tot[(size_t)c * N + first + p] += d[(size_t)c * N + first + p];
+    }
+  }
+  double *ep = fd, *vr = ep + N, *vg = vr + 2 * N, *ep2 = vg + 6 * N, *vr2 = ep2 + N, *vg2 = vr2 + 2 * N;
+  const double e_tot = orc_functional_on_grid_u(f, N, g->w, tot, gga ? tot + 2 * N : NULL, ep, vr, gga ? vg : NULL);
+  const double e_act = orc_functional_on_grid_u(f, N, g->w, dens, gga ? dens + 2 * N : NULL, ep2, vr2, gga ? vg2 : NULL);
+  for (long p = 0; p < 2 * N; ++p) vr[p] -= vr2[p];
+  if (gga)
+    for (long p = 0; p < 6 * N; ++p) vg[p] -= vg2[p];
+  memset(VAa, 0, sizeof(double) * (size_t)bA->nbf * bA->nbf);
+  memset(VAb, 0, sizeof(double) * (size_t)bA->nbf * bA->nbf);
+  if (f->ncomp > 0) {
+    orc_scalar_to_matrix(bA, g, radial_thr, block_ave_thr, vr, gga ? vg : NULL, vg + N, vg + 2 * N, VAa);
+    orc_scalar_to_matrix(bA, g, radial_thr, block_ave_thr, vr + N, gga ? vg + 3 * N : NULL, vg + 4 * N, vg + 5 * N, VAb);
+  }
+  double e = e_tot - e_act;
+  if (E_parts) {
+    E_parts[0] = e_tot;
+    E_parts[1] = e_act;
+  }
+  for (int i = 0; i < nenv; ++i) {
+    const double* d = dens + 8 * (size_t)N * (i + 1);
+    const double ee = orc_functional_on_grid_u(f, N, g->w, d, gga ? d + 2 * N : NULL, ep2, vr2, gga ? vg2 : NULL);
+    e -= ee;
+    if (E_parts) E_parts[2 + i] = ee;
+  }
+  *E_nadd = e;
+  free(dens);
+  free(tot);
+  free(fd);
+  free(nonneg);
+  return 0;
+}

@@ -123,6 +123,24 @@ int orc_build_nadd(const orc_basis* bA, const double* PA, int nenv, const orc_ba
                    const double* const* PE, const orc_grid* g, const orc_functional* f, double radial_thr,
                    double block_ave_thr, double* VA, double* E_nadd, double* E_parts);
 
+/* ---- UNRESTRICTED (SCFMode = UNRESTRICTED: alpha/beta pairs, data/SpinPolarizedData.h) ------------------------ */
+/* pointwise spin-polarised kernel: F and dF/d(rho_a, rho_b, s_aa, s_ab, s_bb) */
+int orc_basic_functional_u(int id, double ra, double rb, double gaa, double gab, double gbb, double* F, double* d5);
+/* 8a-4 unrestricted branch of XCFun::calcData (XCFun.cpp:100-112, :129-153): rho[2][npts], grad[2][3][npts] (may be
+ * NULL for LDA) -> epuv[npts], dFdRho[2][npts], dFdGrad[2][3][npts].  Block skip only if BOTH spin densities are
+ * below the block threshold (:133-137). */
+double orc_functional_on_grid_u(const orc_functional* f, long npts, const double* w, const double* rho,
+                                const double* grad, double* epuv, double* dFdRho, double* dFdGrad);
+/* 8a-6 FuncPotential<UNRESTRICTED>::getMatrix: P = {P_alpha, P_beta}, V = {V_alpha, V_beta}; the grid -> matrix step
+ * runs per spin with its own block-average test (ScalarOperatorToMatrixAdder.cpp:262-268 inside for_spin). */
+int orc_build_xc_u(const orc_basis* b, const orc_grid* g, const orc_functional* f, double radial_thr,
+                   double block_ave_thr, const double* Pa, const double* Pb, double* Va, double* Vb, double* E,
+                   double* nelec);
+/* 8a-7 NAddFuncPotential<UNRESTRICTED>: E_parts = {E_tot, E_act, E_env...} */
+int orc_build_nadd_u(const orc_basis* bA, const double* PAa, const double* PAb, int nenv, const orc_basis* const* bE,
+                     const double* const* PEa, const double* const* PEb, const orc_grid* g, const orc_functional* f,
+                     double radial_thr, double block_ave_thr, double* VAa, double* VAb, double* E_nadd, double* E_parts);
+
 #ifdef __cplusplus
 }
 #endif

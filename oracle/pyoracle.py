@@ -17,7 +17,7 @@ _LIB = None
 
 def build(force: bool = False) -> str:
     path = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle_functionals.c", "oracle.h", "harmonics_table.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle_functionals.c", "oracle_functionals_u.cpp", "oracle.h", "harmonics_table.h")]
     if force or not os.path.exists(path) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
     return path
@@ -50,6 +50,7 @@ def lib():
             build()
         _LIB = C.CDLL(path)
         _LIB.orc_functional_on_grid.restype = C.c_double
+        _LIB.orc_functional_on_grid_u.restype = C.c_double
         _LIB.orc_nblocks.restype = C.c_int
         _LIB.orc_max_threads.restype = C.c_int
     return _LIB
@@ -183,3 +184,56 @@ def build_nadd(basis_a: Basis, P_a, env, grid: Grid, func: Functional, radial_th
     if rc != 0:
         raise MemoryError("orc_build_nadd failed")
     return V, E.value, parts
+
+
+# ---------------------------------------------------------------------------------------------- UNRESTRICTED
+def basic_functional_u(fid: int, ra: float, rb: float, gaa: float, gab: float, gbb: float):
+    F = C.c_double()
+    d = np.zeros(5)
+    rc = lib().orc_basic_functional_u(int(fid), C.c_double(ra), C.c_double(rb), C.c_double(gaa), C.c_double(gab),
+                                      C.c_double(gbb), C.byref(F), _p(d))
+    if rc != 0:
+        raise ValueError("unsupported functional id %d" % fid)
+    return F.value, d
+
+
+def functional_on_grid_u(func: Functional, w, rho2, grad23=None):
+    """rho2 [2, N]; grad23 [2, 3, N] or None -> E, epuv [N], dFdRho [2, N], dFdGrad [2, 3, N]."""
+    rho2 = np.ascontiguousarray(rho2, dtype=np.float64)
+    N = rho2.shape[1]
+    g = None if grad23 is None else np.ascontiguousarray(grad23, dtype=np.float64)
+    ep, vr, vg = np.zeros(N), np.zeros((2, N)), np.zeros((2, 3, N))
+    e = lib().orc_functional_on_grid_u(C.byref(func.c), C.c_long(N), _p(np.ascontiguousarray(w, dtype=np.float64)),
+                                       _p(rho2), _p(g), _p(ep), _p(vr), _p(vg) if g is not None else None)
+    return float(e), ep, vr, vg
+
+
+def build_xc_u(basis: Basis, grid: Grid, func: Functional, Pa, Pb, radial_thr=1e-9, block_ave_thr=1e-11):
+    Pa, Pb = (np.asfortranarray(p, dtype=np.float64) for p in (Pa, Pb))
+    Va, Vb = (np.zeros((basis.nbf, basis.nbf), order="F") for _ in range(2))
+    E, ne = C.c_double(), C.c_double()
+    rc = lib().orc_build_xc_u(C.byref(basis.c), C.byref(grid.c), C.byref(func.c), C.c_double(radial_thr),
+                              C.c_double(block_ave_thr), _p(Pa), _p(Pb), _p(Va), _p(Vb), C.byref(E), C.byref(ne))
+    if rc != 0:
+        raise MemoryError("orc_build_xc_u failed")
+    return (Va, Vb), E.value, ne.value
+
+
+def build_nadd_u(basis_a: Basis, Pa_pair, env, grid: Grid, func: Functional, radial_thr=1e-9, block_ave_thr=1e-11):
+    """env: list of (Basis, (P_alpha, P_beta))."""
+    PAa, PAb = (np.asfortranarray(p, dtype=np.float64) for p in Pa_pair)
+    Pea = [np.asfortranarray(p[0], dtype=np.float64) for _, p in env]
+    Peb = [np.asfortranarray(p[1], dtype=np.float64) for _, p in env]
+    nenv = len(env)
+    barr = (C.POINTER(_Basis) * max(nenv, 1))(*[C.pointer(b.c) for b, _ in env])
+    pa = (C.c_void_p * max(nenv, 1))(*[p.ctypes.data for p in Pea])
+    pb = (C.c_void_p * max(nenv, 1))(*[p.ctypes.data for p in Peb])
+    Va, Vb = (np.zeros((basis_a.nbf, basis_a.nbf), order="F") for _ in range(2))
+    E = C.c_double()
+    parts = np.zeros(2 + nenv)
+    rc = lib().orc_build_nadd_u(C.byref(basis_a.c), _p(PAa), _p(PAb), nenv, barr, pa, pb, C.byref(grid.c),
+                                C.byref(func.c), C.c_double(radial_thr), C.c_double(block_ave_thr), _p(Va), _p(Vb),
+                                C.byref(E), _p(parts))
+    if rc != 0:
+        raise MemoryError("orc_build_nadd_u failed")
+    return (Va, Vb), E.value, parts

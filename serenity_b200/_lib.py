@@ -15,7 +15,7 @@ SYMBOLS = [
     "sxc_create", "sxc_destroy", "sxc_last_error", "sxc_set_stream", "sxc_set_workspace_limit", "sxc_set_timing", "sxc_set_grid",
     "sxc_set_grid_shard", "sxc_add_basis", "sxc_set_functional", "sxc_build_xc", "sxc_build_xc_device",
     "sxc_build_nadd", "sxc_build_nadd_device", "sxc_density_on_grid", "sxc_basis_on_grid",
-    "sxc_functional_on_grid", "sxc_scalar_to_matrix", "sxc_get_stats", "sxc_balance_ranges", "sxc_abi_version",
+    "sxc_functional_on_grid", "sxc_functional_on_grid_u", "sxc_scalar_to_matrix", "sxc_get_stats", "sxc_balance_ranges", "sxc_abi_version",
 ]
 
 
@@ -72,6 +72,7 @@ def load():
     lib.sxc_density_on_grid.argtypes = [vp, i, i, vp, vp, vp, vp, vp]
     lib.sxc_basis_on_grid.argtypes = [vp, i, i, i, vp, vp, vp, vp, vp, ip]
     lib.sxc_functional_on_grid.argtypes = [vp, i, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(d)]
+    lib.sxc_functional_on_grid_u.argtypes = [vp, i, i64, vp, vp, i, vp, vp, C.POINTER(d)]
     lib.sxc_scalar_to_matrix.argtypes = [vp, i, i, d, vp, vp, vp, vp, vp]
     lib.sxc_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.sxc_balance_ranges.argtypes = [i, vp, i, vp]

@@ -129,8 +129,10 @@ constexpr double B88_BETA = 0.0042;
 }  // namespace fc
 
 // ---------------------------------------------------------------------------------------- energy expressions
-template <class T> SXC_HD T f_zeta(const T& z) {  // [(1+z)^(4/3) + (1-z)^(4/3) - 2]/(2^(4/3) - 2)
-  return (pow43(1.0 + z) + pow43(1.0 - z) - 2.0) / (fc::TWO_43 - 2.0);
+// f(zeta) = [(1+z)^(4/3) + (1-z)^(4/3) - 2]/(2^(4/3) - 2) from zp = 1 + zeta = 2 rho_a / n and zm = 1 - zeta = 2 rho_b / n:
+// forming 1 -+ zeta from the spin densities keeps full precision at (nearly) fully polarised points
+template <class T> SXC_HD T f_zeta(const T& zp, const T& zm) {
+  return (pow43(zp) + pow43(zm) - 2.0) / (fc::TWO_43 - 2.0);
 }
 
 template <class T> SXC_HD T e_slaterx(const T& a, const T& b) {
@@ -154,7 +156,7 @@ template <class T> SXC_HD T e_vwn5c(const T& a, const T& b) {
   const T eP = vwn_eps(x, 0.0310907, -0.10498, 3.72744, 12.9352);
   const T eF = vwn_eps(x, 0.01554535, -0.32500, 7.06042, 18.0578);
   const T ac = vwn_eps(x, -1.0 / (6.0 * fc::PI * fc::PI), -0.0047584, 1.13107, 13.0045);
-  const T fz = f_zeta(z);
+  const T fz = f_zeta(2.0 * a / n, 2.0 * b / n);
   const T z2 = z * z, z4 = z2 * z2;
   return n * (eP + ac * fz * (1.0 - z4) / fc::FPP0 + (eF - eP) * fz * z4);
 }
@@ -204,12 +206,12 @@ template <class T> SXC_HD T pw92_G(const T& rs, const T& srs, double A, double a
   const T q1 = (2.0 * A) * (b1 * srs + b2 * rs + b3 * rs * srs + b4 * rs * rs);
   return (-2.0 * A) * (1.0 + a1 * rs) * dlog1p(1.0 / q1);
 }
-template <class T> SXC_HD T pw92_eps(const T& rs, const T& z) {
+template <class T> SXC_HD T pw92_eps(const T& rs, const T& z, const T& zp, const T& zm) {
   const T srs = dsqrt(rs);
   const T e0 = pw92_G(rs, srs, 0.0310907, 0.21370, 7.5957, 3.5876, 1.6382, 0.49294);
   const T e1 = pw92_G(rs, srs, 0.01554535, 0.20548, 14.1189, 6.1977, 3.3662, 0.62517);
   const T mac = pw92_G(rs, srs, 0.0168869, 0.11125, 10.357, 3.6231, 0.88026, 0.49671);  // -alpha_c
-  const T fz = f_zeta(z);
+  const T fz = f_zeta(zp, zm);
   const T z2 = z * z, z4 = z2 * z2;
   return e0 - mac * fz * (1.0 - z4) / fc::FPP0 + (e1 - e0) * fz * z4;
 }
@@ -219,8 +221,9 @@ template <class T> SXC_HD T e_pbec(const T& a, const T& b, const T& gaa, const T
   const T g = gaa + 2.0 * gab + gbb;
   const T z = (a - b) / n;
   const T rs = dcbrt(3.0 / (4.0 * fc::PI * n));
-  const T eps = pw92_eps(rs, z);
-  const T cp = dcbrt(1.0 + z), cm = dcbrt(1.0 - z);
+  const T zp = 2.0 * a / n, zm = 2.0 * b / n;
+  const T eps = pw92_eps(rs, z, zp, zm);
+  const T cp = dcbrt(zp), cm = dcbrt(zm);
   const T phi = 0.5 * (cp * cp + cm * cm);
   const T phi3 = phi * phi * phi;
   const T kF = fc::CBRT_3PI2 * dcbrt(n);
@@ -245,14 +248,14 @@ template <class T> SXC_HD T e_p86c(const T& a, const T& b, const T& gaa, const T
   const T rs = dcbrt(3.0 / (4.0 * fc::PI * n));
   const T eU = pz81_branch(rs, -0.1423, 1.0529, 0.3334, 0.0311, -0.048, 0.0020, -0.0116);
   const T eP = pz81_branch(rs, -0.0843, 1.3981, 0.2611, 0.01555, -0.0269, 0.0007, -0.0048);
-  const T eps = eU + f_zeta(z) * (eP - eU);
+  const T eps = eU + f_zeta(2.0 * a / n, 2.0 * b / n) * (eP - eU);
   const T rs2 = rs * rs;
   const T Cn = 0.001667 + (0.002568 + 0.023266 * rs + 7.389e-6 * rs2) / (1.0 + 8.723 * rs + 0.472 * rs2 + 0.07389 * rs2 * rs);
   const T c = dcbrt(n);
   const T n43 = n * c;
   const T n76 = n * dsqrt(c);  // n^(7/6)
   const T Phi = (1.745 * 0.11 * 0.004235) * dsqrt(g) / (Cn * n76);
-  const T hp = 0.5 * (1.0 + z), hm = 0.5 * (1.0 - z);
+  const T hp = a / n, hm = b / n;
   const T d = fc::TWO_13 * dsqrt(pow53(hp) + pow53(hm));
   return n * eps + dexp(-Phi) * Cn * g / (d * n43);
 }
@@ -379,6 +382,82 @@ k_functional(FuncView f, long npts, const int* __restrict__ lit_blocks, const do
   }
   const double e = block_sum(wp * F, scratch);
   const double ne = block_sum(wp * r, scratch);
+  if (t == 0) {
+    if (e_part) e_part[lb] = e;
+    if (n_part) n_part[lb] = ne;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K3u: UNRESTRICTED functional on literal 128-point blocks (XCFun.cpp:100-112 vars XC_A_B_AX_AY_AZ_BX_BY_BZ, :129-153).
+// dens8 / out8 rows: rho_a, gax, gay, gaz, rho_b, gbx, gby, gbz (each [npts]).  Five seeded directions
+// (rho_a, rho_b, s_aa, s_ab, s_bb); dF/d(grad rho_a) = 2 v_aa grad rho_a + v_ab grad rho_b.  The block is skipped only
+// if BOTH spin densities are below the block threshold (:133-137); output is zero when rho_a + rho_b < 1e-14 and a
+// single channel below 1e-14 is raised to it (xcfun's density regularisation; "parity unpinned").
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FUNC_BLOCK)
+k_functional_u(FuncView f, long npts, const int* __restrict__ lit_blocks, const double* __restrict__ w,
+               const double* __restrict__ dens8, double sign, int accumulate, double* __restrict__ epuv,
+               double* __restrict__ out8, double* __restrict__ e_part, double* __restrict__ n_part) {
+  __shared__ double scratch[32];
+  const int lb = lit_blocks ? lit_blocks[blockIdx.x] : blockIdx.x;
+  const long first = (long)lb * FUNC_BLOCK;
+  const int n = (int)min((long)FUNC_BLOCK, npts - first);
+  const int t = threadIdx.x;
+  const bool valid = t < n;
+  const long p = first + t;
+  const double ra = valid ? dens8[p] : 0.0;
+  const double rb = valid ? dens8[4 * npts + p] : 0.0;
+  const double wp = valid ? w[p] : 0.0;
+  const double sum_a = block_sum(fabs(ra), scratch);
+  const double sum_b = block_sum(fabs(rb), scratch);
+  const bool skip = sum_a < (double)n * 1e-12 && sum_b < (double)n * 1e-12;
+  double F = 0.0, o[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  if (!skip && valid && !(ra + rb < 1e-14)) {
+    double ga[3] = {0.0, 0.0, 0.0}, gb[3] = {0.0, 0.0, 0.0};
+    if (f.gga) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        ga[c] = dens8[(size_t)(1 + c) * npts + p];
+        gb[c] = dens8[(size_t)(5 + c) * npts + p];
+      }
+    }
+    typedef Dual<5> T;
+    T a = mk<5>(fmax(ra, 1e-14)), b = mk<5>(fmax(rb, 1e-14));
+    T saa = mk<5>(ga[0] * ga[0] + ga[1] * ga[1] + ga[2] * ga[2]);
+    T sab = mk<5>(ga[0] * gb[0] + ga[1] * gb[1] + ga[2] * gb[2]);
+    T sbb = mk<5>(gb[0] * gb[0] + gb[1] * gb[1] + gb[2] * gb[2]);
+    a.d[0] = 1.0;
+    b.d[1] = 1.0;
+    saa.d[2] = 1.0;
+    sab.d[3] = 1.0;
+    sbb.d[4] = 1.0;
+    double d[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int c = 0; c < f.ncomp; ++c) {
+      const T e = basic_functional<T>(f.id[c], a, b, saa, sab, sbb);
+      F += f.mix[c] * e.v;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) d[i] += f.mix[c] * e.d[i];
+    }
+    o[0] = d[0];
+    o[4] = d[1];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      o[1 + c] = 2.0 * d[2] * ga[c] + d[3] * gb[c];
+      o[5 + c] = 2.0 * d[4] * gb[c] + d[3] * ga[c];
+    }
+  }
+  if (valid) {
+    if (epuv) epuv[p] = F;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      if (!f.gga && (r & 3)) continue;
+      double* dst = out8 + (size_t)r * npts + p;
+      *dst = (accumulate ? *dst : 0.0) + sign * o[r];
+    }
+  }
+  const double e = block_sum(wp * F, scratch);
+  const double ne = block_sum(wp * (ra + rb), scratch);
   if (t == 0) {
     if (e_part) e_part[lb] = e;
     if (n_part) n_part[lb] = ne;

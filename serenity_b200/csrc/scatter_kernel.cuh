@@ -5,8 +5,8 @@
 //     G = diag(b_x) d_x phi_s + diag(b_y) d_y phi_s + diag(b_z) d_z phi_s + 1/2 diag(a) phi_s;
 //     T = phi_s^T G;  V_s = T + T^T;  V += Proj V_s Proj^T.
 // The LDA variant (:179-223, V_s = phi_s^T diag(a) phi_s) is the same expression with b = 0.
-// B200 design: k_form_g builds G in place of the d_x phi tile (bandwidth-bound: reads 4 tiles, writes 1; fused with
-// the block-average test).  k_vmat is a persistent kernel (8 warps, two CTAs per SM) that pulls blocks from a device
+// B200 design: k_form_g builds G in the fifth slot of the tile (bandwidth-bound: reads 4 tile components, writes 1;
+// fused with the block-average test; phi and grad phi stay intact for the second spin of an UNRESTRICTED build).  k_vmat is a persistent kernel (8 warps, two CTAs per SM) that pulls blocks from a device
 // work queue (largest first) and computes only the upper triangle of V_s, cut into 32 x 32 warp tiles
 //          U[I,J] = [phi_I | G_I] . [G_J | phi_J]^T      (stacked K = 2 x 128 points, DMMA m8n8k4)
 // in host-scheduled "rounds" (sxc_api.cu: scatter_schedule): <= 8 warp tiles that touch <= 6 distinct 32-row groups.
@@ -67,8 +67,8 @@ k_form_g(GridView g, PlanView plan, const int* __restrict__ order, double block_
   const double a = 0.5 * sa[p], bx = sx[p], by = sy[p], bz = sz[p];
   for (int c = tid >> 7; c < sp; c += 2) {
     const size_t i = (size_t)c * BP + p;
-    tile[comp_stride + i] = bx * tile[comp_stride + i] + by * tile[2 * comp_stride + i] +
-                            bz * tile[3 * comp_stride + i] + a * tile[i];  // :276-281
+    tile[4 * comp_stride + i] = bx * tile[comp_stride + i] + by * tile[2 * comp_stride + i] +
+                                bz * tile[3 * comp_stride + i] + a * tile[i];  // :276-281
   }
 }
 
@@ -126,7 +126,7 @@ k_vmat(PlanView plan, int nbf, const int* __restrict__ order, int nblk, int* __r
 
     // ---- 2. rounds of warp tiles
     const double* __restrict__ phi = tile;
-    const double* __restrict__ G = tile + comp_stride;  // G lives in the d_x phi slot
+    const double* __restrict__ G = tile + 4 * comp_stride;  // G slot of the tile
     const int* __restrict__ sig = plan.sig_bf + (size_t)q * plan.nbf_pad;
     const int n32 = sp >> 5;
     const ScatterRound* __restrict__ rounds = tpl + tpl_off[n32];

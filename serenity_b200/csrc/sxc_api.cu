@@ -445,7 +445,7 @@ int get_plan(sxc_ctx* ctx, int gh, int bh, Plan** out) {
     const int sp = std::max(SPAD, ((s + SPAD - 1) / SPAD) * SPAD);
     p.h_s_pad[q] = sp;
     p.s_pad_max = std::max(p.s_pad_max, sp);
-    const size_t tile = (size_t)4 * sp * BP;
+    const size_t tile = (size_t)TILE_COMPS * sp * BP;
     if (cur.nslots > 0 && (int64_t)((cur.doubles + tile) * sizeof(double)) > limit) {
       p.chunks.push_back(cur);
       cur = Chunk();
@@ -506,8 +506,9 @@ int get_plan(sxc_ctx* ctx, int gh, int bh, Plan** out) {
   return SXC_OK;
 }
 
-int ensure_point_arrays(sxc_ctx* ctx, Grid& g, bool nadd) {
-  const size_t n4 = (size_t)4 * std::max<long>(g.npts, 1) * sizeof(double);
+// per-point SoA arrays: rows rho, gx, gy, gz per spin ([4 * nspin][N])
+int ensure_point_arrays(sxc_ctx* ctx, Grid& g, bool nadd, int nspin) {
+  const size_t n4 = (size_t)4 * nspin * std::max<long>(g.npts, 1) * sizeof(double);
   if (g.dens.bytes < n4) {
     CU(g.dens.ensure(n4));
     CU(cudaMemsetAsync(g.dens.p, 0, n4, ctx->stream));
@@ -551,9 +552,10 @@ int phase_density(sxc_ctx* ctx, const Grid& g, const Basis& b, const Plan& p, co
   return SXC_OK;
 }
 
-// functional on the literal blocks covered by the chunk (or on all of them when blocksize != 128)
-int phase_functional(sxc_ctx* ctx, const Grid& g, const Plan& p, const Chunk& c, const FuncView& f, const double* dens4,
-                     double sign, int accumulate, double* pot4, double* e_part, double* n_part) {
+// functional on the literal blocks covered by the chunk (or on all of them when blocksize != 128);
+// dens / pot are [4 * nspin][N]
+int phase_functional(sxc_ctx* ctx, const Grid& g, const Plan& p, const Chunk& c, const FuncView& f, int nspin,
+                     const double* dens, double sign, int accumulate, double* pot, double* e_part, double* n_part) {
   const long N = g.npts;
   const GridView gv = g.view();
   const bool lit_is_block = g.blocksize == FUNC_BLOCK;
@@ -561,10 +563,15 @@ int phase_functional(sxc_ctx* ctx, const Grid& g, const Plan& p, const Chunk& c,
   if (nb == 0) return SXC_OK;
   const int* list = lit_is_block ? p.block_id.as<int>() + c.slot0 : nullptr;
   PhaseTimer t(ctx, SXC_T_FUNCTIONAL);
-  k_functional<<<nb, FUNC_BLOCK, 0, ctx->stream>>>(f, N, list, gv.w, dens4, dens4 + N, dens4 + 2 * N, dens4 + 3 * N,
-                                                   sign, accumulate, nullptr, pot4, f.gga ? pot4 + N : nullptr,
-                                                   f.gga ? pot4 + 2 * N : nullptr, f.gga ? pot4 + 3 * N : nullptr,
-                                                   e_part, n_part);
+  if (nspin == 2) {
+    k_functional_u<<<nb, FUNC_BLOCK, 0, ctx->stream>>>(f, N, list, gv.w, dens, sign, accumulate, nullptr, pot, e_part,
+                                                       n_part);
+  } else {
+    k_functional<<<nb, FUNC_BLOCK, 0, ctx->stream>>>(f, N, list, gv.w, dens, dens + N, dens + 2 * N, dens + 3 * N, sign,
+                                                     accumulate, nullptr, pot, f.gga ? pot + N : nullptr,
+                                                     f.gga ? pot + 2 * N : nullptr, f.gga ? pot + 3 * N : nullptr, e_part,
+                                                     n_part);
+  }
   LAUNCH_CHECK();
   return SXC_OK;
 }
@@ -618,7 +625,7 @@ int reduce_to(sxc_ctx* ctx, const double* part, int n, double* out) {
 // ---------------------------------------------------------------------------------------------- builds
 int build_xc_device(sxc_ctx* ctx, int gh, int bh, int fh, int nspin, const double* dP, double thr, double* dVEN,
                     bool timed) {
-  if (nspin != 1) return fail(ctx, SXC_ERR_UNSUPPORTED, "UNRESTRICTED (nspin = 2) is not implemented yet");
+  if (nspin != 1 && nspin != 2) return fail(ctx, SXC_ERR_INVALID, "nspin must be 1 (RESTRICTED) or 2 (UNRESTRICTED)");
   if (fh < 0 || fh >= (int)ctx->funcs.size()) return fail(ctx, SXC_ERR_INVALID, "invalid functional handle %d", fh);
   Plan* pp = nullptr;
   TRY(get_plan(ctx, gh, bh, &pp));
@@ -626,38 +633,46 @@ int build_xc_device(sxc_ctx* ctx, int gh, int bh, int fh, int nspin, const doubl
   Grid& g = *get_grid(ctx, gh);
   Basis& b = *get_basis(ctx, bh);
   const FuncView f = ctx->funcs[fh];
-  TRY(ensure_point_arrays(ctx, g, false));
+  TRY(ensure_point_arrays(ctx, g, false, nspin));
   ctx->stats = p.stats;
   begin_timing(ctx, timed || ctx->timing_device);
   const int launches0 = ctx->launches;
   const size_t nb2 = (size_t)b.nbf * b.nbf;
+  const long N = g.npts;
   double* parts = g.parts.as<double>();
+  double* dens = g.dens.as<double>();
+  double* pot = g.pot.as<double>();
   {
     PhaseTimer t_all(ctx, T_TOTAL);
-    CU(cudaMemsetAsync(dVEN, 0, (nb2 + 2) * sizeof(double), ctx->stream));
+    CU(cudaMemsetAsync(dVEN, 0, (nspin * nb2 + 2) * sizeof(double), ctx->stream));
     CU(cudaMemsetAsync(parts, 0, (size_t)3 * std::max(g.nlit, 1) * sizeof(double), ctx->stream));
     // the screening is part of every build in the reference (calculateBasisFunctionData :211-255)
     TRY(run_screen(ctx, g, b, p));
     for (const Chunk& c : p.chunks) {
       TRY(phase_basis(ctx, g, b, p, c));
-      TRY(phase_density(ctx, g, b, p, c, dP, g.dens.as<double>(), true, nullptr));
-      TRY(phase_functional(ctx, g, p, c, f, g.dens.as<double>(), 1.0, 0, g.pot.as<double>(), parts, parts + g.nlit));
-      if (f.ncomp > 0) TRY(phase_scatter(ctx, g, b, p, c, f.gga != 0, thr, g.pot.as<double>(), dVEN));
+      // UNRESTRICTED: the same block data is contracted with P_alpha and P_beta (MatrixOperatorToGridTransformer.h:128-146)
+      for (int sp = 0; sp < nspin; ++sp)
+        TRY(phase_density(ctx, g, b, p, c, dP + sp * nb2, dens + (size_t)4 * sp * N, true, nullptr));
+      TRY(phase_functional(ctx, g, p, c, f, nspin, dens, 1.0, 0, pot, parts, parts + g.nlit));
+      if (f.ncomp > 0)  // per spin, each with its own block-average test (ScalarOperatorToMatrixAdder.cpp:262-268)
+        for (int sp = 0; sp < nspin; ++sp)
+          TRY(phase_scatter(ctx, g, b, p, c, f.gga != 0, thr, pot + (size_t)4 * sp * N, dVEN + sp * nb2));
     }
-    TRY(finish_matrix(ctx, b.nbf, dVEN));
-    TRY(reduce_to(ctx, parts, g.nlit, dVEN + nb2));
-    TRY(reduce_to(ctx, parts + g.nlit, g.nlit, dVEN + nb2 + 1));
+    for (int sp = 0; sp < nspin; ++sp) TRY(finish_matrix(ctx, b.nbf, dVEN + sp * nb2));
+    TRY(reduce_to(ctx, parts, g.nlit, dVEN + nspin * nb2));
+    TRY(reduce_to(ctx, parts + g.nlit, g.nlit, dVEN + nspin * nb2 + 1));
   }
   ctx->timing = false;
   ctx->stats.kernel_launches = ctx->launches - launches0;
   return SXC_OK;
 }
 
-__global__ void k_add4(long N, int blocksize, const int* __restrict__ block_id, const double* __restrict__ a,
+// out = a + b (b may be null) on the blocks of a chunk, ncomp rows of length N
+__global__ void k_add4(long N, int blocksize, int ncomp, const int* __restrict__ block_id, const double* __restrict__ a,
                        const double* __restrict__ b, double* __restrict__ out) {
   const long first = (long)block_id[blockIdx.x] * blocksize;
   const long n = min((long)blocksize, N - first);
-  for (int c = 0; c < 4; ++c)
+  for (int c = 0; c < ncomp; ++c)
     for (long i = threadIdx.x; i < n; i += blockDim.x) {
       const size_t k = (size_t)c * N + first + i;
       out[k] = a[k] + (b ? b[k] : 0.0);
@@ -666,7 +681,7 @@ __global__ void k_add4(long N, int blocksize, const int* __restrict__ block_id, 
 
 int build_nadd_device(sxc_ctx* ctx, int gh, int fh, int nspin, int bA, const double* dPA, int nenv, const int* bE,
                       const double* const* dPE, int frozen, double thr, double* dVE, bool timed) {
-  if (nspin != 1) return fail(ctx, SXC_ERR_UNSUPPORTED, "UNRESTRICTED (nspin = 2) is not implemented yet");
+  if (nspin != 1 && nspin != 2) return fail(ctx, SXC_ERR_INVALID, "nspin must be 1 (RESTRICTED) or 2 (UNRESTRICTED)");
   if (fh < 0 || fh >= (int)ctx->funcs.size()) return fail(ctx, SXC_ERR_INVALID, "invalid functional handle %d", fh);
   if (nenv < 0) return fail(ctx, SXC_ERR_INVALID, "nenv < 0");
   Grid* gp = get_grid(ctx, gh);
@@ -681,42 +696,48 @@ int build_nadd_device(sxc_ctx* ctx, int gh, int fh, int nspin, int bA, const dou
     if (!get_basis(ctx, bE[i])) return fail(ctx, SXC_ERR_INVALID, "invalid environment basis handle %d", bE[i]);
     TRY(get_plan(ctx, gh, bE[i], &pe));
   }
-  TRY(ensure_point_arrays(ctx, g, true));
+  TRY(ensure_point_arrays(ctx, g, true, nspin));
   CU(ctx->scratch.ensure(64 * sizeof(double)));
   const long N = g.npts;
+  const int ncomp = 4 * nspin;
   const size_t nb2 = (size_t)ba->nbf * ba->nbf;
   double* parts = g.parts.as<double>();
+  double* dens = g.dens.as<double>();
+  double* pot = g.pot.as<double>();
   ctx->stats = pa->stats;
   begin_timing(ctx, timed || ctx->timing_device);
   const int launches0 = ctx->launches;
   {
     PhaseTimer t_all(ctx, T_TOTAL);
-    CU(cudaMemsetAsync(dVE, 0, (nb2 + 2 + nenv) * sizeof(double), ctx->stream));
+    CU(cudaMemsetAsync(dVE, 0, (nspin * nb2 + 2 + nenv) * sizeof(double), ctx->stream));
 
     // environment: rho_env on the supersystem grid, summed; E[rho_env_i] (NAddEnergyHelper, NAddFuncPotential.cpp:502-516)
     std::vector<int> key(bE, bE + nenv);
     key.push_back(fh);
+    key.push_back(nspin);
     const bool reuse = frozen && g.env_valid && g.env_key == key;
     if (!reuse) {
-      CU(cudaMemsetAsync(g.envsum.p, 0, (size_t)4 * N * sizeof(double), ctx->stream));
+      CU(cudaMemsetAsync(g.envsum.p, 0, (size_t)ncomp * N * sizeof(double), ctx->stream));
       g.env_energy.assign(nenv, 0.0);
       for (int i = 0; i < nenv; ++i) {
         Basis* be = get_basis(ctx, bE[i]);
+        const size_t ne2 = (size_t)be->nbf * be->nbf;
         Plan* pe = nullptr;
         TRY(get_plan(ctx, gh, bE[i], &pe));
         CU(cudaMemsetAsync(parts, 0, (size_t)3 * std::max(g.nlit, 1) * sizeof(double), ctx->stream));
         TRY(run_screen(ctx, g, *be, *pe));
         for (const Chunk& c : pe->chunks) {
           TRY(phase_basis(ctx, g, *be, *pe, c));
-          TRY(phase_density(ctx, g, *be, *pe, c, dPE[i], g.dens.as<double>(), true, nullptr));
+          for (int sp = 0; sp < nspin; ++sp)
+            TRY(phase_density(ctx, g, *be, *pe, c, dPE[i] + sp * ne2, dens + (size_t)4 * sp * N, true, nullptr));
           if (pe->nown) {
             PhaseTimer t(ctx, SXC_T_DENSITY);
-            k_add4<<<c.nslots, 128, 0, ctx->stream>>>(N, g.blocksize, pe->block_id.as<int>() + c.slot0,
-                                                      g.envsum.as<double>(), g.dens.as<double>(), g.envsum.as<double>());
+            k_add4<<<c.nslots, 128, 0, ctx->stream>>>(N, g.blocksize, ncomp, pe->block_id.as<int>() + c.slot0,
+                                                      g.envsum.as<double>(), dens, g.envsum.as<double>());
             LAUNCH_CHECK();
           }
           // energy only: the potential goes to g.pot and is overwritten later
-          TRY(phase_functional(ctx, g, *pe, c, f, g.dens.as<double>(), 1.0, 0, g.pot.as<double>(), parts, nullptr));
+          TRY(phase_functional(ctx, g, *pe, c, f, nspin, dens, 1.0, 0, pot, parts, nullptr));
         }
         TRY(reduce_to(ctx, parts, g.nlit, ctx->scratch.as<double>() + i));
       }
@@ -728,7 +749,8 @@ int build_nadd_device(sxc_ctx* ctx, int gh, int fh, int nspin, int bA, const dou
       g.env_valid = true;
     }
     if (nenv > 0)
-      CU(cudaMemcpyAsync(dVE + nb2 + 2, g.env_energy.data(), nenv * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      CU(cudaMemcpyAsync(dVE + nspin * nb2 + 2, g.env_energy.data(), nenv * sizeof(double), cudaMemcpyHostToDevice,
+                         ctx->stream));
 
     // active system: rho_A, rho_tot = rho_A + sum_env, v = v[rho_tot] - v[rho_A]  (NAddFuncPotential.cpp:197-225)
     Plan& p = *pa;
@@ -736,20 +758,23 @@ int build_nadd_device(sxc_ctx* ctx, int gh, int fh, int nspin, int bA, const dou
     TRY(run_screen(ctx, g, *ba, p));
     for (const Chunk& c : p.chunks) {
       TRY(phase_basis(ctx, g, *ba, p, c));
-      TRY(phase_density(ctx, g, *ba, p, c, dPA, g.dens.as<double>(), true, nullptr));
+      for (int sp = 0; sp < nspin; ++sp)
+        TRY(phase_density(ctx, g, *ba, p, c, dPA + sp * nb2, dens + (size_t)4 * sp * N, true, nullptr));
       if (p.nown) {
         PhaseTimer t(ctx, SXC_T_DENSITY);
-        k_add4<<<c.nslots, 128, 0, ctx->stream>>>(N, g.blocksize, p.block_id.as<int>() + c.slot0, g.dens.as<double>(),
+        k_add4<<<c.nslots, 128, 0, ctx->stream>>>(N, g.blocksize, ncomp, p.block_id.as<int>() + c.slot0, dens,
                                                   g.envsum.as<double>(), g.tot.as<double>());
         LAUNCH_CHECK();
       }
-      TRY(phase_functional(ctx, g, p, c, f, g.tot.as<double>(), 1.0, 0, g.pot.as<double>(), parts, nullptr));
-      TRY(phase_functional(ctx, g, p, c, f, g.dens.as<double>(), -1.0, 1, g.pot.as<double>(), parts + g.nlit, nullptr));
-      if (f.ncomp > 0) TRY(phase_scatter(ctx, g, *ba, p, c, f.gga != 0, thr, g.pot.as<double>(), dVE));
+      TRY(phase_functional(ctx, g, p, c, f, nspin, g.tot.as<double>(), 1.0, 0, pot, parts, nullptr));
+      TRY(phase_functional(ctx, g, p, c, f, nspin, dens, -1.0, 1, pot, parts + g.nlit, nullptr));
+      if (f.ncomp > 0)
+        for (int sp = 0; sp < nspin; ++sp)
+          TRY(phase_scatter(ctx, g, *ba, p, c, f.gga != 0, thr, pot + (size_t)4 * sp * N, dVE + sp * nb2));
     }
-    TRY(finish_matrix(ctx, ba->nbf, dVE));
-    TRY(reduce_to(ctx, parts, g.nlit, dVE + nb2));
-    TRY(reduce_to(ctx, parts + g.nlit, g.nlit, dVE + nb2 + 1));
+    for (int sp = 0; sp < nspin; ++sp) TRY(finish_matrix(ctx, ba->nbf, dVE + sp * nb2));
+    TRY(reduce_to(ctx, parts, g.nlit, dVE + nspin * nb2));
+    TRY(reduce_to(ctx, parts + g.nlit, g.nlit, dVE + nspin * nb2 + 1));
   }
   ctx->timing = false;
   ctx->stats.kernel_launches = ctx->launches - launches0;
@@ -950,19 +975,20 @@ int sxc_build_xc_device(sxc_ctx* ctx, int grid, int basis, int func, int nspin, 
 int sxc_build_xc(sxc_ctx* ctx, int grid, int basis, int func, int nspin, const double* P, double thr, double* V,
                  double* E, double* nelec) {
   if (!ctx || !P || !V || !E) return fail(ctx, SXC_ERR_INVALID, "sxc_build_xc: bad arguments");
+  if (nspin != 1 && nspin != 2) return fail(ctx, SXC_ERR_INVALID, "nspin must be 1 or 2");
   Basis* b = get_basis(ctx, basis);
   if (!b) return fail(ctx, SXC_ERR_INVALID, "invalid basis handle %d", basis);
   CU(cudaSetDevice(ctx->device));
-  const size_t nb2 = (size_t)b->nbf * b->nbf;
-  CU(ctx->dP.ensure(nb2 * sizeof(double)));
-  CU(ctx->dOut.ensure((nb2 + 2) * sizeof(double)));
-  CU(cudaMemcpyAsync(ctx->dP.p, P, nb2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  const size_t nv = (size_t)nspin * b->nbf * b->nbf;
+  CU(ctx->dP.ensure(nv * sizeof(double)));
+  CU(ctx->dOut.ensure((nv + 2) * sizeof(double)));
+  CU(cudaMemcpyAsync(ctx->dP.p, P, nv * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   int rc = build_xc_device(ctx, grid, basis, func, nspin, ctx->dP.as<double>(), thr, ctx->dOut.as<double>(), true);
   ctx->timing = false;
   if (rc != SXC_OK) return rc;
   std::vector<double> tail(2);
-  CU(cudaMemcpyAsync(V, ctx->dOut.p, nb2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaMemcpyAsync(tail.data(), ctx->dOut.as<double>() + nb2, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(V, ctx->dOut.p, nv * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(tail.data(), ctx->dOut.as<double>() + nv, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   collect_timers(ctx);
   *E = tail[0];
@@ -983,34 +1009,35 @@ int sxc_build_nadd(sxc_ctx* ctx, int grid, int func, int nspin, int basis_act, c
                    const int* basis_env, const double* const* P_env, int env_frozen, double thr, double* V_act, double* E) {
   if (!ctx || !P_act || !V_act || !E || nenv < 0 || (nenv > 0 && (!basis_env || !P_env)))
     return fail(ctx, SXC_ERR_INVALID, "sxc_build_nadd: bad arguments");
+  if (nspin != 1 && nspin != 2) return fail(ctx, SXC_ERR_INVALID, "nspin must be 1 or 2");
   Basis* ba = get_basis(ctx, basis_act);
   if (!ba) return fail(ctx, SXC_ERR_INVALID, "invalid active basis handle %d", basis_act);
   CU(cudaSetDevice(ctx->device));
-  const size_t nbA2 = (size_t)ba->nbf * ba->nbf;
-  size_t total = nbA2;
+  const size_t nvA = (size_t)nspin * ba->nbf * ba->nbf;
+  size_t total = nvA;
   std::vector<size_t> offs(nenv);
   for (int i = 0; i < nenv; ++i) {
     Basis* be = get_basis(ctx, basis_env[i]);
     if (!be) return fail(ctx, SXC_ERR_INVALID, "invalid environment basis handle %d", basis_env[i]);
     offs[i] = total;
-    total += (size_t)be->nbf * be->nbf;
+    total += (size_t)nspin * be->nbf * be->nbf;
   }
   CU(ctx->dP.ensure(total * sizeof(double)));
-  CU(ctx->dOut.ensure((nbA2 + 2 + nenv) * sizeof(double)));
-  CU(cudaMemcpyAsync(ctx->dP.p, P_act, nbA2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx->dOut.ensure((nvA + 2 + nenv) * sizeof(double)));
+  CU(cudaMemcpyAsync(ctx->dP.p, P_act, nvA * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   std::vector<const double*> dpe(nenv);
   for (int i = 0; i < nenv; ++i) {
     Basis* be = get_basis(ctx, basis_env[i]);
     dpe[i] = ctx->dP.as<double>() + offs[i];
-    CU(cudaMemcpyAsync(ctx->dP.as<double>() + offs[i], P_env[i], (size_t)be->nbf * be->nbf * sizeof(double),
+    CU(cudaMemcpyAsync(ctx->dP.as<double>() + offs[i], P_env[i], (size_t)nspin * be->nbf * be->nbf * sizeof(double),
                        cudaMemcpyHostToDevice, ctx->stream));
   }
   int rc = build_nadd_device(ctx, grid, func, nspin, basis_act, ctx->dP.as<double>(), nenv, basis_env, dpe.data(),
                              env_frozen, thr, ctx->dOut.as<double>(), true);
   ctx->timing = false;
   if (rc != SXC_OK) return rc;
-  CU(cudaMemcpyAsync(V_act, ctx->dOut.p, nbA2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaMemcpyAsync(E, ctx->dOut.as<double>() + nbA2, (2 + nenv) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(V_act, ctx->dOut.p, nvA * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(E, ctx->dOut.as<double>() + nvA, (2 + nenv) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   collect_timers(ctx);
   return SXC_OK;
@@ -1024,7 +1051,7 @@ int sxc_density_on_grid(sxc_ctx* ctx, int grid, int basis, const double* P, doub
   TRY(get_plan(ctx, grid, basis, &pp));
   Grid& g = *get_grid(ctx, grid);
   Basis& b = *get_basis(ctx, basis);
-  TRY(ensure_point_arrays(ctx, g, false));
+  TRY(ensure_point_arrays(ctx, g, false, 1));
   const size_t nb2 = (size_t)b.nbf * b.nbf;
   const long N = g.npts;
   CU(ctx->dP.ensure(nb2 * sizeof(double)));
@@ -1137,6 +1164,36 @@ int sxc_functional_on_grid(sxc_ctx* ctx, int func, int64_t npts, const double* w
   return SXC_OK;
 }
 
+int sxc_functional_on_grid_u(sxc_ctx* ctx, int func, int64_t npts, const double* w, const double* dens8, int has_grad,
+                             double* epuv, double* out8, double* energy) {
+  if (!ctx || npts <= 0 || !w || !dens8 || !epuv || !out8)
+    return fail(ctx, SXC_ERR_INVALID, "sxc_functional_on_grid_u: bad arguments");
+  if (func < 0 || func >= (int)ctx->funcs.size()) return fail(ctx, SXC_ERR_INVALID, "invalid functional handle %d", func);
+  CU(cudaSetDevice(ctx->device));
+  FuncView f = ctx->funcs[func];
+  if (f.gga && !has_grad) return fail(ctx, SXC_ERR_INVALID, "GGA functional needs the density gradients");
+  const int nlit = (int)((npts + FUNC_BLOCK - 1) / FUNC_BLOCK);
+  DevMem buf;
+  const size_t N = (size_t)npts;
+  CU(buf.ensure((18 * N + nlit + 1) * sizeof(double)));
+  double* d = buf.as<double>();
+  double *d_w = d, *d_in = d + N, *d_ep = d + 9 * N, *d_out = d + 10 * N, *d_part = d + 18 * N;
+  CU(cudaMemcpyAsync(d_w, w, N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_in, dens8, 8 * N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemsetAsync(d_out, 0, 8 * N * sizeof(double), ctx->stream));
+  k_functional_u<<<nlit, FUNC_BLOCK, 0, ctx->stream>>>(f, npts, nullptr, d_w, d_in, 1.0, 0, d_ep, d_out, d_part, nullptr);
+  LAUNCH_CHECK();
+  k_reduce_partials<<<1, 256, 0, ctx->stream>>>(d_part, nlit, 1.0, 0, d_part + nlit);
+  LAUNCH_CHECK();
+  CU(cudaMemcpyAsync(epuv, d_ep, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(out8, d_out, 8 * N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  double e = 0.0;
+  CU(cudaMemcpyAsync(&e, d_part + nlit, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (energy) *energy = e;
+  return SXC_OK;
+}
+
 int sxc_scalar_to_matrix(sxc_ctx* ctx, int grid, int basis, double thr, const double* v, const double* gx,
                          const double* gy, const double* gz, double* V) {
   if (!ctx || !v || !V) return fail(ctx, SXC_ERR_INVALID, "sxc_scalar_to_matrix: bad arguments");
@@ -1145,7 +1202,7 @@ int sxc_scalar_to_matrix(sxc_ctx* ctx, int grid, int basis, double thr, const do
   TRY(get_plan(ctx, grid, basis, &pp));
   Grid& g = *get_grid(ctx, grid);
   Basis& b = *get_basis(ctx, basis);
-  TRY(ensure_point_arrays(ctx, g, false));
+  TRY(ensure_point_arrays(ctx, g, false, 1));
   const size_t nb2 = (size_t)b.nbf * b.nbf;
   const long N = g.npts;
   const bool gga = gx != nullptr;

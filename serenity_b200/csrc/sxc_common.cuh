@@ -9,6 +9,7 @@ namespace sxc {
 constexpr int BP = 128;       // points per tile (blocks are padded to this; reference default blocksize)
 constexpr int SPAD = 32;      // significant-function count is padded to a multiple of this
 constexpr int LMAX = 6;       // AM_MAX, src/parameters/Constants.h:31
+constexpr int TILE_COMPS = 5;  // tile = [phi, d/dx, d/dy, d/dz, G][s_pad][128]; G is written by the scatter phase
 constexpr int FUNC_BLOCK = 128;  // the literal block size of the functional evaluation (FuncPotential.cpp:85)
 
 // D(8x8) += A(8x4, row) * B(4x8, col) in FP64 on the tensor cores (SASS: DMMA.8x8x4).

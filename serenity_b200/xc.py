@@ -22,6 +22,17 @@ def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
+def _spin_pack(pair):
+    """(M_alpha, M_beta), each [nb, nb] -> one buffer [2, nb*nb] of two column-major matrices back to back."""
+    a, b = (np.asarray(m, dtype=np.float64) for m in pair)
+    return np.ascontiguousarray(np.stack([a.reshape(-1, order="F"), b.reshape(-1, order="F")]))
+
+
+def _spin_unpack(buf):
+    nb = int(round(np.sqrt(buf.shape[1])))
+    return tuple(np.asfortranarray(buf[s].reshape(nb, nb, order="F")) for s in range(2))
+
+
 class XCContext:
     """One context per process and GPU (sxc_create)."""
 
@@ -86,12 +97,17 @@ class XCContext:
 
     # ---- hot path
     def build_xc(self, grid, basis, func, P, block_ave_threshold: float = 1e-11, nspin: int = 1):
-        P = np.asfortranarray(P, dtype=np.float64)
-        V = np.zeros(P.shape, order="F")
+        """RESTRICTED: P [nb, nb] -> V [nb, nb].  UNRESTRICTED (nspin = 2): P = (P_alpha, P_beta) -> (V_alpha, V_beta)."""
+        if nspin == 2:
+            P = _spin_pack(P)
+            V = np.zeros_like(P)
+        else:
+            P = np.asfortranarray(P, dtype=np.float64)
+            V = np.zeros(P.shape, order="F")
         E, ne = C.c_double(), C.c_double()
         self._check(self._lib.sxc_build_xc(self._h, grid, basis, func, nspin, _ptr(P), block_ave_threshold, _ptr(V),
                                            C.byref(E), C.byref(ne)))
-        return V, E.value, ne.value
+        return (_spin_unpack(V) if nspin == 2 else V), E.value, ne.value
 
     def build_xc_device(self, grid, basis, func, d_P_ptr: int, d_VEN_ptr: int, block_ave_threshold: float = 1e-11,
                         nspin: int = 1):
@@ -100,16 +116,21 @@ class XCContext:
 
     def build_nadd(self, grid, func, basis_act, P_act, basis_env, P_env, env_frozen: bool = False,
                    block_ave_threshold: float = 1e-11, nspin: int = 1):
-        P_act = np.asfortranarray(P_act, dtype=np.float64)
-        P_env = [np.asfortranarray(p, dtype=np.float64) for p in P_env]
+        if nspin == 2:
+            P_act = _spin_pack(P_act)
+            P_env = [_spin_pack(p) for p in P_env]
+            V = np.zeros_like(P_act)
+        else:
+            P_act = np.asfortranarray(P_act, dtype=np.float64)
+            P_env = [np.asfortranarray(p, dtype=np.float64) for p in P_env]
+            V = np.zeros(P_act.shape, order="F")
         nenv = len(P_env)
         be = np.ascontiguousarray(basis_env, dtype=np.int32)
         pp = (C.c_void_p * max(nenv, 1))(*[p.ctypes.data for p in P_env])
-        V = np.zeros(P_act.shape, order="F")
         E = np.zeros(2 + nenv)
         self._check(self._lib.sxc_build_nadd(self._h, grid, func, nspin, basis_act, _ptr(P_act), nenv, _ptr(be), pp,
                                              1 if env_frozen else 0, block_ave_threshold, _ptr(V), _ptr(E)))
-        return V, E
+        return (_spin_unpack(V) if nspin == 2 else V), E
 
     def build_nadd_device(self, grid, func, basis_act, d_P_act: int, basis_env, d_P_env, d_VE: int,
                           env_frozen: bool = False, block_ave_threshold: float = 1e-11, nspin: int = 1):
@@ -149,6 +170,20 @@ class XCContext:
             _ptr(_f64(gy)) if gga else None, _ptr(_f64(gz)) if gga else None, _ptr(out[0]), _ptr(out[1]),
             _ptr(out[2]) if gga else None, _ptr(out[3]) if gga else None, _ptr(out[4]) if gga else None, C.byref(e)))
         return e.value, out
+
+    def functional_on_grid_u(self, func, w, rho2, grad23=None):
+        """rho2 [2, N], grad23 [2, 3, N] or None -> E, epuv [N], dFdRho [2, N], dFdGrad [2, 3, N]."""
+        rho2 = _f64(rho2)
+        N = rho2.shape[1]
+        dens8 = np.zeros((8, N))
+        dens8[0], dens8[4] = rho2[0], rho2[1]
+        if grad23 is not None:
+            dens8[1:4], dens8[5:8] = grad23[0], grad23[1]
+        ep, out8 = np.zeros(N), np.zeros((8, N))
+        e = C.c_double()
+        self._check(self._lib.sxc_functional_on_grid_u(self._h, func, N, _ptr(_f64(w)), _ptr(dens8),
+                                                       0 if grad23 is None else 1, _ptr(ep), _ptr(out8), C.byref(e)))
+        return e.value, ep, out8[[0, 4]], np.stack([out8[1:4], out8[5:8]])
 
     def scalar_to_matrix(self, grid, basis, nbf, v, gx=None, gy=None, gz=None, block_ave_threshold: float = 1e-11,
                          V=None):

@@ -60,7 +60,9 @@ int main(int argc, char** argv) {
     std::ifstream in(argv[1], std::ios::binary);
     std::ofstream out(argv[2], std::ios::binary);
     auto dev = std::make_shared<B200::XCDevice>(0);
-    auto grid = std::make_shared<GridController>(rd<double>(in), rd<double>(in));
+    std::vector<double> xyz = rd<double>(in);  // (function arguments have no evaluation order: read first)
+    std::vector<double> wts = rd<double>(in);
+    auto grid = std::make_shared<GridController>(std::move(xyz), std::move(wts));
     Functional xc{rd<int>(in), rd<double>(in)};
     Functional kin{rd<int>(in), rd<double>(in)};
     auto basisA = readBasis(in);

@@ -172,3 +172,12 @@ def closed_shell(fid, rho, sigma):
     if vs is None:
         vs = torch.zeros_like(r)
     return F.detach().numpy(), vr.numpy(), vs.numpy()
+
+
+def spin_resolved(fid, ra, rb, gaa, gab, gbb):
+    """F and dF/d(rho_a, rho_b, s_aa, s_ab, s_bb) by autograd (numpy arrays in, F [n] and d [5, n] out)."""
+    xs = [torch.tensor(x, dtype=torch.float64, requires_grad=True) for x in (ra, rb, gaa, gab, gbb)]
+    F = BY_ID[fid](*xs)
+    gr = torch.autograd.grad(F.sum(), xs, allow_unused=True)
+    d = [torch.zeros_like(xs[0]) if g is None else g for g in gr]
+    return F.detach().numpy(), torch.stack(d).numpy()

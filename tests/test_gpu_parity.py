@@ -296,3 +296,104 @@ def test_tetracene_full_size_properties(ctx, orc):
     assert np.abs(parts[0][0] + parts[1][0] - V).max() < 1e-9
     V_ref, E_ref, ne_ref, _ = orc.build_xc(orc.Basis(sub.basis), orc.Grid(cfg.xyz, cfg.w, 128), orc.Functional(ids, mix), P)
     assert abs(E - E_ref) <= E_TOL and np.abs(V - V_ref).max() <= V_TOL and abs(ne - ne_ref) < 1e-8
+
+
+# ------------------------------------------------------------------------------------------- UNRESTRICTED
+def _open_shell_P(sub, seed=21):
+    """P_alpha with one occupied orbital more than P_beta (random PSD matrices of the closed-shell magnitude)."""
+    nb, nocc = sub.basis.nbf, sub.n_electrons // 2
+    rng = np.random.default_rng(seed)
+    C = rng.normal(size=(nb, nocc + 1)) / np.sqrt(nb)
+    Pa = np.asfortranarray(C @ C.T)
+    Pb = np.asfortranarray(C[:, : nocc - 1] @ C[:, : nocc - 1].T)
+    return Pa, Pb
+
+
+@pytest.mark.parametrize("fid", [2, 45, 66, 80, 135, 184, 193, 197, 283, 286])
+def test_unrestricted_functional_kernels_vs_oracle(ctx, orc, fid):
+    rng = np.random.default_rng(100 + fid)
+    n = 700
+    rho = 10.0 ** rng.uniform(-9, 2.0, size=n)
+    zeta = rng.uniform(-1.0, 1.0, size=n)
+    zeta[::50] = 1.0                      # fully polarised points: rho_b = 0 is raised to the tiny density
+    rho2 = np.stack([0.5 * rho * (1 + zeta), 0.5 * rho * (1 - zeta)])
+    rho2[:, 5::97] = 2e-15                # below the tiny-density cut
+    grad = rng.normal(size=(2, 3, n)) * (rho2[:, None, :] + 1e-12) ** (4 / 3)
+    w = rng.uniform(0.1, 1.0, size=n)
+    f = ctx.set_functional([fid], [1.0])
+    e, ep, vr, vg = ctx.functional_on_grid_u(f, w, rho2, grad)
+    e_ref, ep_r, vr_r, vg_r = orc.functional_on_grid_u(orc.Functional([fid], [1.0]), w, rho2, grad)
+    for got, ref in ((ep, ep_r), (vr, vr_r), (vg, vg_r)):
+        scale = np.maximum(np.abs(ref), 1e-6 * np.abs(ref).max(axis=tuple(range(ref.ndim - 1)), keepdims=True) + 1e-300)
+        err = np.abs(got - ref)
+        assert np.all((err / scale < 1e-9) | (err < 1e-15)), (fid, float((err / scale).max()))
+    assert abs(e - e_ref) <= 1e-11 * max(1.0, abs(e_ref))
+
+
+@pytest.mark.parametrize("func_name", ["PBE", "B3LYP", "LDA", "BP86", "PW91K"])
+def test_h2o_unrestricted_build_matches_oracle(ctx, orc, func_name):
+    """FuncPotential<UNRESTRICTED>: {V_alpha, V_beta}, E_xc for an open-shell density pair."""
+    cfg = _cfg("h2o")
+    sub = cfg.subsystems[0]
+    ids, mix = _functional(func_name)
+    Pa, Pb = _open_shell_P(sub)
+    (Va_r, Vb_r), E_r, ne_r = orc.build_xc_u(orc.Basis(sub.basis), orc.Grid(cfg.xyz, cfg.w, 128), orc.Functional(ids, mix),
+                                             Pa, Pb)
+    g = ctx.set_grid(cfg.xyz, cfg.w, 128)
+    b = ctx.add_basis(sub.basis, 1e-9)
+    f = ctx.set_functional(ids, mix)
+    (Va, Vb), E, ne = ctx.build_xc(g, b, f, (Pa, Pb), nspin=2)
+    assert abs(E - E_r) <= E_TOL and abs(ne - ne_r) <= 1e-10 * abs(ne_r)
+    assert np.abs(Va - Va_r).max() <= V_TOL and np.abs(Vb - Vb_r).max() <= V_TOL
+    assert np.array_equal(Va, Va.T) and np.array_equal(Vb, Vb.T) and np.abs(Va - Vb).max() > 1e-4
+
+
+def test_unrestricted_reduces_to_restricted(ctx):
+    """P_alpha = P_beta = P/2 gives V_alpha = V_beta = V_restricted and the same E_xc."""
+    cfg = _cfg("water8")
+    sub = cfg.subsystems[0]
+    g = ctx.set_grid(cfg.xyz, cfg.w, 128)
+    b = ctx.add_basis(sub.basis, 1e-9)
+    f = ctx.set_functional(*_functional("PBE"))
+    V, E, ne = ctx.build_xc(g, b, f, sub.P)
+    (Va, Vb), Eu, neu = ctx.build_xc(g, b, f, (0.5 * sub.P, 0.5 * sub.P), nspin=2)
+    assert abs(E - Eu) < 1e-10 and abs(ne - neu) < 1e-10
+    assert np.abs(Va - V).max() < 1e-10 and np.abs(Vb - V).max() < 1e-10
+
+
+def test_unrestricted_empty_beta_channel(ctx, orc):
+    """One-electron-like case: P_beta = 0.  The beta blocks fail the per-spin block test in the density-dependent part
+    (Appendix E.9) but the functional is still evaluated because alpha is not negligible."""
+    cfg = _cfg("h2o", 2)
+    sub = cfg.subsystems[0]
+    ids, mix = _functional("PBE")
+    Pa = np.asfortranarray(0.5 * sub.P)
+    Pb = np.zeros_like(Pa)
+    (Va_r, Vb_r), E_r, _ = orc.build_xc_u(orc.Basis(sub.basis), orc.Grid(cfg.xyz, cfg.w, 128), orc.Functional(ids, mix), Pa, Pb)
+    g = ctx.set_grid(cfg.xyz, cfg.w, 128)
+    b = ctx.add_basis(sub.basis, 1e-9)
+    f = ctx.set_functional(ids, mix)
+    (Va, Vb), E, _ = ctx.build_xc(g, b, f, (Pa, Pb), nspin=2)
+    assert abs(E - E_r) <= E_TOL and np.abs(Va - Va_r).max() <= V_TOL and np.abs(Vb - Vb_r).max() <= V_TOL
+
+
+def test_nadd_unrestricted_dimer_matches_oracle(ctx, orc):
+    """NAddFuncPotential<UNRESTRICTED> on the water dimer: open-shell active system, closed-shell environment."""
+    cfg = _cfg("fde_dimer")
+    act, env = cfg.subsystems
+    PA = _open_shell_P(act)
+    PE = (np.asfortranarray(0.5 * env.P), np.asfortranarray(0.5 * env.P))
+    g = ctx.set_grid(cfg.xyz, cfg.w, 128)
+    bA = ctx.add_basis(act.basis, 1e-9)
+    bE = ctx.add_basis(env.basis, 1e-9)
+    og = orc.Grid(cfg.xyz, cfg.w, 128)
+    for name in ["PBE", "PW91K"]:
+        ids, mix = _functional(name)
+        f = ctx.set_functional(ids, mix)
+        (Va, Vb), E = ctx.build_nadd(g, f, bA, PA, [bE], [PE], nspin=2)
+        (Va_r, Vb_r), E_ref, parts = orc.build_nadd_u(orc.Basis(act.basis), PA, [(orc.Basis(env.basis), PE)], og,
+                                                      orc.Functional(ids, mix))
+        assert np.abs(Va - Va_r).max() <= V_TOL and np.abs(Vb - Vb_r).max() <= V_TOL, name
+        assert np.allclose(E, parts, rtol=0, atol=E_TOL) and abs((E[0] - E[1] - E[2]) - E_ref) <= E_TOL
+        (Va2, Vb2), E2 = ctx.build_nadd(g, f, bA, PA, [bE], [PE], env_frozen=True, nspin=2)
+        assert np.abs(Va2 - Va).max() < 1e-12 and np.abs(E2 - E).max() < 1e-12
