@@ -73,30 +73,41 @@ k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, cons
   const int nk = sp / TK;                 // K chunks per j-tile
   const int n32 = sp / 32;                // 32-function column groups
   const int njt = (n32 + NJW - 1) / NJW;  // j-tiles of 64
-  const int total = njt * nk;
   const int pw = warp & 3, jw = warp >> 2;
   const int lr = lane >> 2, lc = lane & 3;
 
-  auto issue = [&](int gi) {
-    if (gi < total) {
-      const int jt = gi / nk, kc = gi - jt * nk;
-      double* As = stage_base + (gi % STAGES) * STAGE_ELEMS;
-      double* Bs = As + A_ELEMS;
-      const double* src = tile + (size_t)kc * TK * BP;
+  // Producer side of the ring.  Every thread copies 4 x 16 B of the phi chunk and gathers 4 elements of the P_s chunk per
+  // stage; all per-thread address parts are loop invariants or advance by constants (no divisions in the loop).
+  const double* a_src = tile + (size_t)(tid >> 6) * BP + (tid & 63) * 2;  // + kc * TK * BP
+  const int a_dst = (tid >> 6) * A_STRIDE + (tid & 63) * 2;
+  const int bk = tid & (TK - 1), bj = tid >> 4;                           // gather: k = bk, j = bj + 16 i
+  const int b_dst = A_ELEMS + bj * B_STRIDE + bk;
+  int is_jt = 0, is_kc = 0, is_stage = 0;
+  int colbase[4] = {0, 0, 0, 0};  // sig[j] * nbf of this thread's four columns of the j-tile being issued
+  auto load_colbase = [&]() {
+    if (is_jt < njt) {  // (sig holds s_pad + TJ entries: nothing to read past the last j-tile)
 #pragma unroll
-      for (int i = 0; i < (TK * BP / 2) / THREADS; ++i) {  // 1024 x 16 B
-        const int idx = tid + i * THREADS;
-        const int row = idx >> 6, c16 = idx & 63;
-        cp_async16(As + row * A_STRIDE + c16 * 2, src + (size_t)row * BP + c16 * 2);
-      }
-      const int j0 = jt * TJ, k0 = kc * TK;
-      const int ncol = min(TJ, sp - j0);
+      for (int i = 0; i < 4; ++i) colbase[i] = sig[is_jt * TJ + bj + 16 * i] * nbf;
+    }
+  };
+  load_colbase();
+  auto issue = [&]() {
+    if (is_jt < njt) {
+      double* st = stage_base + is_stage * STAGE_ELEMS;
+      const double* src = a_src + (size_t)is_kc * (TK * BP);
 #pragma unroll
-      for (int i = 0; i < (TJ * TK) / THREADS; ++i) {  // <= 1024 x 8 B gathers: B[j][k] = P[sig[k], sig[j]]
-        const int idx = tid + i * THREADS;
-        const int k = idx & (TK - 1), j = idx >> 4;
-        if (j < ncol) cp_async8(Bs + j * B_STRIDE + k, P + (size_t)sig[k0 + k] + (size_t)sig[j0 + j] * nbf);
+      for (int i = 0; i < 4; ++i) cp_async16(st + a_dst + i * 4 * A_STRIDE, src + i * 4 * BP);
+      const int ncol = sp - is_jt * TJ;  // columns of this j-tile that exist (>= 64 except for the last tile)
+      const double* prow = P + sig[is_kc * TK + bk];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (bj + 16 * i < ncol) cp_async8(st + b_dst + i * 16 * B_STRIDE, prow + colbase[i]);
+      if (++is_kc == nk) {
+        is_kc = 0;
+        ++is_jt;
+        load_colbase();
       }
+      is_stage = (is_stage + 1 == STAGES) ? 0 : is_stage + 1;
     }
     cp_async_commit();
   };
@@ -105,9 +116,9 @@ k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, cons
   for (int i = tid; i < NJW * BP * 4; i += THREADS) red[i] = 0.0;
   const int pf_kc = max(0, nk - 6);  // ~6 K chunks (tens of microseconds) before the epilogue
 
-  issue(0);
-  issue(1);
-  int gi = 0;
+  issue();
+  issue();
+  int c_stage = 0;
   for (int jt = 0; jt < njt; ++jt) {
     // a last j-tile with one 32-function group: both function-group warps work on it, on alternating k-steps
     const bool split = (n32 - jt * NJW) == 1;
@@ -116,10 +127,10 @@ k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, cons
     for (int m = 0; m < 4; ++m)
 #pragma unroll
       for (int nn = 0; nn < 4; ++nn) acc[m][nn][0] = acc[m][nn][1] = 0.0;
-    for (int kc = 0; kc < nk; ++kc, ++gi) {
+    for (int kc = 0; kc < nk; ++kc) {
       cp_async_wait<STAGES - 2>();
       __syncthreads();
-      issue(gi + STAGES - 1);
+      issue();
       if (kc == pf_kc) {  // pull the epilogue operands of this j-tile (4 components x <= 64 rows) into L2 ahead of use
         const int ncol = min(TJ, sp - jt * TJ);
         const int per_comp = ncol * (BP / 16);  // 128-byte lines
@@ -128,8 +139,9 @@ k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, cons
           prefetch_l2(tile + comp * comp_stride + (size_t)(jt * TJ + (rem >> 3)) * BP + (rem & 7) * 16);
         }
       }
-      const double* As = stage_base + (gi % STAGES) * STAGE_ELEMS;
+      const double* As = stage_base + c_stage * STAGE_ELEMS;
       const double* Bs = As + A_ELEMS;
+      c_stage = (c_stage + 1 == STAGES) ? 0 : c_stage + 1;
 #pragma unroll
       for (int ks = 0; ks < TK / 4; ++ks) {
         if (split && (ks & 1) != jw) continue;

@@ -86,15 +86,15 @@ constexpr size_t smem_bytes() { return (size_t)STAGES * STAGE_ELEMS * sizeof(dou
 }  // namespace scat
 
 // one round of the schedule of a block with s_pad / 32 row groups: which groups to stage, which tile each warp owns
-struct ScatterRound {
+struct __align__(8) ScatterRound {
   unsigned char ngroups;       // staged groups (<= MAXG)
-  unsigned char pad[3];
-  unsigned char group[8];      // 32-row group index inside the block, [0, s_pad / 32)
+  unsigned char pad[7];
+  unsigned char group[8];      // 32-row group index inside the block, [0, s_pad / 32)  (8-byte aligned: one load)
   unsigned char ta[8];         // per warp: staged slot of the row group I (0xff: idle warp)
   unsigned char tb[8];         // per warp: staged slot of the column group J >= I
   unsigned char kmask[8];      // per warp: k-steps of a chunk it multiplies (bit 0 / bit 1)
 };
-static_assert(sizeof(ScatterRound) == 36, "ScatterRound layout");
+static_assert(sizeof(ScatterRound) == 40, "ScatterRound layout");
 
 // ------------------------------------------------------------------------------------------------------------
 // K4: persistent scatter.  grid <= 2 x SMs; blocks are taken from `order` through the atomic `counter`.
@@ -131,28 +131,46 @@ k_vmat(PlanView plan, int nbf, const int* __restrict__ order, int nblk, int* __r
     const int n32 = sp >> 5;
     const ScatterRound* __restrict__ rounds = tpl + tpl_off[n32];
     const int nr = tpl_off[n32 + 1] - tpl_off[n32];
-    const int total = nr * NKC;
 
-    auto issue = [&](int gi) {
-      if (gi < total) {
-        const int r = gi / NKC, kc = gi - r * NKC;
-        const ScatterRound* rd = rounds + r;
-        const int nload = rd->ngroups * 64 * 4;  // 16-byte pieces per stage
-        double* st = stage_base + (gi % STAGES) * STAGE_ELEMS;
-        for (int idx = tid; idx < nload; idx += THREADS) {
-          const int row = idx >> 2, c16 = idx & 3;
-          const int grp = row >> 6, rr = row & 63;
-          const double* src = ((rr & 32) ? G : phi) + (size_t)(rd->group[grp] * 32 + (rr & 31)) * BP + kc * TKP + c16 * 2;
-          cp_async16(st + row * STRIDE + c16 * 2, src);
+    // Producer side of the ring: in iteration i all 256 threads copy the 64 rows x 64 B of staged group i (32 phi rows,
+    // then 32 G rows); per-thread source / destination offsets are loop invariants, the group ids of the round being
+    // issued sit packed in two registers.
+    const int rr = tid >> 2, c16 = tid & 3;
+    const double* src_base = ((rr & 32) ? G : phi) + (size_t)(rr & 31) * BP + c16 * 2;
+    const int dst_off = rr * STRIDE + c16 * 2;
+    int is_r = 0, is_kc = 0, is_stage = 0, is_ng = 0;
+    uint2 is_grp = make_uint2(0u, 0u);
+    auto load_round = [&]() {
+      if (is_r < nr) {
+        is_grp = __ldg(reinterpret_cast<const uint2*>(rounds[is_r].group));
+        is_ng = rounds[is_r].ngroups;
+      }
+    };
+    load_round();
+    auto issue = [&]() {
+      if (is_r < nr) {
+        double* st = stage_base + is_stage * STAGE_ELEMS + dst_off;
+        const double* src = src_base + is_kc * TKP;
+#pragma unroll
+        for (int i = 0; i < MAXG; ++i)
+          if (i < is_ng) {
+            const unsigned grp = ((i < 4 ? is_grp.x : is_grp.y) >> (8 * (i & 3))) & 0xffu;
+            cp_async16(st + i * GROUP_ELEMS, src + (size_t)grp * (32 * BP));
+          }
+        if (++is_kc == NKC) {
+          is_kc = 0;
+          ++is_r;
+          load_round();
         }
+        is_stage = (is_stage + 1 == STAGES) ? 0 : is_stage + 1;
       }
       cp_async_commit();
     };
 
     double acc[4][4][2];
-    issue(0);
-    issue(1);
-    int gi = 0;
+    issue();
+    issue();
+    int c_stage = 0;
     for (int r = 0; r < nr; ++r) {
       const ScatterRound* rd = rounds + r;
       const int slot_a = rd->ta[warp], slot_b = rd->tb[warp], kmask = rd->kmask[warp];
@@ -161,12 +179,13 @@ k_vmat(PlanView plan, int nbf, const int* __restrict__ order, int nblk, int* __r
       for (int m = 0; m < 4; ++m)
 #pragma unroll
         for (int nn = 0; nn < 4; ++nn) acc[m][nn][0] = acc[m][nn][1] = 0.0;
-      for (int kc = 0; kc < NKC; ++kc, ++gi) {
+      for (int kc = 0; kc < NKC; ++kc) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
-        issue(gi + STAGES - 1);
+        issue();
+        const double* st = stage_base + c_stage * STAGE_ELEMS;
+        c_stage = (c_stage + 1 == STAGES) ? 0 : c_stage + 1;
         if (active) {
-          const double* st = stage_base + (gi % STAGES) * STAGE_ELEMS;
           const double* sI = st + slot_a * GROUP_ELEMS;  // phi_I rows 0..31, G_I rows 32..63
           const double* sJ = st + slot_b * GROUP_ELEMS;
 #pragma unroll
