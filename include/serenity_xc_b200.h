@@ -100,6 +100,10 @@ const char* sxc_last_error(const sxc_ctx* ctx);
 int sxc_set_stream(sxc_ctx* ctx, void* cuda_stream);
 /* cap of the phi/grad-phi tile buffer in bytes (default: 40 % of free device memory at plan time) */
 int sxc_set_workspace_limit(sxc_ctx* ctx, int64_t bytes);
+/* One-shot: the next *_device build waits for this cudaEvent_t (passed as void*) before it first reads P - i.e. after
+ * the screening and basis kernels - so that the caller's asynchronous upload of P on another stream overlaps with them.
+ * (The host-buffer entry points do the same internally.) */
+int sxc_set_p_ready_event(sxc_ctx* ctx, void* cuda_event);
 /* per-kernel CUDA-event timing of the *_device builds (off by default: events cost a few microseconds each);
  * sxc_get_stats() then synchronises on the last build's events */
 int sxc_set_timing(sxc_ctx* ctx, int on);

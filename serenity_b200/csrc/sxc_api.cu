@@ -167,6 +167,9 @@ struct sxc_ctx {
   sxc_stats stats{};
   int launches = 0;
   bool attrs_set = false;
+  cudaEvent_t p_ready = nullptr;     // one-shot: the next build waits for it before it first reads P
+  cudaStream_t copy_stream = nullptr; // H2D of P in the host-buffer entry points (overlaps screening + basis)
+  cudaEvent_t copy_done = nullptr;
   bool timing = false;        // record events during the current build
   bool timing_device = false; // sxc_set_timing: also for the *_device entry points
   struct Stamp {
@@ -220,6 +223,32 @@ int set_kernel_attrs(sxc_ctx* ctx) {
   CU(cudaFuncSetAttribute(k_density, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CU(cudaFuncSetAttribute(k_vmat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scat::smem_bytes()));
   ctx->attrs_set = true;
+  return SXC_OK;
+}
+
+// P is first read by the density phase: a pending upload (sxc_set_p_ready_event / host-buffer entry points) is
+// awaited only there, so that it overlaps with the screening and basis kernels
+int wait_p_ready(sxc_ctx* ctx) {
+  if (ctx->p_ready) {
+    cudaEvent_t ev = ctx->p_ready;
+    ctx->p_ready = nullptr;
+    CU(cudaStreamWaitEvent(ctx->stream, ev, 0));
+  }
+  return SXC_OK;
+}
+
+// host-buffer entry points: upload on a side stream, hand its completion event to the build
+int upload_async(sxc_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (!ctx->copy_stream) {
+    CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
+  }
+  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+  return SXC_OK;
+}
+int upload_done(sxc_ctx* ctx) {
+  CU(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
+  ctx->p_ready = ctx->copy_done;
   return SXC_OK;
 }
 
@@ -650,6 +679,7 @@ int build_xc_device(sxc_ctx* ctx, int gh, int bh, int fh, int nspin, const doubl
     TRY(run_screen(ctx, g, b, p));
     for (const Chunk& c : p.chunks) {
       TRY(phase_basis(ctx, g, b, p, c));
+      TRY(wait_p_ready(ctx));
       // UNRESTRICTED: the same block data is contracted with P_alpha and P_beta (MatrixOperatorToGridTransformer.h:128-146)
       for (int sp = 0; sp < nspin; ++sp)
         TRY(phase_density(ctx, g, b, p, c, dP + sp * nb2, dens + (size_t)4 * sp * N, true, nullptr));
@@ -710,6 +740,7 @@ int build_nadd_device(sxc_ctx* ctx, int gh, int fh, int nspin, int bA, const dou
   {
     PhaseTimer t_all(ctx, T_TOTAL);
     CU(cudaMemsetAsync(dVE, 0, (nspin * nb2 + 2 + nenv) * sizeof(double), ctx->stream));
+    TRY(wait_p_ready(ctx));
 
     // environment: rho_env on the supersystem grid, summed; E[rho_env_i] (NAddEnergyHelper, NAddFuncPotential.cpp:502-516)
     std::vector<int> key(bE, bE + nenv);
@@ -786,7 +817,7 @@ int build_nadd_device(sxc_ctx* ctx, int gh, int fh, int nspin, int bA, const dou
 // ================================================================================================ C ABI
 extern "C" {
 
-int sxc_abi_version(void) { return 2; }
+int sxc_abi_version(void) { return 3; }
 
 // host-only: contiguous ranges [bounds[r], bounds[r+1]) of nearly equal summed cost
 int sxc_balance_ranges(int n, const double* cost, int world, int* bounds) {
@@ -846,6 +877,8 @@ void sxc_destroy(sxc_ctx* ctx) {
     cudaEventDestroy(st.b);
   }
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
+  if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -982,7 +1015,8 @@ int sxc_build_xc(sxc_ctx* ctx, int grid, int basis, int func, int nspin, const d
   const size_t nv = (size_t)nspin * b->nbf * b->nbf;
   CU(ctx->dP.ensure(nv * sizeof(double)));
   CU(ctx->dOut.ensure((nv + 2) * sizeof(double)));
-  CU(cudaMemcpyAsync(ctx->dP.p, P, nv * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  TRY(upload_async(ctx, ctx->dP.p, P, nv * sizeof(double)));
+  TRY(upload_done(ctx));
   int rc = build_xc_device(ctx, grid, basis, func, nspin, ctx->dP.as<double>(), thr, ctx->dOut.as<double>(), true);
   ctx->timing = false;
   if (rc != SXC_OK) return rc;
@@ -1024,14 +1058,14 @@ int sxc_build_nadd(sxc_ctx* ctx, int grid, int func, int nspin, int basis_act, c
   }
   CU(ctx->dP.ensure(total * sizeof(double)));
   CU(ctx->dOut.ensure((nvA + 2 + nenv) * sizeof(double)));
-  CU(cudaMemcpyAsync(ctx->dP.p, P_act, nvA * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  TRY(upload_async(ctx, ctx->dP.p, P_act, nvA * sizeof(double)));
   std::vector<const double*> dpe(nenv);
   for (int i = 0; i < nenv; ++i) {
     Basis* be = get_basis(ctx, basis_env[i]);
     dpe[i] = ctx->dP.as<double>() + offs[i];
-    CU(cudaMemcpyAsync(ctx->dP.as<double>() + offs[i], P_env[i], (size_t)nspin * be->nbf * be->nbf * sizeof(double),
-                       cudaMemcpyHostToDevice, ctx->stream));
+    TRY(upload_async(ctx, ctx->dP.as<double>() + offs[i], P_env[i], (size_t)nspin * be->nbf * be->nbf * sizeof(double)));
   }
+  TRY(upload_done(ctx));
   int rc = build_nadd_device(ctx, grid, func, nspin, basis_act, ctx->dP.as<double>(), nenv, basis_env, dpe.data(),
                              env_frozen, thr, ctx->dOut.as<double>(), true);
   ctx->timing = false;
@@ -1226,6 +1260,12 @@ int sxc_scalar_to_matrix(sxc_ctx* ctx, int grid, int basis, double thr, const do
   CU(cudaMemcpyAsync(h.data(), ctx->dOut.p, nb2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   for (size_t i = 0; i < nb2; ++i) V[i] += h[i];  // the reference adds into the caller's matrix
+  return SXC_OK;
+}
+
+int sxc_set_p_ready_event(sxc_ctx* ctx, void* cuda_event) {
+  if (!ctx) return SXC_ERR_INVALID;
+  ctx->p_ready = static_cast<cudaEvent_t>(cuda_event);
   return SXC_OK;
 }
 

@@ -35,7 +35,7 @@ def shard_bounds(costs, world: int):
 class ShardedBuild:
     """[V | E | N] of one XC build summed over the ranks of `group`.
 
-    local_build(d_P, d_VEN) must enqueue this rank's partial build on the current stream / device of d_VEN
+    local_build(d_P, d_VEN, p_ready_event_or_None) must enqueue this rank's partial build on the current stream / device of d_VEN
     (CUDA: XCContext.build_xc_device with the context's stream set to torch's current stream).
     """
 
@@ -49,29 +49,45 @@ class ShardedBuild:
         n = nbf * nbf
         self.d_P = torch.zeros(n, dtype=torch.float64, device=self.device)
         self.d_VEN = torch.zeros(n + ntail, dtype=torch.float64, device=self.device)
-        pin = self.device.type == "cuda"
-        self.h_P = torch.zeros(n, dtype=torch.float64, pin_memory=pin)
-        self.h_VEN = torch.zeros(n + ntail, dtype=torch.float64, pin_memory=pin)
+        cuda = self.device.type == "cuda"
+        self.h_P = torch.zeros(n, dtype=torch.float64, pin_memory=cuda)      # pinned staging buffers of the host API
+        self.h_VEN = torch.zeros(n + ntail, dtype=torch.float64, pin_memory=cuda)
+        self._copy_stream = torch.cuda.Stream(self.device) if cuda else None
+        self._p_event = torch.cuda.Event() if cuda else None
 
     # device-resident: P already in d_P, result stays in d_VEN (asynchronous on CUDA)
-    def build_device(self) -> torch.Tensor:
-        self._local(self.d_P, self.d_VEN)
+    def build_device(self, p_ready=None) -> torch.Tensor:
+        self._local(self.d_P, self.d_VEN, p_ready)
         if self.world > 1:
             dist.all_reduce(self.d_VEN, op=dist.ReduceOp.SUM, group=self.group)
         return self.d_VEN
 
+    def build_pinned(self):
+        """P has been written into the pinned buffer h_P (column-major); returns views into the pinned result buffer
+        h_VEN: (V [nb, nb], E, N).  The upload runs on a side stream and is awaited by the library only before the
+        density kernel, i.e. it overlaps with the screening and basis kernels."""
+        n = self.nbf * self.nbf
+        if self._copy_stream is not None:
+            cur = torch.cuda.current_stream(self.device)
+            self._copy_stream.wait_stream(cur)  # the previous build no longer reads d_P
+            with torch.cuda.stream(self._copy_stream):
+                self.d_P.copy_(self.h_P, non_blocking=True)
+                self._p_event.record(self._copy_stream)
+            self.build_device(self._p_event)
+            self.h_VEN.copy_(self.d_VEN, non_blocking=True)
+            cur.synchronize()
+        else:
+            self.d_P.copy_(self.h_P)
+            self.build_device()
+            self.h_VEN.copy_(self.d_VEN)
+        out = self.h_VEN.numpy()
+        return out[:n].reshape(self.nbf, self.nbf, order="F"), float(out[n]), float(out[n + 1])
+
     # host buffers in, host buffers out: what FuncPotential::getMatrix/getEnergy hand to the SCF driver
     def build(self, P: np.ndarray):
-        n = self.nbf * self.nbf
         self.h_P.numpy()[:] = np.asarray(P, dtype=np.float64).reshape(-1, order="F")
-        self.d_P.copy_(self.h_P, non_blocking=True)
-        self.build_device()
-        self.h_VEN.copy_(self.d_VEN, non_blocking=True)
-        if self.device.type == "cuda":
-            torch.cuda.current_stream(self.device).synchronize()
-        out = self.h_VEN.numpy()
-        V = out[:n].reshape(self.nbf, self.nbf, order="F").copy(order="F")
-        return V, float(out[n]), float(out[n + 1])
+        V, E, N = self.build_pinned()
+        return V.copy(order="F"), E, N
 
     @property
     def h2d_bytes(self) -> int:
@@ -85,7 +101,9 @@ class ShardedBuild:
 def cuda_local_build(ctx, grid: int, basis: int, func: int, block_ave_threshold: float = 1e-11):
     """local_build for ShardedBuild on a CUDA rank: sxc_build_xc_device on torch's current stream."""
 
-    def run(d_P: torch.Tensor, d_VEN: torch.Tensor):
+    def run(d_P: torch.Tensor, d_VEN: torch.Tensor, p_ready=None):
+        if p_ready is not None:
+            ctx.set_p_ready_event(p_ready.cuda_event)
         # torch's default stream is the legacy NULL stream (handle 0); the C ABI reads NULL as "the context's own
         # stream", so name the legacy stream explicitly (cudaStreamLegacy == (cudaStream_t)0x1)
         ctx.set_stream(torch.cuda.current_stream(d_P.device).cuda_stream or 1)

@@ -68,6 +68,9 @@ class XCContext:
     def set_workspace_limit(self, nbytes: int):
         self._check(self._lib.sxc_set_workspace_limit(self._h, int(nbytes)))
 
+    def set_p_ready_event(self, cuda_event_ptr: int):
+        self._check(self._lib.sxc_set_p_ready_event(self._h, C.c_void_p(cuda_event_ptr)))
+
     def set_timing(self, on: bool):
         self._check(self._lib.sxc_set_timing(self._h, 1 if on else 0))
 

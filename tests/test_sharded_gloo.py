@@ -32,7 +32,7 @@ def _worker(rank, world, port, out_path):
         lo, hi = int(bounds[rank]) * 128, min(int(bounds[rank + 1]) * 128, cfg.npts)
         ob, of = orc.Basis(sub.basis), orc.Functional(ids, mix)
 
-        def local_build(d_P, d_VEN):
+        def local_build(d_P, d_VEN, p_ready=None):
             P = d_P.numpy().reshape(nbf, nbf, order="F")
             V, E, ne, _ = orc.build_xc(ob, orc.Grid(cfg.xyz[lo:hi], cfg.w[lo:hi], 128), of, P)
             d_VEN[: nbf * nbf] = torch.from_numpy(V.reshape(-1, order="F").copy())
