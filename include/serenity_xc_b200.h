@@ -157,6 +157,13 @@ int sxc_build_nadd_device(sxc_ctx* ctx, int grid, int func, int nspin, int basis
                           int nenv, const int* basis_env, const double* const* d_P_env, int env_frozen,
                           double block_ave_threshold, double* d_VE /* nspin*nbA*nbA + 2 + nenv */);
 
+/* FuncPotential<SCFMode>::getGeomGradients (src/potentials/FuncPotential.cpp:114-239), SURVEY.md row f-3: the XC
+ * contribution to the nuclear gradient.  atom_of_bf[nbf] = BasisController::getAtomIndicesOfBasis() (:127); grad is the
+ * nAtoms x 3 column-major matrix the reference returns (element (A, c) at A + c * natoms), overwritten.  P as in
+ * sxc_build_xc.  With a shard set, grad is this rank's partial sum. */
+int sxc_xc_gradient(sxc_ctx* ctx, int grid, int basis, int func, int nspin, const double* P, int natoms,
+                    const int* atom_of_bf, double* grad);
+
 /* ---- stage-level entry points (the reference classes one level below the Potentials) -------------------- */
 /* DensityOnGridCalculator::calcDensityAndGradientOnGrid (DensityOnGridCalculator.cpp:55-65): host outputs [N];
  * gx/gy/gz may be NULL.  With a shard set only the owned points are filled (others 0). */

@@ -799,3 +799,88 @@ int orc_build_nadd_u(const orc_basis* bA, const double* PAa, const double* PAb, 
   free(nonneg);
   return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * row f-3  FuncPotential::getGeomGradients, potentials/FuncPotential.cpp:114-239
+ * ------------------------------------------------------------------------------------------------ */
+int orc_xc_gradient(const orc_basis* b, const orc_grid* g, const orc_functional* f, double radial_thr, int nspin,
+                    const double* Pa, const double* Pb, int natoms, const int* atom_of_bf, double* grad) {
+  const long N = g->npts;
+  const int nbf = b->nbf;
+  const int gga = orc_functional_is_gga(f);
+  const int nblocks = orc_nblocks(g);
+  /* rho[2][N], grad[2][3][N], epuv[N], vr[2][N], vg[2][3][N] (restricted uses the first halves) */
+  double* buf = (double*)calloc(17 * (size_t)N, sizeof(double));
+  if (!buf) return -1;
+  double *rho = buf, *gr = rho + 2 * N, *ep = gr + 6 * N, *vr = ep + N, *vg = vr + 2 * N;
+  const double* Ps[2] = {Pa, Pb};
+  if (nspin == 1) {
+    orc_density_on_grid(b, g, radial_thr, Pa, rho, gr, gr + N, gr + 2 * N, NULL, NULL);
+    orc_functional_on_grid(f, N, g->w, rho, gga ? gr : NULL, gr + N, gr + 2 * N, ep, vr, gga ? vg : NULL, vg + N, vg + 2 * N);
+  } else {
+    orc_density_on_grid(b, g, radial_thr, Pa, rho, gr, gr + N, gr + 2 * N, NULL, NULL);
+    orc_density_on_grid(b, g, radial_thr, Pb, rho + N, gr + 3 * N, gr + 4 * N, gr + 5 * N, NULL, NULL);
+    orc_functional_on_grid_u(f, N, g->w, rho, gga ? gr : NULL, ep, vr, gga ? vg : NULL);
+  }
+  memset(grad, 0, sizeof(double) * 3 * (size_t)natoms);
+#pragma omp parallel
+  {
+    orc_ws w;
+    ws_alloc(&w, b, g->blocksize, gga ? 2 : 1);
+    double* priv = (double*)calloc(3 * (size_t)natoms, sizeof(double)); /* gradientContrPriv, :149 */
+#pragma omp for schedule(dynamic)
+    for (int blk = 0; blk < nblocks; ++blk) {
+      const long first = (long)blk * g->blocksize;
+      int n = 0;
+      const int s = ws_block(&w, b, g, radial_thr, gga ? 2 : 1, blk, &n, NULL);
+      for (int sp = 0; sp < nspin; ++sp) {
+        const double* P = Ps[sp];
+        const double* v = vr + (size_t)sp * N + first;
+        const double* vx = vg + (size_t)(3 * sp) * N + first;
+        const double* vy = vg + (size_t)(3 * sp + 1) * N + first;
+        const double* vz = vg + (size_t)(3 * sp + 2) * N + first;
+        const double* wt = g->w + first;
+        for (int im = 0; im < s; ++im) { /* negligible functions are skipped, :170 */
+          const int mu = w.sig[im];
+          const double* fm = w.val + (size_t)mu * n;
+          const double *mx = w.d1[0] + (size_t)mu * n, *my = w.d1[1] + (size_t)mu * n, *mz = w.d1[2] + (size_t)mu * n;
+          for (int in = 0; in < s; ++in) { /* :178 */
+            const int nu = w.sig[in];
+            const int A = atom_of_bf[nu];
+            const double pre = 2.0 * P[mu + (size_t)nu * nbf]; /* :183 */
+            const double *nx = w.d1[0] + (size_t)nu * n, *ny = w.d1[1] + (size_t)nu * n, *nz = w.d1[2] + (size_t)nu * n;
+            double gx = 0.0, gy = 0.0, gz = 0.0;
+            for (int p = 0; p < n; ++p) { /* LDA-type part, :184-186 */
+              const double pm = wt[p] * v[p] * fm[p];
+              gx += pm * nx[p];
+              gy += pm * ny[p];
+              gz += pm * nz[p];
+            }
+            if (gga) { /* :188-227 */
+              const double *hxx = w.d2[0] + (size_t)nu * n, *hxy = w.d2[1] + (size_t)nu * n, *hxz = w.d2[2] + (size_t)nu * n,
+                           *hyy = w.d2[3] + (size_t)nu * n, *hyz = w.d2[4] + (size_t)nu * n, *hzz = w.d2[5] + (size_t)nu * n;
+              for (int p = 0; p < n; ++p) {
+                const double px = wt[p] * vx[p], py = wt[p] * vy[p], pz = wt[p] * vz[p];
+                gx += px * (fm[p] * hxx[p] + mx[p] * nx[p]) + py * (fm[p] * hxy[p] + my[p] * nx[p]) +
+                      pz * (fm[p] * hxz[p] + mz[p] * nx[p]);
+                gy += px * (fm[p] * hxy[p] + mx[p] * ny[p]) + py * (fm[p] * hyy[p] + my[p] * ny[p]) +
+                      pz * (fm[p] * hyz[p] + mz[p] * ny[p]);
+                gz += px * (fm[p] * hxz[p] + mx[p] * nz[p]) + py * (fm[p] * hyz[p] + my[p] * nz[p]) +
+                      pz * (fm[p] * hzz[p] + mz[p] * nz[p]);
+              }
+            }
+            priv[A] -= pre * gx;
+            priv[A + natoms] -= pre * gy;
+            priv[A + 2 * natoms] -= pre * gz;
+          }
+        }
+      }
+    }
+#pragma omp critical
+    for (int i = 0; i < 3 * natoms; ++i) grad[i] += priv[i]; /* :231-232 */
+    free(priv);
+    ws_free(&w);
+  }
+  free(buf);
+  return 0;
+}

@@ -123,6 +123,12 @@ int orc_build_nadd(const orc_basis* bA, const double* PA, int nenv, const orc_ba
                    const double* const* PE, const orc_grid* g, const orc_functional* f, double radial_thr,
                    double block_ave_thr, double* VA, double* E_nadd, double* E_parts);
 
+/* row f-3  FuncPotential<RESTRICTED / UNRESTRICTED>::getGeomGradients (potentials/FuncPotential.cpp:114-239): the
+ * reference's double loop over the significant functions of every block, with second basis-function derivatives for GGAs.
+ * nspin = 1: Pa = total density matrix, Pb ignored.  grad: natoms x 3 column-major, overwritten. */
+int orc_xc_gradient(const orc_basis* b, const orc_grid* g, const orc_functional* f, double radial_thr, int nspin,
+                    const double* Pa, const double* Pb, int natoms, const int* atom_of_bf, double* grad);
+
 /* ---- UNRESTRICTED (SCFMode = UNRESTRICTED: alpha/beta pairs, data/SpinPolarizedData.h) ------------------------ */
 /* pointwise spin-polarised kernel: F and dF/d(rho_a, rho_b, s_aa, s_ab, s_bb) */
 int orc_basic_functional_u(int id, double ra, double rb, double gaa, double gab, double gbb, double* F, double* d5);

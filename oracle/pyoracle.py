@@ -237,3 +237,17 @@ def build_nadd_u(basis_a: Basis, Pa_pair, env, grid: Grid, func: Functional, rad
     if rc != 0:
         raise MemoryError("orc_build_nadd_u failed")
     return (Va, Vb), E.value, parts
+
+
+def xc_gradient(basis: Basis, grid: Grid, func: Functional, P, atom_of_bf, natoms: int, radial_thr=1e-9):
+    """P: matrix (RESTRICTED) or (P_alpha, P_beta) -> [natoms, 3]."""
+    unres = isinstance(P, (tuple, list))
+    Pa = np.asfortranarray(P[0] if unres else P, dtype=np.float64)
+    Pb = np.asfortranarray(P[1], dtype=np.float64) if unres else None
+    amap = np.ascontiguousarray(atom_of_bf, dtype=np.int32)
+    grad = np.zeros((natoms, 3), order="F")
+    rc = lib().orc_xc_gradient(C.byref(basis.c), C.byref(grid.c), C.byref(func.c), C.c_double(radial_thr),
+                               2 if unres else 1, _p(Pa), _p(Pb), natoms, _p(amap), _p(grad))
+    if rc != 0:
+        raise MemoryError("orc_xc_gradient failed")
+    return grad

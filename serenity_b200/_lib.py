@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libserenity_xc_b200.so")
 SYMBOLS = [
     "sxc_create", "sxc_destroy", "sxc_last_error", "sxc_set_stream", "sxc_set_workspace_limit", "sxc_set_timing", "sxc_set_p_ready_event", "sxc_set_grid",
     "sxc_set_grid_shard", "sxc_add_basis", "sxc_set_functional", "sxc_build_xc", "sxc_build_xc_device",
-    "sxc_build_nadd", "sxc_build_nadd_device", "sxc_density_on_grid", "sxc_basis_on_grid",
+    "sxc_build_nadd", "sxc_build_nadd_device", "sxc_xc_gradient", "sxc_density_on_grid", "sxc_basis_on_grid",
     "sxc_functional_on_grid", "sxc_functional_on_grid_u", "sxc_scalar_to_matrix", "sxc_get_stats", "sxc_balance_ranges", "sxc_abi_version",
 ]
 
@@ -70,6 +70,7 @@ def load():
     lib.sxc_build_xc_device.argtypes = [vp, i, i, i, i, vp, d, vp]
     lib.sxc_build_nadd.argtypes = [vp, i, i, i, i, vp, i, vp, vp, i, d, vp, vp]
     lib.sxc_build_nadd_device.argtypes = [vp, i, i, i, i, vp, i, vp, vp, i, d, vp]
+    lib.sxc_xc_gradient.argtypes = [vp, i, i, i, i, vp, i, vp, vp]
     lib.sxc_density_on_grid.argtypes = [vp, i, i, vp, vp, vp, vp, vp]
     lib.sxc_basis_on_grid.argtypes = [vp, i, i, i, vp, vp, vp, vp, vp, ip]
     lib.sxc_functional_on_grid.argtypes = [vp, i, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(d)]

@@ -27,7 +27,7 @@ namespace sxc {
 // K3b: per block: weights x potential, block-average test, G in place of d_x phi.  256 threads.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_form_g(GridView g, PlanView plan, const int* __restrict__ order, double block_ave_thr,
+k_form_g(GridView g, PlanView plan, const int* __restrict__ order, double block_ave_thr, double a_scale,
          const double* __restrict__ v_rho, const double* __restrict__ v_gx, const double* __restrict__ v_gy,
          const double* __restrict__ v_gz, double* __restrict__ phi_buf, int* __restrict__ skip_flag) {
   __shared__ double sa[BP], sx[BP], sy[BP], sz[BP];
@@ -64,7 +64,7 @@ k_form_g(GridView g, PlanView plan, const int* __restrict__ order, double block_
   const size_t comp_stride = (size_t)sp * BP;
   double* __restrict__ tile = phi_buf + plan.phi_off[q];
   const int p = tid & (BP - 1);
-  const double a = 0.5 * sa[p], bx = sx[p], by = sy[p], bz = sz[p];
+  const double a = a_scale * sa[p], bx = sx[p], by = sy[p], bz = sz[p];  // a_scale = 1/2: the T + T^T trick of :281
   for (int c = tid >> 7; c < sp; c += 2) {
     const size_t i = (size_t)c * BP + p;
     tile[4 * comp_stride + i] = bx * tile[comp_stride + i] + by * tile[2 * comp_stride + i] +

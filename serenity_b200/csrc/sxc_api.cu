@@ -24,6 +24,7 @@
 #include "density_kernel.cuh"
 #include "functionals.cuh"
 #include "scatter_kernel.cuh"
+#include "gradient_kernels.cuh"
 #include "sxc_common.cuh"
 
 using namespace sxc;
@@ -221,6 +222,7 @@ Basis* get_basis(sxc_ctx* ctx, int h) { return (h >= 0 && h < (int)ctx->bases.si
 int set_kernel_attrs(sxc_ctx* ctx) {
   if (ctx->attrs_set) return SXC_OK;
   CU(cudaFuncSetAttribute(k_density, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CU(cudaFuncSetAttribute(k_grad_contract, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CU(cudaFuncSetAttribute(k_vmat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scat::smem_bytes()));
   ctx->attrs_set = true;
   return SXC_OK;
@@ -410,11 +412,13 @@ const std::vector<ScatterRound>& scatter_schedule(sxc_ctx* ctx, int n32) {
   return ctx->scatter_tpl[n32] = out;
 }
 
-int get_plan(sxc_ctx* ctx, int gh, int bh, Plan** out) {
+constexpr int GRAD_PLAN = 1 << 20;  // key offset of the 8-slot plans of the gradient path
+
+int get_plan(sxc_ctx* ctx, int gh, int bh, Plan** out, int comps = TILE_COMPS) {
   Grid* g = get_grid(ctx, gh);
   Basis* b = get_basis(ctx, bh);
   if (!g || !b) return fail(ctx, SXC_ERR_INVALID, "invalid grid (%d) or basis (%d) handle", gh, bh);
-  auto key = std::make_pair(gh, bh);
+  auto key = std::make_pair(gh, bh + (comps == TILE_COMPS ? 0 : GRAD_PLAN));
   auto it = ctx->plans.find(key);
   if (it != ctx->plans.end()) {
     *out = it->second.get();
@@ -474,7 +478,7 @@ int get_plan(sxc_ctx* ctx, int gh, int bh, Plan** out) {
     const int sp = std::max(SPAD, ((s + SPAD - 1) / SPAD) * SPAD);
     p.h_s_pad[q] = sp;
     p.s_pad_max = std::max(p.s_pad_max, sp);
-    const size_t tile = (size_t)TILE_COMPS * sp * BP;
+    const size_t tile = (size_t)comps * sp * BP;
     if (cur.nslots > 0 && (int64_t)((cur.doubles + tile) * sizeof(double)) > limit) {
       p.chunks.push_back(cur);
       cur = Chunk();
@@ -620,8 +624,8 @@ int phase_scatter(sxc_ctx* ctx, const Grid& g, const Basis& b, const Plan& p, co
   if (c.nslots == 0) return SXC_OK;
   {
     PhaseTimer t(ctx, SXC_T_FORM_G);
-    k_form_g<<<c.nslots, 256, 0, ctx->stream>>>(g.view(), p.view(), p.order.as<int>() + c.order_off, block_ave_thr, pot4,
-                                                gga ? pot4 + N : nullptr, gga ? pot4 + 2 * N : nullptr,
+    k_form_g<<<c.nslots, 256, 0, ctx->stream>>>(g.view(), p.view(), p.order.as<int>() + c.order_off, block_ave_thr, 0.5,
+                                                pot4, gga ? pot4 + N : nullptr, gga ? pot4 + 2 * N : nullptr,
                                                 gga ? pot4 + 3 * N : nullptr, ctx->phi.as<double>(), p.skip.as<int>());
     LAUNCH_CHECK();
   }
@@ -806,6 +810,70 @@ int build_nadd_device(sxc_ctx* ctx, int gh, int fh, int nspin, int bA, const dou
     for (int sp = 0; sp < nspin; ++sp) TRY(finish_matrix(ctx, ba->nbf, dVE + sp * nb2));
     TRY(reduce_to(ctx, parts, g.nlit, dVE + nspin * nb2));
     TRY(reduce_to(ctx, parts + g.nlit, g.nlit, dVE + nspin * nb2 + 1));
+  }
+  ctx->timing = false;
+  ctx->stats.kernel_launches = ctx->launches - launches0;
+  return SXC_OK;
+}
+
+// XC nuclear gradient (row f-3): FuncPotential<SCFMode>::getGeomGradients (FuncPotential.cpp:114-239).
+// d_gfunc [nbf][3] receives t[nu, c] (gradient_kernels.cuh); the caller folds functions into atoms with the factor -2.
+int build_gradient_device(sxc_ctx* ctx, int gh, int bh, int fh, int nspin, const double* dP, double* d_gfunc) {
+  if (nspin != 1 && nspin != 2) return fail(ctx, SXC_ERR_INVALID, "nspin must be 1 (RESTRICTED) or 2 (UNRESTRICTED)");
+  if (fh < 0 || fh >= (int)ctx->funcs.size()) return fail(ctx, SXC_ERR_INVALID, "invalid functional handle %d", fh);
+  Plan* pp = nullptr;
+  TRY(get_plan(ctx, gh, bh, &pp, GRAD_TILE_COMPS));
+  Plan& p = *pp;
+  Grid& g = *get_grid(ctx, gh);
+  Basis& b = *get_basis(ctx, bh);
+  const FuncView f = ctx->funcs[fh];
+  TRY(ensure_point_arrays(ctx, g, false, nspin));
+  ctx->stats = p.stats;
+  begin_timing(ctx, ctx->timing_device);
+  const int launches0 = ctx->launches;
+  const size_t nb2 = (size_t)b.nbf * b.nbf;
+  const long N = g.npts;
+  double* parts = g.parts.as<double>();
+  double* dens = g.dens.as<double>();
+  double* pot = g.pot.as<double>();
+  {
+    PhaseTimer t_all(ctx, T_TOTAL);
+    CU(cudaMemsetAsync(d_gfunc, 0, (size_t)b.nbf * 3 * sizeof(double), ctx->stream));
+    CU(cudaMemsetAsync(parts, 0, (size_t)3 * std::max(g.nlit, 1) * sizeof(double), ctx->stream));
+    TRY(run_screen(ctx, g, b, p));
+    for (const Chunk& c : p.chunks) {
+      if (c.nslots == 0) continue;
+      TRY(phase_basis(ctx, g, b, p, c));
+      TRY(wait_p_ready(ctx));
+      for (int sp = 0; sp < nspin; ++sp)
+        TRY(phase_density(ctx, g, b, p, c, dP + sp * nb2, dens + (size_t)4 * sp * N, true, nullptr));
+      TRY(phase_functional(ctx, g, p, c, f, nspin, dens, 1.0, 0, pot, parts, parts + g.nlit));
+      if (f.ncomp == 0) continue;
+      for (int sp = 0; sp < nspin; ++sp) {
+        const double* pot4 = pot + (size_t)4 * sp * N;
+        const bool gga = f.gga != 0;
+        {  // K = a phi + b . grad phi into slot 4 (no block-average test in the gradient: threshold 0)
+          PhaseTimer t(ctx, SXC_T_FORM_G);
+          k_form_g<<<c.nslots, 256, 0, ctx->stream>>>(g.view(), p.view(), p.order.as<int>() + c.order_off, 0.0, 1.0, pot4,
+                                                      gga ? pot4 + N : nullptr, gga ? pot4 + 2 * N : nullptr,
+                                                      gga ? pot4 + 3 * N : nullptr, ctx->phi.as<double>(), p.skip.as<int>());
+          LAUNCH_CHECK();
+        }
+        PhaseTimer t(ctx, SXC_T_SCATTER);
+        k_grad_contract<<<c.nslots, dens::THREADS, dens::smem_bytes(p.s_pad_max), ctx->stream>>>(
+            p.view(), b.nbf, dP + sp * nb2, p.order.as<int>() + c.order_off, ctx->phi.as<double>(), 4, 1, d_gfunc);
+        LAUNCH_CHECK();
+        if (gga) {
+          k_hessq<<<c.nslots, BASIS_GROUPS * BP, 0, ctx->stream>>>(g.view(), b.view(), p.view(), c.slot0,
+                                                                   p.order.as<int>() + c.order_off, pot4 + N, pot4 + 2 * N,
+                                                                   pot4 + 3 * N, ctx->phi.as<double>());
+          LAUNCH_CHECK();
+          k_grad_contract<<<c.nslots, dens::THREADS, dens::smem_bytes(p.s_pad_max), ctx->stream>>>(
+              p.view(), b.nbf, dP + sp * nb2, p.order.as<int>() + c.order_off, ctx->phi.as<double>(), 0, 5, d_gfunc);
+          LAUNCH_CHECK();
+        }
+      }
+    }
   }
   ctx->timing = false;
   ctx->stats.kernel_launches = ctx->launches - launches0;
@@ -1272,6 +1340,31 @@ int sxc_set_p_ready_event(sxc_ctx* ctx, void* cuda_event) {
 int sxc_set_timing(sxc_ctx* ctx, int on) {
   if (!ctx) return SXC_ERR_INVALID;
   ctx->timing_device = on != 0;
+  return SXC_OK;
+}
+
+int sxc_xc_gradient(sxc_ctx* ctx, int grid, int basis, int func, int nspin, const double* P, int natoms,
+                    const int* atom_of_bf, double* grad) {
+  if (!ctx || !P || !grad || !atom_of_bf || natoms <= 0) return fail(ctx, SXC_ERR_INVALID, "sxc_xc_gradient: bad arguments");
+  if (nspin != 1 && nspin != 2) return fail(ctx, SXC_ERR_INVALID, "nspin must be 1 or 2");
+  Basis* b = get_basis(ctx, basis);
+  if (!b) return fail(ctx, SXC_ERR_INVALID, "invalid basis handle %d", basis);
+  for (int i = 0; i < b->nbf; ++i)
+    if (atom_of_bf[i] < 0 || atom_of_bf[i] >= natoms) return fail(ctx, SXC_ERR_INVALID, "atom_of_bf[%d] out of range", i);
+  CU(cudaSetDevice(ctx->device));
+  const size_t nv = (size_t)nspin * b->nbf * b->nbf;
+  CU(ctx->dP.ensure(nv * sizeof(double)));
+  CU(ctx->dOut.ensure((size_t)b->nbf * 3 * sizeof(double)));
+  TRY(upload_async(ctx, ctx->dP.p, P, nv * sizeof(double)));
+  TRY(upload_done(ctx));
+  TRY(build_gradient_device(ctx, grid, basis, func, nspin, ctx->dP.as<double>(), ctx->dOut.as<double>()));
+  std::vector<double> t((size_t)b->nbf * 3);
+  CU(cudaMemcpyAsync(t.data(), ctx->dOut.p, t.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  collect_timers(ctx);
+  std::fill(grad, grad + (size_t)natoms * 3, 0.0);
+  for (int nu = 0; nu < b->nbf; ++nu)  // g[atom(nu), c] = -2 t[nu, c], Eigen nAtoms x 3 column-major
+    for (int c = 0; c < 3; ++c) grad[atom_of_bf[nu] + (size_t)c * natoms] -= 2.0 * t[(size_t)nu * 3 + c];
   return SXC_OK;
 }
 

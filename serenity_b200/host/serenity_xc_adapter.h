@@ -117,12 +117,16 @@ class GridController : public Notifying {
 struct ShellTable {
   std::vector<int> l, pure, nprim, firstBf;          // per shell (firstBf = extendedIndex)
   std::vector<double> centre, alpha, coeff, normfac;  // 3 per shell | per primitive (renormalised) | per function
+  std::vector<int> atomOfBf;                          // BasisController::getAtomIndicesOfBasis() (gradients only)
+  int nAtoms = 0;
 };
 class BasisController {
  public:
   BasisController(ShellTable t, int nBasisFunctions, double radialThreshold = 1e-9)
     : _t(std::move(t)), _nbf(nBasisFunctions), _thr(radialThreshold) {}
   unsigned int getNBasisFunctions() const { return (unsigned int)_nbf; }
+  const std::vector<int>& getAtomIndicesOfBasis() const { return _t.atomOfBf; }
+  int getNAtoms() const { return _t.nAtoms; }
   int handle(const B200::XCDevice& dev) {
     if (_handle < 0)
       dev.check(sxc_add_basis(dev.get(), (int)_t.l.size(), _t.l.data(), _t.pure.data(), _t.nprim.data(), _t.firstBf.data(),
@@ -215,8 +219,15 @@ class FuncPotential : public Potential<SCFMode>, public ObjectSensitive {
     if (!_potential) getMatrix();
     return _energy;
   }
-  Matrix getGeomGradients() override final {
-    throw SerenityError("FuncPotential::getGeomGradients is not part of the B200 hot path (SURVEY.md row f-3)");
+  Matrix getGeomGradients() override final {  // FuncPotential.cpp:114-239
+    auto basis = _dMatController->getBasisController();
+    if (basis->getNAtoms() <= 0 || basis->getAtomIndicesOfBasis().size() != basis->getNBasisFunctions())
+      throw SerenityError("FuncPotential::getGeomGradients: the basis carries no atom indices");
+    Matrix grad(basis->getNAtoms(), 3);
+    _dev->check(sxc_xc_gradient(_dev->get(), _grid->handle(*_dev), basis->handle(*_dev), _func, detail::nspin<SCFMode>(),
+                                _dMatController->getDensityMatrix().data(), basis->getNAtoms(),
+                                basis->getAtomIndicesOfBasis().data(), grad.data()));
+    return grad;
   }
   void notify() override final { _potential = nullptr; }  // FuncPotential.h:107-109
   Functional getFunctional() { return _functional; }
@@ -287,7 +298,7 @@ class NAddFuncPotential : public Potential<SCFMode>, public ObjectSensitive {
     return _energy;
   }
   Matrix getGeomGradients() override final {
-    throw SerenityError("NAddFuncPotential::getGeomGradients is not part of the B200 hot path (SURVEY.md row f-3)");
+    throw SerenityError("NAddFuncPotential::getGeomGradients is not implemented on the B200 path yet (SURVEY.md row f-3)");
   }
   void notify() override final { _potential = nullptr; }
   const std::vector<double>& getEnergyParts() const { return _energyParts; }

@@ -117,3 +117,15 @@ def build_shell_table(symbols, coords_bohr, basis_name: str, spherical: bool = T
             shells.append({"l": sh["l"], "pure": spherical, "exps": sh["exps"], "coefs": sh["coefs"],
                            "centre": xyz.tolist()})
     return shell_table_from_list(shells)
+
+
+def atom_indices_of_basis(tab: ShellTable, coords_bohr) -> np.ndarray:
+    """BasisController::getAtomIndicesOfBasis (used by FuncPotential::getGeomGradients, FuncPotential.cpp:127):
+    index of the atom every basis function sits on (shell centre == atom position)."""
+    coords = np.asarray(coords_bohr, dtype=np.float64)
+    out = np.zeros(tab.nbf, dtype=np.int32)
+    for sh in range(tab.nshell):
+        atom = int(np.argmin(np.linalg.norm(coords - tab.centre[sh], axis=1)))
+        n = nfunc(int(tab.l[sh]), bool(tab.pure[sh]))
+        out[tab.first_bf[sh]: tab.first_bf[sh] + n] = atom
+    return out

@@ -144,6 +144,14 @@ class XCContext:
                                                     _ptr(be), pp, 1 if env_frozen else 0, block_ave_threshold,
                                                     C.c_void_p(d_VE)))
 
+    def xc_gradient(self, grid, basis, func, P, atom_of_bf, natoms: int, nspin: int = 1):
+        """FuncPotential::getGeomGradients: [natoms, 3] XC contribution to the nuclear gradient."""
+        P = _spin_pack(P) if nspin == 2 else np.asfortranarray(P, dtype=np.float64)
+        amap = np.ascontiguousarray(atom_of_bf, dtype=np.int32)
+        grad = np.zeros((natoms, 3), order="F")
+        self._check(self._lib.sxc_xc_gradient(self._h, grid, basis, func, nspin, _ptr(P), natoms, _ptr(amap), _ptr(grad)))
+        return grad
+
     # ---- stage level
     def density_on_grid(self, grid, basis, P, npts: int, gradient: bool = True):
         P = np.asfortranarray(P, dtype=np.float64)

@@ -36,6 +36,8 @@ static std::shared_ptr<BasisController> readBasis(std::ifstream& f) {
   t.alpha = rd<double>(f);
   t.coeff = rd<double>(f);
   t.normfac = rd<double>(f);
+  t.atomOfBf = rd<int>(f);
+  t.nAtoms = t.atomOfBf.empty() ? 0 : *std::max_element(t.atomOfBf.begin(), t.atomOfBf.end()) + 1;
   const int nbf = (int)t.normfac.size();
   return std::make_shared<BasisController>(std::move(t), nbf);
 }
@@ -101,14 +103,17 @@ int main(int argc, char** argv) {
     wr(out, naddXC->getMatrix().data(), (int64_t)nA * nA);
     e = naddXC->getEnergy(PA2);
     wr(out, &e, 1);
+    // XC nuclear gradient of the active system (FuncPotential_test.cpp:234-330 pattern)
+    Matrix grad = pot->getGeomGradients();
+    wr(out, grad.data(), (int64_t)grad.rows() * 3);
     // error convention: SerenityError, as the reference throws
     bool threw = false;
     try {
-      pot->getGeomGradients();
+      naddXC->getGeomGradients();
     } catch (const SerenityError&) {
       threw = true;
     }
-    if (!threw) throw SerenityError("getGeomGradients must throw");
+    if (!threw) throw SerenityError("NAddFuncPotential::getGeomGradients must throw");
   } catch (const std::exception& e) {
     std::cerr << "host_adapter_test failed: " << e.what() << "\n";
     return 1;

@@ -32,9 +32,11 @@ def _w(f, a, dtype):
     f.write(a.tobytes())
 
 
-def _basis(f, t):
+def _basis(f, t, coords):
+    from serenity_b200.inputs.basis import atom_indices_of_basis
     for a, dt in ((t.l, np.int32), (t.pure, np.int32), (t.nprim, np.int32), (t.first_bf, np.int32), (t.centre, np.float64),
-                  (t.alpha, np.float64), (t.coeff, np.float64), (t.normfac, np.float64)):
+                  (t.alpha, np.float64), (t.coeff, np.float64), (t.normfac, np.float64),
+                  (atom_indices_of_basis(t, coords), np.int32)):
         _w(f, a, dt)
 
 
@@ -60,8 +62,8 @@ def test_cpp_potentials_match_oracle(tmp_path):
         for ids, mix in (xc, kin):
             _w(f, ids, np.int32)
             _w(f, mix, np.float64)
-        _basis(f, act.basis)
-        _basis(f, env.basis)
+        _basis(f, act.basis, act.coords)
+        _basis(f, env.basis, env.coords)
         _w(f, act.P.reshape(-1, order="F"), np.float64)
         _w(f, env.P.reshape(-1, order="F"), np.float64)
         _w(f, PA2.reshape(-1, order="F"), np.float64)
@@ -70,6 +72,7 @@ def test_cpp_potentials_match_oracle(tmp_path):
     nA = act.basis.nbf
     with open(fout, "rb") as f:
         got = [(_r(f, (nA, nA)), _r(f)) for _ in range(5)]
+        grad = _r(f, (len(act.symbols), 3))
     og = orc.Grid(cfg.xyz, cfg.w, 128)
     bA, bE = orc.Basis(act.basis), orc.Basis(env.basis)
 
@@ -84,3 +87,6 @@ def test_cpp_potentials_match_oracle(tmp_path):
     want = [ks(act.P), nadd(act.P, xc), nadd(act.P, kin), ks(PA2), nadd(PA2, xc)]
     for (V, E), (Vr, Er) in zip(got, want):
         assert np.abs(V - Vr).max() <= 1e-8 and abs(E - Er) <= 1e-9
+    from serenity_b200.inputs.basis import atom_indices_of_basis
+    grad_ref = orc.xc_gradient(bA, og, orc.Functional(*xc), PA2, atom_indices_of_basis(act.basis, act.coords), len(act.symbols))
+    assert np.abs(grad - grad_ref).max() <= 1e-9
