@@ -48,6 +48,8 @@ def parse_args():
                     help="tetracene | water64 | peptide | h2o | water8 (serenity_b200.inputs.make_config)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--emulate-world", type=int, default=0,
+                    help="development aid: time rank 0's shard of a W-rank run on one GPU (no collective)")
     return ap.parse_args()
 
 
@@ -229,6 +231,8 @@ def run_b200(args):
     g = ctx.set_grid(cfg.xyz, cfg.w, 128)
     if world > 1:
         ctx.set_grid_shard(g, rank, world)
+    elif args.emulate_world > 1:
+        ctx.set_grid_shard(g, 0, args.emulate_world)
     b = ctx.add_basis(sub.basis, 1e-9)
     f = ctx.set_functional(ids, mix)
     sb = ShardedBuild(nbf, cuda_local_build(ctx, g, b, f, 1e-11), dev)
@@ -270,8 +274,8 @@ def run_b200(args):
         sb.h_P.numpy()[:] = P.reshape(-1, order="F")  # the caller's P lives in the pinned staging buffer
         ms_e2e, _, t1 = timed(sb.build_pinned, args.steps, args.warmup)
         e2e = {"value": cfg.npts / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-               "h2d_bytes_per_step": sb.h2d_bytes * world, "d2h_bytes_per_step": sb.d2h_bytes * world,
-               "api": "ShardedBuild.build_pinned: pinned host P -> H2D (side stream, awaited before k_density) -> sxc_build_xc_device -> all_reduce -> D2H [V|E|N] on every rank -> synchronize"}
+               "h2d_bytes_per_step": sb.h2d_bytes, "d2h_bytes_per_step": sb.d2h_bytes,
+               "api": "ShardedBuild.build_pinned: pinned host P -> H2D (one slice per rank + all-gather; side stream, awaited before k_density) -> sxc_build_xc_device -> all_reduce -> D2H [V|E|N] on rank 0, [E|N] elsewhere -> synchronize"}
     clocks = sampler.stop(t0, t1) if sampler else None  # samples span both timed regions (device-resident and e2e)
 
     # per-kernel CUDA-event times (separate short pass: the events cost a few microseconds per kernel)

@@ -36,7 +36,7 @@ constexpr size_t smem_bytes(int s_pad_max) {
 }  // namespace dens
 
 __global__ void __launch_bounds__(dens::THREADS, 2)
-k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, const int* __restrict__ order,
+k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, const WorkItem* __restrict__ items,
           const double* __restrict__ phi_buf, double* __restrict__ rho, double* __restrict__ gx,
           double* __restrict__ gy, double* __restrict__ gz, int* __restrict__ nonneg) {
   using namespace dens;
@@ -45,7 +45,8 @@ k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, cons
   double* red = stage_base + STAGES * STAGE_ELEMS;          // [NJW][128][4]
   int* sig = reinterpret_cast<int*>(red + NJW * BP * 4);    // [s_pad + TJ]
 
-  const int q = order[blockIdx.x];
+  const WorkItem item = items[blockIdx.x];
+  const int q = item.q;
   const int blk = plan.block_id[q];
   const long first = (long)blk * g.blocksize;
   const int n = (int)min((long)g.blocksize, g.npts - first);
@@ -72,7 +73,9 @@ k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, cons
 
   const int nk = sp / TK;                 // K chunks per j-tile
   const int n32 = sp / 32;                // 32-function column groups
-  const int njt = (n32 + NJW - 1) / NJW;  // j-tiles of 64
+  const int njt_all = (n32 + NJW - 1) / NJW;  // j-tiles of 64 of the block
+  const int jt_begin = item.begin, njt = item.end;  // this CTA's segment of them (normally all)
+  const bool partial = jt_begin != 0 || njt != njt_all;
   const int pw = warp & 3, jw = warp >> 2;
   const int lr = lane >> 2, lc = lane & 3;
 
@@ -82,7 +85,7 @@ k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, cons
   const int a_dst = (tid >> 6) * A_STRIDE + (tid & 63) * 2;
   const int bk = tid & (TK - 1), bj = tid >> 4;                           // gather: k = bk, j = bj + 16 i
   const int b_dst = A_ELEMS + bj * B_STRIDE + bk;
-  int is_jt = 0, is_kc = 0, is_stage = 0;
+  int is_jt = jt_begin, is_kc = 0, is_stage = 0;
   int colbase[4] = {0, 0, 0, 0};  // sig[j] * nbf of this thread's four columns of the j-tile being issued
   auto load_colbase = [&]() {
     if (is_jt < njt) {  // (sig holds s_pad + TJ entries: nothing to read past the last j-tile)
@@ -119,7 +122,7 @@ k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, cons
   issue();
   issue();
   int c_stage = 0;
-  for (int jt = 0; jt < njt; ++jt) {
+  for (int jt = jt_begin; jt < njt; ++jt) {
     // a last j-tile with one 32-function group: both function-group warps work on it, on alternating k-steps
     const bool split = (n32 - jt * NJW) == 1;
     const int cg = split ? 0 : jw;
@@ -212,11 +215,20 @@ k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, cons
       r2 += a[2];
       r3 += a[3];
     }
-    rho[first + tid] = r0;
-    if (gx) {
-      gx[first + tid] = 2.0 * r1;
-      gy[first + tid] = 2.0 * r2;
-      gz[first + tid] = 2.0 * r3;
+    if (partial) {  // several CTAs share the block: the (pre-zeroed) outputs are accumulated
+      atomicAdd(rho + first + tid, r0);
+      if (gx) {
+        atomicAdd(gx + first + tid, 2.0 * r1);
+        atomicAdd(gy + first + tid, 2.0 * r2);
+        atomicAdd(gz + first + tid, 2.0 * r3);
+      }
+    } else {
+      rho[first + tid] = r0;
+      if (gx) {
+        gx[first + tid] = 2.0 * r1;
+        gy[first + tid] = 2.0 * r2;
+        gz[first + tid] = 2.0 * r3;
+      }
     }
   }
 }

@@ -97,10 +97,11 @@ struct __align__(8) ScatterRound {
 static_assert(sizeof(ScatterRound) == 40, "ScatterRound layout");
 
 // ------------------------------------------------------------------------------------------------------------
-// K4: persistent scatter.  grid <= 2 x SMs; blocks are taken from `order` through the atomic `counter`.
+// K4: persistent scatter.  grid <= 2 x SMs; work items (blocks, or segments of a block's rounds when the shard is small)
+// are taken from `items` through the atomic `counter`.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(scat::THREADS, 2)
-k_vmat(PlanView plan, int nbf, const int* __restrict__ order, int nblk, int* __restrict__ counter,
+k_vmat(PlanView plan, int nbf, const WorkItem* __restrict__ items, int nitems, int* __restrict__ counter,
        const int* __restrict__ skip_flag, const ScatterRound* __restrict__ tpl, const int* __restrict__ tpl_off,
        const double* __restrict__ phi_buf, double* __restrict__ W) {
   using namespace scat;
@@ -116,8 +117,9 @@ k_vmat(PlanView plan, int nbf, const int* __restrict__ order, int nblk, int* __r
     if (tid == 0) s_next = atomicAdd(counter, 1);
     __syncthreads();
     const int qi = s_next;
-    if (qi >= nblk) break;
-    const int q = order[qi];
+    if (qi >= nitems) break;
+    const WorkItem item = items[qi];
+    const int q = item.q;
     if (skip_flag[q]) continue;
     const int s = plan.s[q];
     const int sp = plan.s_pad[q];
@@ -129,8 +131,8 @@ k_vmat(PlanView plan, int nbf, const int* __restrict__ order, int nblk, int* __r
     const double* __restrict__ G = tile + 4 * comp_stride;  // G slot of the tile
     const int* __restrict__ sig = plan.sig_bf + (size_t)q * plan.nbf_pad;
     const int n32 = sp >> 5;
-    const ScatterRound* __restrict__ rounds = tpl + tpl_off[n32];
-    const int nr = tpl_off[n32 + 1] - tpl_off[n32];
+    const ScatterRound* __restrict__ rounds = tpl + tpl_off[n32] + item.begin;  // this item's segment of the rounds
+    const int nr = item.end - item.begin;
 
     // Producer side of the ring: in iteration i all 256 threads copy the 64 rows x 64 B of staged group i (32 phi rows,
     // then 32 G rows); per-thread source / destination offsets are loop invariants, the group ids of the round being

@@ -117,6 +117,9 @@ struct Chunk {
   int slot0 = 0, nslots = 0;
   size_t doubles = 0;     // tile buffer size of the chunk
   int order_off = 0;      // offset into Plan::order (sorted slots of this chunk)
+  int ditem_off = 0, nditems = 0;  // k_density work items
+  int vitem_off = 0, nvitems = 0;  // k_vmat work items
+  bool dens_split = false;         // some block's j-tiles are spread over several CTAs (outputs accumulated)
 };
 
 struct Plan {
@@ -124,7 +127,7 @@ struct Plan {
   int nown = 0;
   int nbf_pad = 0;
   int s_pad_max = 0;
-  DevMem block_id, nsig_shell, s, sig_shell, sig_c0, sig_bf, s_pad, phi_off, order, tpl, tpl_off, skip;
+  DevMem block_id, nsig_shell, s, sig_shell, sig_c0, sig_bf, s_pad, phi_off, order, tpl, tpl_off, skip, ditems, vitems;
   std::vector<int> h_s, h_s_pad;
   std::vector<Chunk> chunks;
   sxc_stats stats{};
@@ -521,6 +524,53 @@ int get_plan(sxc_ctx* ctx, int gh, int bh, Plan** out, int comps = TILE_COMPS) {
   tpl_off[n32max + 1] = (int)tpl.size();
   tpl_off[0] = 0;
   CU(p.order.ensure(order.size() * sizeof(int)));
+  // work items of the DMMA kernels: whole blocks, unless that leaves fewer than ~3 waves of the resident CTAs (strong
+  // scaling of a small grid over many GPUs): then blocks are cut into segments of j-tiles / rounds
+  std::vector<WorkItem> ditems, vitems;
+  const int target = 3 * 2 * ctx->num_sms;
+  for (Chunk& c : p.chunks) {
+    long tot_jt = 0, tot_r = 0;
+    for (int k = 0; k < c.nslots; ++k) {
+      const int q = order[c.slot0 + k];
+      if (p.h_s[q] == 0) continue;
+      const int n32 = p.h_s_pad[q] / 32;
+      tot_jt += (n32 + dens::NJW - 1) / dens::NJW;
+      tot_r += tpl_off[n32 + 1] - tpl_off[n32];
+    }
+    const int seg_jt = (int)std::max<long>(1, tot_jt / target), seg_r = (int)std::max<long>(1, tot_r / target);
+    c.ditem_off = (int)ditems.size();
+    c.vitem_off = (int)vitems.size();
+    for (int k = 0; k < c.nslots; ++k) {
+      const int q = order[c.slot0 + k];
+      const int n32 = p.h_s_pad[q] / 32;
+      const int njt = p.h_s[q] == 0 ? 0 : (n32 + dens::NJW - 1) / dens::NJW;
+      if (njt <= seg_jt || c.nslots >= target) {
+        ditems.push_back(WorkItem{q, 0, (short)njt});
+      } else {
+        c.dens_split = true;
+        const int nseg = (njt + seg_jt - 1) / seg_jt;
+        for (int sgi = 0; sgi < nseg; ++sgi)  // equal-sized segments
+          ditems.push_back(WorkItem{q, (short)((long)njt * sgi / nseg), (short)((long)njt * (sgi + 1) / nseg)});
+      }
+      if (p.h_s[q] == 0) continue;
+      const int nr = tpl_off[n32 + 1] - tpl_off[n32];
+      if (nr <= seg_r || c.nslots >= target) {
+        vitems.push_back(WorkItem{q, 0, (short)nr});
+      } else {
+        const int nseg = (nr + seg_r - 1) / seg_r;
+        for (int sgi = 0; sgi < nseg; ++sgi)
+          vitems.push_back(WorkItem{q, (short)((long)nr * sgi / nseg), (short)((long)nr * (sgi + 1) / nseg)});
+      }
+    }
+    c.nditems = (int)ditems.size() - c.ditem_off;
+    c.nvitems = (int)vitems.size() - c.vitem_off;
+  }
+  CU(p.ditems.ensure(std::max<size_t>(ditems.size(), 1) * sizeof(WorkItem)));
+  CU(p.vitems.ensure(std::max<size_t>(vitems.size(), 1) * sizeof(WorkItem)));
+  if (!ditems.empty())
+    CU(cudaMemcpyAsync(p.ditems.p, ditems.data(), ditems.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, ctx->stream));
+  if (!vitems.empty())
+    CU(cudaMemcpyAsync(p.vitems.p, vitems.data(), vitems.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, ctx->stream));
   CU(p.tpl.ensure(std::max<size_t>(tpl.size(), 1) * sizeof(ScatterRound)));
   CU(p.tpl_off.ensure(tpl_off.size() * sizeof(int)));
   if (p.nown) {
@@ -574,12 +624,24 @@ int phase_basis(sxc_ctx* ctx, const Grid& g, const Basis& b, const Plan& p, cons
   return SXC_OK;
 }
 
+__global__ void k_zero_blocks(long N, int blocksize, int ncomp, const int* __restrict__ block_id, double* __restrict__ out) {
+  const long first = (long)block_id[blockIdx.x] * blocksize;
+  const long n = min((long)blocksize, N - first);
+  for (int c = 0; c < ncomp; ++c)
+    for (long i = threadIdx.x; i < n; i += blockDim.x) out[(size_t)c * N + first + i] = 0.0;
+}
+
 int phase_density(sxc_ctx* ctx, const Grid& g, const Basis& b, const Plan& p, const Chunk& c, const double* dP,
                   double* dens4, bool with_grad, int* nonneg) {
   const long N = g.npts;
+  if (c.nditems == 0) return SXC_OK;
   PhaseTimer t(ctx, SXC_T_DENSITY);
-  k_density<<<c.nslots, dens::THREADS, dens::smem_bytes(p.s_pad_max), ctx->stream>>>(
-      g.view(), p.view(), b.nbf, dP, p.order.as<int>() + c.order_off, ctx->phi.as<double>(), dens4,
+  if (c.dens_split) {  // blocks shared by several CTAs accumulate into their outputs: clear the chunk's points first
+    k_zero_blocks<<<c.nslots, 128, 0, ctx->stream>>>(N, g.blocksize, with_grad ? 4 : 1, p.block_id.as<int>() + c.slot0, dens4);
+    LAUNCH_CHECK();
+  }
+  k_density<<<c.nditems, dens::THREADS, dens::smem_bytes(p.s_pad_max), ctx->stream>>>(
+      g.view(), p.view(), b.nbf, dP, p.ditems.as<WorkItem>() + c.ditem_off, ctx->phi.as<double>(), dens4,
       with_grad ? dens4 + N : nullptr, with_grad ? dens4 + 2 * N : nullptr, with_grad ? dens4 + 3 * N : nullptr, nonneg);
   LAUNCH_CHECK();
   return SXC_OK;
@@ -632,9 +694,10 @@ int phase_scatter(sxc_ctx* ctx, const Grid& g, const Basis& b, const Plan& p, co
   int* counter = nullptr;
   TRY(next_counter(ctx, &counter));
   PhaseTimer t(ctx, SXC_T_SCATTER);
-  const int grid = std::min(c.nslots, 2 * ctx->num_sms);
+  if (c.nvitems == 0) return SXC_OK;
+  const int grid = std::min(c.nvitems, 2 * ctx->num_sms);
   k_vmat<<<grid, scat::THREADS, scat::smem_bytes(), ctx->stream>>>(
-      p.view(), b.nbf, p.order.as<int>() + c.order_off, c.nslots, counter, p.skip.as<int>(), p.tpl.as<ScatterRound>(),
+      p.view(), b.nbf, p.vitems.as<WorkItem>() + c.vitem_off, c.nvitems, counter, p.skip.as<int>(), p.tpl.as<ScatterRound>(),
       p.tpl_off.as<int>(), ctx->phi.as<double>(), dW);
   LAUNCH_CHECK();
   return SXC_OK;

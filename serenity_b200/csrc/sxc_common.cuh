@@ -68,6 +68,13 @@ __device__ __forceinline__ double block_max(double v, double* scratch) {
   return r;
 }
 
+// Work item of the two DMMA kernels: a block (plan slot q) or, when a shard leaves too few blocks to fill the GPU,
+// a segment [begin, end) of its j-tiles (k_density) / rounds (k_vmat).
+struct WorkItem {
+  int q;
+  short begin, end;
+};
+
 // Device view of a shell table (structure of arrays), see sxc_add_basis.
 struct ShellView {
   int nshell;

@@ -47,7 +47,11 @@ class ShardedBuild:
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.device = torch.device(device)
         n = nbf * nbf
-        self.d_P = torch.zeros(n, dtype=torch.float64, device=self.device)
+        # P travels in `world` equal slices (one per rank), so its device buffer is padded to a multiple of world
+        self._slice = (n + self.world - 1) // self.world
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self._d_P_all = torch.zeros(self._slice * self.world, dtype=torch.float64, device=self.device)
+        self.d_P = self._d_P_all[:n]
         self.d_VEN = torch.zeros(n + ntail, dtype=torch.float64, device=self.device)
         cuda = self.device.type == "cuda"
         self.h_P = torch.zeros(n, dtype=torch.float64, pin_memory=cuda)      # pinned staging buffers of the host API
@@ -62,22 +66,40 @@ class ShardedBuild:
             dist.all_reduce(self.d_VEN, op=dist.ReduceOp.SUM, group=self.group)
         return self.d_VEN
 
+    def _upload(self):
+        """H2D of P: every rank copies ONE slice of the (identical) host matrix over its own PCIe link and the slices
+        are all-gathered over NVLink - nb^2 * 8 bytes cross PCIe once per build instead of once per rank."""
+        n = self.nbf * self.nbf
+        if self.world == 1:
+            self.d_P.copy_(self.h_P, non_blocking=True)
+            return
+        lo = self.rank * self._slice
+        hi = min(lo + self._slice, n)
+        mine = self._d_P_all[lo: lo + self._slice]
+        if hi > lo:
+            mine[: hi - lo].copy_(self.h_P[lo:hi], non_blocking=True)
+        dist.all_gather_into_tensor(self._d_P_all, mine, group=self.group)  # in place: slice r of the output is rank r's input
+
     def build_pinned(self):
         """P has been written into the pinned buffer h_P (column-major); returns views into the pinned result buffer
-        h_VEN: (V [nb, nb], E, N).  The upload runs on a side stream and is awaited by the library only before the
-        density kernel, i.e. it overlaps with the screening and basis kernels."""
+        h_VEN: (V [nb, nb], E, N) - V only on rank 0 (the SCF driver's process), E and N on
+        every rank.  The upload runs on a side stream and is awaited by the library only before the density kernel,
+        i.e. it overlaps with the screening and basis kernels."""
         n = self.nbf * self.nbf
         if self._copy_stream is not None:
             cur = torch.cuda.current_stream(self.device)
             self._copy_stream.wait_stream(cur)  # the previous build no longer reads d_P
             with torch.cuda.stream(self._copy_stream):
-                self.d_P.copy_(self.h_P, non_blocking=True)
+                self._upload()
                 self._p_event.record(self._copy_stream)
             self.build_device(self._p_event)
-            self.h_VEN.copy_(self.d_VEN, non_blocking=True)
+            if self.rank == 0:
+                self.h_VEN.copy_(self.d_VEN, non_blocking=True)
+            else:
+                self.h_VEN[n:].copy_(self.d_VEN[n:], non_blocking=True)
             cur.synchronize()
         else:
-            self.d_P.copy_(self.h_P)
+            self._upload()
             self.build_device()
             self.h_VEN.copy_(self.d_VEN)
         out = self.h_VEN.numpy()
@@ -91,11 +113,13 @@ class ShardedBuild:
 
     @property
     def h2d_bytes(self) -> int:
+        """bytes uploaded per build, all ranks together"""
         return self.h_P.numel() * 8
 
     @property
     def d2h_bytes(self) -> int:
-        return self.h_VEN.numel() * 8
+        """bytes downloaded per build, all ranks together: [V|E|N] on rank 0, [E|N] elsewhere"""
+        return self.h_VEN.numel() * 8 + (self.world - 1) * self.ntail * 8
 
 
 def cuda_local_build(ctx, grid: int, basis: int, func: int, block_ave_threshold: float = 1e-11):

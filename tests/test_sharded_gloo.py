@@ -44,6 +44,7 @@ def _worker(rank, world, port, out_path):
         V, E, ne = sb.build(sub.P)
         V2, E2, ne2 = sb.build(sub.P)  # buffers are reused: a second build must not accumulate
         assert abs(E2 - E) < 1e-12 and np.abs(V - V2).max() < 1e-12  # (oracle sums in OpenMP order)
+        assert np.array_equal(sb.d_P.numpy(), sub.P.reshape(-1, order="F"))  # slices + all-gather rebuilt P everywhere
         if rank == 0:
             V_ref, E_ref, ne_ref, _ = orc.build_xc(ob, orc.Grid(cfg.xyz, cfg.w, 128), of, sub.P)
             np.savez(out_path, dV=np.abs(V - V_ref).max(), dE=abs(E - E_ref), dn=abs(ne - ne_ref), sym=np.abs(V - V.T).max())
