@@ -178,7 +178,7 @@ J p86c(const J& a, const J& b, const J& gaa, const J& gab, const J& gbb) {
   const J eps = eU + f_zeta(a, b) * (eP - eU);
   const J rs2 = rs * rs;
   const J Cn = 0.001667 + (0.002568 + 0.023266 * rs + 7.389e-6 * rs2) / (1.0 + 8.723 * rs + 0.472 * rs2 + 0.07389 * rs2 * rs);
-  const J Phi = (1.745 * 0.11 * 0.004235) * jsqrt(g) / (Cn * jpow(n, 7.0 / 6.0));
+  const J Phi = (1.7454151061251240 /* (9 pi)^(1/6) */ * 0.11 * 0.004235) * jsqrt(g) / (Cn * jpow(n, 7.0 / 6.0));
   const J d = std::cbrt(2.0) * jsqrt(jpow(a / n, 5.0 / 3.0) + jpow(b / n, 5.0 / 3.0));
   return n * eps + jexp(-Phi) * Cn * g / (d * jpow(n, 4.0 / 3.0));
 }

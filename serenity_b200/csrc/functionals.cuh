@@ -254,7 +254,7 @@ template <class T> SXC_HD T e_p86c(const T& a, const T& b, const T& gaa, const T
   const T c = dcbrt(n);
   const T n43 = n * c;
   const T n76 = n * dsqrt(c);  // n^(7/6)
-  const T Phi = (1.745 * 0.11 * 0.004235) * dsqrt(g) / (Cn * n76);
+  const T Phi = (1.7454151061251240 /* (9 pi)^(1/6), pinned by FuncPotential_test.cpp:148-187 */ * 0.11 * 0.004235) * dsqrt(g) / (Cn * n76);
   const T hp = a / n, hm = b / n;
   const T d = fc::TWO_13 * dsqrt(pow53(hp) + pow53(hm));
   return n * eps + dexp(-Phi) * Cn * g / (d * n43);

@@ -133,7 +133,7 @@ def p86c(a, b, gaa, gab, gbb):
     z = (a - b) / n
     rs = (3.0 / (4.0 * PI * n)) ** (1.0 / 3.0)
     Cn = 0.001667 + (0.002568 + 0.023266 * rs + 7.389e-6 * rs * rs) / (1 + 8.723 * rs + 0.472 * rs * rs + 0.07389 * rs ** 3)
-    Phi = 1.745 * 0.11 * 0.004235 / Cn * torch.sqrt(g) / n ** (7.0 / 6.0)
+    Phi = (9.0 * PI) ** (1.0 / 6.0) * 0.11 * 0.004235 / Cn * torch.sqrt(g) / n ** (7.0 / 6.0)
     d = 2.0 ** (1.0 / 3.0) * torch.sqrt(((1 + z) / 2) ** (5.0 / 3.0) + ((1 - z) / 2) ** (5.0 / 3.0))
     return n * _pz81_eps(rs, z) + torch.exp(-Phi) * Cn * g / (d * n ** (4.0 / 3.0))
 

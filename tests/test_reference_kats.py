@@ -6,10 +6,13 @@ These pin the WHOLE path - grid restatement (Becke / SSF partition, Ahlrichs rad
 renormalisation, Cartesian shells, density, functional kernels, grid -> matrix - against numbers produced by the
 reference itself (xcfun route):
   LDA  = slaterx + vwn5c : agrees to 5e-9 (reference tolerance 1e-6)           -> Slater and VWN5 kernels PINNED
-  BP86 = beckex + p86c   : agrees to 8e-6, the reference's own tolerance of 1e-6 is NOT met; the deviation sits entirely
-                           in the gradient-dependent parts (B88 correction and P86 gradient term fit with a common
-                           factor 1.0002) -> GGA kernels stay "parity unpinned" at 1e-6
+  BP86 = beckex + p86c   : agrees to 8.4e-8 (reference tolerance 1e-6)        -> B88, PZ81 and P86 kernels PINNED.
+                           (With the paper's rounded prefactor 1.745 in the P86 exponent the deviation was 8e-6; a
+                           one-parameter fit of the reference matrix gave 1.000238 = (9 pi)^(1/6) / 1.745, i.e. xcfun
+                           uses the exact constant; all other parameters then fit to 1 +- 2e-7)
   NAdd LDA / BP86 elements (RESTRICTED): inside the reference tolerance 1e-5.
+  E_xc[BP86] stored in data/testresources/TestSystem_H2_6_31Gs_{ACTIVE,ENVIRONMENT}_FDE/*.energies.res (6 decimals):
+                           reproduced to 4e-7 from the density matrices stored next to them.
 """
 import numpy as np
 import pytest
@@ -73,9 +76,9 @@ def test_oracle_h2_vxc_bp86(func_case):
     ob, og = orc.Basis(tab), orc.Grid(gx, gw, 128)
     V, _, _, _ = orc.build_xc(ob, og, orc.Functional(*BP86), mat("P_restricted"))
     dev = np.abs(V - mat("V_BP86")).max()
-    assert dev < 1e-5, dev          # NOT the reference's 1e-6: measured 8.0e-6 (module docstring)
+    assert dev < 2e-7, dev          # reference tolerance 1e-6; measured 8.4e-8 (module docstring)
     (Va, Vb), _, _ = orc.build_xc_u(ob, og, orc.Functional(*BP86), mat("P_alpha"), mat("P_beta"))
-    assert np.abs(Va - mat("V_BP86_unres")).max() < 1e-5 and np.abs(Vb - mat("V_BP86_unres")).max() < 1e-5
+    assert np.abs(Va - mat("V_BP86_unres")).max() < 2e-7 and np.abs(Vb - mat("V_BP86_unres")).max() < 2e-7
 
 
 def _check_elements(V, rows):
@@ -100,6 +103,26 @@ def test_oracle_h2_dimer_nadd(nadd_case):
         assert np.abs(Va - V).max() < 1e-10 and np.abs(Vb - V).max() < 1e-10
 
 
+def _stored_energy_cases():
+    """(system entry, shell table, grid) of the two H2 / 6-31G* FDE test systems whose `.energies.res` is consistent with
+    the stored density matrix: E_xc[BP86] printed with 6 decimals (EnergyContributions.h:49, entry 202)."""
+    k = load_golden("h2_kats.json")["nadd_potential"]
+    for key in ("act", "env"):
+        e = k[key]
+        syms, xyz, tab = _system(k["basis_shells_H"], e["geometry_angstrom"], e["settings"]["spherical"])
+        gx, gw = _grid(syms, xyz, e["settings"])
+        yield e, tab, gx, gw
+
+
+def test_oracle_stored_bp86_energies():
+    from oracle import pyoracle as orc
+    for e, tab, gx, gw in _stored_energy_cases():
+        _, E, _, _ = orc.build_xc(orc.Basis(tab), orc.Grid(gx, gw, 128), orc.Functional(*BP86),
+                                  np.asarray(e["P_restricted"]).reshape(4, 4), e["settings"]["radial_threshold"],
+                                  e["settings"]["block_ave_threshold"])
+        assert abs(E - e["E_xc_BP86_stored"]) < 1e-6, (e["system"], E)   # the file holds 6 decimals
+
+
 # ------------------------------------------------------------------------------------------- CUDA path
 @pytest.mark.gpu
 def test_gpu_h2_vxc_kats(func_case):
@@ -115,7 +138,23 @@ def test_gpu_h2_vxc_kats(func_case):
     assert np.abs(Va - mat("V_LDA_unres")).max() < 3e-8 and np.abs(Vb - mat("V_LDA_unres")).max() < 3e-8
     f = ctx.set_functional(*BP86)
     V, _, _ = ctx.build_xc(g, b, f, mat("P_restricted"))
-    assert np.abs(V - mat("V_BP86")).max() < 1e-5
+    assert np.abs(V - mat("V_BP86")).max() < 2e-7   # reference tolerance 1e-6
+    (Va, Vb), _, _ = ctx.build_xc(g, b, f, (mat("P_alpha"), mat("P_beta")), nspin=2)
+    assert np.abs(Va - mat("V_BP86_unres")).max() < 2e-7 and np.abs(Vb - mat("V_BP86_unres")).max() < 2e-7
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_stored_bp86_energies():
+    from serenity_b200.xc import XCContext
+    ctx = XCContext(0)
+    f = ctx.set_functional(*BP86)
+    for e, tab, gx, gw in _stored_energy_cases():
+        g = ctx.set_grid(gx, gw, 128)
+        b = ctx.add_basis(tab, e["settings"]["radial_threshold"])
+        _, E, _ = ctx.build_xc(g, b, f, np.asarray(e["P_restricted"]).reshape(4, 4),
+                               block_ave_threshold=e["settings"]["block_ave_threshold"])
+        assert abs(E - e["E_xc_BP86_stored"]) < 1e-6, (e["system"], E)
     ctx.close()
 
 
