@@ -188,6 +188,19 @@ int sxc_functional_on_grid_u(sxc_ctx* ctx, int func, int64_t npts, const double*
 int sxc_scalar_to_matrix(sxc_ctx* ctx, int grid, int basis, double block_ave_threshold, const double* v,
                          const double* gx, const double* gy, const double* gz, double* V);
 
+/* ---- grid construction ---------------------------------------------------------------------- */
+/* The partition-weight step of GridFactory::produce (src/grid/construction/GridFactory.cpp:139-266), the O(N n_atoms^2)
+ * part of the reference's grid set-up.  coords [natoms][3] (bohr); xyz 3 x npts interleaved = every atom's reference
+ * grid already shifted to its nucleus; parent[p] = index of the atom point p belongs to; w in: atomic quadrature weights
+ * (AtomGridFactory), out: molecular weights (0 where the SSF screen removes the point; the caller applies the
+ * weightThreshold cut of :264 and the Hilbert sort).  flavour 0 = BECKE (aij = size adjustments a(j + natoms * l) of
+ * :95-113, may be NULL; becke_smoothing = GridFactory's _smoothing, max(1, k)-fold iterated polynomial :324-347),
+ * 1 = SSF (aij, becke_smoothing ignored), 2 = VORONOI (:194-203). */
+int sxc_partition_weights(sxc_ctx* ctx, int flavour, int becke_smoothing, int natoms, const double* coords,
+                          const double* aij, int64_t npts, const double* xyz, const int* parent, double* w);
+/* device time (ms, CUDA events) of the kernel inside the last sxc_partition_weights call */
+double sxc_last_partition_ms(sxc_ctx* ctx);
+
 int sxc_get_stats(sxc_ctx* ctx, sxc_stats* out);
 /* host-only helper behind sxc_set_grid_shard: splits n blocks into `world` contiguous ranges of nearly equal summed
  * cost; bounds[world + 1] receives the range starts (bounds[0] = 0, bounds[world] = n). */

@@ -117,7 +117,6 @@ k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, cons
 
   double acc[4][4][2];
   for (int i = tid; i < NJW * BP * 4; i += THREADS) red[i] = 0.0;
-  const int pf_kc = max(0, nk - 6);  // ~6 K chunks (tens of microseconds) before the epilogue
 
   issue();
   issue();
@@ -134,14 +133,6 @@ k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, cons
       cp_async_wait<STAGES - 2>();
       __syncthreads();
       issue();
-      if (kc == pf_kc) {  // pull the epilogue operands of this j-tile (4 components x <= 64 rows) into L2 ahead of use
-        const int ncol = min(TJ, sp - jt * TJ);
-        const int per_comp = ncol * (BP / 16);  // 128-byte lines
-        for (int idx = tid; idx < 4 * per_comp; idx += THREADS) {
-          const int comp = idx / per_comp, rem = idx - comp * per_comp;
-          prefetch_l2(tile + comp * comp_stride + (size_t)(jt * TJ + (rem >> 3)) * BP + (rem & 7) * 16);
-        }
-      }
       const double* As = stage_base + c_stage * STAGE_ELEMS;
       const double* Bs = As + A_ELEMS;
       c_stage = (c_stage + 1 == STAGES) ? 0 : c_stage + 1;

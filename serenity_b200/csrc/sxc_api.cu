@@ -25,6 +25,7 @@
 #include "functionals.cuh"
 #include "scatter_kernel.cuh"
 #include "gradient_kernels.cuh"
+#include "grid_kernels.cuh"
 #include "sxc_common.cuh"
 
 using namespace sxc;
@@ -168,6 +169,7 @@ struct sxc_ctx {
   int counter_next = NCOUNTERS;
   int num_sms = 148;
   int64_t ws_limit = 0;
+  float last_partition_ms = 0.f;  // device time of the last k_partition_weights launch
   sxc_stats stats{};
   int launches = 0;
   bool attrs_set = false;
@@ -1430,6 +1432,73 @@ int sxc_xc_gradient(sxc_ctx* ctx, int grid, int basis, int func, int nspin, cons
     for (int c = 0; c < 3; ++c) grad[atom_of_bf[nu] + (size_t)c * natoms] -= 2.0 * t[(size_t)nu * 3 + c];
   return SXC_OK;
 }
+
+int sxc_partition_weights(sxc_ctx* ctx, int flavour, int becke_smoothing, int natoms, const double* coords,
+                          const double* aij, int64_t npts, const double* xyz, const int* parent, double* w) {
+  if (!ctx || natoms <= 0 || npts < 0 || !coords || (npts > 0 && (!xyz || !parent || !w)))
+    return fail(ctx, SXC_ERR_INVALID, "sxc_partition_weights: bad arguments");
+  if (flavour < 0 || flavour > 2)
+    return fail(ctx, SXC_ERR_UNSUPPORTED, "grid flavour %d (0 = BECKE, 1 = SSF, 2 = VORONOI)", flavour);
+  if ((size_t)PW_WARPS * natoms * sizeof(double) > 200 * 1024)
+    return fail(ctx, SXC_ERR_UNSUPPORTED, "more than %d atoms", (int)(200 * 1024 / (PW_WARPS * sizeof(double))));
+  if (npts == 0) return SXC_OK;
+  for (int64_t p = 0; p < npts; ++p)
+    if (parent[p] < 0 || parent[p] >= natoms) return fail(ctx, SXC_ERR_INVALID, "parent[%lld] out of range", (long long)p);
+  CU(cudaSetDevice(ctx->device));
+  // atom-atom distances and the nearest neighbour of every atom (GridFactory.cpp:76-92, :152-159)
+  std::vector<double> adist((size_t)natoms * natoms), mind(natoms, 999999999.9);
+  for (int i = 0; i < natoms; ++i)
+    for (int j = 0; j < natoms; ++j) {
+      const double dx = coords[3 * i] - coords[3 * j], dy = coords[3 * i + 1] - coords[3 * j + 1],
+                   dz = coords[3 * i + 2] - coords[3 * j + 2];
+      const double d = std::sqrt(dx * dx + dy * dy + dz * dz);
+      adist[i + (size_t)natoms * j] = d;
+      if (i != j) mind[j] = std::min(mind[j], d);
+    }
+  DevMem dc, da, daij, dm, dx, dp, dw;
+  const size_t n2 = (size_t)natoms * natoms * sizeof(double);
+  CU(dc.ensure((size_t)3 * natoms * sizeof(double)));
+  CU(da.ensure(n2));
+  CU(dm.ensure(natoms * sizeof(double)));
+  CU(dx.ensure((size_t)3 * npts * sizeof(double)));
+  CU(dp.ensure((size_t)npts * sizeof(int)));
+  CU(dw.ensure((size_t)npts * sizeof(double)));
+  if (aij) {
+    CU(daij.ensure(n2));
+    CU(cudaMemcpyAsync(daij.p, aij, n2, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CU(cudaMemcpyAsync(dc.p, coords, (size_t)3 * natoms * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(da.p, adist.data(), n2, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(dm.p, mind.data(), natoms * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(dx.p, xyz, (size_t)3 * npts * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(dp.p, parent, (size_t)npts * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(dw.p, w, (size_t)npts * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  const size_t smem = (size_t)PW_WARPS * natoms * sizeof(double);
+  if (smem > 48 * 1024)
+    CU(cudaFuncSetAttribute(k_partition_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t want = (npts + PW_WARPS - 1) / PW_WARPS;
+  const int grid = (int)std::min<int64_t>(want, (int64_t)ctx->num_sms * 8);  // grid-stride over the points
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  CU(cudaEventRecord(e0, ctx->stream));
+  k_partition_weights<<<grid, PW_WARPS * 32, smem, ctx->stream>>>(flavour, std::max(1, becke_smoothing), natoms, dc.as<double>(), da.as<double>(),
+                                                                   aij ? daij.as<double>() : nullptr, dm.as<double>(),
+                                                                   (long)npts, dx.as<double>(), dp.as<int>(), dw.as<double>());
+  CU(cudaEventRecord(e1, ctx->stream));
+  LAUNCH_CHECK();
+  CU(cudaMemcpyAsync(w, dw.p, (size_t)npts * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  ctx->last_partition_ms = ms;
+  ctx->stats.kernel_launches += 1;
+  return SXC_OK;
+}
+
+double sxc_last_partition_ms(sxc_ctx* ctx) { return ctx ? (double)ctx->last_partition_ms : -1.0; }
 
 int sxc_get_stats(sxc_ctx* ctx, sxc_stats* out) {
   if (!ctx || !out) return SXC_ERR_INVALID;

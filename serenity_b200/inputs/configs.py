@@ -58,6 +58,20 @@ def _subsystem(symbols, coords, basis_name, seed):
     return Subsystem(list(symbols), np.asarray(coords), tab, random_density_matrix(tab.nbf, nel, seed), nel)
 
 
+def geometry_of(name: str):
+    """(symbols, coordinates in bohr) of a named synthetic system."""
+    n = name.lower()
+    if n == "h2o":
+        return geo.water()
+    if n == "tetracene":
+        return geo.tetracene()
+    if n in ("water64", "water8", "water27"):
+        return geo.water_cluster({"water64": 4, "water27": 3, "water8": 2}[n])
+    if n == "peptide":
+        return geo.peptide_stand_in()
+    raise ValueError("unknown geometry " + name)
+
+
 def make_config(name: str, acc: int | None = None) -> Config:
     """name in {h2o, tetracene, water64, fde_dimer, fde_water64, peptide} (+ small test variants)."""
     n = name.lower()

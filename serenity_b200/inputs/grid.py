@@ -98,13 +98,14 @@ def _load_helper():
         raise RuntimeError("serenity_b200/inputs/libsxc_inputs.so missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
     lib = ctypes.CDLL(path)
     lib.sxc_partition_weights.restype = None
-    lib.sxc_partition_weights.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+    lib.sxc_partition_weights.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                           ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_void_p,
                                           ctypes.c_void_p]
     return lib
 
 
 _HELPER = None
+_FLAVOURS = {"BECKE": 0, "SSF": 1, "VORONOI": 2}
 
 
 def hilbert_index(ipts: np.ndarray, bits: int = 10) -> np.ndarray:
@@ -137,44 +138,75 @@ def hilbert_index(ipts: np.ndarray, bits: int = 10) -> np.ndarray:
     return idx
 
 
-def molecular_grid(symbols, coords_bohr, acc: int = 4, flavour: str = "SSF", radial: str = "AHLRICHS",
-                   weight_threshold: float = 1e-14, sort: bool = True):
-    """Returns (xyz [N,3] float64 C-contiguous == Matrix3Xd column-major interleaved, w [N])."""
+def becke_size_adjustments(zs):
+    """a(j + nAtoms * i) of GridFactory.cpp:95-113 (Bragg-Slater radii), as a [nat, nat] C-contiguous array."""
+    from .geometry import ANGSTROM_TO_BOHR
+    nat = len(zs)
+    bs = np.asarray([_BRAGG_SLATER[z] for z in zs]) * ANGSTROM_TO_BOHR
+    aij = np.zeros((nat, nat))
+    for i in range(nat):
+        for j in range(nat):
+            q = math.sqrt(bs[j] / bs[i])
+            u = (q - 1.0) / (q + 1.0)
+            a = u / (u * u - 1.0)
+            aij[i, j] = min(0.5, max(-0.5, a))  # aOfAtomPair(j, i) stored at data()[j + nAtoms*i]
+    return np.ascontiguousarray(aij)
+
+
+def reference_atom_grids(symbols, coords_bohr, acc: int = 4, radial: str = "AHLRICHS"):
+    """Every atom's reference grid shifted to its nucleus: (xyz [N, 3], atomic weights [N], parent atom [N])."""
+    from .geometry import atomic_numbers
+    zs = atomic_numbers(symbols)
+    coords = np.ascontiguousarray(coords_bohr, dtype=np.float64)
+    cache, pts, wts, par = {}, [], [], []
+    for k, z in enumerate(zs):
+        if z not in cache:
+            cache[z] = atom_grid(z, acc, radial)
+        p0, w0 = cache[z]
+        pts.append(p0 + coords[k])
+        wts.append(w0)
+        par.append(np.full(w0.shape[0], k, dtype=np.int32))
+    return np.ascontiguousarray(np.concatenate(pts, axis=0)), np.concatenate(wts), np.concatenate(par)
+
+
+def host_partition_weights(flavour, zs, coords, xyz, w_atomic, parent, smoothing: int = 3):
+    """CPU restatement of the weight step (gridweights.c), atom by atom; the checker of XCContext.partition_weights."""
     global _HELPER
     if _HELPER is None:
         _HELPER = _load_helper()
-    from .geometry import atomic_numbers, ANGSTROM_TO_BOHR
-    zs = atomic_numbers(symbols)
-    coords = np.ascontiguousarray(coords_bohr, dtype=np.float64)
     nat = len(zs)
+    coords = np.ascontiguousarray(coords, dtype=np.float64)
     adist = np.ascontiguousarray(np.linalg.norm(coords[:, None, :] - coords[None, :, :], axis=2))
-    aij = None
-    if flavour == "BECKE":  # GridFactory.cpp:95-113
-        bs = np.asarray([_BRAGG_SLATER[z] for z in zs]) * ANGSTROM_TO_BOHR
-        aij = np.zeros((nat, nat))
-        for i in range(nat):
-            for j in range(nat):
-                q = math.sqrt(bs[j] / bs[i])
-                u = (q - 1.0) / (q + 1.0)
-                a = u / (u * u - 1.0)
-                aij[i, j] = min(0.5, max(-0.5, a))  # aOfAtomPair(j, i) stored at data()[j + nAtoms*i]
-        aij = np.ascontiguousarray(aij)
-    cache = {}
-    all_p, all_w = [], []
+    aij = becke_size_adjustments(zs) if flavour != "SSF" else None
+    out = np.array(w_atomic, dtype=np.float64, copy=True)
     for k in range(nat):
-        if zs[k] not in cache:
-            cache[zs[k]] = atom_grid(zs[k], acc, radial)
-        p0, w0 = cache[zs[k]]
-        pts = np.ascontiguousarray(p0 + coords[k])
-        w = w0.copy()
-        _HELPER.sxc_partition_weights(0 if flavour == "BECKE" else 1, nat, coords.ctypes.data, adist.ctypes.data,
+        sel = np.nonzero(parent == k)[0]
+        pts = np.ascontiguousarray(xyz[sel])
+        w = np.ascontiguousarray(out[sel])
+        _HELPER.sxc_partition_weights(_FLAVOURS[flavour], smoothing, nat, coords.ctypes.data, adist.ctypes.data,
                                       aij.ctypes.data if aij is not None else None, k, pts.shape[0],
                                       pts.ctypes.data, w.ctypes.data)
-        keep = w > weight_threshold  # GridFactory.cpp:264
-        all_p.append(pts[keep])
-        all_w.append(w[keep])
-    xyz = np.concatenate(all_p, axis=0)
-    w = np.concatenate(all_w)
+        out[sel] = w
+    return out
+
+
+def molecular_grid(symbols, coords_bohr, acc: int = 4, flavour: str = "SSF", radial: str = "AHLRICHS",
+                   weight_threshold: float = 1e-14, sort: bool = True, device_ctx=None, smoothing: int = 3):
+    """Returns (xyz [N,3] float64 C-contiguous == Matrix3Xd column-major interleaved, w [N]).
+
+    device_ctx: an XCContext -> the O(N n_atoms^2) partition-weight step runs on the GPU (sxc_partition_weights);
+    default: the host restatement (the synthetic inputs of tests and bench.py are made this way)."""
+    from .geometry import atomic_numbers
+    zs = atomic_numbers(symbols)
+    coords = np.ascontiguousarray(coords_bohr, dtype=np.float64)
+    xyz, w0, parent = reference_atom_grids(symbols, coords, acc, radial)
+    if device_ctx is not None:
+        w, _ = device_ctx.partition_weights(flavour, coords, xyz, parent, w0,
+                                            becke_size_adjustments(zs) if flavour != "SSF" else None, smoothing)
+    else:
+        w = host_partition_weights(flavour, zs, coords, xyz, w0, parent, smoothing)
+    keep = w > weight_threshold  # GridFactory.cpp:264
+    xyz, w = xyz[keep], w[keep]
     if sort:
         lo = xyz.min(axis=0)
         span = np.maximum(xyz.max(axis=0) - lo, 1e-300)

@@ -5,7 +5,7 @@
  * src/grid/construction/GridFactory.cpp:139-266 (Becke: J. Chem. Phys. 88 (1988) 2547;
  * SSF: Stratmann/Scuseria/Frisch, Chem. Phys. Lett. 257 (1996) 213) for one parent atom's points.
  *
- *   flavour 0 = BECKE (with Bragg-Slater size adjustment a_ij passed in), 1 = SSF
+ *   flavour 0 = BECKE (with Bragg-Slater size adjustment a_ij passed in), 1 = SSF, 2 = VORONOI (:194-203)
  *
  * pts:  [3*n] points of parent atom k (already shifted to the molecule frame)
  * w:    [n] in: atomic quadrature weights, out: molecular weights (0 where screened out)
@@ -13,13 +13,14 @@
 #include <math.h>
 #include <stdlib.h>
 
-static double becke_smooth(double nu) {
-  /* three-fold iterated p(x) = 1.5 x - 0.5 x^3, s = 0.5 (1 - p3)  (GridFactory.cpp:324-347, smoothing 3) */
-  for (int i = 0; i < 3; ++i) nu = 1.5 * nu - 0.5 * nu * nu * nu;
+static double becke_smooth(double nu, int smoothing) {
+  /* k-fold iterated p(x) = (3 - x^2) x / 2, s = 0.5 (1 - p_k); k = max(1, smoothing)  (GridFactory.cpp:324-347) */
+  const int k = smoothing > 1 ? smoothing : 1;
+  for (int i = 0; i < k; ++i) nu = (3.0 - nu * nu) * nu / 2.0;
   return 0.5 * (1.0 - nu);
 }
 
-void sxc_partition_weights(int flavour, int natoms, const double* coords /*[3*natoms]*/,
+void sxc_partition_weights(int flavour, int smoothing, int natoms, const double* coords /*[3*natoms]*/,
                            const double* adist /*[natoms*natoms]*/, const double* aij /*[natoms*natoms] or NULL*/,
                            int k, long n, const double* pts, double* w) {
   double min_dist = 999999999.9;
@@ -46,12 +47,22 @@ void sxc_partition_weights(int flavour, int natoms, const double* coords /*[3*na
             if (l == j || adist[j + natoms * k] >= 40.0) continue;
             const double mu = (rd[l] - rd[j]) / adist[l + natoms * j];
             const double nu = mu + (aij ? aij[j + natoms * l] : 0.0) * (1.0 - mu * mu);
-            cell *= becke_smooth(nu);
+            cell *= becke_smooth(nu, smoothing);
           }
           if (l == k) weight *= cell;
           sum += cell;
         }
         weight /= sum;
+      } else if (flavour == 2) {
+        for (int l = 0; l < natoms; ++l) {
+          if (adist[l + natoms * k] >= 40.0) continue;
+          const double mu = (rd[l] - rd[k]) / adist[l + natoms * k];
+          const double nu = mu + (aij ? aij[k + natoms * l] : 0.0) * (1.0 - mu * mu);
+          if (nu < 0.0) {
+            weight = 0.0;
+            break;
+          }
+        }
       } else {
         /* SSF, GridFactory.cpp:211-263 */
         if (rd[k] >= 0.5 * (1.0 - 0.64) * min_dist) {

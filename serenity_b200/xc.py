@@ -206,6 +206,21 @@ class XCContext:
                                                    _ptr(_f64(gz)) if gga else None, _ptr(V)))
         return V
 
+    def partition_weights(self, flavour: str, coords, xyz, parent, w, aij=None, smoothing: int = 3):
+        """GridFactory.cpp:139-266 on the device: molecular partition weights (BECKE / SSF) of the atoms' reference
+        grids.  xyz [N, 3] points (already shifted to their nuclei), parent [N] atom index, w [N] atomic weights;
+        returns the molecular weights (0 where the SSF screen removes a point) and the kernel time in ms."""
+        coords = _f64(coords).reshape(-1, 3)
+        xyz = _f64(xyz).reshape(-1, 3)
+        parent = np.ascontiguousarray(parent, dtype=np.int32)
+        out = _f64(w).copy()
+        a = None if aij is None else _f64(aij)
+        self._check(self._lib.sxc_partition_weights(self._h, {"BECKE": 0, "SSF": 1, "VORONOI": 2}[flavour], int(smoothing),
+                                                    coords.shape[0], _ptr(coords),
+                                                    None if a is None else _ptr(a), xyz.shape[0], _ptr(xyz), _ptr(parent),
+                                                    _ptr(out)))
+        return out, float(self._lib.sxc_last_partition_ms(self._h))
+
     def stats(self) -> dict:
         s = Stats()
         self._check(self._lib.sxc_get_stats(self._h, C.byref(s)))
