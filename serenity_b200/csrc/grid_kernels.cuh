@@ -11,7 +11,8 @@
 // B200 design: one warp per grid point.  The lanes compute the n_atoms point-atom distances into a per-warp shared
 // array, run the nu_kj screen with a ballot, then take the atoms l round-robin: every lane walks j in the reference's
 // order with the reference's early exits (so each P_l is the same product in the same order) and the warp sums the
-// cells with shuffles.  Atom-atom distances (n_atoms^2 doubles) are read through L1/L2.
+// cells with shuffles.  SSF cells that a single test against the atom nearest to the point proves to be exactly zero
+// skip the j loop (most atoms of a large molecule).  Atom-atom distances (n_atoms^2 doubles) are read through L1/L2.
 #pragma once
 
 #include "sxc_common.cuh"
@@ -78,9 +79,28 @@ k_partition_weights(int flavour, int smooth_k, int natoms, const double* __restr
         if (lane == 0) w[p] = 0.0;
         continue;
       }
+      // nearest atom to the point: one test against it settles most cells (P_i = 0 exactly as soon as ANY nu_ij >= 0.64,
+      // whichever j the reference's loop meets first), so only the few atoms around the point walk the full j loop
+      double dmin = 1.0e300;
+      int amin = 0;
+      for (int a = lane; a < natoms; a += 32)
+        if (rd[a] < dmin) {
+          dmin = rd[a];
+          amin = a;
+        }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, dmin, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, amin, o);
+        if (od < dmin || (od == dmin && oa < amin)) {
+          dmin = od;
+          amin = oa;
+        }
+      }
       for (int i = lane; i < natoms; i += 32) {
-        double cell = 1.0;
         const double ri = rd[i];
+        if (i != amin && (ri - dmin) / adist[i + natoms * amin] >= 0.64) continue;  // P_i = 0
+        double cell = 1.0;
         for (int j = 0; j < natoms; ++j) {
           if (i == j) continue;
           double nu = (ri - rd[j]) / adist[i + natoms * j];
