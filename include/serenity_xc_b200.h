@@ -188,6 +188,18 @@ int sxc_functional_on_grid_u(sxc_ctx* ctx, int func, int64_t npts, const double*
 int sxc_scalar_to_matrix(sxc_ctx* ctx, int grid, int basis, double block_ave_threshold, const double* v,
                          const double* gx, const double* gy, const double* gz, double* V);
 
+/* ---- two-basis operators -------------------------------------------------------------------- */
+/* ScalarOperatorToMatrixAdder(basisFunctionOnGridControllerA, basisFunctionOnGridControllerB, ...)::addScalarOperatorToMatrix
+ * with A != B (ScalarOperatorToMatrixAdder.cpp:216-220 LDA, :286-300 GGA): V is nbf_A x nbf_B column-major and is ADDED
+ * to; gx == NULL selects the LDA variant.  Both bases must live on the same grid handle. */
+int sxc_scalar_to_matrix_ab(sxc_ctx* ctx, int grid, int basis_a, int basis_b, double block_ave_threshold, const double* v,
+                            const double* gx, const double* gy, const double* gz, double* V);
+/* ABFuncPotential<SCFMode>::getMatrix (potentials/ABFockMatrixConstruction/ABFuncPotential.cpp:54-160): the densities of
+ * the ndens (basis_c[i], P_c[i]) pairs are summed on the grid, the functional is evaluated once and scattered into the
+ * nbf_A x nbf_B matrix (per spin: nspin of them back to back).  E[0] = E_xc of the summed density, E[1] = its integral. */
+int sxc_build_ab(sxc_ctx* ctx, int grid, int func, int nspin, int basis_a, int basis_b, int ndens, const int* basis_c,
+                 const double* const* P_c, double block_ave_threshold, double* V_ab, double* E);
+
 /* ---- grid construction ---------------------------------------------------------------------- */
 /* The partition-weight step of GridFactory::produce (src/grid/construction/GridFactory.cpp:139-266), the O(N n_atoms^2)
  * part of the reference's grid set-up.  coords [natoms][3] (bohr); xyz 3 x npts interleaved = every atom's reference

@@ -638,6 +638,104 @@ int orc_build_xc(const orc_basis* b, const orc_grid* g, const orc_functional* f,
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * f-4  two-basis scatter: ScalarOperatorToMatrixAdder::addBlock with basis A != basis B
+ *      (ScalarOperatorToMatrixAdder.cpp:179-223 LDA, :225-303 GGA, branch !useSym :216-220 / :286-300), the operator of
+ *      ABFuncPotential / ABNAddFuncPotential (potentials/ABFockMatrixConstruction/ABFuncPotential.cpp:54-160):
+ *        m_AB += pA [ phi_A^T diag(a) phi_B + phi_A^T grad_B + grad_A^T phi_B ] pB^T,  grad_X = sum_c diag(b_c) d_c phi_X
+ *      V is nbf_A x nbf_B column-major, added into.
+ * ------------------------------------------------------------------------------------------------ */
+void orc_scalar_to_matrix_ab(const orc_basis* bA, const orc_basis* bB, const orc_grid* g, double radial_thr,
+                             double block_ave_thr, const double* v, const double* gx, const double* gy, const double* gz,
+                             double* V) {
+  const int nblocks = orc_nblocks(g);
+  const int nA = bA->nbf, nB = bB->nbf;
+  const int gga = gx != NULL;
+  const int nthreads = omp_get_max_threads();
+  double** acc = (double**)calloc((size_t)nthreads, sizeof(double*));
+#pragma omp parallel
+  {
+    const int tid = omp_get_thread_num();
+    acc[tid] = (double*)calloc((size_t)nA * nB, sizeof(double));
+    orc_ws wA, wB;
+    ws_alloc(&wA, bA, g->blocksize, gga ? 1 : 0);
+    ws_alloc(&wB, bB, g->blocksize, gga ? 1 : 0);
+    double* a = (double*)malloc(sizeof(double) * 4 * (size_t)g->blocksize);
+    double *bx = a + g->blocksize, *by = bx + g->blocksize, *bz = by + g->blocksize;
+    double* T = (double*)malloc(sizeof(double) * (size_t)nA * nB);
+#pragma omp for schedule(dynamic)
+    for (int blk = 0; blk < nblocks; ++blk) {
+      int n, n2;
+      const int sA = ws_block(&wA, bA, g, radial_thr, gga ? 1 : 0, blk, &n, NULL);
+      const int sB = ws_block(&wB, bB, g, radial_thr, gga ? 1 : 0, blk, &n2, NULL);
+      const long first = (long)blk * g->blocksize;
+      double ave = 0.0;
+      for (int p = 0; p < n; ++p) {
+        a[p] = g->w[first + p] * v[first + p];
+        ave += fabs(a[p]);
+      }
+      if (gga) { /* :253-268 */
+        double sx = 0, sy = 0, sz = 0;
+        for (int p = 0; p < n; ++p) {
+          bx[p] = g->w[first + p] * gx[first + p];
+          by[p] = g->w[first + p] * gy[first + p];
+          bz[p] = g->w[first + p] * gz[first + p];
+          sx += fabs(bx[p]);
+          sy += fabs(by[p]);
+          sz += fabs(bz[p]);
+        }
+        ave += sx;
+        ave += sy;
+        ave += sz;
+      }
+      if (ave / n < block_ave_thr) continue;
+      if (sA == 0 || sB == 0) continue;
+      /* A side: phi_A and grad_A;  B side: phi_B and  a phi_B + grad_B  (so that one product pair gives all three terms) */
+      for (int j = 0; j < sA; ++j) {
+        const double* f = wA.val + (size_t)wA.sig[j] * n;
+        memcpy(wA.cval + (size_t)j * n, f, sizeof(double) * (size_t)n);
+        double* G = wA.G + (size_t)j * n;
+        if (gga) {
+          const double *fx = wA.d1[0] + (size_t)wA.sig[j] * n, *fy = wA.d1[1] + (size_t)wA.sig[j] * n,
+                       *fz = wA.d1[2] + (size_t)wA.sig[j] * n;
+          for (int p = 0; p < n; ++p) G[p] = bx[p] * fx[p] + by[p] * fy[p] + bz[p] * fz[p];
+        }
+      }
+      for (int j = 0; j < sB; ++j) {
+        const double* f = wB.val + (size_t)wB.sig[j] * n;
+        memcpy(wB.cval + (size_t)j * n, f, sizeof(double) * (size_t)n);
+        double* G = wB.G + (size_t)j * n;
+        if (gga) {
+          const double *fx = wB.d1[0] + (size_t)wB.sig[j] * n, *fy = wB.d1[1] + (size_t)wB.sig[j] * n,
+                       *fz = wB.d1[2] + (size_t)wB.sig[j] * n;
+          for (int p = 0; p < n; ++p) G[p] = a[p] * f[p] + bx[p] * fx[p] + by[p] * fy[p] + bz[p] * fz[p];
+        } else {
+          for (int p = 0; p < n; ++p) G[p] = a[p] * f[p];
+        }
+      }
+      double* A = acc[tid];
+      gemm_tn(sA, sB, n, wA.cval, n, wB.G, n, T, sA); /* phi_A^T (a phi_B + grad_B) */
+      for (int j = 0; j < sB; ++j)
+        for (int i = 0; i < sA; ++i) A[wA.sig[i] + (size_t)wB.sig[j] * nA] += T[i + (size_t)j * sA];
+      if (gga) {
+        gemm_tn(sA, sB, n, wA.G, n, wB.cval, n, T, sA); /* grad_A^T phi_B */
+        for (int j = 0; j < sB; ++j)
+          for (int i = 0; i < sA; ++i) A[wA.sig[i] + (size_t)wB.sig[j] * nA] += T[i + (size_t)j * sA];
+      }
+    }
+    free(T);
+    free(a);
+    ws_free(&wA);
+    ws_free(&wB);
+  }
+  for (int t = 0; t < nthreads; ++t) {
+    if (!acc[t]) continue;
+    for (size_t i = 0; i < (size_t)nA * nB; ++i) V[i] += acc[t][i];
+    free(acc[t]);
+  }
+  free(acc);
+}
+
+/* ------------------------------------------------------------------------------------------------
  * 8a-7  NAddFuncPotential::getMatrix / getEnergy, 8a-3 SupersystemDensityOnGridController::updateData
  * ------------------------------------------------------------------------------------------------ */
 int orc_build_nadd(const orc_basis* bA, const double* PA, int nenv, const orc_basis* const* bE,

@@ -110,6 +110,10 @@ int orc_basic_functional(int id, double rho, double sigma, double* F, double* vr
  * ADDED to, as in the reference. */
 void orc_scalar_to_matrix(const orc_basis* b, const orc_grid* g, double radial_thr, double block_ave_thr,
                           const double* v, const double* gx, const double* gy, const double* gz, double* V);
+/* f-4: two-basis variant (basis A != basis B), ScalarOperatorToMatrixAdder.cpp:216-220 / :286-300; V is nbf_A x nbf_B */
+void orc_scalar_to_matrix_ab(const orc_basis* bA, const orc_basis* bB, const orc_grid* g, double radial_thr,
+                             double block_ave_thr, const double* v, const double* gx, const double* gy, const double* gz,
+                             double* V);
 
 /* 8a-6  FuncPotential::getMatrix / getEnergy (potentials/FuncPotential.cpp:74-111), RESTRICTED.
  * V is overwritten. nelec = sum_p w_p rho_p (gridAccuracyCheck, DensityMatrixDensityOnGridController.cpp:152-160). */

@@ -157,6 +157,33 @@ def scalar_to_matrix(basis: Basis, grid: Grid, radial_thr: float, block_ave_thr:
     return V
 
 
+def scalar_to_matrix_ab(basis_a: Basis, basis_b: Basis, grid: Grid, radial_thr: float, block_ave_thr: float, v, gx=None,
+                        gy=None, gz=None):
+    """Two-basis scatter (ScalarOperatorToMatrixAdder.cpp:216-220 / :286-300): [nbf_A, nbf_B]."""
+    V = np.zeros((basis_a.nbf, basis_b.nbf), order="F")
+    c = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (v, gx, gy, gz)]
+    lib().orc_scalar_to_matrix_ab(C.byref(basis_a.c), C.byref(basis_b.c), C.byref(grid.c), C.c_double(radial_thr),
+                                  C.c_double(block_ave_thr), _p(c[0]), _p(c[1]), _p(c[2]), _p(c[3]), _p(V))
+    return V
+
+
+def build_ab(basis_a: Basis, basis_b: Basis, densities, grid: Grid, func: Functional, radial_thr=1e-9, block_ave_thr=1e-11):
+    """ABFuncPotential::getMatrix (ABFuncPotential.cpp:54-160), RESTRICTED: the densities of all (basis_C, P_C) pairs are
+    summed on the grid, the functional is evaluated once, and its potential is scattered into the A x B matrix.
+    Returns (V_AB, E_xc)."""
+    N = grid.npts
+    gga = func.is_gga
+    tot = [np.zeros(N) for _ in range(4)]
+    for bc, P in densities:
+        rho, g, _, _ = density_on_grid(bc, grid, radial_thr, P, 1)
+        tot[0] += rho
+        for k in range(3):
+            tot[1 + k] += g[k]
+    e, out = functional_on_grid(func, grid.w, tot[0], *(tot[1:] if gga else (None,) * 3))
+    V = scalar_to_matrix_ab(basis_a, basis_b, grid, radial_thr, block_ave_thr, out[1], *(out[2:5] if gga else (None,) * 3))
+    return V, e
+
+
 def build_xc(basis: Basis, grid: Grid, func: Functional, P, radial_thr=1e-9, block_ave_thr=1e-11):
     P = np.asfortranarray(P, dtype=np.float64)
     V = np.zeros((basis.nbf, basis.nbf), order="F")

@@ -234,6 +234,136 @@ k_vmat(PlanView plan, int nbf, const WorkItem* __restrict__ items, int nitems, i
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// K4-AB: two-basis scatter: ScalarOperatorToMatrixAdder::addBlock for basis A != basis B
+// (ScalarOperatorToMatrixAdder.cpp:216-220 LDA, :286-300 GGA), the operator of ABFuncPotential / ABNAddFuncPotential:
+//     m_AB += pA [ phi_A^T diag(a) phi_B + phi_A^T grad_B + grad_A^T phi_B ] pB^T,   grad_X = sum_c diag(b_c) d_c phi_X.
+// With G_A = grad_A (k_form_g, a_scale = 0) and G_B = a phi_B + grad_B (a_scale = 1) every 32 x 32 tile is the same stacked
+// product as in k_vmat,  U[I, J] = [phi_A,I | G_A,I] . [G_B,J | phi_B,J]^T, over the full s_A x s_B rectangle.  Rounds are
+// formed on the fly: a band of two A row groups against four B column groups = 8 warp tiles on 6 staged groups.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(scat::THREADS, 2)
+k_vmat_ab(PlanView planA, PlanView planB, int nbfA, const int* __restrict__ order, int nitems, int* __restrict__ counter,
+          const int* __restrict__ skipA, const int* __restrict__ skipB, const double* __restrict__ phiA,
+          const double* __restrict__ phiB, double* __restrict__ W) {
+  using namespace scat;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* stage_base = reinterpret_cast<double*>(smem_raw);
+  __shared__ int s_next;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lc = lane & 3;
+  const int wi = warp >> 2, wj = warp & 3;  // this warp's A slot (0, 1) and B slot (2 + wj)
+
+  for (;;) {
+    __syncthreads();  // the ring of the previous block is no longer read
+    if (tid == 0) s_next = atomicAdd(counter, 1);
+    __syncthreads();
+    const int qi = s_next;
+    if (qi >= nitems) break;
+    const int q = order[qi];  // both plans own the same blocks in the same slots
+    if (skipA[q] || skipB[q]) continue;
+    const int sA = planA.s[q], sB = planB.s[q];
+    const int spA = planA.s_pad[q], spB = planB.s_pad[q];
+    const double* __restrict__ tA = phiA + planA.phi_off[q];
+    const double* __restrict__ tB = phiB + planB.phi_off[q];
+    const size_t gA = (size_t)4 * spA * BP, gB = (size_t)4 * spB * BP;  // offset of the G slot
+    const int* __restrict__ sigA = planA.sig_bf + (size_t)q * planA.nbf_pad;
+    const int* __restrict__ sigB = planB.sig_bf + (size_t)q * planB.nbf_pad;
+    const int nA32 = spA >> 5, nB32 = spB >> 5;
+    const int njb = (nB32 + 3) >> 2;
+    const int nr = ((nA32 + 1) >> 1) * njb;
+
+    // producer: thread (rr, c16) copies 16 B of row rr (32 phi rows, then 32 G rows) of every staged group
+    const int rr = tid >> 2, c16 = tid & 3;
+    const size_t row_off = (size_t)(rr & 31) * BP + c16 * 2;
+    const double* srcA = tA + ((rr & 32) ? gA : 0) + row_off;
+    const double* srcB = tB + ((rr & 32) ? gB : 0) + row_off;
+    const int dst_off = rr * STRIDE + c16 * 2;
+    int is_r = 0, is_kc = 0, is_stage = 0;
+    auto issue = [&]() {
+      if (is_r < nr) {
+        const int ib = is_r / njb, jb = is_r - ib * njb;
+        double* st = stage_base + is_stage * STAGE_ELEMS + dst_off;
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          if (2 * ib + i < nA32) cp_async16(st + i * GROUP_ELEMS, srcA + (size_t)(2 * ib + i) * (32 * BP) + is_kc * TKP);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (4 * jb + j < nB32)
+            cp_async16(st + (2 + j) * GROUP_ELEMS, srcB + (size_t)(4 * jb + j) * (32 * BP) + is_kc * TKP);
+        if (++is_kc == NKC) {
+          is_kc = 0;
+          ++is_r;
+        }
+        is_stage = (is_stage + 1 == STAGES) ? 0 : is_stage + 1;
+      }
+      cp_async_commit();
+    };
+
+    double acc[4][4][2];
+    issue();
+    issue();
+    int c_stage = 0;
+    for (int r = 0; r < nr; ++r) {
+      const int ib = r / njb, jb = r - ib * njb;
+      const int gI = 2 * ib + wi, gJ = 4 * jb + wj;
+      const bool active = gI < nA32 && gJ < nB32;
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int nn = 0; nn < 4; ++nn) acc[m][nn][0] = acc[m][nn][1] = 0.0;
+      for (int kc = 0; kc < NKC; ++kc) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        issue();
+        const double* st = stage_base + c_stage * STAGE_ELEMS;
+        c_stage = (c_stage + 1 == STAGES) ? 0 : c_stage + 1;
+        if (active) {
+          const double* sI = st + wi * GROUP_ELEMS;        // phi_A rows 0..31, G_A rows 32..63
+          const double* sJ = st + (2 + wj) * GROUP_ELEMS;  // phi_B rows 0..31, G_B rows 32..63
+#pragma unroll
+          for (int ks = 0; ks < TKP / 4; ++ks) {
+            double a1[4], a2[4], b1[4], b2[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              const int o = (m * 8 + lr) * STRIDE + ks * 4 + lc;
+              a1[m] = sI[o];
+              a2[m] = sI[o + 32 * STRIDE];
+              b2[m] = sJ[o];
+              b1[m] = sJ[o + 32 * STRIDE];
+            }
+#pragma unroll
+            for (int m = 0; m < 4; ++m)
+#pragma unroll
+              for (int nn = 0; nn < 4; ++nn) {
+                dmma884(acc[m][nn][0], acc[m][nn][1], a1[m], b1[nn]);
+                dmma884(acc[m][nn][0], acc[m][nn][1], a2[m], b2[nn]);
+              }
+          }
+        }
+      }
+      if (active) {  // m_AB += pA U pB^T
+        const int i0 = gI * 32, j0 = gJ * 32;
+#pragma unroll
+        for (int nn = 0; nn < 4; ++nn)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int j = j0 + nn * 8 + 2 * lc + e;
+            if (j >= sB) continue;
+            const size_t col = (size_t)sigB[j] * nbfA;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              const int i = i0 + m * 8 + lr;
+              if (i < sA) atomicAdd(W + col + sigA[i], acc[m][nn][e]);
+            }
+          }
+      }
+    }
+    cp_async_wait<0>();
+  }
+}
+
 // V[j,i] = V[i,j] for i < j (column-major, upper triangle holds the sums)
 __global__ void k_mirror(int nbf, double* __restrict__ V) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -161,6 +161,7 @@ struct sxc_ctx {
   std::map<std::pair<int, int>, std::unique_ptr<Plan>> plans;
   std::map<int, std::vector<ScatterRound>> scatter_tpl;  // round templates per s_pad / 32
   DevMem phi;     // tile workspace (one chunk)
+  DevMem phi2;    // second tile workspace: basis B of the two-basis scatter (row f-4)
   DevMem dP;      // staged density matrices (host API)
   DevMem dOut;    // staged V | E | N (host API)
   DevMem scratch; // small device scalars
@@ -229,6 +230,7 @@ int set_kernel_attrs(sxc_ctx* ctx) {
   CU(cudaFuncSetAttribute(k_density, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CU(cudaFuncSetAttribute(k_grad_contract, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CU(cudaFuncSetAttribute(k_vmat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scat::smem_bytes()));
+  CU(cudaFuncSetAttribute(k_vmat_ab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scat::smem_bytes()));
   ctx->attrs_set = true;
   return SXC_OK;
 }
@@ -617,11 +619,12 @@ int ensure_point_arrays(sxc_ctx* ctx, Grid& g, bool nadd, int nspin) {
 }
 
 // phases of one chunk ------------------------------------------------------------------------------------------
-int phase_basis(sxc_ctx* ctx, const Grid& g, const Basis& b, const Plan& p, const Chunk& c) {
-  CU(ctx->phi.ensure(c.doubles * sizeof(double)));
+int phase_basis(sxc_ctx* ctx, const Grid& g, const Basis& b, const Plan& p, const Chunk& c, DevMem* buf = nullptr) {
+  DevMem& phi = buf ? *buf : ctx->phi;
+  CU(phi.ensure(c.doubles * sizeof(double)));
   PhaseTimer t(ctx, SXC_T_BASIS);
   k_basis<<<c.nslots, BASIS_GROUPS * BP, 0, ctx->stream>>>(g.view(), b.view(), p.view(), c.slot0,
-                                                            p.order.as<int>() + c.order_off, ctx->phi.as<double>());
+                                                            p.order.as<int>() + c.order_off, phi.as<double>());
   LAUNCH_CHECK();
   return SXC_OK;
 }
@@ -702,6 +705,46 @@ int phase_scatter(sxc_ctx* ctx, const Grid& g, const Basis& b, const Plan& p, co
       p.view(), b.nbf, p.vitems.as<WorkItem>() + c.vitem_off, c.nvitems, counter, p.skip.as<int>(), p.tpl.as<ScatterRound>(),
       p.tpl_off.as<int>(), ctx->phi.as<double>(), dW);
   LAUNCH_CHECK();
+  return SXC_OK;
+}
+
+// two-basis scatter of one spin: tiles of A in ctx->phi, of B in ctx->phi2 (both plans single-chunk, same blocks / slots)
+int phase_scatter_ab(sxc_ctx* ctx, const Grid& g, const Basis& bA, const Plan& pA, const Plan& pB, bool gga,
+                     double block_ave_thr, const double* pot4, double* dW) {
+  const long N = g.npts;
+  const Chunk& cA = pA.chunks[0];
+  const Chunk& cB = pB.chunks[0];
+  if (cA.nslots == 0) return SXC_OK;
+  {
+    PhaseTimer t(ctx, SXC_T_FORM_G);  // G_A = grad_A (no scalar part), G_B = a phi_B + grad_B
+    k_form_g<<<cA.nslots, 256, 0, ctx->stream>>>(g.view(), pA.view(), pA.order.as<int>() + cA.order_off, block_ave_thr, 0.0,
+                                                 pot4, gga ? pot4 + N : nullptr, gga ? pot4 + 2 * N : nullptr,
+                                                 gga ? pot4 + 3 * N : nullptr, ctx->phi.as<double>(), pA.skip.as<int>());
+    LAUNCH_CHECK();
+    k_form_g<<<cB.nslots, 256, 0, ctx->stream>>>(g.view(), pB.view(), pB.order.as<int>() + cB.order_off, block_ave_thr, 1.0,
+                                                 pot4, gga ? pot4 + N : nullptr, gga ? pot4 + 2 * N : nullptr,
+                                                 gga ? pot4 + 3 * N : nullptr, ctx->phi2.as<double>(), pB.skip.as<int>());
+    LAUNCH_CHECK();
+  }
+  int* counter = nullptr;
+  TRY(next_counter(ctx, &counter));
+  PhaseTimer t(ctx, SXC_T_SCATTER);
+  const int grid = std::min(cA.nslots, 2 * ctx->num_sms);
+  k_vmat_ab<<<grid, scat::THREADS, scat::smem_bytes(), ctx->stream>>>(
+      pA.view(), pB.view(), bA.nbf, pA.order.as<int>() + cA.order_off, cA.nslots, counter, pA.skip.as<int>(),
+      pB.skip.as<int>(), ctx->phi.as<double>(), ctx->phi2.as<double>(), dW);
+  LAUNCH_CHECK();
+  return SXC_OK;
+}
+
+int ab_plans(sxc_ctx* ctx, int gh, int bA, int bB, Plan** pa, Plan** pb) {
+  if (!get_grid(ctx, gh) || !get_basis(ctx, bA) || !get_basis(ctx, bB))
+    return fail(ctx, SXC_ERR_INVALID, "invalid grid (%d) or basis (%d, %d) handle", gh, bA, bB);
+  TRY(get_plan(ctx, gh, bA, pa));
+  TRY(get_plan(ctx, gh, bB, pb));
+  if ((*pa)->chunks.size() > 1 || (*pb)->chunks.size() > 1)
+    return fail(ctx, SXC_ERR_UNSUPPORTED, "the two-basis scatter needs the tiles of both bases resident at once "
+                                           "(raise sxc_set_workspace_limit)");
   return SXC_OK;
 }
 
@@ -948,9 +991,80 @@ int build_gradient_device(sxc_ctx* ctx, int gh, int bh, int fh, int nspin, const
 }  // namespace
 
 // ================================================================================================ C ABI
+// ABFuncPotential<SCFMode>::getMatrix (potentials/ABFockMatrixConstruction/ABFuncPotential.cpp:54-160): the densities of all
+// (basis_C, P_C) pairs are summed on the grid, the functional is evaluated once, its potential is scattered into the
+// nbf_A x nbf_B matrix.  dVE = [nspin * nA * nB | E_xc | N_el].
+int build_ab_device(sxc_ctx* ctx, int gh, int fh, int nspin, int bA, int bB, int ndens, const int* bC,
+                    const double* const* dPC, double thr, double* dVE) {
+  if (nspin != 1 && nspin != 2) return fail(ctx, SXC_ERR_INVALID, "nspin must be 1 (RESTRICTED) or 2 (UNRESTRICTED)");
+  if (fh < 0 || fh >= (int)ctx->funcs.size()) return fail(ctx, SXC_ERR_INVALID, "invalid functional handle %d", fh);
+  if (ndens <= 0) return fail(ctx, SXC_ERR_INVALID, "at least one density matrix is needed");
+  Plan *pa = nullptr, *pb = nullptr;
+  TRY(ab_plans(ctx, gh, bA, bB, &pa, &pb));
+  Grid& g = *get_grid(ctx, gh);
+  Basis& ba = *get_basis(ctx, bA);
+  Basis& bb = *get_basis(ctx, bB);
+  const FuncView f = ctx->funcs[fh];
+  for (int i = 0; i < ndens; ++i) {
+    Plan* pc = nullptr;
+    if (!get_basis(ctx, bC[i])) return fail(ctx, SXC_ERR_INVALID, "invalid density basis handle %d", bC[i]);
+    TRY(get_plan(ctx, gh, bC[i], &pc));
+  }
+  TRY(ensure_point_arrays(ctx, g, true, nspin));
+  const long N = g.npts;
+  const int ncomp = 4 * nspin;
+  const size_t nab = (size_t)ba.nbf * bb.nbf;
+  double* parts = g.parts.as<double>();
+  double* dens = g.dens.as<double>();
+  double* tot = g.tot.as<double>();
+  double* pot = g.pot.as<double>();
+  ctx->stats = pa->stats;
+  begin_timing(ctx, true);
+  const int launches0 = ctx->launches;
+  {
+    PhaseTimer t_all(ctx, T_TOTAL);
+    CU(cudaMemsetAsync(dVE, 0, (nspin * nab + 2) * sizeof(double), ctx->stream));
+    CU(cudaMemsetAsync(parts, 0, (size_t)3 * std::max(g.nlit, 1) * sizeof(double), ctx->stream));
+    CU(cudaMemsetAsync(tot, 0, (size_t)ncomp * N * sizeof(double), ctx->stream));
+    TRY(wait_p_ready(ctx));
+    for (int i = 0; i < ndens; ++i) {  // rho += rho_C, grad rho += grad rho_C  (ABFuncPotential.cpp:66-90)
+      Basis& bc = *get_basis(ctx, bC[i]);
+      const size_t nc2 = (size_t)bc.nbf * bc.nbf;
+      Plan* pc = nullptr;
+      TRY(get_plan(ctx, gh, bC[i], &pc));
+      TRY(run_screen(ctx, g, bc, *pc));
+      for (const Chunk& c : pc->chunks) {
+        TRY(phase_basis(ctx, g, bc, *pc, c));
+        for (int sp = 0; sp < nspin; ++sp)
+          TRY(phase_density(ctx, g, bc, *pc, c, dPC[i] + sp * nc2, dens + (size_t)4 * sp * N, true, nullptr));
+        if (pc->nown) {
+          PhaseTimer t(ctx, SXC_T_DENSITY);
+          k_add4<<<c.nslots, 128, 0, ctx->stream>>>(N, g.blocksize, ncomp, pc->block_id.as<int>() + c.slot0, tot, dens, tot);
+          LAUNCH_CHECK();
+        }
+      }
+    }
+    TRY(phase_functional(ctx, g, *pa, pa->chunks.empty() ? Chunk() : pa->chunks[0], f, nspin, tot, 1.0, 0, pot, parts,
+                         parts + g.nlit));
+    if (f.ncomp > 0 && !pa->chunks.empty()) {
+      TRY(run_screen(ctx, g, ba, *pa));
+      TRY(run_screen(ctx, g, bb, *pb));
+      TRY(phase_basis(ctx, g, ba, *pa, pa->chunks[0]));
+      TRY(phase_basis(ctx, g, bb, *pb, pb->chunks[0], &ctx->phi2));
+      for (int sp = 0; sp < nspin; ++sp)
+        TRY(phase_scatter_ab(ctx, g, ba, *pa, *pb, f.gga != 0, thr, pot + (size_t)4 * sp * N, dVE + sp * nab));
+    }
+    TRY(reduce_to(ctx, parts, g.nlit, dVE + nspin * nab));
+    TRY(reduce_to(ctx, parts + g.nlit, g.nlit, dVE + nspin * nab + 1));
+  }
+  ctx->timing = false;
+  ctx->stats.kernel_launches = ctx->launches - launches0;
+  return SXC_OK;
+}
+
 extern "C" {
 
-int sxc_abi_version(void) { return 3; }
+int sxc_abi_version(void) { return 4; }
 
 // host-only: contiguous ranges [bounds[r], bounds[r+1]) of nearly equal summed cost
 int sxc_balance_ranges(int n, const double* cost, int world, int* bounds) {
@@ -1393,6 +1507,79 @@ int sxc_scalar_to_matrix(sxc_ctx* ctx, int grid, int basis, double thr, const do
   CU(cudaMemcpyAsync(h.data(), ctx->dOut.p, nb2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   for (size_t i = 0; i < nb2; ++i) V[i] += h[i];  // the reference adds into the caller's matrix
+  return SXC_OK;
+}
+
+int sxc_scalar_to_matrix_ab(sxc_ctx* ctx, int grid, int basis_a, int basis_b, double thr, const double* v, const double* gx,
+                            const double* gy, const double* gz, double* V) {
+  if (!ctx || !v || !V) return fail(ctx, SXC_ERR_INVALID, "sxc_scalar_to_matrix_ab: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  Plan *pa = nullptr, *pb = nullptr;
+  TRY(ab_plans(ctx, grid, basis_a, basis_b, &pa, &pb));
+  Grid& g = *get_grid(ctx, grid);
+  Basis& ba = *get_basis(ctx, basis_a);
+  Basis& bb = *get_basis(ctx, basis_b);
+  TRY(ensure_point_arrays(ctx, g, false, 1));
+  const size_t nab = (size_t)ba.nbf * bb.nbf;
+  const long N = g.npts;
+  const bool gga = gx != nullptr;
+  if (gga && !(gy && gz)) return fail(ctx, SXC_ERR_INVALID, "gradient operator needs all three components");
+  CU(ctx->dOut.ensure((nab + 2) * sizeof(double)));
+  double* pot = g.pot.as<double>();
+  CU(cudaMemcpyAsync(pot, v, N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (gga) {
+    CU(cudaMemcpyAsync(pot + N, gx, N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(pot + 2 * N, gy, N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(pot + 3 * N, gz, N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CU(cudaMemsetAsync(ctx->dOut.p, 0, nab * sizeof(double), ctx->stream));
+  if (!pa->chunks.empty()) {
+    TRY(run_screen(ctx, g, ba, *pa));
+    TRY(run_screen(ctx, g, bb, *pb));
+    TRY(phase_basis(ctx, g, ba, *pa, pa->chunks[0]));
+    TRY(phase_basis(ctx, g, bb, *pb, pb->chunks[0], &ctx->phi2));
+    TRY(phase_scatter_ab(ctx, g, ba, *pa, *pb, gga, thr, pot, ctx->dOut.as<double>()));
+  }
+  std::vector<double> h(nab);
+  CU(cudaMemcpyAsync(h.data(), ctx->dOut.p, nab * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (size_t i = 0; i < nab; ++i) V[i] += h[i];  // the reference adds into the caller's matrix
+  return SXC_OK;
+}
+
+int sxc_build_ab(sxc_ctx* ctx, int grid, int func, int nspin, int basis_a, int basis_b, int ndens, const int* basis_c,
+                 const double* const* P_c, double thr, double* V_ab, double* E) {
+  if (!ctx || !V_ab || !E || ndens <= 0 || !basis_c || !P_c) return fail(ctx, SXC_ERR_INVALID, "sxc_build_ab: bad arguments");
+  if (nspin != 1 && nspin != 2) return fail(ctx, SXC_ERR_INVALID, "nspin must be 1 or 2");
+  Basis* ba = get_basis(ctx, basis_a);
+  Basis* bb = get_basis(ctx, basis_b);
+  if (!ba || !bb) return fail(ctx, SXC_ERR_INVALID, "invalid basis handle (%d, %d)", basis_a, basis_b);
+  CU(cudaSetDevice(ctx->device));
+  const size_t nab = (size_t)nspin * ba->nbf * bb->nbf;
+  size_t total = 0;
+  std::vector<size_t> offs(ndens);
+  for (int i = 0; i < ndens; ++i) {
+    Basis* bc = get_basis(ctx, basis_c[i]);
+    if (!bc || !P_c[i]) return fail(ctx, SXC_ERR_INVALID, "invalid density basis handle %d", basis_c[i]);
+    offs[i] = total;
+    total += (size_t)nspin * bc->nbf * bc->nbf;
+  }
+  CU(ctx->dP.ensure(total * sizeof(double)));
+  CU(ctx->dOut.ensure((nab + 2) * sizeof(double)));
+  std::vector<const double*> dpc(ndens);
+  for (int i = 0; i < ndens; ++i) {
+    Basis* bc = get_basis(ctx, basis_c[i]);
+    dpc[i] = ctx->dP.as<double>() + offs[i];
+    TRY(upload_async(ctx, ctx->dP.as<double>() + offs[i], P_c[i], (size_t)nspin * bc->nbf * bc->nbf * sizeof(double)));
+  }
+  TRY(upload_done(ctx));
+  int rc = build_ab_device(ctx, grid, func, nspin, basis_a, basis_b, ndens, basis_c, dpc.data(), thr, ctx->dOut.as<double>());
+  ctx->timing = false;
+  if (rc != SXC_OK) return rc;
+  CU(cudaMemcpyAsync(V_ab, ctx->dOut.p, nab * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(E, ctx->dOut.as<double>() + nab, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  collect_timers(ctx);
   return SXC_OK;
 }
 

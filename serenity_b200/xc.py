@@ -206,6 +206,35 @@ class XCContext:
                                                    _ptr(_f64(gz)) if gga else None, _ptr(V)))
         return V
 
+    def scalar_to_matrix_ab(self, grid, basis_a, basis_b, nbf_a, nbf_b, v, gx=None, gy=None, gz=None,
+                            block_ave_threshold: float = 1e-11, V=None):
+        """Two-basis scatter (ScalarOperatorToMatrixAdder.cpp:216-220 / :286-300): V [nbf_a, nbf_b] is added to."""
+        if V is None:
+            V = np.zeros((nbf_a, nbf_b), order="F")
+        gga = gx is not None
+        self._check(self._lib.sxc_scalar_to_matrix_ab(self._h, grid, basis_a, basis_b, block_ave_threshold, _ptr(_f64(v)),
+                                                      _ptr(_f64(gx)) if gga else None, _ptr(_f64(gy)) if gga else None,
+                                                      _ptr(_f64(gz)) if gga else None, _ptr(V)))
+        return V
+
+    def build_ab(self, grid, func, basis_a, basis_b, nbf_a, nbf_b, basis_c, P_c, block_ave_threshold: float = 1e-11,
+                 nspin: int = 1):
+        """ABFuncPotential::getMatrix (ABFuncPotential.cpp:54-160).  basis_c / P_c: handles and density matrices whose
+        densities are summed; nspin = 2: every P_c is a (P_alpha, P_beta) pair and (V_alpha, V_beta) is returned.
+        Returns (V_ab [nbf_a, nbf_b], E_xc, integral of the density)."""
+        if nspin == 2:
+            mats = [_spin_pack(p) for p in P_c]
+        else:
+            mats = [np.asfortranarray(p, dtype=np.float64) for p in P_c]
+        V = np.zeros((nspin, nbf_a * nbf_b))
+        ptrs = (C.c_void_p * len(mats))(*[m.ctypes.data for m in mats])
+        hb = np.ascontiguousarray(basis_c, dtype=np.int32)
+        E = (C.c_double * 2)()
+        self._check(self._lib.sxc_build_ab(self._h, grid, func, nspin, basis_a, basis_b, len(mats), _ptr(hb), ptrs,
+                                           block_ave_threshold, _ptr(V), E))
+        out = [np.asfortranarray(V[s].reshape(nbf_a, nbf_b, order="F")) for s in range(nspin)]
+        return (tuple(out) if nspin == 2 else out[0]), E[0], E[1]
+
     def partition_weights(self, flavour: str, coords, xyz, parent, w, aij=None, smoothing: int = 3):
         """GridFactory.cpp:139-266 on the device: molecular partition weights (BECKE / SSF) of the atoms' reference
         grids.  xyz [N, 3] points (already shifted to their nuclei), parent [N] atom index, w [N] atomic weights;
