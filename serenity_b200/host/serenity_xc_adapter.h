@@ -318,5 +318,55 @@ class NAddFuncPotential : public Potential<SCFMode>, public ObjectSensitive {
   bool _envFrozen = false;
 };
 
+// potentials/ABFockMatrixConstruction/ABFuncPotential.h: the XC operator between two different basis
+// sets A and B on one grid, from the sum of the densities of `dMats` (each in its own basis).  getMatrix() returns the
+// nbf_A x nbf_B matrix (UNRESTRICTED: alpha and beta blocks side by side) and caches it until a density, the grid or a
+// basis notifies (ABFuncPotential.cpp:40-52).
+template<Options::SCF_MODES SCFMode>
+class ABFuncPotential : public ObjectSensitive {
+ public:
+  ABFuncPotential(std::shared_ptr<B200::XCDevice> device, std::shared_ptr<BasisController> basisA,
+                  std::shared_ptr<BasisController> basisB, std::shared_ptr<GridController> grid,
+                  std::vector<std::shared_ptr<DensityMatrixController<SCFMode>>> dMats, Functional functional,
+                  double blockAveThreshold = 1e-11)
+    : _dev(std::move(device)), _basisA(std::move(basisA)), _basisB(std::move(basisB)), _grid(std::move(grid)),
+      _dMats(std::move(dMats)), _functional(std::move(functional)), _thr(blockAveThreshold),
+      _func(detail::functionalHandle(*_dev, _functional)) {
+    if (_dMats.empty()) throw SerenityError("ABFuncPotential: at least one density matrix controller is needed");
+  }
+  void registerSensitivity(const std::shared_ptr<ABFuncPotential>& self) {
+    for (auto& d : _dMats) d->addSensitiveObject(self);
+    _grid->addSensitiveObject(self);
+  }
+  Matrix& getMatrix() {  // ABFuncPotential.cpp:54-160
+    if (!_abPotential) {
+      const int nA = (int)_basisA->getNBasisFunctions(), nB = (int)_basisB->getNBasisFunctions();
+      auto V = std::make_unique<Matrix>(nA, nB * detail::nspin<SCFMode>());
+      std::vector<int> bc;
+      std::vector<const double*> pc;
+      for (auto& d : _dMats) {
+        bc.push_back(d->getBasisController()->handle(*_dev));
+        pc.push_back(d->getDensityMatrix().data());
+      }
+      double e[2] = {0.0, 0.0};
+      _dev->check(sxc_build_ab(_dev->get(), _grid->handle(*_dev), _func, detail::nspin<SCFMode>(), _basisA->handle(*_dev),
+                               _basisB->handle(*_dev), (int)bc.size(), bc.data(), pc.data(), _thr, V->data(), e));
+      _abPotential = std::move(V);
+    }
+    return *_abPotential;
+  }
+  void notify() override final { _abPotential = nullptr; }
+
+ private:
+  std::shared_ptr<B200::XCDevice> _dev;
+  std::shared_ptr<BasisController> _basisA, _basisB;
+  std::shared_ptr<GridController> _grid;
+  std::vector<std::shared_ptr<DensityMatrixController<SCFMode>>> _dMats;
+  Functional _functional;
+  double _thr;
+  int _func;
+  std::unique_ptr<Matrix> _abPotential;
+};
+
 }  // namespace Serenity
 #endif

@@ -106,6 +106,13 @@ int main(int argc, char** argv) {
     // XC nuclear gradient of the active system (FuncPotential_test.cpp:234-330 pattern)
     Matrix grad = pot->getGeomGradients();
     wr(out, grad.data(), (int64_t)grad.rows() * 3);
+    // the XC operator between the two different basis sets from the sum of both densities (ABFuncPotential.cpp:54-160)
+    auto abPot = std::make_shared<ABFuncPotential<R::RESTRICTED>>(
+        dev, basisA, basisB, grid, std::vector<std::shared_ptr<DensityMatrixController<R::RESTRICTED>>>{dA, dB}, xc);
+    abPot->registerSensitivity(abPot);
+    Matrix& Vab = abPot->getMatrix();
+    if (&abPot->getMatrix() != &Vab) throw SerenityError("ABFuncPotential::getMatrix() must cache");
+    wr(out, Vab.data(), (int64_t)nA * nB);
     // error convention: SerenityError, as the reference throws
     bool threw = false;
     try {

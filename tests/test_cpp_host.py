@@ -73,6 +73,7 @@ def test_cpp_potentials_match_oracle(tmp_path):
     with open(fout, "rb") as f:
         got = [(_r(f, (nA, nA)), _r(f)) for _ in range(5)]
         grad = _r(f, (len(act.symbols), 3))
+        Vab = _r(f, (nA, env.basis.nbf))
     og = orc.Grid(cfg.xyz, cfg.w, 128)
     bA, bE = orc.Basis(act.basis), orc.Basis(env.basis)
 
@@ -90,3 +91,5 @@ def test_cpp_potentials_match_oracle(tmp_path):
     from serenity_b200.inputs.basis import atom_indices_of_basis
     grad_ref = orc.xc_gradient(bA, og, orc.Functional(*xc), PA2, atom_indices_of_basis(act.basis, act.coords), len(act.symbols))
     assert np.abs(grad - grad_ref).max() <= 1e-9
+    Vab_ref, _ = orc.build_ab(bA, bE, [(bA, PA2), (bE, env.P)], og, orc.Functional(*xc))
+    assert np.abs(Vab - Vab_ref).max() <= 1e-8
