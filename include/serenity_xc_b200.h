@@ -163,6 +163,11 @@ int sxc_build_nadd_device(sxc_ctx* ctx, int grid, int func, int nspin, int basis
  * sxc_build_xc.  With a shard set, grad is this rank's partial sum. */
 int sxc_xc_gradient(sxc_ctx* ctx, int grid, int basis, int func, int nspin, const double* P, int natoms,
                     const int* atom_of_bf, double* grad);
+/* NAddFuncPotential<SCFMode>::getGeomGradients (potentials/NAddFuncPotential.cpp:329-493): the same contraction with the
+ * non-additive potential v[rho_act + sum rho_env] - v[rho_act] and the ACTIVE density matrix; grad [natoms x 3]
+ * column-major over the atoms of the active system (atom_of_bf maps its basis functions to them). */
+int sxc_nadd_gradient(sxc_ctx* ctx, int grid, int func, int nspin, int basis_act, const double* P_act, int nenv,
+                      const int* basis_env, const double* const* P_env, int natoms, const int* atom_of_bf, double* grad);
 
 /* ---- stage-level entry points (the reference classes one level below the Potentials) -------------------- */
 /* DensityOnGridCalculator::calcDensityAndGradientOnGrid (DensityOnGridCalculator.cpp:55-65): host outputs [N];

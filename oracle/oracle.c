@@ -901,25 +901,14 @@ int orc_build_nadd_u(const orc_basis* bA, const double* PAa, const double* PAb, 
 /* ------------------------------------------------------------------------------------------------
  * row f-3  FuncPotential::getGeomGradients, potentials/FuncPotential.cpp:114-239
  * ------------------------------------------------------------------------------------------------ */
-int orc_xc_gradient(const orc_basis* b, const orc_grid* g, const orc_functional* f, double radial_thr, int nspin,
-                    const double* Pa, const double* Pb, int natoms, const int* atom_of_bf, double* grad) {
+/* the O(s^2 n) double loop of FuncPotential.cpp:145-233 / NAddFuncPotential.cpp:383-490 for a given potential on the grid:
+ * vr [nspin][N], vg [nspin][3][N] */
+static void xc_gradient_contract(const orc_basis* b, const orc_grid* g, double radial_thr, int nspin, const double* const* Ps,
+                                 const double* vr, const double* vg, int gga, int natoms, const int* atom_of_bf,
+                                 double* grad) {
   const long N = g->npts;
   const int nbf = b->nbf;
-  const int gga = orc_functional_is_gga(f);
   const int nblocks = orc_nblocks(g);
-  /* rho[2][N], grad[2][3][N], epuv[N], vr[2][N], vg[2][3][N] (restricted uses the first halves) */
-  double* buf = (double*)calloc(17 * (size_t)N, sizeof(double));
-  if (!buf) return -1;
-  double *rho = buf, *gr = rho + 2 * N, *ep = gr + 6 * N, *vr = ep + N, *vg = vr + 2 * N;
-  const double* Ps[2] = {Pa, Pb};
-  if (nspin == 1) {
-    orc_density_on_grid(b, g, radial_thr, Pa, rho, gr, gr + N, gr + 2 * N, NULL, NULL);
-    orc_functional_on_grid(f, N, g->w, rho, gga ? gr : NULL, gr + N, gr + 2 * N, ep, vr, gga ? vg : NULL, vg + N, vg + 2 * N);
-  } else {
-    orc_density_on_grid(b, g, radial_thr, Pa, rho, gr, gr + N, gr + 2 * N, NULL, NULL);
-    orc_density_on_grid(b, g, radial_thr, Pb, rho + N, gr + 3 * N, gr + 4 * N, gr + 5 * N, NULL, NULL);
-    orc_functional_on_grid_u(f, N, g->w, rho, gga ? gr : NULL, ep, vr, gga ? vg : NULL);
-  }
   memset(grad, 0, sizeof(double) * 3 * (size_t)natoms);
 #pragma omp parallel
   {
@@ -979,6 +968,55 @@ int orc_xc_gradient(const orc_basis* b, const orc_grid* g, const orc_functional*
     free(priv);
     ws_free(&w);
   }
+}
+
+int orc_xc_gradient(const orc_basis* b, const orc_grid* g, const orc_functional* f, double radial_thr, int nspin,
+                    const double* Pa, const double* Pb, int natoms, const int* atom_of_bf, double* grad) {
+  const long N = g->npts;
+  const int gga = orc_functional_is_gga(f);
+  /* rho[2][N], grad[2][3][N], epuv[N], vr[2][N], vg[2][3][N] (restricted uses the first halves) */
+  double* buf = (double*)calloc(17 * (size_t)N, sizeof(double));
+  if (!buf) return -1;
+  double *rho = buf, *gr = rho + 2 * N, *ep = gr + 6 * N, *vr = ep + N, *vg = vr + 2 * N;
+  const double* Ps[2] = {Pa, Pb};
+  if (nspin == 1) {
+    orc_density_on_grid(b, g, radial_thr, Pa, rho, gr, gr + N, gr + 2 * N, NULL, NULL);
+    orc_functional_on_grid(f, N, g->w, rho, gga ? gr : NULL, gr + N, gr + 2 * N, ep, vr, gga ? vg : NULL, vg + N, vg + 2 * N);
+  } else {
+    orc_density_on_grid(b, g, radial_thr, Pa, rho, gr, gr + N, gr + 2 * N, NULL, NULL);
+    orc_density_on_grid(b, g, radial_thr, Pb, rho + N, gr + 3 * N, gr + 4 * N, gr + 5 * N, NULL, NULL);
+    orc_functional_on_grid_u(f, N, g->w, rho, gga ? gr : NULL, ep, vr, gga ? vg : NULL);
+  }
+  xc_gradient_contract(b, g, radial_thr, nspin, Ps, vr, vg, gga, natoms, atom_of_bf, grad);
   free(buf);
   return 0;
 }
+
+/* NAddFuncPotential::getGeomGradients (NAddFuncPotential.cpp:329-493), RESTRICTED: v = v[rho_act + sum rho_env] - v[rho_act]
+ * (:331-341) contracted with the ACTIVE density matrix over the active system's basis functions and atoms. */
+int orc_nadd_gradient(const orc_basis* bA, const double* PA, int nenv, const orc_basis* const* bE, const double* const* PE,
+                      const orc_grid* g, const orc_functional* f, double radial_thr, int natoms, const int* atom_of_bf,
+                      double* grad) {
+  const long N = g->npts;
+  const int gga = orc_functional_is_gga(f);
+  /* act[4][N], tot[4][N], tmp[4][N], ep[N], vt[4][N], va[4][N] */
+  double* buf = (double*)calloc(21 * (size_t)N, sizeof(double));
+  if (!buf) return -1;
+  double *act = buf, *tot = act + 4 * N, *tmp = tot + 4 * N, *ep = tmp + 4 * N, *vt = ep + N, *va = vt + 4 * N;
+  orc_density_on_grid(bA, g, radial_thr, PA, act, act + N, act + 2 * N, act + 3 * N, NULL, NULL);
+  memcpy(tot, act, sizeof(double) * 4 * (size_t)N);
+  for (int i = 0; i < nenv; ++i) {
+    orc_density_on_grid(bE[i], g, radial_thr, PE[i], tmp, tmp + N, tmp + 2 * N, tmp + 3 * N, NULL, NULL);
+    for (size_t k = 0; k < 4 * (size_t)N; ++k) tot[k] += tmp[k];
+  }
+  orc_functional_on_grid(f, N, g->w, tot, gga ? tot + N : NULL, tot + 2 * N, tot + 3 * N, ep, vt, gga ? vt + N : NULL,
+                         vt + 2 * N, vt + 3 * N);
+  orc_functional_on_grid(f, N, g->w, act, gga ? act + N : NULL, act + 2 * N, act + 3 * N, ep, va, gga ? va + N : NULL,
+                         va + 2 * N, va + 3 * N);
+  for (size_t k = 0; k < 4 * (size_t)N; ++k) vt[k] -= va[k];
+  const double* Ps[2] = {PA, NULL};
+  xc_gradient_contract(bA, g, radial_thr, 1, Ps, vt, vt + N, gga, natoms, atom_of_bf, grad);
+  free(buf);
+  return 0;
+}
+

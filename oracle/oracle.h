@@ -132,6 +132,10 @@ int orc_build_nadd(const orc_basis* bA, const double* PA, int nenv, const orc_ba
  * nspin = 1: Pa = total density matrix, Pb ignored.  grad: natoms x 3 column-major, overwritten. */
 int orc_xc_gradient(const orc_basis* b, const orc_grid* g, const orc_functional* f, double radial_thr, int nspin,
                     const double* Pa, const double* Pb, int natoms, const int* atom_of_bf, double* grad);
+/* NAddFuncPotential::getGeomGradients (NAddFuncPotential.cpp:329-493), RESTRICTED; grad [natoms x 3] column-major */
+int orc_nadd_gradient(const orc_basis* bA, const double* PA, int nenv, const orc_basis* const* bE, const double* const* PE,
+                      const orc_grid* g, const orc_functional* f, double radial_thr, int natoms, const int* atom_of_bf,
+                      double* grad);
 
 /* ---- UNRESTRICTED (SCFMode = UNRESTRICTED: alpha/beta pairs, data/SpinPolarizedData.h) ------------------------ */
 /* pointwise spin-polarised kernel: F and dF/d(rho_a, rho_b, s_aa, s_ab, s_bb) */

@@ -278,3 +278,18 @@ def xc_gradient(basis: Basis, grid: Grid, func: Functional, P, atom_of_bf, natom
     if rc != 0:
         raise MemoryError("orc_xc_gradient failed")
     return grad
+
+
+def nadd_gradient(basis_a: Basis, P_a, env, grid: Grid, func: Functional, atom_of_bf, natoms: int, radial_thr=1e-9):
+    """NAddFuncPotential::getGeomGradients (RESTRICTED): env = [(Basis, P), ...] -> [natoms, 3] of the active system."""
+    Pa = np.asfortranarray(P_a, dtype=np.float64)
+    amap = np.ascontiguousarray(atom_of_bf, dtype=np.int32)
+    mats = [np.asfortranarray(P, dtype=np.float64) for _, P in env]
+    bptr = (C.c_void_p * max(len(env), 1))(*[C.addressof(b.c) for b, _ in env])
+    pptr = (C.c_void_p * max(len(env), 1))(*[m.ctypes.data for m in mats])
+    grad = np.zeros((natoms, 3), order="F")
+    rc = lib().orc_nadd_gradient(C.byref(basis_a.c), _p(Pa), len(env), bptr, pptr, C.byref(grid.c), C.byref(func.c),
+                                 C.c_double(radial_thr), natoms, _p(amap), _p(grad))
+    if rc != 0:
+        raise MemoryError("orc_nadd_gradient failed")
+    return grad

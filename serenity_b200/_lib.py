@@ -16,7 +16,7 @@ SYMBOLS = [
     "sxc_set_grid_shard", "sxc_add_basis", "sxc_set_functional", "sxc_build_xc", "sxc_build_xc_device",
     "sxc_build_nadd", "sxc_build_nadd_device", "sxc_xc_gradient", "sxc_density_on_grid", "sxc_basis_on_grid",
     "sxc_functional_on_grid", "sxc_functional_on_grid_u", "sxc_scalar_to_matrix", "sxc_get_stats", "sxc_balance_ranges", "sxc_abi_version",
-    "sxc_partition_weights", "sxc_last_partition_ms", "sxc_scalar_to_matrix_ab", "sxc_build_ab",
+    "sxc_partition_weights", "sxc_last_partition_ms", "sxc_scalar_to_matrix_ab", "sxc_build_ab", "sxc_nadd_gradient",
 ]
 
 
@@ -81,6 +81,7 @@ def load():
     lib.sxc_balance_ranges.argtypes = [i, vp, i, vp]
     lib.sxc_partition_weights.argtypes = [vp, i, i, i, vp, vp, i64, vp, vp, vp]
     lib.sxc_last_partition_ms.argtypes = [vp]
+    lib.sxc_nadd_gradient.argtypes = [vp, i, i, i, i, vp, i, vp, vp, i, vp, vp]
     lib.sxc_scalar_to_matrix_ab.argtypes = [vp, i, i, i, d, vp, vp, vp, vp, vp]
     lib.sxc_build_ab.argtypes = [vp, i, i, i, i, i, i, vp, vp, d, vp, vp]
     lib.sxc_last_partition_ms.restype = d

@@ -926,16 +926,27 @@ int build_nadd_device(sxc_ctx* ctx, int gh, int fh, int nspin, int bA, const dou
 
 // XC nuclear gradient (row f-3): FuncPotential<SCFMode>::getGeomGradients (FuncPotential.cpp:114-239).
 // d_gfunc [nbf][3] receives t[nu, c] (gradient_kernels.cuh); the caller folds functions into atoms with the factor -2.
-int build_gradient_device(sxc_ctx* ctx, int gh, int bh, int fh, int nspin, const double* dP, double* d_gfunc) {
+// With nenv > 0 it is NAddFuncPotential<SCFMode>::getGeomGradients (NAddFuncPotential.cpp:329-493): the potential on the
+// grid is v[rho_act + sum rho_env] - v[rho_act] (:331-341), contracted with the ACTIVE density matrix.
+int build_gradient_device(sxc_ctx* ctx, int gh, int bh, int fh, int nspin, const double* dP, double* d_gfunc, int nenv = 0,
+                          const int* bE = nullptr, const double* const* dPE = nullptr) {
   if (nspin != 1 && nspin != 2) return fail(ctx, SXC_ERR_INVALID, "nspin must be 1 (RESTRICTED) or 2 (UNRESTRICTED)");
   if (fh < 0 || fh >= (int)ctx->funcs.size()) return fail(ctx, SXC_ERR_INVALID, "invalid functional handle %d", fh);
+  if (!get_grid(ctx, gh) || !get_basis(ctx, bh)) return fail(ctx, SXC_ERR_INVALID, "invalid grid (%d) or basis (%d) handle", gh, bh);
+  // (the regular plan of the active basis fixes the block ownership before any environment plan is made)
   Plan* pp = nullptr;
   TRY(get_plan(ctx, gh, bh, &pp, GRAD_TILE_COMPS));
   Plan& p = *pp;
   Grid& g = *get_grid(ctx, gh);
   Basis& b = *get_basis(ctx, bh);
   const FuncView f = ctx->funcs[fh];
-  TRY(ensure_point_arrays(ctx, g, false, nspin));
+  const bool nadd = nenv > 0;
+  for (int i = 0; i < nenv; ++i) {
+    Plan* pe = nullptr;
+    if (!get_basis(ctx, bE[i])) return fail(ctx, SXC_ERR_INVALID, "invalid environment basis handle %d", bE[i]);
+    TRY(get_plan(ctx, gh, bE[i], &pe));
+  }
+  TRY(ensure_point_arrays(ctx, g, nadd, nspin));
   ctx->stats = p.stats;
   begin_timing(ctx, ctx->timing_device);
   const int launches0 = ctx->launches;
@@ -948,6 +959,28 @@ int build_gradient_device(sxc_ctx* ctx, int gh, int bh, int fh, int nspin, const
     PhaseTimer t_all(ctx, T_TOTAL);
     CU(cudaMemsetAsync(d_gfunc, 0, (size_t)b.nbf * 3 * sizeof(double), ctx->stream));
     CU(cudaMemsetAsync(parts, 0, (size_t)3 * std::max(g.nlit, 1) * sizeof(double), ctx->stream));
+    if (nadd) {  // sum of the environment densities on the grid (SupersystemDensityOnGridController::updateData)
+      TRY(wait_p_ready(ctx));
+      g.env_valid = false;  // the cache of sxc_build_nadd is overwritten
+      CU(cudaMemsetAsync(g.envsum.p, 0, (size_t)4 * nspin * N * sizeof(double), ctx->stream));
+      for (int i = 0; i < nenv; ++i) {
+        Basis* be = get_basis(ctx, bE[i]);
+        const size_t ne2 = (size_t)be->nbf * be->nbf;
+        Plan* pe = nullptr;
+        TRY(get_plan(ctx, gh, bE[i], &pe));
+        TRY(run_screen(ctx, g, *be, *pe));
+        for (const Chunk& c : pe->chunks) {
+          if (c.nslots == 0) continue;
+          TRY(phase_basis(ctx, g, *be, *pe, c));
+          for (int sp = 0; sp < nspin; ++sp)
+            TRY(phase_density(ctx, g, *be, *pe, c, dPE[i] + sp * ne2, dens + (size_t)4 * sp * N, true, nullptr));
+          PhaseTimer t(ctx, SXC_T_DENSITY);
+          k_add4<<<c.nslots, 128, 0, ctx->stream>>>(N, g.blocksize, 4 * nspin, pe->block_id.as<int>() + c.slot0,
+                                                    g.envsum.as<double>(), dens, g.envsum.as<double>());
+          LAUNCH_CHECK();
+        }
+      }
+    }
     TRY(run_screen(ctx, g, b, p));
     for (const Chunk& c : p.chunks) {
       if (c.nslots == 0) continue;
@@ -955,7 +988,18 @@ int build_gradient_device(sxc_ctx* ctx, int gh, int bh, int fh, int nspin, const
       TRY(wait_p_ready(ctx));
       for (int sp = 0; sp < nspin; ++sp)
         TRY(phase_density(ctx, g, b, p, c, dP + sp * nb2, dens + (size_t)4 * sp * N, true, nullptr));
-      TRY(phase_functional(ctx, g, p, c, f, nspin, dens, 1.0, 0, pot, parts, parts + g.nlit));
+      if (nadd) {  // v = v[rho_tot] - v[rho_act]
+        {
+          PhaseTimer t(ctx, SXC_T_DENSITY);
+          k_add4<<<c.nslots, 128, 0, ctx->stream>>>(N, g.blocksize, 4 * nspin, p.block_id.as<int>() + c.slot0, dens,
+                                                    g.envsum.as<double>(), g.tot.as<double>());
+          LAUNCH_CHECK();
+        }
+        TRY(phase_functional(ctx, g, p, c, f, nspin, g.tot.as<double>(), 1.0, 0, pot, parts, nullptr));
+        TRY(phase_functional(ctx, g, p, c, f, nspin, dens, -1.0, 1, pot, parts + g.nlit, nullptr));
+      } else {
+        TRY(phase_functional(ctx, g, p, c, f, nspin, dens, 1.0, 0, pot, parts, parts + g.nlit));
+      }
       if (f.ncomp == 0) continue;
       for (int sp = 0; sp < nspin; ++sp) {
         const double* pot4 = pot + (size_t)4 * sp * N;
@@ -1686,6 +1730,47 @@ int sxc_partition_weights(sxc_ctx* ctx, int flavour, int becke_smoothing, int na
 }
 
 double sxc_last_partition_ms(sxc_ctx* ctx) { return ctx ? (double)ctx->last_partition_ms : -1.0; }
+
+int sxc_nadd_gradient(sxc_ctx* ctx, int grid, int func, int nspin, int basis_act, const double* P_act, int nenv,
+                      const int* basis_env, const double* const* P_env, int natoms, const int* atom_of_bf, double* grad) {
+  if (!ctx || !P_act || !grad || !atom_of_bf || natoms <= 0 || nenv < 0 || (nenv > 0 && (!basis_env || !P_env)))
+    return fail(ctx, SXC_ERR_INVALID, "sxc_nadd_gradient: bad arguments");
+  if (nspin != 1 && nspin != 2) return fail(ctx, SXC_ERR_INVALID, "nspin must be 1 or 2");
+  Basis* b = get_basis(ctx, basis_act);
+  if (!b) return fail(ctx, SXC_ERR_INVALID, "invalid active basis handle %d", basis_act);
+  for (int i = 0; i < b->nbf; ++i)
+    if (atom_of_bf[i] < 0 || atom_of_bf[i] >= natoms) return fail(ctx, SXC_ERR_INVALID, "atom_of_bf[%d] out of range", i);
+  CU(cudaSetDevice(ctx->device));
+  const size_t nvA = (size_t)nspin * b->nbf * b->nbf;
+  size_t total = nvA;
+  std::vector<size_t> offs(nenv);
+  for (int i = 0; i < nenv; ++i) {
+    Basis* be = get_basis(ctx, basis_env[i]);
+    if (!be || !P_env[i]) return fail(ctx, SXC_ERR_INVALID, "invalid environment basis handle %d", basis_env[i]);
+    offs[i] = total;
+    total += (size_t)nspin * be->nbf * be->nbf;
+  }
+  CU(ctx->dP.ensure(total * sizeof(double)));
+  CU(ctx->dOut.ensure((size_t)b->nbf * 3 * sizeof(double)));
+  TRY(upload_async(ctx, ctx->dP.p, P_act, nvA * sizeof(double)));
+  std::vector<const double*> dpe(nenv);
+  for (int i = 0; i < nenv; ++i) {
+    Basis* be = get_basis(ctx, basis_env[i]);
+    dpe[i] = ctx->dP.as<double>() + offs[i];
+    TRY(upload_async(ctx, ctx->dP.as<double>() + offs[i], P_env[i], (size_t)nspin * be->nbf * be->nbf * sizeof(double)));
+  }
+  TRY(upload_done(ctx));
+  TRY(build_gradient_device(ctx, grid, basis_act, func, nspin, ctx->dP.as<double>(), ctx->dOut.as<double>(), nenv, basis_env,
+                            dpe.data()));
+  std::vector<double> t((size_t)b->nbf * 3);
+  CU(cudaMemcpyAsync(t.data(), ctx->dOut.p, t.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  collect_timers(ctx);
+  std::fill(grad, grad + (size_t)natoms * 3, 0.0);
+  for (int nu = 0; nu < b->nbf; ++nu)
+    for (int c = 0; c < 3; ++c) grad[atom_of_bf[nu] + (size_t)c * natoms] -= 2.0 * t[(size_t)nu * 3 + c];
+  return SXC_OK;
+}
 
 int sxc_get_stats(sxc_ctx* ctx, sxc_stats* out) {
   if (!ctx || !out) return SXC_ERR_INVALID;

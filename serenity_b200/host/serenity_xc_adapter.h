@@ -297,8 +297,22 @@ class NAddFuncPotential : public Potential<SCFMode>, public ObjectSensitive {
     if (!_potential) getMatrix();
     return _energy;
   }
-  Matrix getGeomGradients() override final {
-    throw SerenityError("NAddFuncPotential::getGeomGradients is not implemented on the B200 path yet (SURVEY.md row f-3)");
+  Matrix getGeomGradients() override final {  // NAddFuncPotential.cpp:329-493
+    auto basis = _act->getBasisController();
+    if (basis->getNAtoms() <= 0 || basis->getAtomIndicesOfBasis().size() != basis->getNBasisFunctions())
+      throw SerenityError("NAddFuncPotential: Missed gradient element in gradient evaluation.");  // :367-369
+    std::vector<int> be;
+    std::vector<const double*> pe;
+    for (auto& e : _env) {
+      be.push_back(e->getBasisController()->handle(*_dev));
+      pe.push_back(e->getDensityMatrix().data());
+    }
+    Matrix grad(basis->getNAtoms(), 3);
+    _dev->check(sxc_nadd_gradient(_dev->get(), _grid->handle(*_dev), _func, detail::nspin<SCFMode>(), basis->handle(*_dev),
+                                  _act->getDensityMatrix().data(), (int)_env.size(), be.data(), pe.data(), basis->getNAtoms(),
+                                  basis->getAtomIndicesOfBasis().data(), grad.data()));
+    _envFrozen = false;  // the gradient reuses the device buffer of the cached environment density
+    return grad;
   }
   void notify() override final { _potential = nullptr; }
   const std::vector<double>& getEnergyParts() const { return _energyParts; }

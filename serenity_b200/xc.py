@@ -152,6 +152,22 @@ class XCContext:
         self._check(self._lib.sxc_xc_gradient(self._h, grid, basis, func, nspin, _ptr(P), natoms, _ptr(amap), _ptr(grad)))
         return grad
 
+    def nadd_gradient(self, grid, func, basis_act, P_act, basis_env, P_env, atom_of_bf, natoms: int, nspin: int = 1):
+        """NAddFuncPotential::getGeomGradients: [natoms, 3] over the atoms of the active system."""
+        if nspin == 2:
+            Pa = _spin_pack(P_act)
+            mats = [_spin_pack(p) for p in P_env]
+        else:
+            Pa = np.asfortranarray(P_act, dtype=np.float64)
+            mats = [np.asfortranarray(p, dtype=np.float64) for p in P_env]
+        amap = np.ascontiguousarray(atom_of_bf, dtype=np.int32)
+        hb = np.ascontiguousarray(basis_env, dtype=np.int32)
+        ptrs = (C.c_void_p * max(len(mats), 1))(*[m.ctypes.data for m in mats])
+        grad = np.zeros((natoms, 3), order="F")
+        self._check(self._lib.sxc_nadd_gradient(self._h, grid, func, nspin, basis_act, _ptr(Pa), len(mats), _ptr(hb), ptrs,
+                                                natoms, _ptr(amap), _ptr(grad)))
+        return grad
+
     # ---- stage level
     def density_on_grid(self, grid, basis, P, npts: int, gradient: bool = True):
         P = np.asfortranarray(P, dtype=np.float64)

@@ -113,14 +113,17 @@ int main(int argc, char** argv) {
     Matrix& Vab = abPot->getMatrix();
     if (&abPot->getMatrix() != &Vab) throw SerenityError("ABFuncPotential::getMatrix() must cache");
     wr(out, Vab.data(), (int64_t)nA * nB);
-    // error convention: SerenityError, as the reference throws
+    // gradient of the non-additive XC potential over the active atoms (NAddFuncPotential.cpp:329-493)
+    Matrix gradN = naddXC->getGeomGradients();
+    wr(out, gradN.data(), (int64_t)gradN.rows() * 3);
+    // error convention: SerenityError, as the reference throws (here: a functional id the library does not implement)
     bool threw = false;
     try {
-      naddXC->getGeomGradients();
+      FuncPotential<R::RESTRICTED> bad(dev, dA, grid, Functional{{9999}, {1.0}});
     } catch (const SerenityError&) {
       threw = true;
     }
-    if (!threw) throw SerenityError("NAddFuncPotential::getGeomGradients must throw");
+    if (!threw) throw SerenityError("an unsupported functional must throw SerenityError");
   } catch (const std::exception& e) {
     std::cerr << "host_adapter_test failed: " << e.what() << "\n";
     return 1;

@@ -74,6 +74,7 @@ def test_cpp_potentials_match_oracle(tmp_path):
         got = [(_r(f, (nA, nA)), _r(f)) for _ in range(5)]
         grad = _r(f, (len(act.symbols), 3))
         Vab = _r(f, (nA, env.basis.nbf))
+        gradN = _r(f, (len(act.symbols), 3))
     og = orc.Grid(cfg.xyz, cfg.w, 128)
     bA, bE = orc.Basis(act.basis), orc.Basis(env.basis)
 
@@ -93,3 +94,6 @@ def test_cpp_potentials_match_oracle(tmp_path):
     assert np.abs(grad - grad_ref).max() <= 1e-9
     Vab_ref, _ = orc.build_ab(bA, bE, [(bA, PA2), (bE, env.P)], og, orc.Functional(*xc))
     assert np.abs(Vab - Vab_ref).max() <= 1e-8
+    gradN_ref = orc.nadd_gradient(bA, PA2, [(bE, env.P)], og, orc.Functional(*xc), atom_indices_of_basis(act.basis, act.coords),
+                                  len(act.symbols))
+    assert np.abs(gradN - gradN_ref).max() <= 1e-9

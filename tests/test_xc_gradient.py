@@ -102,3 +102,59 @@ def test_gpu_gradient_unrestricted_and_cartesian():
     gotc = ctx.xc_gradient(g, bc, f, Pc, amapc, natoms)
     assert np.abs(gotc - refc).max() < 1e-9
     ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------- NAdd gradient
+def _nadd_case():
+    from serenity_b200.inputs import make_config
+    from serenity_b200.inputs.basis import atom_indices_of_basis
+    cfg = make_config("fde_dimer", 2)
+    act, env = cfg.subsystems
+    return cfg, act, env, atom_indices_of_basis(act.basis, act.coords), len(act.symbols)
+
+
+@pytest.mark.parametrize("func", ["PBE", "PW91K"])
+def test_oracle_nadd_gradient_is_derivative_of_e_nadd(func):
+    """NAddFuncPotential::getGeomGradients (NAddFuncPotential.cpp:329-493) pinned to its definition: with all density
+    matrices and the grid fixed, g[A] = dE_nadd / d(rigid shift of the ACTIVE basis functions on atom A)."""
+    from oracle import pyoracle as orc
+    from serenity_b200.inputs.configs import FUNCTIONALS
+    cfg, act, env, amap, natoms = _nadd_case()
+    og, of = orc.Grid(cfg.xyz, cfg.w, 128), orc.Functional(*FUNCTIONALS[func])
+    bE = orc.Basis(env.basis)
+    g = orc.nadd_gradient(orc.Basis(act.basis), act.P, [(bE, env.P)], og, of, amap, natoms)
+    h = 1e-4
+    for atom, c in ((0, 2), (1, 0), (2, 1)):
+        d = np.zeros(3)
+        d[c] = h
+        ep = orc.build_nadd(orc.Basis(_shifted(act.basis, amap, atom, d)), act.P, [(bE, env.P)], og, of)[1]
+        em = orc.build_nadd(orc.Basis(_shifted(act.basis, amap, atom, -d)), act.P, [(bE, env.P)], og, of)[1]
+        fd = (ep - em) / (2 * h)
+        assert abs(fd - g[atom, c]) < 2e-7 * max(1.0, abs(fd)), (atom, c, fd, g[atom, c])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("func", ["LDA", "PBE", "PW91K"])
+def test_gpu_nadd_gradient_matches_oracle(func):
+    from oracle import pyoracle as orc
+    from serenity_b200.inputs.configs import FUNCTIONALS
+    from serenity_b200.xc import XCContext
+    cfg, act, env, amap, natoms = _nadd_case()
+    ids, mix = FUNCTIONALS[func]
+    ref = orc.nadd_gradient(orc.Basis(act.basis), act.P, [(orc.Basis(env.basis), env.P)], orc.Grid(cfg.xyz, cfg.w, 128),
+                            orc.Functional(ids, mix), amap, natoms)
+    ctx = XCContext(0)
+    g = ctx.set_grid(cfg.xyz, cfg.w, 128)
+    ba, be = ctx.add_basis(act.basis, 1e-9), ctx.add_basis(env.basis, 1e-9)
+    f = ctx.set_functional(ids, mix)
+    got = ctx.nadd_gradient(g, f, ba, act.P, [be], [env.P], amap, natoms)
+    assert np.abs(got - ref).max() <= 1e-9
+    gu = ctx.nadd_gradient(g, f, ba, (0.5 * act.P, 0.5 * act.P), [be], [(0.5 * env.P, 0.5 * env.P)], amap, natoms, nspin=2)
+    assert np.abs(gu - got).max() <= 1e-10
+    # without an environment the entry point degenerates to FuncPotential::getGeomGradients
+    assert np.abs(ctx.nadd_gradient(g, f, ba, act.P, [], [], amap, natoms) - ctx.xc_gradient(g, ba, f, act.P, amap, natoms)).max() < 1e-12
+    V1, E1 = ctx.build_nadd(g, f, ba, act.P, [be], [env.P])  # the NAdd build still works after the gradient reused its buffers
+    V_ref, E_ref, _ = orc.build_nadd(orc.Basis(act.basis), act.P, [(orc.Basis(env.basis), env.P)], orc.Grid(cfg.xyz, cfg.w, 128),
+                                     orc.Functional(ids, mix))
+    assert np.abs(V1 - V_ref).max() <= 1e-8
+    ctx.close()
