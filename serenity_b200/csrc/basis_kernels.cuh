@@ -3,8 +3,8 @@
 // Row 8a-1 of SURVEY.md: BasisFunctionOnGridController::calculateBasisFunctionData
 // (src/data/grid/BasisFunctionOnGridController.cpp:150-1105), derivative level 1.
 // B200 design: one CTA per block; one thread per grid point (x/y/z/w coalesced SoA loads), warps of a CTA
-// walk the block's significant-shell list (warp-uniform shell data -> broadcast loads, no divergence in the
-// switch over l); outputs are written function-major [comp][c][128] so every store is a 256-byte coalesced
+// walk the block's significant-shell list, whose shell data (centre, l, primitives) is staged in shared memory in
+// batches of 128 shells (warp-uniform -> broadcast reads, no divergence in the switch over l); outputs are written function-major [comp][c][128] so every store is a 256-byte coalesced
 // row segment and the tiles feed the DMMA kernels without a transpose.
 #pragma once
 
@@ -197,16 +197,35 @@ __device__ __noinline__ void store_cartesian(int l, const double* __restrict__ n
 }
 
 constexpr int BASIS_GROUPS = 4;  // 4 shell groups x 128 points = 512 threads
+constexpr int SHELL_BATCH = 128;  // significant shells staged in shared memory at a time
+constexpr int PRIM_BATCH = 1024;  // primitives (exponent, coefficient) staged with them
+
+// one significant shell of the block, staged in shared memory
+struct __align__(8) StagedShell {
+  double cx, cy, cz;
+  int c0;      // first compact function index (row of the tile)
+  int l;
+  int nf;
+  int pure;
+  int np;
+  int poff;    // offset into the staged primitives, or -(global offset) - 1 if they did not fit
+  int bf0;     // first basis function (Cartesian norm factors)
+  int pad;
+};
 
 __global__ void __launch_bounds__(BASIS_GROUPS* BP) k_basis(GridView g, ShellView b, PlanView plan, int slot0,
                                                              const int* __restrict__ order,
                                                              double* __restrict__ phi_buf) {
+  __shared__ StagedShell sh_rec[SHELL_BATCH];
+  __shared__ double sh_alpha[PRIM_BATCH], sh_coeff[PRIM_BATCH];
+  __shared__ int sh_scan[SHELL_BATCH / 32];
   const int q = order ? order[blockIdx.x] : slot0 + blockIdx.x;
   const int blk = plan.block_id[q];
   const long first = (long)blk * g.blocksize;
   const int n = (int)min((long)g.blocksize, g.npts - first);
-  const int p = threadIdx.x & (BP - 1);
-  const int grp = threadIdx.x >> 7;
+  const int tid = threadIdx.x;
+  const int p = tid & (BP - 1);
+  const int grp = tid >> 7;
   const int sp = plan.s_pad[q];
   const int s = plan.s[q];
   const size_t comp_stride = (size_t)sp * BP;
@@ -222,45 +241,94 @@ __global__ void __launch_bounds__(BASIS_GROUPS* BP) k_basis(GridView g, ShellVie
   const int* __restrict__ sig_shell = plan.sig_shell + (size_t)q * b.nshell;
   const int* __restrict__ sig_c0 = plan.sig_c0 + (size_t)q * b.nshell;
 
-  for (int k = grp; k < nsig; k += BASIS_GROUPS) {
-    const int sh = sig_shell[k];
-    const int c0 = sig_c0[k];
-    const int l = b.l[sh];
-    const int nf = b.nfunc[sh];
-    double* __restrict__ out = tile + (size_t)c0 * BP + p;
-    const double dx = px - b.centre[3 * sh], dy = py - b.centre[3 * sh + 1], dz = pz - b.centre[3 * sh + 2];
-    const double r2 = dx * dx + dy * dy + dz * dz;
-    double radial = 0.0, dradial = 0.0;
-    const int o = b.prim_off[sh];
-    const int np = b.nprim[sh];
-    for (int i = 0; i < np; ++i) {
-      const double al = b.alpha[o + i];
-      const double tmp = al * r2;
-      if (tmp < b.exp_thr) {  // :300
-        const double e = b.coeff[o + i] * exp(-tmp);
-        radial += e;
-        dradial -= 2.0 * al * e;
+  for (int base = 0; base < nsig; base += SHELL_BATCH) {
+    const int nb = min(SHELL_BATCH, nsig - base);
+    // ---- stage the shell data of this batch (centres, angular momenta, primitives) in shared memory
+    __syncthreads();  // the previous batch is no longer read
+    if (tid < SHELL_BATCH) {
+      int np = 0, sh = 0;
+      if (tid < nb) {
+        sh = sig_shell[base + tid];
+        np = b.nprim[sh];
+      }
+      int incl = np;  // inclusive prefix sum of the primitive counts over the batch
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((tid & 31) >= o) incl += v;
+      }
+      if ((tid & 31) == 31) sh_scan[tid >> 5] = incl;
+      asm volatile("bar.sync 1, %0;" ::"n"(SHELL_BATCH));  // the first four warps only
+      int off = incl - np;
+      for (int w = 0; w < (tid >> 5); ++w) off += sh_scan[w];
+      if (tid < nb) {
+        StagedShell r;
+        r.cx = b.centre[3 * sh];
+        r.cy = b.centre[3 * sh + 1];
+        r.cz = b.centre[3 * sh + 2];
+        r.c0 = sig_c0[base + tid];
+        r.l = b.l[sh];
+        r.nf = b.nfunc[sh];
+        r.pure = b.pure[sh];
+        r.np = np;
+        r.bf0 = b.first_bf[sh];
+        r.pad = 0;
+        const int o = b.prim_off[sh];
+        if (off + np <= PRIM_BATCH) {
+          r.poff = off;
+          for (int i = 0; i < np; ++i) {
+            sh_alpha[off + i] = b.alpha[o + i];
+            sh_coeff[off + i] = b.coeff[o + i];
+          }
+        } else {
+          r.poff = -o - 1;  // rare: read the primitives from global memory
+        }
+        sh_rec[tid] = r;
       }
     }
-    if (!valid || fabs(radial) < b.radial_thr) {  // :312-329 (and the padding points of a short block)
-      for (int m = 0; m < nf; ++m) {
-        out[(size_t)m * BP] = 0.0;
-        out[comp_stride + (size_t)m * BP] = 0.0;
-        out[2 * comp_stride + (size_t)m * BP] = 0.0;
-        out[3 * comp_stride + (size_t)m * BP] = 0.0;
+    __syncthreads();
+
+    for (int k = grp; k < nb; k += BASIS_GROUPS) {
+      const StagedShell& r = sh_rec[k];
+      const int l = r.l;
+      const int nf = r.nf;
+      double* __restrict__ out = tile + (size_t)r.c0 * BP + p;
+      const double dx = px - r.cx, dy = py - r.cy, dz = pz - r.cz;
+      const double r2 = dx * dx + dy * dy + dz * dz;
+      double radial = 0.0, dradial = 0.0;
+      const int np = r.np;
+      const bool staged = r.poff >= 0;
+      const double* __restrict__ al_p = staged ? sh_alpha + r.poff : b.alpha + (-r.poff - 1);
+      const double* __restrict__ co_p = staged ? sh_coeff + r.poff : b.coeff + (-r.poff - 1);
+      for (int i = 0; i < np; ++i) {
+        const double al = al_p[i];
+        const double tmp = al * r2;
+        if (tmp < b.exp_thr) {  // :300
+          const double e = co_p[i] * exp(-tmp);
+          radial += e;
+          dradial -= 2.0 * al * e;
+        }
       }
-      continue;
-    }
-    if (b.pure[sh]) {
-      switch (l) {
-        case 0: store_spherical<0>(out, comp_stride, radial, dradial, dx, dy, dz); break;
-        case 1: store_spherical<1>(out, comp_stride, radial, dradial, dx, dy, dz); break;
-        case 2: store_spherical<2>(out, comp_stride, radial, dradial, dx, dy, dz); break;
-        case 3: store_spherical<3>(out, comp_stride, radial, dradial, dx, dy, dz); break;
-        default: store_spherical_generic(l, out, comp_stride, radial, dradial, dx, dy, dz); break;
+      if (!valid || fabs(radial) < b.radial_thr) {  // :312-329 (and the padding points of a short block)
+        for (int m = 0; m < nf; ++m) {
+          out[(size_t)m * BP] = 0.0;
+          out[comp_stride + (size_t)m * BP] = 0.0;
+          out[2 * comp_stride + (size_t)m * BP] = 0.0;
+          out[3 * comp_stride + (size_t)m * BP] = 0.0;
+        }
+        continue;
       }
-    } else {
-      store_cartesian(l, b.normfac + b.first_bf[sh], out, comp_stride, radial, dradial, dx, dy, dz);
+      if (r.pure) {
+        switch (l) {
+          case 0: store_spherical<0>(out, comp_stride, radial, dradial, dx, dy, dz); break;
+          case 1: store_spherical<1>(out, comp_stride, radial, dradial, dx, dy, dz); break;
+          case 2: store_spherical<2>(out, comp_stride, radial, dradial, dx, dy, dz); break;
+          case 3: store_spherical<3>(out, comp_stride, radial, dradial, dx, dy, dz); break;
+          default: store_spherical_generic(l, out, comp_stride, radial, dradial, dx, dy, dz); break;
+        }
+      } else {
+        store_cartesian(l, b.normfac + r.bf0, out, comp_stride, radial, dradial, dx, dy, dz);
+      }
     }
   }
   // zero the padding rows c in [s, s_pad)
