@@ -6,12 +6,12 @@
 //     T = phi_s^T G;  V_s = T + T^T;  V += Proj V_s Proj^T.
 // The LDA variant (:179-223, V_s = phi_s^T diag(a) phi_s) is the same expression with b = 0.
 // B200 design: k_form_g builds G in the fifth slot of the tile (bandwidth-bound: reads 4 tile components, writes 1;
-// fused with the block-average test; phi and grad phi stay intact for the second spin of an UNRESTRICTED build).  k_vmat is a persistent kernel (8 warps, two CTAs per SM) that pulls blocks from a device
+// fused with the block-average test; phi and grad phi stay intact for the second spin of an UNRESTRICTED build).  k_vmat is a persistent kernel (8 DMMA warps + 2 producer warps, two CTAs per SM) that pulls blocks from a device
 // work queue (largest first) and computes only the upper triangle of V_s, cut into 32 x 32 warp tiles
 //          U[I,J] = [phi_I | G_I] . [G_J | phi_J]^T      (stacked K = 2 x 128 points, DMMA m8n8k4)
 // in host-scheduled "rounds" (sxc_api.cu: scatter_schedule): <= 8 warp tiles that touch <= 6 distinct 32-row groups.
-// The CTA stages phi and G rows of those groups through a 3-stage cp.async ring over 8-point K chunks (the ring runs
-// across round boundaries, so only the first round of a block pays the fill latency); every warp owns one tile
+// The producer warps stage phi and G rows of those groups through a 3-stage cp.async ring over 8-point K chunks (the
+// ring runs across round and block boundaries, so only the first round of a CTA pays the fill latency); every DMMA warp owns one tile
 // (rounds with <= 4 tiles split the two k-steps of a chunk over two warps), and the accumulators go straight into
 // the GPU-resident upper triangle with FP64 red.global (RED.E.ADD.F64).  k_mirror copies the strict upper triangle
 // down once per build.  Scheduling at warp-tile granularity keeps > 90 % of the DMMA slots busy for any s (128 x 128
@@ -98,22 +98,42 @@ static_assert(sizeof(ScatterRound) == 40, "ScatterRound layout");
 
 // ------------------------------------------------------------------------------------------------------------
 // K4: persistent scatter.  grid <= 2 x SMs; work items (blocks, or segments of a block's rounds when the shard is small)
-// are taken from `items` through the atomic `counter`.
+// are taken from `items` through the atomic `counter`.  8 DMMA warps + 2 producer warps: warps 8 and 9 alone issue the
+// cp.async copies of a stage (warp 8 the phi rows, warp 9 the G rows of the staged groups: 24 x 16 B per lane and chunk)
+// and a "full" mbarrier tracks their completion (cp.async.mbarrier.arrive.noinc); the DMMA warps wait on "full",
+// multiply and arrive on the stage's "empty" mbarrier, which the producers await before refilling.  No CTA-wide barrier
+// and no producer code in the K loop of the DMMA warps (together 23 % of the warp time of the barrier-synchronised ring
+// this replaced, profiles/r01_ncu_source_density.md: 2.93 -> 2.82 ms); warps may drift by up to a stage.  10 warps cap
+// ptxas at 96 registers, so the two products of a k-step are loaded and issued one after the other.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(scat::THREADS, 2)
+namespace scat {
+constexpr int PWARPS = 2;
+constexpr int PTHREADS = (WARPS + PWARPS) * 32;
+constexpr size_t smem_bytes_pipe() { return smem_bytes() + 2 * STAGES * sizeof(uint64_t); }
+}  // namespace scat
+
+__global__ void __launch_bounds__(scat::PTHREADS, 2)
 k_vmat(PlanView plan, int nbf, const WorkItem* __restrict__ items, int nitems, int* __restrict__ counter,
-       const int* __restrict__ skip_flag, const ScatterRound* __restrict__ tpl, const int* __restrict__ tpl_off,
-       const double* __restrict__ phi_buf, double* __restrict__ W) {
+            const int* __restrict__ skip_flag, const ScatterRound* __restrict__ tpl, const int* __restrict__ tpl_off,
+            const double* __restrict__ phi_buf, double* __restrict__ W) {
   using namespace scat;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* stage_base = reinterpret_cast<double*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(stage_base + STAGES * STAGE_ELEMS);
+  uint64_t* empty = full + STAGES;
   __shared__ int s_next;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lr = lane >> 2, lc = lane & 3;
+  if (tid < STAGES) {
+    mbar_init(full + tid, PWARPS * 32);
+    mbar_init(empty + tid, WARPS);
+  }
+  // ring position: both sides walk the stages in the same order over the whole life of the CTA
+  int stage = 0, pass = 0;  // pass = completed trips around the ring
 
   for (;;) {
-    __syncthreads();  // the ring of the previous block is no longer read
+    __syncthreads();  // (also orders the mbarrier initialisation before their first use)
     if (tid == 0) s_next = atomicAdd(counter, 1);
     __syncthreads();
     const int qi = s_next;
@@ -125,112 +145,98 @@ k_vmat(PlanView plan, int nbf, const WorkItem* __restrict__ items, int nitems, i
     const int sp = plan.s_pad[q];
     const size_t comp_stride = (size_t)sp * BP;
     const double* __restrict__ tile = phi_buf + plan.phi_off[q];
-
-    // ---- 2. rounds of warp tiles
-    const double* __restrict__ phi = tile;
-    const double* __restrict__ G = tile + 4 * comp_stride;  // G slot of the tile
-    const int* __restrict__ sig = plan.sig_bf + (size_t)q * plan.nbf_pad;
     const int n32 = sp >> 5;
     const ScatterRound* __restrict__ rounds = tpl + tpl_off[n32] + item.begin;  // this item's segment of the rounds
     const int nr = item.end - item.begin;
 
-    // Producer side of the ring: in iteration i all 256 threads copy the 64 rows x 64 B of staged group i (32 phi rows,
-    // then 32 G rows); per-thread source / destination offsets are loop invariants, the group ids of the round being
-    // issued sit packed in two registers.
-    const int rr = tid >> 2, c16 = tid & 3;
-    const double* src_base = ((rr & 32) ? G : phi) + (size_t)(rr & 31) * BP + c16 * 2;
-    const int dst_off = rr * STRIDE + c16 * 2;
-    int is_r = 0, is_kc = 0, is_stage = 0, is_ng = 0;
-    uint2 is_grp = make_uint2(0u, 0u);
-    auto load_round = [&]() {
-      if (is_r < nr) {
-        is_grp = __ldg(reinterpret_cast<const uint2*>(rounds[is_r].group));
-        is_ng = rounds[is_r].ngroups;
-      }
-    };
-    load_round();
-    auto issue = [&]() {
-      if (is_r < nr) {
-        double* st = stage_base + is_stage * STAGE_ELEMS + dst_off;
-        const double* src = src_base + is_kc * TKP;
+    if (warp >= WARPS) {
+      // ---------------- producers: warp 8 copies the 32 phi rows, warp 9 the 32 G rows of every staged group
+      const double* src_base = tile + (warp == WARPS ? 0 : 4 * comp_stride) + (size_t)(lane >> 2) * BP + (lane & 3) * 2;
+      const int dst_off = ((warp - WARPS) * 32 + (lane >> 2)) * STRIDE + (lane & 3) * 2;
+      for (int r = 0; r < nr; ++r) {
+        const uint2 grp = __ldg(reinterpret_cast<const uint2*>(rounds[r].group));
+        const int ng = rounds[r].ngroups;
+        for (int kc = 0; kc < NKC; ++kc) {
+          if (pass > 0) mbar_wait(empty + stage, (pass - 1) & 1);
+          double* st = stage_base + stage * STAGE_ELEMS + dst_off;
+          const double* src = src_base + kc * TKP;
 #pragma unroll
-        for (int i = 0; i < MAXG; ++i)
-          if (i < is_ng) {
-            const unsigned grp = ((i < 4 ? is_grp.x : is_grp.y) >> (8 * (i & 3))) & 0xffu;
-            cp_async16(st + i * GROUP_ELEMS, src + (size_t)grp * (32 * BP));
-          }
-        if (++is_kc == NKC) {
-          is_kc = 0;
-          ++is_r;
-          load_round();
-        }
-        is_stage = (is_stage + 1 == STAGES) ? 0 : is_stage + 1;
-      }
-      cp_async_commit();
-    };
-
-    double acc[4][4][2];
-    issue();
-    issue();
-    int c_stage = 0;
-    for (int r = 0; r < nr; ++r) {
-      const ScatterRound* rd = rounds + r;
-      const int slot_a = rd->ta[warp], slot_b = rd->tb[warp], kmask = rd->kmask[warp];
-      const bool active = slot_a != 0xff;
+          for (int i = 0; i < MAXG; ++i)
+            if (i < ng) {
+              const unsigned gi = ((i < 4 ? grp.x : grp.y) >> (8 * (i & 3))) & 0xffu;
+              const double* sg = src + (size_t)gi * (32 * BP);
 #pragma unroll
-      for (int m = 0; m < 4; ++m)
-#pragma unroll
-        for (int nn = 0; nn < 4; ++nn) acc[m][nn][0] = acc[m][nn][1] = 0.0;
-      for (int kc = 0; kc < NKC; ++kc) {
-        cp_async_wait<STAGES - 2>();
-        __syncthreads();
-        issue();
-        const double* st = stage_base + c_stage * STAGE_ELEMS;
-        c_stage = (c_stage + 1 == STAGES) ? 0 : c_stage + 1;
-        if (active) {
-          const double* sI = st + slot_a * GROUP_ELEMS;  // phi_I rows 0..31, G_I rows 32..63
-          const double* sJ = st + slot_b * GROUP_ELEMS;
-#pragma unroll
-          for (int ks = 0; ks < TKP / 4; ++ks) {
-            if (!((kmask >> ks) & 1)) continue;
-            double a1[4], a2[4], b1[4], b2[4];
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
-              const int o = (m * 8 + lr) * STRIDE + ks * 4 + lc;
-              a1[m] = sI[o];
-              a2[m] = sI[o + 32 * STRIDE];
-              b2[m] = sJ[o];
-              b1[m] = sJ[o + 32 * STRIDE];
+              for (int t = 0; t < 4; ++t) cp_async16(st + i * GROUP_ELEMS + t * 8 * STRIDE, sg + t * 8 * BP);
             }
+          mbar_arrive_cp_async(full + stage);
+          if (++stage == STAGES) {
+            stage = 0;
+            ++pass;
+          }
+        }
+      }
+    } else {
+      // ---------------- DMMA warps
+      const int* __restrict__ sig = plan.sig_bf + (size_t)q * plan.nbf_pad;
+      double acc[4][4][2];
+      for (int r = 0; r < nr; ++r) {
+        const ScatterRound* rd = rounds + r;
+        const int slot_a = rd->ta[warp], slot_b = rd->tb[warp], kmask = rd->kmask[warp];
+        const bool active = slot_a != 0xff;
 #pragma unroll
-            for (int m = 0; m < 4; ++m)
+        for (int m = 0; m < 4; ++m)
 #pragma unroll
-              for (int nn = 0; nn < 4; ++nn) {
-                dmma884(acc[m][nn][0], acc[m][nn][1], a1[m], b1[nn]);
-                dmma884(acc[m][nn][0], acc[m][nn][1], a2[m], b2[nn]);
+          for (int nn = 0; nn < 4; ++nn) acc[m][nn][0] = acc[m][nn][1] = 0.0;
+        for (int kc = 0; kc < NKC; ++kc) {
+          mbar_wait(full + stage, pass & 1);
+          if (active) {
+            const double* sI = stage_base + stage * STAGE_ELEMS + slot_a * GROUP_ELEMS;  // phi_I rows 0..31, G_I rows 32..63
+            const double* sJ = stage_base + stage * STAGE_ELEMS + slot_b * GROUP_ELEMS;
+#pragma unroll
+            for (int ks = 0; ks < TKP / 4; ++ks) {
+              if (!((kmask >> ks) & 1)) continue;
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {  // phi_I . G_J^T, then G_I . phi_J^T
+                double a[4], bq[4];
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                  const int o = (m * 8 + lr) * STRIDE + ks * 4 + lc;
+                  a[m] = sI[o + (half ? 32 * STRIDE : 0)];
+                  bq[m] = sJ[o + (half ? 0 : 32 * STRIDE)];
+                }
+#pragma unroll
+                for (int m = 0; m < 4; ++m)
+#pragma unroll
+                  for (int nn = 0; nn < 4; ++nn) dmma884(acc[m][nn][0], acc[m][nn][1], a[m], bq[nn]);
               }
-          }
-        }
-      }
-      if (active) {
-        // V += Proj V_s Proj^T (:301), upper triangle (compact i <= j <=> global sig[i] <= sig[j])
-        const int i0 = rd->group[slot_a] * 32, j0 = rd->group[slot_b] * 32;
-#pragma unroll
-        for (int nn = 0; nn < 4; ++nn)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int j = j0 + nn * 8 + 2 * lc + e;
-            if (j >= s) continue;
-            const size_t col = (size_t)sig[j] * nbf;
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
-              const int i = i0 + m * 8 + lr;
-              if (i <= j) atomicAdd(W + col + sig[i], acc[m][nn][e]);
             }
           }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty + stage);
+          if (++stage == STAGES) {
+            stage = 0;
+            ++pass;
+          }
+        }
+        if (active) {
+          // V += Proj V_s Proj^T (:301), upper triangle (compact i <= j <=> global sig[i] <= sig[j])
+          const int i0 = rd->group[slot_a] * 32, j0 = rd->group[slot_b] * 32;
+#pragma unroll
+          for (int nn = 0; nn < 4; ++nn)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int j = j0 + nn * 8 + 2 * lc + e;
+              if (j >= s) continue;
+              const size_t col = (size_t)sig[j] * nbf;
+#pragma unroll
+              for (int m = 0; m < 4; ++m) {
+                const int i = i0 + m * 8 + lr;
+                if (i <= j) atomicAdd(W + col + sig[i], acc[m][nn][e]);
+              }
+            }
+        }
       }
     }
-    cp_async_wait<0>();
   }
 }
 

@@ -229,7 +229,7 @@ int set_kernel_attrs(sxc_ctx* ctx) {
   if (ctx->attrs_set) return SXC_OK;
   CU(cudaFuncSetAttribute(k_density, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CU(cudaFuncSetAttribute(k_grad_contract, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  CU(cudaFuncSetAttribute(k_vmat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scat::smem_bytes()));
+  CU(cudaFuncSetAttribute(k_vmat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scat::smem_bytes_pipe()));
   CU(cudaFuncSetAttribute(k_vmat_ab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scat::smem_bytes()));
   ctx->attrs_set = true;
   return SXC_OK;
@@ -701,7 +701,7 @@ int phase_scatter(sxc_ctx* ctx, const Grid& g, const Basis& b, const Plan& p, co
   PhaseTimer t(ctx, SXC_T_SCATTER);
   if (c.nvitems == 0) return SXC_OK;
   const int grid = std::min(c.nvitems, 2 * ctx->num_sms);
-  k_vmat<<<grid, scat::THREADS, scat::smem_bytes(), ctx->stream>>>(
+  k_vmat<<<grid, scat::PTHREADS, scat::smem_bytes_pipe(), ctx->stream>>>(
       p.view(), b.nbf, p.vitems.as<WorkItem>() + c.vitem_off, c.nvitems, counter, p.skip.as<int>(), p.tpl.as<ScatterRound>(),
       p.tpl_off.as<int>(), ctx->phi.as<double>(), dW);
   LAUNCH_CHECK();
