@@ -10,7 +10,7 @@
 // work queue (largest first) and computes only the upper triangle of V_s, cut into 32 x 32 warp tiles
 //          U[I,J] = [phi_I | G_I] . [G_J | phi_J]^T      (stacked K = 2 x 128 points, DMMA m8n8k4)
 // in host-scheduled "rounds" (sxc_api.cu: scatter_schedule): <= 8 warp tiles that touch <= 6 distinct 32-row groups.
-// The producer warps stage phi and G rows of those groups through a 3-stage cp.async ring over 8-point K chunks (the
+// The producer warps stage phi and G rows of those groups through a 4-stage cp.async ring over 8-point K chunks (the
 // ring runs across round and block boundaries, so only the first round of a CTA pays the fill latency); every DMMA warp owns one tile
 // (rounds with <= 4 tiles split the two k-steps of a chunk over two warps), and the accumulators go straight into
 // the GPU-resident upper triangle with FP64 red.global (RED.E.ADD.F64).  k_mirror copies the strict upper triangle
@@ -109,7 +109,13 @@ static_assert(sizeof(ScatterRound) == 40, "ScatterRound layout");
 namespace scat {
 constexpr int PWARPS = 2;
 constexpr int PTHREADS = (WARPS + PWARPS) * 32;
-constexpr size_t smem_bytes_pipe() { return smem_bytes() + 2 * STAGES * sizeof(uint64_t); }
+// dense, XOR-swizzled staging (no padding columns): row r of a group holds its 8 points at r * 8 + (col ^ 4 * ((r >> 1) & 1)),
+// which keeps the fragment loads (8 rows x 4 columns per request) conflict free and makes room for a fourth stage
+constexpr int PSTRIDE = TKP;                        // 8 doubles
+constexpr int PGROUP_ELEMS = 64 * PSTRIDE;          // 512
+constexpr int PSTAGE_ELEMS = MAXG * PGROUP_ELEMS;   // 3072 doubles = 24 KB
+constexpr int PSTAGES = 4;
+constexpr size_t smem_bytes_pipe() { return (size_t)PSTAGES * PSTAGE_ELEMS * sizeof(double) + 2 * PSTAGES * sizeof(uint64_t); }
 }  // namespace scat
 
 __global__ void __launch_bounds__(scat::PTHREADS, 2)
@@ -119,13 +125,13 @@ k_vmat(PlanView plan, int nbf, const WorkItem* __restrict__ items, int nitems, i
   using namespace scat;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* stage_base = reinterpret_cast<double*>(smem_raw);
-  uint64_t* full = reinterpret_cast<uint64_t*>(stage_base + STAGES * STAGE_ELEMS);
-  uint64_t* empty = full + STAGES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(stage_base + PSTAGES * PSTAGE_ELEMS);
+  uint64_t* empty = full + PSTAGES;
   __shared__ int s_next;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lr = lane >> 2, lc = lane & 3;
-  if (tid < STAGES) {
+  if (tid < PSTAGES) {
     mbar_init(full + tid, PWARPS * 32);
     mbar_init(empty + tid, WARPS);
   }
@@ -152,13 +158,13 @@ k_vmat(PlanView plan, int nbf, const WorkItem* __restrict__ items, int nitems, i
     if (warp >= WARPS) {
       // ---------------- producers: warp 8 copies the 32 phi rows, warp 9 the 32 G rows of every staged group
       const double* src_base = tile + (warp == WARPS ? 0 : 4 * comp_stride) + (size_t)(lane >> 2) * BP + (lane & 3) * 2;
-      const int dst_off = ((warp - WARPS) * 32 + (lane >> 2)) * STRIDE + (lane & 3) * 2;
+      const int dst_off = ((warp - WARPS) * 32 + (lane >> 2)) * PSTRIDE + (((lane & 3) * 2) ^ (4 * ((lane >> 3) & 1)));
       for (int r = 0; r < nr; ++r) {
         const uint2 grp = __ldg(reinterpret_cast<const uint2*>(rounds[r].group));
         const int ng = rounds[r].ngroups;
         for (int kc = 0; kc < NKC; ++kc) {
           if (pass > 0) mbar_wait(empty + stage, (pass - 1) & 1);
-          double* st = stage_base + stage * STAGE_ELEMS + dst_off;
+          double* st = stage_base + stage * PSTAGE_ELEMS + dst_off;
           const double* src = src_base + kc * TKP;
 #pragma unroll
           for (int i = 0; i < MAXG; ++i)
@@ -166,10 +172,10 @@ k_vmat(PlanView plan, int nbf, const WorkItem* __restrict__ items, int nitems, i
               const unsigned gi = ((i < 4 ? grp.x : grp.y) >> (8 * (i & 3))) & 0xffu;
               const double* sg = src + (size_t)gi * (32 * BP);
 #pragma unroll
-              for (int t = 0; t < 4; ++t) cp_async16(st + i * GROUP_ELEMS + t * 8 * STRIDE, sg + t * 8 * BP);
+              for (int t = 0; t < 4; ++t) cp_async16(st + i * PGROUP_ELEMS + t * 8 * PSTRIDE, sg + t * 8 * BP);
             }
           mbar_arrive_cp_async(full + stage);
-          if (++stage == STAGES) {
+          if (++stage == PSTAGES) {
             stage = 0;
             ++pass;
           }
@@ -190,8 +196,8 @@ k_vmat(PlanView plan, int nbf, const WorkItem* __restrict__ items, int nitems, i
         for (int kc = 0; kc < NKC; ++kc) {
           mbar_wait(full + stage, pass & 1);
           if (active) {
-            const double* sI = stage_base + stage * STAGE_ELEMS + slot_a * GROUP_ELEMS;  // phi_I rows 0..31, G_I rows 32..63
-            const double* sJ = stage_base + stage * STAGE_ELEMS + slot_b * GROUP_ELEMS;
+            const double* sI = stage_base + stage * PSTAGE_ELEMS + slot_a * PGROUP_ELEMS;  // phi_I rows 0..31, G_I rows 32..63
+            const double* sJ = stage_base + stage * PSTAGE_ELEMS + slot_b * PGROUP_ELEMS;
 #pragma unroll
             for (int ks = 0; ks < TKP / 4; ++ks) {
               if (!((kmask >> ks) & 1)) continue;
@@ -200,9 +206,9 @@ k_vmat(PlanView plan, int nbf, const WorkItem* __restrict__ items, int nitems, i
                 double a[4], bq[4];
 #pragma unroll
                 for (int m = 0; m < 4; ++m) {
-                  const int o = (m * 8 + lr) * STRIDE + ks * 4 + lc;
-                  a[m] = sI[o + (half ? 32 * STRIDE : 0)];
-                  bq[m] = sJ[o + (half ? 0 : 32 * STRIDE)];
+                  const int o = (m * 8 + lr) * PSTRIDE + ((ks * 4 + lc) ^ (4 * ((lr >> 1) & 1)));
+                  a[m] = sI[o + (half ? 32 * PSTRIDE : 0)];
+                  bq[m] = sJ[o + (half ? 0 : 32 * PSTRIDE)];
                 }
 #pragma unroll
                 for (int m = 0; m < 4; ++m)
@@ -213,7 +219,7 @@ k_vmat(PlanView plan, int nbf, const WorkItem* __restrict__ items, int nitems, i
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(empty + stage);
-          if (++stage == STAGES) {
+          if (++stage == PSTAGES) {
             stage = 0;
             ++pass;
           }
