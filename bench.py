@@ -328,7 +328,7 @@ def run_b200(args):
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
                 tr = json.load(fh)
-            roof["traffic"] = tr.get(cfg.name, {}).get(top)
+            roof["traffic"] = tr.get(cfg.name, {}).get({"k_scatter": "k_vmat"}.get(top, top))  # timer slot -> kernel name
         except (OSError, ValueError):
             pass
         # whole-build view against both ceilings (all kernels of one build on rank 0)
