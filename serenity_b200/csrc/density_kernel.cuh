@@ -4,14 +4,16 @@
 // (src/data/grid/MatrixOperatorToGridTransformer.cpp:103-165):
 //     phi_s = phi Proj,  P_s = Proj^T P Proj,  B = phi_s P_s,
 //     rho_p = sum_mu B_pmu phi_pmu,   grad rho_p = 2 sum_mu B_pmu grad phi_pmu.
-// B200 design: one CTA (8 warps = 4 point groups x 2 function groups, warp tile 32 points x 32 functions; two CTAs
-// per SM) per 128-point block.  The product runs as DMMA m8n8k4 tiles (mma.sync ... f64, the only FP64 tensor path on
-// sm_100a): per j-tile of 64 functions the K loop streams 16-function chunks of the phi tile (cp.async, 16 B) and the
-// matching gathered P_s chunk (cp.async, 8 B, straight from the L2-resident nb x nb matrix through the block's
-// compact->function map) through a 3-stage shared-memory ring; B never leaves registers - the epilogue multiplies the
-// accumulator fragments with phi / grad phi read in fragment layout (full 32-byte sectors) and reduces over functions
-// with warp shuffles.  s_pad is a multiple of 32, so the last j-tile may hold a single 32-function group: its K range
-// is then split over the two function-group warps (rho is linear in B, so the halves need no extra reduction).
+// B200 design: one CTA (8 DMMA warps = 4 point groups x 2 function groups, warp tile 32 points x 32 functions, plus two
+// producer warps; two CTAs per SM) per 128-point block.  The product runs as DMMA m8n8k4 tiles (mma.sync ... f64, the only
+// FP64 tensor path on sm_100a): per j-tile of 64 functions the K loop streams 16-function chunks of the phi tile
+// (cp.async, 16 B) and the matching gathered P_s chunk (cp.async, 8 B, straight from the L2-resident nb x nb matrix
+// through the block's compact->function map) through a 4-stage shared-memory ring; B never leaves registers - the
+// epilogue multiplies the accumulator fragments with phi / grad phi rows that the producers stream through the same
+// ring and reduces over functions with warp shuffles.  s_pad is a multiple of 32, so the last j-tile may hold a single
+// 32-function group: its K range is then split over the two function-group warps (rho is linear in B, so the halves
+// need no extra reduction).  (dens::THREADS / STAGES / B_STRIDE describe the barrier-synchronised ring that
+// k_grad_contract, gradient_kernels.cuh, still uses.)
 #pragma once
 
 #include "sxc_common.cuh"
@@ -29,20 +31,43 @@ constexpr int A_ELEMS = TK * A_STRIDE;   // 2112 doubles
 constexpr int B_ELEMS = TJ * B_STRIDE;   // 1280 doubles
 constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
 constexpr int NJW = 2;
+constexpr int CWARPS = 8;                           // DMMA warps of the producer-warp pipeline
+constexpr int PTHREADS = (CWARPS + 2) * 32;         // + two producer warps
+// producer-warp kernel: the P_s chunk is stored dense and XOR-swizzled (column j holds k at j * 16 + (k ^ 4 (j & 3)): the
+// fragment loads stay conflict free without padding columns), which makes room for a fourth stage
+constexpr int PB_STRIDE = TK;
+constexpr int PB_ELEMS = TJ * PB_STRIDE;            // 1024 doubles
+constexpr int PSTAGE_ELEMS = A_ELEMS + PB_ELEMS;    // 3136 doubles = 24.5 KB
+constexpr int PSTAGES = 4;
+constexpr size_t smem_bytes_pipe(int s_pad_max) {
+  return (size_t)PSTAGES * PSTAGE_ELEMS * sizeof(double) + (size_t)NJW * BP * 4 * sizeof(double) +
+         (((size_t)(s_pad_max + TJ) * sizeof(int) + 7) & ~(size_t)7) + 2 * PSTAGES * sizeof(uint64_t);
+}
 constexpr size_t smem_bytes(int s_pad_max) {
   return (size_t)STAGES * STAGE_ELEMS * sizeof(double) + (size_t)NJW * BP * 4 * sizeof(double) +
          (size_t)(s_pad_max + TJ) * sizeof(int);
 }
 }  // namespace dens
 
-__global__ void __launch_bounds__(dens::THREADS, 2)
+// ------------------------------------------------------------------------------------------------------------
+// Warps 8 and 9 are dedicated producers (warp 8: phi rows, 32 x 16 B per lane and chunk; warp 9: the gathered P_s chunk,
+// 32 x 8 B per lane) whose copies a "full" mbarrier tracks (cp.async.mbarrier.arrive.noinc); the 8 DMMA warps wait on
+// "full", multiply and arrive on "empty" - no CTA-wide barrier and no producer code in their K loop.  The epilogue
+// operands ride the same ring: after the K chunks of a j-tile the producers stream its phi / grad phi rows (per
+// component, 16 rows x 128 points per chunk) through the A part of the stages, so the DMMA warps read them from shared
+// memory instead of keeping global loads in flight in registers.  History (profiles/r01_ncu_source_density.md): a
+// barrier-synchronised ring whose 8 warps all issued the copies and whose epilogue read its operands with 128 global
+// loads per thread took 2.78 ms (23 % of the warp time at the barrier / in producer code, 0.37 ms in register-limited
+// loads); this kernel takes 2.61 ms.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(dens::PTHREADS, 2)
 k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, const WorkItem* __restrict__ items,
           const double* __restrict__ phi_buf, double* __restrict__ rho, double* __restrict__ gx,
           double* __restrict__ gy, double* __restrict__ gz, int* __restrict__ nonneg) {
   using namespace dens;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* stage_base = reinterpret_cast<double*>(smem_raw);
-  double* red = stage_base + STAGES * STAGE_ELEMS;          // [NJW][128][4]
+  double* red = stage_base + PSTAGES * PSTAGE_ELEMS;        // [NJW][128][4]
   int* sig = reinterpret_cast<int*>(red + NJW * BP * 4);    // [s_pad + TJ]
 
   const WorkItem item = items[blockIdx.x];
@@ -65,10 +90,18 @@ k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, cons
     }
     return;
   }
+  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(sig) +
+                                               (((size_t)(sp + TJ) * sizeof(int) + 7) & ~(size_t)7));
+  uint64_t* empty = full + PSTAGES;
   const double* __restrict__ tile = phi_buf + plan.phi_off[q];
   const size_t comp_stride = (size_t)sp * BP;
   const int* __restrict__ sig_g = plan.sig_bf + (size_t)q * plan.nbf_pad;
-  for (int c = tid; c < sp + TJ; c += THREADS) sig[c] = c < sp ? sig_g[c] : 0;
+  for (int c = tid; c < sp + TJ; c += PTHREADS) sig[c] = c < sp ? sig_g[c] : 0;
+  for (int i = tid; i < NJW * BP * 4; i += PTHREADS) red[i] = 0.0;
+  if (tid < PSTAGES) {
+    mbar_init(full + tid, 64);       // the 64 producer lanes
+    mbar_init(empty + tid, CWARPS);  // one arrive per DMMA warp
+  }
   __syncthreads();
 
   const int nk = sp / TK;                 // K chunks per j-tile
@@ -76,125 +109,132 @@ k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, cons
   const int njt_all = (n32 + NJW - 1) / NJW;  // j-tiles of 64 of the block
   const int jt_begin = item.begin, njt = item.end;  // this CTA's segment of them (normally all)
   const bool partial = jt_begin != 0 || njt != njt_all;
-  const int pw = warp & 3, jw = warp >> 2;
-  const int lr = lane >> 2, lc = lane & 3;
+  const int ncomp = gx ? 4 : 1;
+  int stage = 0, pass = 0;  // ring position; every warp walks the same chunk sequence
 
-  // Producer side of the ring.  Every thread copies 4 x 16 B of the phi chunk and gathers 4 elements of the P_s chunk per
-  // stage; all per-thread address parts are loop invariants or advance by constants (no divisions in the loop).
-  const double* a_src = tile + (size_t)(tid >> 6) * BP + (tid & 63) * 2;  // + kc * TK * BP
-  const int a_dst = (tid >> 6) * A_STRIDE + (tid & 63) * 2;
-  const int bk = tid & (TK - 1), bj = tid >> 4;                           // gather: k = bk, j = bj + 16 i
-  const int b_dst = A_ELEMS + bj * B_STRIDE + bk;
-  int is_jt = jt_begin, is_kc = 0, is_stage = 0;
-  int colbase[4] = {0, 0, 0, 0};  // sig[j] * nbf of this thread's four columns of the j-tile being issued
-  auto load_colbase = [&]() {
-    if (is_jt < njt) {  // (sig holds s_pad + TJ entries: nothing to read past the last j-tile)
+  if (warp == CWARPS) {
+    // ---------------- producer A: phi rows of the K chunks, then the epilogue rows of the j-tile
+    const int a_off = lane * 2;  // 16-byte piece t * 32 + lane of a chunk: row t / 2, doubles (t & 1) * 64 + 2 lane ..
+    auto copy_rows = [&](const double* src) {  // 16 rows x 128 points -> A part of the stage
+      if (pass > 0) mbar_wait(empty + stage, (pass - 1) & 1);
+      double* st = stage_base + stage * PSTAGE_ELEMS + a_off;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) colbase[i] = sig[is_jt * TJ + bj + 16 * i] * nbf;
-    }
-  };
-  load_colbase();
-  auto issue = [&]() {
-    if (is_jt < njt) {
-      double* st = stage_base + is_stage * STAGE_ELEMS;
-      const double* src = a_src + (size_t)is_kc * (TK * BP);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) cp_async16(st + a_dst + i * 4 * A_STRIDE, src + i * 4 * BP);
-      const int ncol = sp - is_jt * TJ;  // columns of this j-tile that exist (>= 64 except for the last tile)
-      const double* prow = P + sig[is_kc * TK + bk];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (bj + 16 * i < ncol) cp_async8(st + b_dst + i * 16 * B_STRIDE, prow + colbase[i]);
-      if (++is_kc == nk) {
-        is_kc = 0;
-        ++is_jt;
-        load_colbase();
+      for (int t = 0; t < 32; ++t) cp_async16(st + (t >> 1) * A_STRIDE + (t & 1) * 64, src + a_off + (t >> 1) * BP + (t & 1) * 64);
+      mbar_arrive_cp_async(full + stage);
+      if (++stage == PSTAGES) {
+        stage = 0;
+        ++pass;
       }
-      is_stage = (is_stage + 1 == STAGES) ? 0 : is_stage + 1;
+    };
+    for (int jt = jt_begin; jt < njt; ++jt) {
+      const int nrg = min(TJ, sp - jt * TJ) / TK;
+      for (int kc = 0; kc < nk; ++kc) copy_rows(tile + (size_t)kc * (TK * BP));
+      for (int comp = 0; comp < ncomp; ++comp)
+        for (int rg = 0; rg < nrg; ++rg) copy_rows(tile + comp * comp_stride + (size_t)(jt * TJ + rg * TK) * BP);
     }
-    cp_async_commit();
-  };
-
-  double acc[4][4][2];
-  for (int i = tid; i < NJW * BP * 4; i += THREADS) red[i] = 0.0;
-
-  issue();
-  issue();
-  int c_stage = 0;
-  for (int jt = jt_begin; jt < njt; ++jt) {
-    // a last j-tile with one 32-function group: both function-group warps work on it, on alternating k-steps
-    const bool split = (n32 - jt * NJW) == 1;
-    const int cg = split ? 0 : jw;
+  } else if (warp == CWARPS + 1) {
+    // ---------------- producer B: the gathered P_s chunk ("Proj^T P Proj" without materialising it)
+    const int bk = lane & (TK - 1), bj0 = lane >> 4;  // gather element t * 32 + lane: k = bk, j = 2 t + bj0
+    for (int jt = jt_begin; jt < njt; ++jt) {
+      const int ncol = min(TJ, sp - jt * TJ);
+      int colbase[32];
 #pragma unroll
-    for (int m = 0; m < 4; ++m)
+      for (int t = 0; t < 32; ++t) colbase[t] = sig[jt * TJ + 2 * t + bj0] * nbf;
+      for (int c = 0; c < nk + ncomp * (ncol / TK); ++c) {
+        if (pass > 0) mbar_wait(empty + stage, (pass - 1) & 1);
+        if (c < nk) {
+          const double* prow = P + sig[c * TK + bk];
+          double* bdst = stage_base + stage * PSTAGE_ELEMS + A_ELEMS + bj0 * PB_STRIDE;
 #pragma unroll
-      for (int nn = 0; nn < 4; ++nn) acc[m][nn][0] = acc[m][nn][1] = 0.0;
-    for (int kc = 0; kc < nk; ++kc) {
-      cp_async_wait<STAGES - 2>();
-      __syncthreads();
-      issue();
-      const double* As = stage_base + c_stage * STAGE_ELEMS;
-      const double* Bs = As + A_ELEMS;
-      c_stage = (c_stage + 1 == STAGES) ? 0 : c_stage + 1;
-#pragma unroll
-      for (int ks = 0; ks < TK / 4; ++ks) {
-        if (split && (ks & 1) != jw) continue;
-        double a[4], bfrag[4];
-#pragma unroll
-        for (int m = 0; m < 4; ++m) a[m] = As[(ks * 4 + lc) * A_STRIDE + pw * 32 + m * 8 + lr];
-#pragma unroll
-        for (int nn = 0; nn < 4; ++nn) bfrag[nn] = Bs[(cg * 32 + nn * 8 + lr) * B_STRIDE + ks * 4 + lc];
-#pragma unroll
-        for (int m = 0; m < 4; ++m)
-#pragma unroll
-          for (int nn = 0; nn < 4; ++nn) dmma884(acc[m][nn][0], acc[m][nn][1], a[m], bfrag[nn]);
+          for (int t = 0; t < 32; ++t)  // column j = 2 t + bj0, swizzle 4 (j & 3) = 4 ((2 t & 3) + bj0)
+            if (2 * t + bj0 < ncol) cp_async8(bdst + 2 * t * PB_STRIDE + (bk ^ (4 * (((2 * t) & 3) + bj0))), prow + colbase[t]);
+        }
+        mbar_arrive_cp_async(full + stage);  // (fires at once for an epilogue chunk: nothing of this warp is in flight)
+        if (++stage == PSTAGES) {
+          stage = 0;
+          ++pass;
+        }
       }
     }
-    {
-      // epilogue: rho += B o phi, grad rho += B o grad phi   (MatrixOperatorToGridTransformer.cpp:158-163)
-      const int jbase = jt * TJ + cg * 32 + 2 * lc;
-      double r_rho[4], r_x[4], r_y[4], r_z[4];
+  } else {
+    // ---------------- DMMA warps: 4 point groups x 2 function groups
+    const int pw = warp & 3, jw = warp >> 2;
+    const int lr = lane >> 2, lc = lane & 3;
+    double acc[4][4][2];
+    for (int jt = jt_begin; jt < njt; ++jt) {
+      // a last j-tile with one 32-function group: both function-group warps work on it, on alternating k-steps
+      const bool split = (n32 - jt * NJW) == 1;
+      const int cg = split ? 0 : jw;
 #pragma unroll
-      for (int m = 0; m < 4; ++m) r_rho[m] = r_x[m] = r_y[m] = r_z[m] = 0.0;
+      for (int m = 0; m < 4; ++m)
 #pragma unroll
-      for (int nn = 0; nn < 4; ++nn) {
+        for (int nn = 0; nn < 4; ++nn) acc[m][nn][0] = acc[m][nn][1] = 0.0;
+      for (int kc = 0; kc < nk; ++kc) {
+        mbar_wait(full + stage, pass & 1);
+        const double* As = stage_base + stage * PSTAGE_ELEMS;
+        const double* Bs = As + A_ELEMS;
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const size_t row = (size_t)(jbase + nn * 8 + e) * BP;
+        for (int ks = 0; ks < TK / 4; ++ks) {
+          if (split && (ks & 1) != jw) continue;
+          double a[4], bfrag[4];
 #pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            const int p = pw * 32 + m * 8 + lr;
-            const double c = acc[m][nn][e];
-            r_rho[m] += c * tile[row + p];
-            if (gx) {
-              r_x[m] += c * tile[comp_stride + row + p];
-              r_y[m] += c * tile[2 * comp_stride + row + p];
-              r_z[m] += c * tile[3 * comp_stride + row + p];
+          for (int m = 0; m < 4; ++m) a[m] = As[(ks * 4 + lc) * A_STRIDE + pw * 32 + m * 8 + lr];
+#pragma unroll
+          for (int nn = 0; nn < 4; ++nn) bfrag[nn] = Bs[(cg * 32 + nn * 8 + lr) * PB_STRIDE + ((ks * 4 + lc) ^ (4 * (lr & 3)))];
+#pragma unroll
+          for (int m = 0; m < 4; ++m)
+#pragma unroll
+            for (int nn = 0; nn < 4; ++nn) dmma884(acc[m][nn][0], acc[m][nn][1], a[m], bfrag[nn]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + stage);
+        if (++stage == PSTAGES) {
+          stage = 0;
+          ++pass;
+        }
+      }
+      // epilogue: rho += B o phi, grad rho += B o grad phi   (MatrixOperatorToGridTransformer.cpp:158-163); chunk rg of a
+      // component holds rows rg * 16 .. + 15 of the j-tile = the fragments nn = 2 (rg & 1), + 1 of column group rg / 2
+      const int nrg = min(TJ, sp - jt * TJ) / TK;
+      for (int comp = 0; comp < ncomp; ++comp) {
+        double r[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int rg = 0; rg < nrg; ++rg) {
+          mbar_wait(full + stage, pass & 1);
+          if ((rg >> 1) == cg) {
+            const double* Es = stage_base + stage * PSTAGE_ELEMS + (2 * lc) * A_STRIDE + pw * 32 + lr;
+            if (rg & 1) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+#pragma unroll
+                  for (int m = 0; m < 4; ++m) r[m] += acc[m][2 + h][e] * Es[(h * 8 + e) * A_STRIDE + m * 8];
+            } else {
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+#pragma unroll
+                  for (int m = 0; m < 4; ++m) r[m] += acc[m][h][e] * Es[(h * 8 + e) * A_STRIDE + m * 8];
             }
           }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty + stage);
+          if (++stage == PSTAGES) {
+            stage = 0;
+            ++pass;
+          }
         }
-      }
-      // reduce over the 4 lanes of a fragment row; lane lc == 0 owns the (jw, point) slot of the CTA scratch
+        // reduce over the 4 lanes of a fragment row; lane lc == 0 owns the (jw, point) slot of the CTA scratch
 #pragma unroll
-      for (int m = 0; m < 4; ++m) {
-#pragma unroll
-        for (int o = 1; o <= 2; o <<= 1) {
-          r_rho[m] += __shfl_xor_sync(0xffffffffu, r_rho[m], o);
-          r_x[m] += __shfl_xor_sync(0xffffffffu, r_x[m], o);
-          r_y[m] += __shfl_xor_sync(0xffffffffu, r_y[m], o);
-          r_z[m] += __shfl_xor_sync(0xffffffffu, r_z[m], o);
-        }
-        if (lc == 0) {
-          double* dst = red + ((size_t)jw * BP + pw * 32 + m * 8 + lr) * 4;
-          dst[0] += r_rho[m];
-          dst[1] += r_x[m];
-          dst[2] += r_y[m];
-          dst[3] += r_z[m];
+        for (int m = 0; m < 4; ++m) {
+          r[m] += __shfl_xor_sync(0xffffffffu, r[m], 1);
+          r[m] += __shfl_xor_sync(0xffffffffu, r[m], 2);
+          if (lc == 0) red[((size_t)jw * BP + pw * 32 + m * 8 + lr) * 4 + comp] += r[m];
         }
       }
     }
   }
-  cp_async_wait<0>();
   __syncthreads();
   if (tid < n) {
     double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;

@@ -586,7 +586,7 @@ int get_plan(sxc_ctx* ctx, int gh, int bh, Plan** out, int comps = TILE_COMPS) {
     CU(cudaMemcpyAsync(p.tpl.p, tpl.data(), tpl.size() * sizeof(ScatterRound), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(p.tpl_off.p, tpl_off.data(), tpl_off.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  if (dens::smem_bytes(p.s_pad_max) > 227 * 1024 || p.s_pad_max / 32 > 255)
+  if (dens::smem_bytes_pipe(p.s_pad_max) > 227 * 1024 || p.s_pad_max / 32 > 255)
     return fail(ctx, SXC_ERR_UNSUPPORTED, "more than %d significant functions in one block", p.s_pad_max);
   *out = plan.get();
   ctx->plans[key] = std::move(plan);
@@ -645,7 +645,7 @@ int phase_density(sxc_ctx* ctx, const Grid& g, const Basis& b, const Plan& p, co
     k_zero_blocks<<<c.nslots, 128, 0, ctx->stream>>>(N, g.blocksize, with_grad ? 4 : 1, p.block_id.as<int>() + c.slot0, dens4);
     LAUNCH_CHECK();
   }
-  k_density<<<c.nditems, dens::THREADS, dens::smem_bytes(p.s_pad_max), ctx->stream>>>(
+  k_density<<<c.nditems, dens::PTHREADS, dens::smem_bytes_pipe(p.s_pad_max), ctx->stream>>>(
       g.view(), p.view(), b.nbf, dP, p.ditems.as<WorkItem>() + c.ditem_off, ctx->phi.as<double>(), dens4,
       with_grad ? dens4 + N : nullptr, with_grad ? dens4 + 2 * N : nullptr, with_grad ? dens4 + 3 * N : nullptr, nonneg);
   LAUNCH_CHECK();
