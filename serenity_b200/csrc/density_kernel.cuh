@@ -115,11 +115,17 @@ k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, cons
   if (warp == CWARPS) {
     // ---------------- producer A: phi rows of the K chunks, then the epilogue rows of the j-tile
     const int a_off = lane * 2;  // 16-byte piece t * 32 + lane of a chunk: row t / 2, doubles (t & 1) * 64 + 2 lane ..
-    auto copy_rows = [&](const double* src) {  // 16 rows x 128 points -> A part of the stage
+    // 16 rows x 128 points -> A part of the stage.  Epilogue chunks are stored with the rows of every group of 8 in the order
+    // 0 2 4 6 1 3 5 7: a DMMA lane lc owns rows 2 lc + e, and consecutive slots keep its loads bank-conflict free.
+    auto copy_rows = [&](const double* src, bool epi) {
       if (pass > 0) mbar_wait(empty + stage, (pass - 1) & 1);
       double* st = stage_base + stage * PSTAGE_ELEMS + a_off;
 #pragma unroll
-      for (int t = 0; t < 32; ++t) cp_async16(st + (t >> 1) * A_STRIDE + (t & 1) * 64, src + a_off + (t >> 1) * BP + (t & 1) * 64);
+      for (int t = 0; t < 32; ++t) {
+        const int row = t >> 1;
+        const int slot = epi ? ((row & 8) | ((row & 1) << 2) | ((row >> 1) & 3)) : row;
+        cp_async16(st + slot * A_STRIDE + (t & 1) * 64, src + a_off + row * BP + (t & 1) * 64);
+      }
       mbar_arrive_cp_async(full + stage);
       if (++stage == PSTAGES) {
         stage = 0;
@@ -128,9 +134,9 @@ k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, cons
     };
     for (int jt = jt_begin; jt < njt; ++jt) {
       const int nrg = min(TJ, sp - jt * TJ) / TK;
-      for (int kc = 0; kc < nk; ++kc) copy_rows(tile + (size_t)kc * (TK * BP));
+      for (int kc = 0; kc < nk; ++kc) copy_rows(tile + (size_t)kc * (TK * BP), false);
       for (int comp = 0; comp < ncomp; ++comp)
-        for (int rg = 0; rg < nrg; ++rg) copy_rows(tile + comp * comp_stride + (size_t)(jt * TJ + rg * TK) * BP);
+        for (int rg = 0; rg < nrg; ++rg) copy_rows(tile + comp * comp_stride + (size_t)(jt * TJ + rg * TK) * BP, true);
     }
   } else if (warp == CWARPS + 1) {
     // ---------------- producer B: the gathered P_s chunk ("Proj^T P Proj" without materialising it)
@@ -201,21 +207,21 @@ k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, cons
         for (int rg = 0; rg < nrg; ++rg) {
           mbar_wait(full + stage, pass & 1);
           if ((rg >> 1) == cg) {
-            const double* Es = stage_base + stage * PSTAGE_ELEMS + (2 * lc) * A_STRIDE + pw * 32 + lr;
+            const double* Es = stage_base + stage * PSTAGE_ELEMS + lc * A_STRIDE + pw * 32 + lr;  // row 2 lc + e + 8 h sits in slot lc + 4 e + 8 h
             if (rg & 1) {
 #pragma unroll
               for (int h = 0; h < 2; ++h)
 #pragma unroll
                 for (int e = 0; e < 2; ++e)
 #pragma unroll
-                  for (int m = 0; m < 4; ++m) r[m] += acc[m][2 + h][e] * Es[(h * 8 + e) * A_STRIDE + m * 8];
+                  for (int m = 0; m < 4; ++m) r[m] += acc[m][2 + h][e] * Es[(h * 8 + e * 4) * A_STRIDE + m * 8];
             } else {
 #pragma unroll
               for (int h = 0; h < 2; ++h)
 #pragma unroll
                 for (int e = 0; e < 2; ++e)
 #pragma unroll
-                  for (int m = 0; m < 4; ++m) r[m] += acc[m][h][e] * Es[(h * 8 + e) * A_STRIDE + m * 8];
+                  for (int m = 0; m < 4; ++m) r[m] += acc[m][h][e] * Es[(h * 8 + e * 4) * A_STRIDE + m * 8];
             }
           }
           __syncwarp();
