@@ -10,9 +10,9 @@
 // (cp.async, 16 B) and the matching gathered P_s chunk (cp.async, 8 B, straight from the L2-resident nb x nb matrix
 // through the block's compact->function map) through a 4-stage shared-memory ring; B never leaves registers - the
 // epilogue multiplies the accumulator fragments with phi / grad phi rows that the producers stream through the same
-// ring and reduces over functions with warp shuffles.  s_pad is a multiple of 32, so the last j-tile may hold a single
-// 32-function group: its K range is then split over the two function-group warps (rho is linear in B, so the halves
-// need no extra reduction).  (dens::THREADS / STAGES / B_STRIDE describe the barrier-synchronised ring that
+// ring and reduces over functions with warp shuffles.  Tiles are stored with s padded to 32, the product runs over s
+// rounded up to 8; a last j-tile with <= 4 fragments of 8 functions is K-split over the two function-group warps (rho is
+// linear in B, so the halves need no extra reduction).  (dens::THREADS / STAGES / B_STRIDE describe the barrier-synchronised ring that
 // k_grad_contract, gradient_kernels.cuh, still uses.)
 #pragma once
 
@@ -104,9 +104,11 @@ k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, cons
   }
   __syncthreads();
 
-  const int nk = sp / TK;                 // K chunks per j-tile
-  const int n32 = sp / 32;                // 32-function column groups
-  const int njt_all = (n32 + NJW - 1) / NJW;  // j-tiles of 64 of the block
+  // The tile is stored with s padded to 32 (zero rows), but the product only runs over s8 = s rounded up to 8: whole
+  // 8-function fragments and 4-function k-steps beyond it are skipped (executed / algorithmic flops 1.10 -> ~1.03).
+  const int s8 = (s + 7) & ~7;
+  const int nk = (s8 + TK - 1) / TK;          // K chunks per j-tile (the last one may hold 8 functions)
+  const int njt_all = (s8 + TJ - 1) / TJ;     // j-tiles of 64 of the block (= ceil(s_pad / 64), the host's count)
   const int jt_begin = item.begin, njt = item.end;  // this CTA's segment of them (normally all)
   const bool partial = jt_begin != 0 || njt != njt_all;
   const int ncomp = gx ? 4 : 1;
@@ -133,7 +135,7 @@ k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, cons
       }
     };
     for (int jt = jt_begin; jt < njt; ++jt) {
-      const int nrg = min(TJ, sp - jt * TJ) / TK;
+      const int nrg = (min(TJ, s8 - jt * TJ) + TK - 1) / TK;
       for (int kc = 0; kc < nk; ++kc) copy_rows(tile + (size_t)kc * (TK * BP), false);
       for (int comp = 0; comp < ncomp; ++comp)
         for (int rg = 0; rg < nrg; ++rg) copy_rows(tile + comp * comp_stride + (size_t)(jt * TJ + rg * TK) * BP, true);
@@ -142,11 +144,11 @@ k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, cons
     // ---------------- producer B: the gathered P_s chunk ("Proj^T P Proj" without materialising it)
     const int bk = lane & (TK - 1), bj0 = lane >> 4;  // gather element t * 32 + lane: k = bk, j = 2 t + bj0
     for (int jt = jt_begin; jt < njt; ++jt) {
-      const int ncol = min(TJ, sp - jt * TJ);
+      const int ncol = min(TJ, s8 - jt * TJ);
       int colbase[32];
 #pragma unroll
       for (int t = 0; t < 32; ++t) colbase[t] = sig[jt * TJ + 2 * t + bj0] * nbf;
-      for (int c = 0; c < nk + ncomp * (ncol / TK); ++c) {
+      for (int c = 0; c < nk + ncomp * ((ncol + TK - 1) / TK); ++c) {
         if (pass > 0) mbar_wait(empty + stage, (pass - 1) & 1);
         if (c < nk) {
           const double* prow = P + sig[c * TK + bk];
@@ -168,9 +170,12 @@ k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, cons
     const int lr = lane >> 2, lc = lane & 3;
     double acc[4][4][2];
     for (int jt = jt_begin; jt < njt; ++jt) {
-      // a last j-tile with one 32-function group: both function-group warps work on it, on alternating k-steps
-      const bool split = (n32 - jt * NJW) == 1;
+      // fragments (8 functions) of this j-tile; with <= 4 of them both function-group warps work on the same
+      // fragments, on alternating k-steps
+      const int nf = min(8, (s8 - jt * TJ) >> 3);
+      const bool split = nf <= 4;
       const int cg = split ? 0 : jw;
+      const int nfrag = split ? nf : min(4, nf - 4 * jw);
 #pragma unroll
       for (int m = 0; m < 4; ++m)
 #pragma unroll
@@ -180,17 +185,20 @@ k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, cons
         const double* As = stage_base + stage * PSTAGE_ELEMS;
         const double* Bs = As + A_ELEMS;
 #pragma unroll
+        const int kvalid = min(TK, s8 - kc * TK) >> 2;  // k-steps of this chunk that exist
         for (int ks = 0; ks < TK / 4; ++ks) {
-          if (split && (ks & 1) != jw) continue;
+          if (ks >= kvalid || (split && (ks & 1) != jw)) continue;
           double a[4], bfrag[4];
 #pragma unroll
           for (int m = 0; m < 4; ++m) a[m] = As[(ks * 4 + lc) * A_STRIDE + pw * 32 + m * 8 + lr];
 #pragma unroll
           for (int nn = 0; nn < 4; ++nn) bfrag[nn] = Bs[(cg * 32 + nn * 8 + lr) * PB_STRIDE + ((ks * 4 + lc) ^ (4 * (lr & 3)))];
 #pragma unroll
-          for (int m = 0; m < 4; ++m)
+          for (int nn = 0; nn < 4; ++nn)
+            if (nn < nfrag) {
 #pragma unroll
-            for (int nn = 0; nn < 4; ++nn) dmma884(acc[m][nn][0], acc[m][nn][1], a[m], bfrag[nn]);
+              for (int m = 0; m < 4; ++m) dmma884(acc[m][nn][0], acc[m][nn][1], a[m], bfrag[nn]);
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + stage);
@@ -201,7 +209,7 @@ k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, cons
       }
       // epilogue: rho += B o phi, grad rho += B o grad phi   (MatrixOperatorToGridTransformer.cpp:158-163); chunk rg of a
       // component holds rows rg * 16 .. + 15 of the j-tile = the fragments nn = 2 (rg & 1), + 1 of column group rg / 2
-      const int nrg = min(TJ, sp - jt * TJ) / TK;
+      const int nrg = (min(TJ, s8 - jt * TJ) + TK - 1) / TK;
       for (int comp = 0; comp < ncomp; ++comp) {
         double r[4] = {0.0, 0.0, 0.0, 0.0};
         for (int rg = 0; rg < nrg; ++rg) {

@@ -118,6 +118,47 @@ constexpr int PSTAGES = 4;
 constexpr size_t smem_bytes_pipe() { return (size_t)PSTAGES * PSTAGE_ELEMS * sizeof(double) + 2 * PSTAGES * sizeof(uint64_t); }
 }  // namespace scat
 
+// K loop of one round for a warp tile with MFR x NFR valid 8 x 8 fragments (4 x 4 except where the last, short row group of
+// a block is involved: rows beyond s rounded up to 8 are zero padding).  Compile-time fragment counts keep the DMMA stream
+// free of predicates (predicating the 4 x 4 loop nest cost 14 %).
+template <int MFR, int NFR>
+__device__ __forceinline__ void vmat_round(double (&acc)[4][4][2], const double* __restrict__ stage_base, uint64_t* full,
+                                           uint64_t* empty, int& stage, int& pass, int slot_a, int slot_b, int kmask,
+                                           bool active, int lane) {
+  using namespace scat;
+  const int lr = lane >> 2, lc = lane & 3;
+  for (int kc = 0; kc < NKC; ++kc) {
+    mbar_wait(full + stage, pass & 1);
+    if (active) {
+      const double* sI = stage_base + stage * PSTAGE_ELEMS + slot_a * PGROUP_ELEMS;  // phi_I rows 0..31, G_I rows 32..63
+      const double* sJ = stage_base + stage * PSTAGE_ELEMS + slot_b * PGROUP_ELEMS;
+#pragma unroll
+      for (int ks = 0; ks < TKP / 4; ++ks) {
+        if (!((kmask >> ks) & 1)) continue;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {  // phi_I . G_J^T, then G_I . phi_J^T
+          double a[MFR], bq[NFR];
+          const int o = lr * PSTRIDE + ((ks * 4 + lc) ^ (4 * ((lr >> 1) & 1)));
+#pragma unroll
+          for (int m = 0; m < MFR; ++m) a[m] = sI[o + m * 8 * PSTRIDE + (half ? 32 * PSTRIDE : 0)];
+#pragma unroll
+          for (int nn = 0; nn < NFR; ++nn) bq[nn] = sJ[o + nn * 8 * PSTRIDE + (half ? 0 : 32 * PSTRIDE)];
+#pragma unroll
+          for (int m = 0; m < MFR; ++m)
+#pragma unroll
+            for (int nn = 0; nn < NFR; ++nn) dmma884(acc[m][nn][0], acc[m][nn][1], a[m], bq[nn]);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + stage);
+    if (++stage == PSTAGES) {
+      stage = 0;
+      ++pass;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(scat::PTHREADS, 2)
 k_vmat(PlanView plan, int nbf, const WorkItem* __restrict__ items, int nitems, int* __restrict__ counter,
             const int* __restrict__ skip_flag, const ScatterRound* __restrict__ tpl, const int* __restrict__ tpl_off,
@@ -184,44 +225,31 @@ k_vmat(PlanView plan, int nbf, const WorkItem* __restrict__ items, int nitems, i
     } else {
       // ---------------- DMMA warps
       const int* __restrict__ sig = plan.sig_bf + (size_t)q * plan.nbf_pad;
+      const int s8 = (s + 7) & ~7;  // rows beyond s rounded up to 8 are zero padding: their 8 x 8 fragments are skipped
       double acc[4][4][2];
       for (int r = 0; r < nr; ++r) {
         const ScatterRound* rd = rounds + r;
         const int slot_a = rd->ta[warp], slot_b = rd->tb[warp], kmask = rd->kmask[warp];
         const bool active = slot_a != 0xff;
+        // valid 8-row fragments of the row group I and the column group J (only the last group of a block is short)
+        const int mfr = active ? min(4, (s8 - rd->group[slot_a] * 32) >> 3) : 0;
+        const int nfr = active ? min(4, (s8 - rd->group[slot_b] * 32) >> 3) : 0;
 #pragma unroll
         for (int m = 0; m < 4; ++m)
 #pragma unroll
           for (int nn = 0; nn < 4; ++nn) acc[m][nn][0] = acc[m][nn][1] = 0.0;
-        for (int kc = 0; kc < NKC; ++kc) {
-          mbar_wait(full + stage, pass & 1);
-          if (active) {
-            const double* sI = stage_base + stage * PSTAGE_ELEMS + slot_a * PGROUP_ELEMS;  // phi_I rows 0..31, G_I rows 32..63
-            const double* sJ = stage_base + stage * PSTAGE_ELEMS + slot_b * PGROUP_ELEMS;
-#pragma unroll
-            for (int ks = 0; ks < TKP / 4; ++ks) {
-              if (!((kmask >> ks) & 1)) continue;
-#pragma unroll
-              for (int half = 0; half < 2; ++half) {  // phi_I . G_J^T, then G_I . phi_J^T
-                double a[4], bq[4];
-#pragma unroll
-                for (int m = 0; m < 4; ++m) {
-                  const int o = (m * 8 + lr) * PSTRIDE + ((ks * 4 + lc) ^ (4 * ((lr >> 1) & 1)));
-                  a[m] = sI[o + (half ? 32 * PSTRIDE : 0)];
-                  bq[m] = sJ[o + (half ? 0 : 32 * PSTRIDE)];
-                }
-#pragma unroll
-                for (int m = 0; m < 4; ++m)
-#pragma unroll
-                  for (int nn = 0; nn < 4; ++nn) dmma884(acc[m][nn][0], acc[m][nn][1], a[m], bq[nn]);
-              }
-            }
+        if (mfr == 4 || !active) {
+          switch (active ? nfr : 4) {
+            case 1: vmat_round<4, 1>(acc, stage_base, full, empty, stage, pass, slot_a, slot_b, kmask, active, lane); break;
+            case 2: vmat_round<4, 2>(acc, stage_base, full, empty, stage, pass, slot_a, slot_b, kmask, active, lane); break;
+            case 3: vmat_round<4, 3>(acc, stage_base, full, empty, stage, pass, slot_a, slot_b, kmask, active, lane); break;
+            default: vmat_round<4, 4>(acc, stage_base, full, empty, stage, pass, slot_a, slot_b, kmask, active, lane); break;
           }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(empty + stage);
-          if (++stage == PSTAGES) {
-            stage = 0;
-            ++pass;
+        } else {  // a short row group is the last one, so the tile is the last diagonal tile: nfr == mfr
+          switch (mfr) {
+            case 1: vmat_round<1, 1>(acc, stage_base, full, empty, stage, pass, slot_a, slot_b, kmask, active, lane); break;
+            case 2: vmat_round<2, 2>(acc, stage_base, full, empty, stage, pass, slot_a, slot_b, kmask, active, lane); break;
+            default: vmat_round<3, 3>(acc, stage_base, full, empty, stage, pass, slot_a, slot_b, kmask, active, lane); break;
           }
         }
         if (active) {

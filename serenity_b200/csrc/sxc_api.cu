@@ -500,7 +500,7 @@ int get_plan(sxc_ctx* ctx, int gh, int bh, Plan** out, int comps = TILE_COMPS) {
     st.sum_s += s;
     st.sum_ns += n * s;
     st.sum_ns2 += n * (int64_t)s * s;
-    st.sum_ns2_padded += (int64_t)BP * sp * sp;
+    st.sum_ns2_padded += (int64_t)BP * ((s + 7) & ~7) * ((s + 7) & ~7);  // the DMMA kernels run over s rounded up to 8
     st.sum_s2 += (int64_t)s * s;
     st.s_max = std::max<int64_t>(st.s_max, s);
   }
