@@ -49,6 +49,42 @@ constexpr size_t smem_bytes(int s_pad_max) {
 }
 }  // namespace dens
 
+// K loop of one j-tile for a DMMA warp that owns NFRAG (1..4) fragments of 8 functions: compile-time fragment counts keep
+// the DMMA stream free of predicates.
+template <int NFRAG>
+__device__ __forceinline__ void dens_kloop(double (&acc)[4][4][2], const double* __restrict__ stage_base, uint64_t* full,
+                                           uint64_t* empty, int& stage, int& pass, int nk, int s8, bool split, int jw,
+                                           int cg, int pw, int lane) {
+  using namespace dens;
+  const int lr = lane >> 2, lc = lane & 3;
+  for (int kc = 0; kc < nk; ++kc) {
+    mbar_wait(full + stage, pass & 1);
+    const double* As = stage_base + stage * PSTAGE_ELEMS;
+    const double* Bs = As + A_ELEMS;
+    const int kvalid = min(TK, s8 - kc * TK) >> 2;  // k-steps of this chunk that exist
+#pragma unroll
+    for (int ks = 0; ks < TK / 4; ++ks) {
+      if (ks >= kvalid || (split && (ks & 1) != jw)) continue;
+      double a[4], bfrag[NFRAG];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) a[m] = As[(ks * 4 + lc) * A_STRIDE + pw * 32 + m * 8 + lr];
+#pragma unroll
+      for (int nn = 0; nn < NFRAG; ++nn)
+        bfrag[nn] = Bs[(cg * 32 + nn * 8 + lr) * PB_STRIDE + ((ks * 4 + lc) ^ (4 * (lr & 3)))];
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int nn = 0; nn < NFRAG; ++nn) dmma884(acc[m][nn][0], acc[m][nn][1], a[m], bfrag[nn]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + stage);
+    if (++stage == PSTAGES) {
+      stage = 0;
+      ++pass;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Warps 8 and 9 are dedicated producers (warp 8: phi rows, 32 x 16 B per lane and chunk; warp 9: the gathered P_s chunk,
 // 32 x 8 B per lane) whose copies a "full" mbarrier tracks (cp.async.mbarrier.arrive.noinc); the 8 DMMA warps wait on
@@ -180,32 +216,11 @@ k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, cons
       for (int m = 0; m < 4; ++m)
 #pragma unroll
         for (int nn = 0; nn < 4; ++nn) acc[m][nn][0] = acc[m][nn][1] = 0.0;
-      for (int kc = 0; kc < nk; ++kc) {
-        mbar_wait(full + stage, pass & 1);
-        const double* As = stage_base + stage * PSTAGE_ELEMS;
-        const double* Bs = As + A_ELEMS;
-#pragma unroll
-        const int kvalid = min(TK, s8 - kc * TK) >> 2;  // k-steps of this chunk that exist
-        for (int ks = 0; ks < TK / 4; ++ks) {
-          if (ks >= kvalid || (split && (ks & 1) != jw)) continue;
-          double a[4], bfrag[4];
-#pragma unroll
-          for (int m = 0; m < 4; ++m) a[m] = As[(ks * 4 + lc) * A_STRIDE + pw * 32 + m * 8 + lr];
-#pragma unroll
-          for (int nn = 0; nn < 4; ++nn) bfrag[nn] = Bs[(cg * 32 + nn * 8 + lr) * PB_STRIDE + ((ks * 4 + lc) ^ (4 * (lr & 3)))];
-#pragma unroll
-          for (int nn = 0; nn < 4; ++nn)
-            if (nn < nfrag) {
-#pragma unroll
-              for (int m = 0; m < 4; ++m) dmma884(acc[m][nn][0], acc[m][nn][1], a[m], bfrag[nn]);
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty + stage);
-        if (++stage == PSTAGES) {
-          stage = 0;
-          ++pass;
-        }
+      switch (nfrag) {
+        case 1: dens_kloop<1>(acc, stage_base, full, empty, stage, pass, nk, s8, split, jw, cg, pw, lane); break;
+        case 2: dens_kloop<2>(acc, stage_base, full, empty, stage, pass, nk, s8, split, jw, cg, pw, lane); break;
+        case 3: dens_kloop<3>(acc, stage_base, full, empty, stage, pass, nk, s8, split, jw, cg, pw, lane); break;
+        default: dens_kloop<4>(acc, stage_base, full, empty, stage, pass, nk, s8, split, jw, cg, pw, lane); break;
       }
       // epilogue: rho += B o phi, grad rho += B o grad phi   (MatrixOperatorToGridTransformer.cpp:158-163); chunk rg of a
       // component holds rows rg * 16 .. + 15 of the j-tile = the fragments nn = 2 (rg & 1), + 1 of column group rg / 2
