@@ -218,6 +218,44 @@ int sxc_partition_weights(sxc_ctx* ctx, int flavour, int becke_smoothing, int na
 /* device time (ms, CUDA events) of the kernel inside the last sxc_partition_weights call */
 double sxc_last_partition_ms(sxc_ctx* ctx);
 
+/* ---- LR-TDDFT / subsystem-TDDFT kernel -------------------------------------------------------- */
+/* A kernel store is one set of second functional derivatives on a grid, i.e. one of the _pp/_pg/_gg members of
+ * Kernel<SCFMode> (src/postHF/LRSCF/Kernel/Kernel.h:150-200): nspin = 1: [10][N] = d2F/drho2, d2F/drho d(grad rho) x y z,
+ * d2F/d(grad rho)2 xx xy xz yy yz zz ([1][N] if gga = 0); nspin = 2: [33][N] = pp aa ab bb | pg {x,y,z} x {aa,ab,ba,bb} |
+ * gg {xx,xy,xz,yy,yz,zz} x {aa,ab,bb} ([3][N] if gga = 0; the reference sets gg.ba := gg.ab, Kernel.cpp:580-600).
+ * Created zeroed (Kernel.cpp:58-115). */
+int sxc_kernel_create(sxc_ctx* ctx, int grid, int nspin, int gga, int* kernel);
+int sxc_kernel_destroy(sxc_ctx* ctx, int kernel);
+/* One storeDerivatives call of Kernel<SCFMode>::calculateDerivatives (Kernel.cpp:476-683, :686-747): the densities of the
+ * ndens (basis_c[i], P_c[i]) pairs are summed on the grid (a subsystem: ndens = 1; the total density of :693-712: all of
+ * them), FunctionalLibrary::calcData(GRADIENTS, func, order 2) is evaluated on it (XCFun.cpp:39-159, rows :288-298 /
+ * :486-528), added to the store with factor `sign` (pm) and the store is zeroed where that density is below the
+ * reference's hard-coded 1e-8.  nspin = 2: every P_c[i] is an {alpha, beta} pair stored back to back. */
+int sxc_kernel_add(sxc_ctx* ctx, int kernel, int func, double sign, int ndens, const int* basis_c, const double* const* P_c);
+/* copies the store to the host: [sxc_kernel_num_arrays][N] (Kernel::getPP / getPG / getGG without the block cut) */
+int sxc_kernel_get(sxc_ctx* ctx, int kernel, double* out);
+int sxc_kernel_num_arrays(sxc_ctx* ctx, int kernel);
+/* KernelSigmavector<SCFMode>::contractKernel + contractBlock (src/postHF/LRSCF/Sigmavectors/KernelSigmavector.cpp:254-311,
+ * :360-497) for nvec trial vectors: D = nvec x nspin matrices nbf_J x nbf_J (column-major, back to back; symmetrised here
+ * as calcF does, :201-208), contracted to rho~ / grad rho~ on the grid and multiplied with the sum of the nkern (1 or 2)
+ * kernel stores = Kernel::getPP/PG/GG(I, J) (total-density store + subsystem store for I == J, Kernel.cpp:170-230).
+ * mode 0: RESTRICTED singlet; 1: RESTRICTED triplet, stores are UNRESTRICTED ones (aa - ab, :381-404); 2: UNRESTRICTED.
+ * The result stays on the device (per grid); accumulate != 0 adds to the previous one (the supersystem contraction over
+ * all subsystems J, :96-117 and :214-226). */
+int sxc_kernel_contract(sxc_ctx* ctx, int grid, int basis_j, int nkern, const int* kernels, int mode, int nvec,
+                        const double* D, int accumulate);
+/* save != 0: keep a copy of the grid's contracted response (KernelSigmavector::_supersystem_scalar / _supersystem_gradient,
+ * KernelSigmavector.h:105-110); save == 0: make that copy the current response again, so that calcF(I, I) of every
+ * subsystem I starts from the same supersystem contraction (:214-226). */
+int sxc_kernel_response_copy(sxc_ctx* ctx, int grid, int save);
+/* KernelSigmavector<SCFMode>::numericalIntegration (:313-358) + the F += F^T of calcF (:236-249): the contracted response of
+ * the grid integrated with the basis functions of system I.  F = nvec x nspin matrices nbf_I x nbf_I, overwritten.  With a
+ * shard set F is this rank's partial sum. */
+int sxc_kernel_integrate(sxc_ctx* ctx, int grid, int basis_i, double* F);
+/* calcF(I, I) for an isolated system: contract + integrate */
+int sxc_kernel_sigma(sxc_ctx* ctx, int grid, int basis, int nkern, const int* kernels, int mode, int nvec, const double* D,
+                     double* F);
+
 int sxc_get_stats(sxc_ctx* ctx, sxc_stats* out);
 /* host-only helper behind sxc_set_grid_shard: splits n blocks into `world` contiguous ranges of nearly equal summed
  * cost; bounds[world + 1] receives the range starts (bounds[0] = 0, bounds[world] = n). */

@@ -155,6 +155,28 @@ int orc_build_nadd_u(const orc_basis* bA, const double* PAa, const double* PAb, 
                      const double* const* PEa, const double* const* PEb, const orc_grid* g, const orc_functional* f,
                      double radial_thr, double block_ave_thr, double* VAa, double* VAb, double* E_nadd, double* E_parts);
 
+/* ---- row f-4: second functional derivatives and the LR-TDDFT kernel contraction (oracle_kernel2.cpp) ------------- */
+/* F, d5 and the 5 x 5 Hessian (row-major) of one basic functional w.r.t. (rho_a, rho_b, s_aa, s_ab, s_bb) */
+int orc_basic_functional_d2(int id, double ra, double rb, double gaa, double gab, double gbb, double* F, double* d5,
+                            double* h25);
+/* test hook: density screen of storeDerivatives (the reference hard-codes 1e-8, Kernel.cpp:496, :606) */
+void orc_kernel_set_screen(double thr);
+/* Kernel<RESTRICTED>::storeDerivatives (postHF/LRSCF/Kernel/Kernel.cpp:476-520): store [10][npts] (pp, pg x y z,
+ * gg xx xy xz yy yz zz; [1][npts] if !store_gga) += sign * d2F, then zeroed where rho < 1e-8 */
+void orc_kernel_store_r(const orc_functional* f, long npts, const double* rho, const double* gx, const double* gy,
+                        const double* gz, double sign, int store_gga, double* store);
+/* Kernel<UNRESTRICTED>::storeDerivatives (:523-683): rho [2][npts], grad [2][3][npts] (NULL for LDA), store [33][npts] =
+ * pp aa ab bb | pg {x,y,z} x {aa,ab,ba,bb} | gg {xx,xy,xz,yy,yz,zz} x {aa,ab,bb} ([3][npts] if !store_gga) */
+void orc_kernel_store_u(const orc_functional* f, long npts, const double* rho, const double* grad, double sign,
+                        int store_gga, double* store);
+/* KernelSigmavector::contractKernel + contractBlock (postHF/LRSCF/Sigmavectors/KernelSigmavector.cpp:254-311, :360-497) for
+ * one trial vector; mode 0 singlet / 1 triplet (UNRESTRICTED store) / 2 UNRESTRICTED; resp [4 * nspin][N] is added to */
+void orc_kernel_contract(const orc_basis* b, const orc_grid* g, double radial_thr, double block_ave_thr, int mode, int gga,
+                         const double* store, const double* D, double* resp);
+/* KernelSigmavector::numericalIntegration (:313-358) + thread sum and F += F^T (:236-249) for one trial vector */
+void orc_kernel_integrate(const orc_basis* b, const orc_grid* g, double radial_thr, double block_ave_thr, int gga, int nspin,
+                          const double* resp, double* F);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,7 +17,8 @@ _LIB = None
 
 def build(force: bool = False) -> str:
     path = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle_functionals.c", "oracle_functionals_u.cpp", "oracle.h", "harmonics_table.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle_functionals.c", "oracle_functionals_u.cpp", "oracle_kernel2.cpp",
+                                           "functionals_jet.inc", "oracle.h", "harmonics_table.h")]
     if force or not os.path.exists(path) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
     return path
@@ -293,3 +294,68 @@ def nadd_gradient(basis_a: Basis, P_a, env, grid: Grid, func: Functional, atom_o
     if rc != 0:
         raise MemoryError("orc_nadd_gradient failed")
     return grad
+
+
+# ---------------------------------------------------------------------------------------------- row f-4: kernel
+def basic_functional_d2(fid: int, ra: float, rb: float, gaa: float, gab: float, gbb: float):
+    """F, d5, H[5, 5] w.r.t. (rho_a, rho_b, s_aa, s_ab, s_bb)."""
+    F = C.c_double()
+    d, h = np.zeros(5), np.zeros((5, 5))
+    rc = lib().orc_basic_functional_d2(int(fid), C.c_double(ra), C.c_double(rb), C.c_double(gaa), C.c_double(gab),
+                                       C.c_double(gbb), C.byref(F), _p(d), _p(h))
+    if rc != 0:
+        raise ValueError("unsupported functional id %d" % fid)
+    return F.value, d, h
+
+
+def kernel_set_screen(thr: float = 1e-8):
+    """test hook: density screen of storeDerivatives (reference: hard-coded 1e-8)"""
+    lib().orc_kernel_set_screen(C.c_double(thr))
+
+
+def kernel_store_r(func: Functional, rho, grad3=None, sign=1.0, store_gga=True, store=None):
+    """Kernel<RESTRICTED>::storeDerivatives: store [10, N] (or [1, N]) += sign * d2F, screened at rho < 1e-8."""
+    rho = np.ascontiguousarray(rho, dtype=np.float64)
+    N = rho.shape[0]
+    if store is None:
+        store = np.zeros((10 if store_gga else 1, N))
+    g = [None] * 3 if grad3 is None else [np.ascontiguousarray(x, dtype=np.float64) for x in grad3]
+    lib().orc_kernel_store_r(C.byref(func.c), C.c_long(N), _p(rho), _p(g[0]), _p(g[1]), _p(g[2]), C.c_double(sign),
+                             int(store_gga), _p(store))
+    return store
+
+
+def kernel_store_u(func: Functional, rho2, grad23=None, sign=1.0, store_gga=True, store=None):
+    """Kernel<UNRESTRICTED>::storeDerivatives: rho2 [2, N], grad23 [2, 3, N] -> store [33, N] (or [3, N])."""
+    rho2 = np.ascontiguousarray(rho2, dtype=np.float64)
+    N = rho2.shape[1]
+    if store is None:
+        store = np.zeros((33 if store_gga else 3, N))
+    g = None if grad23 is None else np.ascontiguousarray(grad23, dtype=np.float64)
+    lib().orc_kernel_store_u(C.byref(func.c), C.c_long(N), _p(rho2), _p(g), C.c_double(sign), int(store_gga), _p(store))
+    return store
+
+
+def kernel_contract(basis: Basis, grid: Grid, store, D, mode: int, gga: bool, resp=None, radial_thr=1e-9,
+                    block_ave_thr=1e-11):
+    """contractKernel + contractBlock for one trial vector: D [nb, nb] (modes 0, 1) or [2, nb, nb] (mode 2), each
+    column-major; resp [4 * nspin, N] is added to (created if None)."""
+    nspin = 2 if mode == 2 else 1
+    Dm = np.stack([np.asfortranarray(d, dtype=np.float64).ravel(order="F") for d in (D if mode == 2 else [D])])
+    if resp is None:
+        resp = np.zeros((4 * nspin, grid.npts))
+    store = np.ascontiguousarray(store, dtype=np.float64)
+    lib().orc_kernel_contract(C.byref(basis.c), C.byref(grid.c), C.c_double(radial_thr), C.c_double(block_ave_thr),
+                              int(mode), int(gga), _p(store), _p(Dm), _p(resp))
+    return resp
+
+
+def kernel_integrate(basis: Basis, grid: Grid, resp, gga: bool, nspin: int = 1, radial_thr=1e-9, block_ave_thr=1e-11):
+    """numericalIntegration + F += F^T for one trial vector -> [nspin] matrices (a single one for nspin = 1)."""
+    nb = basis.nbf
+    F = np.zeros((nspin, nb * nb))
+    resp = np.ascontiguousarray(resp, dtype=np.float64)
+    lib().orc_kernel_integrate(C.byref(basis.c), C.byref(grid.c), C.c_double(radial_thr), C.c_double(block_ave_thr),
+                               int(gga), int(nspin), _p(resp), _p(F))
+    mats = [F[s].reshape(nb, nb, order="F") for s in range(nspin)]
+    return mats[0] if nspin == 1 else mats

@@ -17,6 +17,8 @@ SYMBOLS = [
     "sxc_build_nadd", "sxc_build_nadd_device", "sxc_xc_gradient", "sxc_density_on_grid", "sxc_basis_on_grid",
     "sxc_functional_on_grid", "sxc_functional_on_grid_u", "sxc_scalar_to_matrix", "sxc_get_stats", "sxc_balance_ranges", "sxc_abi_version",
     "sxc_partition_weights", "sxc_last_partition_ms", "sxc_scalar_to_matrix_ab", "sxc_build_ab", "sxc_nadd_gradient",
+    "sxc_kernel_create", "sxc_kernel_destroy", "sxc_kernel_add", "sxc_kernel_get", "sxc_kernel_num_arrays", "sxc_kernel_contract",
+    "sxc_kernel_integrate", "sxc_kernel_sigma", "sxc_kernel_response_copy",
 ]
 
 
@@ -85,5 +87,14 @@ def load():
     lib.sxc_scalar_to_matrix_ab.argtypes = [vp, i, i, i, d, vp, vp, vp, vp, vp]
     lib.sxc_build_ab.argtypes = [vp, i, i, i, i, i, i, vp, vp, d, vp, vp]
     lib.sxc_last_partition_ms.restype = d
+    lib.sxc_kernel_create.argtypes = [vp, i, i, i, ip]
+    lib.sxc_kernel_destroy.argtypes = [vp, i]
+    lib.sxc_kernel_add.argtypes = [vp, i, i, d, i, vp, vp]
+    lib.sxc_kernel_get.argtypes = [vp, i, vp]
+    lib.sxc_kernel_num_arrays.argtypes = [vp, i]
+    lib.sxc_kernel_contract.argtypes = [vp, i, i, i, vp, i, i, vp, i]
+    lib.sxc_kernel_integrate.argtypes = [vp, i, i, vp]
+    lib.sxc_kernel_response_copy.argtypes = [vp, i, i]
+    lib.sxc_kernel_sigma.argtypes = [vp, i, i, i, vp, i, i, vp, vp]
     _LIB = lib
     return lib

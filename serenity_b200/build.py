@@ -56,8 +56,22 @@ def build_host_test(force=False):
     return out
 
 
+def build_jet_probe(force=False):
+    """Host-compiled probe of the device functional source (functionals.cuh, kernel2.cuh) for the CPU test suite; the
+    arithmetic is __host__ __device__, the probe never touches a GPU and is not part of the product library."""
+    src = os.path.join(ROOT, "tests", "cpp", "jet_host_probe.cu")
+    csrc = os.path.join(HERE, "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in ("functionals.cuh", "kernel2.cuh", "sxc_common.cuh")]
+    out = os.path.join(ROOT, "tests", "cpp", "libjet_host_probe.so")
+    if force or _newer(out, deps):
+        nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+        subprocess.check_call([nvcc, "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
+                               "-shared", "-ccbin", "/usr/bin/g++", "-o", out, src])
+    return out
+
+
 def build_all(force=False, verbose=False):
-    return [build_cuda(force, verbose), build_inputs_helper(force), build_host_test(force)]
+    return [build_cuda(force, verbose), build_inputs_helper(force), build_host_test(force), build_jet_probe(force)]
 
 
 if __name__ == "__main__":

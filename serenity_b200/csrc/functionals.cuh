@@ -21,7 +21,7 @@ struct Dual {
   double d[N];
 };
 
-#define SXC_HD __device__ __forceinline__
+#define SXC_HD __host__ __device__ __forceinline__
 
 template <int N> SXC_HD Dual<N> mk(double v) {
   Dual<N> r;
@@ -276,7 +276,7 @@ template <class T> SXC_HD T llp_spin(const T& r, const T& g) {
 
 // one basic functional by BASIC_FUNCTIONALS id (src/dft/functionals/BasicFunctionals.h:39-...)
 template <class T>
-__device__ T basic_functional(int id, const T& a, const T& b, const T& gaa, const T& gab, const T& gbb) {
+__host__ __device__ T basic_functional(int id, const T& a, const T& b, const T& gaa, const T& gab, const T& gbb) {
   switch (id) {
     case 2: return e_slaterx(a, b);
     case 45: return e_vwn5c(a, b);

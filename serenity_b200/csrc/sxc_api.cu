@@ -26,6 +26,7 @@
 #include "scatter_kernel.cuh"
 #include "gradient_kernels.cuh"
 #include "grid_kernels.cuh"
+#include "kernel2.cuh"
 #include "sxc_common.cuh"
 
 using namespace sxc;
@@ -72,6 +73,10 @@ struct Grid {
   std::vector<int> env_key;       // basis handles the cached envsum belongs to
   std::vector<double> env_energy; // cached E[rho_env_i] (this rank's partial sums)
   bool env_valid = false;
+  DevMem resp;     // row f-4: contracted kernel x response density, [nvec][4 * nspin][N]
+  DevMem resp_saved;  // copy kept by sxc_kernel_response_copy (the supersystem contraction, reused for every subsystem I)
+  int saved_nvec = 0, saved_nspin = 0, saved_gga = 0;
+  int resp_nvec = 0, resp_nspin = 0, resp_gga = 0;
   GridView view() const {
     GridView v;
     v.npts = npts;
@@ -148,6 +153,15 @@ struct Plan {
   }
 };
 
+// row f-4: second functional derivatives on a grid (one Kernel::_pp/_pg/_gg set, Kernel.h:150-200)
+struct KernelStore {
+  int grid = -1;
+  int nspin = 1;
+  int gga = 1;
+  int narr = 0;
+  DevMem data;  // [narr][N]
+};
+
 }  // namespace
 
 struct sxc_ctx {
@@ -159,6 +173,7 @@ struct sxc_ctx {
   std::vector<std::unique_ptr<Basis>> bases;
   std::vector<FuncView> funcs;
   std::map<std::pair<int, int>, std::unique_ptr<Plan>> plans;
+  std::vector<std::unique_ptr<KernelStore>> kstores;
   std::map<int, std::vector<ScatterRound>> scatter_tpl;  // round templates per s_pad / 32
   DevMem phi;     // tile workspace (one chunk)
   DevMem phi2;    // second tile workspace: basis B of the two-basis scatter (row f-4)
@@ -1108,7 +1123,7 @@ int build_ab_device(sxc_ctx* ctx, int gh, int fh, int nspin, int bA, int bB, int
 
 extern "C" {
 
-int sxc_abi_version(void) { return 4; }
+int sxc_abi_version(void) { return 5; }
 
 // host-only: contiguous ranges [bounds[r], bounds[r+1]) of nearly equal summed cost
 int sxc_balance_ranges(int n, const double* cost, int world, int* bounds) {
@@ -1770,6 +1785,307 @@ int sxc_nadd_gradient(sxc_ctx* ctx, int grid, int func, int nspin, int basis_act
   for (int nu = 0; nu < b->nbf; ++nu)
     for (int c = 0; c < 3; ++c) grad[atom_of_bf[nu] + (size_t)c * natoms] -= 2.0 * t[(size_t)nu * 3 + c];
   return SXC_OK;
+}
+
+// ---- row f-4: LR-TDDFT / subsystem-TDDFT kernel ------------------------------------------------------------------
+int sxc_kernel_create(sxc_ctx* ctx, int grid, int nspin, int gga, int* kernel) {
+  if (!ctx || !kernel) return fail(ctx, SXC_ERR_INVALID, "sxc_kernel_create: bad arguments");
+  if (nspin != 1 && nspin != 2) return fail(ctx, SXC_ERR_INVALID, "nspin must be 1 or 2");
+  Grid* g = get_grid(ctx, grid);
+  if (!g) return fail(ctx, SXC_ERR_INVALID, "invalid grid handle %d", grid);
+  CU(cudaSetDevice(ctx->device));
+  auto ks = std::make_unique<KernelStore>();
+  ks->grid = grid;
+  ks->nspin = nspin;
+  ks->gga = gga != 0;
+  ks->narr = nspin == 1 ? (ks->gga ? KR_ARRAYS : 1) : (ks->gga ? KU_ARRAYS : 3);
+  const size_t bytes = (size_t)ks->narr * std::max<long>(g->npts, 1) * sizeof(double);
+  CU(ks->data.ensure(bytes));
+  CU(cudaMemsetAsync(ks->data.p, 0, bytes, ctx->stream));
+  // reuse a released slot
+  for (size_t i = 0; i < ctx->kstores.size(); ++i)
+    if (!ctx->kstores[i]) {
+      ctx->kstores[i] = std::move(ks);
+      *kernel = (int)i;
+      return SXC_OK;
+    }
+  ctx->kstores.push_back(std::move(ks));
+  *kernel = (int)ctx->kstores.size() - 1;
+  return SXC_OK;
+}
+
+int sxc_kernel_destroy(sxc_ctx* ctx, int kernel) {
+  if (!ctx || kernel < 0 || kernel >= (int)ctx->kstores.size() || !ctx->kstores[kernel])
+    return fail(ctx, SXC_ERR_INVALID, "invalid kernel handle %d", kernel);
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->kstores[kernel].reset();
+  return SXC_OK;
+}
+
+int sxc_kernel_add(sxc_ctx* ctx, int kernel, int func, double sign, int ndens, const int* basis_c, const double* const* P_c) {
+  if (!ctx || ndens <= 0 || !basis_c || !P_c) return fail(ctx, SXC_ERR_INVALID, "sxc_kernel_add: bad arguments");
+  if (kernel < 0 || kernel >= (int)ctx->kstores.size() || !ctx->kstores[kernel])
+    return fail(ctx, SXC_ERR_INVALID, "invalid kernel handle %d", kernel);
+  if (func < 0 || func >= (int)ctx->funcs.size()) return fail(ctx, SXC_ERR_INVALID, "invalid functional handle %d", func);
+  CU(cudaSetDevice(ctx->device));
+  KernelStore& ks = *ctx->kstores[kernel];
+  const int gh = ks.grid, nspin = ks.nspin;
+  Grid& g = *get_grid(ctx, gh);
+  const FuncView f = ctx->funcs[func];
+  if (f.ncomp == 0) return SXC_OK;  // CompositeFunctionals::CLASSES::NONE adds nothing (Kernel.cpp:716, :722)
+  if (f.gga && !ks.gga) return fail(ctx, SXC_ERR_INVALID, "a GGA functional needs a kernel store created with gga = 1");
+  size_t total = 0;
+  std::vector<size_t> offs(ndens);
+  for (int i = 0; i < ndens; ++i) {
+    Basis* bc = get_basis(ctx, basis_c[i]);
+    if (!bc || !P_c[i]) return fail(ctx, SXC_ERR_INVALID, "invalid density basis handle %d", basis_c[i]);
+    Plan* pc = nullptr;
+    TRY(get_plan(ctx, gh, basis_c[i], &pc));
+    offs[i] = total;
+    total += (size_t)nspin * bc->nbf * bc->nbf;
+  }
+  CU(ctx->dP.ensure(total * sizeof(double)));
+  for (int i = 0; i < ndens; ++i) {
+    Basis* bc = get_basis(ctx, basis_c[i]);
+    TRY(upload_async(ctx, ctx->dP.as<double>() + offs[i], P_c[i], (size_t)nspin * bc->nbf * bc->nbf * sizeof(double)));
+  }
+  TRY(upload_done(ctx));
+  TRY(ensure_point_arrays(ctx, g, true, nspin));
+  const long N = g.npts;
+  const int ncomp = 4 * nspin;
+  double* dens = g.dens.as<double>();
+  double* tot = g.tot.as<double>();
+  begin_timing(ctx, true);
+  const int launches0 = ctx->launches;
+  Plan* p0 = nullptr;
+  TRY(get_plan(ctx, gh, basis_c[0], &p0));
+  ctx->stats = p0->stats;
+  {
+    PhaseTimer t_all(ctx, T_TOTAL);
+    CU(cudaMemsetAsync(tot, 0, (size_t)ncomp * N * sizeof(double), ctx->stream));
+    TRY(wait_p_ready(ctx));
+    for (int i = 0; i < ndens; ++i) {  // total density of the listed systems (Kernel.cpp:693-712)
+      Basis& bc = *get_basis(ctx, basis_c[i]);
+      const size_t nc2 = (size_t)bc.nbf * bc.nbf;
+      Plan* pc = nullptr;
+      TRY(get_plan(ctx, gh, basis_c[i], &pc));
+      TRY(run_screen(ctx, g, bc, *pc));
+      for (const Chunk& c : pc->chunks) {
+        TRY(phase_basis(ctx, g, bc, *pc, c));
+        for (int sp = 0; sp < nspin; ++sp)
+          TRY(phase_density(ctx, g, bc, *pc, c, ctx->dP.as<double>() + offs[i] + sp * nc2, dens + (size_t)4 * sp * N, true,
+                            nullptr));
+        if (pc->nown) {
+          PhaseTimer t(ctx, SXC_T_DENSITY);
+          k_add4<<<c.nslots, 128, 0, ctx->stream>>>(N, g.blocksize, ncomp, pc->block_id.as<int>() + c.slot0, tot, dens, tot);
+          LAUNCH_CHECK();
+        }
+      }
+    }
+    // storeDerivatives on the literal blocks this context owns
+    const bool lit_is_block = g.blocksize == FUNC_BLOCK;
+    for (const Chunk& c : p0->chunks) {
+      const int nb = lit_is_block ? c.nslots : g.nlit;
+      if (nb == 0) continue;
+      const int* list = lit_is_block ? p0->block_id.as<int>() + c.slot0 : nullptr;
+      PhaseTimer t(ctx, SXC_T_FUNCTIONAL);
+      if (nspin == 2)
+        k_kernel2_u<<<nb, FUNC_BLOCK, 0, ctx->stream>>>(f, N, list, tot, sign, ks.gga, ks.data.as<double>());
+      else
+        k_kernel2_r<<<nb, FUNC_BLOCK, 0, ctx->stream>>>(f, N, list, tot, sign, ks.gga, ks.data.as<double>());
+      LAUNCH_CHECK();
+      if (!lit_is_block) break;
+    }
+  }
+  ctx->timing = false;
+  ctx->stats.kernel_launches = ctx->launches - launches0;
+  CU(cudaStreamSynchronize(ctx->stream));
+  collect_timers(ctx);
+  return SXC_OK;
+}
+
+int sxc_kernel_get(sxc_ctx* ctx, int kernel, double* out) {
+  if (!ctx || !out || kernel < 0 || kernel >= (int)ctx->kstores.size() || !ctx->kstores[kernel])
+    return fail(ctx, SXC_ERR_INVALID, "invalid kernel handle %d", kernel);
+  CU(cudaSetDevice(ctx->device));
+  KernelStore& ks = *ctx->kstores[kernel];
+  Grid& g = *get_grid(ctx, ks.grid);
+  CU(cudaMemcpyAsync(out, ks.data.p, (size_t)ks.narr * g.npts * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SXC_OK;
+}
+
+int sxc_kernel_num_arrays(sxc_ctx* ctx, int kernel) {
+  if (!ctx || kernel < 0 || kernel >= (int)ctx->kstores.size() || !ctx->kstores[kernel])
+    return fail(ctx, SXC_ERR_INVALID, "invalid kernel handle %d", kernel);
+  return ctx->kstores[kernel]->narr;
+}
+
+namespace {
+__global__ void k_symmetrise(int n, double* __restrict__ D) {  // D += D^T (KernelSigmavector.cpp:201-208)
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i < n && j <= i) {
+    const double s = D[i + (size_t)j * n] + D[j + (size_t)i * n];
+    D[i + (size_t)j * n] = s;
+    D[j + (size_t)i * n] = s;
+  }
+}
+}  // namespace
+
+int sxc_kernel_contract(sxc_ctx* ctx, int grid, int basis_j, int nkern, const int* kernels, int mode, int nvec, const double* D,
+                        int accumulate) {
+  if (!ctx || !kernels || !D || nvec <= 0 || nkern < 1 || nkern > 2)
+    return fail(ctx, SXC_ERR_INVALID, "sxc_kernel_contract: bad arguments (1 or 2 kernel stores, nvec > 0)");
+  if (mode < 0 || mode > 2) return fail(ctx, SXC_ERR_INVALID, "mode must be 0 (singlet), 1 (triplet) or 2 (UNRESTRICTED)");
+  Grid* gp = get_grid(ctx, grid);
+  Basis* bp = get_basis(ctx, basis_j);
+  if (!gp || !bp) return fail(ctx, SXC_ERR_INVALID, "invalid grid (%d) or basis (%d) handle", grid, basis_j);
+  const int store_nspin = mode == 0 ? 1 : 2, nspin = mode == 2 ? 2 : 1;
+  const double* st[2] = {nullptr, nullptr};
+  int gga = -1;
+  for (int k = 0; k < nkern; ++k) {
+    const int h = kernels[k];
+    if (h < 0 || h >= (int)ctx->kstores.size() || !ctx->kstores[h]) return fail(ctx, SXC_ERR_INVALID, "invalid kernel handle %d", h);
+    KernelStore& ks = *ctx->kstores[h];
+    if (ks.grid != grid || ks.nspin != store_nspin || (gga >= 0 && ks.gga != gga))
+      return fail(ctx, SXC_ERR_INVALID, "kernel store %d does not match (grid, spin mode, gga) of this contraction", h);
+    gga = ks.gga;
+    st[k] = ks.data.as<double>();
+  }
+  CU(cudaSetDevice(ctx->device));
+  Grid& g = *gp;
+  Basis& b = *bp;
+  Plan* pp = nullptr;
+  TRY(get_plan(ctx, grid, basis_j, &pp));
+  Plan& p = *pp;
+  TRY(ensure_point_arrays(ctx, g, false, nspin));
+  const long N = g.npts;
+  const size_t nb2 = (size_t)b.nbf * b.nbf;
+  const size_t rows = (size_t)4 * nspin;
+  const size_t resp_bytes = (size_t)nvec * rows * std::max<long>(N, 1) * sizeof(double);
+  const bool fresh = !accumulate || g.resp_nvec != nvec || g.resp_nspin != nspin || g.resp_gga != gga;
+  if (accumulate && fresh && g.resp_nvec != 0)
+    return fail(ctx, SXC_ERR_INVALID, "accumulate: the stored response (nvec %d, nspin %d) does not match", g.resp_nvec, g.resp_nspin);
+  if (fresh) {
+    CU(g.resp.ensure(resp_bytes));
+    CU(cudaMemsetAsync(g.resp.p, 0, resp_bytes, ctx->stream));
+    g.resp_nvec = nvec;
+    g.resp_nspin = nspin;
+    g.resp_gga = gga;
+  }
+  CU(ctx->dP.ensure((size_t)nvec * nspin * nb2 * sizeof(double)));
+  TRY(upload_async(ctx, ctx->dP.p, D, (size_t)nvec * nspin * nb2 * sizeof(double)));
+  TRY(upload_done(ctx));
+  begin_timing(ctx, true);
+  ctx->stats = p.stats;
+  const int launches0 = ctx->launches;
+  {
+    PhaseTimer t_all(ctx, T_TOTAL);
+    TRY(run_screen(ctx, g, b, p));
+    TRY(wait_p_ready(ctx));
+    {
+      dim3 blk(32, 8), grd((b.nbf + 31) / 32, (b.nbf + 7) / 8);
+      for (int m = 0; m < nvec * nspin; ++m) {
+        k_symmetrise<<<grd, blk, 0, ctx->stream>>>(b.nbf, ctx->dP.as<double>() + (size_t)m * nb2);
+        LAUNCH_CHECK();
+      }
+    }
+    double* dens = g.dens.as<double>();
+    for (const Chunk& c : p.chunks) {
+      if (c.nslots == 0) continue;
+      TRY(phase_basis(ctx, g, b, p, c));
+      for (int v = 0; v < nvec; ++v) {
+        for (int sp = 0; sp < nspin; ++sp)
+          TRY(phase_density(ctx, g, b, p, c, ctx->dP.as<double>() + ((size_t)v * nspin + sp) * nb2, dens + (size_t)4 * sp * N,
+                            gga != 0, nullptr));
+        PhaseTimer t(ctx, SXC_T_FUNCTIONAL);
+        k_kernel_apply<<<c.nslots, 128, 0, ctx->stream>>>(N, g.blocksize, p.block_id.as<int>() + c.slot0, mode, gga, st[0], st[1],
+                                                          dens, 1, g.resp.as<double>() + (size_t)v * rows * N);
+        LAUNCH_CHECK();
+      }
+    }
+  }
+  ctx->timing = false;
+  ctx->stats.kernel_launches = ctx->launches - launches0;
+  CU(cudaStreamSynchronize(ctx->stream));
+  collect_timers(ctx);
+  return SXC_OK;
+}
+
+int sxc_kernel_response_copy(sxc_ctx* ctx, int grid, int save) {
+  Grid* gp = ctx ? get_grid(ctx, grid) : nullptr;
+  if (!gp) return fail(ctx, SXC_ERR_INVALID, "invalid grid handle %d", grid);
+  Grid& g = *gp;
+  CU(cudaSetDevice(ctx->device));
+  if (save) {
+    if (g.resp_nvec == 0) return fail(ctx, SXC_ERR_INVALID, "no contracted response on grid %d to save", grid);
+    const size_t bytes = (size_t)g.resp_nvec * 4 * g.resp_nspin * std::max<long>(g.npts, 1) * sizeof(double);
+    CU(g.resp_saved.ensure(bytes));
+    CU(cudaMemcpyAsync(g.resp_saved.p, g.resp.p, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    g.saved_nvec = g.resp_nvec;
+    g.saved_nspin = g.resp_nspin;
+    g.saved_gga = g.resp_gga;
+  } else {
+    if (g.saved_nvec == 0) return fail(ctx, SXC_ERR_INVALID, "no saved response on grid %d", grid);
+    const size_t bytes = (size_t)g.saved_nvec * 4 * g.saved_nspin * std::max<long>(g.npts, 1) * sizeof(double);
+    CU(g.resp.ensure(bytes));
+    CU(cudaMemcpyAsync(g.resp.p, g.resp_saved.p, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    g.resp_nvec = g.saved_nvec;
+    g.resp_nspin = g.saved_nspin;
+    g.resp_gga = g.saved_gga;
+  }
+  return SXC_OK;
+}
+
+int sxc_kernel_integrate(sxc_ctx* ctx, int grid, int basis_i, double* F) {
+  if (!ctx || !F) return fail(ctx, SXC_ERR_INVALID, "sxc_kernel_integrate: bad arguments");
+  Grid* gp = get_grid(ctx, grid);
+  Basis* bp = get_basis(ctx, basis_i);
+  if (!gp || !bp) return fail(ctx, SXC_ERR_INVALID, "invalid grid (%d) or basis (%d) handle", grid, basis_i);
+  Grid& g = *gp;
+  Basis& b = *bp;
+  if (g.resp_nvec == 0) return fail(ctx, SXC_ERR_INVALID, "no contracted response on grid %d (call sxc_kernel_contract first)", grid);
+  CU(cudaSetDevice(ctx->device));
+  Plan* pp = nullptr;
+  TRY(get_plan(ctx, grid, basis_i, &pp));
+  Plan& p = *pp;
+  const int nvec = g.resp_nvec, nspin = g.resp_nspin;
+  const bool gga = g.resp_gga != 0;
+  const long N = g.npts;
+  const size_t nb2 = (size_t)b.nbf * b.nbf, nmat = (size_t)nvec * nspin;
+  const size_t rows = (size_t)4 * nspin;
+  CU(ctx->dOut.ensure((nmat * nb2 + 2) * sizeof(double)));
+  begin_timing(ctx, true);
+  ctx->stats = p.stats;
+  const int launches0 = ctx->launches;
+  {
+    PhaseTimer t_all(ctx, T_TOTAL);
+    CU(cudaMemsetAsync(ctx->dOut.p, 0, nmat * nb2 * sizeof(double), ctx->stream));
+    TRY(run_screen(ctx, g, b, p));
+    for (const Chunk& c : p.chunks) {
+      if (c.nslots == 0) continue;
+      TRY(phase_basis(ctx, g, b, p, c));
+      // F + F^T = sum_p scal phi_i phi_j + grad . (phi_i grad phi_j + grad phi_i phi_j): the XC scatter with the
+      // weights already inside scal / grad ... which the contraction left out, so the scatter's w restores them
+      for (size_t m = 0; m < nmat; ++m)
+        TRY(phase_scatter(ctx, g, b, p, c, gga, 0.0, g.resp.as<double>() + (m / nspin) * rows * N + (m % nspin) * 4 * N,
+                          ctx->dOut.as<double>() + m * nb2));
+    }
+    for (size_t m = 0; m < nmat; ++m) TRY(finish_matrix(ctx, b.nbf, ctx->dOut.as<double>() + m * nb2));
+  }
+  ctx->timing = false;
+  ctx->stats.kernel_launches = ctx->launches - launches0;
+  CU(cudaMemcpyAsync(F, ctx->dOut.p, nmat * nb2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  collect_timers(ctx);
+  return SXC_OK;
+}
+
+int sxc_kernel_sigma(sxc_ctx* ctx, int grid, int basis, int nkern, const int* kernels, int mode, int nvec, const double* D,
+                     double* F) {
+  TRY(sxc_kernel_contract(ctx, grid, basis, nkern, kernels, mode, nvec, D, 0));
+  return sxc_kernel_integrate(ctx, grid, basis, F);
 }
 
 int sxc_get_stats(sxc_ctx* ctx, sxc_stats* out) {

@@ -382,5 +382,156 @@ class ABFuncPotential : public ObjectSensitive {
   std::unique_ptr<Matrix> _abPotential;
 };
 
+// postHF/LRSCF/Kernel/Kernel.h:50-208: the second functional derivatives of the subsystem XC functionals
+// and of the non-additive XC / kinetic functionals on one grid.  Like the reference the object keeps a "total" set
+// (non-additive functionals on the summed density, _pptot/_pgtot/_ggtot) and one set per subsystem (func_I - naddXC - naddKin
+// on rho_I, _pp/_pg/_gg); getPP(I, J) = total + (I == J ? subsystem I : 0) (Kernel.cpp:170-230).  The data stays on the device;
+// the handles are what KernelSigmavector contracts with.  SCFMode = UNRESTRICTED with RESTRICTED-halved densities is the
+// reference's "ukernel" of the triplet case (Kernel.cpp:905-930).
+template<Options::SCF_MODES SCFMode>
+class Kernel {
+ public:
+  Kernel(std::shared_ptr<B200::XCDevice> device, std::shared_ptr<GridController> grid,
+         std::vector<std::shared_ptr<DensityMatrixController<SCFMode>>> dMats, std::vector<Functional> funcs,
+         Functional naddXCFunc = Functional(), Functional naddKinFunc = Functional(), bool gga = true)
+    : _dev(std::move(device)), _grid(std::move(grid)), _dMats(std::move(dMats)), _gga(gga) {
+    if (_dMats.empty() || funcs.size() != _dMats.size())
+      throw SerenityError("Kernel: one functional per subsystem is needed");
+    const int g = _grid->handle(*_dev);
+    const int nspin = detail::nspin<SCFMode>();
+    const bool embedded = !naddXCFunc.basicFunctionals.empty() || !naddKinFunc.basicFunctionals.empty();
+    std::vector<int> bc;
+    std::vector<const double*> pc;
+    for (auto& d : _dMats) {
+      bc.push_back(d->getBasisController()->handle(*_dev));
+      pc.push_back(d->getDensityMatrix().data());
+    }
+    // calculateDerivatives (Kernel.cpp:686-747)
+    for (size_t I = 0; I < _dMats.size(); ++I) {
+      int k = -1;
+      _dev->check(sxc_kernel_create(_dev->get(), g, nspin, _gga ? 1 : 0, &k));
+      _sub.push_back(k);
+      _dev->check(sxc_kernel_add(_dev->get(), k, detail::functionalHandle(*_dev, funcs[I]), 1.0, 1, &bc[I], &pc[I]));
+      if (!naddXCFunc.basicFunctionals.empty())
+        _dev->check(sxc_kernel_add(_dev->get(), k, detail::functionalHandle(*_dev, naddXCFunc), -1.0, 1, &bc[I], &pc[I]));
+      if (!naddKinFunc.basicFunctionals.empty())
+        _dev->check(sxc_kernel_add(_dev->get(), k, detail::functionalHandle(*_dev, naddKinFunc), -1.0, 1, &bc[I], &pc[I]));
+    }
+    if (embedded) {
+      _dev->check(sxc_kernel_create(_dev->get(), g, nspin, _gga ? 1 : 0, &_tot));
+      if (!naddXCFunc.basicFunctionals.empty())
+        _dev->check(sxc_kernel_add(_dev->get(), _tot, detail::functionalHandle(*_dev, naddXCFunc), 1.0, (int)bc.size(), bc.data(),
+                                   pc.data()));
+      if (!naddKinFunc.basicFunctionals.empty())
+        _dev->check(sxc_kernel_add(_dev->get(), _tot, detail::functionalHandle(*_dev, naddKinFunc), 1.0, (int)bc.size(), bc.data(),
+                                   pc.data()));
+    }
+  }
+  ~Kernel() {
+    for (int k : _sub) sxc_kernel_destroy(_dev->get(), k);
+    if (_tot >= 0) sxc_kernel_destroy(_dev->get(), _tot);
+  }
+  Kernel(const Kernel&) = delete;
+  Kernel& operator=(const Kernel&) = delete;
+  bool isGGA() const { return _gga; }
+  unsigned int getNSystems() const { return (unsigned int)_dMats.size(); }
+  std::shared_ptr<GridController> getGridController() const { return _grid; }
+  std::shared_ptr<BasisController> getBasisController(unsigned I) const { return _dMats[I]->getBasisController(); }
+  // device handles behind getPP/getPG/getGG(I, J, ...)
+  std::vector<int> stores(unsigned I, unsigned J) const {
+    std::vector<int> k;
+    if (_tot >= 0) k.push_back(_tot);
+    if (I == J) k.push_back(_sub[I]);
+    return k;
+  }
+  int totalStore() const { return _tot; }
+  // Kernel::getPP(I, J, blockSize, iGridStart) (Kernel.cpp:170-230): first array(s) of the summed stores for one block
+  std::vector<double> getPP(unsigned I, unsigned J, unsigned blockSize, unsigned iGridStart) const {
+    const unsigned N = _grid->getNGridPoints();
+    const int npp = SCFMode == Options::SCF_MODES::RESTRICTED ? 1 : 3;
+    std::vector<double> out((size_t)npp * blockSize, 0.0);
+    for (int k : stores(I, J)) {
+      const int narr = sxc_kernel_num_arrays(_dev->get(), k);
+      std::vector<double> all((size_t)narr * N);
+      _dev->check(sxc_kernel_get(_dev->get(), k, all.data()));
+      for (int a = 0; a < npp; ++a)
+        for (unsigned p = 0; p < blockSize && iGridStart + p < N; ++p) out[(size_t)a * blockSize + p] += all[(size_t)a * N + iGridStart + p];
+    }
+    return out;
+  }
+
+ private:
+  std::shared_ptr<B200::XCDevice> _dev;
+  std::shared_ptr<GridController> _grid;
+  std::vector<std::shared_ptr<DensityMatrixController<SCFMode>>> _dMats;
+  bool _gga;
+  std::vector<int> _sub;
+  int _tot = -1;
+};
+
+// postHF/LRSCF/Sigmavectors/KernelSigmavector.h:40-123.  calcF(I, J, D) returns the Fock-like matrices of
+// KernelSigmavector.cpp:119-252 for the trial densities D (in the basis of subsystem J; UNRESTRICTED: alpha and beta matrices
+// of every vector back to back); contractSupersystemDensity() is :60-117 (all subsystems' densities contracted once with the
+// total-density kernel).  A RESTRICTED sigma vector built with an UNRESTRICTED kernel is the triplet case (:381-404).
+template<Options::SCF_MODES SCFMode, Options::SCF_MODES KernelMode = SCFMode>
+class KernelSigmavector {
+ public:
+  KernelSigmavector(std::shared_ptr<B200::XCDevice> device, std::shared_ptr<Kernel<KernelMode>> kernel)
+    : _dev(std::move(device)), _kernel(std::move(kernel)) {
+    if (!_kernel) throw SerenityError("A kernel sigma vector was requested with no kernel present.");
+  }
+  // D[J] = trial densities of subsystem J (nvec x nspin matrices); afterwards calcF(I, I, ...) adds the supersystem part
+  void contractSupersystemDensity(const std::vector<std::vector<Matrix>>& D) {
+    if (_kernel->totalStore() < 0) throw SerenityError("KernelSigmavector: no embedding kernel to contract");
+    const int tot = _kernel->totalStore();
+    for (unsigned J = 0; J < D.size(); ++J) contract(J, {tot}, D[J], J != 0);
+    _dev->check(sxc_kernel_response_copy(_dev->get(), _kernel->getGridController()->handle(*_dev), 1));
+    _supersystem = true;
+  }
+  std::vector<Matrix> calcF(unsigned I, unsigned J, const std::vector<Matrix>& densityMatrices) {
+    if (I != J && _supersystem) return {};  // already inside the supersystem contraction (:142-145)
+    std::vector<int> k = _kernel->stores(I, J);
+    if (_supersystem) {  // the total-density part is in the saved supersystem response: add the subsystem store only
+      k = {k.back()};
+      _dev->check(sxc_kernel_response_copy(_dev->get(), _kernel->getGridController()->handle(*_dev), 0));
+    }
+    if (k.empty()) return {};
+    contract(J, k, densityMatrices, _supersystem);
+    const int nb = (int)_kernel->getBasisController(I)->getNBasisFunctions();
+    const size_t nmat = densityMatrices.size();
+    std::vector<double> flat(nmat * (size_t)nb * nb);
+    _dev->check(sxc_kernel_integrate(_dev->get(), _kernel->getGridController()->handle(*_dev),
+                                     _kernel->getBasisController(I)->handle(*_dev), flat.data()));
+    std::vector<Matrix> F;
+    for (size_t m = 0; m < nmat; ++m) {
+      Matrix M(nb, nb);
+      std::copy(flat.begin() + m * (size_t)nb * nb, flat.begin() + (m + 1) * (size_t)nb * nb, M.values.begin());
+      F.push_back(std::move(M));
+    }
+    return F;
+  }
+
+ private:
+  static constexpr int mode() {
+    return SCFMode == Options::SCF_MODES::UNRESTRICTED ? 2 : (KernelMode == Options::SCF_MODES::UNRESTRICTED ? 1 : 0);
+  }
+  void contract(unsigned J, const std::vector<int>& stores, const std::vector<Matrix>& D, bool accumulate) {
+    const int nb = (int)_kernel->getBasisController(J)->getNBasisFunctions();
+    const int nspin = detail::nspin<SCFMode>();
+    if (D.empty() || D.size() % nspin) throw SerenityError("KernelSigmavector: nvec x nspin density matrices are needed");
+    std::vector<double> flat;
+    for (const Matrix& M : D) {
+      if (M.rows() != nb || M.cols() != nb) throw SerenityError("KernelSigmavector: density matrix of the wrong dimension");
+      flat.insert(flat.end(), M.values.begin(), M.values.end());
+    }
+    _dev->check(sxc_kernel_contract(_dev->get(), _kernel->getGridController()->handle(*_dev),
+                                    _kernel->getBasisController(J)->handle(*_dev), (int)stores.size(), stores.data(), mode(),
+                                    (int)D.size() / nspin, flat.data(), accumulate ? 1 : 0));
+  }
+  std::shared_ptr<B200::XCDevice> _dev;
+  std::shared_ptr<Kernel<KernelMode>> _kernel;
+  bool _supersystem = false;
+};
+
 }  // namespace Serenity
 #endif

@@ -266,6 +266,62 @@ class XCContext:
                                                     _ptr(out)))
         return out, float(self._lib.sxc_last_partition_ms(self._h))
 
+    # ---- row f-4: LR-TDDFT kernel
+    def kernel_create(self, grid: int, nspin: int = 1, gga: bool = True) -> int:
+        k = C.c_int(-1)
+        self._check(self._lib.sxc_kernel_create(self._h, grid, nspin, 1 if gga else 0, C.byref(k)))
+        return k.value
+
+    def kernel_destroy(self, kernel: int):
+        self._check(self._lib.sxc_kernel_destroy(self._h, kernel))
+
+    def kernel_add(self, kernel: int, func: int, basis_c, P_c, sign: float = 1.0, nspin: int = 1):
+        """One storeDerivatives call (Kernel.cpp:476-683) on the summed density of the (basis, P) pairs; nspin = 2: every
+        P is a (P_alpha, P_beta) pair."""
+        mats = [_spin_pack(p) if nspin == 2 else np.asfortranarray(p, dtype=np.float64) for p in P_c]
+        ptrs = (C.c_void_p * len(mats))(*[m.ctypes.data for m in mats])
+        hb = np.ascontiguousarray(basis_c, dtype=np.int32)
+        self._check(self._lib.sxc_kernel_add(self._h, kernel, func, float(sign), len(mats), _ptr(hb), ptrs))
+
+    def kernel_get(self, kernel: int, npts: int):
+        n = self._lib.sxc_kernel_num_arrays(self._h, kernel)
+        self._check(min(n, 0))
+        out = np.zeros((n, npts))
+        self._check(self._lib.sxc_kernel_get(self._h, kernel, _ptr(out)))
+        return out
+
+    @staticmethod
+    def _pack_vectors(D, mode):
+        """D: list of matrices (modes 0, 1) or of (D_alpha, D_beta) pairs (mode 2) -> [nvec * nspin, nb * nb]."""
+        rows = []
+        for d in D:
+            for m in (d if mode == 2 else [d]):
+                rows.append(np.asarray(m, dtype=np.float64).reshape(-1, order="F"))
+        return np.ascontiguousarray(np.stack(rows))
+
+    def kernel_contract(self, grid: int, basis_j: int, kernels, D, mode: int = 0, accumulate: bool = False):
+        """contractKernel + contractBlock (KernelSigmavector.cpp:254-311, :360-497) for the trial densities D."""
+        buf = self._pack_vectors(D, mode)
+        hk = np.ascontiguousarray(kernels, dtype=np.int32)
+        self._check(self._lib.sxc_kernel_contract(self._h, grid, basis_j, len(hk), _ptr(hk), mode, len(D), _ptr(buf),
+                                                  1 if accumulate else 0))
+
+    def kernel_response_copy(self, grid: int, save: bool):
+        """save: keep the current contracted response (the supersystem contraction); not save: restore it."""
+        self._check(self._lib.sxc_kernel_response_copy(self._h, grid, 1 if save else 0))
+
+    def kernel_integrate(self, grid: int, basis_i: int, nbf: int, nvec: int, mode: int = 0):
+        """numericalIntegration + F += F^T (KernelSigmavector.cpp:313-358, :236-249) -> list of matrices / spin pairs."""
+        nspin = 2 if mode == 2 else 1
+        F = np.zeros((nvec * nspin, nbf * nbf))
+        self._check(self._lib.sxc_kernel_integrate(self._h, grid, basis_i, _ptr(F)))
+        mats = [np.asfortranarray(F[m].reshape(nbf, nbf, order="F")) for m in range(nvec * nspin)]
+        return mats if nspin == 1 else [tuple(mats[2 * v:2 * v + 2]) for v in range(nvec)]
+
+    def kernel_sigma(self, grid: int, basis: int, nbf: int, kernels, D, mode: int = 0):
+        self.kernel_contract(grid, basis, kernels, D, mode, False)
+        return self.kernel_integrate(grid, basis, nbf, len(D), mode)
+
     def stats(self) -> dict:
         s = Stats()
         self._check(self._lib.sxc_get_stats(self._h, C.byref(s)))

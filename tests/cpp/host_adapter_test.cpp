@@ -73,6 +73,8 @@ int main(int argc, char** argv) {
     auto dA = std::make_shared<DensityMatrixController<R::RESTRICTED>>(basisA, readMatrix(in, nA));
     auto dB = std::make_shared<DensityMatrixController<R::RESTRICTED>>(basisB, readMatrix(in, nB));
     DensityMatrix PA2 = readMatrix(in, nA);
+    Matrix DA = readMatrix(in, nA);  // trial densities of the LR-TDDFT sigma vector (row f-4)
+    Matrix DB = readMatrix(in, nB);
 
     // KS-DFT potential of subsystem A on the common grid
     auto pot = std::make_shared<FuncPotential<R::RESTRICTED>>(dev, dA, grid, xc);
@@ -116,6 +118,28 @@ int main(int argc, char** argv) {
     // gradient of the non-additive XC potential over the active atoms (NAddFuncPotential.cpp:329-493)
     Matrix gradN = naddXC->getGeomGradients();
     wr(out, gradN.data(), (int64_t)gradN.rows() * 3);
+    // subsystem-TDDFT kernel sigma vector of subsystem A (Kernel.cpp:686-747, KernelSigmavector.cpp:60-252): supersystem
+    // contraction of both subsystems' trial densities with the non-additive kernel, then the intra-subsystem part
+    {
+      using DMC = DensityMatrixController<R::RESTRICTED>;
+      auto kernel = std::make_shared<Kernel<R::RESTRICTED>>(dev, grid, std::vector<std::shared_ptr<DMC>>{dA, dB},
+                                                            std::vector<Functional>{xc, xc}, xc, kin);
+      KernelSigmavector<R::RESTRICTED> sigma(dev, kernel);
+      sigma.contractSupersystemDensity({{DA}, {DB}});
+      if (!sigma.calcF(0, 1, {DB}).empty()) throw SerenityError("calcF(I != J) must defer to the supersystem contraction");
+      std::vector<Matrix> F = sigma.calcF(0, 0, {DA});
+      wr(out, F[0].data(), (int64_t)nA * nA);
+      std::vector<Matrix> FB = sigma.calcF(1, 1, {DB});  // every subsystem starts from the same supersystem contraction
+      wr(out, FB[0].data(), (int64_t)nB * nB);
+      // isolated system, two vectors at once
+      auto iso = std::make_shared<Kernel<R::RESTRICTED>>(dev, grid, std::vector<std::shared_ptr<DMC>>{dA}, std::vector<Functional>{xc});
+      KernelSigmavector<R::RESTRICTED> sigmaIso(dev, iso);
+      std::vector<Matrix> F2 = sigmaIso.calcF(0, 0, {DA, PA2});
+      wr(out, F2[0].data(), (int64_t)nA * nA);
+      wr(out, F2[1].data(), (int64_t)nA * nA);
+      std::vector<double> pp = iso->getPP(0, 0, 128, 256);
+      wr(out, pp.data(), 128);
+    }
     // error convention: SerenityError, as the reference throws (here: a functional id the library does not implement)
     bool threw = false;
     try {

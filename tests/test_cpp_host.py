@@ -67,6 +67,11 @@ def test_cpp_potentials_match_oracle(tmp_path):
         _w(f, act.P.reshape(-1, order="F"), np.float64)
         _w(f, env.P.reshape(-1, order="F"), np.float64)
         _w(f, PA2.reshape(-1, order="F"), np.float64)
+        rng = np.random.default_rng(9)
+        DA = rng.standard_normal((act.basis.nbf, act.basis.nbf))
+        DB = rng.standard_normal((env.basis.nbf, env.basis.nbf))
+        _w(f, DA.reshape(-1, order="F"), np.float64)
+        _w(f, DB.reshape(-1, order="F"), np.float64)
     r = subprocess.run([_exe(), fin, fout], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     nA = act.basis.nbf
@@ -75,6 +80,9 @@ def test_cpp_potentials_match_oracle(tmp_path):
         grad = _r(f, (len(act.symbols), 3))
         Vab = _r(f, (nA, env.basis.nbf))
         gradN = _r(f, (len(act.symbols), 3))
+        nB = env.basis.nbf
+        F_fde, F_fde_B, F_iso0, F_iso1 = _r(f, (nA, nA)), _r(f, (nB, nB)), _r(f, (nA, nA)), _r(f, (nA, nA))
+        pp_block = _r(f, (128,))
     og = orc.Grid(cfg.xyz, cfg.w, 128)
     bA, bE = orc.Basis(act.basis), orc.Basis(env.basis)
 
@@ -97,3 +105,29 @@ def test_cpp_potentials_match_oracle(tmp_path):
     gradN_ref = orc.nadd_gradient(bA, PA2, [(bE, env.P)], og, orc.Functional(*xc), atom_indices_of_basis(act.basis, act.coords),
                                   len(act.symbols))
     assert np.abs(gradN - gradN_ref).max() <= 1e-9
+
+    # row f-4: subsystem-TDDFT kernel sigma vector through Kernel / KernelSigmavector (the density is PA2 at that point)
+    fx, fk = orc.Functional(*xc), orc.Functional(*kin)
+    ra, ga, _, _ = orc.density_on_grid(bA, og, 1e-9, PA2, 1)
+    rb, gb, _, _ = orc.density_on_grid(bE, og, 1e-9, env.P, 1)
+    rt, gt = ra + rb, [x + y for x, y in zip(ga, gb)]
+    tot = orc.kernel_store_r(fk, rt, gt, store=orc.kernel_store_r(fx, rt, gt))
+    sub = orc.kernel_store_r(fx, ra, ga)
+    sub = orc.kernel_store_r(fx, ra, ga, sign=-1.0, store=sub)
+    sub = orc.kernel_store_r(fk, ra, ga, sign=-1.0, store=sub)
+    resp_tot = orc.kernel_contract(bA, og, tot, DA, 0, True, block_ave_thr=0.0)
+    resp_tot = orc.kernel_contract(bE, og, tot, DB, 0, True, resp=resp_tot, block_ave_thr=0.0)
+    resp = orc.kernel_contract(bA, og, sub, DA, 0, True, resp=resp_tot.copy(), block_ave_thr=0.0)
+    F_ref = orc.kernel_integrate(bA, og, resp, True, block_ave_thr=0.0)
+    assert np.abs(F_fde - F_ref).max() <= 1e-10 * np.abs(F_ref).max()
+    subB = orc.kernel_store_r(fx, rb, gb)
+    subB = orc.kernel_store_r(fx, rb, gb, sign=-1.0, store=subB)
+    subB = orc.kernel_store_r(fk, rb, gb, sign=-1.0, store=subB)
+    resp = orc.kernel_contract(bE, og, subB, DB, 0, True, resp=resp_tot.copy(), block_ave_thr=0.0)
+    F_ref = orc.kernel_integrate(bE, og, resp, True, block_ave_thr=0.0)
+    assert np.abs(F_fde_B - F_ref).max() <= 1e-10 * np.abs(F_ref).max()
+    iso = orc.kernel_store_r(fx, ra, ga)
+    for F, D in ((F_iso0, DA), (F_iso1, PA2)):
+        F_ref = orc.kernel_integrate(bA, og, orc.kernel_contract(bA, og, iso, D, 0, True, block_ave_thr=0.0), True, block_ave_thr=0.0)
+        assert np.abs(F - F_ref).max() <= 1e-10 * np.abs(F_ref).max()
+    assert np.abs(pp_block - iso[0, 256:384]).max() <= 1e-6 * np.abs(iso[0, 256:384]).max()

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), "libserenity_xc_b200.so lacks %s" % name
     assert sorted(_lib.SYMBOLS) == declared  # the ctypes binding covers the whole header
-    assert lib.sxc_abi_version() == 4
+    assert lib.sxc_abi_version() == 5
 
 
 def test_stats_struct_matches_header():

@@ -1,0 +1,410 @@
+"""LR-TDDFT / subsystem-TDDFT kernel: second functional derivatives on the grid
+(src/postHF/LRSCF/Kernel/Kernel.cpp:476-747) and their contraction with trial densities
+(src/postHF/LRSCF/Sigmavectors/KernelSigmavector.cpp:119-497).
+
+The reference holds no known-answer value for this path (Kernel_test.cpp:51-66 only demands that getPP/getPG/getGG do not
+fail and points to a KernelSigmaVector_test.cpp that does not exist), so the oracle restatement is pinned to the DEFINITION:
+  * the Hessian of every basic functional = finite differences of its (pinned) first derivatives,
+  * the sigma matrix F[D] = d/d eps V_xc[P + eps (D + D^T)/2] - the directional derivative of the XC potential matrix of
+    FuncPotential (rows 8a-1 ... 8a-6, pinned against the reference's KATs), restricted, unrestricted and triplet.
+GPU tests compare the CUDA path with that oracle.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ALL_IDS = (2, 45, 66, 80, 81, 135, 184, 193, 197, 283, 286)
+
+
+def _points(rng, n):
+    """random spin densities / gradients spanning the density range of a molecular grid"""
+    for _ in range(n):
+        dens = 10.0 ** rng.uniform(-8, 0.5)
+        pol = rng.uniform(0.05, 0.95)
+        ga = rng.normal(size=3) * dens ** (4 / 3) * rng.uniform(0.1, 3)
+        gb = rng.normal(size=3) * dens ** (4 / 3) * rng.uniform(0.1, 3)
+        yield np.array([dens * pol, dens * (1 - pol), ga @ ga, ga @ gb, gb @ gb])
+
+
+@pytest.mark.parametrize("fid", ALL_IDS)
+def test_oracle_hessian_is_the_derivative_of_the_pinned_first_derivatives(fid):
+    from oracle import pyoracle as orc
+    rng = np.random.default_rng(fid)
+    for _ in range(4):
+        ga, gb = rng.normal(size=3) * 0.3, rng.normal(size=3) * 0.3
+        x = np.array([rng.uniform(0.01, 1.0), rng.uniform(0.01, 1.0), ga @ ga, ga @ gb, gb @ gb])
+        F, d, h = orc.basic_functional_d2(fid, *x)
+        F1, d1 = orc.basic_functional_u(fid, *x)
+        assert abs(F - F1) <= 1e-13 * (1 + abs(F)) and np.abs(d - d1).max() <= 1e-12 * (1 + np.abs(d).max())
+        assert np.abs(h - h.T).max() <= 1e-10 * (1 + np.abs(h).max())
+        for j in range(5):
+            step = 1e-5 * max(abs(x[j]), 1e-2)
+            xp, xm = x.copy(), x.copy()
+            xp[j] += step
+            xm[j] -= step
+            fd = (orc.basic_functional_u(fid, *xp)[1] - orc.basic_functional_u(fid, *xm)[1]) / (2 * step)
+            assert np.abs(fd - h[:, j]).max() <= 2e-8 * (1 + np.abs(h).max()), (fid, j)
+
+
+@pytest.fixture(scope="module")
+def probe():
+    """the DEVICE functional source (functionals.cuh + kernel2.cuh) compiled for the host by nvcc"""
+    from serenity_b200.build import build_jet_probe
+    lib = C.CDLL(build_jet_probe())
+    return lib
+
+
+@pytest.mark.parametrize("fid", ALL_IDS)
+def test_device_jets_agree_with_the_oracle_on_the_host(probe, fid):
+    """Jet2<5> / Jet2<2> of kernel2.cuh (packed-Hessian forward mode) against the oracle's nested first-order jets."""
+    from oracle import pyoracle as orc
+    d = C.c_double
+    rng = np.random.default_rng(100 + fid)
+    iu = np.triu_indices(5)
+    tol = 2e-11 if fid == 197 else 2e-12  # PBE correlation: expm1 / log1p cancellation at low density
+    for x in _points(rng, 100):
+        F, d5, h15 = d(), np.zeros(5), np.zeros(15)
+        rc = probe.jet_probe_u(fid, *[d(v) for v in x], C.byref(F), d5.ctypes.data_as(C.c_void_p), h15.ctypes.data_as(C.c_void_p))
+        assert rc == 0
+        Fo, do, ho = orc.basic_functional_d2(fid, *x)
+        H = np.zeros((5, 5))
+        H[iu] = h15
+        H = H + H.T - np.diag(np.diag(H))
+        sc = np.array([x[0], x[1], x[2], max(abs(x[3]), 1e-300), x[4]])  # derivative i scales like 1 / x_i
+        assert abs(F.value - Fo) <= tol * abs(Fo)
+        assert np.abs((d5 - do) * sc).max() <= tol * np.abs(do * sc).max()
+        assert np.abs((H - ho) * np.outer(sc, sc)).max() <= tol * np.abs(ho * np.outer(sc, sc)).max()
+        # the closed-shell seeding of k_kernel2_r: F(n, sigma) = f(n/2, n/2, sigma/4, sigma/4, sigma/4)
+        rho, sig = x[0] + x[1], x[2]
+        o6 = np.zeros(6)
+        probe.jet_probe_r(fid, d(rho), d(sig), o6.ctypes.data_as(C.c_void_p))
+        _, dc, hc = orc.basic_functional_d2(fid, rho / 2, rho / 2, sig / 4, sig / 4, sig / 4)
+        ref = np.array([0.25 * hc[:2, :2].sum() * rho * rho, 0.125 * hc[:2, 2:].sum() * rho * sig, hc[2:, 2:].sum() / 16 * sig * sig])
+        got = np.array([o6[3] * rho * rho, o6[4] * rho * sig, o6[5] * sig * sig])
+        assert np.abs(ref - got).max() <= tol * np.abs(ref).max()
+        assert abs(o6[2] - 0.25 * dc[2:].sum()) * sig <= tol * abs(0.25 * dc[2:].sum() * sig) + 1e-300
+
+
+# ------------------------------------------------------------------------------------------------ oracle: sigma vectors
+def _h2o():
+    from oracle import pyoracle as orc
+    from serenity_b200.inputs import make_config
+    cfg = make_config("h2o", 2)
+    sub = cfg.subsystems[0]
+    return cfg, sub, orc.Basis(sub.basis), orc.Grid(cfg.xyz, cfg.w, 128)
+
+
+def _trial(nb, seed, scale=1.0):
+    rng = np.random.default_rng(seed)
+    return rng.standard_normal((nb, nb)) * scale  # NOT symmetric: calcF symmetrises (KernelSigmavector.cpp:201-208)
+
+
+def _oracle_store_r(orc, ob, og, func, P, gga, sign=1.0, store=None):
+    rho, g, _, _ = orc.density_on_grid(ob, og, 1e-9, P, 1)
+    return orc.kernel_store_r(func, rho, g if func.is_gga else None, sign, gga, store)
+
+
+def _oracle_store_u(orc, ob, og, func, Pa, Pb, gga, sign=1.0, store=None):
+    ra, ga, _, _ = orc.density_on_grid(ob, og, 1e-9, Pa, 1)
+    rb, gb, _, _ = orc.density_on_grid(ob, og, 1e-9, Pb, 1)
+    return orc.kernel_store_u(func, np.stack([ra, rb]), np.stack([np.stack(ga), np.stack(gb)]) if func.is_gga else None, sign, gga,
+                              store)
+
+
+@pytest.mark.parametrize("fname", ["LDA", "PBE", "B3LYP"])
+def test_oracle_singlet_sigma_is_the_directional_derivative_of_vxc(fname):
+    from oracle import pyoracle as orc
+    from serenity_b200.inputs.configs import FUNCTIONALS
+    cfg, sub, ob, og = _h2o()
+    func = orc.Functional(*FUNCTIONALS[fname])
+    gga = func.is_gga
+    store = _oracle_store_r(orc, ob, og, func, sub.P, gga)
+    D = _trial(ob.nbf, 7)
+    resp = orc.kernel_contract(ob, og, store, D, 0, gga)
+    F = orc.kernel_integrate(ob, og, resp, gga)
+    assert np.abs(F - F.T).max() == 0.0
+    eps = 2e-6  # the central difference converges as eps^2 down to ~1e-9 relative (3.7e-6 at 2e-4, 1.2e-9 at 2e-6)
+    S = 0.5 * (D + D.T)
+    Vp = orc.build_xc(ob, og, func, sub.P + eps * S)[0]
+    Vm = orc.build_xc(ob, og, func, sub.P - eps * S)[0]
+    fd = (Vp - Vm) / (2 * eps)
+    assert np.abs(F - fd).max() <= 2e-8 * np.abs(fd).max()
+
+
+@pytest.mark.parametrize("fname", ["LDA", "PBE", "BLYP"])
+def test_oracle_unrestricted_and_triplet_sigma(fname):
+    from oracle import pyoracle as orc
+    from serenity_b200.inputs.configs import FUNCTIONALS
+    cfg, sub, ob, og = _h2o()
+    func = orc.Functional(*FUNCTIONALS[fname])
+    gga = func.is_gga
+    nb = ob.nbf
+    # a spin-polarised reference density: P_alpha != P_beta, both positive
+    Pa = 0.5 * sub.P + 0.02 * np.eye(nb)
+    Pb = 0.5 * sub.P
+    # the reference zeroes the kernel where rho_sigma < 1e-8 (Kernel.cpp:606-680; 5 % of this grid's points): with that
+    # screen switched off the sigma matrix must be the exact directional derivative, with it the deviation stays < 1e-7
+    orc.kernel_set_screen(0.0)
+    store = _oracle_store_u(orc, ob, og, func, Pa, Pb, gga)
+    orc.kernel_set_screen(1e-8)
+    Da, Db = _trial(nb, 11), _trial(nb, 12)
+    resp = orc.kernel_contract(ob, og, store, (Da, Db), 2, gga)
+    Fa, Fb = orc.kernel_integrate(ob, og, resp, gga, nspin=2)
+    screened = _oracle_store_u(orc, ob, og, func, Pa, Pb, gga)
+    Fsa, Fsb = orc.kernel_integrate(ob, og, orc.kernel_contract(ob, og, screened, (Da, Db), 2, gga), gga, nspin=2)
+    assert np.abs(Fsa - Fa).max() <= 1e-7 * np.abs(Fa).max() and np.abs(Fsb - Fb).max() <= 1e-7 * np.abs(Fb).max()
+    eps = 5e-7  # truncation error of the central difference: 1.4e-6 at 1e-5, 5.6e-8 at 2e-6 (beta channel), ~ eps^2
+    Sa, Sb = 0.5 * (Da + Da.T), 0.5 * (Db + Db.T)
+    (Vap, Vbp), _, _ = orc.build_xc_u(ob, og, func, Pa + eps * Sa, Pb + eps * Sb)
+    (Vam, Vbm), _, _ = orc.build_xc_u(ob, og, func, Pa - eps * Sa, Pb - eps * Sb)
+    for F, fd in ((Fa, (Vap - Vam) / (2 * eps)), (Fb, (Vbp - Vbm) / (2 * eps))):
+        assert np.abs(F - fd).max() <= 2e-8 * np.abs(fd).max()
+    # triplet of a closed shell (KernelSigmavector.cpp:381-404) = alpha response to (+D, -D) with the UNRESTRICTED kernel
+    store_cs = _oracle_store_u(orc, ob, og, func, 0.5 * sub.P, 0.5 * sub.P, gga)
+    Ft = orc.kernel_integrate(ob, og, orc.kernel_contract(ob, og, store_cs, Da, 1, gga), gga)
+    Fu, _ = orc.kernel_integrate(ob, og, orc.kernel_contract(ob, og, store_cs, (Da, -Da), 2, gga), gga, nspin=2)
+    assert np.abs(Ft - Fu).max() <= 1e-12 * np.abs(Fu).max()
+    # and the singlet of the RESTRICTED kernel (total density changes by rho~[D]) = alpha response to (D/2, D/2)
+    store_r = _oracle_store_r(orc, ob, og, func, sub.P, gga)
+    Fs = orc.kernel_integrate(ob, og, orc.kernel_contract(ob, og, store_r, Da, 0, gga), gga)
+    Fu, _ = orc.kernel_integrate(ob, og, orc.kernel_contract(ob, og, store_cs, (0.5 * Da, 0.5 * Da), 2, gga), gga, nspin=2)
+    # (the 1e-8 screen acts on rho in the RESTRICTED and on rho_alpha = rho/2 in the UNRESTRICTED store: 3e-10 apart)
+    assert np.abs(Fs - Fu).max() <= 1e-8 * np.abs(Fu).max()
+
+
+def test_oracle_store_screening_and_sign():
+    """storeDerivatives adds with pm and then zeroes where THIS density is below 1e-8 (Kernel.cpp:484-511, :606-680)."""
+    from oracle import pyoracle as orc
+    from serenity_b200.inputs.configs import FUNCTIONALS
+    func = orc.Functional(*FUNCTIONALS["PBE"])
+    rho = np.array([1e-9, 0.5e-8, 2e-8, 0.3, 1.2])
+    g = [np.array([0.0, 1e-9, 1e-8, 0.1, -0.4]), np.array([0.0, 0.0, 2e-8, 0.2, 0.3]), np.array([0.0, 0.0, 0.0, -0.1, 0.2])]
+    st = orc.kernel_store_r(func, rho, g)
+    assert st.shape == (10, 5) and np.all(st[:, :2] == 0.0) and np.all(st[0, 2:] != 0.0)
+    st2 = orc.kernel_store_r(func, rho, g, sign=-1.0, store=st.copy())
+    assert np.abs(st2).max() <= 1e-12 * np.abs(st).max()
+    # gg = 4 F_ss g g^T + 2 F_s 1: symmetric 3 x 3 per point with trace-free part along g
+    p = 3
+    G = np.array([[st[4, p], st[5, p], st[6, p]], [st[5, p], st[7, p], st[8, p]], [st[6, p], st[8, p], st[9, p]]])
+    gv = np.array([g[0][p], g[1][p], g[2][p]])
+    perp = np.cross(gv, [1.0, 0.0, 0.0])
+    _, _, vs = orc.basic_functional(135, rho[p], gv @ gv)
+    _, _, vc = orc.basic_functional(197, rho[p], gv @ gv)
+    assert abs(perp @ G @ perp / (perp @ perp) - 2.0 * (vs + vc)) <= 1e-12 * abs(2 * (vs + vc))
+    # UNRESTRICTED screening incl. the reference's gg.xy.aa entry in the beta list (Kernel.cpp:661)
+    rho2 = np.array([[0.3, 0.5e-8, 0.3], [0.2, 0.2, 0.5e-8]])
+    gr = np.random.default_rng(0).normal(size=(2, 3, 3)) * 0.1
+    su = orc.kernel_store_u(func, rho2, gr)
+    assert np.all(su[:, 0] != 0.0)
+    assert su[0, 1] == 0.0 and su[1, 1] == 0.0 and su[2, 1] != 0.0          # alpha below: aa, ab zero, bb kept
+    assert su[0, 2] != 0.0 and su[1, 2] == 0.0 and su[2, 2] == 0.0          # beta below: ab, bb zero, aa kept
+    gg_aa = su[15::3]                                                          # xx xy xz yy yz zz (aa)
+    assert gg_aa[1, 2] == 0.0 and np.all(gg_aa[[0, 2, 3, 4, 5], 2] != 0.0)
+
+
+# ------------------------------------------------------------------------------------------------ GPU parity
+def _rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def _oracle_sigma(orc, ob, og, store, D, mode, gga, thr):
+    nspin = 2 if mode == 2 else 1
+    return orc.kernel_integrate(ob, og, orc.kernel_contract(ob, og, store, D, mode, gga, block_ave_thr=thr), gga, nspin=nspin,
+                                block_ave_thr=thr)
+
+
+# The reference drops every (i, j) term with |D_ij ave_i ave_j| <= blockAveThreshold (1e-11) in the contraction and with
+# sum|scal| ave_i ave_j <= 1e-11 in the integration (KernelSigmavector.cpp:283, :340).  The device multiplies full tiles on
+# the tensor cores, i.e. it is the reference with that screen at 0: parity is asserted tightly against the oracle at
+# threshold 0 and, separately, the effect of the reference's screen itself is bounded.
+def _store_deviation(st, ref, rho, sigma, nspin):
+    """Worst deviation of a kernel store in units of the local energy-density scale rho^(4/3): second derivatives are
+    weighted with the variables they multiply (pp rho^2, pg rho |grad rho|, gg |grad rho|^2), which is how they enter any
+    contraction; pure pointwise relative errors are meaningless where exchange and correlation terms cancel."""
+    E = np.maximum(rho, 1e-300) ** (4.0 / 3.0)
+    s1 = np.sqrt(sigma)
+    npp = 1 if nspin == 1 else 3
+    worst = 0.0
+    for a in range(st.shape[0]):
+        wgt = rho * rho if a < npp else (rho * s1 if a < npp + (3 if nspin == 1 else 12) else sigma)
+        worst = max(worst, float((np.abs(st[a] - ref[a]) * wgt / E).max()))
+    return worst
+
+
+TOL_EXACT, TOL_SCREEN = 1e-11, 2e-7   # measured: 3e-12 / 1.8e-7 on tetracene, 4e-8 on the water dimer
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fname", ["LDA", "PBE", "B3LYP", "PW91K"])
+def test_gpu_kernel_store_and_singlet_sigma_match_oracle(fname):
+    from oracle import pyoracle as orc
+    from serenity_b200.inputs.configs import FUNCTIONALS
+    from serenity_b200.xc import XCContext
+    cfg, sub, ob, og = _h2o()
+    ids, mix = FUNCTIONALS[fname]
+    func = orc.Functional(ids, mix)
+    gga = func.is_gga
+    ctx = XCContext(0)
+    g = ctx.set_grid(cfg.xyz, cfg.w, 128)
+    b = ctx.add_basis(sub.basis, 1e-9)
+    f = ctx.set_functional(ids, mix)
+    k = ctx.kernel_create(g, 1, gga)
+    ctx.kernel_add(k, f, [b], [sub.P])
+    st = ctx.kernel_get(k, cfg.npts)
+    st_ref = _oracle_store_r(orc, ob, og, func, sub.P, gga)
+    # pointwise: the second derivatives scale like rho^(-k), so rounding-level differences of the DENSITY at low-density
+    # points would dominate - the functional kernel is compared on the device's own density, the integrated quantities below
+    # on the oracle's
+    rho, grad = ctx.density_on_grid(g, b, sub.P, cfg.npts)
+    st_same = orc.kernel_store_r(func, rho, grad if gga else None, 1.0, gga)
+    assert st.shape == st_ref.shape == st_same.shape
+    sigma = grad[0] ** 2 + grad[1] ** 2 + grad[2] ** 2
+    dev = _store_deviation(st, st_same, rho, sigma, 1)
+    assert dev <= 1e-10, dev
+    assert np.array_equal(st == 0.0, st_same == 0.0)  # identical screening decisions
+    nvec = 3
+    D = [_trial(ob.nbf, 20 + v) for v in range(nvec)]
+    F = ctx.kernel_sigma(g, b, ob.nbf, [k], D, 0)
+    for v in range(nvec):
+        assert _rel(F[v], _oracle_sigma(orc, ob, og, st_ref, D[v], 0, gga, 0.0)) <= TOL_EXACT
+        assert _rel(F[v], _oracle_sigma(orc, ob, og, st_ref, D[v], 0, gga, 1e-11)) <= TOL_SCREEN
+        assert np.abs(F[v] - F[v].T).max() == 0.0
+    # the device path against its own definition: d/d eps of the device V_xc
+    eps = 1e-5
+    S = 0.5 * (D[0] + D[0].T)
+    fd = (ctx.build_xc(g, b, f, sub.P + eps * S)[0] - ctx.build_xc(g, b, f, sub.P - eps * S)[0]) / (2 * eps)
+    assert _rel(F[0], fd) <= 2e-7
+    # pm = -1 cancels the store (Kernel.cpp:716-727 subtracts the non-additive parts with the same routine)
+    ctx.kernel_add(k, f, [b], [sub.P], sign=-1.0)
+    assert np.abs(ctx.kernel_get(k, cfg.npts)).max() <= 1e-12 * np.abs(st_ref).max()
+    ctx.kernel_destroy(k)
+    ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fname", ["LDA", "PBE", "BLYP"])
+def test_gpu_unrestricted_and_triplet_sigma_match_oracle(fname):
+    from oracle import pyoracle as orc
+    from serenity_b200.inputs.configs import FUNCTIONALS
+    from serenity_b200.xc import XCContext
+    cfg, sub, ob, og = _h2o()
+    ids, mix = FUNCTIONALS[fname]
+    func = orc.Functional(ids, mix)
+    gga = func.is_gga
+    nb = ob.nbf
+    Pa, Pb = 0.5 * sub.P + 0.02 * np.eye(nb), 0.5 * sub.P
+    ctx = XCContext(0)
+    g = ctx.set_grid(cfg.xyz, cfg.w, 128)
+    b = ctx.add_basis(sub.basis, 1e-9)
+    f = ctx.set_functional(ids, mix)
+    k = ctx.kernel_create(g, 2, gga)
+    ctx.kernel_add(k, f, [b], [(Pa, Pb)], nspin=2)
+    st = ctx.kernel_get(k, cfg.npts)
+    st_ref = _oracle_store_u(orc, ob, og, func, Pa, Pb, gga)
+    ra, ga = ctx.density_on_grid(g, b, Pa, cfg.npts)   # the device's own densities (see the RESTRICTED test)
+    rb, gb = ctx.density_on_grid(g, b, Pb, cfg.npts)
+    st_same = orc.kernel_store_u(func, np.stack([ra, rb]), np.stack([np.stack(ga), np.stack(gb)]) if gga else None, 1.0, gga)
+    assert st.shape == st_ref.shape == st_same.shape == ((33 if gga else 3), cfg.npts)
+    sigma = sum((x + y) ** 2 for x, y in zip(ga, gb))
+    dev = _store_deviation(st, st_same, ra + rb, sigma, 2)
+    assert dev <= 1e-10, dev
+    assert np.array_equal(st == 0.0, st_same == 0.0)
+    D = [(_trial(nb, 31), _trial(nb, 32)), (_trial(nb, 33), _trial(nb, 34))]
+    F = ctx.kernel_sigma(g, b, nb, [k], D, 2)
+    for v in range(2):
+        for thr, tol in ((0.0, TOL_EXACT), (1e-11, TOL_SCREEN)):
+            Fa, Fb = _oracle_sigma(orc, ob, og, st_ref, D[v], 2, gga, thr)
+            assert _rel(F[v][0], Fa) <= tol and _rel(F[v][1], Fb) <= tol
+    # triplet from the closed-shell UNRESTRICTED store
+    kc = ctx.kernel_create(g, 2, gga)
+    ctx.kernel_add(kc, f, [b], [(0.5 * sub.P, 0.5 * sub.P)], nspin=2)
+    st_cs = _oracle_store_u(orc, ob, og, func, 0.5 * sub.P, 0.5 * sub.P, gga)
+    Dt = [_trial(nb, 41), _trial(nb, 42)]
+    Ft = ctx.kernel_sigma(g, b, nb, [kc], Dt, 1)
+    for v in range(2):
+        assert _rel(Ft[v], _oracle_sigma(orc, ob, og, st_cs, Dt[v], 1, gga, 0.0)) <= TOL_EXACT
+        assert _rel(Ft[v], _oracle_sigma(orc, ob, og, st_cs, Dt[v], 1, gga, 1e-11)) <= TOL_SCREEN
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_subsystem_kernel_two_stores_and_supersystem_accumulation():
+    """FDE-TDDFT bookkeeping of Kernel::calculateDerivatives (Kernel.cpp:686-747) and
+    KernelSigmavector::contractSupersystemDensity / calcF (KernelSigmavector.cpp:60-117, :119-252) on the water dimer:
+    total-density store = naddXC + naddKin on rho_A + rho_B; subsystem store = func - naddXC - naddKin on rho_I; the response
+    of both subsystems' trial densities is accumulated with the total store, then F_I adds the I == I part."""
+    from oracle import pyoracle as orc
+    from serenity_b200.inputs import make_config
+    from serenity_b200.inputs.configs import FUNCTIONALS
+    from serenity_b200.xc import XCContext
+    cfg = make_config("fde_dimer", 2)
+    sa, sb = cfg.subsystems
+    oa, ob_, og = orc.Basis(sa.basis), orc.Basis(sb.basis), orc.Grid(cfg.xyz, cfg.w, 128)
+    xc, kin = FUNCTIONALS["PBE"], FUNCTIONALS["PW91K"]
+    fx, fk = orc.Functional(*xc), orc.Functional(*kin)
+    ra, ga, _, _ = orc.density_on_grid(oa, og, 1e-9, sa.P, 1)
+    rb, gb, _, _ = orc.density_on_grid(ob_, og, 1e-9, sb.P, 1)
+    rt, gt = ra + rb, [x + y for x, y in zip(ga, gb)]
+    tot_ref = orc.kernel_store_r(fx, rt, gt)
+    tot_ref = orc.kernel_store_r(fk, rt, gt, store=tot_ref)
+    sub_ref = orc.kernel_store_r(fx, ra, ga)
+    sub_ref = orc.kernel_store_r(fx, ra, ga, sign=-1.0, store=sub_ref)
+    sub_ref = orc.kernel_store_r(fk, ra, ga, sign=-1.0, store=sub_ref)
+    DA, DB = _trial(oa.nbf, 51), _trial(ob_.nbf, 52)
+    # supersystem contraction: both subsystems with the total store (I != J pattern), then the I == I subsystem part
+    resp = orc.kernel_contract(oa, og, tot_ref, DA, 0, True, block_ave_thr=0.0)
+    resp = orc.kernel_contract(ob_, og, tot_ref, DB, 0, True, resp=resp, block_ave_thr=0.0)
+    resp = orc.kernel_contract(oa, og, sub_ref, DA, 0, True, resp=resp, block_ave_thr=0.0)
+    F_ref = orc.kernel_integrate(oa, og, resp, True, block_ave_thr=0.0)
+
+    ctx = XCContext(0)
+    g = ctx.set_grid(cfg.xyz, cfg.w, 128)
+    ba, bb = ctx.add_basis(sa.basis, 1e-9), ctx.add_basis(sb.basis, 1e-9)
+    hx, hk = ctx.set_functional(*xc), ctx.set_functional(*kin)
+    kt, ks = ctx.kernel_create(g, 1, True), ctx.kernel_create(g, 1, True)
+    ctx.kernel_add(kt, hx, [ba, bb], [sa.P, sb.P])
+    ctx.kernel_add(kt, hk, [ba, bb], [sa.P, sb.P])
+    ctx.kernel_add(ks, hx, [ba], [sa.P])
+    ctx.kernel_add(ks, hx, [ba], [sa.P], sign=-1.0)
+    ctx.kernel_add(ks, hk, [ba], [sa.P], sign=-1.0)
+    ctx.kernel_contract(g, ba, [kt], [DA], 0, accumulate=False)
+    ctx.kernel_contract(g, bb, [kt], [DB], 0, accumulate=True)
+    ctx.kernel_contract(g, ba, [ks], [DA], 0, accumulate=True)
+    F = ctx.kernel_integrate(g, ba, oa.nbf, 1, 0)[0]
+    assert _rel(F, F_ref) <= TOL_EXACT
+    # Kernel::getPP(I, I) = total + subsystem store in ONE contraction (two store handles)
+    F2 = ctx.kernel_sigma(g, ba, oa.nbf, [kt, ks], [DA], 0)[0]
+    assert _rel(F2, _oracle_sigma(orc, oa, og, tot_ref + sub_ref, DA, 0, True, 0.0)) <= TOL_EXACT
+    assert _rel(F2, _oracle_sigma(orc, oa, og, tot_ref + sub_ref, DA, 0, True, 1e-11)) <= TOL_SCREEN
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_sigma_tetracene_many_vectors_is_linear_and_matches_fd():
+    """BASELINE size (tetracene B3LYP/def2-TZVP, accuracy 4 grid): size-independent properties - linearity in D and the
+    directional derivative of the device V_xc."""
+    from serenity_b200.inputs import make_config
+    from serenity_b200.inputs.configs import FUNCTIONALS
+    from serenity_b200.xc import XCContext
+    cfg = make_config("tetracene", 4)
+    sub = cfg.subsystems[0]
+    nb = sub.basis.nbf
+    ctx = XCContext(0)
+    g = ctx.set_grid(cfg.xyz, cfg.w, 128)
+    b = ctx.add_basis(sub.basis, 1e-9)
+    f = ctx.set_functional(*FUNCTIONALS["B3LYP"])
+    k = ctx.kernel_create(g, 1, True)
+    ctx.kernel_add(k, f, [b], [sub.P])
+    rng = np.random.default_rng(5)
+    D = [rng.standard_normal((nb, nb)) * 1e-2 for _ in range(3)]
+    D.append(2.0 * D[0] - 0.5 * D[1])
+    F = ctx.kernel_sigma(g, b, nb, [k], D, 0)
+    assert _rel(F[3], 2.0 * F[0] - 0.5 * F[1]) <= 1e-11
+    eps = 1e-3
+    S = 0.5 * (D[2] + D[2].T)
+    fd = (ctx.build_xc(g, b, f, sub.P + eps * S)[0] - ctx.build_xc(g, b, f, sub.P - eps * S)[0]) / (2 * eps)
+    assert _rel(F[2], fd) <= 1e-6, _rel(F[2], fd)
+    ctx.close()
