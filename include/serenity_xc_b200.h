@@ -244,6 +244,9 @@ int sxc_kernel_num_arrays(sxc_ctx* ctx, int kernel);
  * all subsystems J, :96-117 and :214-226). */
 int sxc_kernel_contract(sxc_ctx* ctx, int grid, int basis_j, int nkern, const int* kernels, int mode, int nvec,
                         const double* D, int accumulate);
+/* same with device-resident trial densities (left untouched); asynchronous on the context's stream */
+int sxc_kernel_contract_device(sxc_ctx* ctx, int grid, int basis_j, int nkern, const int* kernels, int mode, int nvec,
+                               const double* d_D, int accumulate);
 /* save != 0: keep a copy of the grid's contracted response (KernelSigmavector::_supersystem_scalar / _supersystem_gradient,
  * KernelSigmavector.h:105-110); save == 0: make that copy the current response again, so that calcF(I, I) of every
  * subsystem I starts from the same supersystem contraction (:214-226). */
@@ -252,6 +255,9 @@ int sxc_kernel_response_copy(sxc_ctx* ctx, int grid, int save);
  * the grid integrated with the basis functions of system I.  F = nvec x nspin matrices nbf_I x nbf_I, overwritten.  With a
  * shard set F is this rank's partial sum. */
 int sxc_kernel_integrate(sxc_ctx* ctx, int grid, int basis_i, double* F);
+/* same with the result left on the device (nvec x nspin x nbf_I^2 doubles: the buffer of the single all-reduce of a
+ * multi-GPU sigma build); asynchronous on the context's stream */
+int sxc_kernel_integrate_device(sxc_ctx* ctx, int grid, int basis_i, double* d_F);
 /* calcF(I, I) for an isolated system: contract + integrate */
 int sxc_kernel_sigma(sxc_ctx* ctx, int grid, int basis, int nkern, const int* kernels, int mode, int nvec, const double* D,
                      double* F);

@@ -18,7 +18,7 @@ SYMBOLS = [
     "sxc_functional_on_grid", "sxc_functional_on_grid_u", "sxc_scalar_to_matrix", "sxc_get_stats", "sxc_balance_ranges", "sxc_abi_version",
     "sxc_partition_weights", "sxc_last_partition_ms", "sxc_scalar_to_matrix_ab", "sxc_build_ab", "sxc_nadd_gradient",
     "sxc_kernel_create", "sxc_kernel_destroy", "sxc_kernel_add", "sxc_kernel_get", "sxc_kernel_num_arrays", "sxc_kernel_contract",
-    "sxc_kernel_integrate", "sxc_kernel_sigma", "sxc_kernel_response_copy",
+    "sxc_kernel_integrate", "sxc_kernel_sigma", "sxc_kernel_response_copy", "sxc_kernel_contract_device", "sxc_kernel_integrate_device",
 ]
 
 
@@ -95,6 +95,8 @@ def load():
     lib.sxc_kernel_contract.argtypes = [vp, i, i, i, vp, i, i, vp, i]
     lib.sxc_kernel_integrate.argtypes = [vp, i, i, vp]
     lib.sxc_kernel_response_copy.argtypes = [vp, i, i]
+    lib.sxc_kernel_contract_device.argtypes = [vp, i, i, i, vp, i, i, vp, i]
+    lib.sxc_kernel_integrate_device.argtypes = [vp, i, i, vp]
     lib.sxc_kernel_sigma.argtypes = [vp, i, i, i, vp, i, i, vp, vp]
     _LIB = lib
     return lib

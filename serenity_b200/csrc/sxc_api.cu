@@ -1933,8 +1933,11 @@ __global__ void k_symmetrise(int n, double* __restrict__ D) {  // D += D^T (Kern
 }
 }  // namespace
 
-int sxc_kernel_contract(sxc_ctx* ctx, int grid, int basis_j, int nkern, const int* kernels, int mode, int nvec, const double* D,
-                        int accumulate) {
+namespace {
+// D_host != nullptr: uploaded on the side stream; else D_dev (device) is copied into the staging buffer on the build stream
+int kernel_contract_impl(sxc_ctx* ctx, int grid, int basis_j, int nkern, const int* kernels, int mode, int nvec,
+                         const double* D_host, const double* D_dev, int accumulate, bool sync) {
+  const double* D = D_host ? D_host : D_dev;
   if (!ctx || !kernels || !D || nvec <= 0 || nkern < 1 || nkern > 2)
     return fail(ctx, SXC_ERR_INVALID, "sxc_kernel_contract: bad arguments (1 or 2 kernel stores, nvec > 0)");
   if (mode < 0 || mode > 2) return fail(ctx, SXC_ERR_INVALID, "mode must be 0 (singlet), 1 (triplet) or 2 (UNRESTRICTED)");
@@ -1975,9 +1978,13 @@ int sxc_kernel_contract(sxc_ctx* ctx, int grid, int basis_j, int nkern, const in
     g.resp_gga = gga;
   }
   CU(ctx->dP.ensure((size_t)nvec * nspin * nb2 * sizeof(double)));
-  TRY(upload_async(ctx, ctx->dP.p, D, (size_t)nvec * nspin * nb2 * sizeof(double)));
-  TRY(upload_done(ctx));
-  begin_timing(ctx, true);
+  if (D_host) {
+    TRY(upload_async(ctx, ctx->dP.p, D_host, (size_t)nvec * nspin * nb2 * sizeof(double)));
+    TRY(upload_done(ctx));
+  } else {  // the caller's matrices are left untouched: D += D^T works on the staged copy
+    CU(cudaMemcpyAsync(ctx->dP.p, D_dev, (size_t)nvec * nspin * nb2 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  begin_timing(ctx, sync || ctx->timing_device);
   ctx->stats = p.stats;
   const int launches0 = ctx->launches;
   {
@@ -2008,9 +2015,21 @@ int sxc_kernel_contract(sxc_ctx* ctx, int grid, int basis_j, int nkern, const in
   }
   ctx->timing = false;
   ctx->stats.kernel_launches = ctx->launches - launches0;
-  CU(cudaStreamSynchronize(ctx->stream));
-  collect_timers(ctx);
+  if (sync) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    collect_timers(ctx);
+  }
   return SXC_OK;
+}
+}  // namespace
+
+int sxc_kernel_contract(sxc_ctx* ctx, int grid, int basis_j, int nkern, const int* kernels, int mode, int nvec, const double* D,
+                        int accumulate) {
+  return kernel_contract_impl(ctx, grid, basis_j, nkern, kernels, mode, nvec, D, nullptr, accumulate, true);
+}
+int sxc_kernel_contract_device(sxc_ctx* ctx, int grid, int basis_j, int nkern, const int* kernels, int mode, int nvec,
+                               const double* d_D, int accumulate) {
+  return kernel_contract_impl(ctx, grid, basis_j, nkern, kernels, mode, nvec, nullptr, d_D, accumulate, false);
 }
 
 int sxc_kernel_response_copy(sxc_ctx* ctx, int grid, int save) {
@@ -2038,8 +2057,10 @@ int sxc_kernel_response_copy(sxc_ctx* ctx, int grid, int save) {
   return SXC_OK;
 }
 
-int sxc_kernel_integrate(sxc_ctx* ctx, int grid, int basis_i, double* F) {
-  if (!ctx || !F) return fail(ctx, SXC_ERR_INVALID, "sxc_kernel_integrate: bad arguments");
+namespace {
+// F_host: result staged in ctx->dOut and copied back; else written to d_F (device), asynchronously
+int kernel_integrate_impl(sxc_ctx* ctx, int grid, int basis_i, double* F, double* d_F) {
+  if (!ctx || (!F && !d_F)) return fail(ctx, SXC_ERR_INVALID, "sxc_kernel_integrate: bad arguments");
   Grid* gp = get_grid(ctx, grid);
   Basis* bp = get_basis(ctx, basis_i);
   if (!gp || !bp) return fail(ctx, SXC_ERR_INVALID, "invalid grid (%d) or basis (%d) handle", grid, basis_i);
@@ -2055,13 +2076,17 @@ int sxc_kernel_integrate(sxc_ctx* ctx, int grid, int basis_i, double* F) {
   const long N = g.npts;
   const size_t nb2 = (size_t)b.nbf * b.nbf, nmat = (size_t)nvec * nspin;
   const size_t rows = (size_t)4 * nspin;
-  CU(ctx->dOut.ensure((nmat * nb2 + 2) * sizeof(double)));
-  begin_timing(ctx, true);
+  double* dF = d_F;
+  if (!dF) {
+    CU(ctx->dOut.ensure((nmat * nb2 + 2) * sizeof(double)));
+    dF = ctx->dOut.as<double>();
+  }
+  begin_timing(ctx, F != nullptr || ctx->timing_device);
   ctx->stats = p.stats;
   const int launches0 = ctx->launches;
   {
     PhaseTimer t_all(ctx, T_TOTAL);
-    CU(cudaMemsetAsync(ctx->dOut.p, 0, nmat * nb2 * sizeof(double), ctx->stream));
+    CU(cudaMemsetAsync(dF, 0, nmat * nb2 * sizeof(double), ctx->stream));
     TRY(run_screen(ctx, g, b, p));
     for (const Chunk& c : p.chunks) {
       if (c.nslots == 0) continue;
@@ -2070,16 +2095,28 @@ int sxc_kernel_integrate(sxc_ctx* ctx, int grid, int basis_i, double* F) {
       // weights already inside scal / grad ... which the contraction left out, so the scatter's w restores them
       for (size_t m = 0; m < nmat; ++m)
         TRY(phase_scatter(ctx, g, b, p, c, gga, 0.0, g.resp.as<double>() + (m / nspin) * rows * N + (m % nspin) * 4 * N,
-                          ctx->dOut.as<double>() + m * nb2));
+                          dF + m * nb2));
     }
-    for (size_t m = 0; m < nmat; ++m) TRY(finish_matrix(ctx, b.nbf, ctx->dOut.as<double>() + m * nb2));
+    for (size_t m = 0; m < nmat; ++m) TRY(finish_matrix(ctx, b.nbf, dF + m * nb2));
   }
   ctx->timing = false;
   ctx->stats.kernel_launches = ctx->launches - launches0;
-  CU(cudaMemcpyAsync(F, ctx->dOut.p, nmat * nb2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
-  collect_timers(ctx);
+  if (F) {
+    CU(cudaMemcpyAsync(F, dF, nmat * nb2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    collect_timers(ctx);
+  }
   return SXC_OK;
+}
+}  // namespace
+
+int sxc_kernel_integrate(sxc_ctx* ctx, int grid, int basis_i, double* F) {
+  if (!F) return fail(ctx, SXC_ERR_INVALID, "sxc_kernel_integrate: bad arguments");
+  return kernel_integrate_impl(ctx, grid, basis_i, F, nullptr);
+}
+int sxc_kernel_integrate_device(sxc_ctx* ctx, int grid, int basis_i, double* d_F) {
+  if (!d_F) return fail(ctx, SXC_ERR_INVALID, "sxc_kernel_integrate_device: bad arguments");
+  return kernel_integrate_impl(ctx, grid, basis_i, nullptr, d_F);
 }
 
 int sxc_kernel_sigma(sxc_ctx* ctx, int grid, int basis, int nkern, const int* kernels, int mode, int nvec, const double* D,

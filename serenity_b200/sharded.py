@@ -134,3 +134,57 @@ def cuda_local_build(ctx, grid: int, basis: int, func: int, block_ave_threshold:
         ctx.build_xc_device(grid, basis, func, d_P.data_ptr(), d_VEN.data_ptr(), block_ave_threshold)
 
     return run
+
+
+class ShardedSigma:
+    """LR-TDDFT kernel sigma build (row f-4) over the ranks of `group`: every rank holds the kernel store of its own grid
+    blocks, contracts / integrates all nvec trial vectors on them and the partial Fock-like matrices are summed by ONE
+    all_reduce of nvec * nspin * nb * nb doubles (KernelSigmavector.cpp:236-249 sums its per-thread matrices the same way).
+
+    local_sigma(d_D, d_F) must enqueue this rank's partial contraction + integration (CUDA: XCContext.kernel_sigma_device).
+    """
+
+    def __init__(self, nbf: int, nvec: int, local_sigma: Callable[[torch.Tensor, torch.Tensor], None], device,
+                 group: Optional[dist.ProcessGroup] = None, nspin: int = 1):
+        self.nbf, self.nvec, self.nspin = nbf, nvec, nspin
+        self._local = local_sigma
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.device = torch.device(device)
+        n = nvec * nspin * nbf * nbf
+        cuda = self.device.type == "cuda"
+        self.d_D = torch.zeros(n, dtype=torch.float64, device=self.device)
+        self.d_F = torch.zeros(n, dtype=torch.float64, device=self.device)
+        self.h_D = torch.zeros(n, dtype=torch.float64, pin_memory=cuda)
+        self.h_F = torch.zeros(n, dtype=torch.float64, pin_memory=cuda)
+
+    def sigma_device(self) -> torch.Tensor:
+        self._local(self.d_D, self.d_F)
+        if self.world > 1:
+            dist.all_reduce(self.d_F, op=dist.ReduceOp.SUM, group=self.group)
+        return self.d_F
+
+    def sigma(self, D):
+        """D: nvec (x nspin) matrices [nb, nb] -> list of nvec * nspin Fock-like matrices (host buffers in and out)."""
+        flat = np.concatenate([np.asarray(m, dtype=np.float64).reshape(-1, order="F") for m in D])
+        assert flat.size == self.h_D.numel()
+        self.h_D.numpy()[:] = flat
+        self.d_D.copy_(self.h_D, non_blocking=True)
+        self.sigma_device()
+        self.h_F.copy_(self.d_F, non_blocking=True)
+        if self.device.type == "cuda":
+            torch.cuda.current_stream(self.device).synchronize()
+        nb = self.nbf
+        out = self.h_F.numpy().reshape(self.nvec * self.nspin, nb * nb)
+        return [out[m].reshape(nb, nb, order="F").copy(order="F") for m in range(out.shape[0])]
+
+
+def cuda_local_sigma(ctx, grid: int, basis: int, kernels, nvec: int, mode: int = 0):
+    """local_sigma for ShardedSigma on a CUDA rank: sxc_kernel_contract_device + sxc_kernel_integrate_device on torch's
+    current stream."""
+
+    def run(d_D: torch.Tensor, d_F: torch.Tensor):
+        ctx.set_stream(torch.cuda.current_stream(d_D.device).cuda_stream or 1)
+        ctx.kernel_sigma_device(grid, basis, kernels, d_D.data_ptr(), d_F.data_ptr(), nvec, mode)
+
+    return run

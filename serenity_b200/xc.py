@@ -306,6 +306,13 @@ class XCContext:
         self._check(self._lib.sxc_kernel_contract(self._h, grid, basis_j, len(hk), _ptr(hk), mode, len(D), _ptr(buf),
                                                   1 if accumulate else 0))
 
+    def kernel_sigma_device(self, grid: int, basis: int, kernels, d_D_ptr: int, d_F_ptr: int, nvec: int, mode: int = 0):
+        """contract + integrate with device-resident D (nvec x nspin x nb^2) and F; asynchronous on the context's stream."""
+        hk = np.ascontiguousarray(kernels, dtype=np.int32)
+        self._check(self._lib.sxc_kernel_contract_device(self._h, grid, basis, len(hk), _ptr(hk), mode, nvec,
+                                                         C.c_void_p(d_D_ptr), 0))
+        self._check(self._lib.sxc_kernel_integrate_device(self._h, grid, basis, C.c_void_p(d_F_ptr)))
+
     def kernel_response_copy(self, grid: int, save: bool):
         """save: keep the current contracted response (the supersystem contraction); not save: restore it."""
         self._check(self._lib.sxc_kernel_response_copy(self._h, grid, 1 if save else 0))

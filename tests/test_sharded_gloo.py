@@ -59,3 +59,55 @@ def test_sharded_build_allreduce_gloo(tmp_path, world):
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
     r = np.load(out)
     assert r["dE"] < 1e-11 and r["dV"] < 1e-11 and r["dn"] < 1e-11 and r["sym"] < 1e-13
+
+
+def _sigma_worker(rank, world, port, out_path):
+    """row f-4: ShardedSigma - every rank contracts / integrates its block range, one all-reduce of the nvec matrices."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import pyoracle as orc
+        from serenity_b200.inputs import make_config
+        from serenity_b200.inputs.configs import FUNCTIONALS
+        from serenity_b200.sharded import ShardedSigma, shard_bounds
+        cfg = make_config("h2o", 2)
+        sub = cfg.subsystems[0]
+        func = orc.Functional(*FUNCTIONALS["PBE"])
+        nbf, nvec = sub.basis.nbf, 3
+        nblk = (cfg.npts + 127) // 128
+        bounds = shard_bounds(np.ones(nblk), world)
+        lo, hi = int(bounds[rank]) * 128, min(int(bounds[rank + 1]) * 128, cfg.npts)
+        ob = orc.Basis(sub.basis)
+
+        def sigma_on(grid, D):
+            rho, g, _, _ = orc.density_on_grid(ob, grid, 1e-9, sub.P, 1)
+            store = orc.kernel_store_r(func, rho, g)
+            return orc.kernel_integrate(ob, grid, orc.kernel_contract(ob, grid, store, D, 0, True), True)
+
+        def local_sigma(d_D, d_F):
+            mine = orc.Grid(cfg.xyz[lo:hi], cfg.w[lo:hi], 128)
+            for v in range(nvec):
+                D = d_D.numpy()[v * nbf * nbf:(v + 1) * nbf * nbf].reshape(nbf, nbf, order="F")
+                d_F[v * nbf * nbf:(v + 1) * nbf * nbf] = torch.from_numpy(sigma_on(mine, D).reshape(-1, order="F").copy())
+
+        ss = ShardedSigma(nbf, nvec, local_sigma, "cpu")
+        rng = np.random.default_rng(3)
+        D = [rng.standard_normal((nbf, nbf)) for _ in range(nvec)]
+        F = ss.sigma(D)
+        F2 = ss.sigma(D)  # reused buffers must not accumulate
+        assert all(np.abs(a - b).max() < 1e-12 for a, b in zip(F, F2))
+        if rank == 0:
+            full = orc.Grid(cfg.xyz, cfg.w, 128)
+            err = max(np.abs(F[v] - sigma_on(full, D[v])).max() / np.abs(F[v]).max() for v in range(nvec))
+            np.savez(out_path, err=err, sym=max(np.abs(f - f.T).max() for f in F))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_sigma_allreduce_gloo(tmp_path):
+    port = 29950 + os.getpid() % 300
+    out = str(tmp_path / "sig.npz")
+    mp.spawn(_sigma_worker, args=(2, port, out), nprocs=2, join=True)
+    r = np.load(out)
+    assert r["err"] < 1e-12 and r["sym"] < 1e-13
