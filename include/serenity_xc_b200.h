@@ -31,6 +31,7 @@ extern "C" {
 #endif
 
 typedef struct sxc_ctx sxc_ctx;
+typedef struct sxc_shell_table sxc_shell_table; /* host-side shell table built from a basis-set file (row f-2) */
 
 typedef enum {
   SXC_OK = 0,
@@ -261,6 +262,24 @@ int sxc_kernel_integrate_device(sxc_ctx* ctx, int grid, int basis_i, double* d_F
 /* calcF(I, I) for an isolated system: contract + integrate */
 int sxc_kernel_sigma(sxc_ctx* ctx, int grid, int basis, int nkern, const int* kernels, int mode, int nvec, const double* D,
                      double* F);
+
+/* ---- basis-set file front end (host only, no device needed) ---------------------------------- */
+/* BasisFunctionProvider::provideAtomWithBasisFunctions (src/basis/BasisFunctionProvider.cpp:32-140) for every atom of a
+ * geometry + the Shell constructor (src/basis/Shell.cpp:29-47: libint2-renormalised coefficients, Cartesian norm factors) +
+ * the extended indices of BasisController (src/basis/BasisController.cpp:62-68): parses the Turbomole-format file `path`
+ * (the reference's data/basis/<LABEL>) for the entry "<element> <basis_label>" of each atom; shells are atom-major in file
+ * order.  elements[natoms] = element symbols (any case), coords_bohr [natoms][3].  spherical = settings basis.makeSphericalBasis.
+ * $ecp sections are not read.  Errors: status < 0 and the reference's SerenityError wording in sxc_host_last_error(). */
+int sxc_shell_table_from_file(const char* path, const char* basis_label, int natoms, const char* const* elements,
+                              const double* coords_bohr, int spherical, sxc_shell_table** out);
+int sxc_shell_table_sizes(const sxc_shell_table* t, int* nshell, int* nprim_total, int* nbf);
+/* copies the arrays sxc_add_basis takes (any pointer may be NULL) and BasisController::getAtomIndicesOfBasis() [nbf] */
+int sxc_shell_table_copy(const sxc_shell_table* t, int* l, int* pure, int* nprim, int* first_bf, double* centre, double* alpha,
+                         double* coeff, double* normfac, int* atom_of_bf);
+void sxc_shell_table_free(sxc_shell_table* t);
+/* sxc_add_basis fed from the table */
+int sxc_add_basis_from_table(sxc_ctx* ctx, const sxc_shell_table* t, double radial_threshold, int* basis);
+const char* sxc_host_last_error(void);
 
 int sxc_get_stats(sxc_ctx* ctx, sxc_stats* out);
 /* host-only helper behind sxc_set_grid_shard: splits n blocks into `world` contiguous ranges of nearly equal summed

@@ -19,6 +19,8 @@ SYMBOLS = [
     "sxc_partition_weights", "sxc_last_partition_ms", "sxc_scalar_to_matrix_ab", "sxc_build_ab", "sxc_nadd_gradient",
     "sxc_kernel_create", "sxc_kernel_destroy", "sxc_kernel_add", "sxc_kernel_get", "sxc_kernel_num_arrays", "sxc_kernel_contract",
     "sxc_kernel_integrate", "sxc_kernel_sigma", "sxc_kernel_response_copy", "sxc_kernel_contract_device", "sxc_kernel_integrate_device",
+    "sxc_shell_table_from_file", "sxc_shell_table_sizes", "sxc_shell_table_copy", "sxc_shell_table_free", "sxc_add_basis_from_table",
+    "sxc_host_last_error",
 ]
 
 
@@ -97,6 +99,13 @@ def load():
     lib.sxc_kernel_response_copy.argtypes = [vp, i, i]
     lib.sxc_kernel_contract_device.argtypes = [vp, i, i, i, vp, i, i, vp, i]
     lib.sxc_kernel_integrate_device.argtypes = [vp, i, i, vp]
+    lib.sxc_shell_table_from_file.argtypes = [C.c_char_p, C.c_char_p, i, vp, vp, i, C.POINTER(vp)]
+    lib.sxc_shell_table_sizes.argtypes = [vp, ip, ip, ip]
+    lib.sxc_shell_table_copy.argtypes = [vp] + [vp] * 9
+    lib.sxc_shell_table_free.argtypes = [vp]
+    lib.sxc_shell_table_free.restype = None
+    lib.sxc_add_basis_from_table.argtypes = [vp, vp, d, ip]
+    lib.sxc_host_last_error.restype = C.c_char_p
     lib.sxc_kernel_sigma.argtypes = [vp, i, i, i, vp, i, i, vp, vp]
     _LIB = lib
     return lib

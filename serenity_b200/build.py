@@ -30,7 +30,8 @@ def build_cuda(force=False, verbose=False):
     if force or _newer(out, srcs):
         nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-ccbin", "/usr/bin/g++", "-o", out,
-                                                                              os.path.join(csrc, "sxc_api.cu")]
+                                                                              os.path.join(csrc, "sxc_api.cu"),
+                                                                              os.path.join(csrc, "basis_provider.cpp")]
         subprocess.check_call(cmd)
     return out
 

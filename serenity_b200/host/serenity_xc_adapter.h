@@ -124,6 +124,28 @@ class BasisController {
  public:
   BasisController(ShellTable t, int nBasisFunctions, double radialThreshold = 1e-9)
     : _t(std::move(t)), _nbf(nBasisFunctions), _thr(radialThreshold) {}
+  // AtomCenteredBasisController + BasisFunctionProvider (basis/BasisFunctionProvider.cpp:32-140): geometry + basis-set file
+  // of the reference's data/basis directory -> shells (row f-2, sxc_shell_table_from_file)
+  static std::shared_ptr<BasisController> fromFile(const std::string& path, const std::string& label,
+                                                   const std::vector<std::string>& elements, const std::vector<double>& coordsBohr,
+                                                   bool spherical = true, double radialThreshold = 1e-9) {
+    std::vector<const char*> names;
+    for (auto& e : elements) names.push_back(e.c_str());
+    sxc_shell_table* h = nullptr;
+    if (sxc_shell_table_from_file(path.c_str(), label.c_str(), (int)elements.size(), names.data(), coordsBohr.data(), spherical ? 1 : 0,
+                                  &h) != SXC_OK)
+      throw SerenityError(sxc_host_last_error());
+    int ns = 0, np = 0, nbf = 0;
+    sxc_shell_table_sizes(h, &ns, &np, &nbf);
+    ShellTable t;
+    t.l.resize(ns), t.pure.resize(ns), t.nprim.resize(ns), t.firstBf.resize(ns);
+    t.centre.resize(3 * (size_t)ns), t.alpha.resize(np), t.coeff.resize(np), t.normfac.resize(nbf), t.atomOfBf.resize(nbf);
+    sxc_shell_table_copy(h, t.l.data(), t.pure.data(), t.nprim.data(), t.firstBf.data(), t.centre.data(), t.alpha.data(),
+                         t.coeff.data(), t.normfac.data(), t.atomOfBf.data());
+    sxc_shell_table_free(h);
+    t.nAtoms = (int)elements.size();
+    return std::make_shared<BasisController>(std::move(t), nbf, radialThreshold);
+  }
   unsigned int getNBasisFunctions() const { return (unsigned int)_nbf; }
   const std::vector<int>& getAtomIndicesOfBasis() const { return _t.atomOfBf; }
   int getNAtoms() const { return _t.nAtoms; }

@@ -33,6 +33,31 @@ def _spin_unpack(buf):
     return tuple(np.asfortranarray(buf[s].reshape(nb, nb, order="F")) for s in range(2))
 
 
+def shell_table_from_file(path: str, basis_label: str, symbols, coords_bohr, spherical: bool = True):
+    """Row f-2 through the C ABI (sxc_shell_table_from_file): BasisFunctionProvider + Shell + extended indices of the
+    reference for a geometry and a Turbomole-format basis file.  Returns (ShellTable, atom_of_bf); host only."""
+    from .inputs.basis import ShellTable
+    lib = _lib.load()
+    coords = _f64(coords_bohr).reshape(-1, 3)
+    names = (C.c_char_p * len(symbols))(*[s.encode() for s in symbols])
+    h = C.c_void_p()
+    rc = lib.sxc_shell_table_from_file(path.encode(), basis_label.encode(), len(symbols), names, _ptr(coords), 1 if spherical else 0,
+                                       C.byref(h))
+    if rc != 0:
+        raise SerenityError(lib.sxc_host_last_error().decode())
+    try:
+        ns, npr, nbf = C.c_int(), C.c_int(), C.c_int()
+        lib.sxc_shell_table_sizes(h, C.byref(ns), C.byref(npr), C.byref(nbf))
+        ns, npr, nbf = ns.value, npr.value, nbf.value
+        li, pu, npm, fb = (np.zeros(ns, dtype=np.int32) for _ in range(4))
+        cen, al, co, nf, aob = np.zeros((ns, 3)), np.zeros(npr), np.zeros(npr), np.zeros(nbf), np.zeros(nbf, dtype=np.int32)
+        lib.sxc_shell_table_copy(h, _ptr(li), _ptr(pu), _ptr(npm), _ptr(fb), _ptr(cen), _ptr(al), _ptr(co), _ptr(nf), _ptr(aob))
+    finally:
+        lib.sxc_shell_table_free(h)
+    off = np.concatenate([[0], np.cumsum(npm)[:-1]]).astype(np.int32)
+    return ShellTable(li, pu, npm, off, fb, cen, al, co, nf, nbf), aob
+
+
 class XCContext:
     """One context per process and GPU (sxc_create)."""
 
