@@ -238,8 +238,9 @@ int sxc_kernel_get(sxc_ctx* ctx, int kernel, double* out);
 int sxc_kernel_num_arrays(sxc_ctx* ctx, int kernel);
 /* KernelSigmavector<SCFMode>::contractKernel + contractBlock (src/postHF/LRSCF/Sigmavectors/KernelSigmavector.cpp:254-311,
  * :360-497) for nvec trial vectors: D = nvec x nspin matrices nbf_J x nbf_J (column-major, back to back; symmetrised here
- * as calcF does, :201-208), contracted to rho~ / grad rho~ on the grid and multiplied with the sum of the nkern (1 or 2)
- * kernel stores = Kernel::getPP/PG/GG(I, J) (total-density store + subsystem store for I == J, Kernel.cpp:170-230).
+ * as calcF does, :201-208), contracted to rho~ / grad rho~ on the grid and multiplied with the sum of the nkern (1 to 3)
+ * kernel stores = Kernel::getPP/PG/GG(I, J) (total-density store + subsystem store for I == J + the _ppExact set of mixed
+ * exact/approximate embedding, Kernel.cpp:170-230).
  * mode 0: RESTRICTED singlet; 1: RESTRICTED triplet, stores are UNRESTRICTED ones (aa - ab, :381-404); 2: UNRESTRICTED.
  * The result stays on the device (per grid); accumulate != 0 adds to the previous one (the supersystem contraction over
  * all subsystems J, :96-117 and :214-226). */

@@ -310,19 +310,22 @@ k_kernel2_u(FuncView f, long npts, const int* __restrict__ lit_blocks, const dou
 // KernelSigmavector<SCFMode>::contractBlock (KernelSigmavector.cpp:360-497) on the owned blocks of a chunk.
 // dens: response density of one trial vector, rho~ = sum D_ij phi_i phi_j and its gradient, rows [4 * nspin][N]
 // (the reference forms p = 1/2 w rho~, g = w sum D_ij grad phi_i phi_j = 1/2 w grad rho~ for symmetric D, :287-301; the
-// weights are applied by the scatter that follows).  Up to two stores are summed on the fly (Kernel::getPP/getPG/getGG:
-// total-density store + subsystem store when I == J, Kernel.cpp:170-230).
+// weights are applied by the scatter that follows).  Up to three stores are summed on the fly (Kernel::getPP/getPG/getGG:
+// total-density store + subsystem store when I == J + the exactly-treated-systems store of mixed embedding, Kernel.cpp:170-230).
 // mode 0: RESTRICTED singlet (10-array stores); 1: RESTRICTED triplet from UNRESTRICTED stores (aa - ab, :381-404);
 // mode 2: UNRESTRICTED.  out rows like dens; accumulate != 0 adds (supersystem contraction, :214-226).
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 k_kernel_apply(long N, int blocksize, const int* __restrict__ block_id, int mode, int gga, const double* __restrict__ st0,
-               const double* __restrict__ st1, const double* __restrict__ dens, int accumulate, double* __restrict__ out) {
+               const double* __restrict__ st1, const double* __restrict__ st2, const double* __restrict__ dens, int accumulate,
+               double* __restrict__ out) {
   const long first = (long)block_id[blockIdx.x] * blocksize;
   const int n = (int)min((long)blocksize, N - first);
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const long p = first + i;
-    auto K = [&](int k) { return st0[(size_t)k * N + p] + (st1 ? st1[(size_t)k * N + p] : 0.0); };
+    auto K = [&](int k) {
+      return st0[(size_t)k * N + p] + (st1 ? st1[(size_t)k * N + p] : 0.0) + (st2 ? st2[(size_t)k * N + p] : 0.0);
+    };
     if (mode == 0 || mode == 1) {
       const double pr = 0.5 * dens[p];
       double g[3] = {0.0, 0.0, 0.0};

@@ -1938,14 +1938,14 @@ namespace {
 int kernel_contract_impl(sxc_ctx* ctx, int grid, int basis_j, int nkern, const int* kernels, int mode, int nvec,
                          const double* D_host, const double* D_dev, int accumulate, bool sync) {
   const double* D = D_host ? D_host : D_dev;
-  if (!ctx || !kernels || !D || nvec <= 0 || nkern < 1 || nkern > 2)
-    return fail(ctx, SXC_ERR_INVALID, "sxc_kernel_contract: bad arguments (1 or 2 kernel stores, nvec > 0)");
+  if (!ctx || !kernels || !D || nvec <= 0 || nkern < 1 || nkern > 3)
+    return fail(ctx, SXC_ERR_INVALID, "sxc_kernel_contract: bad arguments (1 to 3 kernel stores, nvec > 0)");
   if (mode < 0 || mode > 2) return fail(ctx, SXC_ERR_INVALID, "mode must be 0 (singlet), 1 (triplet) or 2 (UNRESTRICTED)");
   Grid* gp = get_grid(ctx, grid);
   Basis* bp = get_basis(ctx, basis_j);
   if (!gp || !bp) return fail(ctx, SXC_ERR_INVALID, "invalid grid (%d) or basis (%d) handle", grid, basis_j);
   const int store_nspin = mode == 0 ? 1 : 2, nspin = mode == 2 ? 2 : 1;
-  const double* st[2] = {nullptr, nullptr};
+  const double* st[3] = {nullptr, nullptr, nullptr};
   int gga = -1;
   for (int k = 0; k < nkern; ++k) {
     const int h = kernels[k];
@@ -2008,7 +2008,7 @@ int kernel_contract_impl(sxc_ctx* ctx, int grid, int basis_j, int nkern, const i
                             gga != 0, nullptr));
         PhaseTimer t(ctx, SXC_T_FUNCTIONAL);
         k_kernel_apply<<<c.nslots, 128, 0, ctx->stream>>>(N, g.blocksize, p.block_id.as<int>() + c.slot0, mode, gga, st[0], st[1],
-                                                          dens, 1, g.resp.as<double>() + (size_t)v * rows * N);
+                                                          st[2], dens, 1, g.resp.as<double>() + (size_t)v * rows * N);
         LAUNCH_CHECK();
       }
     }
