@@ -213,7 +213,7 @@ def run_b200(args):
         if world == 1 and args.gpus > 1:  # convenience: relaunch under torchrun
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                    "--master-addr", "127.0.0.1", "--master-port", "29511"] + sys.argv
-            return subprocess.call(cmd)
+            return subprocess.call(cmd, stdout=sys.stdout)  # (fd 1 of this process points at stderr, see main())
         raise SystemExit("--gpus %d does not match WORLD_SIZE %d" % (args.gpus, world))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the XC build has no CPU fallback (use --impl reference for the CPU arm)")
@@ -369,6 +369,13 @@ def run_b200(args):
 
 def main():
     args = parse_args()
+    # stdout carries exactly ONE line, the JSON: libraries that print from C (NCCL's version banner under NCCL_DEBUG=VERSION
+    # ignores NCCL_DEBUG_FILE on some builds) write to file descriptor 1, so fd 1 points at stderr while the run lasts and
+    # Python's sys.stdout keeps the real one
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)
