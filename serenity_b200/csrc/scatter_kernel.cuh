@@ -24,7 +24,8 @@
 namespace sxc {
 
 // ------------------------------------------------------------------------------------------------------------
-// K3b: per block: weights x potential, block-average test, G in place of d_x phi.  256 threads.
+// K3b: per block: weights x potential, block-average test, G into the fifth tile slot.  256 threads; gridDim.y CTAs share the
+// function rows of a block (a small shard would otherwise leave too few bytes in flight to fill HBM).
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_form_g(GridView g, PlanView plan, const int* __restrict__ order, double block_ave_thr, double a_scale,
@@ -58,14 +59,14 @@ k_form_g(GridView g, PlanView plan, const int* __restrict__ order, double block_
   const double total = block_sum(mag, scratch);
   const int s = plan.s[q];
   const bool skip = (total / (double)n < block_ave_thr) || s == 0;  // :262-268
-  if (tid == 0) skip_flag[q] = skip ? 1 : 0;
+  if (tid == 0 && blockIdx.y == 0) skip_flag[q] = skip ? 1 : 0;
   if (skip) return;
   const int sp = plan.s_pad[q];
   const size_t comp_stride = (size_t)sp * BP;
   double* __restrict__ tile = phi_buf + plan.phi_off[q];
   const int p = tid & (BP - 1);
   const double a = a_scale * sa[p], bx = sx[p], by = sy[p], bz = sz[p];  // a_scale = 1/2: the T + T^T trick of :281
-  for (int c = tid >> 7; c < sp; c += 2) {
+  for (int c = (tid >> 7) + 2 * blockIdx.y; c < sp; c += 2 * gridDim.y) {
     const size_t i = (size_t)c * BP + p;
     tile[4 * comp_stride + i] = bx * tile[comp_stride + i] + by * tile[2 * comp_stride + i] +
                                 bz * tile[3 * comp_stride + i] + a * tile[i];  // :276-281

@@ -700,13 +700,20 @@ int next_counter(sxc_ctx* ctx, int** out) {
   return SXC_OK;
 }
 
+// k_form_g is bandwidth-bound: aim at >= 8 resident CTAs per SM by letting up to 8 CTAs share a block's function rows
+dim3 form_g_grid(const sxc_ctx* ctx, int nslots) {
+  const int want = 8 * ctx->num_sms;
+  const int split = std::max(1, std::min(8, (want + std::max(nslots, 1) - 1) / std::max(nslots, 1)));
+  return dim3((unsigned)nslots, (unsigned)split);
+}
+
 int phase_scatter(sxc_ctx* ctx, const Grid& g, const Basis& b, const Plan& p, const Chunk& c, bool gga,
                   double block_ave_thr, const double* pot4, double* dW) {
   const long N = g.npts;
   if (c.nslots == 0) return SXC_OK;
   {
     PhaseTimer t(ctx, SXC_T_FORM_G);
-    k_form_g<<<c.nslots, 256, 0, ctx->stream>>>(g.view(), p.view(), p.order.as<int>() + c.order_off, block_ave_thr, 0.5,
+    k_form_g<<<form_g_grid(ctx, c.nslots), 256, 0, ctx->stream>>>(g.view(), p.view(), p.order.as<int>() + c.order_off, block_ave_thr, 0.5,
                                                 pot4, gga ? pot4 + N : nullptr, gga ? pot4 + 2 * N : nullptr,
                                                 gga ? pot4 + 3 * N : nullptr, ctx->phi.as<double>(), p.skip.as<int>());
     LAUNCH_CHECK();
@@ -732,11 +739,11 @@ int phase_scatter_ab(sxc_ctx* ctx, const Grid& g, const Basis& bA, const Plan& p
   if (cA.nslots == 0) return SXC_OK;
   {
     PhaseTimer t(ctx, SXC_T_FORM_G);  // G_A = grad_A (no scalar part), G_B = a phi_B + grad_B
-    k_form_g<<<cA.nslots, 256, 0, ctx->stream>>>(g.view(), pA.view(), pA.order.as<int>() + cA.order_off, block_ave_thr, 0.0,
+    k_form_g<<<form_g_grid(ctx, cA.nslots), 256, 0, ctx->stream>>>(g.view(), pA.view(), pA.order.as<int>() + cA.order_off, block_ave_thr, 0.0,
                                                  pot4, gga ? pot4 + N : nullptr, gga ? pot4 + 2 * N : nullptr,
                                                  gga ? pot4 + 3 * N : nullptr, ctx->phi.as<double>(), pA.skip.as<int>());
     LAUNCH_CHECK();
-    k_form_g<<<cB.nslots, 256, 0, ctx->stream>>>(g.view(), pB.view(), pB.order.as<int>() + cB.order_off, block_ave_thr, 1.0,
+    k_form_g<<<form_g_grid(ctx, cB.nslots), 256, 0, ctx->stream>>>(g.view(), pB.view(), pB.order.as<int>() + cB.order_off, block_ave_thr, 1.0,
                                                  pot4, gga ? pot4 + N : nullptr, gga ? pot4 + 2 * N : nullptr,
                                                  gga ? pot4 + 3 * N : nullptr, ctx->phi2.as<double>(), pB.skip.as<int>());
     LAUNCH_CHECK();
@@ -1021,7 +1028,7 @@ int build_gradient_device(sxc_ctx* ctx, int gh, int bh, int fh, int nspin, const
         const bool gga = f.gga != 0;
         {  // K = a phi + b . grad phi into slot 4 (no block-average test in the gradient: threshold 0)
           PhaseTimer t(ctx, SXC_T_FORM_G);
-          k_form_g<<<c.nslots, 256, 0, ctx->stream>>>(g.view(), p.view(), p.order.as<int>() + c.order_off, 0.0, 1.0, pot4,
+          k_form_g<<<form_g_grid(ctx, c.nslots), 256, 0, ctx->stream>>>(g.view(), p.view(), p.order.as<int>() + c.order_off, 0.0, 1.0, pot4,
                                                       gga ? pot4 + N : nullptr, gga ? pot4 + 2 * N : nullptr,
                                                       gga ? pot4 + 3 * N : nullptr, ctx->phi.as<double>(), p.skip.as<int>());
           LAUNCH_CHECK();
