@@ -178,6 +178,8 @@ struct sxc_ctx {
   DevMem phi;     // tile workspace (one chunk)
   DevMem phi2;    // second tile workspace: basis B of the two-basis scatter (row f-4)
   DevMem dP;      // staged density matrices (host API)
+  DevMem dD;      // symmetrised copy of device-resident trial densities (sxc_kernel_contract_device; never touched by the
+                  // side-stream uploads of the host entry points)
   DevMem dOut;    // staged V | E | N (host API)
   DevMem scratch; // small device scalars
   DevMem counters; // work-queue heads of the persistent kernels
@@ -1180,8 +1182,11 @@ void sxc_destroy(sxc_ctx* ctx) {
   ctx->plans.clear();
   ctx->grids.clear();
   ctx->bases.clear();
+  ctx->kstores.clear();
   ctx->phi.release();
+  ctx->phi2.release();
   ctx->dP.release();
+  ctx->dD.release();
   ctx->dOut.release();
   ctx->scratch.release();
   ctx->counters.release();
@@ -1984,12 +1989,14 @@ int kernel_contract_impl(sxc_ctx* ctx, int grid, int basis_j, int nkern, const i
     g.resp_nspin = nspin;
     g.resp_gga = gga;
   }
-  CU(ctx->dP.ensure((size_t)nvec * nspin * nb2 * sizeof(double)));
+  DevMem& stage = D_host ? ctx->dP : ctx->dD;
+  CU(stage.ensure((size_t)nvec * nspin * nb2 * sizeof(double)));
+  double* dDs = stage.as<double>();
   if (D_host) {
-    TRY(upload_async(ctx, ctx->dP.p, D_host, (size_t)nvec * nspin * nb2 * sizeof(double)));
+    TRY(upload_async(ctx, dDs, D_host, (size_t)nvec * nspin * nb2 * sizeof(double)));
     TRY(upload_done(ctx));
   } else {  // the caller's matrices are left untouched: D += D^T works on the staged copy
-    CU(cudaMemcpyAsync(ctx->dP.p, D_dev, (size_t)nvec * nspin * nb2 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dDs, D_dev, (size_t)nvec * nspin * nb2 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   }
   begin_timing(ctx, sync || ctx->timing_device);
   ctx->stats = p.stats;
@@ -2001,7 +2008,7 @@ int kernel_contract_impl(sxc_ctx* ctx, int grid, int basis_j, int nkern, const i
     {
       dim3 blk(32, 8), grd((b.nbf + 31) / 32, (b.nbf + 7) / 8);
       for (int m = 0; m < nvec * nspin; ++m) {
-        k_symmetrise<<<grd, blk, 0, ctx->stream>>>(b.nbf, ctx->dP.as<double>() + (size_t)m * nb2);
+        k_symmetrise<<<grd, blk, 0, ctx->stream>>>(b.nbf, dDs + (size_t)m * nb2);
         LAUNCH_CHECK();
       }
     }
@@ -2011,7 +2018,7 @@ int kernel_contract_impl(sxc_ctx* ctx, int grid, int basis_j, int nkern, const i
       TRY(phase_basis(ctx, g, b, p, c));
       for (int v = 0; v < nvec; ++v) {
         for (int sp = 0; sp < nspin; ++sp)
-          TRY(phase_density(ctx, g, b, p, c, ctx->dP.as<double>() + ((size_t)v * nspin + sp) * nb2, dens + (size_t)4 * sp * N,
+          TRY(phase_density(ctx, g, b, p, c, dDs + ((size_t)v * nspin + sp) * nb2, dens + (size_t)4 * sp * N,
                             gga != 0, nullptr));
         PhaseTimer t(ctx, SXC_T_FUNCTIONAL);
         k_kernel_apply<<<c.nslots, 128, 0, ctx->stream>>>(N, g.blocksize, p.block_id.as<int>() + c.slot0, mode, gga, st[0], st[1],
