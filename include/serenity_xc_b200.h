@@ -206,6 +206,12 @@ int sxc_scalar_to_matrix_ab(sxc_ctx* ctx, int grid, int basis_a, int basis_b, do
 int sxc_build_ab(sxc_ctx* ctx, int grid, int func, int nspin, int basis_a, int basis_b, int ndens, const int* basis_c,
                  const double* const* P_c, double block_ave_threshold, double* V_ab, double* E);
 
+/* ABNAddFuncPotential<SCFMode>::getMatrix (potentials/ABFockMatrixConstruction/ABNAddFuncPotential.cpp:66-176): the
+ * non-additive potential v[rho_act + sum_i rho_env_i] - v[rho_act] of the active system (basis_act, P_act) and the nenv
+ * environment densities, scattered into the nbf_A x nbf_B matrix (per spin: nspin of them back to back), overwritten. */
+int sxc_build_ab_nadd(sxc_ctx* ctx, int grid, int func, int nspin, int basis_a, int basis_b, int basis_act, const double* P_act,
+                      int nenv, const int* basis_env, const double* const* P_env, double block_ave_threshold, double* V_ab);
+
 /* ---- grid construction ---------------------------------------------------------------------- */
 /* The partition-weight step of GridFactory::produce (src/grid/construction/GridFactory.cpp:139-266), the O(N n_atoms^2)
  * part of the reference's grid set-up.  coords [natoms][3] (bohr); xyz 3 x npts interleaved = every atom's reference

@@ -185,6 +185,23 @@ def build_ab(basis_a: Basis, basis_b: Basis, densities, grid: Grid, func: Functi
     return V, e
 
 
+def build_ab_nadd(basis_a: Basis, basis_b: Basis, act, env, grid: Grid, func: Functional, radial_thr=1e-9, block_ave_thr=1e-11):
+    """ABNAddFuncPotential::getMatrix (ABNAddFuncPotential.cpp:66-176), RESTRICTED: act = (Basis, P), env = [(Basis, P), ...];
+    the potential v[rho_act + sum rho_env] - v[rho_act] (:150-170) scattered into the A x B matrix."""
+    gga = func.is_gga
+    ra, ga, _, _ = density_on_grid(act[0], grid, radial_thr, act[1], 1)
+    tot = [ra.copy()] + [x.copy() for x in ga]
+    for bc, P in env:
+        rho, g, _, _ = density_on_grid(bc, grid, radial_thr, P, 1)
+        tot[0] += rho
+        for k in range(3):
+            tot[1 + k] += g[k]
+    _, sup = functional_on_grid(func, grid.w, tot[0], *(tot[1:] if gga else (None,) * 3))
+    _, sub = functional_on_grid(func, grid.w, ra, *(ga if gga else (None,) * 3))
+    v = [sup[k] - sub[k] for k in range(1, 5 if gga else 2)]
+    return scalar_to_matrix_ab(basis_a, basis_b, grid, radial_thr, block_ave_thr, v[0], *(v[1:4] if gga else (None,) * 3))
+
+
 def build_xc(basis: Basis, grid: Grid, func: Functional, P, radial_thr=1e-9, block_ave_thr=1e-11):
     P = np.asfortranarray(P, dtype=np.float64)
     V = np.zeros((basis.nbf, basis.nbf), order="F")

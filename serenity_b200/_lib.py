@@ -16,7 +16,7 @@ SYMBOLS = [
     "sxc_set_grid_shard", "sxc_add_basis", "sxc_set_functional", "sxc_build_xc", "sxc_build_xc_device",
     "sxc_build_nadd", "sxc_build_nadd_device", "sxc_xc_gradient", "sxc_density_on_grid", "sxc_basis_on_grid",
     "sxc_functional_on_grid", "sxc_functional_on_grid_u", "sxc_scalar_to_matrix", "sxc_get_stats", "sxc_balance_ranges", "sxc_abi_version",
-    "sxc_partition_weights", "sxc_last_partition_ms", "sxc_scalar_to_matrix_ab", "sxc_build_ab", "sxc_nadd_gradient",
+    "sxc_partition_weights", "sxc_last_partition_ms", "sxc_scalar_to_matrix_ab", "sxc_build_ab", "sxc_build_ab_nadd", "sxc_nadd_gradient",
     "sxc_kernel_create", "sxc_kernel_destroy", "sxc_kernel_add", "sxc_kernel_get", "sxc_kernel_num_arrays", "sxc_kernel_contract",
     "sxc_kernel_integrate", "sxc_kernel_sigma", "sxc_kernel_response_copy", "sxc_kernel_contract_device", "sxc_kernel_integrate_device",
     "sxc_shell_table_from_file", "sxc_shell_table_sizes", "sxc_shell_table_copy", "sxc_shell_table_free", "sxc_add_basis_from_table",
@@ -88,6 +88,7 @@ def load():
     lib.sxc_nadd_gradient.argtypes = [vp, i, i, i, i, vp, i, vp, vp, i, vp, vp]
     lib.sxc_scalar_to_matrix_ab.argtypes = [vp, i, i, i, d, vp, vp, vp, vp, vp]
     lib.sxc_build_ab.argtypes = [vp, i, i, i, i, i, i, vp, vp, d, vp, vp]
+    lib.sxc_build_ab_nadd.argtypes = [vp, i, i, i, i, i, i, vp, i, vp, vp, d, vp]
     lib.sxc_last_partition_ms.restype = d
     lib.sxc_kernel_create.argtypes = [vp, i, i, i, ip]
     lib.sxc_kernel_destroy.argtypes = [vp, i]

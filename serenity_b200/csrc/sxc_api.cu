@@ -1130,6 +1130,82 @@ int build_ab_device(sxc_ctx* ctx, int gh, int fh, int nspin, int bA, int bB, int
   return SXC_OK;
 }
 
+// ABNAddFuncPotential<SCFMode>::getMatrix (potentials/ABFockMatrixConstruction/ABNAddFuncPotential.cpp:66-176): the
+// non-additive potential v[rho_act + sum rho_env] - v[rho_act] (:150-170) scattered into the nbf_A x nbf_B matrix.
+int build_ab_nadd_device(sxc_ctx* ctx, int gh, int fh, int nspin, int bA, int bB, int bAct, const double* dPact, int nenv,
+                         const int* bE, const double* const* dPE, double thr, double* dV) {
+  if (nspin != 1 && nspin != 2) return fail(ctx, SXC_ERR_INVALID, "nspin must be 1 (RESTRICTED) or 2 (UNRESTRICTED)");
+  if (fh < 0 || fh >= (int)ctx->funcs.size()) return fail(ctx, SXC_ERR_INVALID, "invalid functional handle %d", fh);
+  if (nenv < 0) return fail(ctx, SXC_ERR_INVALID, "nenv < 0");
+  Plan *pa = nullptr, *pb = nullptr, *pact = nullptr;
+  TRY(ab_plans(ctx, gh, bA, bB, &pa, &pb));
+  if (!get_basis(ctx, bAct)) return fail(ctx, SXC_ERR_INVALID, "invalid active basis handle %d", bAct);
+  TRY(get_plan(ctx, gh, bAct, &pact));
+  for (int i = 0; i < nenv; ++i) {
+    Plan* pe = nullptr;
+    if (!get_basis(ctx, bE[i])) return fail(ctx, SXC_ERR_INVALID, "invalid environment basis handle %d", bE[i]);
+    TRY(get_plan(ctx, gh, bE[i], &pe));
+  }
+  Grid& g = *get_grid(ctx, gh);
+  Basis& ba = *get_basis(ctx, bA);
+  Basis& bb = *get_basis(ctx, bB);
+  const FuncView f = ctx->funcs[fh];
+  TRY(ensure_point_arrays(ctx, g, true, nspin));
+  const long N = g.npts;
+  const int ncomp = 4 * nspin;
+  const size_t nab = (size_t)ba.nbf * bb.nbf;
+  double* parts = g.parts.as<double>();
+  double* dens = g.dens.as<double>();
+  double* tot = g.tot.as<double>();
+  double* pot = g.pot.as<double>();
+  ctx->stats = pa->stats;
+  begin_timing(ctx, true);
+  const int launches0 = ctx->launches;
+  {
+    PhaseTimer t_all(ctx, T_TOTAL);
+    CU(cudaMemsetAsync(dV, 0, nspin * nab * sizeof(double), ctx->stream));
+    CU(cudaMemsetAsync(parts, 0, (size_t)3 * std::max(g.nlit, 1) * sizeof(double), ctx->stream));
+    CU(cudaMemsetAsync(tot, 0, (size_t)ncomp * N * sizeof(double), ctx->stream));
+    g.env_valid = false;  // g.tot / g.dens are reused: the cache of sxc_build_nadd is gone
+    TRY(wait_p_ready(ctx));
+    // tot = sum of the environment densities (:73-104), then + rho_act; dens keeps rho_act (:107-147)
+    for (int i = 0; i <= nenv; ++i) {
+      const bool act = i == nenv;
+      const int bh = act ? bAct : bE[i];
+      const double* dP = act ? dPact : dPE[i];
+      Basis& bc = *get_basis(ctx, bh);
+      const size_t nc2 = (size_t)bc.nbf * bc.nbf;
+      Plan* pc = nullptr;
+      TRY(get_plan(ctx, gh, bh, &pc));
+      TRY(run_screen(ctx, g, bc, *pc));
+      for (const Chunk& c : pc->chunks) {
+        TRY(phase_basis(ctx, g, bc, *pc, c));
+        for (int sp = 0; sp < nspin; ++sp)
+          TRY(phase_density(ctx, g, bc, *pc, c, dP + sp * nc2, dens + (size_t)4 * sp * N, true, nullptr));
+        if (pc->nown) {
+          PhaseTimer t(ctx, SXC_T_DENSITY);
+          k_add4<<<c.nslots, 128, 0, ctx->stream>>>(N, g.blocksize, ncomp, pc->block_id.as<int>() + c.slot0, tot, dens, tot);
+          LAUNCH_CHECK();
+        }
+      }
+    }
+    if (f.ncomp > 0 && !pa->chunks.empty()) {
+      const Chunk& c0 = pa->chunks[0];
+      TRY(phase_functional(ctx, g, *pa, c0, f, nspin, tot, 1.0, 0, pot, parts, nullptr));
+      TRY(phase_functional(ctx, g, *pa, c0, f, nspin, dens, -1.0, 1, pot, parts + g.nlit, nullptr));
+      TRY(run_screen(ctx, g, ba, *pa));
+      TRY(run_screen(ctx, g, bb, *pb));
+      TRY(phase_basis(ctx, g, ba, *pa, c0));
+      TRY(phase_basis(ctx, g, bb, *pb, pb->chunks[0], &ctx->phi2));
+      for (int sp = 0; sp < nspin; ++sp)
+        TRY(phase_scatter_ab(ctx, g, ba, *pa, *pb, f.gga != 0, thr, pot + (size_t)4 * sp * N, dV + sp * nab));
+    }
+  }
+  ctx->timing = false;
+  ctx->stats.kernel_launches = ctx->launches - launches0;
+  return SXC_OK;
+}
+
 extern "C" {
 
 int sxc_abi_version(void) { return 5; }
@@ -1649,6 +1725,45 @@ int sxc_build_ab(sxc_ctx* ctx, int grid, int func, int nspin, int basis_a, int b
   if (rc != SXC_OK) return rc;
   CU(cudaMemcpyAsync(V_ab, ctx->dOut.p, nab * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(E, ctx->dOut.as<double>() + nab, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  collect_timers(ctx);
+  return SXC_OK;
+}
+
+int sxc_build_ab_nadd(sxc_ctx* ctx, int grid, int func, int nspin, int basis_a, int basis_b, int basis_act, const double* P_act,
+                      int nenv, const int* basis_env, const double* const* P_env, double thr, double* V_ab) {
+  if (!ctx || !V_ab || !P_act || nenv < 0 || (nenv > 0 && (!basis_env || !P_env)))
+    return fail(ctx, SXC_ERR_INVALID, "sxc_build_ab_nadd: bad arguments");
+  if (nspin != 1 && nspin != 2) return fail(ctx, SXC_ERR_INVALID, "nspin must be 1 or 2");
+  Basis* ba = get_basis(ctx, basis_a);
+  Basis* bb = get_basis(ctx, basis_b);
+  Basis* bact = get_basis(ctx, basis_act);
+  if (!ba || !bb || !bact) return fail(ctx, SXC_ERR_INVALID, "invalid basis handle (%d, %d, %d)", basis_a, basis_b, basis_act);
+  CU(cudaSetDevice(ctx->device));
+  const size_t nab = (size_t)nspin * ba->nbf * bb->nbf;
+  size_t total = (size_t)nspin * bact->nbf * bact->nbf;
+  std::vector<size_t> offs(nenv);
+  for (int i = 0; i < nenv; ++i) {
+    Basis* be = get_basis(ctx, basis_env[i]);
+    if (!be || !P_env[i]) return fail(ctx, SXC_ERR_INVALID, "invalid environment basis handle %d", basis_env[i]);
+    offs[i] = total;
+    total += (size_t)nspin * be->nbf * be->nbf;
+  }
+  CU(ctx->dP.ensure(total * sizeof(double)));
+  CU(ctx->dOut.ensure((nab + 2) * sizeof(double)));
+  TRY(upload_async(ctx, ctx->dP.p, P_act, (size_t)nspin * bact->nbf * bact->nbf * sizeof(double)));
+  std::vector<const double*> dpe(nenv);
+  for (int i = 0; i < nenv; ++i) {
+    Basis* be = get_basis(ctx, basis_env[i]);
+    dpe[i] = ctx->dP.as<double>() + offs[i];
+    TRY(upload_async(ctx, ctx->dP.as<double>() + offs[i], P_env[i], (size_t)nspin * be->nbf * be->nbf * sizeof(double)));
+  }
+  TRY(upload_done(ctx));
+  int rc = build_ab_nadd_device(ctx, grid, func, nspin, basis_a, basis_b, basis_act, ctx->dP.as<double>(), nenv, basis_env,
+                                dpe.data(), thr, ctx->dOut.as<double>());
+  ctx->timing = false;
+  if (rc != SXC_OK) return rc;
+  CU(cudaMemcpyAsync(V_ab, ctx->dOut.p, nab * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   collect_timers(ctx);
   return SXC_OK;

@@ -404,6 +404,55 @@ class ABFuncPotential : public ObjectSensitive {
   std::unique_ptr<Matrix> _abPotential;
 };
 
+// potentials/ABFockMatrixConstruction/ABNAddFuncPotential.h: the non-additive potential v[rho_act + sum rho_env] - v[rho_act]
+// between two different basis sets A and B (ABNAddFuncPotential.cpp:66-176).  The environment density on the grid is kept by
+// the reference until the object dies (:70-72); here the whole matrix is cached until notify().
+template<Options::SCF_MODES SCFMode>
+class ABNAddFuncPotential : public ObjectSensitive {
+ public:
+  ABNAddFuncPotential(std::shared_ptr<B200::XCDevice> device, std::shared_ptr<DensityMatrixController<SCFMode>> actDMat,
+                      std::shared_ptr<BasisController> basisA, std::shared_ptr<BasisController> basisB,
+                      std::vector<std::shared_ptr<DensityMatrixController<SCFMode>>> envDMats,
+                      std::shared_ptr<GridController> grid, Functional functional, double blockAveThreshold = 1e-11)
+    : _dev(std::move(device)), _act(std::move(actDMat)), _basisA(std::move(basisA)), _basisB(std::move(basisB)),
+      _env(std::move(envDMats)), _grid(std::move(grid)), _functional(std::move(functional)), _thr(blockAveThreshold),
+      _func(detail::functionalHandle(*_dev, _functional)) {}
+  void registerSensitivity(const std::shared_ptr<ABNAddFuncPotential>& self) {
+    _act->addSensitiveObject(self);
+    for (auto& d : _env) d->addSensitiveObject(self);
+    _grid->addSensitiveObject(self);
+  }
+  Matrix& getMatrix() {
+    if (!_abPotential) {
+      const int nA = (int)_basisA->getNBasisFunctions(), nB = (int)_basisB->getNBasisFunctions();
+      auto V = std::make_unique<Matrix>(nA, nB * detail::nspin<SCFMode>());
+      std::vector<int> be;
+      std::vector<const double*> pe;
+      for (auto& d : _env) {
+        be.push_back(d->getBasisController()->handle(*_dev));
+        pe.push_back(d->getDensityMatrix().data());
+      }
+      _dev->check(sxc_build_ab_nadd(_dev->get(), _grid->handle(*_dev), _func, detail::nspin<SCFMode>(), _basisA->handle(*_dev),
+                                    _basisB->handle(*_dev), _act->getBasisController()->handle(*_dev),
+                                    _act->getDensityMatrix().data(), (int)be.size(), be.data(), pe.data(), _thr, V->data()));
+      _abPotential = std::move(V);
+    }
+    return *_abPotential;
+  }
+  void notify() override final { _abPotential = nullptr; }
+
+ private:
+  std::shared_ptr<B200::XCDevice> _dev;
+  std::shared_ptr<DensityMatrixController<SCFMode>> _act;
+  std::shared_ptr<BasisController> _basisA, _basisB;
+  std::vector<std::shared_ptr<DensityMatrixController<SCFMode>>> _env;
+  std::shared_ptr<GridController> _grid;
+  Functional _functional;
+  double _thr;
+  int _func;
+  std::unique_ptr<Matrix> _abPotential;
+};
+
 // postHF/LRSCF/Kernel/Kernel.h:50-208: the second functional derivatives of the subsystem XC functionals
 // and of the non-additive XC / kinetic functionals on one grid.  Like the reference the object keeps a "total" set
 // (non-additive functionals on the summed density, _pptot/_pgtot/_ggtot) and one set per subsystem (func_I - naddXC - naddKin

@@ -276,6 +276,21 @@ class XCContext:
         out = [np.asfortranarray(V[s].reshape(nbf_a, nbf_b, order="F")) for s in range(nspin)]
         return (tuple(out) if nspin == 2 else out[0]), E[0], E[1]
 
+    def build_ab_nadd(self, grid, func, basis_a, basis_b, nbf_a, nbf_b, basis_act, P_act, basis_env, P_env,
+                      block_ave_threshold: float = 1e-11, nspin: int = 1):
+        """ABNAddFuncPotential::getMatrix (ABNAddFuncPotential.cpp:66-176): v[rho_act + sum rho_env] - v[rho_act] scattered into
+        the A x B matrix; nspin = 2: every P is a (P_alpha, P_beta) pair and (V_alpha, V_beta) is returned."""
+        pack = (lambda p: _spin_pack(p)) if nspin == 2 else (lambda p: np.asfortranarray(p, dtype=np.float64))
+        Pa = pack(P_act)
+        mats = [pack(p) for p in P_env]
+        V = np.zeros((nspin, nbf_a * nbf_b))
+        ptrs = (C.c_void_p * max(len(mats), 1))(*[m.ctypes.data for m in mats])
+        hb = np.ascontiguousarray(basis_env, dtype=np.int32)
+        self._check(self._lib.sxc_build_ab_nadd(self._h, grid, func, nspin, basis_a, basis_b, basis_act, _ptr(Pa), len(mats),
+                                                _ptr(hb), ptrs, block_ave_threshold, _ptr(V)))
+        out = [np.asfortranarray(V[s].reshape(nbf_a, nbf_b, order="F")) for s in range(nspin)]
+        return tuple(out) if nspin == 2 else out[0]
+
     def partition_weights(self, flavour: str, coords, xyz, parent, w, aij=None, smoothing: int = 3):
         """GridFactory.cpp:139-266 on the device: molecular partition weights (BECKE / SSF) of the atoms' reference
         grids.  xyz [N, 3] points (already shifted to their nuclei), parent [N] atom index, w [N] atomic weights;

@@ -115,6 +115,11 @@ int main(int argc, char** argv) {
     Matrix& Vab = abPot->getMatrix();
     if (&abPot->getMatrix() != &Vab) throw SerenityError("ABFuncPotential::getMatrix() must cache");
     wr(out, Vab.data(), (int64_t)nA * nB);
+    // the non-additive XC operator between the two basis sets (ABNAddFuncPotential.cpp:66-176)
+    auto abNadd = std::make_shared<ABNAddFuncPotential<R::RESTRICTED>>(
+        dev, dA, basisA, basisB, std::vector<std::shared_ptr<DensityMatrixController<R::RESTRICTED>>>{dB}, grid, xc);
+    abNadd->registerSensitivity(abNadd);
+    wr(out, abNadd->getMatrix().data(), (int64_t)nA * nB);
     // gradient of the non-additive XC potential over the active atoms (NAddFuncPotential.cpp:329-493)
     Matrix gradN = naddXC->getGeomGradients();
     wr(out, gradN.data(), (int64_t)gradN.rows() * 3);

@@ -129,3 +129,80 @@ def test_gpu_ab_rectangular_large():
     V, E, _ = ctx.build_ab(g, ctx.set_functional(ids, mix), ba, bb, sa.basis.nbf, tab_b.nbf, [ba], [sa.P])
     assert np.abs(V - V_ref).max() <= 1e-8 and abs(E - E_ref) <= 1e-9
     ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# ABNAddFuncPotential (potentials/ABFockMatrixConstruction/ABNAddFuncPotential.cpp:66-176): known answers of
+# ABNAddFuncPotential_test.cpp:86-151 - H2 (6-31G*, active FDE system, its SSF grid) against the basis of the environment H2,
+# LDA / BP86, one and two environment density matrices; tolerance of the reference 1e-5.
+ABN_LDA = [((0, 0), -0.0083840258804812658), ((1, 0), -0.055300758004326538), ((2, 0), -0.12831003302437624),
+           ((0, 1), -0.005639132369059649), ((0, 2), -0.0039221790739654878), ((0, 3), -0.0044904816299493342)]
+ABN_BP86 = [((0, 0), -0.0076542762861270645), ((1, 0), -0.055253744527196447), ((2, 0), -0.12698015387994177),
+            ((0, 1), -0.0047051305109973322), ((0, 2), -0.0037534727526342374), ((0, 3), -0.0038349418254594093)]
+ABN_BP86_2ENV = [((0, 0), -0.012352511055803322), ((1, 0), -0.080462987092342453), ((2, 0), -0.18794150046341079),
+                 ((0, 1), -0.0081584035257395351), ((0, 2), -0.0057641379450071991), ((0, 3), -0.0065285874827300102)]
+
+
+@pytest.fixture(scope="module")
+def h2_fde():
+    k = load_golden("h2_kats.json")["nadd_potential"]
+    st = k["settings"]
+    syms, xyz, tab_a = _system(k["basis_shells_H"], k["act"]["geometry_angstrom"], st["spherical"])
+    _, _, tab_b = _system(k["basis_shells_H"], k["env"]["geometry_angstrom"], st["spherical"])
+    gx, gw = _grid(syms, xyz, st)  # the active system's grid (ABNAddFuncPotential_test.cpp:65)
+    P = lambda s: np.asarray(k[s]["P_restricted"]).reshape(4, 4)  # noqa: E731
+    return tab_a, tab_b, gx, gw, P("act"), P("env")
+
+
+def test_oracle_abnadd_reference_kats(h2_fde):
+    from oracle import pyoracle as orc
+    tab_a, tab_b, gx, gw, Pa, Pe = h2_fde
+    ba, bb, og = orc.Basis(tab_a), orc.Basis(tab_b), orc.Grid(gx, gw, 128)
+    _check(orc.build_ab_nadd(ba, bb, (ba, Pa), [(bb, Pe)], og, orc.Functional(*LDA)), ABN_LDA, 1e-6)
+    _check(orc.build_ab_nadd(ba, bb, (ba, Pa), [(bb, Pe)], og, orc.Functional(*BP86)), ABN_BP86, 1e-6)
+    _check(orc.build_ab_nadd(ba, bb, (ba, Pa), [(bb, Pe), (bb, Pe)], og, orc.Functional(*BP86)), ABN_BP86_2ENV, 1e-6)
+    # A x A is NAddFuncPotential (:59-80, "accept only white noise")
+    V_aa = orc.build_ab_nadd(ba, ba, (ba, Pa), [(bb, Pe)], og, orc.Functional(*LDA))
+    V_n, _, _ = orc.build_nadd(ba, Pa, [(bb, Pe)], og, orc.Functional(*LDA))
+    assert np.abs(V_aa - V_n).max() < 1e-12
+
+
+@pytest.mark.gpu
+def test_gpu_abnadd_reference_kats(h2_fde):
+    from serenity_b200.xc import XCContext
+    tab_a, tab_b, gx, gw, Pa, Pe = h2_fde
+    ctx = XCContext(0)
+    g = ctx.set_grid(gx, gw, 128)
+    ba, bb = ctx.add_basis(tab_a, 1e-9), ctx.add_basis(tab_b, 1e-9)
+    fl, fb = ctx.set_functional(*LDA), ctx.set_functional(*BP86)
+    _check(ctx.build_ab_nadd(g, fl, ba, bb, 4, 4, ba, Pa, [bb], [Pe]), ABN_LDA, 1e-6)
+    _check(ctx.build_ab_nadd(g, fb, ba, bb, 4, 4, ba, Pa, [bb], [Pe]), ABN_BP86, 1e-6)
+    _check(ctx.build_ab_nadd(g, fb, ba, bb, 4, 4, ba, Pa, [bb, bb], [Pe, Pe]), ABN_BP86_2ENV, 1e-6)
+    V_aa = ctx.build_ab_nadd(g, fl, ba, ba, 4, 4, ba, Pa, [bb], [Pe])
+    V_n, _ = ctx.build_nadd(g, fl, ba, Pa, [bb], [Pe])
+    assert np.abs(V_aa - V_n).max() < 1e-12
+    # closed-shell consistency of the UNRESTRICTED build
+    Va, Vb = ctx.build_ab_nadd(g, fb, ba, bb, 4, 4, ba, (0.5 * Pa, 0.5 * Pa), [bb], [(0.5 * Pe, 0.5 * Pe)], nspin=2)
+    Vr = ctx.build_ab_nadd(g, fb, ba, bb, 4, 4, ba, Pa, [bb], [Pe])
+    assert np.abs(Va - Vr).max() < 1e-12 and np.abs(Vb - Vr).max() < 1e-12
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_abnadd_matches_oracle_on_the_water_dimer():
+    from oracle import pyoracle as orc
+    from serenity_b200.inputs import make_config
+    from serenity_b200.inputs.configs import FUNCTIONALS
+    from serenity_b200.xc import XCContext
+    cfg = make_config("fde_dimer", 2)
+    sa, sb = cfg.subsystems
+    oa, ob, og = orc.Basis(sa.basis), orc.Basis(sb.basis), orc.Grid(cfg.xyz, cfg.w, 128)
+    ctx = XCContext(0)
+    g = ctx.set_grid(cfg.xyz, cfg.w, 128)
+    ba, bb = ctx.add_basis(sa.basis, 1e-9), ctx.add_basis(sb.basis, 1e-9)
+    for name in ("PBE", "PW91K", "LDA"):
+        ids, mix = FUNCTIONALS[name]
+        V_ref = orc.build_ab_nadd(oa, ob, (oa, sa.P), [(ob, sb.P)], og, orc.Functional(ids, mix))
+        V = ctx.build_ab_nadd(g, ctx.set_functional(ids, mix), ba, bb, sa.basis.nbf, sb.basis.nbf, ba, sa.P, [bb], [sb.P])
+        assert np.abs(V - V_ref).max() <= 1e-8, (name, np.abs(V - V_ref).max())
+    ctx.close()

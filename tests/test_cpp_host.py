@@ -79,6 +79,7 @@ def test_cpp_potentials_match_oracle(tmp_path):
         got = [(_r(f, (nA, nA)), _r(f)) for _ in range(5)]
         grad = _r(f, (len(act.symbols), 3))
         Vab = _r(f, (nA, env.basis.nbf))
+        Vabn = _r(f, (nA, env.basis.nbf))
         gradN = _r(f, (len(act.symbols), 3))
         nB = env.basis.nbf
         F_fde, F_fde_B, F_iso0, F_iso1 = _r(f, (nA, nA)), _r(f, (nB, nB)), _r(f, (nA, nA)), _r(f, (nA, nA))
@@ -102,6 +103,8 @@ def test_cpp_potentials_match_oracle(tmp_path):
     assert np.abs(grad - grad_ref).max() <= 1e-9
     Vab_ref, _ = orc.build_ab(bA, bE, [(bA, PA2), (bE, env.P)], og, orc.Functional(*xc))
     assert np.abs(Vab - Vab_ref).max() <= 1e-8
+    Vabn_ref = orc.build_ab_nadd(bA, bE, (bA, PA2), [(bE, env.P)], og, orc.Functional(*xc))
+    assert np.abs(Vabn - Vabn_ref).max() <= 1e-8
     gradN_ref = orc.nadd_gradient(bA, PA2, [(bE, env.P)], og, orc.Functional(*xc), atom_indices_of_basis(act.basis, act.coords),
                                   len(act.symbols))
     assert np.abs(gradN - gradN_ref).max() <= 1e-9
