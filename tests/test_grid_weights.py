@@ -122,3 +122,28 @@ def test_gpu_grid_built_on_device_gives_the_same_xc_build():
     E = [ctx.build_xc(ctx.set_grid(x, ww, 128), b, f, sub.P)[1] for x, ww in ((cfg.xyz, cfg.w), (xyz, w))]
     assert abs(E[0] - E[1]) < 1e-12
     ctx.close()
+
+
+def test_atom_grid_factory_property_tests_of_the_reference():
+    """AtomGridFactory_test.cpp:46-75 (CheckRadialPointsByIntegration) and :80-99 (CheckSphericalPointsByIntegration) replayed on
+    the host restatement of the atom grids (serenity_b200/inputs/grid.py): the Ahlrichs radial rule integrates a Gaussian of
+    width c to 1/2 sqrt(2 pi) c within 1e-6 for every (c, nRad, alpha) of the reference's loops; the Lebedev rules of the
+    first 20 indices have unit-norm points and weights summing to 1 within 1e-8."""
+    import math
+    from serenity_b200.inputs.grid import _lebedev, ahlrichs_radial
+    c = 5.0
+    while c > 0.1:
+        n_rad = 3000
+        while n_rad <= 100000:
+            alpha = 0.8
+            while alpha <= 2.6:
+                r, w = ahlrichs_radial(alpha, n_rad)
+                integral = float(np.sum(np.exp(-(r[1:] ** 2) / (2 * c * c)) * w[1:] / r[1:] ** 2))
+                assert abs(integral - 0.5 * math.sqrt(2.0 * math.pi) * c) < 1e-6, (c, n_rad, alpha, integral)
+                alpha += 0.8
+            n_rad = int(n_rad * 6.37)
+        c *= 0.2
+    for index in range(20):
+        x, w = _lebedev(index)
+        assert x.shape[0] == w.shape[0]
+        assert np.abs(np.sum(x * x, axis=1) - 1.0).max() < 1e-8 and abs(w.sum() - 1.0) < 1e-8
