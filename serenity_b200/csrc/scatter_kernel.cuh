@@ -122,7 +122,9 @@ constexpr size_t smem_bytes_pipe() { return (size_t)PSTAGES * PSTAGE_ELEMS * siz
 // K loop of one round for a warp tile with MFR x NFR valid 8 x 8 fragments (4 x 4 except where the last, short row group of
 // a block is involved: rows beyond s rounded up to 8 are zero padding).  Compile-time fragment counts keep the DMMA stream
 // free of predicates (predicating the 4 x 4 loop nest cost 14 %).
-template <int MFR, int NFR>
+// DIAG: the tile sits on the diagonal of V_s (I == J); only the upper triangle is kept, so the 8 x 8 fragments strictly below
+// the diagonal (m > nn: 6 of 16) are not multiplied at all.
+template <int MFR, int NFR, bool DIAG = false>
 __device__ __forceinline__ void vmat_round(double (&acc)[4][4][2], const double* __restrict__ stage_base, uint64_t* full,
                                            uint64_t* empty, int& stage, int& pass, int slot_a, int slot_b, int kmask,
                                            bool active, int lane) {
@@ -147,7 +149,7 @@ __device__ __forceinline__ void vmat_round(double (&acc)[4][4][2], const double*
 #pragma unroll
           for (int m = 0; m < MFR; ++m)
 #pragma unroll
-            for (int nn = 0; nn < NFR; ++nn) dmma884(acc[m][nn][0], acc[m][nn][1], a[m], bq[nn]);
+            for (int nn = DIAG ? m : 0; nn < NFR; ++nn) dmma884(acc[m][nn][0], acc[m][nn][1], a[m], bq[nn]);
         }
       }
     }
@@ -239,7 +241,9 @@ k_vmat(PlanView plan, int nbf, const WorkItem* __restrict__ items, int nitems, i
         for (int m = 0; m < 4; ++m)
 #pragma unroll
           for (int nn = 0; nn < 4; ++nn) acc[m][nn][0] = acc[m][nn][1] = 0.0;
-        if (mfr == 4 || !active) {
+        if (active && slot_a == slot_b && mfr == 4) {  // full diagonal tile
+          vmat_round<4, 4, true>(acc, stage_base, full, empty, stage, pass, slot_a, slot_b, kmask, active, lane);
+        } else if (mfr == 4 || !active) {
           switch (active ? nfr : 4) {
             case 1: vmat_round<4, 1>(acc, stage_base, full, empty, stage, pass, slot_a, slot_b, kmask, active, lane); break;
             case 2: vmat_round<4, 2>(acc, stage_base, full, empty, stage, pass, slot_a, slot_b, kmask, active, lane); break;
@@ -248,9 +252,9 @@ k_vmat(PlanView plan, int nbf, const WorkItem* __restrict__ items, int nitems, i
           }
         } else {  // a short row group is the last one, so the tile is the last diagonal tile: nfr == mfr
           switch (mfr) {
-            case 1: vmat_round<1, 1>(acc, stage_base, full, empty, stage, pass, slot_a, slot_b, kmask, active, lane); break;
-            case 2: vmat_round<2, 2>(acc, stage_base, full, empty, stage, pass, slot_a, slot_b, kmask, active, lane); break;
-            default: vmat_round<3, 3>(acc, stage_base, full, empty, stage, pass, slot_a, slot_b, kmask, active, lane); break;
+            case 1: vmat_round<1, 1, true>(acc, stage_base, full, empty, stage, pass, slot_a, slot_b, kmask, active, lane); break;
+            case 2: vmat_round<2, 2, true>(acc, stage_base, full, empty, stage, pass, slot_a, slot_b, kmask, active, lane); break;
+            default: vmat_round<3, 3, true>(acc, stage_base, full, empty, stage, pass, slot_a, slot_b, kmask, active, lane); break;
           }
         }
         if (active) {
