@@ -288,6 +288,12 @@ def run_b200(args):
             acc[k] = acc.get(k, 0.0) + v
             nacc[k] = nacc.get(k, 0) + s["n_kernel"][k]
     ctx.set_timing(False)
+    # NOT the headline: the same build with sxc_set_tile_cache(1) - phi / grad phi tiles of the previous build kept in HBM
+    # (they depend on grid and basis only), so k_screen and k_basis run in the first build of an SCF only.  Reported next to
+    # the default (the reference's per-build recomputation), never instead of it.
+    ctx.set_tile_cache(True)
+    ms_cached, _, _ = timed(sb.build_device, max(3, args.steps // 2), 2)
+    ctx.set_tile_cache(False)
     per_build_ms = {k: v / reps for k, v in acc.items()}
     top = max(per_build_ms, key=per_build_ms.get)
     n_top = max(1, nacc[top] // reps)
@@ -343,6 +349,9 @@ def run_b200(args):
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "s_per_build": ms_dev * 1e-3,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
+                "with_tile_cache": {"ms_per_step": ms_cached, "value": cfg.npts / (ms_cached * 1e-3), "unit": UNIT,
+                                    "note": "optional sxc_set_tile_cache(1): basis-function tiles resident across SCF iterations; "
+                                            "not used for value / e2e / roofline"},
                 "config": config_dict(cfg, world, {
                     "l2": "no flush: one build streams %.2f GB of phi/grad-phi tiles (>> 126 MB L2) between uses of any "
                           "input" % (tile_bytes / 1e9),

@@ -101,6 +101,13 @@ const char* sxc_last_error(const sxc_ctx* ctx);
 int sxc_set_stream(sxc_ctx* ctx, void* cuda_stream);
 /* cap of the phi/grad-phi tile buffer in bytes (default: 40 % of free device memory at plan time) */
 int sxc_set_workspace_limit(sxc_ctx* ctx, int64_t bytes);
+/* Keep the phi / grad phi tiles resident between builds (off by default).  The reference re-evaluates the basis functions on
+ * the grid twice per build (MatrixOperatorToGridTransformer.cpp:103, ScalarOperatorToMatrixAdder.cpp:69-70) because host memory
+ * cannot hold them; they depend on grid and basis only, which are fixed during an SCF, and a B200 holds them (tetracene 3.7 GB,
+ * peptide 25 GB of 180 GB).  With the cache on, sxc_build_xc / sxc_build_nadd skip the screening and basis kernels whenever the
+ * workspace still holds the tiles of the same (grid, basis) pair from the previous call (single-chunk plans; any build with
+ * another basis, or a new grid / shard, refills the workspace).  Results are bit-identical to the uncached build. */
+int sxc_set_tile_cache(sxc_ctx* ctx, int on);
 /* One-shot: the next *_device build waits for this cudaEvent_t (passed as void*) before it first reads P - i.e. after
  * the screening and basis kernels - so that the caller's asynchronous upload of P on another stream overlaps with them.
  * (The host-buffer entry points do the same internally.) */

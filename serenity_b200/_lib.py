@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libserenity_xc_b200.so")
 
 # every symbol include/serenity_xc_b200.h declares
 SYMBOLS = [
-    "sxc_create", "sxc_destroy", "sxc_last_error", "sxc_set_stream", "sxc_set_workspace_limit", "sxc_set_timing", "sxc_set_p_ready_event", "sxc_set_grid",
+    "sxc_create", "sxc_destroy", "sxc_last_error", "sxc_set_stream", "sxc_set_workspace_limit", "sxc_set_tile_cache", "sxc_set_timing", "sxc_set_p_ready_event", "sxc_set_grid",
     "sxc_set_grid_shard", "sxc_add_basis", "sxc_set_functional", "sxc_build_xc", "sxc_build_xc_device",
     "sxc_build_nadd", "sxc_build_nadd_device", "sxc_xc_gradient", "sxc_density_on_grid", "sxc_basis_on_grid",
     "sxc_functional_on_grid", "sxc_functional_on_grid_u", "sxc_scalar_to_matrix", "sxc_get_stats", "sxc_balance_ranges", "sxc_abi_version",
@@ -66,6 +66,7 @@ def load():
     lib.sxc_set_stream.argtypes = [vp, vp]
     lib.sxc_set_workspace_limit.argtypes = [vp, i64]
     lib.sxc_set_timing.argtypes = [vp, i]
+    lib.sxc_set_tile_cache.argtypes = [vp, i]
     lib.sxc_set_p_ready_event.argtypes = [vp, vp]
     lib.sxc_set_grid.argtypes = [vp, i64, vp, vp, i, ip]
     lib.sxc_set_grid_shard.argtypes = [vp, i, i, i]

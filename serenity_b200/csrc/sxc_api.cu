@@ -129,6 +129,7 @@ struct Chunk {
 };
 
 struct Plan {
+  long serial = 0;  // unique per context: identifies whose tiles sit in the workspace (sxc_set_tile_cache)
   int grid = -1, basis = -1;
   int nown = 0;
   int nbf_pad = 0;
@@ -187,6 +188,11 @@ struct sxc_ctx {
   int counter_next = NCOUNTERS;
   int num_sms = 148;
   int64_t ws_limit = 0;
+  // sxc_set_tile_cache: the phi / grad phi tiles of a single-chunk plan stay valid in the workspace across builds (grid and
+  // basis are fixed during an SCF; 180 GB of HBM make the reference's recomputation unnecessary)
+  bool tile_cache = false;
+  long phi_owner = 0;    // serial of the plan whose tiles ctx->phi holds (0: none)
+  long plan_serial = 0;
   float last_partition_ms = 0.f;  // device time of the last k_partition_weights launch
   sxc_stats stats{};
   int launches = 0;
@@ -478,6 +484,7 @@ int get_plan(sxc_ctx* ctx, int gh, int bh, Plan** out, int comps = TILE_COMPS) {
   // 2. screening of the owned blocks
   auto plan = std::make_unique<Plan>();
   Plan& p = *plan;
+  p.serial = ++ctx->plan_serial;
   p.grid = gh;
   p.basis = bh;
   std::vector<int> ids(g->own_count);
@@ -636,8 +643,13 @@ int ensure_point_arrays(sxc_ctx* ctx, Grid& g, bool nadd, int nspin) {
 }
 
 // phases of one chunk ------------------------------------------------------------------------------------------
+bool tiles_cached(const sxc_ctx* ctx, const Plan& p) {
+  return ctx->tile_cache && p.chunks.size() == 1 && p.serial != 0 && ctx->phi_owner == p.serial;
+}
+
 int phase_basis(sxc_ctx* ctx, const Grid& g, const Basis& b, const Plan& p, const Chunk& c, DevMem* buf = nullptr) {
   DevMem& phi = buf ? *buf : ctx->phi;
+  if (!buf) ctx->phi_owner = p.chunks.size() == 1 ? p.serial : 0;
   CU(phi.ensure(c.doubles * sizeof(double)));
   PhaseTimer t(ctx, SXC_T_BASIS);
   k_basis<<<c.nslots, BASIS_GROUPS * BP, 0, ctx->stream>>>(g.view(), b.view(), p.view(), c.slot0,
@@ -811,10 +823,12 @@ int build_xc_device(sxc_ctx* ctx, int gh, int bh, int fh, int nspin, const doubl
     PhaseTimer t_all(ctx, T_TOTAL);
     CU(cudaMemsetAsync(dVEN, 0, (nspin * nb2 + 2) * sizeof(double), ctx->stream));
     CU(cudaMemsetAsync(parts, 0, (size_t)3 * std::max(g.nlit, 1) * sizeof(double), ctx->stream));
-    // the screening is part of every build in the reference (calculateBasisFunctionData :211-255)
-    TRY(run_screen(ctx, g, b, p));
+    // the screening is part of every build in the reference (calculateBasisFunctionData :211-255); with sxc_set_tile_cache the
+    // tiles (and the screening lists they were made with) of the previous build of the same plan are reused
+    const bool cached = tiles_cached(ctx, p);
+    if (!cached) TRY(run_screen(ctx, g, b, p));
     for (const Chunk& c : p.chunks) {
-      TRY(phase_basis(ctx, g, b, p, c));
+      if (!cached) TRY(phase_basis(ctx, g, b, p, c));
       TRY(wait_p_ready(ctx));
       // UNRESTRICTED: the same block data is contracted with P_alpha and P_beta (MatrixOperatorToGridTransformer.h:128-146)
       for (int sp = 0; sp < nspin; ++sp)
@@ -922,9 +936,10 @@ int build_nadd_device(sxc_ctx* ctx, int gh, int fh, int nspin, int bA, const dou
     // active system: rho_A, rho_tot = rho_A + sum_env, v = v[rho_tot] - v[rho_A]  (NAddFuncPotential.cpp:197-225)
     Plan& p = *pa;
     CU(cudaMemsetAsync(parts, 0, (size_t)3 * std::max(g.nlit, 1) * sizeof(double), ctx->stream));
-    TRY(run_screen(ctx, g, *ba, p));
+    const bool cached = tiles_cached(ctx, p);  // (frozen environment: the active system's tiles survive from call to call)
+    if (!cached) TRY(run_screen(ctx, g, *ba, p));
     for (const Chunk& c : p.chunks) {
-      TRY(phase_basis(ctx, g, *ba, p, c));
+      if (!cached) TRY(phase_basis(ctx, g, *ba, p, c));
       for (int sp = 0; sp < nspin; ++sp)
         TRY(phase_density(ctx, g, *ba, p, c, dPA + sp * nb2, dens + (size_t)4 * sp * N, true, nullptr));
       if (p.nown) {
@@ -1516,6 +1531,7 @@ int sxc_basis_on_grid(sxc_ctx* ctx, int grid, int basis, int block, double* val,
   for (const Chunk& c : p.chunks)
     if (q >= c.slot0 && q < c.slot0 + c.nslots) ch = &c;
   TRY(run_screen(ctx, g, b, p));
+  ctx->phi_owner = 0;  // the single block is evaluated into the workspace: cached tiles are gone
   CU(ctx->phi.ensure(ch->doubles * sizeof(double)));
   k_basis<<<1, BASIS_GROUPS * BP, 0, ctx->stream>>>(g.view(), b.view(), p.view(), q, nullptr, ctx->phi.as<double>());
   LAUNCH_CHECK();
@@ -1772,6 +1788,13 @@ int sxc_build_ab_nadd(sxc_ctx* ctx, int grid, int func, int nspin, int basis_a, 
 int sxc_set_p_ready_event(sxc_ctx* ctx, void* cuda_event) {
   if (!ctx) return SXC_ERR_INVALID;
   ctx->p_ready = static_cast<cudaEvent_t>(cuda_event);
+  return SXC_OK;
+}
+
+int sxc_set_tile_cache(sxc_ctx* ctx, int on) {
+  if (!ctx) return SXC_ERR_INVALID;
+  ctx->tile_cache = on != 0;
+  if (!on) ctx->phi_owner = 0;
   return SXC_OK;
 }
 

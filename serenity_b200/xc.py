@@ -96,6 +96,10 @@ class XCContext:
     def set_p_ready_event(self, cuda_event_ptr: int):
         self._check(self._lib.sxc_set_p_ready_event(self._h, C.c_void_p(cuda_event_ptr)))
 
+    def set_tile_cache(self, on: bool):
+        """phi / grad phi tiles stay resident between builds of the same (grid, basis) pair (sxc_set_tile_cache)."""
+        self._check(self._lib.sxc_set_tile_cache(self._h, 1 if on else 0))
+
     def set_timing(self, on: bool):
         self._check(self._lib.sxc_set_timing(self._h, 1 if on else 0))
 

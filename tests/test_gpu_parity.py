@@ -397,3 +397,45 @@ def test_nadd_unrestricted_dimer_matches_oracle(ctx, orc):
         assert np.allclose(E, parts, rtol=0, atol=E_TOL) and abs((E[0] - E[1] - E[2]) - E_ref) <= E_TOL
         (Va2, Vb2), E2 = ctx.build_nadd(g, f, bA, PA, [bE], [PE], env_frozen=True, nspin=2)
         assert np.abs(Va2 - Va).max() < 1e-12 and np.abs(E2 - E).max() < 1e-12
+
+
+def test_tile_cache_reproduces_uncached_builds_and_is_invalidated_by_other_work(ctx, orc):
+    """sxc_set_tile_cache: the second and later builds of the same (grid, basis) skip k_screen / k_basis and must reproduce
+    the uncached result (E_xc and N_el bit for bit - their sums are ordered; V to the 1e-13 of its FP64 red.global
+    accumulation order) for RESTRICTED, UNRESTRICTED and NAdd builds; a build with another basis in between refills the
+    workspace, so the next cached-mode build re-evaluates its own tiles."""
+    cfg = _cfg("fde_dimer")
+    act, env = cfg.subsystems
+    g = ctx.set_grid(cfg.xyz, cfg.w, 128)
+    bA, bE = ctx.add_basis(act.basis, 1e-9), ctx.add_basis(env.basis, 1e-9)
+    f = ctx.set_functional(*_functional("PBE"))
+    V0, E0, n0 = ctx.build_xc(g, bA, f, act.P)
+    launches_full = ctx.stats()["kernel_launches"]
+    Vu0, Eu0, _ = ctx.build_xc(g, bA, f, (0.6 * act.P, 0.4 * act.P), nspin=2)
+    Vn0, En0 = ctx.build_nadd(g, f, bA, act.P, [bE], [env.P])
+    ctx.set_tile_cache(True)
+    same = lambda a, b: np.abs(a - b).max() <= 1e-13  # noqa: E731
+    try:
+        V1, E1, n1 = ctx.build_xc(g, bA, f, act.P)            # fills the cache
+        V2, E2, n2 = ctx.build_xc(g, bA, f, act.P)            # served from it
+        assert ctx.stats()["kernel_launches"] == launches_full - 2   # no k_screen, no k_basis
+        assert same(V1, V0) and same(V2, V0) and E1 == E0 == E2 and n2 == n0
+        P2 = act.P * 1.03
+        Vp, Ep, _ = ctx.build_xc(g, bA, f, P2)
+        ctx.set_tile_cache(False)
+        Vq, Eq, _ = ctx.build_xc(g, bA, f, P2)
+        ctx.set_tile_cache(True)
+        assert same(Vp, Vq) and Ep == Eq
+        Vu, Eu, _ = ctx.build_xc(g, bA, f, (0.6 * act.P, 0.4 * act.P), nspin=2)
+        assert same(Vu[0], Vu0[0]) and same(Vu[1], Vu0[1]) and Eu == Eu0
+        # another basis takes the workspace; the active system's next build must not trust stale tiles
+        Ve, Ee, _ = ctx.build_xc(g, bE, f, env.P)
+        V3, E3, _ = ctx.build_xc(g, bA, f, act.P)
+        assert ctx.stats()["kernel_launches"] == launches_full
+        assert same(V3, V0) and E3 == E0
+        # freeze-and-thaw: frozen environment, the active tiles stay valid from call to call
+        Vn1, En1 = ctx.build_nadd(g, f, bA, act.P, [bE], [env.P], env_frozen=True)
+        Vn2, En2 = ctx.build_nadd(g, f, bA, act.P, [bE], [env.P], env_frozen=True)
+        assert same(Vn1, Vn0) and same(Vn2, Vn0) and np.array_equal(En1, En0) and np.array_equal(En2, En0)
+    finally:
+        ctx.set_tile_cache(False)
