@@ -70,8 +70,9 @@ struct Grid {
   DevMem tot;      // supersystem density        [4][N]   (NAdd)
   DevMem envsum;   // sum of environment densities [4][N] (NAdd, cached while frozen)
   DevMem parts;    // e_part, n_part, e_part2 [3][nlit]
-  std::vector<int> env_key;       // basis handles the cached envsum belongs to
-  std::vector<double> env_energy; // cached E[rho_env_i] (this rank's partial sums)
+  std::vector<int> env_key;       // basis handles (+ nspin) the cached envsum belongs to
+  std::map<int, std::vector<double>> env_energy;  // cached E[rho_env_i] per functional handle (this rank's partial sums): the
+                                                  // XC and the kinetic NAdd objects of one FDE iteration alternate
   bool env_valid = false;
   DevMem resp;     // row f-4: contracted kernel x response density, [nvec][4 * nspin][N]
   DevMem resp_saved;  // copy kept by sxc_kernel_response_copy (the supersystem contraction, reused for every subsystem I)
@@ -893,13 +894,17 @@ int build_nadd_device(sxc_ctx* ctx, int gh, int fh, int nspin, int bA, const dou
     TRY(wait_p_ready(ctx));
 
     // environment: rho_env on the supersystem grid, summed; E[rho_env_i] (NAddEnergyHelper, NAddFuncPotential.cpp:502-516)
+    // (the summed density does not depend on the functional, the environment energies do: a functional seen for the first time
+    // with a frozen environment repeats the pass once, afterwards both of an iteration's NAdd objects are served from the cache)
     std::vector<int> key(bE, bE + nenv);
-    key.push_back(fh);
     key.push_back(nspin);
-    const bool reuse = frozen && g.env_valid && g.env_key == key;
+    const bool same_env = frozen && g.env_valid && g.env_key == key;
+    const bool reuse = same_env && g.env_energy.count(fh) != 0;
+    if (!same_env) g.env_energy.clear();
     if (!reuse) {
       CU(cudaMemsetAsync(g.envsum.p, 0, (size_t)ncomp * N * sizeof(double), ctx->stream));
-      g.env_energy.assign(nenv, 0.0);
+      std::vector<double>& env_e = g.env_energy[fh];
+      env_e.assign(nenv, 0.0);
       for (int i = 0; i < nenv; ++i) {
         Basis* be = get_basis(ctx, bE[i]);
         const size_t ne2 = (size_t)be->nbf * be->nbf;
@@ -923,14 +928,14 @@ int build_nadd_device(sxc_ctx* ctx, int gh, int fh, int nspin, int bA, const dou
         TRY(reduce_to(ctx, parts, g.nlit, ctx->scratch.as<double>() + i));
       }
       if (nenv > 0) {
-        CU(cudaMemcpyAsync(g.env_energy.data(), ctx->scratch.p, nenv * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(env_e.data(), ctx->scratch.p, nenv * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
       }
       g.env_key = key;
       g.env_valid = true;
     }
     if (nenv > 0)
-      CU(cudaMemcpyAsync(dVE + nspin * nb2 + 2, g.env_energy.data(), nenv * sizeof(double), cudaMemcpyHostToDevice,
+      CU(cudaMemcpyAsync(dVE + nspin * nb2 + 2, g.env_energy[fh].data(), nenv * sizeof(double), cudaMemcpyHostToDevice,
                          ctx->stream));
 
     // active system: rho_A, rho_tot = rho_A + sum_env, v = v[rho_tot] - v[rho_A]  (NAddFuncPotential.cpp:197-225)

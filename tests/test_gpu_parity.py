@@ -439,3 +439,24 @@ def test_tile_cache_reproduces_uncached_builds_and_is_invalidated_by_other_work(
         assert same(Vn1, Vn0) and same(Vn2, Vn0) and np.array_equal(En1, En0) and np.array_equal(En2, En0)
     finally:
         ctx.set_tile_cache(False)
+
+
+def test_nadd_frozen_environment_cache_serves_alternating_functionals(ctx, orc):
+    """One freeze-and-thaw iteration calls the XC and the kinetic NAddFuncPotential in turn (FDEPotentials.cpp:43-61): the frozen
+    environment's summed density is shared, its energies are cached per functional - both objects must keep returning their own
+    E[rho_env] and the same V as an uncached call."""
+    cfg = _cfg("fde_dimer")
+    act, env = cfg.subsystems
+    g = ctx.set_grid(cfg.xyz, cfg.w, 128)
+    bA, bE = ctx.add_basis(act.basis, 1e-9), ctx.add_basis(env.basis, 1e-9)
+    fx, fk = ctx.set_functional(*_functional("PBE")), ctx.set_functional(*_functional("PW91K"))
+    ref = {f: ctx.build_nadd(g, f, bA, act.P, [bE], [env.P], env_frozen=False) for f in (fx, fk)}
+    assert abs(ref[fx][1][2] - ref[fk][1][2]) > 1e-3       # E_xc[rho_env] and T_s[rho_env] differ
+    for _ in range(3):
+        for f in (fx, fk):
+            V, E = ctx.build_nadd(g, f, bA, act.P, [bE], [env.P], env_frozen=True)
+            assert np.array_equal(E, ref[f][1]) and np.abs(V - ref[f][0]).max() <= 1e-13
+    launches = ctx.stats()["kernel_launches"]
+    V, E = ctx.build_nadd(g, fx, bA, act.P, [bE], [env.P], env_frozen=False)
+    assert ctx.stats()["kernel_launches"] > launches        # an unfrozen call recomputes the environment
+    assert np.array_equal(E, ref[fx][1])
