@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Builds profiles/r01_scaling.md from the bench lines tools/scaling_run.sh left in gpurun_out/ (bench_r1_<workload>_n<N>.json)
-and copies those lines to profiles/r01_bench_<workload>_n<N>.json.  usage: python tools/scaling_table.py [round_tag]"""
+and copies those lines to profiles/r01_scale_<workload>_n<N>.json.  usage: python tools/scaling_table.py [round_tag]"""
 import glob
 import json
 import os
@@ -18,7 +18,7 @@ for path in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "bench_r1_*_n*.jso
         continue
     d = json.loads(line)
     rows.setdefault(m.group(1), {})[int(m.group(2))] = d
-    shutil.copy(path, os.path.join(ROOT, "profiles", "%s_bench_%s_n%s.json" % (tag, m.group(1), m.group(2))))
+    shutil.copy(path, os.path.join(ROOT, "profiles", "%s_scale_%s_n%s.json" % (tag, m.group(1), m.group(2))))
 out = ["# Round 1 - strong scaling on one 8 x B200 box (gpurun --gpus 8, tools/scaling_run.sh; table by tools/scaling_table.py)", "",
        "Grid blocks of ONE molecule sharded over N ranks (contiguous cost-balanced ranges), one NCCL all-reduce of [V|E|N] per build.",
        "`device` = P resident, V left in HBM (kernels + all-reduce); `e2e` = pinned host P -> H2D -> build -> all-reduce -> D2H.", "",
