@@ -450,3 +450,56 @@ def test_gpu_sigma_shards_sum_to_full_and_device_entry_points():
         c2.close()
     assert all(_rel(t, c) <= 1e-12 for t, c in zip(tot, F))
     ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_sigma_edge_cases_empty_blocks_odd_blocksize_and_chunked_workspace():
+    """The reference's edge cases for this path: blocks without any significant function (far points: zero density, kernel
+    screened to zero, no contribution), a block size other than 128 (settings grid.blocksize; the functional still runs on
+    literal 128-point blocks, XCFun.cpp:129-131), and a workspace too small for one chunk (tiles evaluated chunk by chunk)."""
+    from oracle import pyoracle as orc
+    from serenity_b200.inputs import make_config
+    from serenity_b200.inputs.configs import FUNCTIONALS
+    from serenity_b200.xc import XCContext
+    ids, mix = FUNCTIONALS["PBE"]
+    func = orc.Functional(ids, mix)
+    # (a) far points + blocksize 100
+    cfg = make_config("h2o", 2)
+    sub = cfg.subsystems[0]
+    far = np.tile(np.array([[200.0, 150.0, -300.0]]), (256, 1)) + np.random.default_rng(1).uniform(-1, 1, (256, 3))
+    xyz = np.ascontiguousarray(np.concatenate([cfg.xyz[:1000], far, cfg.xyz[1000:]]))
+    w = np.concatenate([cfg.w[:1000], np.full(256, 0.01), cfg.w[1000:]])
+    D = [_trial(sub.basis.nbf, 61), _trial(sub.basis.nbf, 62)]
+    for blocksize in (128, 100):
+        ob, og = orc.Basis(sub.basis), orc.Grid(xyz, w, blocksize)
+        st_ref = _oracle_store_r(orc, ob, og, func, sub.P, True)
+        ctx = XCContext(0)
+        g = ctx.set_grid(xyz, w, blocksize)
+        b = ctx.add_basis(sub.basis, 1e-9)
+        k = ctx.kernel_create(g, 1, True)
+        ctx.kernel_add(k, ctx.set_functional(ids, mix), [b], [sub.P])
+        st = ctx.kernel_get(k, len(w))
+        assert np.all(st[:, 1000:1256] == 0.0)
+        F = ctx.kernel_sigma(g, b, sub.basis.nbf, [k], D, 0)
+        for v in range(2):
+            assert _rel(F[v], _oracle_sigma(orc, ob, og, st_ref, D[v], 0, True, 0.0)) <= TOL_EXACT, blocksize
+        ctx.close()
+    # (b) (H2O)8 with a 48 MB workspace: several chunks
+    cfg = make_config("water8", 2)
+    sub = cfg.subsystems[0]
+    nb = sub.basis.nbf
+    D = [_trial(nb, 71, 0.1)]
+    res = []
+    for limit in (0, 48 << 20):
+        ctx = XCContext(0)
+        if limit:
+            ctx.set_workspace_limit(limit)
+        g = ctx.set_grid(cfg.xyz, cfg.w, 128)
+        b = ctx.add_basis(sub.basis, 1e-9)
+        k = ctx.kernel_create(g, 1, True)
+        ctx.kernel_add(k, ctx.set_functional(ids, mix), [b], [sub.P])
+        res.append(ctx.kernel_sigma(g, b, nb, [k], D, 0)[0])
+        nchunks = ctx.stats()["nchunks"]
+        assert (nchunks > 1) == bool(limit), nchunks
+        ctx.close()
+    assert _rel(res[1], res[0]) <= 1e-12
