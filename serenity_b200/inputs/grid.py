@@ -6,8 +6,9 @@ weights and block structure:
     pruned Lebedev shells (zones :170-190); Lebedev rules come from scipy.integrate.lebedev_rule
     (the reference ships Burkardt's table, sphere_lebedev_rule.cpp - same rules, different point order)
   * src/grid/construction/GridFactory.cpp:52-321        SSF / Becke partition weights, weight cut 1e-14
-  * src/grid/HilbertRTreeSorting.cpp:46-214             locality sort (here: 3-D Hilbert index, 10 bits/axis;
-    same purpose, curve orientation differs from the reference's lookup tables)
+  * src/grid/HilbertRTreeSorting.cpp:46-214             locality sort: `hilbert_rtree_order` restates the reference's curve and
+    order exactly (sort="reference"; pinned by its 2x2x2 test); the default of the synthetic configs is a plain 3-D Hilbert
+    index with 10 bits per axis (same purpose, different orientation)
 Blocks are runs of `blocksize` consecutive points of the returned order.
 """
 from __future__ import annotations
@@ -138,6 +139,44 @@ def hilbert_index(ipts: np.ndarray, bits: int = 10) -> np.ndarray:
     return idx
 
 
+# lookup tables of the reference's Hilbert sort (src/grid/HilbertRTreeSorting.cpp:57-78): cube transformation to the next
+# level of depth, and the number of a point inside the first cube from its relation to the centre
+_HRT_TRANS = np.array([[0, 7, 6, 1, 2, 5, 4, 3], [0, 3, 4, 6, 7, 5, 2, 1], [0, 3, 4, 6, 7, 5, 2, 1], [2, 3, 0, 1, 6, 7, 4, 5],
+                       [2, 3, 0, 1, 6, 7, 4, 5], [6, 5, 2, 1, 0, 3, 4, 7], [6, 5, 2, 1, 0, 3, 4, 7], [4, 3, 2, 5, 6, 1, 0, 7]])
+_HRT_VAL = np.array([[[5, 6], [4, 7]], [[2, 1], [3, 0]]])
+
+
+def hilbert_rtree_order(xyz: np.ndarray) -> np.ndarray:
+    """The permutation HilbertRTreeSorting::sort applies (src/grid/HilbertRTreeSorting.cpp:29-214): depth from the number of
+    points (:32-39), integer coordinates (pt - min) * length / extent truncated (:83-86), the index from the two lookup tables
+    (:88-108), points moved in DESCENDING index order (:134-140 take the maximum first, the merge :171-181 keeps the larger
+    one).  Ties keep their input order (what the reference does with one sorting node; with several nodes its order of
+    equal indices depends on the thread count)."""
+    xyz = np.asarray(xyz, dtype=np.float64).reshape(-1, 3)
+    n = xyz.shape[0]
+    depth, length, nvert = 1, 2, 8
+    while n * 8 > nvert:
+        depth, length, nvert = depth + 1, length * 2, nvert * 8
+    if depth > 20:
+        raise ValueError("grid too large for a 63-bit Hilbert index")
+    lo = xyz.min(axis=0)
+    spread = float(length) / (xyz.max(axis=0) - lo)
+    pt = ((xyz - lo) * spread).astype(np.int64)  # C++ int(): truncation
+    l = length // 2
+    g = pt > l
+    v = _HRT_VAL[g[:, 0].astype(int), g[:, 1].astype(int), g[:, 2].astype(int)]
+    idx = v.astype(np.int64)
+    while l > 1:
+        idx *= 8
+        pt = pt - g * l
+        l //= 2
+        g = pt > l
+        x = _HRT_VAL[g[:, 0].astype(int), g[:, 1].astype(int), g[:, 2].astype(int)]
+        v = _HRT_TRANS[v, x]
+        idx += v
+    return np.argsort(-idx, kind="stable")
+
+
 def becke_size_adjustments(zs):
     """a(j + nAtoms * i) of GridFactory.cpp:95-113 (Bragg-Slater radii), as a [nat, nat] C-contiguous array."""
     from .geometry import ANGSTROM_TO_BOHR
@@ -207,7 +246,10 @@ def molecular_grid(symbols, coords_bohr, acc: int = 4, flavour: str = "SSF", rad
         w = host_partition_weights(flavour, zs, coords, xyz, w0, parent, smoothing)
     keep = w > weight_threshold  # GridFactory.cpp:264
     xyz, w = xyz[keep], w[keep]
-    if sort:
+    if sort == "reference":  # the reference's own curve and order (HilbertRTreeSorting.cpp)
+        order = hilbert_rtree_order(xyz)
+        xyz, w = xyz[order], w[order]
+    elif sort:
         lo = xyz.min(axis=0)
         span = np.maximum(xyz.max(axis=0) - lo, 1e-300)
         ip = np.minimum(((xyz - lo) / span * 1024.0).astype(np.int64), 1023)

@@ -147,3 +147,26 @@ def test_atom_grid_factory_property_tests_of_the_reference():
         x, w = _lebedev(index)
         assert x.shape[0] == w.shape[0]
         assert np.abs(np.sum(x * x, axis=1) - 1.0).max() < 1e-8 and abs(w.sum() - 1.0) < 1e-8
+
+
+def test_hilbert_rtree_sort_known_answer_of_the_reference():
+    """HilbertRTreeSorting_test.cpp:32-54 (2x2x2): eight cube corners with weights 0..7 come out in the order 3 7 1 4 6 2 5 0."""
+    from serenity_b200.inputs.grid import hilbert_rtree_order, molecular_grid
+    # Eigen's comma initialiser fills the 3 x 8 matrix row by row: all x, then all y, then all z
+    x = [+0.5, -0.5, +0.5, -0.5, -0.5, +0.5, +0.5, -0.5]
+    y = [+0.5, -0.5, -0.5, +0.5, +0.5, -0.5, +0.5, -0.5]
+    z = [+0.5, -0.5, -0.5, +0.5, -0.5, +0.5, -0.5, +0.5]
+    xyz = np.stack([x, y, z], axis=1)
+    order = hilbert_rtree_order(xyz)
+    assert list(order) == [3, 7, 1, 4, 6, 2, 5, 0]
+    px = [-0.5, -0.5, -0.5, -0.5, +0.5, +0.5, +0.5, +0.5]
+    py = [+0.5, -0.5, -0.5, +0.5, +0.5, -0.5, -0.5, +0.5]
+    pz = [+0.5, +0.5, -0.5, -0.5, -0.5, -0.5, +0.5, +0.5]
+    assert np.array_equal(xyz[order], np.stack([px, py, pz], axis=1))
+    # the sort is a permutation that keeps neighbours together: on a molecular grid consecutive points are close
+    gx, gw = molecular_grid(["O", "H", "H"], np.array([[0.0, 0.0, 0.2], [0.0, 1.4, -0.9], [0.0, -1.4, -0.9]]), 2, sort="reference")
+    gu, wu = molecular_grid(["O", "H", "H"], np.array([[0.0, 0.0, 0.2], [0.0, 1.4, -0.9], [0.0, -1.4, -0.9]]), 2, sort=False)
+    assert gx.shape == gu.shape and abs(gw.sum() - wu.sum()) < 1e-12 * abs(wu.sum())
+    step_sorted = np.linalg.norm(np.diff(gx, axis=0), axis=1).mean()
+    step_unsorted = np.linalg.norm(np.diff(gu, axis=0), axis=1).mean()
+    assert step_sorted < 0.5 * step_unsorted
