@@ -268,6 +268,77 @@ class FuncPotential : public Potential<SCFMode>, public ObjectSensitive {
   double _nElectronsOnGrid = 0.0;
 };
 
+// ---- stage-level classes (one level below the potentials; RESTRICTED) --------------------------------------------------
+// data/grid/DensityOnGridCalculator.h:45-103: rho (and grad rho) of a density matrix on the grid
+struct DensityOnGrid {  // data/grid/DensityOnGrid.h + math/Derivatives.h Gradient<>
+  std::vector<double> rho, x, y, z;
+};
+class DensityOnGridCalculator {
+ public:
+  DensityOnGridCalculator(std::shared_ptr<B200::XCDevice> device, std::shared_ptr<BasisController> basis,
+                          std::shared_ptr<GridController> grid)
+    : _dev(std::move(device)), _basis(std::move(basis)), _grid(std::move(grid)) {}
+  // calcDensityAndGradientOnGrid (DensityOnGridCalculator.cpp:55-65)
+  DensityOnGrid calcDensityAndGradientOnGrid(const DensityMatrix& P) {
+    const size_t n = _grid->getNGridPoints();
+    DensityOnGrid d{std::vector<double>(n), std::vector<double>(n), std::vector<double>(n), std::vector<double>(n)};
+    _dev->check(sxc_density_on_grid(_dev->get(), _grid->handle(*_dev), _basis->handle(*_dev), P.data(), d.rho.data(), d.x.data(),
+                                    d.y.data(), d.z.data()));
+    return d;
+  }
+
+ private:
+  std::shared_ptr<B200::XCDevice> _dev;
+  std::shared_ptr<BasisController> _basis;
+  std::shared_ptr<GridController> _grid;
+};
+
+// dft/functionals/wrappers/XCFun.h / FunctionalLibrary.h: calcData(GRADIENTS, functional, density, order 1)
+struct FunctionalData {  // dft/functionals/FunctionalData: epuv, dFdRho, dFdGradRho, energy
+  std::vector<double> epuv, dFdRho, dFdGradRhoX, dFdGradRhoY, dFdGradRhoZ;
+  double energy = 0.0;
+};
+class FunctionalLibrary {
+ public:
+  FunctionalLibrary(std::shared_ptr<B200::XCDevice> device, std::shared_ptr<GridController> grid)
+    : _dev(std::move(device)), _grid(std::move(grid)) {}
+  FunctionalData calcData(const Functional& functional, const DensityOnGrid& d) {
+    const size_t n = _grid->getNGridPoints();
+    if (d.rho.size() != n) throw SerenityError("FunctionalLibrary: density and grid do not match");
+    FunctionalData f;
+    f.epuv.resize(n), f.dFdRho.resize(n), f.dFdGradRhoX.resize(n), f.dFdGradRhoY.resize(n), f.dFdGradRhoZ.resize(n);
+    _dev->check(sxc_functional_on_grid(_dev->get(), detail::functionalHandle(*_dev, functional), (int64_t)n,
+                                       _grid->getWeights().data(), d.rho.data(), d.x.data(), d.y.data(), d.z.data(), f.epuv.data(),
+                                       f.dFdRho.data(), f.dFdGradRhoX.data(), f.dFdGradRhoY.data(), f.dFdGradRhoZ.data(), &f.energy));
+    return f;
+  }
+
+ private:
+  std::shared_ptr<B200::XCDevice> _dev;
+  std::shared_ptr<GridController> _grid;
+};
+
+// data/grid/ScalarOperatorToMatrixAdder.h:44-135: adds <mu| v + g . nabla |nu> (symmetrised, :262-303) to a matrix
+class ScalarOperatorToMatrixAdder {
+ public:
+  ScalarOperatorToMatrixAdder(std::shared_ptr<B200::XCDevice> device, std::shared_ptr<BasisController> basis,
+                              std::shared_ptr<GridController> grid, double blockAveThreshold = 1e-11)
+    : _dev(std::move(device)), _basis(std::move(basis)), _grid(std::move(grid)), _thr(blockAveThreshold) {}
+  // addScalarOperatorToMatrix(matrix, scalarPart, gradientPart) (ScalarOperatorToMatrixAdder.cpp:97-116); LDA: pass empty vectors
+  void addScalarOperatorToMatrix(Matrix& m, const std::vector<double>& scalar, const std::vector<double>& gx = {},
+                                 const std::vector<double>& gy = {}, const std::vector<double>& gz = {}) {
+    const bool gga = !gx.empty();
+    _dev->check(sxc_scalar_to_matrix(_dev->get(), _grid->handle(*_dev), _basis->handle(*_dev), _thr, scalar.data(),
+                                     gga ? gx.data() : nullptr, gga ? gy.data() : nullptr, gga ? gz.data() : nullptr, m.data()));
+  }
+
+ private:
+  std::shared_ptr<B200::XCDevice> _dev;
+  std::shared_ptr<BasisController> _basis;
+  std::shared_ptr<GridController> _grid;
+  double _thr;
+};
+
 // potentials/NAddFuncPotential.h:118-155 (first constructor; exact-exchange and solvation parts are ERI work and stay
 // with the reference's ExchangeInteractionPotential).
 template<Options::SCF_MODES SCFMode>

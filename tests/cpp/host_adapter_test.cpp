@@ -145,6 +145,18 @@ int main(int argc, char** argv) {
       std::vector<double> pp = iso->getPP(0, 0, 128, 256);
       wr(out, pp.data(), 128);
     }
+    // stage-level classes: density on the grid -> functional data -> grid to matrix reproduce FuncPotential::getMatrix
+    {
+      DensityOnGridCalculator dens(dev, basisA, grid);
+      DensityOnGrid d = dens.calcDensityAndGradientOnGrid(PA2);
+      FunctionalLibrary flib(dev, grid);
+      FunctionalData fd = flib.calcData(xc, d);
+      ScalarOperatorToMatrixAdder adder(dev, basisA, grid);
+      Matrix Vst(nA, nA);
+      adder.addScalarOperatorToMatrix(Vst, fd.dFdRho, fd.dFdGradRhoX, fd.dFdGradRhoY, fd.dFdGradRhoZ);
+      wr(out, Vst.data(), (int64_t)nA * nA);
+      wr(out, &fd.energy, 1);
+    }
     // error convention: SerenityError, as the reference throws (here: a functional id the library does not implement)
     bool threw = false;
     try {

@@ -84,6 +84,7 @@ def test_cpp_potentials_match_oracle(tmp_path):
         nB = env.basis.nbf
         F_fde, F_fde_B, F_iso0, F_iso1 = _r(f, (nA, nA)), _r(f, (nB, nB)), _r(f, (nA, nA)), _r(f, (nA, nA))
         pp_block = _r(f, (128,))
+        V_stage, E_stage = _r(f, (nA, nA)), _r(f)
     og = orc.Grid(cfg.xyz, cfg.w, 128)
     bA, bE = orc.Basis(act.basis), orc.Basis(env.basis)
 
@@ -134,3 +135,5 @@ def test_cpp_potentials_match_oracle(tmp_path):
         F_ref = orc.kernel_integrate(bA, og, orc.kernel_contract(bA, og, iso, D, 0, True, block_ave_thr=0.0), True, block_ave_thr=0.0)
         assert np.abs(F - F_ref).max() <= 1e-10 * np.abs(F_ref).max()
     assert np.abs(pp_block - iso[0, 256:384]).max() <= 1e-6 * np.abs(iso[0, 256:384]).max()
+    # DensityOnGridCalculator -> FunctionalLibrary -> ScalarOperatorToMatrixAdder stand-ins = FuncPotential of the same density
+    assert np.abs(V_stage - want[3][0]).max() <= 1e-8 and abs(E_stage - want[3][1]) <= 1e-9
