@@ -93,6 +93,8 @@ def oracle_sample(cfg, target_s=4.0):
 
 def time_oracle(cfg, ids, mix, steps, warmup, target_s=4.0):
     orc, sub, pick, probe_k = oracle_sample(cfg)
+    # all host cores of this process (torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must not inherit that)
+    orc.set_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     ob, of = orc.Basis(sub.basis), orc.Functional(ids, mix)
     xyz, w = pick(probe_k)
     t0 = time.perf_counter()
