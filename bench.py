@@ -91,14 +91,17 @@ def oracle_sample(cfg, target_s=4.0):
     return orc, sub, pick, probe_k
 
 
-def time_oracle(cfg, ids, mix, steps, warmup, target_s=4.0):
+def time_oracle(cfg, ids, mix, steps, warmup, target_s=4.0, P=None):
+    """P: density matrix to use instead of the config's (timing does not depend on it); with a full-grid sample the last
+    build's (V, E, N_el) come back under 'result' so that the caller can state parity."""
     orc, sub, pick, probe_k = oracle_sample(cfg)
+    P = sub.P if P is None else P
     # all host cores of this process (torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must not inherit that)
     orc.set_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     ob, of = orc.Basis(sub.basis), orc.Functional(ids, mix)
     xyz, w = pick(probe_k)
     t0 = time.perf_counter()
-    orc.build_xc(ob, orc.Grid(xyz, w, 128), of, sub.P)
+    orc.build_xc(ob, orc.Grid(xyz, w, 128), of, P)
     t_probe = time.perf_counter() - t0
     k = 1
     while t_probe * probe_k / k > target_s and k < 64:
@@ -106,18 +109,19 @@ def time_oracle(cfg, ids, mix, steps, warmup, target_s=4.0):
     xyz, w = pick(k)
     og = orc.Grid(xyz, w, 128)
     for _ in range(warmup):
-        orc.build_xc(ob, og, of, sub.P)
-    times, phases = [], None
+        orc.build_xc(ob, og, of, P)
+    times, phases, last = [], None, None
     for _ in range(steps):
         t0 = time.perf_counter()
-        _, _, _, tm = orc.build_xc(ob, og, of, sub.P)
+        Vo, Eo, No, tm = orc.build_xc(ob, og, of, P)
+        last = (Vo, Eo, No) if k == 1 else None
         times.append(time.perf_counter() - t0)
         phases = tm
     t = sum(times) / len(times)
     sample = ("%d of %d grid points (every %s128-point block of the workload), full XC build per step, "
               "%d steps" % (len(w), cfg.npts, "" if k == 1 else "%d-th " % k, steps))
     return {"value": len(w) / t, "unit": UNIT, "cores": orc.max_threads(), "kind": "port", "sample": sample,
-            "s_per_build_sample": t,
+            "s_per_build_sample": t, "result": last,
             "phases_s": {"density_on_grid": phases.density_on_grid, "functional": phases.functional,
                          "grid_to_matrix": phases.grid_to_matrix}}
 
@@ -369,8 +373,13 @@ def run_b200(args):
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             try:
-                cb = time_oracle(cfg, ids, mix, steps=3, warmup=1)
+                cb = time_oracle(cfg, ids, mix, steps=3, warmup=1, P=P)
                 line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "phases_s")}
+                if cb.get("result") is not None:  # the sample was the whole grid: parity of this very build
+                    Vo, Eo, No = cb["result"]
+                    line["parity"] = {"dE_xc": float(abs(E0 - Eo)), "max_dV_xc": float(np.abs(V0 - Vo).max()),
+                                      "dN_el": float(abs(ne0 - No)), "against": "CPU oracle, same P, full grid",
+                                      "tolerance": {"dE_xc": 1e-9, "max_dV_xc": 1e-8}}
             except Exception as exc:  # the oracle is a checker; its absence must not hide the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
                                         "sample": "failed: %s" % exc}
