@@ -300,6 +300,10 @@ int sxc_get_stats(sxc_ctx* ctx, sxc_stats* out);
  * cost; bounds[world + 1] receives the range starts (bounds[0] = 0, bounds[world] = n). */
 int sxc_balance_ranges(int n, const double* cost, int world, int* bounds);
 int sxc_abi_version(void);
+/* host-only introspection for the CPU test-suite: the warp-tile round schedule of the scatter kernel for a block with n32 =
+ * s_pad / 32 row groups, 40 bytes per round (ngroups, 7 x pad, group[8], slot_a[8], slot_b[8], kmask[8]; slot 0xff = idle
+ * warp); returns the number of rounds (rounds40 may be NULL) */
+int sxc_debug_scatter_schedule(int n32, unsigned char* rounds40, int max_rounds);
 
 #ifdef __cplusplus
 }

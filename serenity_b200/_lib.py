@@ -20,7 +20,7 @@ SYMBOLS = [
     "sxc_kernel_create", "sxc_kernel_destroy", "sxc_kernel_add", "sxc_kernel_get", "sxc_kernel_num_arrays", "sxc_kernel_contract",
     "sxc_kernel_integrate", "sxc_kernel_sigma", "sxc_kernel_response_copy", "sxc_kernel_contract_device", "sxc_kernel_integrate_device",
     "sxc_shell_table_from_file", "sxc_shell_table_sizes", "sxc_shell_table_copy", "sxc_shell_table_free", "sxc_add_basis_from_table",
-    "sxc_host_last_error",
+    "sxc_host_last_error", "sxc_debug_scatter_schedule",
 ]
 
 
@@ -108,6 +108,7 @@ def load():
     lib.sxc_shell_table_free.restype = None
     lib.sxc_add_basis_from_table.argtypes = [vp, vp, d, ip]
     lib.sxc_host_last_error.restype = C.c_char_p
+    lib.sxc_debug_scatter_schedule.argtypes = [i, vp, i]
     lib.sxc_kernel_sigma.argtypes = [vp, i, i, i, vp, i, i, vp, vp]
     _LIB = lib
     return lib

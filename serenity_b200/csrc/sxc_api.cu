@@ -386,9 +386,7 @@ int64_t workspace_limit(sxc_ctx* ctx) {
 // Scatter schedule of a block with n32 = s_pad / 32 row groups: the n32 (n32 + 1) / 2 upper-triangle warp tiles are
 // walked in bands of two row groups (column-major inside a band) and cut into rounds of <= WARPS tiles that touch
 // <= MAXG distinct groups; rounds of <= WARPS / 2 tiles give every tile to two warps (one k-step of each chunk each).
-const std::vector<ScatterRound>& scatter_schedule(sxc_ctx* ctx, int n32) {
-  auto it = ctx->scatter_tpl.find(n32);
-  if (it != ctx->scatter_tpl.end()) return it->second;
+std::vector<ScatterRound> build_scatter_schedule(int n32) {
   std::vector<std::pair<int, int>> tiles;
   for (int b0 = 0; b0 < n32; b0 += 2)
     for (int j = b0; j < n32; ++j)
@@ -440,7 +438,13 @@ const std::vector<ScatterRound>& scatter_schedule(sxc_ctx* ctx, int n32) {
     groups = g2;
   }
   flush();
-  return ctx->scatter_tpl[n32] = out;
+  return out;
+}
+
+const std::vector<ScatterRound>& scatter_schedule(sxc_ctx* ctx, int n32) {
+  auto it = ctx->scatter_tpl.find(n32);
+  if (it != ctx->scatter_tpl.end()) return it->second;
+  return ctx->scatter_tpl[n32] = build_scatter_schedule(n32);
 }
 
 constexpr int GRAD_PLAN = 1 << 20;  // key offset of the 8-slot plans of the gradient path
@@ -1229,6 +1233,16 @@ int build_ab_nadd_device(sxc_ctx* ctx, int gh, int fh, int nspin, int bA, int bB
 extern "C" {
 
 int sxc_abi_version(void) { return 5; }
+
+// host-only: the k_vmat round schedule of a block with n32 row groups (40 bytes per round, struct ScatterRound of
+// scatter_kernel.cuh: ngroups, 7 pad, group[8], ta[8], tb[8], kmask[8]); returns the number of rounds
+int sxc_debug_scatter_schedule(int n32, unsigned char* rounds40, int max_rounds) {
+  if (n32 < 1 || n32 > 255) return SXC_ERR_INVALID;
+  const std::vector<ScatterRound> r = build_scatter_schedule(n32);
+  if (rounds40)
+    for (int i = 0; i < (int)r.size() && i < max_rounds; ++i) std::memcpy(rounds40 + (size_t)40 * i, &r[i], 40);
+  return (int)r.size();
+}
 
 // host-only: contiguous ranges [bounds[r], bounds[r+1]) of nearly equal summed cost
 int sxc_balance_ranges(int n, const double* cost, int world, int* bounds) {

@@ -67,3 +67,34 @@ def test_balance_ranges_contiguous_and_balanced():
     assert b[0] == 0 and b[-1] == 3 and np.all(np.diff(b) >= 0) and np.diff(b).sum() == 3
     b = shard_bounds(np.zeros(0), 4)
     assert list(b) == [0, 0, 0, 0, 0]
+
+
+def test_scatter_schedule_covers_the_upper_triangle_once():
+    """Host logic of k_vmat (sxc_api.cu: build_scatter_schedule): for every block size the rounds hold each upper-triangle
+    32 x 32 warp tile exactly once (or twice with complementary k-step masks when a round has <= 4 tiles), stage at most 6
+    distinct row groups, give every warp at most one tile, and refer only to staged groups."""
+    from serenity_b200 import _lib
+    lib = _lib.load()
+    for n32 in list(range(1, 40)) + [64, 100, 255]:
+        nr = lib.sxc_debug_scatter_schedule(n32, None, 0)
+        assert nr > 0
+        buf = np.zeros((nr, 40), dtype=np.uint8)
+        assert lib.sxc_debug_scatter_schedule(n32, buf.ctypes.data_as(C.c_void_p), nr) == nr
+        seen = {}
+        for r in buf:
+            ng, group, ta, tb, km = int(r[0]), r[8:16], r[16:24], r[24:32], r[32:40]
+            assert 1 <= ng <= 6 and len(set(group[:ng].tolist())) == ng and all(g < n32 for g in group[:ng])
+            for w in range(8):
+                if ta[w] == 0xFF:
+                    assert tb[w] == 0xFF
+                    continue
+                assert ta[w] < ng and tb[w] < ng and km[w] in (1, 2, 3)
+                i, j = int(group[ta[w]]), int(group[tb[w]])
+                assert i <= j
+                seen[(i, j)] = seen.get((i, j), 0) | int(km[w])
+                if km[w] != 3:  # a split tile: the other k-step must be in the same round
+                    partner = [v for v in range(8) if v != w and ta[v] == ta[w] and tb[v] == tb[w]]
+                    assert len(partner) == 1 and km[partner[0]] == 3 - km[w]
+        assert sorted(seen) == [(i, j) for i in range(n32) for j in range(i, n32)]
+        assert all(v == 3 for v in seen.values())
+        assert nr <= (n32 * (n32 + 1) // 2 + 7) // 8 + n32  # never far from the slot bound
