@@ -14,6 +14,7 @@
 #define SERENITY_XC_ADAPTER_H
 
 #include <algorithm>
+#include <cctype>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -185,6 +186,41 @@ struct Functional {
   std::vector<int> basicFunctionals;
   std::vector<double> mixingFactors;
 };
+
+// dft/functionals/CompositeFunctionals.h:165-169 resolveFunctional, for the composites whose basic functionals this library
+// implements (rows of dft/functionals/functional_definitions.dat, XCFun route).  The exact-exchange fraction of the hybrids is
+// returned separately: it is ERI work and stays with the reference's exchange potentials.
+namespace CompositeFunctionals {
+inline Functional resolveFunctional(std::string name, double* exactExchange = nullptr) {
+  std::transform(name.begin(), name.end(), name.begin(), [](unsigned char c) { return (char)std::toupper(c); });
+  struct Row {
+    const char* name;
+    std::vector<int> ids;
+    std::vector<double> mix;
+    double hfx;
+  };
+  static const std::vector<Row> table = {
+      {"NONE", {}, {}, 0.0},
+      {"LDA", {SXC_X_SLATER, SXC_C_VWN}, {1.0, 1.0}, 0.0},
+      {"SLATER", {SXC_X_SLATER}, {1.0}, 0.0},
+      {"BLYP", {SXC_X_B88, SXC_C_LYP}, {1.0, 1.0}, 0.0},
+      {"PBE", {SXC_X_PBE, SXC_C_PBE}, {1.0, 1.0}, 0.0},
+      {"BP86", {SXC_X_B88, SXC_C_P86}, {1.0, 1.0}, 0.0},
+      {"BHLYP", {SXC_X_B88, SXC_C_LYP}, {0.50, 1.0}, 0.50},
+      {"PBE0", {SXC_X_PBE, SXC_C_PBE}, {0.75, 1.0}, 0.25},
+      {"B3LYP", {SXC_X_SLATER, SXC_X_B88_CORR, SXC_C_LYP, SXC_C_VWN}, {0.80, 0.72, 0.81, 0.19}, 0.20},
+      {"TF", {SXC_K_TF}, {1.0}, 0.0},
+      {"PW91K", {SXC_K_PW91}, {1.0}, 0.0},
+      {"LLP91K", {SXC_K_LLP}, {1.0}, 0.0},
+  };
+  for (const Row& r : table)
+    if (name == r.name) {
+      if (exactExchange) *exactExchange = r.hfx;
+      return Functional{r.ids, r.mix};
+    }
+  throw SerenityError("CompositeFunctionals::resolveFunctional: functional " + name + " is not available on the B200 path");
+}
+}  // namespace CompositeFunctionals
 
 // potentials/Potential.h:43-86
 template<Options::SCF_MODES SCFMode>

@@ -57,6 +57,19 @@ int main(int argc, char** argv) {
     }
     return 1;
   }
+  if (argc == 3 && std::strcmp(argv[1], "--resolve") == 0) {  // host-only: CompositeFunctionals::resolveFunctional
+    try {
+      double hfx = 0.0;
+      Functional f = CompositeFunctionals::resolveFunctional(argv[2], &hfx);
+      std::cout << argv[2] << " hfx=" << hfx;
+      for (size_t i = 0; i < f.basicFunctionals.size(); ++i) std::cout << " " << f.basicFunctionals[i] << ":" << f.mixingFactors[i];
+      std::cout << "\n";
+      return 0;
+    } catch (const SerenityError& e) {
+      std::cout << "SerenityError: " << e.what() << "\n";
+      return 3;
+    }
+  }
   if (argc != 3) return 2;
   try {
     std::ifstream in(argv[1], std::ios::binary);

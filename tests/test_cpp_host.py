@@ -26,6 +26,21 @@ def test_adapter_fails_loudly_without_device():
     assert r.returncode == 0 and "SerenityError" in r.stdout and "no CPU fallback" in r.stdout
 
 
+def test_resolve_functional_matches_the_python_table():
+    """CompositeFunctionals::resolveFunctional of the adapter (host only) against serenity_b200.inputs.configs.FUNCTIONALS, both
+    restating dft/functionals/functional_definitions.dat."""
+    from serenity_b200.inputs.configs import FUNCTIONALS
+    for name, (ids, mix) in FUNCTIONALS.items():
+        r = subprocess.run([_exe(), "--resolve", name.lower()], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout
+        parts = r.stdout.split()
+        got = [(int(p.split(":")[0]), float(p.split(":")[1])) for p in parts[2:]]
+        assert got == list(zip(ids, mix)), (name, got)
+    assert "hfx=0.2 " in subprocess.run([_exe(), "--resolve", "B3LYP"], capture_output=True, text=True).stdout
+    r = subprocess.run([_exe(), "--resolve", "PW91"], capture_output=True, text=True)
+    assert r.returncode == 3 and "SerenityError" in r.stdout
+
+
 def _w(f, a, dtype):
     a = np.ascontiguousarray(a, dtype=dtype).reshape(-1)
     f.write(struct.pack("<q", a.size))
