@@ -136,6 +136,25 @@ def cuda_local_build(ctx, grid: int, basis: int, func: int, block_ave_threshold:
     return run
 
 
+def cuda_local_nadd_build(ctx, grid: int, func: int, basis_act: int, basis_env, d_P_env, env_frozen: bool = True,
+                          block_ave_threshold: float = 1e-11):
+    """local_build for ShardedBuild(nbf_act, ..., ntail = 2 + len(basis_env)) on a CUDA rank: one NAddFuncPotential build
+    (sxc_build_nadd_device) of the active system against device-resident environment density matrices `d_P_env` (torch
+    tensors).  The all-reduced buffer is [V_nadd | E[rho_tot] | E[rho_act] | E[rho_env_i] ...]: every term is a sum over
+    grid blocks, so the freeze-and-thaw potentials shard like the KS potential (ShardedBuild.build_pinned returns the first
+    two energies; the environment terms stay in h_VEN[nb * nb + 2:])."""
+    ptrs = [t.data_ptr() for t in d_P_env]
+
+    def run(d_P: torch.Tensor, d_VE: torch.Tensor, p_ready=None):
+        if p_ready is not None:
+            ctx.set_p_ready_event(p_ready.cuda_event)
+        ctx.set_stream(torch.cuda.current_stream(d_P.device).cuda_stream or 1)
+        ctx.build_nadd_device(grid, func, basis_act, d_P.data_ptr(), list(basis_env), ptrs, d_VE.data_ptr(), env_frozen,
+                              block_ave_threshold)
+
+    return run
+
+
 class ShardedSigma:
     """LR-TDDFT kernel sigma build (row f-4) over the ranks of `group`: every rank holds the kernel store of its own grid
     blocks, contracts / integrates all nvec trial vectors on them and the partial Fock-like matrices are summed by ONE

@@ -111,3 +111,48 @@ def test_sharded_sigma_allreduce_gloo(tmp_path):
     mp.spawn(_sigma_worker, args=(2, port, out), nprocs=2, join=True)
     r = np.load(out)
     assert r["err"] < 1e-12 and r["sym"] < 1e-13
+
+
+def _nadd_worker(rank, world, port, out_path):
+    """ShardedBuild with ntail = 2 + nenv: the non-additive potential of config 4 sharded over ranks (every term of
+    [V_nadd | E_tot | E_act | E_env] is a sum over grid blocks)."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import pyoracle as orc
+        from serenity_b200.inputs import make_config
+        from serenity_b200.inputs.configs import FUNCTIONALS
+        from serenity_b200.sharded import ShardedBuild, shard_bounds
+        cfg = make_config("fde_dimer", 2)
+        act, env = cfg.subsystems
+        func = orc.Functional(*FUNCTIONALS["PW91K"])
+        nbf = act.basis.nbf
+        nblk = (cfg.npts + 127) // 128
+        bounds = shard_bounds(np.ones(nblk), world)
+        lo, hi = int(bounds[rank]) * 128, min(int(bounds[rank + 1]) * 128, cfg.npts)
+        oa, oe = orc.Basis(act.basis), orc.Basis(env.basis)
+
+        def local_build(d_P, d_VE, p_ready=None):
+            P = d_P.numpy().reshape(nbf, nbf, order="F")
+            V, _, parts = orc.build_nadd(oa, P, [(oe, env.P)], orc.Grid(cfg.xyz[lo:hi], cfg.w[lo:hi], 128), func)
+            d_VE[: nbf * nbf] = torch.from_numpy(V.reshape(-1, order="F").copy())
+            d_VE[nbf * nbf:] = torch.from_numpy(np.asarray(parts))
+
+        sb = ShardedBuild(nbf, local_build, "cpu", ntail=3)
+        V, E_tot, E_act = sb.build(act.P)
+        E_env = float(sb.h_VEN[nbf * nbf + 2])
+        if rank == 0:
+            V_ref, E_nadd_ref, parts = orc.build_nadd(oa, act.P, [(oe, env.P)], orc.Grid(cfg.xyz, cfg.w, 128), func)
+            np.savez(out_path, dV=np.abs(V - V_ref).max(), dE=abs((E_tot - E_act - E_env) - E_nadd_ref),
+                     dparts=np.abs(np.array([E_tot, E_act, E_env]) - parts).max())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_nadd_build_allreduce_gloo(tmp_path):
+    port = 29300 + os.getpid() % 300
+    out = str(tmp_path / "nadd.npz")
+    mp.spawn(_nadd_worker, args=(2, port, out), nprocs=2, join=True)
+    r = np.load(out)
+    assert r["dV"] < 1e-12 and r["dE"] < 1e-12 and r["dparts"] < 1e-12
