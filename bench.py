@@ -91,6 +91,17 @@ def oracle_sample(cfg, target_s=4.0):
     return orc, sub, pick, probe_k
 
 
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for ln in fh:
+                if ln.lower().startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def time_oracle(cfg, ids, mix, steps, warmup, target_s=4.0, P=None):
     """P: density matrix to use instead of the config's (timing does not depend on it); with a full-grid sample the last
     build's (V, E, N_el) come back under 'result' so that the caller can state parity."""
@@ -121,6 +132,8 @@ def time_oracle(cfg, ids, mix, steps, warmup, target_s=4.0, P=None):
     sample = ("%d of %d grid points (every %s128-point block of the workload), full XC build per step, "
               "%d steps" % (len(w), cfg.npts, "" if k == 1 else "%d-th " % k, steps))
     return {"value": len(w) / t, "unit": UNIT, "cores": orc.max_threads(), "kind": "port", "sample": sample,
+            "cpu_model": cpu_model(), "omp_proc_bind": os.environ.get("OMP_PROC_BIND", "unset"),
+            "omp_places": os.environ.get("OMP_PLACES", "unset"),
             "s_per_build_sample": t, "result": last,
             "phases_s": {"density_on_grid": phases.density_on_grid, "functional": phases.functional,
                          "grid_to_matrix": phases.grid_to_matrix}}
@@ -137,7 +150,8 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(cfg, args.gpus),
-            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "phases_s")},
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "phases_s", "cpu_model", "omp_proc_bind",
+                                                     "omp_places")},
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
             "note": "CPU restatement of Serenity's OpenMP path (oracle/, kind=port): the reference needs Eigen3, libint2, "
@@ -374,7 +388,8 @@ def run_b200(args):
         if world == 1 and not args.no_cpu_baseline:
             try:
                 cb = time_oracle(cfg, ids, mix, steps=3, warmup=1, P=P)
-                line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "phases_s")}
+                line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "phases_s", "cpu_model",
+                                                         "omp_proc_bind", "omp_places")}
                 if cb.get("result") is not None:  # the sample was the whole grid: parity of this very build
                     Vo, Eo, No = cb["result"]
                     line["parity"] = {"dE_xc": float(abs(E0 - Eo)), "max_dV_xc": float(np.abs(V0 - Vo).max()),
