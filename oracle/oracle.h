@@ -177,6 +177,14 @@ void orc_kernel_contract(const orc_basis* b, const orc_grid* g, double radial_th
 void orc_kernel_integrate(const orc_basis* b, const orc_grid* g, double radial_thr, double block_ave_thr, int gga, int nspin,
                           const double* resp, double* F);
 
+/* ---- INT8-slice ("Ozaki") reference of the contractions (ozaki.c): groundwork for the tcgen05 kind::i8 path ------- */
+/* rows of X [rows][cols] -> k signed 7-bit slices S [k][rows][cols] and one exponent per row */
+void orc_ozaki_slice_rows(const double* X, int rows, int cols, int k, signed char* S, int* e);
+/* acc [k][m][n] (INT32, exact): acc_d[a][b] = sum_{i+j=d} sum_c A_i[a][c] B_j[b][c]  (both operands K-contiguous) */
+void orc_ozaki_gemm_i32(const signed char* A, const signed char* B, int k, int m, int n, int K, int* acc);
+/* C[m][n] = 2^(eA_m + eB_n) sum_d 128^-(d+2) acc_d */
+void orc_ozaki_combine(const int* acc, int k, int m, int n, const int* eA, const int* eB, double* C);
+
 #ifdef __cplusplus
 }
 #endif

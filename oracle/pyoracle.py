@@ -17,7 +17,7 @@ _LIB = None
 
 def build(force: bool = False) -> str:
     path = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle_functionals.c", "oracle_functionals_u.cpp", "oracle_kernel2.cpp",
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle_functionals.c", "oracle_functionals_u.cpp", "oracle_kernel2.cpp", "ozaki.c",
                                            "functionals_jet.inc", "oracle.h", "harmonics_table.h")]
     if force or not os.path.exists(path) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
@@ -376,3 +376,27 @@ def kernel_integrate(basis: Basis, grid: Grid, resp, gga: bool, nspin: int = 1, 
                                int(gga), int(nspin), _p(resp), _p(F))
     mats = [F[s].reshape(nb, nb, order="F") for s in range(nspin)]
     return mats[0] if nspin == 1 else mats
+
+
+# ---------------------------------------------------------------------------------------------- INT8-slice reference
+def ozaki_slice_rows(X, k: int):
+    """rows of X [rows, cols] -> (slices int8 [k, rows, cols], exponents int32 [rows])"""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    rows, cols = X.shape
+    S = np.zeros((k, rows, cols), dtype=np.int8)
+    e = np.zeros(rows, dtype=np.int32)
+    lib().orc_ozaki_slice_rows(_p(X), rows, cols, int(k), _p(S), _p(e))
+    return S, e
+
+
+def ozaki_matmul(A, B, k: int):
+    """A [m, K] . B [n, K]^T with k INT8 slices per operand row: (C float64 [m, n], acc int32 [k, m, n])."""
+    Sa, ea = ozaki_slice_rows(A, k)
+    Sb, eb = ozaki_slice_rows(B, k)
+    m, K = Sa.shape[1], Sa.shape[2]
+    n = Sb.shape[1]
+    acc = np.zeros((k, m, n), dtype=np.int32)
+    lib().orc_ozaki_gemm_i32(_p(Sa), _p(Sb), int(k), m, n, K, _p(acc))
+    C_ = np.zeros((m, n))
+    lib().orc_ozaki_combine(_p(acc), int(k), m, n, _p(ea), _p(eb), _p(C_))
+    return C_, acc
