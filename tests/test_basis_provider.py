@@ -96,3 +96,58 @@ def test_gpu_build_from_basis_file():
     V, E, _ = ctx.build_xc(g, b.value, f, sub.P)
     assert np.abs(V - V_ref).max() <= 1e-13 and abs(E - E_ref) <= 1e-13
     ctx.close()
+
+
+def test_parser_round_trip_on_generated_files(tmp_path):
+    """Property test of the C++ parser (hypothesis): random element entries written in Turbomole format with varying white
+    space, D / E exponents and optional comment lines come back with exactly the written exponents, contraction lengths and
+    angular momenta, in file order, atom-major."""
+    from hypothesis import given, settings, strategies as st
+    from serenity_b200.xc import shell_table_from_file
+
+    shell = st.tuples(st.sampled_from("spdfg"), st.lists(st.tuples(st.floats(1e-3, 1e5), st.floats(-2.0, 2.0).filter(lambda c: abs(c) > 1e-3)),
+                                                          min_size=1, max_size=6))
+    entry = st.lists(shell, min_size=1, max_size=5)
+
+    @settings(max_examples=40, deadline=None)
+    @given(entries=st.lists(entry, min_size=1, max_size=3), fortran=st.booleans(), comment=st.booleans(), pad=st.integers(1, 6))
+    def run(entries, fortran, comment, pad):
+        names = ["h", "c", "o"][:len(entries)]
+        lines = ["# generated", "$basis", "*"]
+        for el, shells in zip(names, entries):
+            lines.append("%s%sTEST-BASIS" % (el, " " * pad))
+            if comment:
+                lines.append("# %s  (generated)" % el)
+            lines.append("*")
+            for typ, prim in shells:
+                lines.append("%s%d  %s" % (" " * pad, len(prim), typ))
+                for a, c in prim:
+                    fa, fc = "%.17e" % a, "%.17e" % c
+                    if fortran:
+                        fa, fc = fa.replace("e", "D"), fc.replace("e", "D")
+                    lines.append("%s%s%s%s" % (" " * pad, fa, " " * pad, fc))
+            lines.append("*")
+        lines.append("$end")
+        path = tmp_path / "gen_basis"
+        path.write_text("\n".join(lines) + "\n")
+        syms = [n.upper() for n in reversed(names)]          # atoms in another order than the file
+        xyz = np.arange(3.0 * len(syms)).reshape(-1, 3)
+        tab, atom_of_bf = shell_table_from_file(str(path), "test-basis", syms, xyz, True)
+        want = [sh for n in reversed(names) for sh in entries[names.index(n)]]
+        assert tab.nshell == len(want)
+        assert list(tab.l) == ["spdfg".index(t) for t, _ in want]
+        assert list(tab.nprim) == [len(p) for _, p in want]
+        assert np.array_equal(tab.alpha, np.array([a for _, p in want for a, _ in p]))
+        assert tab.nbf == sum(2 * "spdfg".index(t) + 1 for t, _ in want) == len(atom_of_bf)
+        assert np.all(np.diff(atom_of_bf) >= 0) and atom_of_bf[-1] == len(syms) - 1
+        # libint renormalisation: unit self-overlap of every contraction whose coefficients do not cancel
+        for s in range(tab.nshell):
+            l, o, n = int(tab.l[s]), int(tab.prim_off[s]), int(tab.nprim[s])
+            a, c = tab.alpha[o:o + n], tab.coeff[o:o + n]
+            if not np.all(np.isfinite(c)):
+                continue
+            ovl = sum(c[p] * c[q] * _dfact(2 * l - 1) * math.pi ** 1.5 / (2.0 ** l * (a[p] + a[q]) ** (l + 1.5))
+                      for p in range(n) for q in range(n))
+            assert abs(ovl - 1.0) < 1e-9
+
+    run()
