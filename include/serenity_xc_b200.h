@@ -24,6 +24,7 @@
 #ifndef SERENITY_XC_B200_H
 #define SERENITY_XC_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -66,6 +67,7 @@ enum {
   SXC_T_FORM_G = 4,   /* k_form_g: weights x potential, block test, G tile (8a-5)           */
   SXC_T_SCATTER = 5,  /* k_scatter: phi^T G + G^T phi DMMA, accumulation   (8a-5)           */
   SXC_T_FINISH = 6,   /* k_mirror + k_reduce_partials                                       */
+  SXC_T_ALLREDUCE = 7, /* ncclAllReduce of [V | E | N] (multi-GPU, 8e)                      */
   SXC_T_COUNT = 8
 };
 
@@ -116,6 +118,30 @@ int sxc_set_p_ready_event(sxc_ctx* ctx, void* cuda_event);
  * sxc_get_stats() then synchronises on the last build's events */
 int sxc_set_timing(sxc_ctx* ctx, int on);
 
+/* Optional page-locked host memory (cudaHostAlloc) for the P / V buffers of the host-buffer builds: with it their copies are
+ * asynchronous DMA; with ordinary (pageable) caller memory - what Eigen matrices in Serenity are - the driver stages them. */
+void* sxc_host_alloc(size_t bytes);
+void sxc_host_free(void* p);
+
+/* ---- multi-GPU ------------------------------------------------------------------ */
+/* Grid blocks are sharded over the GPUs of one node, one context (= one process or host thread) per GPU; the only exchange is
+ * ONE ncclAllReduce of the build's result buffer [V | E | N ...] (nspin*nb*nb + 2 doubles) over NVLink 5 / NVSwitch, issued by
+ * the library on the build's stream right behind its last kernel - the device-side replacement of the serial reduction over
+ * per-thread accumulators in ScalarOperatorToMatrixAdder.cpp:73-75 / :108-110.  NCCL is bound at run time (libnccl.so.2).
+ *   rank 0:      sxc_comm_unique_id(id);  ship the 128 bytes to the other ranks by any means (MPI, file, torch store)
+ *   every rank:  sxc_create(&ctx, local_device);  sxc_comm_init_rank(ctx, rank, world, id);
+ * From then on every grid of the context is this rank's shard (sxc_set_grid_shard is applied automatically) and sxc_build_xc /
+ * sxc_build_nadd / sxc_build_nadd_multi / sxc_xc_gradient / sxc_nadd_gradient / sxc_build_ab / sxc_build_ab_nadd /
+ * sxc_kernel_integrate return the SUM over ranks on every rank; all ranks must make the same calls in the same order.  In the
+ * host-buffer builds a rank that does not need the matrix may pass V = NULL (only E and nelec are copied back). */
+#define SXC_COMM_ID_BYTES 128
+int sxc_comm_unique_id(void* id128);
+int sxc_comm_init_rank(sxc_ctx* ctx, int rank, int world, const void* id128);
+int sxc_comm_destroy(sxc_ctx* ctx);
+/* rank / world of the context's communicator (0 / 1 without one), all-reduces issued so far, NCCL version code; any pointer
+ * may be NULL */
+int sxc_comm_info(sxc_ctx* ctx, int* rank, int* world, int64_t* collectives, int* nccl_version);
+
 /* ---- inputs -------------------------------------------------------------------------------------------- */
 /* replaces GridController::getGridPoints()/getWeights() (src/grid/GridController.cpp:31-50); re-upload only
  * on a Grid notify.  blocksize = settings grid.blocksize (128; 1..128 supported). */
@@ -134,16 +160,24 @@ int sxc_add_basis(sxc_ctx* ctx, int nshell, const int* l, const int* pure, const
                   const double* centre /*3*nshell*/, const double* alpha, const double* coeff,
                   const double* normfac, double radial_threshold, int* basis);
 
-/* replaces XCFun::getFunctional (src/dft/functionals/wrappers/XCFun.cpp:721-745) */
+/* replaces XCFun::getFunctional (src/dft/functionals/wrappers/XCFun.cpp:721-745); equal definitions share one handle */
 int sxc_set_functional(sxc_ctx* ctx, int ncomp, const int* basic_id, const double* mix, int* func);
+/* Release a grid (points, per-point work arrays, cached environment density, kernel stores on it), a basis (shell table) and
+ * every screening plan that involves them; the handle value may be handed out again.  What ~GridController / ~BasisController
+ * trigger in the adapter: geometry steps and regenerated FDE grids do not pile up in HBM.  Functional handles are a few
+ * bytes, shared and kept until sxc_destroy (the call only validates the handle). */
+int sxc_release_grid(sxc_ctx* ctx, int grid);
+int sxc_release_basis(sxc_ctx* ctx, int basis);
+int sxc_release_functional(sxc_ctx* ctx, int func);
 
 /* ---- the hot path -------------------------------------------------------------------------------------- */
 /* FuncPotential<SCFMode>::getMatrix + getEnergy (src/potentials/FuncPotential.cpp:67-111).
  * nspin = 1 (RESTRICTED): P, V nb x nb.  nspin = 2 (UNRESTRICTED): P = {P_alpha, P_beta} and V = {V_alpha, V_beta}
  * stored back to back (2 nb^2 doubles each, the alpha/beta pair of src/data/SpinPolarizedData.h).
  * V is overwritten, E = sum_p w_p F_p, nelec = sum_p w_p (rho_alpha + rho_beta).  block_ave_threshold = settings
- * grid.blockAveThreshold (1e-11), applied per spin as in the reference.  With a shard set, V/E/nelec are this
- * rank's partial sums. */
+ * grid.blockAveThreshold (1e-11), applied per spin as in the reference.  With a shard set by hand (sxc_set_grid_shard, no
+ * communicator) V/E/nelec are this rank's partial sums; with a communicator they are the sums over all ranks and V may be
+ * NULL on ranks that do not need the matrix. */
 int sxc_build_xc(sxc_ctx* ctx, int grid, int basis, int func, int nspin, const double* P,
                  double block_ave_threshold, double* V, double* E, double* nelec);
 /* same with device-resident P and result: d_VEN holds nspin*nb*nb doubles of V followed by E and nelec
@@ -155,15 +189,34 @@ int sxc_build_xc_device(sxc_ctx* ctx, int grid, int basis, int func, int nspin, 
  * density of SupersystemDensityOnGridController::updateData (SupersystemDensityOnGridController.cpp:95-193):
  * V_A = scatter of v[rho_A + sum rho_env] - v[rho_A] in the active basis; E[0] = E[rho_tot], E[1] = E[rho_A],
  * E[2+i] = E[rho_env_i]  (E_nadd = E[0] - E[1] - sum E[2+i]).  nspin = 2: every P / V is an {alpha, beta} pair
- * stored back to back.  env_frozen != 0: environment densities on the
- * grid and their energies are kept from the previous call with the same handles (they are frozen during one
- * FDE SCF, DensityOnGridFactory.cpp:41-48). */
+ * stored back to back.  env_frozen != 0: environment densities on the grid and their energies are kept from the previous
+ * call with the same handles AND the same env_frozen value (they are frozen during one FDE SCF,
+ * DensityOnGridFactory.cpp:41-48).  The value is the caller's tag of the environment state: the cache lives on the grid, so
+ * two NAdd objects on one grid whose environments share basis handles but hold different density matrices must pass
+ * different tags, and a caller whose environment density changed passes a new one (the adapter draws them from a counter;
+ * the XC and kinetic objects of one FDE iteration see the same environment and share a tag). */
 int sxc_build_nadd(sxc_ctx* ctx, int grid, int func, int nspin, int basis_act, const double* P_act, int nenv,
                    const int* basis_env, const double* const* P_env, int env_frozen, double block_ave_threshold,
                    double* V_act, double* E /*[2+nenv]*/);
 int sxc_build_nadd_device(sxc_ctx* ctx, int grid, int func, int nspin, int basis_act, const double* d_P_act,
                           int nenv, const int* basis_env, const double* const* d_P_env, int env_frozen,
                           double block_ave_threshold, double* d_VE /* nspin*nbA*nbA + 2 + nenv */);
+
+/* One device pass for the nfunc non-additive functionals of an FDE iteration: FDEPotentials::getFockMatrix
+ * (src/potentials/bundles/FDEPotentials.cpp:43-61) adds naddXC->getMatrix() and naddKin->getMatrix(), two NAddFuncPotential
+ * objects on the SAME active / environment densities and grid.  rho_act (the DMMA contraction) and sum rho_env are built once;
+ * per functional E[k*(2+nenv) + 0] = E_k[rho_tot], [+1] = E_k[rho_act], [+2+i] = E_k[rho_env_i].
+ *   sum_matrices != 0: V_act = sum_k V_nadd,k (nspin*nbA*nbA doubles): the potentials are summed on the grid and scattered
+ *                      once - exactly what the bundle hands to the Fock matrix;
+ *   sum_matrices == 0: V_act = nfunc matrices back to back (every object gets its own; one scatter each).
+ * nfunc = 1, sum_matrices = 0 is sxc_build_nadd. */
+int sxc_build_nadd_multi(sxc_ctx* ctx, int grid, int nfunc, const int* funcs, int nspin, int basis_act, const double* P_act,
+                         int nenv, const int* basis_env, const double* const* P_env, int env_frozen,
+                         double block_ave_threshold, int sum_matrices, double* V_act, double* E /*[nfunc*(2+nenv)]*/);
+int sxc_build_nadd_multi_device(sxc_ctx* ctx, int grid, int nfunc, const int* funcs, int nspin, int basis_act,
+                                const double* d_P_act, int nenv, const int* basis_env, const double* const* d_P_env,
+                                int env_frozen, double block_ave_threshold, int sum_matrices,
+                                double* d_VE /* (sum ? 1 : nfunc)*nspin*nbA*nbA + nfunc*(2+nenv) */);
 
 /* FuncPotential<SCFMode>::getGeomGradients (src/potentials/FuncPotential.cpp:114-239), SURVEY.md row f-3: the XC
  * contribution to the nuclear gradient.  atom_of_bf[nbf] = BasisController::getAtomIndicesOfBasis() (:127); grad is the

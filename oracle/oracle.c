@@ -21,11 +21,16 @@ static void omp_set_num_threads(int n) { (void)n; }
 #endif
 
 #include "harmonics_table.h"
+#include "harmonics_gen.h"
 
 #define ORC_AM_MAX 6 /* parameters/Constants.h:31 */
 
 int orc_max_threads(void) { return omp_get_max_threads(); }
 void orc_set_threads(int n) { omp_set_num_threads(n); }
+/* thread 0's share of the work, split by phase (bench.py reports the GEMM rate per core from it) */
+static double g_probe[3]; /* seconds in basis evaluation, seconds in the dense products, flops of those products */
+void orc_probe_reset(void) { g_probe[0] = g_probe[1] = g_probe[2] = 0.0; }
+void orc_probe_get(double* out3) { memcpy(out3, g_probe, sizeof(g_probe)); }
 
 /* nBlocks = ceil(nPoints / maxBlockSize), BasisFunctionOnGridController.cpp:83 */
 int orc_nblocks(const orc_grid* g) { return (int)((g->npts + g->blocksize - 1) / g->blocksize); }
@@ -204,6 +209,26 @@ static void block_evaluate(const orc_basis* b, const orc_grid* g, double radial_
         }
       } else {
         /* spherical, :441-1095: phi = R*Y, d_x phi = R dY/dx + R' x Y, ... (finalisation :1068-1095) */
+        if (deriv <= 1 && l <= ORC_GEN_LMAX) { /* straight-line formulas per l, like the reference's switch(l) */
+          double Y[2 * ORC_GEN_LMAX + 1], Yx[2 * ORC_GEN_LMAX + 1], Yy[2 * ORC_GEN_LMAX + 1], Yz[2 * ORC_GEN_LMAX + 1];
+          switch (l) {
+            case 0: orc_harm_l0(x, y, z, Y, Yx, Yy, Yz); break;
+            case 1: orc_harm_l1(x, y, z, Y, Yx, Yy, Yz); break;
+            case 2: orc_harm_l2(x, y, z, Y, Yx, Yy, Yz); break;
+            case 3: orc_harm_l3(x, y, z, Y, Yx, Yy, Yz); break;
+            default: orc_harm_l4(x, y, z, Y, Yx, Yy, Yz); break;
+          }
+          for (int m = 0; m < nf; ++m) {
+            const long idx = i0 + (long)m * n;
+            val[idx] = radial * Y[m];
+            if (deriv >= 1) {
+              d1[0][idx] = radial * Yx[m] + dradial * x[1] * Y[m];
+              d1[1][idx] = radial * Yy[m] + dradial * y[1] * Y[m];
+              d1[2][idx] = radial * Yz[m] + dradial * z[1] * Y[m];
+            }
+          }
+          continue;
+        }
         for (int m = 0; m < nf; ++m) {
           const orc_harm_t* h = &ORC_HARM[l][m];
           const long idx = i0 + (long)m * n;
@@ -309,10 +334,15 @@ static int ws_block(orc_ws* w, const orc_basis* b, const orc_grid* g, double rad
                     int* n_out, double* t_basis) {
   const int n = block_size(g, block);
   const long first = (long)block * g->blocksize;
-  const double t0 = (t_basis && omp_get_thread_num() == 0) ? omp_get_wtime() : 0.0;
+  const int probe = omp_get_thread_num() == 0;
+  const double t0 = probe ? omp_get_wtime() : 0.0;
   block_prescreen(b, g, radial_thr, first, n, w->shell_neg, NULL);
   block_evaluate(b, g, radial_thr, deriv, first, n, w->shell_neg, w->val, w->d1, w->d2);
-  if (t_basis && omp_get_thread_num() == 0) *t_basis += omp_get_wtime() - t0;
+  if (probe) {
+    const double dt = omp_get_wtime() - t0;
+    g_probe[0] += dt;
+    if (t_basis) *t_basis += dt;
+  }
   int s = 0;
   for (int sh = 0; sh < b->nshell; ++sh) {
     if (w->shell_neg[sh]) continue;
@@ -327,8 +357,23 @@ static int ws_block(orc_ws* w, const orc_basis* b, const orc_grid* g, double rad
  * small dense kernels (stand-in for Eigen's GEMM; column-major)
  * ------------------------------------------------------------------------------------------------ */
 /* C (m x n) = A (m x k) * B (k x n) */
-static void gemm_nn(int m, int n, int k, const double* restrict A, int lda, const double* restrict B, int ldb,
+/* Optional BLAS back end (bench.py: OpenBLAS cblas_dgemm from the scipy wheel, single-threaded per call inside the
+ * OpenMP loop over blocks): the reference's products are Eigen GEMMs (MatrixOperatorToGridTransformer.cpp:157,
+ * ScalarOperatorToMatrixAdder.cpp:282); a tuned library GEMM is the honest stand-in for the timed CPU baseline.  Without
+ * it the compiler-vectorised loops below run (golden-vector tests, machines without the wheel). */
+typedef void (*orc_dgemm_fn)(int order, int transa, int transb, int m, int n, int k, double alpha, const double* A, int lda,
+                             const double* B, int ldb, double beta, double* C, int ldc);
+static orc_dgemm_fn g_dgemm = NULL;
+void orc_set_dgemm(void* fn) { g_dgemm = (orc_dgemm_fn)fn; }
+int orc_has_dgemm(void) { return g_dgemm != NULL; }
+enum { ORC_COLMAJOR = 102, ORC_NOTRANS = 111, ORC_TRANS = 112 };
+
+static void gemm_nn_impl(int m, int n, int k, const double* restrict A, int lda, const double* restrict B, int ldb,
                     double* restrict C, int ldc) {
+  if (g_dgemm && m > 0 && n > 0 && k > 0) {
+    g_dgemm(ORC_COLMAJOR, ORC_NOTRANS, ORC_NOTRANS, m, n, k, 1.0, A, lda, B, ldb, 0.0, C, ldc);
+    return;
+  }
   for (int j = 0; j < n; ++j) memset(C + (size_t)j * ldc, 0, sizeof(double) * (size_t)m);
   int j = 0;
   for (; j + 4 <= n; j += 4) {
@@ -384,8 +429,12 @@ static void gemm_nn(int m, int n, int k, const double* restrict A, int lda, cons
 }
 
 /* C (m x n) = A^T (A is k x m) * B (k x n) */
-static void gemm_tn(int m, int n, int k, const double* restrict A, int lda, const double* restrict B, int ldb,
+static void gemm_tn_impl(int m, int n, int k, const double* restrict A, int lda, const double* restrict B, int ldb,
                     double* restrict C, int ldc) {
+  if (g_dgemm && m > 0 && n > 0 && k > 0) {
+    g_dgemm(ORC_COLMAJOR, ORC_TRANS, ORC_NOTRANS, m, n, k, 1.0, A, lda, B, ldb, 0.0, C, ldc);
+    return;
+  }
   int j = 0;
   for (; j + 2 <= n; j += 2) {
     const double* restrict b0 = B + (size_t)j * ldb;
@@ -439,6 +488,25 @@ static void gemm_tn(int m, int n, int k, const double* restrict A, int lda, cons
       for (int p = 0; p < k; ++p) s0 += a0[p] * b0[p];
       C[i + (size_t)j * ldc] = s0;
     }
+  }
+}
+
+static void gemm_nn(int m, int n, int k, const double* A, int lda, const double* B, int ldb, double* C, int ldc) {
+  const int probe = omp_get_thread_num() == 0;
+  const double t0 = probe ? omp_get_wtime() : 0.0;
+  gemm_nn_impl(m, n, k, A, lda, B, ldb, C, ldc);
+  if (probe) {
+    g_probe[1] += omp_get_wtime() - t0;
+    g_probe[2] += 2.0 * m * (double)n * k;
+  }
+}
+static void gemm_tn(int m, int n, int k, const double* A, int lda, const double* B, int ldb, double* C, int ldc) {
+  const int probe = omp_get_thread_num() == 0;
+  const double t0 = probe ? omp_get_wtime() : 0.0;
+  gemm_tn_impl(m, n, k, A, lda, B, ldb, C, ldc);
+  if (probe) {
+    g_probe[1] += omp_get_wtime() - t0;
+    g_probe[2] += 2.0 * m * (double)n * k;
   }
 }
 

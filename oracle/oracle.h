@@ -79,6 +79,12 @@ typedef struct {
 int orc_nblocks(const orc_grid* g);
 int orc_max_threads(void);
 void orc_set_threads(int n);
+/* optional BLAS back end for the dense products: a cblas_dgemm-compatible function pointer (NULL: built-in loops) */
+void orc_set_dgemm(void* cblas_dgemm_fn);
+int orc_has_dgemm(void);
+/* phase probe of OpenMP thread 0: seconds in basis-function evaluation, seconds in the dense products, their flops */
+void orc_probe_reset(void);
+void orc_probe_get(double* out3);
 int orc_functional_is_gga(const orc_functional* f);
 
 /* 8a-1  BasisFunctionOnGridController::calculateBasisFunctionData (data/grid/BasisFunctionOnGridController.cpp:150-1105).

@@ -15,13 +15,80 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 
+_SRCS = ("oracle.c", "oracle_functionals.c", "oracle_functionals_u.cpp", "oracle_kernel2.cpp", "ozaki.c",
+         "functionals_jet.inc", "oracle.h", "harmonics_table.h", "harmonics_gen.h", "Makefile")
+
+
+def _cpu_has_avx512() -> bool:
+    need = {"avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl"}
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for ln in fh:
+                if ln.startswith("flags"):
+                    return need <= set(ln.split(":", 1)[1].split())
+    except OSError:
+        pass
+    return False
+
+
+def variant() -> str:
+    """'avx512' (x86-64-v4 build, 512-bit vectors) when the host CPU has it and ORACLE_VARIANT does not say otherwise, else 'avx2'."""
+    want = os.environ.get("ORACLE_VARIANT", "")
+    if want in ("avx2", "avx512"):
+        return want
+    return "avx512" if _cpu_has_avx512() else "avx2"
+
+
+def _lib_path(var=None) -> str:
+    return os.path.join(_HERE, "liboracle_avx512.so" if (var or variant()) == "avx512" else "liboracle.so")
+
+
 def build(force: bool = False) -> str:
-    path = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle_functionals.c", "oracle_functionals_u.cpp", "oracle_kernel2.cpp", "ozaki.c",
-                                           "functionals_jet.inc", "oracle.h", "harmonics_table.h")]
-    if force or not os.path.exists(path) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in srcs):
-        subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
-    return path
+    """Both variants (they travel prebuilt to the GPU box); returns the portable one."""
+    srcs = [os.path.join(_HERE, f) for f in _SRCS]
+    for path in (_lib_path("avx2"), _lib_path("avx512")):
+        if force or not os.path.exists(path) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in srcs):
+            subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "-j4"])
+            break
+    return _lib_path("avx2")
+
+
+_BLAS = None
+
+
+def use_openblas(on: bool = True) -> dict:
+    """Route the oracle's dense products (phi_s P_s, phi_s^T G) through OpenBLAS' cblas_dgemm from the scipy / numpy wheel,
+    one thread per call (the OpenMP loop over blocks supplies the parallelism, as in the reference where Eigen's GEMM runs
+    inside `omp parallel for`).  Returns {'gemm': ..., 'library': ..., 'core': ...}; falls back to the built-in loops."""
+    global _BLAS
+    L = lib()
+    if not on:
+        L.orc_set_dgemm(None)
+        return {"gemm": "builtin loops (gcc auto-vectorised, %s)" % variant()}
+    import glob
+    import site
+    cands = []
+    for sp in site.getsitepackages() + [os.path.dirname(os.path.dirname(np.__file__))]:
+        cands += sorted(glob.glob(os.path.join(sp, "scipy.libs", "libscipy_openblas-*.so")))
+        cands += sorted(glob.glob(os.path.join(sp, "numpy.libs", "libscipy_openblas-*.so")))
+    for path in cands:
+        try:
+            B = C.CDLL(path)
+            fn = B.scipy_cblas_dgemm
+        except (OSError, AttributeError):
+            continue
+        try:
+            B.scipy_openblas_set_num_threads(1)
+            B.scipy_openblas_get_corename.restype = C.c_char_p
+            core = B.scipy_openblas_get_corename().decode()
+        except AttributeError:
+            core = "unknown"
+        _BLAS = B
+        L.orc_set_dgemm(C.cast(fn, C.c_void_p))
+        return {"gemm": "OpenBLAS cblas_dgemm (LP64, 1 thread per call inside the OpenMP block loop)",
+                "library": os.path.basename(path), "core": core}
+    L.orc_set_dgemm(None)
+    return {"gemm": "builtin loops (gcc auto-vectorised, %s): no loadable OpenBLAS with scipy_cblas_dgemm found" % variant()}
 
 
 class _Basis(C.Structure):
@@ -46,10 +113,11 @@ class Timings(C.Structure):
 def lib():
     global _LIB
     if _LIB is None:
-        path = os.path.join(_HERE, "liboracle.so")
+        path = _lib_path()
         if not os.path.exists(path):
             build()
         _LIB = C.CDLL(path)
+        _LIB.orc_set_dgemm.argtypes = [C.c_void_p]
         _LIB.orc_functional_on_grid.restype = C.c_double
         _LIB.orc_functional_on_grid_u.restype = C.c_double
         _LIB.orc_nblocks.restype = C.c_int

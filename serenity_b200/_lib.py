@@ -21,6 +21,8 @@ SYMBOLS = [
     "sxc_kernel_integrate", "sxc_kernel_sigma", "sxc_kernel_response_copy", "sxc_kernel_contract_device", "sxc_kernel_integrate_device",
     "sxc_shell_table_from_file", "sxc_shell_table_sizes", "sxc_shell_table_copy", "sxc_shell_table_free", "sxc_add_basis_from_table",
     "sxc_host_last_error", "sxc_debug_scatter_schedule",
+    "sxc_comm_unique_id", "sxc_comm_init_rank", "sxc_comm_destroy", "sxc_comm_info", "sxc_release_grid", "sxc_release_basis",
+    "sxc_release_functional", "sxc_host_alloc", "sxc_host_free", "sxc_build_nadd_multi", "sxc_build_nadd_multi_device",
 ]
 
 
@@ -28,7 +30,7 @@ class SerenityError(RuntimeError):
     """Mirror of src/misc/SerenityError.h:36 - what the adapter throws when the C ABI returns an error."""
 
 
-KERNEL_SLOTS = ["k_screen", "k_basis", "k_density", "k_functional", "k_form_g", "k_scatter", "finish"]  # SXC_T_*
+KERNEL_SLOTS = ["k_screen", "k_basis", "k_density", "k_functional", "k_form_g", "k_scatter", "finish", "allreduce"]  # SXC_T_*
 
 
 class Stats(C.Structure):
@@ -110,5 +112,18 @@ def load():
     lib.sxc_host_last_error.restype = C.c_char_p
     lib.sxc_debug_scatter_schedule.argtypes = [i, vp, i]
     lib.sxc_kernel_sigma.argtypes = [vp, i, i, i, vp, i, i, vp, vp]
+    lib.sxc_build_nadd_multi.argtypes = [vp, i, i, vp, i, i, vp, i, vp, vp, i, d, i, vp, vp]
+    lib.sxc_build_nadd_multi_device.argtypes = [vp, i, i, vp, i, i, vp, i, vp, vp, i, d, i, vp]
+    lib.sxc_comm_unique_id.argtypes = [vp]
+    lib.sxc_comm_init_rank.argtypes = [vp, i, i, vp]
+    lib.sxc_comm_destroy.argtypes = [vp]
+    lib.sxc_comm_info.argtypes = [vp, ip, ip, C.POINTER(i64), ip]
+    lib.sxc_release_grid.argtypes = [vp, i]
+    lib.sxc_release_basis.argtypes = [vp, i]
+    lib.sxc_release_functional.argtypes = [vp, i]
+    lib.sxc_host_alloc.argtypes = [C.c_size_t]
+    lib.sxc_host_alloc.restype = vp
+    lib.sxc_host_free.argtypes = [vp]
+    lib.sxc_host_free.restype = None
     _LIB = lib
     return lib

@@ -21,6 +21,7 @@
 
 #include "../../include/serenity_xc_b200.h"
 #include "basis_kernels.cuh"
+#include "comm.h"
 #include "density_kernel.cuh"
 #include "functionals.cuh"
 #include "scatter_kernel.cuh"
@@ -197,12 +198,19 @@ struct sxc_ctx {
   float last_partition_ms = 0.f;  // device time of the last k_partition_weights launch
   sxc_stats stats{};
   int launches = 0;
+  long collectives = 0;  // ncclAllReduce calls issued by this context
   bool attrs_set = false;
   cudaEvent_t p_ready = nullptr;     // one-shot: the next build waits for it before it first reads P
   cudaStream_t copy_stream = nullptr; // H2D of P in the host-buffer entry points (overlaps screening + basis)
   cudaEvent_t copy_done = nullptr;
-  bool timing = false;        // record events during the current build
-  bool timing_device = false; // sxc_set_timing: also for the *_device entry points
+  int timing = 0;             // events recorded during the current build: 0 none, 1 first-to-last kernel only, 2 per kernel
+  bool timing_device = false; // sxc_set_timing: per-kernel events in every build (also the *_device entry points)
+  struct PendingUpload {
+    void* dst;
+    const void* src;
+    size_t bytes;
+  };
+  std::vector<PendingUpload> pending;  // host-buffer entry points: P matrices to upload when the build first needs them
   struct Stamp {
     int slot;
     cudaEvent_t a, b;
@@ -210,6 +218,10 @@ struct sxc_ctx {
   std::vector<Stamp> stamps;  // events of the last build, collected lazily
   std::vector<cudaEvent_t> event_pool;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
+  // multi-GPU: communicator of the ranks that share the grid (sxc_comm_init_rank); builds on a sharded grid end with one
+  // all-reduce of their result buffer
+  nccl_comm_t comm = nullptr;
+  int comm_rank = 0, comm_world = 1;
 };
 
 namespace {
@@ -246,6 +258,18 @@ int fail(sxc_ctx* c, int code, const char* fmt, ...) {
     if (rc_ != SXC_OK) return rc_; \
   } while (0)
 
+// handles are slots of a vector; released slots (sxc_release_*) are reused
+template <class T>
+int store_handle(std::vector<std::unique_ptr<T>>& v, std::unique_ptr<T> obj) {
+  for (size_t i = 0; i < v.size(); ++i)
+    if (!v[i]) {
+      v[i] = std::move(obj);
+      return (int)i;
+    }
+  v.push_back(std::move(obj));
+  return (int)v.size() - 1;
+}
+
 Grid* get_grid(sxc_ctx* ctx, int h) { return (h >= 0 && h < (int)ctx->grids.size()) ? ctx->grids[h].get() : nullptr; }
 Basis* get_basis(sxc_ctx* ctx, int h) { return (h >= 0 && h < (int)ctx->bases.size()) ? ctx->bases[h].get() : nullptr; }
 
@@ -259,9 +283,21 @@ int set_kernel_attrs(sxc_ctx* ctx) {
   return SXC_OK;
 }
 
-// P is first read by the density phase: a pending upload (sxc_set_p_ready_event / host-buffer entry points) is
-// awaited only there, so that it overlaps with the screening and basis kernels
+// P is first read by the density phase: an upload handed over by the caller (sxc_set_p_ready_event) or pending from a host-buffer
+// entry point is started / awaited only there.  For caller-owned (pageable) host memory cudaMemcpyAsync blocks the host while the
+// driver stages the data; issued here, behind the launches of the screening and basis kernels, that host time and the DMA on the
+// side stream overlap with those kernels.
 int wait_p_ready(sxc_ctx* ctx) {
+  if (!ctx->pending.empty()) {
+    if (!ctx->copy_stream) {
+      CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
+    }
+    for (const auto& u : ctx->pending) CU(cudaMemcpyAsync(u.dst, u.src, u.bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    ctx->pending.clear();
+    CU(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
+    ctx->p_ready = ctx->copy_done;
+  }
   if (ctx->p_ready) {
     cudaEvent_t ev = ctx->p_ready;
     ctx->p_ready = nullptr;
@@ -270,20 +306,35 @@ int wait_p_ready(sxc_ctx* ctx) {
   return SXC_OK;
 }
 
-// host-buffer entry points: upload on a side stream, hand its completion event to the build
+// host-buffer entry points: queue the upload (the staging buffer ctx->dP is free: the previous host call synchronised)
 int upload_async(sxc_ctx* ctx, void* dst, const void* src, size_t bytes) {
-  if (!ctx->copy_stream) {
-    CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    CU(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
+  ctx->pending.push_back({dst, src, bytes});
+  return SXC_OK;
+}
+int upload_done(sxc_ctx*) { return SXC_OK; }
+
+// error path of the host-buffer entry points: no armed upload event, no copy in flight, no uncollected time stamps survive
+int abort_build(sxc_ctx* ctx, int rc) {
+  ctx->p_ready = nullptr;
+  ctx->pending.clear();
+  ctx->timing = 0;
+  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& st : ctx->stamps) {
+    ctx->event_pool.push_back(st.a);
+    ctx->event_pool.push_back(st.b);
   }
-  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
-  return SXC_OK;
+  ctx->stamps.clear();
+  return rc;
 }
-int upload_done(sxc_ctx* ctx) {
-  CU(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
-  ctx->p_ready = ctx->copy_done;
-  return SXC_OK;
-}
+
+// scope guard of the host-buffer entry points: an upload that the build never consumed (early error return) is withdrawn
+struct HostCall {
+  sxc_ctx* c;
+  ~HostCall() {
+    if (!c->pending.empty() || c->p_ready) abort_build(c, 0);
+  }
+};
 
 cudaEvent_t take_event(sxc_ctx* ctx) {
   cudaEvent_t e = nullptr;
@@ -302,7 +353,7 @@ struct PhaseTimer {
   int slot;
   cudaEvent_t a = nullptr;
   PhaseTimer(sxc_ctx* c, int s) : ctx(c), slot(s) {
-    if (ctx->timing) {
+    if (ctx->timing >= (s == SXC_T_COUNT ? 1 : 2)) {
       a = take_event(ctx);
       cudaEventRecord(a, ctx->stream);
     }
@@ -317,7 +368,10 @@ struct PhaseTimer {
 };
 constexpr int T_TOTAL = SXC_T_COUNT;  // pseudo slot of the whole build
 
-void begin_timing(sxc_ctx* ctx, bool on) {
+// host-buffer entry points always know the device time of the whole build (two events); per-kernel events are opt-in
+int timing_mode(const sxc_ctx* ctx, bool host_call) { return ctx->timing_device ? 2 : (host_call ? 1 : 0); }
+
+void begin_timing(sxc_ctx* ctx, int on) {
   for (auto& st : ctx->stamps) {
     ctx->event_pool.push_back(st.a);
     ctx->event_pool.push_back(st.b);
@@ -346,6 +400,20 @@ void collect_timers(sxc_ctx* ctx) {
     ctx->event_pool.push_back(t.b);
   }
   ctx->stamps.clear();
+}
+
+// The one collective of the path: the partial [V | E | N ...] of the ranks' block ranges are summed in
+// place, on the build's stream, right behind its last kernel.
+int allreduce_result(sxc_ctx* ctx, const Grid& g, double* buf, size_t count) {
+  if (!ctx->comm || g.world == 1) return SXC_OK;
+  if (g.world != ctx->comm_world || g.rank != ctx->comm_rank)
+    return fail(ctx, SXC_ERR_INVALID, "grid shard %d/%d does not match the communicator's rank %d/%d", g.rank, g.world,
+                ctx->comm_rank, ctx->comm_world);
+  PhaseTimer t(ctx, SXC_T_ALLREDUCE);
+  const int rc = nccl().AllReduce(buf, buf, count, NCCL_DOUBLE, NCCL_SUM, ctx->comm, ctx->stream);
+  if (rc != NCCL_SUCCESS) return fail(ctx, SXC_ERR_CUDA, "ncclAllReduce failed: %s", nccl().GetErrorString(rc));
+  ++ctx->collectives;
+  return SXC_OK;
 }
 
 // ---------------------------------------------------------------------------------------------- plan
@@ -623,7 +691,7 @@ int get_plan(sxc_ctx* ctx, int gh, int bh, Plan** out, int comps = TILE_COMPS) {
 }
 
 // per-point SoA arrays: rows rho, gx, gy, gz per spin ([4 * nspin][N])
-int ensure_point_arrays(sxc_ctx* ctx, Grid& g, bool nadd, int nspin) {
+int ensure_point_arrays(sxc_ctx* ctx, Grid& g, bool nadd, int nspin, int nparts = 3) {
   const size_t n4 = (size_t)4 * nspin * std::max<long>(g.npts, 1) * sizeof(double);
   if (g.dens.bytes < n4) {
     CU(g.dens.ensure(n4));
@@ -633,7 +701,7 @@ int ensure_point_arrays(sxc_ctx* ctx, Grid& g, bool nadd, int nspin) {
     CU(g.pot.ensure(n4));
     CU(cudaMemsetAsync(g.pot.p, 0, n4, ctx->stream));
   }
-  CU(g.parts.ensure((size_t)3 * std::max(g.nlit, 1) * sizeof(double)));
+  CU(g.parts.ensure((size_t)std::max(3, nparts) * std::max(g.nlit, 1) * sizeof(double)));
   if (nadd) {
     if (g.tot.bytes < n4) {
       CU(g.tot.ensure(n4));
@@ -817,7 +885,7 @@ int build_xc_device(sxc_ctx* ctx, int gh, int bh, int fh, int nspin, const doubl
   const FuncView f = ctx->funcs[fh];
   TRY(ensure_point_arrays(ctx, g, false, nspin));
   ctx->stats = p.stats;
-  begin_timing(ctx, timed || ctx->timing_device);
+  begin_timing(ctx, timing_mode(ctx, timed));
   const int launches0 = ctx->launches;
   const size_t nb2 = (size_t)b.nbf * b.nbf;
   const long N = g.npts;
@@ -846,8 +914,9 @@ int build_xc_device(sxc_ctx* ctx, int gh, int bh, int fh, int nspin, const doubl
     for (int sp = 0; sp < nspin; ++sp) TRY(finish_matrix(ctx, b.nbf, dVEN + sp * nb2));
     TRY(reduce_to(ctx, parts, g.nlit, dVEN + nspin * nb2));
     TRY(reduce_to(ctx, parts + g.nlit, g.nlit, dVEN + nspin * nb2 + 1));
+    TRY(allreduce_result(ctx, g, dVEN, nspin * nb2 + 2));
   }
-  ctx->timing = false;
+  ctx->timing = 0;
   ctx->stats.kernel_launches = ctx->launches - launches0;
   return SXC_OK;
 }
@@ -864,16 +933,37 @@ __global__ void k_add4(long N, int blocksize, int ncomp, const int* __restrict__
     }
 }
 
-int build_nadd_device(sxc_ctx* ctx, int gh, int fh, int nspin, int bA, const double* dPA, int nenv, const int* bE,
-                      const double* const* dPE, int frozen, double thr, double* dVE, bool timed) {
+std::vector<int> env_cache_key(int nenv, const int* bE, int nspin, int tag) {
+  std::vector<int> key(bE, bE + nenv);
+  key.push_back(nspin);
+  key.push_back(tag);
+  return key;
+}
+// the grid holds sum rho_env of exactly this environment state and E[rho_env_i] of every requested functional
+bool env_cache_hit(const Grid& g, int nfunc, const int* fhs, int nenv, const int* bE, int nspin, int tag) {
+  if (!tag || !g.env_valid || g.env_key != env_cache_key(nenv, bE, nspin, tag)) return false;
+  for (int k = 0; k < nfunc; ++k)
+    if (!g.env_energy.count(fhs[k])) return false;
+  return true;
+}
+
+// One device pass for nfunc functionals on the same densities (FDEPotentials::getFockMatrix, potentials/bundles/FDEPotentials.cpp:43-61,
+// adds the non-additive XC and the non-additive kinetic potential of the same active / environment densities): rho_act and
+// sum rho_env are built ONCE; per functional the energies E[rho_tot], E[rho_act], E[rho_env_i] are kept apart.
+//   sum_mode != 0: the potentials are summed on the grid and scattered once      -> dVE = [nspin nbA^2 | nfunc x (2 + nenv)]
+//   sum_mode == 0: one scatter per functional, every object gets its own matrix   -> dVE = [nfunc x nspin nbA^2 | nfunc x (2 + nenv)]
+// nfunc == 1 is NAddFuncPotential<SCFMode>::getMatrix + getEnergy (NAddFuncPotential.cpp:192-326).
+int build_nadd_device(sxc_ctx* ctx, int gh, int nfunc, const int* fhs, int nspin, int bA, const double* dPA, int nenv,
+                      const int* bE, const double* const* dPE, int frozen, double thr, int sum_mode, double* dVE, bool timed) {
   if (nspin != 1 && nspin != 2) return fail(ctx, SXC_ERR_INVALID, "nspin must be 1 (RESTRICTED) or 2 (UNRESTRICTED)");
-  if (fh < 0 || fh >= (int)ctx->funcs.size()) return fail(ctx, SXC_ERR_INVALID, "invalid functional handle %d", fh);
+  if (nfunc < 1 || nfunc > 8) return fail(ctx, SXC_ERR_INVALID, "1 to 8 functionals per pass");
+  for (int k = 0; k < nfunc; ++k)
+    if (fhs[k] < 0 || fhs[k] >= (int)ctx->funcs.size()) return fail(ctx, SXC_ERR_INVALID, "invalid functional handle %d", fhs[k]);
   if (nenv < 0) return fail(ctx, SXC_ERR_INVALID, "nenv < 0");
   Grid* gp = get_grid(ctx, gh);
   Basis* ba = get_basis(ctx, bA);
   if (!gp || !ba) return fail(ctx, SXC_ERR_INVALID, "invalid grid or active basis handle");
   Grid& g = *gp;
-  const FuncView f = ctx->funcs[fh];
   Plan* pa = nullptr;
   TRY(get_plan(ctx, gh, bA, &pa));  // the active system fixes the block ownership
   for (int i = 0; i < nenv; ++i) {
@@ -881,40 +971,50 @@ int build_nadd_device(sxc_ctx* ctx, int gh, int fh, int nspin, int bA, const dou
     if (!get_basis(ctx, bE[i])) return fail(ctx, SXC_ERR_INVALID, "invalid environment basis handle %d", bE[i]);
     TRY(get_plan(ctx, gh, bE[i], &pe));
   }
-  TRY(ensure_point_arrays(ctx, g, true, nspin));
+  TRY(ensure_point_arrays(ctx, g, true, nspin, 2 * nfunc));
   CU(ctx->scratch.ensure(64 * sizeof(double)));
   const long N = g.npts;
   const int ncomp = 4 * nspin;
+  const int nlit = std::max(g.nlit, 1);
   const size_t nb2 = (size_t)ba->nbf * ba->nbf;
+  const int nmat = sum_mode ? 1 : nfunc;
+  const size_t nV = (size_t)nmat * nspin * nb2;
+  const int ne = 2 + nenv;  // energies per functional
   double* parts = g.parts.as<double>();
   double* dens = g.dens.as<double>();
   double* pot = g.pot.as<double>();
   ctx->stats = pa->stats;
-  begin_timing(ctx, timed || ctx->timing_device);
+  begin_timing(ctx, timing_mode(ctx, timed));
   const int launches0 = ctx->launches;
+  bool any_gga = false, any_comp = false;
+  for (int k = 0; k < nfunc; ++k) {
+    any_gga |= ctx->funcs[fhs[k]].gga != 0;
+    any_comp |= ctx->funcs[fhs[k]].ncomp > 0;
+  }
   {
     PhaseTimer t_all(ctx, T_TOTAL);
-    CU(cudaMemsetAsync(dVE, 0, (nspin * nb2 + 2 + nenv) * sizeof(double), ctx->stream));
+    CU(cudaMemsetAsync(dVE, 0, (nV + (size_t)nfunc * ne) * sizeof(double), ctx->stream));
     TRY(wait_p_ready(ctx));
 
     // environment: rho_env on the supersystem grid, summed; E[rho_env_i] (NAddEnergyHelper, NAddFuncPotential.cpp:502-516)
     // (the summed density does not depend on the functional, the environment energies do: a functional seen for the first time
-    // with a frozen environment repeats the pass once, afterwards both of an iteration's NAdd objects are served from the cache)
-    std::vector<int> key(bE, bE + nenv);
-    key.push_back(nspin);
+    // with a frozen environment repeats the pass once, afterwards all NAdd objects of an iteration are served from the cache).
+    // The cache is per grid; `frozen` is the caller's tag of the environment STATE (any non-zero value): two NAdd objects on
+    // one grid whose environments share basis handles but hold different densities must use different tags.
+    const std::vector<int> key = env_cache_key(nenv, bE, nspin, frozen);
     const bool same_env = frozen && g.env_valid && g.env_key == key;
-    const bool reuse = same_env && g.env_energy.count(fh) != 0;
+    const bool reuse = env_cache_hit(g, nfunc, fhs, nenv, bE, nspin, frozen);
     if (!same_env) g.env_energy.clear();
     if (!reuse) {
       CU(cudaMemsetAsync(g.envsum.p, 0, (size_t)ncomp * N * sizeof(double), ctx->stream));
-      std::vector<double>& env_e = g.env_energy[fh];
-      env_e.assign(nenv, 0.0);
+      for (int k = 0; k < nfunc; ++k) g.env_energy[fhs[k]].assign(nenv, 0.0);
+      if ((size_t)nenv * nfunc > 64) return fail(ctx, SXC_ERR_UNSUPPORTED, "more than 64 environment energies per pass");
       for (int i = 0; i < nenv; ++i) {
         Basis* be = get_basis(ctx, bE[i]);
         const size_t ne2 = (size_t)be->nbf * be->nbf;
         Plan* pe = nullptr;
         TRY(get_plan(ctx, gh, bE[i], &pe));
-        CU(cudaMemsetAsync(parts, 0, (size_t)3 * std::max(g.nlit, 1) * sizeof(double), ctx->stream));
+        CU(cudaMemsetAsync(parts, 0, (size_t)nfunc * nlit * sizeof(double), ctx->stream));
         TRY(run_screen(ctx, g, *be, *pe));
         for (const Chunk& c : pe->chunks) {
           TRY(phase_basis(ctx, g, *be, *pe, c));
@@ -927,24 +1027,32 @@ int build_nadd_device(sxc_ctx* ctx, int gh, int fh, int nspin, int bA, const dou
             LAUNCH_CHECK();
           }
           // energy only: the potential goes to g.pot and is overwritten later
-          TRY(phase_functional(ctx, g, *pe, c, f, nspin, dens, 1.0, 0, pot, parts, nullptr));
+          for (int k = 0; k < nfunc; ++k)
+            TRY(phase_functional(ctx, g, *pe, c, ctx->funcs[fhs[k]], nspin, dens, 1.0, 0, pot, parts + (size_t)k * nlit, nullptr));
         }
-        TRY(reduce_to(ctx, parts, g.nlit, ctx->scratch.as<double>() + i));
+        for (int k = 0; k < nfunc; ++k)
+          TRY(reduce_to(ctx, parts + (size_t)k * nlit, g.nlit, ctx->scratch.as<double>() + (size_t)k * nenv + i));
       }
       if (nenv > 0) {
-        CU(cudaMemcpyAsync(env_e.data(), ctx->scratch.p, nenv * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        std::vector<double> h((size_t)nenv * nfunc);
+        CU(cudaMemcpyAsync(h.data(), ctx->scratch.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
+        for (int k = 0; k < nfunc; ++k)
+          for (int i = 0; i < nenv; ++i) g.env_energy[fhs[k]][i] = h[(size_t)k * nenv + i];
       }
       g.env_key = key;
       g.env_valid = true;
     }
     if (nenv > 0)
-      CU(cudaMemcpyAsync(dVE + nspin * nb2 + 2, g.env_energy[fh].data(), nenv * sizeof(double), cudaMemcpyHostToDevice,
-                         ctx->stream));
+      for (int k = 0; k < nfunc; ++k)
+        CU(cudaMemcpyAsync(dVE + nV + (size_t)k * ne + 2, g.env_energy[fhs[k]].data(), nenv * sizeof(double),
+                           cudaMemcpyHostToDevice, ctx->stream));
 
     // active system: rho_A, rho_tot = rho_A + sum_env, v = v[rho_tot] - v[rho_A]  (NAddFuncPotential.cpp:197-225)
     Plan& p = *pa;
-    CU(cudaMemsetAsync(parts, 0, (size_t)3 * std::max(g.nlit, 1) * sizeof(double), ctx->stream));
+    CU(cudaMemsetAsync(parts, 0, (size_t)2 * nfunc * nlit * sizeof(double), ctx->stream));
+    if (sum_mode && nfunc > 1)  // summed potential: every functional accumulates (an LDA one leaves the gradient rows alone)
+      CU(cudaMemsetAsync(pot, 0, (size_t)ncomp * N * sizeof(double), ctx->stream));
     const bool cached = tiles_cached(ctx, p);  // (frozen environment: the active system's tiles survive from call to call)
     if (!cached) TRY(run_screen(ctx, g, *ba, p));
     for (const Chunk& c : p.chunks) {
@@ -957,17 +1065,28 @@ int build_nadd_device(sxc_ctx* ctx, int gh, int fh, int nspin, int bA, const dou
                                                   g.envsum.as<double>(), g.tot.as<double>());
         LAUNCH_CHECK();
       }
-      TRY(phase_functional(ctx, g, p, c, f, nspin, g.tot.as<double>(), 1.0, 0, pot, parts, nullptr));
-      TRY(phase_functional(ctx, g, p, c, f, nspin, dens, -1.0, 1, pot, parts + g.nlit, nullptr));
-      if (f.ncomp > 0)
+      for (int k = 0; k < nfunc; ++k) {
+        const FuncView f = ctx->funcs[fhs[k]];
+        const int acc0 = (sum_mode && nfunc > 1) ? 1 : 0;
+        TRY(phase_functional(ctx, g, p, c, f, nspin, g.tot.as<double>(), 1.0, acc0, pot, parts + (size_t)(2 * k) * nlit, nullptr));
+        TRY(phase_functional(ctx, g, p, c, f, nspin, dens, -1.0, 1, pot, parts + (size_t)(2 * k + 1) * nlit, nullptr));
+        if (!sum_mode && f.ncomp > 0)
+          for (int sp = 0; sp < nspin; ++sp)
+            TRY(phase_scatter(ctx, g, *ba, p, c, f.gga != 0, thr, pot + (size_t)4 * sp * N,
+                              dVE + ((size_t)k * nspin + sp) * nb2));
+      }
+      if (sum_mode && any_comp)
         for (int sp = 0; sp < nspin; ++sp)
-          TRY(phase_scatter(ctx, g, *ba, p, c, f.gga != 0, thr, pot + (size_t)4 * sp * N, dVE + sp * nb2));
+          TRY(phase_scatter(ctx, g, *ba, p, c, any_gga, thr, pot + (size_t)4 * sp * N, dVE + sp * nb2));
     }
-    for (int sp = 0; sp < nspin; ++sp) TRY(finish_matrix(ctx, ba->nbf, dVE + sp * nb2));
-    TRY(reduce_to(ctx, parts, g.nlit, dVE + nspin * nb2));
-    TRY(reduce_to(ctx, parts + g.nlit, g.nlit, dVE + nspin * nb2 + 1));
+    for (int m = 0; m < nmat * nspin; ++m) TRY(finish_matrix(ctx, ba->nbf, dVE + (size_t)m * nb2));
+    for (int k = 0; k < nfunc; ++k) {
+      TRY(reduce_to(ctx, parts + (size_t)(2 * k) * nlit, g.nlit, dVE + nV + (size_t)k * ne));
+      TRY(reduce_to(ctx, parts + (size_t)(2 * k + 1) * nlit, g.nlit, dVE + nV + (size_t)k * ne + 1));
+    }
+    TRY(allreduce_result(ctx, g, dVE, nV + (size_t)nfunc * ne));
   }
-  ctx->timing = false;
+  ctx->timing = 0;
   ctx->stats.kernel_launches = ctx->launches - launches0;
   return SXC_OK;
 }
@@ -996,7 +1115,7 @@ int build_gradient_device(sxc_ctx* ctx, int gh, int bh, int fh, int nspin, const
   }
   TRY(ensure_point_arrays(ctx, g, nadd, nspin));
   ctx->stats = p.stats;
-  begin_timing(ctx, ctx->timing_device);
+  begin_timing(ctx, timing_mode(ctx, false));
   const int launches0 = ctx->launches;
   const size_t nb2 = (size_t)b.nbf * b.nbf;
   const long N = g.npts;
@@ -1074,8 +1193,9 @@ int build_gradient_device(sxc_ctx* ctx, int gh, int bh, int fh, int nspin, const
         }
       }
     }
+    TRY(allreduce_result(ctx, g, d_gfunc, (size_t)b.nbf * 3));
   }
-  ctx->timing = false;
+  ctx->timing = 0;
   ctx->stats.kernel_launches = ctx->launches - launches0;
   return SXC_OK;
 }
@@ -1111,7 +1231,7 @@ int build_ab_device(sxc_ctx* ctx, int gh, int fh, int nspin, int bA, int bB, int
   double* tot = g.tot.as<double>();
   double* pot = g.pot.as<double>();
   ctx->stats = pa->stats;
-  begin_timing(ctx, true);
+  begin_timing(ctx, timing_mode(ctx, true));
   const int launches0 = ctx->launches;
   {
     PhaseTimer t_all(ctx, T_TOTAL);
@@ -1148,8 +1268,9 @@ int build_ab_device(sxc_ctx* ctx, int gh, int fh, int nspin, int bA, int bB, int
     }
     TRY(reduce_to(ctx, parts, g.nlit, dVE + nspin * nab));
     TRY(reduce_to(ctx, parts + g.nlit, g.nlit, dVE + nspin * nab + 1));
+    TRY(allreduce_result(ctx, g, dVE, nspin * nab + 2));
   }
-  ctx->timing = false;
+  ctx->timing = 0;
   ctx->stats.kernel_launches = ctx->launches - launches0;
   return SXC_OK;
 }
@@ -1183,7 +1304,7 @@ int build_ab_nadd_device(sxc_ctx* ctx, int gh, int fh, int nspin, int bA, int bB
   double* tot = g.tot.as<double>();
   double* pot = g.pot.as<double>();
   ctx->stats = pa->stats;
-  begin_timing(ctx, true);
+  begin_timing(ctx, timing_mode(ctx, true));
   const int launches0 = ctx->launches;
   {
     PhaseTimer t_all(ctx, T_TOTAL);
@@ -1224,8 +1345,9 @@ int build_ab_nadd_device(sxc_ctx* ctx, int gh, int fh, int nspin, int bA, int bB
       for (int sp = 0; sp < nspin; ++sp)
         TRY(phase_scatter_ab(ctx, g, ba, *pa, *pb, f.gga != 0, thr, pot + (size_t)4 * sp * N, dV + sp * nab));
     }
+    TRY(allreduce_result(ctx, g, dV, nspin * nab));
   }
-  ctx->timing = false;
+  ctx->timing = 0;
   ctx->stats.kernel_launches = ctx->launches - launches0;
   return SXC_OK;
 }
@@ -1289,6 +1411,7 @@ void sxc_destroy(sxc_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm) nccl().CommDestroy(ctx->comm);
   ctx->plans.clear();
   ctx->grids.clear();
   ctx->bases.clear();
@@ -1346,8 +1469,11 @@ int sxc_set_grid(sxc_ctx* ctx, int64_t npts, const double* xyz, const double* w,
   CU(g->xyzw.ensure(soa.size() * sizeof(double)));
   CU(cudaMemcpyAsync(g->xyzw.p, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  ctx->grids.push_back(std::move(g));
-  *grid = (int)ctx->grids.size() - 1;
+  if (ctx->comm && blocksize == FUNC_BLOCK) {  // a context with a communicator evaluates its own shard of every grid
+    g->rank = ctx->comm_rank;
+    g->world = ctx->comm_world;
+  }
+  *grid = store_handle(ctx->grids, std::move(g));
   return SXC_OK;
 }
 
@@ -1402,8 +1528,7 @@ int sxc_add_basis(sxc_ctx* ctx, int nshell, const int* l, const int* pure, const
   CU(cudaMemcpyAsync(b->ints.p, ints.data(), ints.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(b->dbl.p, d.data(), d.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  ctx->bases.push_back(std::move(b));
-  *basis = (int)ctx->bases.size() - 1;
+  *basis = store_handle(ctx->bases, std::move(b));
   return SXC_OK;
 }
 
@@ -1421,8 +1546,124 @@ int sxc_set_functional(sxc_ctx* ctx, int ncomp, const int* ids, const double* mi
     f.gga |= functional_id_is_gga(ids[i]) ? 1 : 0;
     ++f.ncomp;
   }
+  // identical definitions share one handle (FunctionalLibrary::calcData asks per call; handles never pile up)
+  for (size_t i = 0; i < ctx->funcs.size(); ++i) {
+    const FuncView& o = ctx->funcs[i];
+    bool same = o.ncomp == f.ncomp && o.gga == f.gga;
+    for (int k = 0; same && k < f.ncomp; ++k) same = o.id[k] == f.id[k] && o.mix[k] == f.mix[k];
+    if (same) {
+      *func = (int)i;
+      return SXC_OK;
+    }
+  }
   ctx->funcs.push_back(f);
   *func = (int)ctx->funcs.size() - 1;
+  return SXC_OK;
+}
+
+namespace {
+// plans (screening lists, work items) that involve a released grid or basis go with it; tiles in the workspace lose their owner
+void drop_plans(sxc_ctx* ctx, int grid, int basis) {
+  for (auto it = ctx->plans.begin(); it != ctx->plans.end();) {
+    const Plan& p = *it->second;
+    if ((grid >= 0 && p.grid == grid) || (basis >= 0 && p.basis == basis)) {
+      if (ctx->phi_owner == p.serial) ctx->phi_owner = 0;
+      it = ctx->plans.erase(it);
+    } else {
+      ++it;
+    }
+  }
+}
+}  // namespace
+
+int sxc_release_grid(sxc_ctx* ctx, int grid) {
+  if (!ctx || !get_grid(ctx, grid)) return fail(ctx, SXC_ERR_INVALID, "sxc_release_grid: invalid grid handle %d", grid);
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  drop_plans(ctx, grid, -1);
+  for (auto& ks : ctx->kstores)
+    if (ks && ks->grid == grid) ks.reset();
+  ctx->grids[grid].reset();  // frees the points, the per-point work arrays and the cached environment density
+  return SXC_OK;
+}
+
+int sxc_release_basis(sxc_ctx* ctx, int basis) {
+  if (!ctx || !get_basis(ctx, basis)) return fail(ctx, SXC_ERR_INVALID, "sxc_release_basis: invalid basis handle %d", basis);
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  drop_plans(ctx, -1, basis);
+  for (auto& g : ctx->grids)  // a cached environment density that was built with this basis is no longer identifiable
+    if (g && std::find(g->env_key.begin(), g->env_key.end(), basis) != g->env_key.end()) g->env_valid = false;
+  ctx->bases[basis].reset();
+  return SXC_OK;
+}
+
+int sxc_release_functional(sxc_ctx* ctx, int func) {
+  if (!ctx || func < 0 || func >= (int)ctx->funcs.size())
+    return fail(ctx, SXC_ERR_INVALID, "sxc_release_functional: invalid functional handle %d", func);
+  return SXC_OK;  // definitions are a few bytes, shared between equal requests and kept until sxc_destroy
+}
+
+// page-locked host memory for callers that can place P / V in it (the copies of the host-buffer builds are then true DMA)
+void* sxc_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  return cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? p : nullptr;
+}
+void sxc_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+// ---- multi-GPU --------------------------------------------------------------------------------------------------
+int sxc_comm_unique_id(void* id128) {
+  if (!id128) return SXC_ERR_INVALID;
+  if (!nccl().load()) return SXC_ERR_UNSUPPORTED;
+  nccl_unique_id id;
+  if (nccl().GetUniqueId(&id) != NCCL_SUCCESS) return SXC_ERR_CUDA;
+  std::memcpy(id128, &id, sizeof(id));
+  return SXC_OK;
+}
+
+int sxc_comm_init_rank(sxc_ctx* ctx, int rank, int world, const void* id128) {
+  if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world) return fail(ctx, SXC_ERR_INVALID, "sxc_comm_init_rank: bad arguments");
+  if (ctx->comm) return fail(ctx, SXC_ERR_INVALID, "sxc_comm_init_rank: the context already has a communicator");
+  if (!nccl().load()) return fail(ctx, SXC_ERR_UNSUPPORTED, "%s", nccl().error.c_str());
+  CU(cudaSetDevice(ctx->device));
+  nccl_unique_id id;
+  std::memcpy(&id, id128, sizeof(id));
+  const int rc = nccl().CommInitRank(&ctx->comm, world, id, rank);
+  if (rc != NCCL_SUCCESS) {
+    ctx->comm = nullptr;
+    return fail(ctx, SXC_ERR_CUDA, "ncclCommInitRank failed: %s", nccl().GetErrorString(rc));
+  }
+  ctx->comm_rank = rank;
+  ctx->comm_world = world;
+  for (size_t gh = 0; gh < ctx->grids.size(); ++gh)  // grids that are already there become shards
+    if (ctx->grids[gh] && ctx->grids[gh]->blocksize == FUNC_BLOCK) TRY(sxc_set_grid_shard(ctx, (int)gh, rank, world));
+  return SXC_OK;
+}
+
+int sxc_comm_destroy(sxc_ctx* ctx) {
+  if (!ctx) return SXC_ERR_INVALID;
+  if (ctx->comm) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    nccl().CommDestroy(ctx->comm);
+    ctx->comm = nullptr;
+    ctx->comm_rank = 0;
+    ctx->comm_world = 1;
+  }
+  return SXC_OK;
+}
+
+int sxc_comm_info(sxc_ctx* ctx, int* rank, int* world, int64_t* collectives, int* nccl_version) {
+  if (!ctx) return SXC_ERR_INVALID;
+  if (rank) *rank = ctx->comm_rank;
+  if (world) *world = ctx->comm_world;
+  if (collectives) *collectives = ctx->collectives;
+  if (nccl_version) {
+    *nccl_version = 0;
+    if (ctx->comm) nccl().GetVersion(nccl_version);
+  }
   return SXC_OK;
 }
 
@@ -1435,7 +1676,7 @@ int sxc_build_xc_device(sxc_ctx* ctx, int grid, int basis, int func, int nspin, 
 
 int sxc_build_xc(sxc_ctx* ctx, int grid, int basis, int func, int nspin, const double* P, double thr, double* V,
                  double* E, double* nelec) {
-  if (!ctx || !P || !V || !E) return fail(ctx, SXC_ERR_INVALID, "sxc_build_xc: bad arguments");
+  if (!ctx || !P || !E) return fail(ctx, SXC_ERR_INVALID, "sxc_build_xc: bad arguments");
   if (nspin != 1 && nspin != 2) return fail(ctx, SXC_ERR_INVALID, "nspin must be 1 or 2");
   Basis* b = get_basis(ctx, basis);
   if (!b) return fail(ctx, SXC_ERR_INVALID, "invalid basis handle %d", basis);
@@ -1443,13 +1684,14 @@ int sxc_build_xc(sxc_ctx* ctx, int grid, int basis, int func, int nspin, const d
   const size_t nv = (size_t)nspin * b->nbf * b->nbf;
   CU(ctx->dP.ensure(nv * sizeof(double)));
   CU(ctx->dOut.ensure((nv + 2) * sizeof(double)));
+  HostCall host_guard{ctx};
   TRY(upload_async(ctx, ctx->dP.p, P, nv * sizeof(double)));
   TRY(upload_done(ctx));
   int rc = build_xc_device(ctx, grid, basis, func, nspin, ctx->dP.as<double>(), thr, ctx->dOut.as<double>(), true);
-  ctx->timing = false;
-  if (rc != SXC_OK) return rc;
+  ctx->timing = 0;
+  if (rc != SXC_OK) return abort_build(ctx, rc);
   std::vector<double> tail(2);
-  CU(cudaMemcpyAsync(V, ctx->dOut.p, nv * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (V) CU(cudaMemcpyAsync(V, ctx->dOut.p, nv * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(tail.data(), ctx->dOut.as<double>() + nv, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   collect_timers(ctx);
@@ -1458,24 +1700,35 @@ int sxc_build_xc(sxc_ctx* ctx, int grid, int basis, int func, int nspin, const d
   return SXC_OK;
 }
 
-int sxc_build_nadd_device(sxc_ctx* ctx, int grid, int func, int nspin, int basis_act, const double* d_P_act, int nenv,
-                          const int* basis_env, const double* const* d_P_env, int env_frozen, double thr, double* d_VE) {
-  if (!ctx || !d_P_act || !d_VE || (nenv > 0 && (!basis_env || !d_P_env)))
-    return fail(ctx, SXC_ERR_INVALID, "sxc_build_nadd_device: bad arguments");
+int sxc_build_nadd_multi_device(sxc_ctx* ctx, int grid, int nfunc, const int* funcs, int nspin, int basis_act,
+                                const double* d_P_act, int nenv, const int* basis_env, const double* const* d_P_env,
+                                int env_frozen, double thr, int sum_matrices, double* d_VE) {
+  if (!ctx || !funcs || !d_P_act || !d_VE || (nenv > 0 && (!basis_env || !d_P_env)))
+    return fail(ctx, SXC_ERR_INVALID, "sxc_build_nadd_multi_device: bad arguments");
   CU(cudaSetDevice(ctx->device));
-  return build_nadd_device(ctx, grid, func, nspin, basis_act, d_P_act, nenv, basis_env, d_P_env, env_frozen, thr, d_VE,
-                           false);
+  return build_nadd_device(ctx, grid, nfunc, funcs, nspin, basis_act, d_P_act, nenv, basis_env, d_P_env, env_frozen, thr,
+                           sum_matrices, d_VE, false);
 }
 
-int sxc_build_nadd(sxc_ctx* ctx, int grid, int func, int nspin, int basis_act, const double* P_act, int nenv,
-                   const int* basis_env, const double* const* P_env, int env_frozen, double thr, double* V_act, double* E) {
-  if (!ctx || !P_act || !V_act || !E || nenv < 0 || (nenv > 0 && (!basis_env || !P_env)))
-    return fail(ctx, SXC_ERR_INVALID, "sxc_build_nadd: bad arguments");
+int sxc_build_nadd_device(sxc_ctx* ctx, int grid, int func, int nspin, int basis_act, const double* d_P_act, int nenv,
+                          const int* basis_env, const double* const* d_P_env, int env_frozen, double thr, double* d_VE) {
+  return sxc_build_nadd_multi_device(ctx, grid, 1, &func, nspin, basis_act, d_P_act, nenv, basis_env, d_P_env, env_frozen, thr,
+                                     0, d_VE);
+}
+
+int sxc_build_nadd_multi(sxc_ctx* ctx, int grid, int nfunc, const int* funcs, int nspin, int basis_act, const double* P_act,
+                         int nenv, const int* basis_env, const double* const* P_env, int env_frozen, double thr,
+                         int sum_matrices, double* V_act, double* E) {
+  if (!ctx || !funcs || !P_act || !E || nfunc < 1 || nenv < 0 || (nenv > 0 && (!basis_env || !P_env)))
+    return fail(ctx, SXC_ERR_INVALID, "sxc_build_nadd_multi: bad arguments");
   if (nspin != 1 && nspin != 2) return fail(ctx, SXC_ERR_INVALID, "nspin must be 1 or 2");
   Basis* ba = get_basis(ctx, basis_act);
-  if (!ba) return fail(ctx, SXC_ERR_INVALID, "invalid active basis handle %d", basis_act);
+  Grid* g = get_grid(ctx, grid);
+  if (!ba || !g) return fail(ctx, SXC_ERR_INVALID, "invalid grid (%d) or active basis (%d) handle", grid, basis_act);
   CU(cudaSetDevice(ctx->device));
   const size_t nvA = (size_t)nspin * ba->nbf * ba->nbf;
+  const size_t nV = (sum_matrices ? 1 : (size_t)nfunc) * nvA;
+  const size_t nE = (size_t)nfunc * (2 + nenv);
   size_t total = nvA;
   std::vector<size_t> offs(nenv);
   for (int i = 0; i < nenv; ++i) {
@@ -1485,24 +1738,32 @@ int sxc_build_nadd(sxc_ctx* ctx, int grid, int func, int nspin, int basis_act, c
     total += (size_t)nspin * be->nbf * be->nbf;
   }
   CU(ctx->dP.ensure(total * sizeof(double)));
-  CU(ctx->dOut.ensure((nvA + 2 + nenv) * sizeof(double)));
+  CU(ctx->dOut.ensure((nV + nE) * sizeof(double)));
+  HostCall host_guard{ctx};
   TRY(upload_async(ctx, ctx->dP.p, P_act, nvA * sizeof(double)));
+  // a frozen environment whose density and energies are cached on the grid is not uploaded again
+  const bool env_cached = env_cache_hit(*g, nfunc, funcs, nenv, basis_env, nspin, env_frozen);
   std::vector<const double*> dpe(nenv);
   for (int i = 0; i < nenv; ++i) {
     Basis* be = get_basis(ctx, basis_env[i]);
     dpe[i] = ctx->dP.as<double>() + offs[i];
-    TRY(upload_async(ctx, ctx->dP.as<double>() + offs[i], P_env[i], (size_t)nspin * be->nbf * be->nbf * sizeof(double)));
+    if (!env_cached)
+      TRY(upload_async(ctx, ctx->dP.as<double>() + offs[i], P_env[i], (size_t)nspin * be->nbf * be->nbf * sizeof(double)));
   }
-  TRY(upload_done(ctx));
-  int rc = build_nadd_device(ctx, grid, func, nspin, basis_act, ctx->dP.as<double>(), nenv, basis_env, dpe.data(),
-                             env_frozen, thr, ctx->dOut.as<double>(), true);
-  ctx->timing = false;
-  if (rc != SXC_OK) return rc;
-  CU(cudaMemcpyAsync(V_act, ctx->dOut.p, nvA * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaMemcpyAsync(E, ctx->dOut.as<double>() + nvA, (2 + nenv) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  int rc = build_nadd_device(ctx, grid, nfunc, funcs, nspin, basis_act, ctx->dP.as<double>(), nenv, basis_env, dpe.data(),
+                             env_frozen, thr, sum_matrices, ctx->dOut.as<double>(), true);
+  ctx->timing = 0;
+  if (rc != SXC_OK) return abort_build(ctx, rc);
+  if (V_act) CU(cudaMemcpyAsync(V_act, ctx->dOut.p, nV * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(E, ctx->dOut.as<double>() + nV, nE * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   collect_timers(ctx);
   return SXC_OK;
+}
+
+int sxc_build_nadd(sxc_ctx* ctx, int grid, int func, int nspin, int basis_act, const double* P_act, int nenv,
+                   const int* basis_env, const double* const* P_env, int env_frozen, double thr, double* V_act, double* E) {
+  return sxc_build_nadd_multi(ctx, grid, 1, &func, nspin, basis_act, P_act, nenv, basis_env, P_env, env_frozen, thr, 0, V_act, E);
 }
 
 int sxc_density_on_grid(sxc_ctx* ctx, int grid, int basis, const double* P, double* rho, double* gx, double* gy,
@@ -1749,6 +2010,7 @@ int sxc_build_ab(sxc_ctx* ctx, int grid, int func, int nspin, int basis_a, int b
   CU(ctx->dP.ensure(total * sizeof(double)));
   CU(ctx->dOut.ensure((nab + 2) * sizeof(double)));
   std::vector<const double*> dpc(ndens);
+  HostCall host_guard{ctx};
   for (int i = 0; i < ndens; ++i) {
     Basis* bc = get_basis(ctx, basis_c[i]);
     dpc[i] = ctx->dP.as<double>() + offs[i];
@@ -1756,8 +2018,8 @@ int sxc_build_ab(sxc_ctx* ctx, int grid, int func, int nspin, int basis_a, int b
   }
   TRY(upload_done(ctx));
   int rc = build_ab_device(ctx, grid, func, nspin, basis_a, basis_b, ndens, basis_c, dpc.data(), thr, ctx->dOut.as<double>());
-  ctx->timing = false;
-  if (rc != SXC_OK) return rc;
+  ctx->timing = 0;
+  if (rc != SXC_OK) return abort_build(ctx, rc);
   CU(cudaMemcpyAsync(V_ab, ctx->dOut.p, nab * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(E, ctx->dOut.as<double>() + nab, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
@@ -1786,6 +2048,7 @@ int sxc_build_ab_nadd(sxc_ctx* ctx, int grid, int func, int nspin, int basis_a, 
   }
   CU(ctx->dP.ensure(total * sizeof(double)));
   CU(ctx->dOut.ensure((nab + 2) * sizeof(double)));
+  HostCall host_guard{ctx};
   TRY(upload_async(ctx, ctx->dP.p, P_act, (size_t)nspin * bact->nbf * bact->nbf * sizeof(double)));
   std::vector<const double*> dpe(nenv);
   for (int i = 0; i < nenv; ++i) {
@@ -1796,8 +2059,8 @@ int sxc_build_ab_nadd(sxc_ctx* ctx, int grid, int func, int nspin, int basis_a, 
   TRY(upload_done(ctx));
   int rc = build_ab_nadd_device(ctx, grid, func, nspin, basis_a, basis_b, basis_act, ctx->dP.as<double>(), nenv, basis_env,
                                 dpe.data(), thr, ctx->dOut.as<double>());
-  ctx->timing = false;
-  if (rc != SXC_OK) return rc;
+  ctx->timing = 0;
+  if (rc != SXC_OK) return abort_build(ctx, rc);
   CU(cudaMemcpyAsync(V_ab, ctx->dOut.p, nab * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   collect_timers(ctx);
@@ -1835,6 +2098,7 @@ int sxc_xc_gradient(sxc_ctx* ctx, int grid, int basis, int func, int nspin, cons
   const size_t nv = (size_t)nspin * b->nbf * b->nbf;
   CU(ctx->dP.ensure(nv * sizeof(double)));
   CU(ctx->dOut.ensure((size_t)b->nbf * 3 * sizeof(double)));
+  HostCall host_guard{ctx};
   TRY(upload_async(ctx, ctx->dP.p, P, nv * sizeof(double)));
   TRY(upload_done(ctx));
   TRY(build_gradient_device(ctx, grid, basis, func, nspin, ctx->dP.as<double>(), ctx->dOut.as<double>()));
@@ -1893,9 +2157,15 @@ int sxc_partition_weights(sxc_ctx* ctx, int flavour, int becke_smoothing, int na
     CU(cudaFuncSetAttribute(k_partition_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t want = (npts + PW_WARPS - 1) / PW_WARPS;
   const int grid = (int)std::min<int64_t>(want, (int64_t)ctx->num_sms * 8);  // grid-stride over the points
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  CU(cudaEventCreate(&e0));
-  CU(cudaEventCreate(&e1));
+  struct PooledEvents {  // returned to the context's pool on every exit path
+    sxc_ctx* c;
+    cudaEvent_t a, b;
+    ~PooledEvents() {
+      c->event_pool.push_back(a);
+      c->event_pool.push_back(b);
+    }
+  } ev{ctx, take_event(ctx), take_event(ctx)};
+  cudaEvent_t e0 = ev.a, e1 = ev.b;
   CU(cudaEventRecord(e0, ctx->stream));
   k_partition_weights<<<grid, PW_WARPS * 32, smem, ctx->stream>>>(flavour, std::max(1, becke_smoothing), natoms, dc.as<double>(), da.as<double>(),
                                                                    aij ? daij.as<double>() : nullptr, dm.as<double>(),
@@ -1906,8 +2176,6 @@ int sxc_partition_weights(sxc_ctx* ctx, int flavour, int becke_smoothing, int na
   CU(cudaStreamSynchronize(ctx->stream));
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e0, e1);
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   ctx->last_partition_ms = ms;
   ctx->stats.kernel_launches += 1;
   return SXC_OK;
@@ -1936,6 +2204,7 @@ int sxc_nadd_gradient(sxc_ctx* ctx, int grid, int func, int nspin, int basis_act
   }
   CU(ctx->dP.ensure(total * sizeof(double)));
   CU(ctx->dOut.ensure((size_t)b->nbf * 3 * sizeof(double)));
+  HostCall host_guard{ctx};
   TRY(upload_async(ctx, ctx->dP.p, P_act, nvA * sizeof(double)));
   std::vector<const double*> dpe(nenv);
   for (int i = 0; i < nenv; ++i) {
@@ -2015,6 +2284,7 @@ int sxc_kernel_add(sxc_ctx* ctx, int kernel, int func, double sign, int ndens, c
     total += (size_t)nspin * bc->nbf * bc->nbf;
   }
   CU(ctx->dP.ensure(total * sizeof(double)));
+  HostCall host_guard{ctx};
   for (int i = 0; i < ndens; ++i) {
     Basis* bc = get_basis(ctx, basis_c[i]);
     TRY(upload_async(ctx, ctx->dP.as<double>() + offs[i], P_c[i], (size_t)nspin * bc->nbf * bc->nbf * sizeof(double)));
@@ -2025,7 +2295,7 @@ int sxc_kernel_add(sxc_ctx* ctx, int kernel, int func, double sign, int ndens, c
   const int ncomp = 4 * nspin;
   double* dens = g.dens.as<double>();
   double* tot = g.tot.as<double>();
-  begin_timing(ctx, true);
+  begin_timing(ctx, timing_mode(ctx, true));
   const int launches0 = ctx->launches;
   Plan* p0 = nullptr;
   TRY(get_plan(ctx, gh, basis_c[0], &p0));
@@ -2067,7 +2337,7 @@ int sxc_kernel_add(sxc_ctx* ctx, int kernel, int func, double sign, int ndens, c
       if (!lit_is_block) break;
     }
   }
-  ctx->timing = false;
+  ctx->timing = 0;
   ctx->stats.kernel_launches = ctx->launches - launches0;
   CU(cudaStreamSynchronize(ctx->stream));
   collect_timers(ctx);
@@ -2149,13 +2419,14 @@ int kernel_contract_impl(sxc_ctx* ctx, int grid, int basis_j, int nkern, const i
   DevMem& stage = D_host ? ctx->dP : ctx->dD;
   CU(stage.ensure((size_t)nvec * nspin * nb2 * sizeof(double)));
   double* dDs = stage.as<double>();
+  HostCall host_guard{ctx};
   if (D_host) {
     TRY(upload_async(ctx, dDs, D_host, (size_t)nvec * nspin * nb2 * sizeof(double)));
     TRY(upload_done(ctx));
   } else {  // the caller's matrices are left untouched: D += D^T works on the staged copy
     CU(cudaMemcpyAsync(dDs, D_dev, (size_t)nvec * nspin * nb2 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   }
-  begin_timing(ctx, sync || ctx->timing_device);
+  begin_timing(ctx, timing_mode(ctx, sync));
   ctx->stats = p.stats;
   const int launches0 = ctx->launches;
   {
@@ -2184,7 +2455,7 @@ int kernel_contract_impl(sxc_ctx* ctx, int grid, int basis_j, int nkern, const i
       }
     }
   }
-  ctx->timing = false;
+  ctx->timing = 0;
   ctx->stats.kernel_launches = ctx->launches - launches0;
   if (sync) {
     CU(cudaStreamSynchronize(ctx->stream));
@@ -2252,7 +2523,7 @@ int kernel_integrate_impl(sxc_ctx* ctx, int grid, int basis_i, double* F, double
     CU(ctx->dOut.ensure((nmat * nb2 + 2) * sizeof(double)));
     dF = ctx->dOut.as<double>();
   }
-  begin_timing(ctx, F != nullptr || ctx->timing_device);
+  begin_timing(ctx, timing_mode(ctx, F != nullptr));
   ctx->stats = p.stats;
   const int launches0 = ctx->launches;
   {
@@ -2269,8 +2540,9 @@ int kernel_integrate_impl(sxc_ctx* ctx, int grid, int basis_i, double* F, double
                           dF + m * nb2));
     }
     for (size_t m = 0; m < nmat; ++m) TRY(finish_matrix(ctx, b.nbf, dF + m * nb2));
+    TRY(allreduce_result(ctx, g, dF, nmat * nb2));
   }
-  ctx->timing = false;
+  ctx->timing = 0;
   ctx->stats.kernel_launches = ctx->launches - launches0;
   if (F) {
     CU(cudaMemcpyAsync(F, dF, nmat * nb2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

@@ -72,39 +72,41 @@ def geometry_of(name: str):
     raise ValueError("unknown geometry " + name)
 
 
-def make_config(name: str, acc: int | None = None) -> Config:
-    """name in {h2o, tetracene, water64, fde_dimer, fde_water64, peptide} (+ small test variants)."""
+def make_config(name: str, acc: int | None = None, grid=None) -> Config:
+    """name in {h2o, tetracene, water64, fde_dimer, fde_water64, peptide} (+ small test variants).
+    grid = (xyz, w): reuse an already generated grid of the same geometry and accuracy (water64 and fde_water64 share one)."""
     n = name.lower()
+    mg = molecular_grid if grid is None else (lambda *_a, **_k: grid)
     if n == "h2o":
         s, c = geo.water()
-        xyz, w = molecular_grid(s, c, acc or 4)
+        xyz, w = mg(s, c, acc or 4)
         return Config(n, "H2O PBE/def2-SVP, grid accuracy %d" % (acc or 4), "PBE", xyz, w, [_subsystem(s, c, "def2-svp", 7)])
     if n == "tetracene":
         s, c = geo.tetracene()
-        xyz, w = molecular_grid(s, c, acc or 6)
+        xyz, w = mg(s, c, acc or 6)
         return Config(n, "tetracene C18H12 B3LYP/def2-TZVP, grid accuracy %d" % (acc or 6), "B3LYP", xyz, w,
                       [_subsystem(s, c, "def2-tzvp", 7)])
     if n in ("water64", "water8", "water27"):
         side = {"water64": 4, "water27": 3, "water8": 2}[n]
         s, c = geo.water_cluster(side)
-        xyz, w = molecular_grid(s, c, acc or 4)
+        xyz, w = mg(s, c, acc or 4)
         return Config(n, "(H2O)%d PBE/def2-SVP, grid accuracy %d" % (side ** 3, acc or 4), "PBE", xyz, w,
                       [_subsystem(s, c, "def2-svp", 7)])
     if n == "fde_dimer":
         s, c = geo.water_dimer()
-        xyz, w = molecular_grid(s, c, acc or 4)
+        xyz, w = mg(s, c, acc or 4)
         return Config(n, "freeze-and-thaw FDE water dimer, PW91k + PBE, supersystem grid accuracy %d" % (acc or 4), "PBE",
                       xyz, w, [_subsystem(s[:3], c[:3], "def2-svp", 7), _subsystem(s[3:], c[3:], "def2-svp", 8)], "PW91K")
     if n in ("fde_water64", "fde_water8"):
         side = 4 if n == "fde_water64" else 2
         s, c = geo.water_cluster(side)
-        xyz, w = molecular_grid(s, c, acc or 4)
+        xyz, w = mg(s, c, acc or 4)
         h = len(s) // 2
         return Config(n, "freeze-and-thaw FDE (H2O)%d split in two halves, PW91k + PBE" % (side ** 3), "PBE", xyz, w,
                       [_subsystem(s[:h], c[:h], "def2-svp", 7), _subsystem(s[h:], c[h:], "def2-svp", 8)], "PW91K")
     if n == "peptide":
         s, c = geo.peptide_stand_in()
-        xyz, w = molecular_grid(s, c, acc or 6)
+        xyz, w = mg(s, c, acc or 6)
         return Config(n, "216-atom peptide stand-in PBE/def2-SVP, grid accuracy %d" % (acc or 6), "PBE", xyz, w,
                       [_subsystem(s, c, "def2-svp", 7)])
     raise ValueError("unknown config " + name)

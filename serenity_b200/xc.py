@@ -75,6 +75,8 @@ class XCContext:
         if getattr(self, "_h", None):
             self._lib.sxc_destroy(self._h)
             self._h = None
+            for ptr in self.__dict__.pop("_pinned", []):
+                self._lib.sxc_host_free(ptr)
 
     def __del__(self):
         try:
@@ -113,6 +115,40 @@ class XCContext:
     def set_grid_shard(self, grid: int, rank: int, world: int):
         self._check(self._lib.sxc_set_grid_shard(self._h, grid, rank, world))
 
+    def release_grid(self, grid: int):
+        self._check(self._lib.sxc_release_grid(self._h, grid))
+
+    def release_basis(self, basis: int):
+        self._check(self._lib.sxc_release_basis(self._h, basis))
+
+    # ---- multi-GPU: the communicator lives in the library (NCCL); only the 128-byte id travels through the caller
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = _lib.load().sxc_comm_unique_id(buf)
+        if rc != 0:
+            raise SerenityError("sxc_comm_unique_id failed (status %d): NCCL (libnccl.so.2) not loadable" % rc)
+        return buf.raw
+
+    def comm_init_rank(self, rank: int, world: int, unique_id: bytes):
+        """Every grid of this context becomes shard `rank` of `world`; builds return the sum over ranks (one all-reduce)."""
+        self._check(self._lib.sxc_comm_init_rank(self._h, int(rank), int(world), C.create_string_buffer(bytes(unique_id), 128)))
+
+    def comm_info(self) -> dict:
+        r, w, v, n = C.c_int(), C.c_int(), C.c_int(), C.c_int64()
+        self._check(self._lib.sxc_comm_info(self._h, C.byref(r), C.byref(w), C.byref(n), C.byref(v)))
+        return {"rank": r.value, "world": w.value, "collectives": n.value, "nccl_version": v.value}
+
+    def pinned_array(self, shape, order="F"):
+        """float64 array in page-locked memory (sxc_host_alloc); freed with the context."""
+        n = int(np.prod(shape))
+        ptr = self._lib.sxc_host_alloc(max(n, 1) * 8)
+        if not ptr:
+            raise SerenityError("sxc_host_alloc failed")
+        self.__dict__.setdefault("_pinned", []).append(ptr)
+        buf = (C.c_double * max(n, 1)).from_address(ptr)
+        return np.frombuffer(buf, dtype=np.float64, count=n).reshape(shape, order=order)
+
     def add_basis(self, tab, radial_threshold: float = 1e-9) -> int:
         arrs = [np.ascontiguousarray(a) for a in (tab.l, tab.pure, tab.nprim, tab.first_bf, tab.centre, tab.alpha,
                                                   tab.coeff, tab.normfac)]
@@ -141,6 +177,14 @@ class XCContext:
                                            C.byref(E), C.byref(ne)))
         return (_spin_unpack(V) if nspin == 2 else V), E.value, ne.value
 
+    def build_xc_into(self, grid, basis, func, P, V, block_ave_threshold: float = 1e-11, nspin: int = 1):
+        """sxc_build_xc on caller-owned host buffers (column-major float64 arrays, pageable or pinned): no allocation on the
+        way; V may be None on ranks of a communicator that do not need the matrix.  Returns (E, nelec)."""
+        E, ne = C.c_double(), C.c_double()
+        self._check(self._lib.sxc_build_xc(self._h, grid, basis, func, nspin, P.ctypes.data_as(C.c_void_p), block_ave_threshold,
+                                           None if V is None else V.ctypes.data_as(C.c_void_p), C.byref(E), C.byref(ne)))
+        return E.value, ne.value
+
     def build_xc_device(self, grid, basis, func, d_P_ptr: int, d_VEN_ptr: int, block_ave_threshold: float = 1e-11,
                         nspin: int = 1):
         self._check(self._lib.sxc_build_xc_device(self._h, grid, basis, func, nspin, C.c_void_p(d_P_ptr),
@@ -161,8 +205,32 @@ class XCContext:
         pp = (C.c_void_p * max(nenv, 1))(*[p.ctypes.data for p in P_env])
         E = np.zeros(2 + nenv)
         self._check(self._lib.sxc_build_nadd(self._h, grid, func, nspin, basis_act, _ptr(P_act), nenv, _ptr(be), pp,
-                                             1 if env_frozen else 0, block_ave_threshold, _ptr(V), _ptr(E)))
+                                             int(env_frozen), block_ave_threshold, _ptr(V), _ptr(E)))
         return (_spin_unpack(V) if nspin == 2 else V), E
+
+    def build_nadd_multi(self, grid, funcs, basis_act, P_act, basis_env, P_env, env_frozen: int = 0, sum_matrices: bool = True,
+                         block_ave_threshold: float = 1e-11, nspin: int = 1):
+        """All non-additive functionals of one FDE iteration in one device pass (sxc_build_nadd_multi).  Returns
+        (V, E): V = the summed matrix (sum_matrices) or a list of one matrix per functional; E [nfunc, 2 + nenv]."""
+        if nspin == 2:
+            P_act = _spin_pack(P_act)
+            P_env = [_spin_pack(p) for p in P_env]
+        else:
+            P_act = np.asfortranarray(P_act, dtype=np.float64)
+            P_env = [np.asfortranarray(p, dtype=np.float64) for p in P_env]
+        nenv, nf = len(P_env), len(funcs)
+        nmat = 1 if sum_matrices else nf
+        V = np.zeros((nmat,) + ((2, P_act.shape[1]) if nspin == 2 else (P_act.size,)))
+        fh = np.ascontiguousarray(funcs, dtype=np.int32)
+        be = np.ascontiguousarray(basis_env, dtype=np.int32)
+        pp = (C.c_void_p * max(nenv, 1))(*[p.ctypes.data for p in P_env])
+        E = np.zeros((nf, 2 + nenv))
+        self._check(self._lib.sxc_build_nadd_multi(self._h, grid, nf, _ptr(fh), nspin, basis_act, _ptr(P_act), nenv, _ptr(be), pp,
+                                                   int(env_frozen), block_ave_threshold, 1 if sum_matrices else 0, _ptr(V),
+                                                   _ptr(E)))
+        nb = int(round(np.sqrt(P_act.shape[-1] if nspin == 2 else P_act.size)))
+        mats = [(_spin_unpack(V[m]) if nspin == 2 else np.asfortranarray(V[m].reshape(nb, nb, order="F"))) for m in range(nmat)]
+        return (mats[0] if sum_matrices else mats), E
 
     def build_nadd_device(self, grid, func, basis_act, d_P_act: int, basis_env, d_P_env, d_VE: int,
                           env_frozen: bool = False, block_ave_threshold: float = 1e-11, nspin: int = 1):
@@ -170,7 +238,7 @@ class XCContext:
         be = np.ascontiguousarray(basis_env, dtype=np.int32)
         pp = (C.c_void_p * max(nenv, 1))(*d_P_env)
         self._check(self._lib.sxc_build_nadd_device(self._h, grid, func, nspin, basis_act, C.c_void_p(d_P_act), nenv,
-                                                    _ptr(be), pp, 1 if env_frozen else 0, block_ave_threshold,
+                                                    _ptr(be), pp, int(env_frozen), block_ave_threshold,
                                                     C.c_void_p(d_VE)))
 
     def xc_gradient(self, grid, basis, func, P, atom_of_bf, natoms: int, nspin: int = 1):
