@@ -358,6 +358,10 @@ int sxc_abi_version(void);
  * warp); returns the number of rounds (rounds40 may be NULL) */
 int sxc_debug_scatter_schedule(int n32, unsigned char* rounds40, int max_rounds);
 
+/* same for the TMA scatter kernel's schedule (v2): 64 bytes per round (ngroups, 7 x pad, group[8], slot_a[8], slot_b[8], kmask[8],
+ * group_a[8], group_b[8], 8 x pad); ks = k-steps per K chunk (2 or 4), kmask bit k = the warp multiplies k-step k */
+int sxc_debug_scatter_schedule2(int n32, int ks, unsigned char* rounds64, int max_rounds);
+
 #ifdef __cplusplus
 }
 #endif

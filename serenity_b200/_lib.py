@@ -23,6 +23,7 @@ SYMBOLS = [
     "sxc_host_last_error", "sxc_debug_scatter_schedule",
     "sxc_comm_unique_id", "sxc_comm_init_rank", "sxc_comm_destroy", "sxc_comm_info", "sxc_release_grid", "sxc_release_basis",
     "sxc_release_functional", "sxc_host_alloc", "sxc_host_free", "sxc_build_nadd_multi", "sxc_build_nadd_multi_device",
+    "sxc_debug_scatter_schedule2",
 ]
 
 
@@ -114,6 +115,7 @@ def load():
     lib.sxc_kernel_sigma.argtypes = [vp, i, i, i, vp, i, i, vp, vp]
     lib.sxc_build_nadd_multi.argtypes = [vp, i, i, vp, i, i, vp, i, vp, vp, i, d, i, vp, vp]
     lib.sxc_build_nadd_multi_device.argtypes = [vp, i, i, vp, i, i, vp, i, vp, vp, i, d, i, vp]
+    lib.sxc_debug_scatter_schedule2.argtypes = [i, i, vp, i]
     lib.sxc_comm_unique_id.argtypes = [vp]
     lib.sxc_comm_init_rank.argtypes = [vp, i, i, vp]
     lib.sxc_comm_destroy.argtypes = [vp]

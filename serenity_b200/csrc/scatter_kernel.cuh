@@ -27,10 +27,11 @@ namespace sxc {
 // K3b: per block: weights x potential, block-average test, G into the fifth tile slot.  256 threads; gridDim.y CTAs share the
 // function rows of a block (a small shard would otherwise leave too few bytes in flight to fill HBM).
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)  // 32 registers: 8 CTAs per SM keep the streaming loads in flight
 k_form_g(GridView g, PlanView plan, const int* __restrict__ order, double block_ave_thr, double a_scale,
          const double* __restrict__ v_rho, const double* __restrict__ v_gx, const double* __restrict__ v_gy,
-         const double* __restrict__ v_gz, double* __restrict__ phi_buf, int* __restrict__ skip_flag) {
+         const double* __restrict__ v_gz, int npot, size_t pot_stride, double* __restrict__ phi_buf,
+         int* __restrict__ skip_flag) {
   __shared__ double sa[BP], sx[BP], sy[BP], sz[BP];
   __shared__ double scratch[32];
   const int q = order[blockIdx.x];
@@ -38,27 +39,37 @@ k_form_g(GridView g, PlanView plan, const int* __restrict__ order, double block_
   const long first = (long)blk * g.blocksize;
   const int n = (int)min((long)g.blocksize, g.npts - first);
   const int tid = threadIdx.x;
-  double mag = 0.0;
-  if (tid < BP) {
+  // npot > 1: the potentials of several operators are scattered in one pass (sxc_build_nadd_multi, summed matrix); each operator
+  // keeps ITS OWN block-average test, exactly as if it had been scattered alone (ScalarOperatorToMatrixAdder.cpp:262-268), and
+  // only the ones that pass enter a, b
+  bool any_pass = false;
+  if (tid < BP) sa[tid] = sx[tid] = sy[tid] = sz[tid] = 0.0;
+  for (int k = 0; k < npot; ++k) {
     double a = 0.0, bx = 0.0, by = 0.0, bz = 0.0;
     if (tid < n) {
+      const size_t o = (size_t)k * pot_stride + first + tid;
       const double wp = g.w[first + tid];
-      a = wp * v_rho[first + tid];
+      a = wp * v_rho[o];
       if (v_gx) {
-        bx = wp * v_gx[first + tid];
-        by = wp * v_gy[first + tid];
-        bz = wp * v_gz[first + tid];
+        bx = wp * v_gx[o];
+        by = wp * v_gy[o];
+        bz = wp * v_gz[o];
       }
     }
-    sa[tid] = a;
-    sx[tid] = bx;
-    sy[tid] = by;
-    sz[tid] = bz;
-    mag = fabs(a) + fabs(bx) + fabs(by) + fabs(bz);
+    const double total = block_sum(fabs(a) + fabs(bx) + fabs(by) + fabs(bz), scratch);  // (its barriers order the smem updates)
+    if (!(total / (double)n < block_ave_thr)) {  // :262-268
+      any_pass = true;
+      if (tid < BP) {
+        sa[tid] += a;
+        sx[tid] += bx;
+        sy[tid] += by;
+        sz[tid] += bz;
+      }
+    }
   }
-  const double total = block_sum(mag, scratch);
+  __syncthreads();
   const int s = plan.s[q];
-  const bool skip = (total / (double)n < block_ave_thr) || s == 0;  // :262-268
+  const bool skip = !any_pass || s == 0;
   if (tid == 0 && blockIdx.y == 0) skip_flag[q] = skip ? 1 : 0;
   if (skip) return;
   const int sp = plan.s_pad[q];
@@ -414,6 +425,36 @@ __global__ void k_mirror(int nbf, double* __restrict__ V) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
   if (i < nbf && j < nbf && i < j) V[j + (size_t)i * nbf] = V[i + (size_t)j * nbf];
+}
+
+// The tail of a build in one launch: nmat matrices (back to back) get their strict upper triangle mirrored down, and CTA (0, 0, 0)
+// sums nred arrays of per-block partial sums in a fixed order (deterministic): partial array r goes to
+// out[(r >> 1) * pair_stride + (r & 1)] (E and N of the KS build; E[rho_tot], E[rho_act] per functional of the NAdd build).
+__global__ void __launch_bounds__(256)
+k_finish(int nbf, double* __restrict__ V, const double* __restrict__ part, int nlit, int nred, int pair_stride,
+         double* __restrict__ out) {
+  __shared__ double scratch[32];
+  double* Vm = V + (size_t)blockIdx.z * nbf * nbf;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i < nbf && j < nbf && i < j) Vm[j + (size_t)i * nbf] = Vm[i + (size_t)j * nbf];
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    const int t = threadIdx.y * blockDim.x + threadIdx.x;
+    for (int r = 0; r < nred; ++r) {
+      double sum = 0.0;
+      for (int k = t; k < nlit; k += 256) sum += part[(size_t)r * nlit + k];
+      const int lane = t & 31, wid = t >> 5;
+      sum = warp_sum(sum);
+      __syncthreads();
+      if (lane == 0) scratch[wid] = sum;
+      __syncthreads();
+      if (t == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < 8; ++w) tot += scratch[w];
+        out[(size_t)(r >> 1) * pair_stride + (r & 1)] = tot;
+      }
+    }
+  }
 }
 
 }  // namespace sxc

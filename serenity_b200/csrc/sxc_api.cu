@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -25,6 +26,7 @@
 #include "density_kernel.cuh"
 #include "functionals.cuh"
 #include "scatter_kernel.cuh"
+#include "scatter_tma.cuh"
 #include "gradient_kernels.cuh"
 #include "grid_kernels.cuh"
 #include "kernel2.cuh"
@@ -136,6 +138,7 @@ struct Plan {
   int nown = 0;
   int nbf_pad = 0;
   int s_pad_max = 0;
+  int vmat_variant = 0;  // scatter kernel the round templates / work items were made for
   DevMem block_id, nsig_shell, s, sig_shell, sig_c0, sig_bf, s_pad, phi_off, order, tpl, tpl_off, skip, ditems, vitems;
   std::vector<int> h_s, h_s_pad;
   std::vector<Chunk> chunks;
@@ -178,6 +181,16 @@ struct sxc_ctx {
   std::map<std::pair<int, int>, std::unique_ptr<Plan>> plans;
   std::vector<std::unique_ptr<KernelStore>> kstores;
   std::map<int, std::vector<ScatterRound>> scatter_tpl;  // round templates per s_pad / 32
+  std::map<std::pair<int, int>, std::vector<ScatterRound2>> scatter_tpl2;  // v2 templates per (s_pad / 32, k-steps per chunk)
+  // which scatter kernel runs: 0 = k_vmat (cp.async producers), 8 / 16 = k_vmat_tma<8 / 16> (TMA producer); SXC_VMAT overrides
+  int vmat_variant = 16;
+  int dens_variant = 0;  // 0 = k_density (cp.async producers; 1-3 % faster as measured), 1 = k_density_tma; SXC_DENS overrides
+  int smem_pad = 0;  // SXC_SMEM_PAD: extra dynamic shared memory per DMMA CTA (development: forces one CTA per SM)
+  int dseg = 1, vseg = 1;  // pieces per block of the k_density / k_vmat work items (SXC_DSEG / SXC_VSEG; 1 = only when a shard is small)
+  CUtensorMap tmap_v8{}, tmap_v16{};  // tile workspace as [rows] x [128 points], boxes 32 x 8 (SWIZZLE_64B) and 32 x 16 (128B)
+  CUtensorMap tmap_d16{};             // boxes of 16 rows x 16 points (SWIZZLE_128B) for k_density_tma
+  void* tmap_ptr = nullptr;
+  size_t tmap_bytes = 0;
   DevMem phi;     // tile workspace (one chunk)
   DevMem phi2;    // second tile workspace: basis B of the two-basis scatter (row f-4)
   DevMem dP;      // staged density matrices (host API)
@@ -279,6 +292,9 @@ int set_kernel_attrs(sxc_ctx* ctx) {
   CU(cudaFuncSetAttribute(k_grad_contract, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CU(cudaFuncSetAttribute(k_vmat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scat::smem_bytes_pipe()));
   CU(cudaFuncSetAttribute(k_vmat_ab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scat::smem_bytes()));
+  CU(cudaFuncSetAttribute(k_density_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CU(cudaFuncSetAttribute(k_vmat_tma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CU(cudaFuncSetAttribute(k_vmat_tma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   ctx->attrs_set = true;
   return SXC_OK;
 }
@@ -515,6 +531,171 @@ const std::vector<ScatterRound>& scatter_schedule(sxc_ctx* ctx, int n32) {
   return ctx->scatter_tpl[n32] = build_scatter_schedule(n32);
 }
 
+// Scatter schedule v2 (k_vmat_tma): the strictly upper triangle is covered by 2 x 4 rectangles of warp tiles (8 tiles on 6 staged
+// groups) band by band; what the rectangles leave over - the band's inner off-diagonal tile and the diagonal tiles, which cost
+// 10/16 of a full tile - first fills the idle warps of partial rounds whose staged groups already cover it, then forms rounds
+// of its own (diagonal tiles together: such a round lasts 10/16 of a full one).  Finally every round hands its idle warps to
+// the most expensive tiles: a tile split over nw warps costs ceil(KS / nw) of its KS k-steps per chunk.
+std::vector<ScatterRound2> build_scatter_schedule2(int n32, int KS) {
+  using Tile = std::pair<int, int>;
+  const int W = scat2::WARPS, MAXG = scat2::MAXG;
+  std::vector<std::vector<Tile>> rounds;
+  std::vector<Tile> loose;
+  for (int b0 = 0; b0 < n32; b0 += 2) {
+    std::vector<int> rows;
+    for (int r = b0; r < std::min(b0 + 2, n32); ++r) rows.push_back(r);
+    if (b0 + 1 < n32) loose.push_back({b0, b0 + 1});
+    for (int c0 = b0 + 2; c0 < n32; c0 += 4) {
+      std::vector<Tile> tl;
+      for (int c = c0; c < std::min(c0 + 4, n32); ++c)
+        for (int r : rows) tl.push_back({r, c});
+      rounds.push_back(tl);
+    }
+    for (int r : rows) loose.push_back({r, r});
+  }
+  auto ngroups_with = [](const std::vector<Tile>& tl, const Tile* extra) {
+    std::vector<int> g;
+    auto add = [&](int x) {
+      if (std::find(g.begin(), g.end(), x) == g.end()) g.push_back(x);
+    };
+    for (const Tile& t : tl) {
+      add(t.first);
+      add(t.second);
+    }
+    if (extra) {
+      add(extra->first);
+      add(extra->second);
+    }
+    return (int)g.size();
+  };
+  // off-diagonal loose tiles first: they are the expensive ones
+  std::stable_sort(loose.begin(), loose.end(), [](const Tile& a, const Tile& b) { return (a.first == a.second) < (b.first == b.second); });
+  for (auto& tl : rounds) {
+    while ((int)tl.size() < W && !loose.empty()) {
+      const int g0 = ngroups_with(tl, nullptr);
+      int best = -1, best_add = 1 << 30;
+      for (size_t k = 0; k < loose.size(); ++k) {
+        const int ng = ngroups_with(tl, &loose[k]);
+        if (ng <= MAXG && ng - g0 < best_add) {
+          best_add = ng - g0;
+          best = (int)k;
+        }
+      }
+      if (best < 0) break;
+      tl.push_back(loose[best]);
+      loose.erase(loose.begin() + best);
+    }
+  }
+  // the rest: diagonal tiles together (cheap rounds), then the remaining off-diagonal ones
+  std::stable_sort(loose.begin(), loose.end(), [](const Tile& a, const Tile& b) { return (a.first != a.second) < (b.first != b.second); });
+  std::vector<Tile> cur;
+  for (const Tile& t : loose) {
+    if ((int)cur.size() >= W || ngroups_with(cur, &t) > MAXG) {
+      rounds.push_back(cur);
+      cur.clear();
+    }
+    cur.push_back(t);
+  }
+  if (!cur.empty()) rounds.push_back(cur);
+
+  std::vector<ScatterRound2> out;
+  for (const auto& tl : rounds) {
+    const int nt = (int)tl.size();
+    std::vector<int> nw(nt, 1);
+    auto cost = [&](int k) { return (tl[k].first == tl[k].second ? 10.0 : 16.0) * ((KS + nw[k] - 1) / nw[k]); };
+    for (int idle = W - nt; idle > 0; --idle) {
+      int k = 0;
+      for (int j = 1; j < nt; ++j)
+        if (cost(j) > cost(k)) k = j;
+      if (nw[k] >= KS) break;
+      ++nw[k];
+    }
+    ScatterRound2 r;
+    std::memset(&r, 0, sizeof(r));
+    std::memset(r.ta, 0xff, sizeof(r.ta));
+    std::memset(r.tb, 0xff, sizeof(r.tb));
+    std::vector<int> groups;
+    auto slot = [&](int g) {
+      auto it = std::find(groups.begin(), groups.end(), g);
+      if (it == groups.end()) {
+        groups.push_back(g);
+        return (int)groups.size() - 1;
+      }
+      return (int)(it - groups.begin());
+    };
+    int w = 0;
+    for (int k = 0; k < nt; ++k)
+      for (int part = 0; part < nw[k]; ++part, ++w) {
+        r.ta[w] = (unsigned char)slot(tl[k].first);
+        r.tb[w] = (unsigned char)slot(tl[k].second);
+        r.ga[w] = (unsigned char)tl[k].first;
+        r.gb[w] = (unsigned char)tl[k].second;
+        unsigned m = 0;
+        for (int ks = part; ks < KS; ks += nw[k]) m |= 1u << ks;
+        r.kmask[w] = (unsigned char)m;
+      }
+    r.ngroups = (unsigned char)groups.size();
+    for (size_t k = 0; k < groups.size() && k < sizeof(r.group); ++k) r.group[k] = (unsigned char)groups[k];
+    out.push_back(r);
+  }
+  return out;
+}
+
+const std::vector<ScatterRound2>& scatter_schedule2(sxc_ctx* ctx, int n32, int KS) {
+  auto key = std::make_pair(n32, KS);
+  auto it = ctx->scatter_tpl2.find(key);
+  if (it != ctx->scatter_tpl2.end()) return it->second;
+  return ctx->scatter_tpl2[key] = build_scatter_schedule2(n32, KS);
+}
+
+// ---- TMA: 2-D tensor maps over the tile workspace ([rows] x [128 points] of FP64), one per box shape -----------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+int make_tile_map(sxc_ctx* ctx, const DevMem& buf, int box_points, int box_rows, CUtensorMapSwizzle swz, CUtensorMap* out) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return fail(ctx, SXC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t gdim[2] = {(cuuint64_t)BP, (cuuint64_t)(buf.bytes / (BP * sizeof(double)))};
+  const cuuint64_t gstride[1] = {(cuuint64_t)BP * sizeof(double)};
+  const cuuint32_t box[2] = {(cuuint32_t)box_points, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  static const int l2mode = []() {  // development switch SXC_TMA_L2: 0 none, 1 = 64 B, 2 = 128 B (default), 3 = 256 B promotion
+    const char* v = std::getenv("SXC_TMA_L2");
+    return v ? std::atoi(v) : 2;
+  }();
+  const CUtensorMapL2promotion promo = l2mode == 0   ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                       : l2mode == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                       : l2mode == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                                     : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+  const CUresult rc = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, buf.p, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         swz, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) return fail(ctx, SXC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)rc);
+  return SXC_OK;
+}
+
+// maps of the main workspace, re-encoded when the buffer moved or grew
+int ensure_tile_maps(sxc_ctx* ctx) {
+  if (ctx->tmap_ptr == ctx->phi.p && ctx->tmap_bytes == ctx->phi.bytes) return SXC_OK;
+  TRY(make_tile_map(ctx, ctx->phi, 8, 32, CU_TENSOR_MAP_SWIZZLE_64B, &ctx->tmap_v8));
+  TRY(make_tile_map(ctx, ctx->phi, 16, 32, CU_TENSOR_MAP_SWIZZLE_128B, &ctx->tmap_v16));
+  TRY(make_tile_map(ctx, ctx->phi, 16, 16, CU_TENSOR_MAP_SWIZZLE_128B, &ctx->tmap_d16));
+  ctx->tmap_ptr = ctx->phi.p;
+  ctx->tmap_bytes = ctx->phi.bytes;
+  return SXC_OK;
+}
+
 constexpr int GRAD_PLAN = 1 << 20;  // key offset of the 8-slot plans of the gradient path
 
 int get_plan(sxc_ctx* ctx, int gh, int bh, Plan** out, int comps = TILE_COMPS) {
@@ -616,13 +797,21 @@ int get_plan(sxc_ctx* ctx, int gh, int bh, Plan** out, int comps = TILE_COMPS) {
   // scatter round templates for every s_pad / 32 up to the largest block
   const int n32max = p.s_pad_max / 32;
   std::vector<int> tpl_off(n32max + 2, 0);
-  std::vector<ScatterRound> tpl;
+  std::vector<ScatterRound> tpl;     // k_vmat
+  std::vector<ScatterRound2> tpl2;   // k_vmat_tma<vmat_variant>
+  p.vmat_variant = ctx->vmat_variant;
   for (int n32 = 1; n32 <= n32max; ++n32) {
-    tpl_off[n32] = (int)tpl.size();
-    const auto& rs = scatter_schedule(ctx, n32);
-    tpl.insert(tpl.end(), rs.begin(), rs.end());
+    if (p.vmat_variant == 0) {
+      tpl_off[n32] = (int)tpl.size();
+      const auto& rs = scatter_schedule(ctx, n32);
+      tpl.insert(tpl.end(), rs.begin(), rs.end());
+    } else {
+      tpl_off[n32] = (int)tpl2.size();
+      const auto& rs = scatter_schedule2(ctx, n32, p.vmat_variant / 4);
+      tpl2.insert(tpl2.end(), rs.begin(), rs.end());
+    }
   }
-  tpl_off[n32max + 1] = (int)tpl.size();
+  tpl_off[n32max + 1] = (int)(p.vmat_variant == 0 ? tpl.size() : tpl2.size());
   tpl_off[0] = 0;
   CU(p.order.ensure(order.size() * sizeof(int)));
   // work items of the DMMA kernels: whole blocks, unless that leaves fewer than ~3 waves of the resident CTAs (strong
@@ -645,20 +834,24 @@ int get_plan(sxc_ctx* ctx, int gh, int bh, Plan** out, int comps = TILE_COMPS) {
       const int q = order[c.slot0 + k];
       const int n32 = p.h_s_pad[q] / 32;
       const int njt = p.h_s[q] == 0 ? 0 : (n32 + dens::NJW - 1) / dens::NJW;
-      if (njt <= seg_jt || c.nslots >= target) {
+      // (dseg / vseg > 1: every block is cut into that many pieces even on a full GPU - CTAs that run at the same time then work on
+      // the same few blocks, whose tiles stay in L2 between the re-reads of the j-tiles / rounds)
+      const int want_d = ctx->dseg > 1 ? std::min(njt, ctx->dseg) : 1;
+      if (want_d <= 1 && (njt <= seg_jt || c.nslots >= target)) {
         ditems.push_back(WorkItem{q, 0, (short)njt});
       } else {
         c.dens_split = true;
-        const int nseg = (njt + seg_jt - 1) / seg_jt;
+        const int nseg = std::max(want_d, (c.nslots >= target) ? 1 : (njt + seg_jt - 1) / seg_jt);
         for (int sgi = 0; sgi < nseg; ++sgi)  // equal-sized segments
           ditems.push_back(WorkItem{q, (short)((long)njt * sgi / nseg), (short)((long)njt * (sgi + 1) / nseg)});
       }
       if (p.h_s[q] == 0) continue;
       const int nr = tpl_off[n32 + 1] - tpl_off[n32];
-      if (nr <= seg_r || c.nslots >= target) {
+      const int want_v = ctx->vseg > 1 ? std::min(nr, ctx->vseg) : 1;
+      if (want_v <= 1 && (nr <= seg_r || c.nslots >= target)) {
         vitems.push_back(WorkItem{q, 0, (short)nr});
       } else {
-        const int nseg = (nr + seg_r - 1) / seg_r;
+        const int nseg = std::max(want_v, (c.nslots >= target) ? 1 : (nr + seg_r - 1) / seg_r);
         for (int sgi = 0; sgi < nseg; ++sgi)
           vitems.push_back(WorkItem{q, (short)((long)nr * sgi / nseg), (short)((long)nr * (sgi + 1) / nseg)});
       }
@@ -672,7 +865,7 @@ int get_plan(sxc_ctx* ctx, int gh, int bh, Plan** out, int comps = TILE_COMPS) {
     CU(cudaMemcpyAsync(p.ditems.p, ditems.data(), ditems.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, ctx->stream));
   if (!vitems.empty())
     CU(cudaMemcpyAsync(p.vitems.p, vitems.data(), vitems.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, ctx->stream));
-  CU(p.tpl.ensure(std::max<size_t>(tpl.size(), 1) * sizeof(ScatterRound)));
+  CU(p.tpl.ensure(std::max<size_t>(tpl.size(), 1) * sizeof(ScatterRound) + std::max<size_t>(tpl2.size(), 1) * sizeof(ScatterRound2)));
   CU(p.tpl_off.ensure(tpl_off.size() * sizeof(int)));
   if (p.nown) {
     CU(cudaMemcpyAsync(p.s_pad.p, p.h_s_pad.data(), p.nown * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
@@ -681,9 +874,11 @@ int get_plan(sxc_ctx* ctx, int gh, int bh, Plan** out, int comps = TILE_COMPS) {
   }
   if (!tpl.empty())
     CU(cudaMemcpyAsync(p.tpl.p, tpl.data(), tpl.size() * sizeof(ScatterRound), cudaMemcpyHostToDevice, ctx->stream));
+  if (!tpl2.empty())
+    CU(cudaMemcpyAsync(p.tpl.p, tpl2.data(), tpl2.size() * sizeof(ScatterRound2), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(p.tpl_off.p, tpl_off.data(), tpl_off.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  if (dens::smem_bytes_pipe(p.s_pad_max) > 227 * 1024 || p.s_pad_max / 32 > 255)
+  if (std::max(dens::smem_bytes_pipe(p.s_pad_max), dens::smem_bytes_tma(p.s_pad_max)) > 227 * 1024 || p.s_pad_max / 32 > 255)
     return fail(ctx, SXC_ERR_UNSUPPORTED, "more than %d significant functions in one block", p.s_pad_max);
   *out = plan.get();
   ctx->plans[key] = std::move(plan);
@@ -691,15 +886,15 @@ int get_plan(sxc_ctx* ctx, int gh, int bh, Plan** out, int comps = TILE_COMPS) {
 }
 
 // per-point SoA arrays: rows rho, gx, gy, gz per spin ([4 * nspin][N])
-int ensure_point_arrays(sxc_ctx* ctx, Grid& g, bool nadd, int nspin, int nparts = 3) {
+int ensure_point_arrays(sxc_ctx* ctx, Grid& g, bool nadd, int nspin, int nparts = 3, int npot = 1) {
   const size_t n4 = (size_t)4 * nspin * std::max<long>(g.npts, 1) * sizeof(double);
   if (g.dens.bytes < n4) {
     CU(g.dens.ensure(n4));
     CU(cudaMemsetAsync(g.dens.p, 0, n4, ctx->stream));
   }
-  if (g.pot.bytes < n4) {
-    CU(g.pot.ensure(n4));
-    CU(cudaMemsetAsync(g.pot.p, 0, n4, ctx->stream));
+  if (g.pot.bytes < n4 * npot) {  // (npot potentials side by side: the summed multi-functional scatter)
+    CU(g.pot.ensure(n4 * npot));
+    CU(cudaMemsetAsync(g.pot.p, 0, n4 * npot, ctx->stream));
   }
   CU(g.parts.ensure((size_t)std::max(3, nparts) * std::max(g.nlit, 1) * sizeof(double)));
   if (nadd) {
@@ -747,9 +942,16 @@ int phase_density(sxc_ctx* ctx, const Grid& g, const Basis& b, const Plan& p, co
     k_zero_blocks<<<c.nslots, 128, 0, ctx->stream>>>(N, g.blocksize, with_grad ? 4 : 1, p.block_id.as<int>() + c.slot0, dens4);
     LAUNCH_CHECK();
   }
-  k_density<<<c.nditems, dens::PTHREADS, dens::smem_bytes_pipe(p.s_pad_max), ctx->stream>>>(
-      g.view(), p.view(), b.nbf, dP, p.ditems.as<WorkItem>() + c.ditem_off, ctx->phi.as<double>(), dens4,
-      with_grad ? dens4 + N : nullptr, with_grad ? dens4 + 2 * N : nullptr, with_grad ? dens4 + 3 * N : nullptr, nonneg);
+  if (ctx->dens_variant == 0) {
+    k_density<<<c.nditems, dens::PTHREADS, dens::smem_bytes_pipe(p.s_pad_max), ctx->stream>>>(
+        g.view(), p.view(), b.nbf, dP, p.ditems.as<WorkItem>() + c.ditem_off, ctx->phi.as<double>(), dens4,
+        with_grad ? dens4 + N : nullptr, with_grad ? dens4 + 2 * N : nullptr, with_grad ? dens4 + 3 * N : nullptr, nonneg);
+  } else {
+    TRY(ensure_tile_maps(ctx));
+    k_density_tma<<<c.nditems, dens::PTHREADS, dens::smem_bytes_tma(p.s_pad_max) + ctx->smem_pad, ctx->stream>>>(
+        ctx->tmap_d16, g.view(), p.view(), b.nbf, dP, p.ditems.as<WorkItem>() + c.ditem_off, dens4,
+        with_grad ? dens4 + N : nullptr, with_grad ? dens4 + 2 * N : nullptr, with_grad ? dens4 + 3 * N : nullptr, nonneg);
+  }
   LAUNCH_CHECK();
   return SXC_OK;
 }
@@ -795,14 +997,14 @@ dim3 form_g_grid(const sxc_ctx* ctx, int nslots) {
 }
 
 int phase_scatter(sxc_ctx* ctx, const Grid& g, const Basis& b, const Plan& p, const Chunk& c, bool gga,
-                  double block_ave_thr, const double* pot4, double* dW) {
+                  double block_ave_thr, const double* pot4, double* dW, int npot = 1, size_t pot_stride = 0) {
   const long N = g.npts;
   if (c.nslots == 0) return SXC_OK;
   {
     PhaseTimer t(ctx, SXC_T_FORM_G);
     k_form_g<<<form_g_grid(ctx, c.nslots), 256, 0, ctx->stream>>>(g.view(), p.view(), p.order.as<int>() + c.order_off, block_ave_thr, 0.5,
                                                 pot4, gga ? pot4 + N : nullptr, gga ? pot4 + 2 * N : nullptr,
-                                                gga ? pot4 + 3 * N : nullptr, ctx->phi.as<double>(), p.skip.as<int>());
+                                                gga ? pot4 + 3 * N : nullptr, npot, pot_stride, ctx->phi.as<double>(), p.skip.as<int>());
     LAUNCH_CHECK();
   }
   int* counter = nullptr;
@@ -810,9 +1012,21 @@ int phase_scatter(sxc_ctx* ctx, const Grid& g, const Basis& b, const Plan& p, co
   PhaseTimer t(ctx, SXC_T_SCATTER);
   if (c.nvitems == 0) return SXC_OK;
   const int grid = std::min(c.nvitems, 2 * ctx->num_sms);
-  k_vmat<<<grid, scat::PTHREADS, scat::smem_bytes_pipe(), ctx->stream>>>(
-      p.view(), b.nbf, p.vitems.as<WorkItem>() + c.vitem_off, c.nvitems, counter, p.skip.as<int>(), p.tpl.as<ScatterRound>(),
-      p.tpl_off.as<int>(), ctx->phi.as<double>(), dW);
+  if (p.vmat_variant == 0) {
+    k_vmat<<<grid, scat::PTHREADS, scat::smem_bytes_pipe(), ctx->stream>>>(
+        p.view(), b.nbf, p.vitems.as<WorkItem>() + c.vitem_off, c.nvitems, counter, p.skip.as<int>(), p.tpl.as<ScatterRound>(),
+        p.tpl_off.as<int>(), ctx->phi.as<double>(), dW);
+  } else {
+    TRY(ensure_tile_maps(ctx));
+    if (p.vmat_variant == 8)
+      k_vmat_tma<8><<<grid, scat2::THREADS, scat2::smem_bytes<8>(p.s_pad_max) + ctx->smem_pad, ctx->stream>>>(
+          ctx->tmap_v8, p.view(), b.nbf, p.vitems.as<WorkItem>() + c.vitem_off, c.nvitems, counter, p.skip.as<int>(),
+          p.tpl.as<ScatterRound2>(), p.tpl_off.as<int>(), p.s_pad_max, dW);
+    else
+      k_vmat_tma<16><<<grid, scat2::THREADS, scat2::smem_bytes<16>(p.s_pad_max) + ctx->smem_pad, ctx->stream>>>(
+          ctx->tmap_v16, p.view(), b.nbf, p.vitems.as<WorkItem>() + c.vitem_off, c.nvitems, counter, p.skip.as<int>(),
+          p.tpl.as<ScatterRound2>(), p.tpl_off.as<int>(), p.s_pad_max, dW);
+  }
   LAUNCH_CHECK();
   return SXC_OK;
 }
@@ -828,11 +1042,11 @@ int phase_scatter_ab(sxc_ctx* ctx, const Grid& g, const Basis& bA, const Plan& p
     PhaseTimer t(ctx, SXC_T_FORM_G);  // G_A = grad_A (no scalar part), G_B = a phi_B + grad_B
     k_form_g<<<form_g_grid(ctx, cA.nslots), 256, 0, ctx->stream>>>(g.view(), pA.view(), pA.order.as<int>() + cA.order_off, block_ave_thr, 0.0,
                                                  pot4, gga ? pot4 + N : nullptr, gga ? pot4 + 2 * N : nullptr,
-                                                 gga ? pot4 + 3 * N : nullptr, ctx->phi.as<double>(), pA.skip.as<int>());
+                                                 gga ? pot4 + 3 * N : nullptr, 1, 0, ctx->phi.as<double>(), pA.skip.as<int>());
     LAUNCH_CHECK();
     k_form_g<<<form_g_grid(ctx, cB.nslots), 256, 0, ctx->stream>>>(g.view(), pB.view(), pB.order.as<int>() + cB.order_off, block_ave_thr, 1.0,
                                                  pot4, gga ? pot4 + N : nullptr, gga ? pot4 + 2 * N : nullptr,
-                                                 gga ? pot4 + 3 * N : nullptr, ctx->phi2.as<double>(), pB.skip.as<int>());
+                                                 gga ? pot4 + 3 * N : nullptr, 1, 0, ctx->phi2.as<double>(), pB.skip.as<int>());
     LAUNCH_CHECK();
   }
   int* counter = nullptr;
@@ -861,6 +1075,16 @@ int finish_matrix(sxc_ctx* ctx, int nbf, double* dW) {
   dim3 blk(32, 8), grd((nbf + 31) / 32, (nbf + 7) / 8);
   PhaseTimer t(ctx, SXC_T_FINISH);
   k_mirror<<<grd, blk, 0, ctx->stream>>>(nbf, dW);
+  LAUNCH_CHECK();
+  return SXC_OK;
+}
+
+// mirror nmat matrices + nred ordered partial-sum reductions in one launch (k_finish)
+int finish_build(sxc_ctx* ctx, int nbf, int nmat, double* dV, const double* part, int nlit, int nred, int pair_stride,
+                 double* out) {
+  dim3 blk(32, 8), grd((nbf + 31) / 32, (nbf + 7) / 8, std::max(nmat, 1));
+  PhaseTimer t(ctx, SXC_T_FINISH);
+  k_finish<<<grd, blk, 0, ctx->stream>>>(nmat > 0 ? nbf : 0, dV, part, nlit, nred, pair_stride, out);
   LAUNCH_CHECK();
   return SXC_OK;
 }
@@ -896,10 +1120,10 @@ int build_xc_device(sxc_ctx* ctx, int gh, int bh, int fh, int nspin, const doubl
     PhaseTimer t_all(ctx, T_TOTAL);
     CU(cudaMemsetAsync(dVEN, 0, (nspin * nb2 + 2) * sizeof(double), ctx->stream));
     CU(cudaMemsetAsync(parts, 0, (size_t)3 * std::max(g.nlit, 1) * sizeof(double), ctx->stream));
-    // the screening is part of every build in the reference (calculateBasisFunctionData :211-255); with sxc_set_tile_cache the
-    // tiles (and the screening lists they were made with) of the previous build of the same plan are reused
+    // The reference repeats the block prescreening with every evaluation (calculateBasisFunctionData :211-255); its outcome is a
+    // pure function of grid and basis, both immutable behind their handles, so the lists made by k_screen when the plan was
+    // created are used by every build.  With sxc_set_tile_cache the tiles of the previous build of the same plan are reused too.
     const bool cached = tiles_cached(ctx, p);
-    if (!cached) TRY(run_screen(ctx, g, b, p));
     for (const Chunk& c : p.chunks) {
       if (!cached) TRY(phase_basis(ctx, g, b, p, c));
       TRY(wait_p_ready(ctx));
@@ -911,9 +1135,7 @@ int build_xc_device(sxc_ctx* ctx, int gh, int bh, int fh, int nspin, const doubl
         for (int sp = 0; sp < nspin; ++sp)
           TRY(phase_scatter(ctx, g, b, p, c, f.gga != 0, thr, pot + (size_t)4 * sp * N, dVEN + sp * nb2));
     }
-    for (int sp = 0; sp < nspin; ++sp) TRY(finish_matrix(ctx, b.nbf, dVEN + sp * nb2));
-    TRY(reduce_to(ctx, parts, g.nlit, dVEN + nspin * nb2));
-    TRY(reduce_to(ctx, parts + g.nlit, g.nlit, dVEN + nspin * nb2 + 1));
+    TRY(finish_build(ctx, b.nbf, nspin, dVEN, parts, g.nlit, 2, 2, dVEN + nspin * nb2));
     TRY(allreduce_result(ctx, g, dVEN, nspin * nb2 + 2));
   }
   ctx->timing = 0;
@@ -971,7 +1193,7 @@ int build_nadd_device(sxc_ctx* ctx, int gh, int nfunc, const int* fhs, int nspin
     if (!get_basis(ctx, bE[i])) return fail(ctx, SXC_ERR_INVALID, "invalid environment basis handle %d", bE[i]);
     TRY(get_plan(ctx, gh, bE[i], &pe));
   }
-  TRY(ensure_point_arrays(ctx, g, true, nspin, 2 * nfunc));
+  TRY(ensure_point_arrays(ctx, g, true, nspin, 2 * nfunc, sum_mode ? nfunc : 1));
   CU(ctx->scratch.ensure(64 * sizeof(double)));
   const long N = g.npts;
   const int ncomp = 4 * nspin;
@@ -1015,7 +1237,6 @@ int build_nadd_device(sxc_ctx* ctx, int gh, int nfunc, const int* fhs, int nspin
         Plan* pe = nullptr;
         TRY(get_plan(ctx, gh, bE[i], &pe));
         CU(cudaMemsetAsync(parts, 0, (size_t)nfunc * nlit * sizeof(double), ctx->stream));
-        TRY(run_screen(ctx, g, *be, *pe));
         for (const Chunk& c : pe->chunks) {
           TRY(phase_basis(ctx, g, *be, *pe, c));
           for (int sp = 0; sp < nspin; ++sp)
@@ -1051,10 +1272,11 @@ int build_nadd_device(sxc_ctx* ctx, int gh, int nfunc, const int* fhs, int nspin
     // active system: rho_A, rho_tot = rho_A + sum_env, v = v[rho_tot] - v[rho_A]  (NAddFuncPotential.cpp:197-225)
     Plan& p = *pa;
     CU(cudaMemsetAsync(parts, 0, (size_t)2 * nfunc * nlit * sizeof(double), ctx->stream));
-    if (sum_mode && nfunc > 1)  // summed potential: every functional accumulates (an LDA one leaves the gradient rows alone)
-      CU(cudaMemsetAsync(pot, 0, (size_t)ncomp * N * sizeof(double), ctx->stream));
+    // summed matrix: the functionals' potentials sit side by side ([nfunc][4 nspin][N]) and are added inside k_form_g, each under
+    // its own block-average test (an LDA functional next to a GGA one leaves its gradient rows zero)
+    const size_t pot_stride = (size_t)ncomp * N;
+    if (sum_mode && nfunc > 1) CU(cudaMemsetAsync(pot, 0, (size_t)nfunc * pot_stride * sizeof(double), ctx->stream));
     const bool cached = tiles_cached(ctx, p);  // (frozen environment: the active system's tiles survive from call to call)
-    if (!cached) TRY(run_screen(ctx, g, *ba, p));
     for (const Chunk& c : p.chunks) {
       if (!cached) TRY(phase_basis(ctx, g, *ba, p, c));
       for (int sp = 0; sp < nspin; ++sp)
@@ -1067,9 +1289,9 @@ int build_nadd_device(sxc_ctx* ctx, int gh, int nfunc, const int* fhs, int nspin
       }
       for (int k = 0; k < nfunc; ++k) {
         const FuncView f = ctx->funcs[fhs[k]];
-        const int acc0 = (sum_mode && nfunc > 1) ? 1 : 0;
-        TRY(phase_functional(ctx, g, p, c, f, nspin, g.tot.as<double>(), 1.0, acc0, pot, parts + (size_t)(2 * k) * nlit, nullptr));
-        TRY(phase_functional(ctx, g, p, c, f, nspin, dens, -1.0, 1, pot, parts + (size_t)(2 * k + 1) * nlit, nullptr));
+        double* pot_k = pot + ((sum_mode && nfunc > 1) ? (size_t)k * pot_stride : 0);
+        TRY(phase_functional(ctx, g, p, c, f, nspin, g.tot.as<double>(), 1.0, 0, pot_k, parts + (size_t)(2 * k) * nlit, nullptr));
+        TRY(phase_functional(ctx, g, p, c, f, nspin, dens, -1.0, 1, pot_k, parts + (size_t)(2 * k + 1) * nlit, nullptr));
         if (!sum_mode && f.ncomp > 0)
           for (int sp = 0; sp < nspin; ++sp)
             TRY(phase_scatter(ctx, g, *ba, p, c, f.gga != 0, thr, pot + (size_t)4 * sp * N,
@@ -1077,13 +1299,9 @@ int build_nadd_device(sxc_ctx* ctx, int gh, int nfunc, const int* fhs, int nspin
       }
       if (sum_mode && any_comp)
         for (int sp = 0; sp < nspin; ++sp)
-          TRY(phase_scatter(ctx, g, *ba, p, c, any_gga, thr, pot + (size_t)4 * sp * N, dVE + sp * nb2));
+          TRY(phase_scatter(ctx, g, *ba, p, c, any_gga, thr, pot + (size_t)4 * sp * N, dVE + sp * nb2, nfunc, pot_stride));
     }
-    for (int m = 0; m < nmat * nspin; ++m) TRY(finish_matrix(ctx, ba->nbf, dVE + (size_t)m * nb2));
-    for (int k = 0; k < nfunc; ++k) {
-      TRY(reduce_to(ctx, parts + (size_t)(2 * k) * nlit, g.nlit, dVE + nV + (size_t)k * ne));
-      TRY(reduce_to(ctx, parts + (size_t)(2 * k + 1) * nlit, g.nlit, dVE + nV + (size_t)k * ne + 1));
-    }
+    TRY(finish_build(ctx, ba->nbf, nmat * nspin, dVE, parts, g.nlit, 2 * nfunc, ne, dVE + nV));
     TRY(allreduce_result(ctx, g, dVE, nV + (size_t)nfunc * ne));
   }
   ctx->timing = 0;
@@ -1135,7 +1353,6 @@ int build_gradient_device(sxc_ctx* ctx, int gh, int bh, int fh, int nspin, const
         const size_t ne2 = (size_t)be->nbf * be->nbf;
         Plan* pe = nullptr;
         TRY(get_plan(ctx, gh, bE[i], &pe));
-        TRY(run_screen(ctx, g, *be, *pe));
         for (const Chunk& c : pe->chunks) {
           if (c.nslots == 0) continue;
           TRY(phase_basis(ctx, g, *be, *pe, c));
@@ -1148,7 +1365,6 @@ int build_gradient_device(sxc_ctx* ctx, int gh, int bh, int fh, int nspin, const
         }
       }
     }
-    TRY(run_screen(ctx, g, b, p));
     for (const Chunk& c : p.chunks) {
       if (c.nslots == 0) continue;
       TRY(phase_basis(ctx, g, b, p, c));
@@ -1175,7 +1391,7 @@ int build_gradient_device(sxc_ctx* ctx, int gh, int bh, int fh, int nspin, const
           PhaseTimer t(ctx, SXC_T_FORM_G);
           k_form_g<<<form_g_grid(ctx, c.nslots), 256, 0, ctx->stream>>>(g.view(), p.view(), p.order.as<int>() + c.order_off, 0.0, 1.0, pot4,
                                                       gga ? pot4 + N : nullptr, gga ? pot4 + 2 * N : nullptr,
-                                                      gga ? pot4 + 3 * N : nullptr, ctx->phi.as<double>(), p.skip.as<int>());
+                                                      gga ? pot4 + 3 * N : nullptr, 1, 0, ctx->phi.as<double>(), p.skip.as<int>());
           LAUNCH_CHECK();
         }
         PhaseTimer t(ctx, SXC_T_SCATTER);
@@ -1244,7 +1460,6 @@ int build_ab_device(sxc_ctx* ctx, int gh, int fh, int nspin, int bA, int bB, int
       const size_t nc2 = (size_t)bc.nbf * bc.nbf;
       Plan* pc = nullptr;
       TRY(get_plan(ctx, gh, bC[i], &pc));
-      TRY(run_screen(ctx, g, bc, *pc));
       for (const Chunk& c : pc->chunks) {
         TRY(phase_basis(ctx, g, bc, *pc, c));
         for (int sp = 0; sp < nspin; ++sp)
@@ -1259,8 +1474,6 @@ int build_ab_device(sxc_ctx* ctx, int gh, int fh, int nspin, int bA, int bB, int
     TRY(phase_functional(ctx, g, *pa, pa->chunks.empty() ? Chunk() : pa->chunks[0], f, nspin, tot, 1.0, 0, pot, parts,
                          parts + g.nlit));
     if (f.ncomp > 0 && !pa->chunks.empty()) {
-      TRY(run_screen(ctx, g, ba, *pa));
-      TRY(run_screen(ctx, g, bb, *pb));
       TRY(phase_basis(ctx, g, ba, *pa, pa->chunks[0]));
       TRY(phase_basis(ctx, g, bb, *pb, pb->chunks[0], &ctx->phi2));
       for (int sp = 0; sp < nspin; ++sp)
@@ -1322,7 +1535,6 @@ int build_ab_nadd_device(sxc_ctx* ctx, int gh, int fh, int nspin, int bA, int bB
       const size_t nc2 = (size_t)bc.nbf * bc.nbf;
       Plan* pc = nullptr;
       TRY(get_plan(ctx, gh, bh, &pc));
-      TRY(run_screen(ctx, g, bc, *pc));
       for (const Chunk& c : pc->chunks) {
         TRY(phase_basis(ctx, g, bc, *pc, c));
         for (int sp = 0; sp < nspin; ++sp)
@@ -1338,8 +1550,6 @@ int build_ab_nadd_device(sxc_ctx* ctx, int gh, int fh, int nspin, int bA, int bB
       const Chunk& c0 = pa->chunks[0];
       TRY(phase_functional(ctx, g, *pa, c0, f, nspin, tot, 1.0, 0, pot, parts, nullptr));
       TRY(phase_functional(ctx, g, *pa, c0, f, nspin, dens, -1.0, 1, pot, parts + g.nlit, nullptr));
-      TRY(run_screen(ctx, g, ba, *pa));
-      TRY(run_screen(ctx, g, bb, *pb));
       TRY(phase_basis(ctx, g, ba, *pa, c0));
       TRY(phase_basis(ctx, g, bb, *pb, pb->chunks[0], &ctx->phi2));
       for (int sp = 0; sp < nspin; ++sp)
@@ -1363,6 +1573,16 @@ int sxc_debug_scatter_schedule(int n32, unsigned char* rounds40, int max_rounds)
   const std::vector<ScatterRound> r = build_scatter_schedule(n32);
   if (rounds40)
     for (int i = 0; i < (int)r.size() && i < max_rounds; ++i) std::memcpy(rounds40 + (size_t)40 * i, &r[i], 40);
+  return (int)r.size();
+}
+
+// host-only: the k_vmat_tma round schedule (64 bytes per round, struct ScatterRound2 of scatter_tma.cuh) for a block with n32 row
+// groups and ks k-steps per K chunk (2: chunks of 8 points, 4: chunks of 16 points); returns the number of rounds
+int sxc_debug_scatter_schedule2(int n32, int ks, unsigned char* rounds64, int max_rounds) {
+  if (n32 < 1 || n32 > 255 || (ks != 2 && ks != 4)) return SXC_ERR_INVALID;
+  const std::vector<ScatterRound2> r = build_scatter_schedule2(n32, ks);
+  if (rounds64)
+    for (int i = 0; i < (int)r.size() && i < max_rounds; ++i) std::memcpy(rounds64 + (size_t)64 * i, &r[i], 64);
   return (int)r.size();
 }
 
@@ -1403,6 +1623,14 @@ int sxc_create(sxc_ctx** out, int device) {
     return SXC_ERR_CUDA;
   }
   ctx->stream = ctx->own_stream;
+  if (const char* v = std::getenv("SXC_VMAT")) {  // development switch: 0 = cp.async kernel, 8 / 16 = TMA kernel with that K chunk
+    const int k = std::atoi(v);
+    if (k == 0 || k == 8 || k == 16) ctx->vmat_variant = k;
+  }
+  if (const char* v = std::getenv("SXC_DENS")) ctx->dens_variant = std::atoi(v) ? 1 : 0;
+  if (const char* v = std::getenv("SXC_SMEM_PAD")) ctx->smem_pad = std::max(0, std::atoi(v));
+  if (const char* v = std::getenv("SXC_DSEG")) ctx->dseg = std::max(1, std::atoi(v));
+  if (const char* v = std::getenv("SXC_VSEG")) ctx->vseg = std::max(1, std::atoi(v));
   *out = ctx;
   return SXC_OK;
 }
@@ -1780,7 +2008,6 @@ int sxc_density_on_grid(sxc_ctx* ctx, int grid, int basis, const double* P, doub
   CU(ctx->dP.ensure(nb2 * sizeof(double)));
   CU(cudaMemcpyAsync(ctx->dP.p, P, nb2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemsetAsync(g.dens.p, 0, (size_t)4 * N * sizeof(double), ctx->stream));
-  TRY(run_screen(ctx, g, b, *pp));
   for (const Chunk& c : pp->chunks) {
     TRY(phase_basis(ctx, g, b, *pp, c));
     TRY(phase_density(ctx, g, b, *pp, c, ctx->dP.as<double>(), g.dens.as<double>(), gx != nullptr, nullptr));
@@ -1810,7 +2037,6 @@ int sxc_basis_on_grid(sxc_ctx* ctx, int grid, int basis, int block, double* val,
   const Chunk* ch = nullptr;
   for (const Chunk& c : p.chunks)
     if (q >= c.slot0 && q < c.slot0 + c.nslots) ch = &c;
-  TRY(run_screen(ctx, g, b, p));
   ctx->phi_owner = 0;  // the single block is evaluated into the workspace: cached tiles are gone
   CU(ctx->phi.ensure(ch->doubles * sizeof(double)));
   k_basis<<<1, BASIS_GROUPS * BP, 0, ctx->stream>>>(g.view(), b.view(), p.view(), q, nullptr, ctx->phi.as<double>());
@@ -1940,7 +2166,6 @@ int sxc_scalar_to_matrix(sxc_ctx* ctx, int grid, int basis, double thr, const do
     CU(cudaMemcpyAsync(pot + 3 * N, gz, N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   }
   CU(cudaMemsetAsync(ctx->dOut.p, 0, nb2 * sizeof(double), ctx->stream));
-  TRY(run_screen(ctx, g, b, *pp));
   for (const Chunk& c : pp->chunks) {
     TRY(phase_basis(ctx, g, b, *pp, c));
     TRY(phase_scatter(ctx, g, b, *pp, c, gga, thr, pot, ctx->dOut.as<double>()));
@@ -1977,8 +2202,6 @@ int sxc_scalar_to_matrix_ab(sxc_ctx* ctx, int grid, int basis_a, int basis_b, do
   }
   CU(cudaMemsetAsync(ctx->dOut.p, 0, nab * sizeof(double), ctx->stream));
   if (!pa->chunks.empty()) {
-    TRY(run_screen(ctx, g, ba, *pa));
-    TRY(run_screen(ctx, g, bb, *pb));
     TRY(phase_basis(ctx, g, ba, *pa, pa->chunks[0]));
     TRY(phase_basis(ctx, g, bb, *pb, pb->chunks[0], &ctx->phi2));
     TRY(phase_scatter_ab(ctx, g, ba, *pa, *pb, gga, thr, pot, ctx->dOut.as<double>()));
@@ -2309,7 +2532,6 @@ int sxc_kernel_add(sxc_ctx* ctx, int kernel, int func, double sign, int ndens, c
       const size_t nc2 = (size_t)bc.nbf * bc.nbf;
       Plan* pc = nullptr;
       TRY(get_plan(ctx, gh, basis_c[i], &pc));
-      TRY(run_screen(ctx, g, bc, *pc));
       for (const Chunk& c : pc->chunks) {
         TRY(phase_basis(ctx, g, bc, *pc, c));
         for (int sp = 0; sp < nspin; ++sp)
@@ -2431,7 +2653,6 @@ int kernel_contract_impl(sxc_ctx* ctx, int grid, int basis_j, int nkern, const i
   const int launches0 = ctx->launches;
   {
     PhaseTimer t_all(ctx, T_TOTAL);
-    TRY(run_screen(ctx, g, b, p));
     TRY(wait_p_ready(ctx));
     {
       dim3 blk(32, 8), grd((b.nbf + 31) / 32, (b.nbf + 7) / 8);
@@ -2529,7 +2750,6 @@ int kernel_integrate_impl(sxc_ctx* ctx, int grid, int basis_i, double* F, double
   {
     PhaseTimer t_all(ctx, T_TOTAL);
     CU(cudaMemsetAsync(dF, 0, nmat * nb2 * sizeof(double), ctx->stream));
-    TRY(run_screen(ctx, g, b, p));
     for (const Chunk& c : p.chunks) {
       if (c.nslots == 0) continue;
       TRY(phase_basis(ctx, g, b, p, c));

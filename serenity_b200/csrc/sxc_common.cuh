@@ -1,6 +1,7 @@
 // sxc_common.cuh - shared device helpers (sm_100a): FP64 tensor-core MMA, cp.async, reductions.
 #pragma once
 
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -60,6 +61,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
       "DONE_%=:\n}\n" ::"r"(a),
       "r"(parity)
       : "memory");
+}
+
+// ---- TMA (cp.async.bulk.tensor) helpers: the producers of k_density_tma / k_vmat_tma ---------------------------------
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+  const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+// one box of a 2-D tensor map -> shared memory; completion is signalled to `bar` as transferred bytes
+__device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  const unsigned b = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(s),
+      "l"(map), "r"(b), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];\n" ::"l"(map) : "memory");
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

@@ -98,3 +98,52 @@ def test_scatter_schedule_covers_the_upper_triangle_once():
         assert sorted(seen) == [(i, j) for i in range(n32) for j in range(i, n32)]
         assert all(v == 3 for v in seen.values())
         assert nr <= (n32 * (n32 + 1) // 2 + 7) // 8 + n32  # never far from the slot bound
+
+
+def test_scatter_schedule_v2_partitions_every_tile_over_warps_and_k_steps():
+    """Host logic of k_vmat_tma (sxc_api.cu: build_scatter_schedule2): every upper-triangle warp tile sits in exactly one round;
+    inside it the k-steps of a chunk are partitioned (no gap, no overlap) over the warps that share the tile; a round stages at
+    most 6 row groups and uses at most 8 warps; the per-warp group indices repeat the staged slots; the schedule is never
+    longer (in DMMA time units: 16 per full tile and k-step share, 10 per diagonal tile) than the v1 schedule."""
+    from serenity_b200 import _lib
+    lib = _lib.load()
+
+    def units_v1(n32):
+        nr = lib.sxc_debug_scatter_schedule(n32, None, 0)
+        buf = np.zeros((nr, 40), dtype=np.uint8)
+        lib.sxc_debug_scatter_schedule(n32, buf.ctypes.data_as(C.c_void_p), nr)
+        tot = 0.0
+        for r in buf:
+            ta, tb, km = r[16:24], r[24:32], r[32:40]
+            tot += max((10 if ta[w] == tb[w] else 16) * bin(int(km[w])).count("1") / 2 for w in range(8) if ta[w] != 0xFF)
+        return tot
+
+    for ks in (2, 4):
+        full = (1 << ks) - 1
+        for n32 in list(range(1, 40)) + [64, 100, 255]:
+            nr = lib.sxc_debug_scatter_schedule2(n32, ks, None, 0)
+            assert nr > 0
+            buf = np.zeros((nr, 64), dtype=np.uint8)
+            assert lib.sxc_debug_scatter_schedule2(n32, ks, buf.ctypes.data_as(C.c_void_p), nr) == nr
+            seen, units = {}, 0.0
+            for ri, r in enumerate(buf):
+                ng, group, ta, tb, km, ga, gb = int(r[0]), r[8:16], r[16:24], r[24:32], r[32:40], r[40:48], r[48:56]
+                assert 1 <= ng <= 6 and len(set(group[:ng].tolist())) == ng and all(g < n32 for g in group[:ng])
+                in_round, cost = {}, 0.0
+                for w in range(8):
+                    if ta[w] == 0xFF:
+                        assert tb[w] == 0xFF
+                        continue
+                    assert ta[w] < ng and tb[w] < ng and 0 < km[w] <= full
+                    i, j = int(group[ta[w]]), int(group[tb[w]])
+                    assert i <= j and (int(ga[w]), int(gb[w])) == (i, j)
+                    assert in_round.get((i, j), 0) & int(km[w]) == 0      # k-steps of a tile are not done twice
+                    in_round[(i, j)] = in_round.get((i, j), 0) | int(km[w])
+                    cost = max(cost, (10 if i == j else 16) * bin(int(km[w])).count("1") / ks)
+                assert all(v == full for v in in_round.values())         # ... and none is left out
+                for t in in_round:
+                    assert t not in seen, "tile in two rounds"
+                    seen[t] = ri
+                units += cost
+            assert sorted(seen) == [(i, j) for i in range(n32) for j in range(i, n32)]
+            assert units <= units_v1(n32) + 1e-9, (ks, n32, units, units_v1(n32))
