@@ -142,6 +142,33 @@ int sxc_comm_destroy(sxc_ctx* ctx);
  * may be NULL */
 int sxc_comm_info(sxc_ctx* ctx, int* rank, int* world, int64_t* collectives, int* nccl_version);
 
+/* ---- one process, N GPUs -------------------------------------------------------------------------------- */
+/* The reference calls getMatrix() from its single SCF driver thread; a single-process host gets the multi-GPU build through a
+ * group (the form SURVEY.md section 8b sketches as sxc_create(ctx, ngpu, devices)): one context and one host worker thread per
+ * GPU, communicators created inside (ncclCommInitRank from every worker), every call below handed to all workers.  Handles
+ * returned by the group name the same object on every context.  A group build returns the all-reduced result through the
+ * first context's copy-back; P / V are caller-owned host buffers as in sxc_build_xc.  ngpu = 1 works (no NCCL needed). */
+typedef struct sxc_group sxc_group;
+int sxc_group_create(sxc_group** group, int ngpu, const int* devices /* NULL: 0 .. ngpu-1 */);
+void sxc_group_destroy(sxc_group* group);
+int sxc_group_size(const sxc_group* group);
+sxc_ctx* sxc_group_ctx(sxc_group* group, int rank); /* introspection (sxc_get_stats, sxc_comm_info) */
+const char* sxc_group_last_error(const sxc_group* group);
+int sxc_group_set_grid(sxc_group* group, int64_t npts, const double* xyz, const double* w, int blocksize, int* grid);
+int sxc_group_add_basis(sxc_group* group, int nshell, const int* l, const int* pure, const int* nprim, const int* first_bf,
+                        const double* centre, const double* alpha, const double* coeff, const double* normfac,
+                        double radial_threshold, int* basis);
+int sxc_group_set_functional(sxc_group* group, int ncomp, const int* basic_id, const double* mix, int* func);
+int sxc_group_release_grid(sxc_group* group, int grid);
+int sxc_group_release_basis(sxc_group* group, int basis);
+int sxc_group_build_xc(sxc_group* group, int grid, int basis, int func, int nspin, const double* P,
+                       double block_ave_threshold, double* V, double* E, double* nelec);
+int sxc_group_build_nadd_multi(sxc_group* group, int grid, int nfunc, const int* funcs, int nspin, int basis_act,
+                               const double* P_act, int nenv, const int* basis_env, const double* const* P_env, int env_frozen,
+                               double block_ave_threshold, int sum_matrices, double* V_act, double* E);
+int sxc_group_xc_gradient(sxc_group* group, int grid, int basis, int func, int nspin, const double* P, int natoms,
+                          const int* atom_of_bf, double* grad);
+
 /* ---- inputs -------------------------------------------------------------------------------------------- */
 /* replaces GridController::getGridPoints()/getWeights() (src/grid/GridController.cpp:31-50); re-upload only
  * on a Grid notify.  blocksize = settings grid.blocksize (128; 1..128 supported). */

@@ -24,6 +24,9 @@ SYMBOLS = [
     "sxc_comm_unique_id", "sxc_comm_init_rank", "sxc_comm_destroy", "sxc_comm_info", "sxc_release_grid", "sxc_release_basis",
     "sxc_release_functional", "sxc_host_alloc", "sxc_host_free", "sxc_build_nadd_multi", "sxc_build_nadd_multi_device",
     "sxc_debug_scatter_schedule2",
+    "sxc_group_create", "sxc_group_destroy", "sxc_group_size", "sxc_group_ctx", "sxc_group_last_error", "sxc_group_set_grid",
+    "sxc_group_add_basis", "sxc_group_set_functional", "sxc_group_release_grid", "sxc_group_release_basis", "sxc_group_build_xc",
+    "sxc_group_build_nadd_multi", "sxc_group_xc_gradient",
 ]
 
 

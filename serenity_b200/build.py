@@ -31,7 +31,8 @@ def build_cuda(force=False, verbose=False):
         nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-ccbin", "/usr/bin/g++", "-o", out,
                                                                               os.path.join(csrc, "sxc_api.cu"),
-                                                                              os.path.join(csrc, "basis_provider.cpp")]
+                                                                              os.path.join(csrc, "basis_provider.cpp"),
+                                                                              os.path.join(csrc, "group.cpp"), "-lpthread", "-ldl"]
         subprocess.check_call(cmd)
     return out
 

@@ -10,6 +10,8 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <cstdlib>
+
 #include <string>
 
 namespace sxc {
@@ -38,10 +40,15 @@ struct NcclApi {
 
   bool load() {
     if (handle) return true;
+    // 1. an explicit choice (SXC_NCCL_LIBRARY: a host that will load its own NCCL later, e.g. PyTorch's bundled copy, names that
+    //    file so that both end up with the same library), 2. the copy already in the process, 3. the system library
+    if (const char* path = std::getenv("SXC_NCCL_LIBRARY"))
+      if (*path) handle = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+    if (!handle) handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL | RTLD_NOLOAD);
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char* n : names) {
-      handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
       if (handle) break;
+      handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
     }
     if (!handle) {
       error = std::string("NCCL not found (dlopen libnccl.so.2): ") + dlerror();

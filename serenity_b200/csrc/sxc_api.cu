@@ -25,6 +25,7 @@
 #include "comm.h"
 #include "density_kernel.cuh"
 #include "functionals.cuh"
+#include "host_copy.h"
 #include "scatter_kernel.cuh"
 #include "scatter_tma.cuh"
 #include "gradient_kernels.cuh"
@@ -224,6 +225,13 @@ struct sxc_ctx {
     size_t bytes;
   };
   std::vector<PendingUpload> pending;  // host-buffer entry points: P matrices to upload when the build first needs them
+  // staged transfers of caller-owned pageable memory (host_copy.h): worker threads, page-locked staging buffers, chunk events
+  std::unique_ptr<HostCopier> copier;
+  void* h_up = nullptr;    // staging of the uploads (P)
+  void* h_down = nullptr;  // staging of the downloads (V)
+  size_t h_up_bytes = 0, h_down_bytes = 0;
+  std::vector<cudaEvent_t> chunk_events;
+  int copy_threads = 4;    // SXC_COPY_THREADS (0: leave pageable transfers to the driver)
   struct Stamp {
     int slot;
     cudaEvent_t a, b;
@@ -299,6 +307,73 @@ int set_kernel_attrs(sxc_ctx* ctx) {
   return SXC_OK;
 }
 
+constexpr size_t STAGE_MIN_BYTES = (size_t)1 << 20;  // smaller transfers are left to the driver
+constexpr size_t STAGE_CHUNK = (size_t)4 << 20;
+
+bool is_pageable(const void* p) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+
+int ensure_staging(sxc_ctx* ctx, void** buf, size_t* have, size_t need) {
+  if (!ctx->copier) ctx->copier = std::make_unique<HostCopier>(std::max(0, ctx->copy_threads - 1));
+  if (*have >= need) return SXC_OK;
+  if (*buf) cudaFreeHost(*buf);
+  *buf = nullptr;
+  *have = 0;
+  CU(cudaHostAlloc(buf, need, cudaHostAllocDefault));
+  *have = need;
+  return SXC_OK;
+}
+
+// caller memory -> device on `stream`: pageable sources of >= 1 MB go through the page-locked staging buffer at `stage_off`,
+// chunk by chunk (worker threads fill chunk i + 1 while the DMA engine moves chunk i)
+int staged_h2d(sxc_ctx* ctx, void* dst, const void* src, size_t bytes, size_t stage_off, cudaStream_t stream) {
+  if (ctx->copy_threads <= 0 || bytes < STAGE_MIN_BYTES || !is_pageable(src)) {
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
+    return SXC_OK;
+  }
+  char* st = static_cast<char*>(ctx->h_up) + stage_off;
+  for (size_t off = 0; off < bytes; off += STAGE_CHUNK) {
+    const size_t n = std::min(STAGE_CHUNK, bytes - off);
+    ctx->copier->copy(st + off, static_cast<const char*>(src) + off, n);
+    CU(cudaMemcpyAsync(static_cast<char*>(dst) + off, st + off, n, cudaMemcpyHostToDevice, stream));
+  }
+  return SXC_OK;
+}
+
+// device -> caller memory, complete on return (the stream is synchronised up to the copy)
+int staged_d2h(sxc_ctx* ctx, void* dst, const void* src, size_t bytes, cudaStream_t stream) {
+  if (ctx->copy_threads <= 0 || bytes < STAGE_MIN_BYTES || !is_pageable(dst)) {
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    return SXC_OK;
+  }
+  TRY(ensure_staging(ctx, &ctx->h_down, &ctx->h_down_bytes, bytes));
+  const size_t nchunk = (bytes + STAGE_CHUNK - 1) / STAGE_CHUNK;
+  while (ctx->chunk_events.size() < nchunk) {
+    cudaEvent_t e = nullptr;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->chunk_events.push_back(e);
+  }
+  char* st = static_cast<char*>(ctx->h_down);
+  for (size_t c = 0; c < nchunk; ++c) {
+    const size_t off = c * STAGE_CHUNK, n = std::min(STAGE_CHUNK, bytes - off);
+    CU(cudaMemcpyAsync(st + off, static_cast<const char*>(src) + off, n, cudaMemcpyDeviceToHost, stream));
+    CU(cudaEventRecord(ctx->chunk_events[c], stream));
+  }
+  for (size_t c = 0; c < nchunk; ++c) {
+    const size_t off = c * STAGE_CHUNK, n = std::min(STAGE_CHUNK, bytes - off);
+    CU(cudaEventSynchronize(ctx->chunk_events[c]));
+    ctx->copier->copy(static_cast<char*>(dst) + off, st + off, n);
+  }
+  return SXC_OK;
+}
+
 // P is first read by the density phase: an upload handed over by the caller (sxc_set_p_ready_event) or pending from a host-buffer
 // entry point is started / awaited only there.  For caller-owned (pageable) host memory cudaMemcpyAsync blocks the host while the
 // driver stages the data; issued here, behind the launches of the screening and basis kernels, that host time and the DMA on the
@@ -309,7 +384,14 @@ int wait_p_ready(sxc_ctx* ctx) {
       CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
       CU(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
     }
-    for (const auto& u : ctx->pending) CU(cudaMemcpyAsync(u.dst, u.src, u.bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    size_t total = 0;
+    for (const auto& u : ctx->pending) total += u.bytes;
+    if (ctx->copy_threads > 0 && total >= STAGE_MIN_BYTES) TRY(ensure_staging(ctx, &ctx->h_up, &ctx->h_up_bytes, total));
+    size_t off = 0;
+    for (const auto& u : ctx->pending) {
+      TRY(staged_h2d(ctx, u.dst, u.src, u.bytes, off, ctx->copy_stream));
+      off += u.bytes;
+    }
     ctx->pending.clear();
     CU(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
     ctx->p_ready = ctx->copy_done;
@@ -1628,6 +1710,7 @@ int sxc_create(sxc_ctx** out, int device) {
     if (k == 0 || k == 8 || k == 16) ctx->vmat_variant = k;
   }
   if (const char* v = std::getenv("SXC_DENS")) ctx->dens_variant = std::atoi(v) ? 1 : 0;
+  if (const char* v = std::getenv("SXC_COPY_THREADS")) ctx->copy_threads = std::max(0, std::min(16, std::atoi(v)));
   if (const char* v = std::getenv("SXC_SMEM_PAD")) ctx->smem_pad = std::max(0, std::atoi(v));
   if (const char* v = std::getenv("SXC_DSEG")) ctx->dseg = std::max(1, std::atoi(v));
   if (const char* v = std::getenv("SXC_VSEG")) ctx->vseg = std::max(1, std::atoi(v));
@@ -1656,6 +1739,10 @@ void sxc_destroy(sxc_ctx* ctx) {
     cudaEventDestroy(st.b);
   }
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->chunk_events) cudaEventDestroy(e);
+  if (ctx->h_up) cudaFreeHost(ctx->h_up);
+  if (ctx->h_down) cudaFreeHost(ctx->h_down);
+  ctx->copier.reset();
   if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -1919,8 +2006,8 @@ int sxc_build_xc(sxc_ctx* ctx, int grid, int basis, int func, int nspin, const d
   ctx->timing = 0;
   if (rc != SXC_OK) return abort_build(ctx, rc);
   std::vector<double> tail(2);
-  if (V) CU(cudaMemcpyAsync(V, ctx->dOut.p, nv * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(tail.data(), ctx->dOut.as<double>() + nv, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (V) TRY(staged_d2h(ctx, V, ctx->dOut.p, nv * sizeof(double), ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   collect_timers(ctx);
   *E = tail[0];
@@ -1982,8 +2069,8 @@ int sxc_build_nadd_multi(sxc_ctx* ctx, int grid, int nfunc, const int* funcs, in
                              env_frozen, thr, sum_matrices, ctx->dOut.as<double>(), true);
   ctx->timing = 0;
   if (rc != SXC_OK) return abort_build(ctx, rc);
-  if (V_act) CU(cudaMemcpyAsync(V_act, ctx->dOut.p, nV * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(E, ctx->dOut.as<double>() + nV, nE * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (V_act) TRY(staged_d2h(ctx, V_act, ctx->dOut.p, nV * sizeof(double), ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   collect_timers(ctx);
   return SXC_OK;

@@ -72,7 +72,10 @@ class Notifying {
 
 namespace B200 {
 
-// One device context per process and GPU (sxc_create); shared by all potentials of the process.
+// The device side of the process, shared by all potentials: ONE GPU (sxc_create) or, for a single-process host like Serenity,
+// N GPUs of the node as a group (sxc_group_create: one context + one host worker thread per GPU, grid blocks sharded, one
+// ncclAllReduce of [V | E | N] inside the library per build).  The potentials only use the dispatchers below, so the same
+// FuncPotential / NAddFuncPotential code runs on either.
 class XCDevice {
  public:
   explicit XCDevice(int device = 0) {
@@ -81,16 +84,75 @@ class XCDevice {
       throw SerenityError("serenity_xc_b200: no usable CUDA device " + std::to_string(device) + " (status " +
                           std::to_string(rc) + "); the XC build has no CPU fallback");
   }
-  ~XCDevice() { sxc_destroy(_ctx); }
+  explicit XCDevice(const std::vector<int>& devices) {
+    if (devices.size() == 1) {
+      const int rc = sxc_create(&_ctx, devices[0]);
+      if (rc != SXC_OK) throw SerenityError("serenity_xc_b200: no usable CUDA device (status " + std::to_string(rc) + ")");
+      return;
+    }
+    const int rc = sxc_group_create(&_group, (int)devices.size(), devices.data());
+    if (rc != SXC_OK)
+      throw SerenityError("serenity_xc_b200: could not create a group of " + std::to_string(devices.size()) +
+                          " GPUs (status " + std::to_string(rc) + "); the XC build has no CPU fallback");
+  }
+  ~XCDevice() {
+    if (_group) sxc_group_destroy(_group);
+    if (_ctx) sxc_destroy(_ctx);
+  }
   XCDevice(const XCDevice&) = delete;
   XCDevice& operator=(const XCDevice&) = delete;
-  sxc_ctx* get() const { return _ctx; }
+  int nGPUs() const { return _group ? sxc_group_size(_group) : 1; }
+  // the single context, for the classes that are not sharded through a group (stage-level classes, AB potentials, LR-TDDFT kernel)
+  sxc_ctx* get() const {
+    if (_group) throw SerenityError("serenity_xc_b200: this class runs on a single-GPU XCDevice (the group shards FuncPotential and "
+                                    "NAddFuncPotential builds only)");
+    return _ctx;
+  }
   void check(int rc) const {
-    if (rc != SXC_OK) throw SerenityError(std::string("serenity_xc_b200: ") + sxc_last_error(_ctx));
+    if (rc != SXC_OK)
+      throw SerenityError(std::string("serenity_xc_b200: ") + (_group ? sxc_group_last_error(_group) : sxc_last_error(_ctx)));
+  }
+  // ---- dispatchers (one GPU or the group)
+  int setGrid(int64_t n, const double* xyz, const double* w, int blocksize) const {
+    int h = -1;
+    check(_group ? sxc_group_set_grid(_group, n, xyz, w, blocksize, &h) : sxc_set_grid(_ctx, n, xyz, w, blocksize, &h));
+    return h;
+  }
+  int addBasis(int nshell, const int* l, const int* pure, const int* nprim, const int* firstBf, const double* centre,
+               const double* alpha, const double* coeff, const double* normfac, double thr) const {
+    int h = -1;
+    check(_group ? sxc_group_add_basis(_group, nshell, l, pure, nprim, firstBf, centre, alpha, coeff, normfac, thr, &h)
+                 : sxc_add_basis(_ctx, nshell, l, pure, nprim, firstBf, centre, alpha, coeff, normfac, thr, &h));
+    return h;
+  }
+  int setFunctional(const std::vector<int>& ids, const std::vector<double>& mix) const {
+    int h = -1;
+    check(_group ? sxc_group_set_functional(_group, (int)ids.size(), ids.data(), mix.data(), &h)
+                 : sxc_set_functional(_ctx, (int)ids.size(), ids.data(), mix.data(), &h));
+    return h;
+  }
+  void releaseGrid(int h) const noexcept { _group ? sxc_group_release_grid(_group, h) : sxc_release_grid(_ctx, h); }
+  void releaseBasis(int h) const noexcept { _group ? sxc_group_release_basis(_group, h) : sxc_release_basis(_ctx, h); }
+  void buildXC(int grid, int basis, int func, int nspin, const double* P, double thr, double* V, double* E, double* nel) const {
+    check(_group ? sxc_group_build_xc(_group, grid, basis, func, nspin, P, thr, V, E, nel)
+                 : sxc_build_xc(_ctx, grid, basis, func, nspin, P, thr, V, E, nel));
+  }
+  void buildNAddMulti(int grid, int nfunc, const int* funcs, int nspin, int basisAct, const double* Pact, int nenv,
+                      const int* basisEnv, const double* const* Penv, int envTag, double thr, bool sumMatrices, double* V,
+                      double* E) const {
+    check(_group ? sxc_group_build_nadd_multi(_group, grid, nfunc, funcs, nspin, basisAct, Pact, nenv, basisEnv, Penv, envTag, thr,
+                                              sumMatrices ? 1 : 0, V, E)
+                 : sxc_build_nadd_multi(_ctx, grid, nfunc, funcs, nspin, basisAct, Pact, nenv, basisEnv, Penv, envTag, thr,
+                                        sumMatrices ? 1 : 0, V, E));
+  }
+  void xcGradient(int grid, int basis, int func, int nspin, const double* P, int natoms, const int* atomOfBf, double* grad) const {
+    check(_group ? sxc_group_xc_gradient(_group, grid, basis, func, nspin, P, natoms, atomOfBf, grad)
+                 : sxc_xc_gradient(_ctx, grid, basis, func, nspin, P, natoms, atomOfBf, grad));
   }
 
  private:
   sxc_ctx* _ctx = nullptr;
+  sxc_group* _group = nullptr;
 };
 
 }  // namespace B200
@@ -100,11 +162,20 @@ class GridController : public Notifying {
  public:
   GridController(std::vector<double> xyz, std::vector<double> weights, int blocksize = 128)
     : _xyz(std::move(xyz)), _w(std::move(weights)), _blocksize(blocksize) {}
+  GridController(const GridController&) = delete;  // (owns a device handle)
+  GridController& operator=(const GridController&) = delete;
   const std::vector<double>& getGridPoints() const { return _xyz; }
   const std::vector<double>& getWeights() const { return _w; }
   unsigned int getNGridPoints() const { return (unsigned int)_w.size(); }
-  int handle(const B200::XCDevice& dev) {  // lazily uploaded (RememberingFactory-style key: this object)
-    if (_handle < 0) dev.check(sxc_set_grid(dev.get(), (int64_t)_w.size(), _xyz.data(), _w.data(), _blocksize, &_handle));
+  ~GridController() {  // the device copy (points, per-point work arrays, screening plans) goes with the host object
+    if (_handle >= 0)
+      if (auto d = _dev.lock()) d->releaseGrid(_handle);
+  }
+  int handle(const std::shared_ptr<B200::XCDevice>& dev) {  // lazily uploaded (RememberingFactory-style key: this object)
+    if (_handle < 0) {
+      _handle = dev->setGrid((int64_t)_w.size(), _xyz.data(), _w.data(), _blocksize);
+      _dev = dev;
+    }
     return _handle;
   }
 
@@ -112,6 +183,7 @@ class GridController : public Notifying {
   std::vector<double> _xyz, _w;
   int _blocksize;
   int _handle = -1;
+  std::weak_ptr<B200::XCDevice> _dev;
 };
 
 // basis/BasisController.h + basis/Shell.h: what BasisFunctionOnGridController reads from the shells.
@@ -125,6 +197,8 @@ class BasisController {
  public:
   BasisController(ShellTable t, int nBasisFunctions, double radialThreshold = 1e-9)
     : _t(std::move(t)), _nbf(nBasisFunctions), _thr(radialThreshold) {}
+  BasisController(const BasisController& o) : _t(o._t), _nbf(o._nbf), _thr(o._thr) {}  // (a copy owns no device handle yet)
+  BasisController& operator=(const BasisController&) = delete;
   // AtomCenteredBasisController + BasisFunctionProvider (basis/BasisFunctionProvider.cpp:32-140): geometry + basis-set file
   // of the reference's data/basis directory -> shells (row f-2, sxc_shell_table_from_file)
   static std::shared_ptr<BasisController> fromFile(const std::string& path, const std::string& label,
@@ -150,10 +224,16 @@ class BasisController {
   unsigned int getNBasisFunctions() const { return (unsigned int)_nbf; }
   const std::vector<int>& getAtomIndicesOfBasis() const { return _t.atomOfBf; }
   int getNAtoms() const { return _t.nAtoms; }
-  int handle(const B200::XCDevice& dev) {
-    if (_handle < 0)
-      dev.check(sxc_add_basis(dev.get(), (int)_t.l.size(), _t.l.data(), _t.pure.data(), _t.nprim.data(), _t.firstBf.data(),
-                              _t.centre.data(), _t.alpha.data(), _t.coeff.data(), _t.normfac.data(), _thr, &_handle));
+  ~BasisController() {  // a new geometry makes a new basis: the old shell table and its plans leave the device
+    if (_handle >= 0)
+      if (auto d = _dev.lock()) d->releaseBasis(_handle);
+  }
+  int handle(const std::shared_ptr<B200::XCDevice>& dev) {
+    if (_handle < 0) {
+      _handle = dev->addBasis((int)_t.l.size(), _t.l.data(), _t.pure.data(), _t.nprim.data(), _t.firstBf.data(), _t.centre.data(),
+                              _t.alpha.data(), _t.coeff.data(), _t.normfac.data(), _thr);
+      _dev = dev;
+    }
     return _handle;
   }
 
@@ -162,6 +242,7 @@ class BasisController {
   int _nbf;
   double _thr;
   int _handle = -1;
+  std::weak_ptr<B200::XCDevice> _dev;
 };
 
 // data/matrices/DensityMatrixController.h: owns P, notifies dependants when it changes.
@@ -234,9 +315,32 @@ class Potential {
 
 namespace detail {
 inline int functionalHandle(const B200::XCDevice& dev, const Functional& f) {
-  int h = -1;
-  dev.check(sxc_set_functional(dev.get(), (int)f.basicFunctionals.size(), f.basicFunctionals.data(), f.mixingFactors.data(), &h));
-  return h;
+  return dev.setFunctional(f.basicFunctionals, f.mixingFactors);  // (equal definitions share one handle inside the library)
+}
+// Tag of an environment STATE for the frozen-environment cache of the NAdd builds (sxc_build_nadd: env_frozen).  All NAdd
+// objects that watch the same environment density controllers on the same grid share one state - the XC and the kinetic
+// object of an FDE iteration are served by one cached sum of environment densities - and a changed environment density
+// draws a new tag for all of them.
+struct EnvState {
+  int tag;
+};
+inline int nextEnvTag() {
+  static int counter = 0;
+  return ++counter;
+}
+inline std::shared_ptr<EnvState> sharedEnvState(const std::vector<const void*>& key) {
+  static std::vector<std::pair<std::vector<const void*>, std::weak_ptr<EnvState>>> registry;
+  for (auto it = registry.begin(); it != registry.end();) {
+    if (it->second.expired()) {
+      it = registry.erase(it);
+      continue;
+    }
+    if (it->first == key) return it->second.lock();
+    ++it;
+  }
+  auto st = std::make_shared<EnvState>(EnvState{nextEnvTag()});
+  registry.emplace_back(key, st);
+  return st;
 }
 template<Options::SCF_MODES SCFMode>
 constexpr int nspin() {
@@ -265,9 +369,8 @@ class FuncPotential : public Potential<SCFMode>, public ObjectSensitive {
       const int nb = (int)_dMatController->getBasisController()->getNBasisFunctions();
       auto V = std::make_unique<FockMatrix>(nb, nb * detail::nspin<SCFMode>());
       double nel = 0.0;
-      _dev->check(sxc_build_xc(_dev->get(), _grid->handle(*_dev), _dMatController->getBasisController()->handle(*_dev), _func,
-                               detail::nspin<SCFMode>(), _dMatController->getDensityMatrix().data(), _thr, V->data(), &_energy,
-                               &nel));
+      _dev->buildXC(_grid->handle(_dev), _dMatController->getBasisController()->handle(_dev), _func, detail::nspin<SCFMode>(),
+                    _dMatController->getDensityMatrix().data(), _thr, V->data(), &_energy, &nel);
       _nElectronsOnGrid = nel;
       _potential = std::move(V);
     }
@@ -282,9 +385,9 @@ class FuncPotential : public Potential<SCFMode>, public ObjectSensitive {
     if (basis->getNAtoms() <= 0 || basis->getAtomIndicesOfBasis().size() != basis->getNBasisFunctions())
       throw SerenityError("FuncPotential::getGeomGradients: the basis carries no atom indices");
     Matrix grad(basis->getNAtoms(), 3);
-    _dev->check(sxc_xc_gradient(_dev->get(), _grid->handle(*_dev), basis->handle(*_dev), _func, detail::nspin<SCFMode>(),
-                                _dMatController->getDensityMatrix().data(), basis->getNAtoms(),
-                                basis->getAtomIndicesOfBasis().data(), grad.data()));
+    _dev->xcGradient(_grid->handle(_dev), basis->handle(_dev), _func, detail::nspin<SCFMode>(),
+                     _dMatController->getDensityMatrix().data(), basis->getNAtoms(), basis->getAtomIndicesOfBasis().data(),
+                     grad.data());
     return grad;
   }
   void notify() override final { _potential = nullptr; }  // FuncPotential.h:107-109
@@ -318,7 +421,7 @@ class DensityOnGridCalculator {
   DensityOnGrid calcDensityAndGradientOnGrid(const DensityMatrix& P) {
     const size_t n = _grid->getNGridPoints();
     DensityOnGrid d{std::vector<double>(n), std::vector<double>(n), std::vector<double>(n), std::vector<double>(n)};
-    _dev->check(sxc_density_on_grid(_dev->get(), _grid->handle(*_dev), _basis->handle(*_dev), P.data(), d.rho.data(), d.x.data(),
+    _dev->check(sxc_density_on_grid(_dev->get(), _grid->handle(_dev), _basis->handle(_dev), P.data(), d.rho.data(), d.x.data(),
                                     d.y.data(), d.z.data()));
     return d;
   }
@@ -364,7 +467,7 @@ class ScalarOperatorToMatrixAdder {
   void addScalarOperatorToMatrix(Matrix& m, const std::vector<double>& scalar, const std::vector<double>& gx = {},
                                  const std::vector<double>& gy = {}, const std::vector<double>& gz = {}) {
     const bool gga = !gx.empty();
-    _dev->check(sxc_scalar_to_matrix(_dev->get(), _grid->handle(*_dev), _basis->handle(*_dev), _thr, scalar.data(),
+    _dev->check(sxc_scalar_to_matrix(_dev->get(), _grid->handle(_dev), _basis->handle(_dev), _thr, scalar.data(),
                                      gga ? gx.data() : nullptr, gga ? gy.data() : nullptr, gga ? gz.data() : nullptr, m.data()));
   }
 
@@ -375,28 +478,76 @@ class ScalarOperatorToMatrixAdder {
   double _thr;
 };
 
-// potentials/NAddFuncPotential.h:118-155 (first constructor; exact-exchange and solvation parts are ERI work and stay
-// with the reference's ExchangeInteractionPotential).
+// potentials/NAddFuncPotential.h:118-155 (exact-exchange and solvation parts are ERI work and stay with the reference's
+// ExchangeInteractionPotential).  Both constructors of the reference are mirrored; getGridPotentialDerivative()
+// (NAddFuncPotential.h:207) is declared there but has no definition and no caller, so there is nothing to mirror.
+template<Options::SCF_MODES SCFMode>
+class FDEPotentials;
 template<Options::SCF_MODES SCFMode>
 class NAddFuncPotential : public Potential<SCFMode>, public ObjectSensitive {
  public:
-  NAddFuncPotential(std::shared_ptr<B200::XCDevice> device, std::shared_ptr<DensityMatrixController<SCFMode>> activeDMat,
-                    std::vector<std::shared_ptr<DensityMatrixController<SCFMode>>> envDMats,
+  using DMC = DensityMatrixController<SCFMode>;
+  NAddFuncPotential(std::shared_ptr<B200::XCDevice> device, std::shared_ptr<DMC> activeDMat, std::vector<std::shared_ptr<DMC>> envDMats,
                     std::shared_ptr<GridController> grid, Functional functional, double blockAveThreshold = 1e-11)
     : _dev(std::move(device)), _act(std::move(activeDMat)), _env(std::move(envDMats)), _grid(std::move(grid)),
-      _functional(std::move(functional)), _thr(blockAveThreshold), _func(detail::functionalHandle(*_dev, _functional)) {}
+      _functional(std::move(functional)), _thr(blockAveThreshold), _func(detail::functionalHandle(*_dev, _functional)) {
+    initEnvState();
+  }
+  // Second constructor (NAddFuncPotential.cpp:105-176): further exactly treated subsystems are folded into the active density
+  // through their basis-set projections, P_comb = P_act + sum_I BtoA_I^T P_I BtoA_I (BtoA_I: nbf_I x nbf_act; the reference
+  // passes Eigen::SparseMatrix, here a dense Matrix).  As in the reference the combination is formed ONCE, here, from the
+  // densities of that moment (:142-151 build a fresh controller around the combined matrix).
+  NAddFuncPotential(std::shared_ptr<B200::XCDevice> device, std::shared_ptr<DMC> activeDMat,
+                    std::vector<std::shared_ptr<DMC>> otherExactDmats, const std::vector<std::shared_ptr<Matrix>>& BtoAProjections,
+                    std::vector<std::shared_ptr<DMC>> envDMats, std::shared_ptr<GridController> grid, Functional functional,
+                    double blockAveThreshold = 1e-11)
+    : _dev(std::move(device)), _act(std::move(activeDMat)), _otherExact(std::move(otherExactDmats)), _env(std::move(envDMats)),
+      _grid(std::move(grid)), _functional(std::move(functional)), _thr(blockAveThreshold),
+      _func(detail::functionalHandle(*_dev, _functional)) {
+    if (BtoAProjections.size() != _otherExact.size())
+      throw SerenityError("NAddFuncPotential: one BtoA projection per exactly treated subsystem is needed");
+    const int nA = (int)_act->getBasisController()->getNBasisFunctions();
+    const int ns = detail::nspin<SCFMode>();
+    DensityMatrix comb = _act->getDensityMatrix();
+    for (size_t I = 0; I < _otherExact.size(); ++I) {
+      const Matrix& B = *BtoAProjections[I];
+      const DensityMatrix& D = _otherExact[I]->getDensityMatrix();
+      const int nI = B.rows();
+      if (B.cols() != nA || D.rows() != nI) throw SerenityError("NAddFuncPotential: BtoA projection has the wrong shape");
+      Matrix T(nI, nA);  // T = D_spin * BtoA, then comb_spin += BtoA^T * T
+      for (int sp = 0; sp < ns; ++sp) {
+        const double* Dp = D.data() + (size_t)sp * nI * nI;
+        for (int a = 0; a < nA; ++a)
+          for (int i = 0; i < nI; ++i) {
+            double t = 0.0;
+            for (int j = 0; j < nI; ++j) t += Dp[i + (size_t)nI * j] * B(j, a);
+            T(i, a) = t;
+          }
+        double* Cp = comb.data() + (size_t)sp * nA * nA;
+        for (int b = 0; b < nA; ++b)
+          for (int a = 0; a < nA; ++a) {
+            double t = 0.0;
+            for (int i = 0; i < nI; ++i) t += B(i, a) * T(i, b);
+            Cp[a + (size_t)nA * b] += t;
+          }
+      }
+    }
+    _combined = std::make_shared<DMC>(_act->getBasisController(), std::move(comb));
+    initEnvState();
+  }
 
-  struct EnvWatcher : ObjectSensitive {  // a changed environment density invalidates the cached rho_env on the grid
+  struct EnvWatcher : ObjectSensitive {  // a changed environment density: new tag -> the cached rho_env on the grid is not used
     explicit EnvWatcher(NAddFuncPotential* o) : owner(o) {}
     void notify() override {
       owner->_potential = nullptr;
-      owner->_envFrozen = false;
+      owner->_envState->tag = detail::nextEnvTag();
     }
     NAddFuncPotential* owner;
   };
   void registerSensitivity(const std::shared_ptr<NAddFuncPotential>& self) {
     _act->addSensitiveObject(self);
     _grid->addSensitiveObject(self);
+    for (auto& o : _otherExact) o->addSensitiveObject(self);
     _watcher = std::make_shared<EnvWatcher>(this);
     for (auto& e : _env) e->addSensitiveObject(_watcher);
   }
@@ -407,18 +558,12 @@ class NAddFuncPotential : public Potential<SCFMode>, public ObjectSensitive {
       auto V = std::make_unique<FockMatrix>(nb, nb * detail::nspin<SCFMode>());
       std::vector<int> be;
       std::vector<const double*> pe;
-      for (auto& e : _env) {
-        be.push_back(e->getBasisController()->handle(*_dev));
-        pe.push_back(e->getDensityMatrix().data());
-      }
-      _energyParts.assign(2 + _env.size(), 0.0);
-      _dev->check(sxc_build_nadd(_dev->get(), _grid->handle(*_dev), _func, detail::nspin<SCFMode>(),
-                                 _act->getBasisController()->handle(*_dev), _act->getDensityMatrix().data(), (int)_env.size(),
-                                 be.data(), pe.data(), _envFrozen ? 1 : 0, _thr, V->data(), _energyParts.data()));
-      _energy = _energyParts[0] - _energyParts[1];  // E[rho_tot] - E[rho_act] - sum_env E[rho_env], :249, :282-286
-      for (size_t i = 2; i < _energyParts.size(); ++i) _energy -= _energyParts[i];
-      _envFrozen = true;
-      _potential = std::move(V);
+      envArguments(be, pe);
+      std::vector<double> parts(2 + _env.size(), 0.0);
+      _dev->buildNAddMulti(_grid->handle(_dev), 1, &_func, detail::nspin<SCFMode>(), _act->getBasisController()->handle(_dev),
+                           activeDensity().data(), (int)_env.size(), be.data(), pe.data(), _envState->tag, _thr, false, V->data(),
+                           parts.data());
+      setResult(std::move(V), parts);
     }
     return *_potential;
   }
@@ -426,39 +571,114 @@ class NAddFuncPotential : public Potential<SCFMode>, public ObjectSensitive {
     if (!_potential) getMatrix();
     return _energy;
   }
+  // NAddFuncPotential.cpp:180-189: scaling * sum_spin sum_ij V_ij P_ij
+  double getLinearizedEnergy(const DensityMatrix& P, double scaling) {
+    if (!_potential) getMatrix();
+    const FockMatrix& pot = *_potential;
+    if ((size_t)P.rows() * P.cols() != (size_t)pot.rows() * pot.cols())
+      throw SerenityError("NAddFuncPotential::getLinearizedEnergy: density matrix and potential do not match");
+    double e = 0.0;
+    for (size_t k = 0; k < pot.values.size(); ++k) e += pot.values[k] * P.values[k];
+    return scaling * e;
+  }
   Matrix getGeomGradients() override final {  // NAddFuncPotential.cpp:329-493
     auto basis = _act->getBasisController();
     if (basis->getNAtoms() <= 0 || basis->getAtomIndicesOfBasis().size() != basis->getNBasisFunctions())
       throw SerenityError("NAddFuncPotential: Missed gradient element in gradient evaluation.");  // :367-369
     std::vector<int> be;
     std::vector<const double*> pe;
-    for (auto& e : _env) {
-      be.push_back(e->getBasisController()->handle(*_dev));
-      pe.push_back(e->getDensityMatrix().data());
-    }
+    envArguments(be, pe);
     Matrix grad(basis->getNAtoms(), 3);
-    _dev->check(sxc_nadd_gradient(_dev->get(), _grid->handle(*_dev), _func, detail::nspin<SCFMode>(), basis->handle(*_dev),
-                                  _act->getDensityMatrix().data(), (int)_env.size(), be.data(), pe.data(), basis->getNAtoms(),
+    _dev->check(sxc_nadd_gradient(_dev->get(), _grid->handle(_dev), _func, detail::nspin<SCFMode>(), basis->handle(_dev),
+                                  activeDensity().data(), (int)_env.size(), be.data(), pe.data(), basis->getNAtoms(),
                                   basis->getAtomIndicesOfBasis().data(), grad.data()));
-    _envFrozen = false;  // the gradient reuses the device buffer of the cached environment density
+    _envState->tag = detail::nextEnvTag();  // the gradient reuses the device buffer of the cached environment density
     return grad;
   }
   void notify() override final { _potential = nullptr; }
   const std::vector<double>& getEnergyParts() const { return _energyParts; }
+  Functional getFunctional() { return _functional; }
+  std::shared_ptr<GridController> getGridController() { return _grid; }
 
  private:
+  friend class FDEPotentials<SCFMode>;
+  void initEnvState() {
+    std::vector<const void*> key{_grid.get()};
+    for (auto& e : _env) key.push_back(e.get());
+    _envState = detail::sharedEnvState(key);
+  }
+  const DensityMatrix& activeDensity() const { return (_combined ? _combined : _act)->getDensityMatrix(); }
+  void envArguments(std::vector<int>& be, std::vector<const double*>& pe) {
+    for (auto& e : _env) {
+      be.push_back(e->getBasisController()->handle(_dev));
+      pe.push_back(e->getDensityMatrix().data());
+    }
+  }
+  void setResult(std::unique_ptr<FockMatrix> V, const std::vector<double>& parts) {
+    _energyParts = parts;
+    _energy = parts[0] - parts[1];  // E[rho_tot] - E[rho_act] - sum_env E[rho_env], :249, :282-286
+    for (size_t i = 2; i < parts.size(); ++i) _energy -= parts[i];
+    _potential = std::move(V);
+  }
+
   std::shared_ptr<B200::XCDevice> _dev;
-  std::shared_ptr<DensityMatrixController<SCFMode>> _act;
-  std::vector<std::shared_ptr<DensityMatrixController<SCFMode>>> _env;
+  std::shared_ptr<DMC> _act;
+  std::vector<std::shared_ptr<DMC>> _otherExact;
+  std::shared_ptr<DMC> _combined;  // second constructor: P_act + projected exactly treated densities
+  std::vector<std::shared_ptr<DMC>> _env;
   std::shared_ptr<GridController> _grid;
   Functional _functional;
   double _thr;
   int _func;
   std::shared_ptr<EnvWatcher> _watcher;
+  std::shared_ptr<detail::EnvState> _envState;
   std::unique_ptr<FockMatrix> _potential;
   std::vector<double> _energyParts;
   double _energy = 0.0;
-  bool _envFrozen = false;
+};
+
+// potentials/bundles/FDEPotentials.h: the part of the bundle that lives on the grid.  FDEPotentials::getFockMatrix
+// (FDEPotentials.cpp:43-61) adds naddXC->getMatrix() and naddKin->getMatrix() of the same active / environment densities; here
+// both objects are evaluated in ONE device pass (sxc_build_nadd_multi: rho_act contracted once, both functionals on the same
+// densities, one scatter per object) and each object receives its own matrix and energies, exactly as if it had been asked
+// alone - later getMatrix() / getEnergy() calls on the objects are served from their caches.
+template<Options::SCF_MODES SCFMode>
+class FDEPotentials {
+ public:
+  FDEPotentials(std::shared_ptr<NAddFuncPotential<SCFMode>> naddXC, std::shared_ptr<NAddFuncPotential<SCFMode>> naddKin)
+    : _xc(std::move(naddXC)), _kin(std::move(naddKin)) {
+    if (_xc->_act != _kin->_act || _xc->_grid != _kin->_grid || _xc->_env != _kin->_env || _xc->_combined || _kin->_combined)
+      throw SerenityError("FDEPotentials: the non-additive XC and kinetic potentials must share active density, environment and grid");
+  }
+  // sum of the two non-additive matrices (what the bundle adds to the Fock matrix)
+  FockMatrix getNAddFockMatrix() {
+    if (!_xc->_potential || !_kin->_potential) {
+      auto& x = *_xc;
+      const int nb = (int)x._act->getBasisController()->getNBasisFunctions();
+      const int ns = detail::nspin<SCFMode>();
+      const size_t nv = (size_t)nb * nb * ns, ne = 2 + x._env.size();
+      std::vector<int> be;
+      std::vector<const double*> pe;
+      x.envArguments(be, pe);
+      std::vector<double> V(2 * nv), parts(2 * ne);
+      const int funcs[2] = {_xc->_func, _kin->_func};
+      x._dev->buildNAddMulti(x._grid->handle(x._dev), 2, funcs, ns, x._act->getBasisController()->handle(x._dev),
+                             x._act->getDensityMatrix().data(), (int)x._env.size(), be.data(), pe.data(), x._envState->tag, x._thr,
+                             false, V.data(), parts.data());
+      for (int k = 0; k < 2; ++k) {
+        auto M = std::make_unique<FockMatrix>(nb, nb * ns);
+        std::copy(V.begin() + k * nv, V.begin() + (k + 1) * nv, M->values.begin());
+        (k == 0 ? _xc : _kin)->setResult(std::move(M), std::vector<double>(parts.begin() + k * ne, parts.begin() + (k + 1) * ne));
+      }
+    }
+    FockMatrix F = _xc->getMatrix();
+    const FockMatrix& K = _kin->getMatrix();
+    for (size_t i = 0; i < F.values.size(); ++i) F.values[i] += K.values[i];
+    return F;
+  }
+
+ private:
+  std::shared_ptr<NAddFuncPotential<SCFMode>> _xc, _kin;
 };
 
 // potentials/ABFockMatrixConstruction/ABFuncPotential.h: the XC operator between two different basis
@@ -488,12 +708,12 @@ class ABFuncPotential : public ObjectSensitive {
       std::vector<int> bc;
       std::vector<const double*> pc;
       for (auto& d : _dMats) {
-        bc.push_back(d->getBasisController()->handle(*_dev));
+        bc.push_back(d->getBasisController()->handle(_dev));
         pc.push_back(d->getDensityMatrix().data());
       }
       double e[2] = {0.0, 0.0};
-      _dev->check(sxc_build_ab(_dev->get(), _grid->handle(*_dev), _func, detail::nspin<SCFMode>(), _basisA->handle(*_dev),
-                               _basisB->handle(*_dev), (int)bc.size(), bc.data(), pc.data(), _thr, V->data(), e));
+      _dev->check(sxc_build_ab(_dev->get(), _grid->handle(_dev), _func, detail::nspin<SCFMode>(), _basisA->handle(_dev),
+                               _basisB->handle(_dev), (int)bc.size(), bc.data(), pc.data(), _thr, V->data(), e));
       _abPotential = std::move(V);
     }
     return *_abPotential;
@@ -536,11 +756,11 @@ class ABNAddFuncPotential : public ObjectSensitive {
       std::vector<int> be;
       std::vector<const double*> pe;
       for (auto& d : _env) {
-        be.push_back(d->getBasisController()->handle(*_dev));
+        be.push_back(d->getBasisController()->handle(_dev));
         pe.push_back(d->getDensityMatrix().data());
       }
-      _dev->check(sxc_build_ab_nadd(_dev->get(), _grid->handle(*_dev), _func, detail::nspin<SCFMode>(), _basisA->handle(*_dev),
-                                    _basisB->handle(*_dev), _act->getBasisController()->handle(*_dev),
+      _dev->check(sxc_build_ab_nadd(_dev->get(), _grid->handle(_dev), _func, detail::nspin<SCFMode>(), _basisA->handle(_dev),
+                                    _basisB->handle(_dev), _act->getBasisController()->handle(_dev),
                                     _act->getDensityMatrix().data(), (int)be.size(), be.data(), pe.data(), _thr, V->data()));
       _abPotential = std::move(V);
     }
@@ -575,13 +795,13 @@ class Kernel {
     : _dev(std::move(device)), _grid(std::move(grid)), _dMats(std::move(dMats)), _gga(gga) {
     if (_dMats.empty() || funcs.size() != _dMats.size())
       throw SerenityError("Kernel: one functional per subsystem is needed");
-    const int g = _grid->handle(*_dev);
+    const int g = _grid->handle(_dev);
     const int nspin = detail::nspin<SCFMode>();
     const bool embedded = !naddXCFunc.basicFunctionals.empty() || !naddKinFunc.basicFunctionals.empty();
     std::vector<int> bc;
     std::vector<const double*> pc;
     for (auto& d : _dMats) {
-      bc.push_back(d->getBasisController()->handle(*_dev));
+      bc.push_back(d->getBasisController()->handle(_dev));
       pc.push_back(d->getDensityMatrix().data());
     }
     // calculateDerivatives (Kernel.cpp:686-747)
@@ -663,7 +883,7 @@ class KernelSigmavector {
     if (_kernel->totalStore() < 0) throw SerenityError("KernelSigmavector: no embedding kernel to contract");
     const int tot = _kernel->totalStore();
     for (unsigned J = 0; J < D.size(); ++J) contract(J, {tot}, D[J], J != 0);
-    _dev->check(sxc_kernel_response_copy(_dev->get(), _kernel->getGridController()->handle(*_dev), 1));
+    _dev->check(sxc_kernel_response_copy(_dev->get(), _kernel->getGridController()->handle(_dev), 1));
     _supersystem = true;
   }
   std::vector<Matrix> calcF(unsigned I, unsigned J, const std::vector<Matrix>& densityMatrices) {
@@ -671,15 +891,15 @@ class KernelSigmavector {
     std::vector<int> k = _kernel->stores(I, J);
     if (_supersystem) {  // the total-density part is in the saved supersystem response: add the subsystem store only
       k = {k.back()};
-      _dev->check(sxc_kernel_response_copy(_dev->get(), _kernel->getGridController()->handle(*_dev), 0));
+      _dev->check(sxc_kernel_response_copy(_dev->get(), _kernel->getGridController()->handle(_dev), 0));
     }
     if (k.empty()) return {};
     contract(J, k, densityMatrices, _supersystem);
     const int nb = (int)_kernel->getBasisController(I)->getNBasisFunctions();
     const size_t nmat = densityMatrices.size();
     std::vector<double> flat(nmat * (size_t)nb * nb);
-    _dev->check(sxc_kernel_integrate(_dev->get(), _kernel->getGridController()->handle(*_dev),
-                                     _kernel->getBasisController(I)->handle(*_dev), flat.data()));
+    _dev->check(sxc_kernel_integrate(_dev->get(), _kernel->getGridController()->handle(_dev),
+                                     _kernel->getBasisController(I)->handle(_dev), flat.data()));
     std::vector<Matrix> F;
     for (size_t m = 0; m < nmat; ++m) {
       Matrix M(nb, nb);
@@ -702,8 +922,8 @@ class KernelSigmavector {
       if (M.rows() != nb || M.cols() != nb) throw SerenityError("KernelSigmavector: density matrix of the wrong dimension");
       flat.insert(flat.end(), M.values.begin(), M.values.end());
     }
-    _dev->check(sxc_kernel_contract(_dev->get(), _kernel->getGridController()->handle(*_dev),
-                                    _kernel->getBasisController(J)->handle(*_dev), (int)stores.size(), stores.data(), mode(),
+    _dev->check(sxc_kernel_contract(_dev->get(), _kernel->getGridController()->handle(_dev),
+                                    _kernel->getBasisController(J)->handle(_dev), (int)stores.size(), stores.data(), mode(),
                                     (int)D.size() / nspin, flat.data(), accumulate ? 1 : 0));
   }
   std::shared_ptr<B200::XCDevice> _dev;

@@ -123,7 +123,23 @@ class XCContext:
 
     # ---- multi-GPU: the communicator lives in the library (NCCL); only the 128-byte id travels through the caller
     @staticmethod
+    def _prefer_bundled_nccl():
+        """A Python process usually also holds PyTorch, which loads the NCCL of the nvidia-nccl wheel; if the library bound the
+        system libnccl.so.2 first, a later `import torch` would find the wrong version under that soname.  Name the wheel's file
+        (SXC_NCCL_LIBRARY) so that both use the same copy."""
+        import os
+        import sys
+        if os.environ.get("SXC_NCCL_LIBRARY"):
+            return
+        for base in sys.path:
+            cand = os.path.join(base, "nvidia", "nccl", "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["SXC_NCCL_LIBRARY"] = cand
+                return
+
+    @staticmethod
     def comm_unique_id() -> bytes:
+        XCContext._prefer_bundled_nccl()
         buf = C.create_string_buffer(128)
         rc = _lib.load().sxc_comm_unique_id(buf)
         if rc != 0:
@@ -132,6 +148,7 @@ class XCContext:
 
     def comm_init_rank(self, rank: int, world: int, unique_id: bytes):
         """Every grid of this context becomes shard `rank` of `world`; builds return the sum over ranks (one all-reduce)."""
+        XCContext._prefer_bundled_nccl()
         self._check(self._lib.sxc_comm_init_rank(self._h, int(rank), int(world), C.create_string_buffer(bytes(unique_id), 128)))
 
     def comm_info(self) -> dict:

@@ -2,8 +2,10 @@
 // classes (potentials/FuncPotential_test.cpp, NAddFuncPotential_test.cpp): build, cached second call, density change ->
 // notify -> rebuild.  Inputs come from a flat binary file written by tests/test_cpp_host.py; results go back the same way.
 //   host_adapter_test --expect-no-device          exit 0 iff constructing the device throws SerenityError
-//   host_adapter_test <in.bin> <out.bin>
+//   host_adapter_test <in.bin> <out.bin> [ngpu]
+#include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -70,7 +72,7 @@ int main(int argc, char** argv) {
       return 3;
     }
   }
-  if (argc != 3) return 2;
+  if (argc != 3 && argc != 4) return 2;
   try {
     std::ifstream in(argv[1], std::ios::binary);
     std::ofstream out(argv[2], std::ios::binary);
@@ -169,6 +171,70 @@ int main(int argc, char** argv) {
       adder.addScalarOperatorToMatrix(Vst, fd.dFdRho, fd.dFdGradRhoX, fd.dFdGradRhoY, fd.dFdGradRhoZ);
       wr(out, Vst.data(), (int64_t)nA * nA);
       wr(out, &fd.energy, 1);
+    }
+    // ---- round-2 additions ------------------------------------------------------------------------------------------
+    using DMC = DensityMatrixController<R::RESTRICTED>;
+    const int ngpu = argc == 4 ? std::atoi(argv[3]) : 1;
+    Matrix BtoA(nB, nA);
+    BtoA.values = rd<double>(in);
+    {
+      // getLinearizedEnergy (NAddFuncPotential.cpp:180-189) of the cached non-additive XC potential
+      const double lin = naddXC->getLinearizedEnergy(PA2, 0.5);
+      wr(out, &lin, 1);
+      // second constructor (NAddFuncPotential.cpp:105-176): subsystem B treated exactly, projected into the active basis; no
+      // approximately treated environment
+      auto comb = std::make_shared<NAddFuncPotential<R::RESTRICTED>>(dev, dA, std::vector<std::shared_ptr<DMC>>{dB},
+                                                                     std::vector<std::shared_ptr<Matrix>>{std::make_shared<Matrix>(BtoA)},
+                                                                     std::vector<std::shared_ptr<DMC>>{dB}, grid, xc);
+      comb->registerSensitivity(comb);
+      wr(out, comb->getMatrix().data(), (int64_t)nA * nA);
+      const double ec = comb->getEnergy(PA2);
+      wr(out, &ec, 1);
+      // the bundle: both non-additive objects in one device pass; each keeps its own matrix and energy
+      auto nx = std::make_shared<NAddFuncPotential<R::RESTRICTED>>(dev, dA, std::vector<std::shared_ptr<DMC>>{dB}, grid, xc);
+      auto nk = std::make_shared<NAddFuncPotential<R::RESTRICTED>>(dev, dA, std::vector<std::shared_ptr<DMC>>{dB}, grid, kin);
+      nx->registerSensitivity(nx);
+      nk->registerSensitivity(nk);
+      FDEPotentials<R::RESTRICTED> bundle(nx, nk);
+      Matrix Fsum = bundle.getNAddFockMatrix();
+      wr(out, Fsum.data(), (int64_t)nA * nA);
+      wr(out, nx->getMatrix().data(), (int64_t)nA * nA);
+      wr(out, nk->getMatrix().data(), (int64_t)nA * nA);
+      const double ex = nx->getEnergy(PA2), ek = nk->getEnergy(PA2);
+      wr(out, &ex, 1);
+      wr(out, &ek, 1);
+      // geometry steps: new grid and basis controllers every step, the old ones release their device copies
+      for (int step = 0; step < 4; ++step) {
+        auto g2 = std::make_shared<GridController>(grid->getGridPoints(), grid->getWeights());
+        auto p2 = std::make_shared<FuncPotential<R::RESTRICTED>>(dev, dA, g2, xc);
+        if (std::abs(p2->getEnergy(PA2) - pot->getEnergy(PA2)) > 1e-12) throw SerenityError("rebuilt grid gives another energy");
+      }
+    }
+    if (ngpu > 1) {
+      // one process, ngpu GPUs: the same potential classes on a group device (sxc_group: one worker thread and context per GPU,
+      // ncclAllReduce inside the library)
+      std::vector<int> devices(ngpu);
+      for (int i = 0; i < ngpu; ++i) devices[i] = i;
+      auto gdev = std::make_shared<B200::XCDevice>(devices);
+      auto ggrid = std::make_shared<GridController>(grid->getGridPoints(), grid->getWeights());
+      auto gA = std::make_shared<BasisController>(*basisA);
+      auto gB = std::make_shared<BasisController>(*basisB);
+      auto gdA = std::make_shared<DMC>(gA, PA2);
+      auto gdB = std::make_shared<DMC>(gB, dB->getDensityMatrix());
+      auto gpot = std::make_shared<FuncPotential<R::RESTRICTED>>(gdev, gdA, ggrid, xc);
+      gpot->registerSensitivity(gpot);
+      wr(out, gpot->getMatrix().data(), (int64_t)nA * nA);
+      const double eg = gpot->getEnergy(PA2);
+      wr(out, &eg, 1);
+      auto gx = std::make_shared<NAddFuncPotential<R::RESTRICTED>>(gdev, gdA, std::vector<std::shared_ptr<DMC>>{gdB}, ggrid, xc);
+      auto gk = std::make_shared<NAddFuncPotential<R::RESTRICTED>>(gdev, gdA, std::vector<std::shared_ptr<DMC>>{gdB}, ggrid, kin);
+      FDEPotentials<R::RESTRICTED> gbundle(gx, gk);
+      Matrix gF = gbundle.getNAddFockMatrix();
+      wr(out, gF.data(), (int64_t)nA * nA);
+      Matrix gg = gpot->getGeomGradients();
+      wr(out, gg.data(), (int64_t)gg.rows() * 3);
+      const double n = (double)gdev->nGPUs();
+      wr(out, &n, 1);
     }
     // error convention: SerenityError, as the reference throws (here: a functional id the library does not implement)
     bool threw = false;

@@ -87,7 +87,11 @@ def test_cpp_potentials_match_oracle(tmp_path):
         DB = rng.standard_normal((env.basis.nbf, env.basis.nbf))
         _w(f, DA.reshape(-1, order="F"), np.float64)
         _w(f, DB.reshape(-1, order="F"), np.float64)
-    r = subprocess.run([_exe(), fin, fout], capture_output=True, text=True)
+        BtoA = 0.3 * rng.standard_normal((env.basis.nbf, act.basis.nbf)) / np.sqrt(env.basis.nbf)
+        _w(f, BtoA.reshape(-1, order="F"), np.float64)
+    import torch
+    ngpu = min(2, torch.cuda.device_count())
+    r = subprocess.run([_exe(), fin, fout, str(ngpu)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     nA = act.basis.nbf
     with open(fout, "rb") as f:
@@ -100,6 +104,11 @@ def test_cpp_potentials_match_oracle(tmp_path):
         F_fde, F_fde_B, F_iso0, F_iso1 = _r(f, (nA, nA)), _r(f, (nB, nB)), _r(f, (nA, nA)), _r(f, (nA, nA))
         pp_block = _r(f, (128,))
         V_stage, E_stage = _r(f, (nA, nA)), _r(f)
+        lin = _r(f)
+        V_comb, E_comb = _r(f, (nA, nA)), _r(f)
+        F_sum, F_x, F_k, E_x, E_k = _r(f, (nA, nA)), _r(f, (nA, nA)), _r(f, (nA, nA)), _r(f), _r(f)
+        if ngpu > 1:
+            Vg, Eg, Fg, gradg, ng = _r(f, (nA, nA)), _r(f), _r(f, (nA, nA)), _r(f, (len(act.symbols), 3)), _r(f)
     og = orc.Grid(cfg.xyz, cfg.w, 128)
     bA, bE = orc.Basis(act.basis), orc.Basis(env.basis)
 
@@ -152,3 +161,19 @@ def test_cpp_potentials_match_oracle(tmp_path):
     assert np.abs(pp_block - iso[0, 256:384]).max() <= 1e-6 * np.abs(iso[0, 256:384]).max()
     # DensityOnGridCalculator -> FunctionalLibrary -> ScalarOperatorToMatrixAdder stand-ins = FuncPotential of the same density
     assert np.abs(V_stage - want[3][0]).max() <= 1e-8 and abs(E_stage - want[3][1]) <= 1e-9
+
+    # round 2: getLinearizedEnergy, the projected-density constructor, the one-pass FDE bundle, and the multi-GPU group
+    assert abs(lin - 0.5 * float((want[4][0] * PA2).sum())) <= 1e-9
+    P_comb = PA2 + BtoA.T @ env.P @ BtoA       # (the combination is formed when the object is constructed: P_A is PA2 by then)
+    Vc_ref, Ec_ref, _ = orc.build_nadd(bA, np.asfortranarray(P_comb), [(bE, env.P)], og, orc.Functional(*xc))
+    assert np.abs(V_comb - Vc_ref).max() <= 1e-8 and abs(E_comb - Ec_ref) <= 1e-9
+    Vx_ref, Ex_ref = nadd(PA2, xc)
+    Vk_ref, Ek_ref = nadd(PA2, kin)
+    assert np.abs(F_x - Vx_ref).max() <= 1e-8 and np.abs(F_k - Vk_ref).max() <= 1e-8
+    assert abs(E_x - Ex_ref) <= 1e-9 and abs(E_k - Ek_ref) <= 1e-9
+    assert np.abs(F_sum - (F_x + F_k)).max() <= 1e-14
+    if ngpu > 1:
+        assert ng == ngpu
+        assert np.abs(Vg - want[3][0]).max() <= 1e-8 and abs(Eg - want[3][1]) <= 1e-9
+        assert np.abs(Fg - (Vx_ref + Vk_ref)).max() <= 1e-8
+        assert np.abs(gradg - grad_ref).max() <= 1e-9
