@@ -266,6 +266,14 @@ int sxc_density_on_grid(sxc_ctx* ctx, int grid, int basis, const double* P, doub
  * level 1: n x nbf column-major values (index mu*n + p) and the negligible flags; returns n through *n_out. */
 int sxc_basis_on_grid(sxc_ctx* ctx, int grid, int basis, int block, double* val, double* dx, double* dy,
                       double* dz, int* negligible, int* n_out);
+/* derivative level 2 of the same call (BasisFunctionOnGridController.cpp:302-304, :381-440, :1081-1095; the six arrays
+ * BasisFunctionBlockOnGridData::secondDerivativeValues xx, xy, xz, yy, yz, zz): n x nbf column-major each. */
+int sxc_basis_hessian_on_grid(sxc_ctx* ctx, int grid, int basis, int block, double* hxx, double* hxy, double* hxz, double* hyy,
+                              double* hyz, double* hzz, int* n_out);
+/* DensityOnGridCalculator::calcDensityAndDerivativesOnGrid, second derivatives of the density
+ * (MatrixOperatorToGridTransformer.cpp:166-188): host outputs [N] each. */
+int sxc_density_hessian_on_grid(sxc_ctx* ctx, int grid, int basis, const double* P, double* hxx, double* hxy, double* hxz,
+                                double* hyy, double* hyz, double* hzz);
 /* FunctionalLibrary::calcData(GRADIENTS) (FunctionalLibrary.cpp:39-72 -> XCFun.cpp:39-159), RESTRICTED, on host
  * arrays of length npts; gx..gz and dFdG* may be NULL for LDA functionals. */
 int sxc_functional_on_grid(sxc_ctx* ctx, int func, int64_t npts, const double* w, const double* rho,

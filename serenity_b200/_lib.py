@@ -26,7 +26,7 @@ SYMBOLS = [
     "sxc_debug_scatter_schedule2",
     "sxc_group_create", "sxc_group_destroy", "sxc_group_size", "sxc_group_ctx", "sxc_group_last_error", "sxc_group_set_grid",
     "sxc_group_add_basis", "sxc_group_set_functional", "sxc_group_release_grid", "sxc_group_release_basis", "sxc_group_build_xc",
-    "sxc_group_build_nadd_multi", "sxc_group_xc_gradient",
+    "sxc_group_build_nadd_multi", "sxc_group_xc_gradient", "sxc_basis_hessian_on_grid", "sxc_density_hessian_on_grid",
 ]
 
 
@@ -85,6 +85,8 @@ def load():
     lib.sxc_xc_gradient.argtypes = [vp, i, i, i, i, vp, i, vp, vp]
     lib.sxc_density_on_grid.argtypes = [vp, i, i, vp, vp, vp, vp, vp]
     lib.sxc_basis_on_grid.argtypes = [vp, i, i, i, vp, vp, vp, vp, vp, ip]
+    lib.sxc_basis_hessian_on_grid.argtypes = [vp, i, i, i, vp, vp, vp, vp, vp, vp, ip]
+    lib.sxc_density_hessian_on_grid.argtypes = [vp, i, i, vp, vp, vp, vp, vp, vp, vp]
     lib.sxc_functional_on_grid.argtypes = [vp, i, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(d)]
     lib.sxc_functional_on_grid_u.argtypes = [vp, i, i64, vp, vp, i, vp, vp, C.POINTER(d)]
     lib.sxc_scalar_to_matrix.argtypes = [vp, i, i, d, vp, vp, vp, vp, vp]

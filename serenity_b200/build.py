@@ -58,6 +58,18 @@ def build_host_test(force=False):
     return out
 
 
+def build_bridge_test(force=False):
+    """serenity_b200/host/B200Bridge.h (the reference-side glue of INTEGRATION.md) compiled against stand-in controller classes."""
+    src = os.path.join(ROOT, "tests", "cpp", "b200_bridge_test.cpp")
+    hdr = os.path.join(HERE, "host", "B200Bridge.h")
+    out = os.path.join(ROOT, "tests", "cpp", "b200_bridge_test")
+    lib = os.path.join(HERE, "libserenity_xc_b200.so")
+    if force or _newer(out, [src, hdr, lib]):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++14", "-Wall", "-Wextra", "-I" + os.path.join(ROOT, "include"), "-o", out,
+                               src, "-L" + HERE, "-lserenity_xc_b200", "-Wl,-rpath,$ORIGIN/../../serenity_b200"])
+    return out
+
+
 def build_jet_probe(force=False):
     """Host-compiled probe of the device functional source (functionals.cuh, kernel2.cuh) for the CPU test suite; the
     arithmetic is __host__ __device__, the probe never touches a GPU and is not part of the product library."""
@@ -73,7 +85,8 @@ def build_jet_probe(force=False):
 
 
 def build_all(force=False, verbose=False):
-    return [build_cuda(force, verbose), build_inputs_helper(force), build_host_test(force), build_jet_probe(force)]
+    return [build_cuda(force, verbose), build_inputs_helper(force), build_host_test(force), build_bridge_test(force),
+            build_jet_probe(force)]
 
 
 if __name__ == "__main__":

@@ -10,6 +10,11 @@
 //   AtomCenteredBasisController: atom-major, file order    src/basis/AtomCenteredBasisController.cpp
 // ECP sections of the files ($ecp) belong to the integral code and are not read.  Errors are reported the way the reference
 // words them (SerenityError text -> sxc_host_last_error()).
+// Deliberately stricter than the reference's search (std::regex_search of "<element>\\s+<label>", icase, unanchored, :61-80), and
+// identical on the Turbomole files it ships: the element symbol must start a line and the label must end at white space, so a
+// label that is a prefix of another label (def2-SVP / def2-SVPD) or a symbol that ends another word cannot select the wrong
+// entry; every '*' / '#' line after the header is skipped (the reference skips one optional '#' line and then 3 characters,
+// :84-91); lower-case Fortran exponents (d+01) are converted as well as D+01 (:93).  tests/test_basis_provider.py pins each.
 #include <algorithm>
 #include <cctype>
 #include <cmath>

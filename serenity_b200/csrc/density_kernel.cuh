@@ -99,7 +99,10 @@ __device__ __forceinline__ void dens_kloop(double (&acc)[4][4][2], const double*
 __global__ void __launch_bounds__(dens::PTHREADS, 2)
 k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, const WorkItem* __restrict__ items,
           const double* __restrict__ phi_buf, double* __restrict__ rho, double* __restrict__ gx,
-          double* __restrict__ gy, double* __restrict__ gz, int* __restrict__ nonneg) {
+          double* __restrict__ gy, double* __restrict__ gz, int* __restrict__ nonneg, int a_slot, int e_slot0,
+          int epi_prefetch) {
+  // a_slot / e_slot0: tile slots of the A operand of the product and of the first epilogue component (0 / 0 for the density and
+  // its gradient; the second derivatives of the density contract other slots of an 8-slot gradient plan, sxc_density_hessian_on_grid)
   using namespace dens;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* stage_base = reinterpret_cast<double*>(smem_raw);
@@ -170,11 +173,28 @@ k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, cons
         ++pass;
       }
     };
+    // The ring keeps 3 stages (48 KB) in flight ahead of the DMMA warps: enough for the K chunks, which are multiplied for ~1 us
+    // each, but the epilogue stages are consumed in a fraction of that and would run at HBM latency (16 stages per j-tile).  Their
+    // rows are therefore pulled into L2 one component ahead with bulk prefetches (64 KB each, one instruction of one lane).
+    auto prefetch_epi = [&](int jt, int comp, int nrg) {
+      if (epi_prefetch && lane == 0 && comp < ncomp)
+        bulk_prefetch_l2(tile + (e_slot0 + comp) * comp_stride + (size_t)(jt * TJ) * BP, (unsigned)(nrg * TK * BP * sizeof(double)));
+    };
     for (int jt = jt_begin; jt < njt; ++jt) {
       const int nrg = (min(TJ, s8 - jt * TJ) + TK - 1) / TK;
-      for (int kc = 0; kc < nk; ++kc) copy_rows(tile + (size_t)kc * (TK * BP), false);
-      for (int comp = 0; comp < ncomp; ++comp)
-        for (int rg = 0; rg < nrg; ++rg) copy_rows(tile + comp * comp_stride + (size_t)(jt * TJ + rg * TK) * BP, true);
+      const int kpf = max(0, nk - 6);  // a few K chunks before the epilogue starts
+      for (int kc = 0; kc < nk; ++kc) {
+        if (kc == kpf) {
+          prefetch_epi(jt, 0, nrg);
+          prefetch_epi(jt, 1, nrg);
+        }
+        copy_rows(tile + a_slot * comp_stride + (size_t)kc * (TK * BP), false);
+      }
+      for (int comp = 0; comp < ncomp; ++comp) {
+        prefetch_epi(jt, comp + 2, nrg);
+        for (int rg = 0; rg < nrg; ++rg)
+          copy_rows(tile + (e_slot0 + comp) * comp_stride + (size_t)(jt * TJ + rg * TK) * BP, true);
+      }
     }
   } else if (warp == CWARPS + 1) {
     // ---------------- producer B: the gathered P_s chunk ("Proj^T P Proj" without materialising it)

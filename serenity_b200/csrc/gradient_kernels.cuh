@@ -29,7 +29,9 @@ __device__ __forceinline__ double pw_(const double* p, int e) { return e >= 0 ? 
 
 __global__ void __launch_bounds__(BASIS_GROUPS* BP)
 k_hessq(GridView g, ShellView b, PlanView plan, int slot0, const int* __restrict__ order, const double* __restrict__ v_gx,
-        const double* __restrict__ v_gy, const double* __restrict__ v_gz, double* __restrict__ phi_buf) {
+        const double* __restrict__ v_gy, const double* __restrict__ v_gz, double* __restrict__ phi_buf, int unit_dir = -1) {
+  // unit_dir = 0, 1, 2: b is the unit vector of that axis at every point (no weights, v_g* unused), so the three outputs are the
+  // second derivatives d_dir d_c phi themselves (sxc_basis_hessian_on_grid)
   const int q = order ? order[blockIdx.x] : slot0 + blockIdx.x;
   const int blk = plan.block_id[q];
   const long first = (long)blk * g.blocksize;
@@ -46,10 +48,16 @@ k_hessq(GridView g, ShellView b, PlanView plan, int slot0, const int* __restrict
     px = g.x[first + p];
     py = g.y[first + p];
     pz = g.z[first + p];
-    const double wp = g.w[first + p];
-    bx = wp * v_gx[first + p];
-    by = wp * v_gy[first + p];
-    bz = wp * v_gz[first + p];
+    if (unit_dir >= 0) {
+      bx = unit_dir == 0 ? 1.0 : 0.0;
+      by = unit_dir == 1 ? 1.0 : 0.0;
+      bz = unit_dir == 2 ? 1.0 : 0.0;
+    } else {
+      const double wp = g.w[first + p];
+      bx = wp * v_gx[first + p];
+      by = wp * v_gy[first + p];
+      bz = wp * v_gz[first + p];
+    }
   }
   const int nsig = plan.nsig_shell[q];
   const int* __restrict__ sig_shell = plan.sig_shell + (size_t)q * b.nshell;

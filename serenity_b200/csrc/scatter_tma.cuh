@@ -38,11 +38,12 @@ namespace scat2 {
 constexpr int WARPS = 8;
 constexpr int THREADS = (WARPS + 1) * 32;
 constexpr int MAXG = 6;
-template <int TKP>
+template <int TKP_, int STAGES_ = (TKP_ == 8 ? 4 : 2)>
 struct Cfg {
+  static constexpr int TKP = TKP_;
   static constexpr int KS = TKP / 4;                  // k-steps per chunk
   static constexpr int NKC = BP / TKP;                // chunks per round
-  static constexpr int STAGES = TKP == 8 ? 4 : 2;
+  static constexpr int STAGES = STAGES_;
   static constexpr int BOX_ELEMS = 32 * TKP;          // 32 rows x TKP points
   static constexpr int GROUP_ELEMS = 2 * BOX_ELEMS;   // phi box, then G box
   static constexpr int STAGE_ELEMS = MAXG * GROUP_ELEMS;
@@ -67,11 +68,11 @@ __device__ __forceinline__ int frag_col(int ks, int lr, int lc) {
 }
 
 // K loop of one round for a warp tile with MFR x NFR valid 8 x 8 fragments; DIAG: only fragments m <= nn are multiplied
-template <int TKP, int MFR, int NFR, bool DIAG>
+template <class C, int MFR, int NFR, bool DIAG>
 __device__ __forceinline__ void vmat2_round(double (&acc)[4][4][2], const double* __restrict__ stage_base, uint64_t* full,
                                             uint64_t* empty, int& stage, int& pass, int slot_a, int slot_b, int kmask,
                                             bool active, int lane) {
-  using C = scat2::Cfg<TKP>;
+  constexpr int TKP = C::TKP;
   const int lr = lane >> 2, lc = lane & 3;
   int col[C::KS];
 #pragma unroll
@@ -107,13 +108,103 @@ __device__ __forceinline__ void vmat2_round(double (&acc)[4][4][2], const double
   }
 }
 
-template <int TKP>
+// producer side of one work item (one elected thread): stage the phi and G boxes of every round's groups, chunk by chunk
+template <class C>
+__device__ __forceinline__ void vmat2_produce_item(const CUtensorMap* tmap, const ScatterRound2* __restrict__ rounds, int nr,
+                                                   int row0, int rowG, double* stage_base, uint64_t* full, uint64_t* empty,
+                                                   int& stage, int& pass) {
+  for (int r = 0; r < nr; ++r) {
+    const uint2 grp = __ldg(reinterpret_cast<const uint2*>(rounds[r].group));
+    const int ng = rounds[r].ngroups;
+    for (int kc = 0; kc < C::NKC; ++kc) {
+      if (pass > 0) mbar_wait(empty + stage, (pass - 1) & 1);
+      double* st = stage_base + stage * C::STAGE_ELEMS;
+      mbar_arrive_expect_tx(full + stage, (unsigned)ng * 2u * C::BOX_BYTES);
+      for (int i = 0; i < ng; ++i) {
+        const int gi = (int)(((i < 4 ? grp.x : grp.y) >> (8 * (i & 3))) & 0xffu);
+        tma_load_2d(st + i * C::GROUP_ELEMS, tmap, kc * C::TKP, row0 + gi * 32, full + stage);
+        tma_load_2d(st + i * C::GROUP_ELEMS + C::BOX_ELEMS, tmap, kc * C::TKP, rowG + gi * 32, full + stage);
+      }
+      if (++stage == C::STAGES) {
+        stage = 0;
+        ++pass;
+      }
+    }
+  }
+}
+
+// DMMA side of one work item: the rounds of a block (or of a segment of them), accumulators into the upper triangle of W
+template <class C>
+__device__ __forceinline__ void vmat2_consume_item(const ScatterRound2* __restrict__ rounds, int nr, int s, int sp, int nbf,
+                                                   const int* s_sig, const double* stage_base, uint64_t* full, uint64_t* empty,
+                                                   int& stage, int& pass, int warp, int lane, double* __restrict__ W) {
+  const int lr = lane >> 2, lc = lane & 3;
+  const int s8 = (s + 7) & ~7;  // rows beyond s rounded up to 8 are zero padding: their 8 x 8 fragments are skipped
+  double acc[4][4][2];
+  // descriptor words of round r: lane l holds word (l & 15)
+  unsigned dw = __ldg(reinterpret_cast<const unsigned*>(rounds) + (lane & 15));
+  for (int r = 0; r < nr; ++r) {
+    const unsigned w_ta = __shfl_sync(0xffffffffu, dw, 4 + (warp >> 2)), w_tb = __shfl_sync(0xffffffffu, dw, 6 + (warp >> 2));
+    const unsigned w_km = __shfl_sync(0xffffffffu, dw, 8 + (warp >> 2)), w_ga = __shfl_sync(0xffffffffu, dw, 10 + (warp >> 2));
+    const unsigned w_gb = __shfl_sync(0xffffffffu, dw, 12 + (warp >> 2));
+    const int sh = 8 * (warp & 3);
+    const int slot_a = (w_ta >> sh) & 0xff, slot_b = (w_tb >> sh) & 0xff, kmask = (w_km >> sh) & 0xff;
+    const int gI = (w_ga >> sh) & 0xff, gJ = (w_gb >> sh) & 0xff;
+    if (r + 1 < nr) dw = __ldg(reinterpret_cast<const unsigned*>(rounds + r + 1) + (lane & 15));  // lands during the K loop
+    const bool active = slot_a != 0xff;
+    // valid 8-row fragments of the row group I and the column group J (only the last group of a block is short)
+    const int mfr = active ? min(4, (s8 - gI * 32) >> 3) : 0;
+    const int nfr = active ? min(4, (s8 - gJ * 32) >> 3) : 0;
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+      for (int nn = 0; nn < 4; ++nn) acc[m][nn][0] = acc[m][nn][1] = 0.0;
+    if (active && slot_a == slot_b && mfr == 4) {  // full diagonal tile
+      vmat2_round<C, 4, 4, true>(acc, stage_base, full, empty, stage, pass, slot_a, slot_b, kmask, active, lane);
+    } else if (mfr == 4 || !active) {
+      switch (active ? nfr : 4) {
+        case 1: vmat2_round<C, 4, 1, false>(acc, stage_base, full, empty, stage, pass, slot_a, slot_b, kmask, active, lane); break;
+        case 2: vmat2_round<C, 4, 2, false>(acc, stage_base, full, empty, stage, pass, slot_a, slot_b, kmask, active, lane); break;
+        case 3: vmat2_round<C, 4, 3, false>(acc, stage_base, full, empty, stage, pass, slot_a, slot_b, kmask, active, lane); break;
+        default: vmat2_round<C, 4, 4, false>(acc, stage_base, full, empty, stage, pass, slot_a, slot_b, kmask, active, lane); break;
+      }
+    } else {  // a short row group is the last one, so the tile is the last diagonal tile: nfr == mfr
+      switch (mfr) {
+        case 1: vmat2_round<C, 1, 1, true>(acc, stage_base, full, empty, stage, pass, slot_a, slot_b, kmask, active, lane); break;
+        case 2: vmat2_round<C, 2, 2, true>(acc, stage_base, full, empty, stage, pass, slot_a, slot_b, kmask, active, lane); break;
+        default: vmat2_round<C, 3, 3, true>(acc, stage_base, full, empty, stage, pass, slot_a, slot_b, kmask, active, lane); break;
+      }
+    }
+    if (active) {
+      // V += Proj V_s Proj^T (:301), upper triangle (compact i <= j <=> global sig[i] <= sig[j])
+      const int i0 = gI * 32, j0 = gJ * 32;
+      int rowi[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) rowi[m] = s_sig[min(i0 + m * 8 + lr, sp - 1)];
+#pragma unroll
+      for (int nn = 0; nn < 4; ++nn)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = j0 + nn * 8 + 2 * lc + e;
+          if (j >= s) continue;
+          const size_t colo = (size_t)s_sig[j] * nbf;
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const int i = i0 + m * 8 + lr;
+            if (i <= j) red_add_f64(W + colo + rowi[m], acc[m][nn][e]);
+          }
+        }
+    }
+  }
+}
+
+template <int TKP, int NSTAGES = (TKP == 8 ? 4 : 2)>
 __global__ void __launch_bounds__(scat2::THREADS, 2)
 k_vmat_tma(const __grid_constant__ CUtensorMap tmap, PlanView plan, int nbf, const WorkItem* __restrict__ items, int nitems,
            int* __restrict__ counter, const int* __restrict__ skip_flag, const ScatterRound2* __restrict__ tpl,
            const int* __restrict__ tpl_off, int sig_cap, double* __restrict__ W) {
   using namespace scat2;
-  using C = Cfg<TKP>;
+  using C = Cfg<TKP, NSTAGES>;
   extern __shared__ unsigned char smem_raw[];
   // the hardware swizzle works on absolute shared-memory address bits: the boxes must start on a multiple of their pattern
   // (512 B / 1024 B), so the ring starts on the next 1 KB boundary (the launch reserves the slack)
@@ -125,7 +216,6 @@ k_vmat_tma(const __grid_constant__ CUtensorMap tmap, PlanView plan, int nbf, con
   int* s_next = s_sig + sig_cap;  // sig_cap >= the largest s_pad of the plan
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int lr = lane >> 2, lc = lane & 3;
   if (tid == 0) {
     for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(full + i, 1);       // the producer's arrive.expect_tx; the TMA unit completes the bytes
@@ -152,29 +242,12 @@ k_vmat_tma(const __grid_constant__ CUtensorMap tmap, PlanView plan, int nbf, con
     const int nr = item.end - item.begin;
 
     if (warp == WARPS) {
-      // ---------------- producer: one thread drives the TMA unit
+      // ---------------- producer: one thread drives the TMA unit (the other lanes of the warp take no part; lane 0 keeps the
+      // ring position in its registers from item to item)
       if (lane == 0) {
         const int row0 = (int)(plan.phi_off[q] / BP);  // first row of the block's tile in the workspace
-        const int rowG = row0 + 4 * sp;                 // its G slot
-        for (int r = 0; r < nr; ++r) {
-          const uint2 grp = __ldg(reinterpret_cast<const uint2*>(rounds[r].group));
-          const int ng = rounds[r].ngroups;
-          for (int kc = 0; kc < C::NKC; ++kc) {
-            if (pass > 0) mbar_wait(empty + stage, (pass - 1) & 1);
-            double* st = stage_base + stage * C::STAGE_ELEMS;
-            mbar_arrive_expect_tx(full + stage, (unsigned)ng * 2u * C::BOX_BYTES);
-            for (int i = 0; i < ng; ++i) {
-              const int gi = (int)(((i < 4 ? grp.x : grp.y) >> (8 * (i & 3))) & 0xffu);
-              tma_load_2d(st + i * C::GROUP_ELEMS, &tmap, kc * TKP, row0 + gi * 32, full + stage);
-              tma_load_2d(st + i * C::GROUP_ELEMS + C::BOX_ELEMS, &tmap, kc * TKP, rowG + gi * 32, full + stage);
-            }
-            if (++stage == C::STAGES) {
-              stage = 0;
-              ++pass;
-            }
-          }
-        }
-      }  // (the other lanes of the warp take no part; lane 0 keeps the ring position in its registers from item to item)
+        vmat2_produce_item<C>(&tmap, rounds, nr, row0, row0 + 4 * sp, stage_base, full, empty, stage, pass);
+      }
     } else {
       // ---------------- DMMA warps
       {  // compact -> function map of the block into shared memory (read by the RED epilogues of every round)
@@ -182,63 +255,7 @@ k_vmat_tma(const __grid_constant__ CUtensorMap tmap, PlanView plan, int nbf, con
         for (int c = tid; c < sp; c += WARPS * 32) s_sig[c] = sig_g[c];
         asm volatile("bar.sync 1, %0;\n" ::"n"(WARPS * 32) : "memory");
       }
-      const int s8 = (s + 7) & ~7;  // rows beyond s rounded up to 8 are zero padding: their 8 x 8 fragments are skipped
-      double acc[4][4][2];
-      // descriptor words of round r: lane l holds word (l & 15)
-      unsigned dw = __ldg(reinterpret_cast<const unsigned*>(rounds) + (lane & 15));
-      for (int r = 0; r < nr; ++r) {
-        const unsigned w_ta = __shfl_sync(0xffffffffu, dw, 4 + (warp >> 2)), w_tb = __shfl_sync(0xffffffffu, dw, 6 + (warp >> 2));
-        const unsigned w_km = __shfl_sync(0xffffffffu, dw, 8 + (warp >> 2)), w_ga = __shfl_sync(0xffffffffu, dw, 10 + (warp >> 2));
-        const unsigned w_gb = __shfl_sync(0xffffffffu, dw, 12 + (warp >> 2));
-        const int sh = 8 * (warp & 3);
-        const int slot_a = (w_ta >> sh) & 0xff, slot_b = (w_tb >> sh) & 0xff, kmask = (w_km >> sh) & 0xff;
-        const int gI = (w_ga >> sh) & 0xff, gJ = (w_gb >> sh) & 0xff;
-        if (r + 1 < nr) dw = __ldg(reinterpret_cast<const unsigned*>(rounds + r + 1) + (lane & 15));  // lands during the K loop
-        const bool active = slot_a != 0xff;
-        // valid 8-row fragments of the row group I and the column group J (only the last group of a block is short)
-        const int mfr = active ? min(4, (s8 - gI * 32) >> 3) : 0;
-        const int nfr = active ? min(4, (s8 - gJ * 32) >> 3) : 0;
-#pragma unroll
-        for (int m = 0; m < 4; ++m)
-#pragma unroll
-          for (int nn = 0; nn < 4; ++nn) acc[m][nn][0] = acc[m][nn][1] = 0.0;
-        if (active && slot_a == slot_b && mfr == 4) {  // full diagonal tile
-          vmat2_round<TKP, 4, 4, true>(acc, stage_base, full, empty, stage, pass, slot_a, slot_b, kmask, active, lane);
-        } else if (mfr == 4 || !active) {
-          switch (active ? nfr : 4) {
-            case 1: vmat2_round<TKP, 4, 1, false>(acc, stage_base, full, empty, stage, pass, slot_a, slot_b, kmask, active, lane); break;
-            case 2: vmat2_round<TKP, 4, 2, false>(acc, stage_base, full, empty, stage, pass, slot_a, slot_b, kmask, active, lane); break;
-            case 3: vmat2_round<TKP, 4, 3, false>(acc, stage_base, full, empty, stage, pass, slot_a, slot_b, kmask, active, lane); break;
-            default: vmat2_round<TKP, 4, 4, false>(acc, stage_base, full, empty, stage, pass, slot_a, slot_b, kmask, active, lane); break;
-          }
-        } else {  // a short row group is the last one, so the tile is the last diagonal tile: nfr == mfr
-          switch (mfr) {
-            case 1: vmat2_round<TKP, 1, 1, true>(acc, stage_base, full, empty, stage, pass, slot_a, slot_b, kmask, active, lane); break;
-            case 2: vmat2_round<TKP, 2, 2, true>(acc, stage_base, full, empty, stage, pass, slot_a, slot_b, kmask, active, lane); break;
-            default: vmat2_round<TKP, 3, 3, true>(acc, stage_base, full, empty, stage, pass, slot_a, slot_b, kmask, active, lane); break;
-          }
-        }
-        if (active) {
-          // V += Proj V_s Proj^T (:301), upper triangle (compact i <= j <=> global sig[i] <= sig[j])
-          const int i0 = gI * 32, j0 = gJ * 32;
-          int rowi[4];
-#pragma unroll
-          for (int m = 0; m < 4; ++m) rowi[m] = s_sig[min(i0 + m * 8 + lr, sp - 1)];
-#pragma unroll
-          for (int nn = 0; nn < 4; ++nn)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int j = j0 + nn * 8 + 2 * lc + e;
-              if (j >= s) continue;
-              const size_t colo = (size_t)s_sig[j] * nbf;
-#pragma unroll
-              for (int m = 0; m < 4; ++m) {
-                const int i = i0 + m * 8 + lr;
-                if (i <= j) atomicAdd(W + colo + rowi[m], acc[m][nn][e]);
-              }
-            }
-        }
-      }
+      vmat2_consume_item<C>(rounds, nr, s, sp, nbf, s_sig, stage_base, full, empty, stage, pass, warp, lane, W);
     }
   }
 }

@@ -28,6 +28,7 @@
 #include "host_copy.h"
 #include "scatter_kernel.cuh"
 #include "scatter_tma.cuh"
+#include "scatter_fused.cuh"
 #include "gradient_kernels.cuh"
 #include "grid_kernels.cuh"
 #include "kernel2.cuh"
@@ -130,6 +131,7 @@ struct Chunk {
   int order_off = 0;      // offset into Plan::order (sorted slots of this chunk)
   int ditem_off = 0, nditems = 0;  // k_density work items
   int vitem_off = 0, nvitems = 0;  // k_vmat work items
+  bool vitems_whole = true;        // every k_vmat work item is a whole block (k_vmat_fg can form G for it)
   bool dens_split = false;         // some block's j-tiles are spread over several CTAs (outputs accumulated)
 };
 
@@ -141,6 +143,7 @@ struct Plan {
   int s_pad_max = 0;
   int vmat_variant = 0;  // scatter kernel the round templates / work items were made for
   DevMem block_id, nsig_shell, s, sig_shell, sig_c0, sig_bf, s_pad, phi_off, order, tpl, tpl_off, skip, ditems, vitems;
+  DevMem gflag;  // [nown] k_vmat_fg: pieces of a block's G formed so far, when the block is cut into several work items
   std::vector<int> h_s, h_s_pad;
   std::vector<Chunk> chunks;
   sxc_stats stats{};
@@ -184,12 +187,16 @@ struct sxc_ctx {
   std::map<int, std::vector<ScatterRound>> scatter_tpl;  // round templates per s_pad / 32
   std::map<std::pair<int, int>, std::vector<ScatterRound2>> scatter_tpl2;  // v2 templates per (s_pad / 32, k-steps per chunk)
   // which scatter kernel runs: 0 = k_vmat (cp.async producers), 8 / 16 = k_vmat_tma<8 / 16> (TMA producer); SXC_VMAT overrides
-  int vmat_variant = 16;
+  // 24 = k_vmat_fg (k_form_g fused behind the DMMA warps of the TKP = 8 kernel; chunks cut into segments fall back to 8)
+  int vmat_variant = 24;
   int dens_variant = 0;  // 0 = k_density (cp.async producers; 1-3 % faster as measured), 1 = k_density_tma; SXC_DENS overrides
+  int dens_prefetch = 1;  // SXC_DPF: L2 prefetch of k_density's epilogue rows
+  int fg_mode = 0;   // SXC_FG_MODE: development switches of k_vmat_fg
   int smem_pad = 0;  // SXC_SMEM_PAD: extra dynamic shared memory per DMMA CTA (development: forces one CTA per SM)
   int dseg = 1, vseg = 1;  // pieces per block of the k_density / k_vmat work items (SXC_DSEG / SXC_VSEG; 1 = only when a shard is small)
   CUtensorMap tmap_v8{}, tmap_v16{};  // tile workspace as [rows] x [128 points], boxes 32 x 8 (SWIZZLE_64B) and 32 x 16 (128B)
   CUtensorMap tmap_d16{};             // boxes of 16 rows x 16 points (SWIZZLE_128B) for k_density_tma
+  CUtensorMap tmap_rows{};            // boxes of scat3::HROWS whole rows (no swizzle) for the G formers of k_vmat_fg
   void* tmap_ptr = nullptr;
   size_t tmap_bytes = 0;
   DevMem phi;     // tile workspace (one chunk)
@@ -303,6 +310,8 @@ int set_kernel_attrs(sxc_ctx* ctx) {
   CU(cudaFuncSetAttribute(k_density_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CU(cudaFuncSetAttribute(k_vmat_tma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CU(cudaFuncSetAttribute(k_vmat_tma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CU(cudaFuncSetAttribute(k_vmat_fg, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CU(cudaFuncSetAttribute(k_vmat_tma<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   ctx->attrs_set = true;
   return SXC_OK;
 }
@@ -773,6 +782,7 @@ int ensure_tile_maps(sxc_ctx* ctx) {
   TRY(make_tile_map(ctx, ctx->phi, 8, 32, CU_TENSOR_MAP_SWIZZLE_64B, &ctx->tmap_v8));
   TRY(make_tile_map(ctx, ctx->phi, 16, 32, CU_TENSOR_MAP_SWIZZLE_128B, &ctx->tmap_v16));
   TRY(make_tile_map(ctx, ctx->phi, 16, 16, CU_TENSOR_MAP_SWIZZLE_128B, &ctx->tmap_d16));
+  TRY(make_tile_map(ctx, ctx->phi, BP, scat3::HROWS, CU_TENSOR_MAP_SWIZZLE_NONE, &ctx->tmap_rows));
   ctx->tmap_ptr = ctx->phi.p;
   ctx->tmap_bytes = ctx->phi.bytes;
   return SXC_OK;
@@ -889,7 +899,7 @@ int get_plan(sxc_ctx* ctx, int gh, int bh, Plan** out, int comps = TILE_COMPS) {
       tpl.insert(tpl.end(), rs.begin(), rs.end());
     } else {
       tpl_off[n32] = (int)tpl2.size();
-      const auto& rs = scatter_schedule2(ctx, n32, p.vmat_variant / 4);
+      const auto& rs = scatter_schedule2(ctx, n32, p.vmat_variant == 16 ? 4 : 2);
       tpl2.insert(tpl2.end(), rs.begin(), rs.end());
     }
   }
@@ -920,27 +930,29 @@ int get_plan(sxc_ctx* ctx, int gh, int bh, Plan** out, int comps = TILE_COMPS) {
       // the same few blocks, whose tiles stay in L2 between the re-reads of the j-tiles / rounds)
       const int want_d = ctx->dseg > 1 ? std::min(njt, ctx->dseg) : 1;
       if (want_d <= 1 && (njt <= seg_jt || c.nslots >= target)) {
-        ditems.push_back(WorkItem{q, 0, (short)njt});
+        ditems.push_back(WorkItem{q, 0, (short)njt, 0, 1});
       } else {
         c.dens_split = true;
         const int nseg = std::max(want_d, (c.nslots >= target) ? 1 : (njt + seg_jt - 1) / seg_jt);
         for (int sgi = 0; sgi < nseg; ++sgi)  // equal-sized segments
-          ditems.push_back(WorkItem{q, (short)((long)njt * sgi / nseg), (short)((long)njt * (sgi + 1) / nseg)});
+          ditems.push_back(WorkItem{q, (short)((long)njt * sgi / nseg), (short)((long)njt * (sgi + 1) / nseg), (short)sgi, (short)nseg});
       }
       if (p.h_s[q] == 0) continue;
       const int nr = tpl_off[n32 + 1] - tpl_off[n32];
       const int want_v = ctx->vseg > 1 ? std::min(nr, ctx->vseg) : 1;
       if (want_v <= 1 && (nr <= seg_r || c.nslots >= target)) {
-        vitems.push_back(WorkItem{q, 0, (short)nr});
+        vitems.push_back(WorkItem{q, 0, (short)nr, 0, 1});
       } else {
+        c.vitems_whole = false;
         const int nseg = std::max(want_v, (c.nslots >= target) ? 1 : (nr + seg_r - 1) / seg_r);
         for (int sgi = 0; sgi < nseg; ++sgi)
-          vitems.push_back(WorkItem{q, (short)((long)nr * sgi / nseg), (short)((long)nr * (sgi + 1) / nseg)});
+          vitems.push_back(WorkItem{q, (short)((long)nr * sgi / nseg), (short)((long)nr * (sgi + 1) / nseg), (short)sgi, (short)nseg});
       }
     }
     c.nditems = (int)ditems.size() - c.ditem_off;
     c.nvitems = (int)vitems.size() - c.vitem_off;
   }
+  CU(p.gflag.ensure(std::max<size_t>(p.nown, 1) * sizeof(int)));
   CU(p.ditems.ensure(std::max<size_t>(ditems.size(), 1) * sizeof(WorkItem)));
   CU(p.vitems.ensure(std::max<size_t>(vitems.size(), 1) * sizeof(WorkItem)));
   if (!ditems.empty())
@@ -1016,7 +1028,7 @@ __global__ void k_zero_blocks(long N, int blocksize, int ncomp, const int* __res
 }
 
 int phase_density(sxc_ctx* ctx, const Grid& g, const Basis& b, const Plan& p, const Chunk& c, const double* dP,
-                  double* dens4, bool with_grad, int* nonneg) {
+                  double* dens4, bool with_grad, int* nonneg, int a_slot = 0, int e_slot0 = 0) {
   const long N = g.npts;
   if (c.nditems == 0) return SXC_OK;
   PhaseTimer t(ctx, SXC_T_DENSITY);
@@ -1024,10 +1036,11 @@ int phase_density(sxc_ctx* ctx, const Grid& g, const Basis& b, const Plan& p, co
     k_zero_blocks<<<c.nslots, 128, 0, ctx->stream>>>(N, g.blocksize, with_grad ? 4 : 1, p.block_id.as<int>() + c.slot0, dens4);
     LAUNCH_CHECK();
   }
-  if (ctx->dens_variant == 0) {
+  if (ctx->dens_variant == 0 || a_slot != 0 || e_slot0 != 0) {
     k_density<<<c.nditems, dens::PTHREADS, dens::smem_bytes_pipe(p.s_pad_max), ctx->stream>>>(
         g.view(), p.view(), b.nbf, dP, p.ditems.as<WorkItem>() + c.ditem_off, ctx->phi.as<double>(), dens4,
-        with_grad ? dens4 + N : nullptr, with_grad ? dens4 + 2 * N : nullptr, with_grad ? dens4 + 3 * N : nullptr, nonneg);
+        with_grad ? dens4 + N : nullptr, with_grad ? dens4 + 2 * N : nullptr, with_grad ? dens4 + 3 * N : nullptr, nonneg,
+        a_slot, e_slot0, ctx->dens_prefetch);
   } else {
     TRY(ensure_tile_maps(ctx));
     k_density_tma<<<c.nditems, dens::PTHREADS, dens::smem_bytes_tma(p.s_pad_max) + ctx->smem_pad, ctx->stream>>>(
@@ -1082,31 +1095,53 @@ int phase_scatter(sxc_ctx* ctx, const Grid& g, const Basis& b, const Plan& p, co
                   double block_ave_thr, const double* pot4, double* dW, int npot = 1, size_t pot_stride = 0) {
   const long N = g.npts;
   if (c.nslots == 0) return SXC_OK;
+  const double* v_gx = gga ? pot4 + N : nullptr;
+  const double* v_gy = gga ? pot4 + 2 * N : nullptr;
+  const double* v_gz = gga ? pot4 + 3 * N : nullptr;
+  const int grid = std::min(c.nvitems, 2 * ctx->num_sms);
+  if (p.vmat_variant == 24) {
+    // one launch: G of block n + 1 is formed by the helper warpgroup while the DMMA warps contract block n (scatter_fused.cuh)
+    if (c.nvitems == 0) return SXC_OK;
+    int* counter = nullptr;
+    TRY(next_counter(ctx, &counter));
+    TRY(ensure_tile_maps(ctx));
+    PhaseTimer t(ctx, SXC_T_SCATTER);
+    if (!c.vitems_whole)  // blocks cut into several work items: their formers count the finished pieces here
+      CU(cudaMemsetAsync(p.gflag.as<int>() + c.slot0, 0, (size_t)c.nslots * sizeof(int), ctx->stream));
+    k_vmat_fg<<<grid, scat3::THREADS, scat3::smem_bytes(p.s_pad_max), ctx->stream>>>(
+        ctx->tmap_v8, ctx->tmap_rows, g.view(), p.view(), b.nbf, p.vitems.as<WorkItem>() + c.vitem_off, c.nvitems, counter,
+        p.tpl.as<ScatterRound2>(), p.tpl_off.as<int>(), p.s_pad_max, block_ave_thr, 0.5, pot4, v_gx, v_gy, v_gz, npot, pot_stride,
+        ctx->phi.as<double>(), dW, p.gflag.as<int>(), ctx->fg_mode);
+    LAUNCH_CHECK();
+    return SXC_OK;
+  }
   {
     PhaseTimer t(ctx, SXC_T_FORM_G);
     k_form_g<<<form_g_grid(ctx, c.nslots), 256, 0, ctx->stream>>>(g.view(), p.view(), p.order.as<int>() + c.order_off, block_ave_thr, 0.5,
-                                                pot4, gga ? pot4 + N : nullptr, gga ? pot4 + 2 * N : nullptr,
-                                                gga ? pot4 + 3 * N : nullptr, npot, pot_stride, ctx->phi.as<double>(), p.skip.as<int>());
+                                                pot4, v_gx, v_gy, v_gz, npot, pot_stride, ctx->phi.as<double>(), p.skip.as<int>());
     LAUNCH_CHECK();
   }
   int* counter = nullptr;
   TRY(next_counter(ctx, &counter));
   PhaseTimer t(ctx, SXC_T_SCATTER);
   if (c.nvitems == 0) return SXC_OK;
-  const int grid = std::min(c.nvitems, 2 * ctx->num_sms);
   if (p.vmat_variant == 0) {
     k_vmat<<<grid, scat::PTHREADS, scat::smem_bytes_pipe(), ctx->stream>>>(
         p.view(), b.nbf, p.vitems.as<WorkItem>() + c.vitem_off, c.nvitems, counter, p.skip.as<int>(), p.tpl.as<ScatterRound>(),
         p.tpl_off.as<int>(), ctx->phi.as<double>(), dW);
   } else {
     TRY(ensure_tile_maps(ctx));
-    if (p.vmat_variant == 8)
-      k_vmat_tma<8><<<grid, scat2::THREADS, scat2::smem_bytes<8>(p.s_pad_max) + ctx->smem_pad, ctx->stream>>>(
+    if (p.vmat_variant == 16)
+      k_vmat_tma<16><<<grid, scat2::THREADS, scat2::smem_bytes<16>(p.s_pad_max) + ctx->smem_pad, ctx->stream>>>(
+          ctx->tmap_v16, p.view(), b.nbf, p.vitems.as<WorkItem>() + c.vitem_off, c.nvitems, counter, p.skip.as<int>(),
+          p.tpl.as<ScatterRound2>(), p.tpl_off.as<int>(), p.s_pad_max, dW);
+    else if (p.vmat_variant == 83)
+      k_vmat_tma<8, 3><<<grid, scat2::THREADS, scat2::smem_bytes<8>(p.s_pad_max) + ctx->smem_pad, ctx->stream>>>(
           ctx->tmap_v8, p.view(), b.nbf, p.vitems.as<WorkItem>() + c.vitem_off, c.nvitems, counter, p.skip.as<int>(),
           p.tpl.as<ScatterRound2>(), p.tpl_off.as<int>(), p.s_pad_max, dW);
     else
-      k_vmat_tma<16><<<grid, scat2::THREADS, scat2::smem_bytes<16>(p.s_pad_max) + ctx->smem_pad, ctx->stream>>>(
-          ctx->tmap_v16, p.view(), b.nbf, p.vitems.as<WorkItem>() + c.vitem_off, c.nvitems, counter, p.skip.as<int>(),
+      k_vmat_tma<8><<<grid, scat2::THREADS, scat2::smem_bytes<8>(p.s_pad_max) + ctx->smem_pad, ctx->stream>>>(
+          ctx->tmap_v8, p.view(), b.nbf, p.vitems.as<WorkItem>() + c.vitem_off, c.nvitems, counter, p.skip.as<int>(),
           p.tpl.as<ScatterRound2>(), p.tpl_off.as<int>(), p.s_pad_max, dW);
   }
   LAUNCH_CHECK();
@@ -1707,10 +1742,12 @@ int sxc_create(sxc_ctx** out, int device) {
   ctx->stream = ctx->own_stream;
   if (const char* v = std::getenv("SXC_VMAT")) {  // development switch: 0 = cp.async kernel, 8 / 16 = TMA kernel with that K chunk
     const int k = std::atoi(v);
-    if (k == 0 || k == 8 || k == 16) ctx->vmat_variant = k;
+    if (k == 0 || k == 8 || k == 16 || k == 24 || k == 83) ctx->vmat_variant = k;  // 83: TKP 8 with a 3-stage ring (development)
   }
   if (const char* v = std::getenv("SXC_DENS")) ctx->dens_variant = std::atoi(v) ? 1 : 0;
   if (const char* v = std::getenv("SXC_COPY_THREADS")) ctx->copy_threads = std::max(0, std::min(16, std::atoi(v)));
+  if (const char* v = std::getenv("SXC_DPF")) ctx->dens_prefetch = std::atoi(v);
+  if (const char* v = std::getenv("SXC_FG_MODE")) ctx->fg_mode = std::atoi(v);
   if (const char* v = std::getenv("SXC_SMEM_PAD")) ctx->smem_pad = std::max(0, std::atoi(v));
   if (const char* v = std::getenv("SXC_DSEG")) ctx->dseg = std::max(1, std::atoi(v));
   if (const char* v = std::getenv("SXC_VSEG")) ctx->vseg = std::max(1, std::atoi(v));
@@ -2153,6 +2190,103 @@ int sxc_basis_on_grid(sxc_ctx* ctx, int grid, int basis, int block, double* val,
       const double* src = tile.data() + ((size_t)comp * sp + c) * BP;
       std::copy(src, src + n, outs[comp] + (size_t)sig[c] * n);
     }
+  }
+  return SXC_OK;
+}
+
+// derivative level 2 of getBlockOnGridData (BasisFunctionOnGridController.cpp:302-304 radial second derivative, :381-440 /
+// :1081-1095 finalisation): the six second derivatives of every basis function on one block, n x nbf column-major like
+// sxc_basis_on_grid.  k_hessq contracts the Hessian with a vector; with the three unit vectors it returns the Hessian itself.
+int sxc_basis_hessian_on_grid(sxc_ctx* ctx, int grid, int basis, int block, double* hxx, double* hxy, double* hxz, double* hyy,
+                              double* hyz, double* hzz, int* n_out) {
+  if (!ctx || !hxx || !hxy || !hxz || !hyy || !hyz || !hzz) return fail(ctx, SXC_ERR_INVALID, "sxc_basis_hessian_on_grid: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  Plan* pp = nullptr;
+  TRY(get_plan(ctx, grid, basis, &pp, GRAD_TILE_COMPS));
+  Plan& p = *pp;
+  Grid& g = *get_grid(ctx, grid);
+  Basis& b = *get_basis(ctx, basis);
+  const int q = block - g.own_first;
+  if (q < 0 || q >= p.nown) return fail(ctx, SXC_ERR_INVALID, "block %d is not owned by this context", block);
+  const Chunk* ch = nullptr;
+  for (const Chunk& c : p.chunks)
+    if (q >= c.slot0 && q < c.slot0 + c.nslots) ch = &c;
+  ctx->phi_owner = 0;
+  CU(ctx->phi.ensure(ch->doubles * sizeof(double)));
+  const int s = p.h_s[q], sp = p.h_s_pad[q];
+  std::vector<long long> off(1);
+  std::vector<int> sig(std::max(s, 1));
+  CU(cudaMemcpyAsync(off.data(), p.phi_off.as<long long>() + q, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  if (s) CU(cudaMemcpyAsync(sig.data(), p.sig_bf.as<int>() + (size_t)q * p.nbf_pad, s * sizeof(int), cudaMemcpyDeviceToHost,
+                            ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  const long first = (long)block * g.blocksize;
+  const int n = (int)std::min<long>(g.blocksize, g.npts - first);
+  if (n_out) *n_out = n;
+  // unit vector d -> slots 5, 6, 7 hold d_d d_x, d_d d_y, d_d d_z
+  double* outs[3][3] = {{hxx, hxy, hxz}, {nullptr, hyy, hyz}, {nullptr, nullptr, hzz}};
+  std::vector<double> tile((size_t)3 * sp * BP);
+  for (int d = 0; d < 3; ++d) {
+    k_hessq<<<1, BASIS_GROUPS * BP, 0, ctx->stream>>>(g.view(), b.view(), p.view(), q, nullptr, nullptr, nullptr, nullptr,
+                                                      ctx->phi.as<double>(), d);
+    LAUNCH_CHECK();
+    CU(cudaMemcpyAsync(tile.data(), ctx->phi.as<double>() + off[0] + (size_t)5 * sp * BP, tile.size() * sizeof(double),
+                       cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int c = d; c < 3; ++c) {
+      double* out = outs[d][c];
+      std::fill(out, out + (size_t)n * b.nbf, 0.0);
+      for (int k = 0; k < s; ++k) {
+        const double* src = tile.data() + ((size_t)c * sp + k) * BP;
+        std::copy(src, src + n, out + (size_t)sig[k] * n);
+      }
+    }
+  }
+  return SXC_OK;
+}
+
+// second derivatives of the density on the grid (MatrixOperatorToGridTransformer.cpp:166-188):
+//   d_c d_d rho = 2 sum_mu,nu P_mu,nu ( phi_mu d_c d_d phi_nu + d_c phi_mu d_d phi_nu )
+// as six runs of the density contraction on other tile slots of the 8-slot gradient plan: for every axis d, k_hessq (unit vector d)
+// leaves d_d d_c phi in slots 5-7 and k_density(A = phi, epilogue slots 4-7) returns 2 sum (phi P) d_d d_c phi; k_density(A =
+// d_d phi, epilogue slots 0-3) returns 2 sum (d_d phi P) d_c phi.  Host outputs [N] each.
+int sxc_density_hessian_on_grid(sxc_ctx* ctx, int grid, int basis, const double* P, double* hxx, double* hxy, double* hxz,
+                                double* hyy, double* hyz, double* hzz) {
+  if (!ctx || !P || !hxx || !hxy || !hxz || !hyy || !hyz || !hzz)
+    return fail(ctx, SXC_ERR_INVALID, "sxc_density_hessian_on_grid: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  Plan* pp = nullptr;
+  TRY(get_plan(ctx, grid, basis, &pp, GRAD_TILE_COMPS));
+  Plan& p = *pp;
+  Grid& g = *get_grid(ctx, grid);
+  Basis& b = *get_basis(ctx, basis);
+  TRY(ensure_point_arrays(ctx, g, false, 2));  // two [4][N] outputs
+  const size_t nb2 = (size_t)b.nbf * b.nbf;
+  const long N = g.npts;
+  CU(ctx->dP.ensure(nb2 * sizeof(double)));
+  CU(cudaMemcpyAsync(ctx->dP.p, P, nb2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  double* t1 = g.dens.as<double>();          // [4][N]: (unused), 2 sum (phi P) d_d d_c phi for c = x, y, z
+  double* t2 = t1 + (size_t)4 * N;           // [4][N]: (unused), 2 sum (d_d phi P) d_c phi
+  double* outs[3][3] = {{hxx, hxy, hxz}, {nullptr, hyy, hyz}, {nullptr, nullptr, hzz}};
+  std::vector<double> h1((size_t)3 * N), h2((size_t)3 * N);
+  for (double* o : {hxx, hxy, hxz, hyy, hyz, hzz}) std::fill(o, o + N, 0.0);
+  for (int d = 0; d < 3; ++d) {
+    CU(cudaMemsetAsync(t1, 0, (size_t)8 * N * sizeof(double), ctx->stream));
+    for (const Chunk& c : p.chunks) {
+      if (c.nslots == 0) continue;
+      TRY(phase_basis(ctx, g, b, p, c));
+      k_hessq<<<c.nslots, BASIS_GROUPS * BP, 0, ctx->stream>>>(g.view(), b.view(), p.view(), c.slot0, p.order.as<int>() + c.order_off,
+                                                               nullptr, nullptr, nullptr, ctx->phi.as<double>(), d);
+      LAUNCH_CHECK();
+      // (slot 4, the scatter's G, is not written on this path; it only feeds the first output row, which is not used)
+      TRY(phase_density(ctx, g, b, p, c, ctx->dP.as<double>(), t1, true, nullptr, 0, 4));
+      TRY(phase_density(ctx, g, b, p, c, ctx->dP.as<double>(), t2, true, nullptr, 1 + d, 0));
+    }
+    CU(cudaMemcpyAsync(h1.data(), t1 + N, 3 * N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(h2.data(), t2 + N, 3 * N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int c = d; c < 3; ++c)
+      for (long i = 0; i < N; ++i) outs[d][c][i] = h1[(size_t)c * N + i] + h2[(size_t)c * N + i];
   }
   return SXC_OK;
 }

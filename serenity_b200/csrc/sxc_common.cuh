@@ -21,6 +21,12 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
                : "d"(a), "d"(b));
 }
 
+// fire-and-forget FP64 accumulation into global memory (SASS: REDG.E.ADD.F64; written as PTX so that no code path turns it
+// into an ATOMG that waits for the old value)
+__device__ __forceinline__ void red_add_f64(double* addr, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;\n" ::"l"(addr), "d"(v) : "memory");
+}
+
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
@@ -30,6 +36,10 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem));
 }
 __device__ __forceinline__ void prefetch_l2(const void* gmem) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(gmem)); }
+// `bytes` (multiple of 16) of contiguous global memory into L2, no destination, no completion
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gmem), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -78,8 +88,18 @@ __device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, 
       "l"(map), "r"(b), "r"(c0), "r"(c1)
       : "memory");
 }
+// the same box into L2 only (no shared memory, no completion): hides the HBM latency of a later tma_load_2d of the box
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];\n" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -120,6 +140,7 @@ __device__ __forceinline__ double block_max(double v, double* scratch) {
 struct WorkItem {
   int q;
   short begin, end;
+  short seg, nseg;  // this item is piece `seg` of the `nseg` pieces the block was cut into (0 of 1: the whole block)
 };
 
 // Device view of a shell table (structure of arrays), see sxc_add_basis.

@@ -40,13 +40,16 @@ class ShardedBuild:
     """
 
     def __init__(self, nbf: int, local_build: Callable[[torch.Tensor, torch.Tensor], None], device,
-                 group: Optional[dist.ProcessGroup] = None, ntail: int = 2):
-        self.nbf, self.ntail = nbf, ntail
+                 group: Optional[dist.ProcessGroup] = None, ntail: int = 2, nspin: int = 1):
+        if nspin not in (1, 2):
+            raise ValueError("nspin must be 1 (RESTRICTED) or 2 (UNRESTRICTED)")
+        self.nbf, self.ntail, self.nspin = nbf, ntail, nspin
         self._local = local_build
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.device = torch.device(device)
-        n = nbf * nbf
+        n = nspin * nbf * nbf  # UNRESTRICTED: {alpha, beta} matrices back to back, in P and in V
+        self._n = n
         # P travels in `world` equal slices (one per rank), so its device buffer is padded to a multiple of world
         self._slice = (n + self.world - 1) // self.world
         self.rank = dist.get_rank(group) if self.world > 1 else 0
@@ -69,7 +72,7 @@ class ShardedBuild:
     def _upload(self):
         """H2D of P: every rank copies ONE slice of the (identical) host matrix over its own PCIe link and the slices
         are all-gathered over NVLink - nb^2 * 8 bytes cross PCIe once per build instead of once per rank."""
-        n = self.nbf * self.nbf
+        n = self._n
         if self.world == 1:
             self.d_P.copy_(self.h_P, non_blocking=True)
             return
@@ -84,8 +87,8 @@ class ShardedBuild:
         """P has been written into the pinned buffer h_P (column-major); returns views into the pinned result buffer
         h_VEN: (V [nb, nb], E, N) - V only on rank 0 (the SCF driver's process), E and N on
         every rank.  The upload runs on a side stream and is awaited by the library only before the density kernel,
-        i.e. it overlaps with the screening and basis kernels."""
-        n = self.nbf * self.nbf
+        i.e. it overlaps with the screening and basis kernels.  nspin = 2: V is [2, nb, nb] (alpha, beta)."""
+        n = self._n
         if self._copy_stream is not None:
             cur = torch.cuda.current_stream(self.device)
             self._copy_stream.wait_stream(cur)  # the previous build no longer reads d_P
@@ -103,13 +106,22 @@ class ShardedBuild:
             self.build_device()
             self.h_VEN.copy_(self.d_VEN)
         out = self.h_VEN.numpy()
-        return out[:n].reshape(self.nbf, self.nbf, order="F"), float(out[n]), float(out[n + 1])
+        nb = self.nbf
+        if self.nspin == 1:
+            V = out[:n].reshape(nb, nb, order="F")
+        else:
+            V = np.stack([out[k * nb * nb:(k + 1) * nb * nb].reshape(nb, nb, order="F") for k in range(2)])
+        return V, float(out[n]), float(out[n + 1])
 
     # host buffers in, host buffers out: what FuncPotential::getMatrix/getEnergy hand to the SCF driver
     def build(self, P: np.ndarray):
-        self.h_P.numpy()[:] = np.asarray(P, dtype=np.float64).reshape(-1, order="F")
+        P = np.asarray(P, dtype=np.float64)
+        if self.nspin == 1:
+            self.h_P.numpy()[:] = P.reshape(-1, order="F")
+        else:
+            self.h_P.numpy()[:] = np.concatenate([P[k].reshape(-1, order="F") for k in range(2)])
         V, E, N = self.build_pinned()
-        return V.copy(order="F"), E, N
+        return (V.copy(order="F") if self.nspin == 1 else V.copy()), E, N
 
     @property
     def h2d_bytes(self) -> int:
@@ -122,8 +134,8 @@ class ShardedBuild:
         return self.h_VEN.numel() * 8 + (self.world - 1) * self.ntail * 8
 
 
-def cuda_local_build(ctx, grid: int, basis: int, func: int, block_ave_threshold: float = 1e-11):
-    """local_build for ShardedBuild on a CUDA rank: sxc_build_xc_device on torch's current stream."""
+def cuda_local_build(ctx, grid: int, basis: int, func: int, block_ave_threshold: float = 1e-11, nspin: int = 1):
+    """local_build for ShardedBuild(..., nspin=nspin) on a CUDA rank: sxc_build_xc_device on torch's current stream."""
 
     def run(d_P: torch.Tensor, d_VEN: torch.Tensor, p_ready=None):
         if p_ready is not None:
@@ -131,7 +143,7 @@ def cuda_local_build(ctx, grid: int, basis: int, func: int, block_ave_threshold:
         # torch's default stream is the legacy NULL stream (handle 0); the C ABI reads NULL as "the context's own
         # stream", so name the legacy stream explicitly (cudaStreamLegacy == (cudaStream_t)0x1)
         ctx.set_stream(torch.cuda.current_stream(d_P.device).cuda_stream or 1)
-        ctx.build_xc_device(grid, basis, func, d_P.data_ptr(), d_VEN.data_ptr(), block_ave_threshold)
+        ctx.build_xc_device(grid, basis, func, d_P.data_ptr(), d_VEN.data_ptr(), block_ave_threshold, nspin)
 
     return run
 

@@ -301,6 +301,21 @@ class XCContext:
         # library layout: n x nbf column-major (index mu*n + p)
         return [a.reshape(-1)[: n * nbf].reshape(nbf, n).T for a in arrs], neg, n
 
+    def basis_hessian_on_grid(self, grid, basis, block: int, nbf: int, blocksize: int = 128):
+        """xx, xy, xz, yy, yz, zz second derivatives of every basis function on one block, each [n, nbf]."""
+        arrs = [np.zeros((nbf, blocksize)) for _ in range(6)]
+        n = C.c_int(0)
+        self._check(self._lib.sxc_basis_hessian_on_grid(self._h, grid, basis, block, *[_ptr(a) for a in arrs], C.byref(n)))
+        n = n.value
+        return [a.reshape(-1)[: n * nbf].reshape(nbf, n).T for a in arrs], n
+
+    def density_hessian_on_grid(self, grid, basis, P, npts: int):
+        """xx, xy, xz, yy, yz, zz second derivatives of the density, each [npts]."""
+        P = np.asfortranarray(P, dtype=np.float64)
+        h = [np.zeros(npts) for _ in range(6)]
+        self._check(self._lib.sxc_density_hessian_on_grid(self._h, grid, basis, _ptr(P), *[_ptr(a) for a in h]))
+        return h
+
     def functional_on_grid(self, func, w, rho, gx=None, gy=None, gz=None):
         N = rho.shape[0]
         out = [np.zeros(N) for _ in range(5)]

@@ -71,6 +71,51 @@ def test_errors_are_worded_like_the_reference():
         shell_table_from_file(os.path.join(GOLDEN, "basis_fixture_6-31GS"), "DEF2-SVP", ["H"], XYZ[:1])
 
 
+def test_label_matching_is_anchored_where_the_reference_regex_is_not(tmp_path):
+    """Deliberate differences from BasisFunctionProvider.cpp:61-96, documented in basis_provider.cpp: the element must start a line
+    and the label must end at white space, so a label that is a prefix of another one (def2-SVP / def2-SVPD) and an element symbol
+    that ends another word cannot resolve to the wrong entry (the reference's unanchored icase regex_search takes the first textual
+    hit); any number of '*' / '#' lines may follow the header; lower-case Fortran exponents (d+01) are accepted as well."""
+    from serenity_b200._lib import SerenityError
+    from serenity_b200.xc import shell_table_from_file
+    text = """$basis
+*
+h def2-SVPD
+# h     (5s2p) / [3s2p]     {311/11}
+*
+    1  s
+      9.0   1.0
+    1  p
+      0.9   1.0
+*
+h def2-SVP
+# h     (4s1p) / [2s1p]     {31/1}
+# a second comment line
+*
+    2  s
+      0.13010701D+02      0.19682158d-01
+      0.19622572D+01      0.13796524D+00
+    1  s
+      0.12179496D+00      1.0
+*
+bh def2-SVP
+*
+    1  s
+      5.0   1.0
+*
+$end
+"""
+    path = tmp_path / "basis_prefix"
+    path.write_text(text)
+    tab, _ = shell_table_from_file(str(path), "def2-SVP", ["H"], XYZ[:1], True)
+    assert list(tab.l) == [0, 0] and list(tab.nprim) == [2, 1]          # the def2-SVP entry, not the def2-SVPD one before it
+    assert np.allclose(tab.alpha, [13.010701, 1.9622572, 0.12179496])    # D+02 and d-01 both read as exponents
+    tab, _ = shell_table_from_file(str(path), "DEF2-SVPD", ["H"], XYZ[:1], True)
+    assert list(tab.l) == [0, 1]
+    with pytest.raises(SerenityError, match="not defined for this element"):
+        shell_table_from_file(str(path), "def2-SV", ["H"], XYZ[:1], True)  # a prefix of a label is not a label
+
+
 @pytest.mark.gpu
 def test_gpu_build_from_basis_file():
     """geometry + basis file -> sxc_add_basis_from_table -> XC build == the build from the Python-made table"""

@@ -65,6 +65,60 @@ def test_golden_density(ctx, fixtures, small_mixed):
         assert np.allclose(grad[k], exp["d" + c], rtol=0, atol=gold["tolerance"])
 
 
+def test_golden_basis_function_hessians(ctx, fixtures, small_mixed):
+    """BasisFunctionOnGridController_test.cpp:84-483, derivative level 2: the 240 second-derivative values on the device."""
+    gold = load_golden("basis_functions_ref.json")
+    xyz, w = grid_arrays(fixtures, "TINY")
+    g = ctx.set_grid(xyz, w, gold["block_size"])
+    b = ctx.add_basis(small_mixed, gold["radial_threshold"])
+    arrs, n = ctx.basis_hessian_on_grid(g, b, 0, small_mixed.nbf, gold["block_size"])
+    assert n == 4
+    checked = 0
+    for name, arr in zip(["hxx", "hxy", "hxz", "hyy", "hyz", "hzz"], arrs):
+        for p, mu, ref in gold["entries"][name]:
+            assert abs(arr[p, mu] - ref) < gold["tolerance"], (name, p, mu, arr[p, mu], ref)
+            checked += 1
+    assert checked == 240
+
+
+def test_golden_density_hessian(ctx, fixtures, small_mixed):
+    """DensityOnGridCalculator_test.cpp:174-253: the 24 second derivatives of the density (block size 3, threshold 0)."""
+    gold = load_golden("density_ref.json")
+    xyz, w = grid_arrays(fixtures, "TINY")
+    g = ctx.set_grid(xyz, w, gold["block_size"])
+    b = ctx.add_basis(small_mixed, 1e-300)
+    hess = ctx.density_hessian_on_grid(g, b, np.asarray(gold["P"]), 4)
+    exp = gold["expected"]
+    for name, h in zip(["hxx", "hxy", "hxz", "hyy", "hyz", "hzz"], hess):
+        assert np.allclose(h, exp[name], rtol=0, atol=gold["tolerance"]), (name, h, exp[name])
+
+
+def test_hessians_vs_oracle_all_l(ctx, orc):
+    """Second derivatives of spherical l = 0..6 and Cartesian l = 0..4 shells and of a density against the oracle (level 2)."""
+    from serenity_b200.inputs.basis import shell_table_from_list
+    rng = np.random.default_rng(12)
+    pts = rng.uniform(-1.5, 1.5, size=(200, 3))
+    w = rng.uniform(0.1, 1.0, size=len(pts))
+    shells = [{"l": l, "pure": True, "exps": [0.3 + 0.1 * l, 1.1], "coefs": [0.7, 0.4], "centre": [0.1 * l, -0.2, 0.3]}
+              for l in range(7)]
+    shells += [{"l": l, "pure": False, "exps": [0.4], "coefs": [1.0], "centre": [0.0, 0.1, -0.1]} for l in range(5)]
+    tab = shell_table_from_list(shells)
+    g = ctx.set_grid(pts, w, 128)
+    b = ctx.add_basis(tab, 1e-9)
+    og, ob = orc.Grid(pts, w, 128), orc.Basis(tab)
+    for blk in range(2):
+        arrs, n = ctx.basis_hessian_on_grid(g, b, blk, tab.nbf, 128)
+        ref, _, _ = orc.basis_block(ob, og, 1e-9, 2, blk)
+        for a, r in zip(arrs, ref[4:10]):
+            assert np.allclose(a, r, rtol=1e-11, atol=1e-13)
+    P = rng.standard_normal((tab.nbf, tab.nbf))
+    P = P + P.T
+    hess = ctx.density_hessian_on_grid(g, b, P, len(pts))
+    _, _, want, _ = orc.density_on_grid(ob, og, 1e-9, P, 2)
+    for h, r in zip(hess, want):
+        assert np.allclose(h, r, rtol=1e-11, atol=1e-11)
+
+
 def test_golden_scalar_to_matrix(ctx, fixtures, small_mixed):
     """ScalarOperatorToMatrixAdder_test.cpp:41-148 (55 elements, GGA variant, block size 3)."""
     gold = load_golden("scatter_ref.json")

@@ -61,6 +61,54 @@ def test_sharded_build_allreduce_gloo(tmp_path, world):
     assert r["dE"] < 1e-11 and r["dV"] < 1e-11 and r["dn"] < 1e-11 and r["sym"] < 1e-13
 
 
+def _worker_u(rank, world, port, out_path):
+    """UNRESTRICTED: ShardedBuild(nspin=2) moves {alpha, beta} pairs of P and V (2 nb^2 + 2 doubles all-reduced)."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import pyoracle as orc
+        from serenity_b200.inputs import make_config
+        from serenity_b200.inputs.configs import FUNCTIONALS
+        from serenity_b200.sharded import ShardedBuild, shard_bounds
+        cfg = make_config("h2o", 2)
+        sub = cfg.subsystems[0]
+        ids, mix = FUNCTIONALS["PBE"]
+        nbf = sub.basis.nbf
+        n2 = nbf * nbf
+        nblk = (cfg.npts + 127) // 128
+        bounds = shard_bounds(np.ones(nblk), world)
+        lo, hi = int(bounds[rank]) * 128, min(int(bounds[rank + 1]) * 128, cfg.npts)
+        ob, of = orc.Basis(sub.basis), orc.Functional(ids, mix)
+        Pa, Pb = 0.6 * sub.P, 0.4 * sub.P + 0.01 * np.eye(nbf)
+
+        def local_build(d_P, d_VEN, p_ready=None):
+            P = d_P.numpy()
+            (Va, Vb), E, ne = orc.build_xc_u(ob, orc.Grid(cfg.xyz[lo:hi], cfg.w[lo:hi], 128), of,
+                                             P[:n2].reshape(nbf, nbf, order="F"), P[n2:].reshape(nbf, nbf, order="F"))
+            d_VEN[:n2] = torch.from_numpy(Va.reshape(-1, order="F").copy())
+            d_VEN[n2:2 * n2] = torch.from_numpy(Vb.reshape(-1, order="F").copy())
+            d_VEN[2 * n2] = E
+            d_VEN[2 * n2 + 1] = ne
+
+        sb = ShardedBuild(nbf, local_build, "cpu", nspin=2)
+        V, E, ne = sb.build(np.stack([Pa, Pb]))
+        assert V.shape == (2, nbf, nbf) and sb.d_VEN.numel() == 2 * n2 + 2
+        if rank == 0:
+            (Va, Vb), E_ref, ne_ref = orc.build_xc_u(ob, orc.Grid(cfg.xyz, cfg.w, 128), of, Pa, Pb)
+            np.savez(out_path, dV=max(np.abs(V[0] - Va).max(), np.abs(V[1] - Vb).max()), dE=abs(E - E_ref), dn=abs(ne - ne_ref))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_build_unrestricted_gloo(tmp_path):
+    port = 29950 + os.getpid() % 300
+    out = str(tmp_path / "res_u.npz")
+    mp.spawn(_worker_u, args=(2, port, out), nprocs=2, join=True)
+    r = np.load(out)
+    assert r["dE"] < 1e-11 and r["dV"] < 1e-11 and r["dn"] < 1e-11
+
+
 def _sigma_worker(rank, world, port, out_path):
     """row f-4: ShardedSigma - every rank contracts / integrates its block range, one all-reduce of the nvec matrices."""
     sys.path.insert(0, ROOT)
