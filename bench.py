@@ -324,14 +324,16 @@ def roofline_of(env, st, per_build_ms, n_launch, nbf, peak_tf, hbm_peak, hbm_src
     top = max(per_build_ms, key=per_build_ms.get)
     n_top = max(1, n_launch.get(top, 1))
     ms_launch = per_build_ms[top] / n_top
-    flops_contraction = 2.0 * st["sum_ns2"]  # each contraction is 2 n s^2 flops
+    # each contraction is 2 n s^2 flops; a launch covers one workspace chunk of the shard's blocks (several
+    # launches per build with one chunk = several full contractions: two spins, or one scatter per NAdd functional)
+    flops_launch = 2.0 * st["sum_ns2"] / max(1, st.get("nchunks", 1))
     if top in ("k_density", "k_scatter"):
-        achieved = flops_contraction / n_top / (ms_launch * 1e-3) / 1e12
+        achieved = flops_launch / (ms_launch * 1e-3) / 1e12
         roof = {"kernel": {"k_scatter": "k_vmat"}.get(top, top), "bound": "tensor", "achieved": achieved, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 "peak_source": "FP64 cuBLAS DGEMM 4096^3 measured live (MEASURED_PEAKS.json has no FP64 figure; B200 nominal "
                                "FP64 = FP64-tensor = 40 TFLOP/s)",
-                "algorithmic_flops_per_launch": flops_contraction / n_top}
+                "algorithmic_flops_per_launch": flops_launch}
     else:
         bytes_build = 32.0 * st["npts"] + 16.0 * st["sum_s2"] + 16.0 * nbf * nbf
         achieved = bytes_build / (ms_launch * n_top * 1e-3) / 1e9
@@ -339,6 +341,14 @@ def roofline_of(env, st, per_build_ms, n_launch, nbf, peak_tf, hbm_peak, hbm_src
                 "frac": achieved / hbm_peak, "peak_source": hbm_src, "algorithmic_bytes_per_build": bytes_build}
     roof["ms_per_launch"] = ms_launch
     roof["launches_per_build"] = n_top
+    # both contractions, each against the DGEMM ceiling (k_scatter = k_vmat_fg on a full GPU: the formation of G - an HBM phase
+    # of 40 * 128 * s_pad bytes per block - runs inside it, so its time is not tensor time alone)
+    roof["contractions"] = {
+        {"k_scatter": "k_vmat"}.get(k, k): {"ms_per_launch": per_build_ms[k] / max(1, n_launch.get(k, 1)),
+                                             "tflops": flops_launch / (per_build_ms[k] / max(1, n_launch.get(k, 1)) * 1e-3) / 1e12,
+                                             "frac_of_dgemm": flops_launch / (per_build_ms[k] / max(1, n_launch.get(k, 1)) * 1e-3) /
+                                             1e12 / peak_tf}
+        for k in ("k_density", "k_scatter") if per_build_ms.get(k, 0.0) > 0.0}
     # dram__bytes of that kernel per launch from a committed `ncu --set full` capture of THIS workload at THIS rank count
     # (profiles/traffic.json: {workload: {"n<N>": {kernel: bytes}}}); null when no such capture exists
     roof["traffic"] = None
@@ -408,6 +418,8 @@ def measure_ks(env, ctx, cfg, steps, warmup, peaks, headline):
     out = {"name": cfg.name, "ms_per_step": ms_dev, "value": cfg.npts / (ms_dev * 1e-3), "unit": UNIT}
     if env.world > 1:
         out["rank_ms_per_step"] = rank_ms
+    # per-kernel CUDA events right after the timed loop (same thermal / power state as `value`)
+    per_build_ms, n_launch = kernel_times(env, ctx, dev_build)
     if not args.no_e2e:
         def host_build():
             ctx.build_xc_into(g, b, f, P_host, V_host)
@@ -427,7 +439,6 @@ def measure_ks(env, ctx, cfg, steps, warmup, peaks, headline):
                       "pinned": {"value": cfg.npts / (ms_pin * 1e-3), "ms_per_step": ms_pin,
                                  "note": "same call, caller's P / V in page-locked memory (sxc_host_alloc)"}}
 
-    per_build_ms, n_launch = kernel_times(env, ctx, dev_build)
     out["kernels_ms_per_build"] = per_build_ms
     if headline:
         # NOT the headline: the same build with sxc_set_tile_cache(1) - phi / grad phi tiles of the previous build kept in HBM

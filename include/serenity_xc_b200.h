@@ -262,6 +262,10 @@ int sxc_nadd_gradient(sxc_ctx* ctx, int grid, int func, int nspin, int basis_act
  * gx/gy/gz may be NULL.  With a shard set only the owned points are filled (others 0). */
 int sxc_density_on_grid(sxc_ctx* ctx, int grid, int basis, const double* P, double* rho, double* gx, double* gy,
                         double* gz);
+/* SupersystemDensityOnGridController::updateData (data/grid/SupersystemDensityOnGridController.cpp:95-193): sum of the
+ * densities (and gradients) of ndens subsystems, each in its own basis, on the common grid; added in the order given. */
+int sxc_supersystem_density_on_grid(sxc_ctx* ctx, int grid, int ndens, const int* basis, const double* const* P, double* rho,
+                                    double* gx, double* gy, double* gz);
 /* BasisFunctionOnGridController::getBlockOnGridData (BasisFunctionOnGridController.cpp:122-131), derivative
  * level 1: n x nbf column-major values (index mu*n + p) and the negligible flags; returns n through *n_out. */
 int sxc_basis_on_grid(sxc_ctx* ctx, int grid, int basis, int block, double* val, double* dx, double* dy,
@@ -317,6 +321,24 @@ int sxc_build_ab_nadd(sxc_ctx* ctx, int grid, int func, int nspin, int basis_a, 
  * 1 = SSF (aij, becke_smoothing ignored), 2 = VORONOI (:194-203). */
 int sxc_partition_weights(sxc_ctx* ctx, int flavour, int becke_smoothing, int natoms, const double* coords,
                           const double* aij, int64_t npts, const double* xyz, const int* parent, double* w);
+
+/* ---- grid construction behind the ABI (row f-1) ---------------------------------------------------------- */
+/* One atom's reference grid (AtomGridFactory::produce, grid/construction/AtomGridFactory.cpp:78-255): radial_type 0 = AHLRICHS,
+ * 1 = BECKE; accuracy 1..7; pruned Lebedev shells; points relative to the nucleus.  H..Kr. */
+typedef struct sxc_grid_points sxc_grid_points;
+int sxc_atom_grid(int nuclear_charge, int accuracy, int radial_type, sxc_grid_points** out);
+/* GridFactory::produce (grid/construction/GridFactory.cpp:52-321): atom grids shifted to the nuclei, partition weights on the
+ * device (flavour 0 = BECKE, 1 = SSF, 2 = VORONOI), weight cut (points with w <= weight_threshold dropped, reference 1e-14) and
+ * the Hilbert R-tree sort of grid/HilbertRTreeSorting.cpp:29-214 (hilbert_sort != 0).  The result feeds sxc_set_grid. */
+int sxc_molecular_grid(sxc_ctx* ctx, int natoms, const int* nuclear_charges, const double* coords_bohr, int accuracy, int flavour,
+                       int radial_type, int becke_smoothing, double weight_threshold, int hilbert_sort, sxc_grid_points** out);
+/* the permutation HilbertRTreeSorting::sort applies (descending Hilbert index, ties in input order); order[k] = input index */
+int sxc_hilbert_rtree_order(int64_t npts, const double* xyz, int64_t* order);
+int64_t sxc_grid_points_size(const sxc_grid_points* g);
+const double* sxc_grid_points_xyz(const sxc_grid_points* g);     /* 3 x N interleaved (Eigen::Matrix3Xd layout) */
+const double* sxc_grid_points_weights(const sxc_grid_points* g);
+void sxc_grid_points_free(sxc_grid_points* g);
+const char* sxc_grid_last_error(void);
 /* device time (ms, CUDA events) of the kernel inside the last sxc_partition_weights call */
 double sxc_last_partition_ms(sxc_ctx* ctx);
 

@@ -27,6 +27,8 @@ SYMBOLS = [
     "sxc_group_create", "sxc_group_destroy", "sxc_group_size", "sxc_group_ctx", "sxc_group_last_error", "sxc_group_set_grid",
     "sxc_group_add_basis", "sxc_group_set_functional", "sxc_group_release_grid", "sxc_group_release_basis", "sxc_group_build_xc",
     "sxc_group_build_nadd_multi", "sxc_group_xc_gradient", "sxc_basis_hessian_on_grid", "sxc_density_hessian_on_grid",
+    "sxc_supersystem_density_on_grid", "sxc_atom_grid", "sxc_molecular_grid", "sxc_hilbert_rtree_order", "sxc_grid_points_size",
+    "sxc_grid_points_xyz", "sxc_grid_points_weights", "sxc_grid_points_free", "sxc_grid_last_error",
 ]
 
 
@@ -87,6 +89,19 @@ def load():
     lib.sxc_basis_on_grid.argtypes = [vp, i, i, i, vp, vp, vp, vp, vp, ip]
     lib.sxc_basis_hessian_on_grid.argtypes = [vp, i, i, i, vp, vp, vp, vp, vp, vp, ip]
     lib.sxc_density_hessian_on_grid.argtypes = [vp, i, i, vp, vp, vp, vp, vp, vp, vp]
+    lib.sxc_supersystem_density_on_grid.argtypes = [vp, i, i, vp, vp, vp, vp, vp, vp]
+    lib.sxc_atom_grid.argtypes = [i, i, i, C.POINTER(vp)]
+    lib.sxc_molecular_grid.argtypes = [vp, i, vp, vp, i, i, i, i, d, i, C.POINTER(vp)]
+    lib.sxc_hilbert_rtree_order.argtypes = [i64, vp, vp]
+    lib.sxc_grid_points_size.argtypes = [vp]
+    lib.sxc_grid_points_size.restype = i64
+    lib.sxc_grid_points_xyz.argtypes = [vp]
+    lib.sxc_grid_points_xyz.restype = vp
+    lib.sxc_grid_points_weights.argtypes = [vp]
+    lib.sxc_grid_points_weights.restype = vp
+    lib.sxc_grid_points_free.argtypes = [vp]
+    lib.sxc_grid_points_free.restype = None
+    lib.sxc_grid_last_error.restype = C.c_char_p
     lib.sxc_functional_on_grid.argtypes = [vp, i, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(d)]
     lib.sxc_functional_on_grid_u.argtypes = [vp, i, i64, vp, vp, i, vp, vp, C.POINTER(d)]
     lib.sxc_scalar_to_matrix.argtypes = [vp, i, i, d, vp, vp, vp, vp, vp]

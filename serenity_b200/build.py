@@ -32,7 +32,8 @@ def build_cuda(force=False, verbose=False):
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-ccbin", "/usr/bin/g++", "-o", out,
                                                                               os.path.join(csrc, "sxc_api.cu"),
                                                                               os.path.join(csrc, "basis_provider.cpp"),
-                                                                              os.path.join(csrc, "group.cpp"), "-lpthread", "-ldl"]
+                                                                              os.path.join(csrc, "group.cpp"),
+                                                                              os.path.join(csrc, "grid_builder.cpp"), "-lpthread", "-ldl"]
         subprocess.check_call(cmd)
     return out
 

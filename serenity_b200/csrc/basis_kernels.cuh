@@ -213,7 +213,8 @@ struct __align__(8) StagedShell {
   int pad;
 };
 
-__global__ void __launch_bounds__(BASIS_GROUPS* BP) k_basis(GridView g, ShellView b, PlanView plan, int slot0,
+template <int MINB>  // resident CTAs per SM the register allocation aims at (1: 128 registers; 2: 64)
+__global__ void __launch_bounds__(BASIS_GROUPS* BP, MINB) k_basis(GridView g, ShellView b, PlanView plan, int slot0,
                                                              const int* __restrict__ order,
                                                              double* __restrict__ phi_buf) {
   __shared__ StagedShell sh_rec[SHELL_BATCH];

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(dens::PTHREADS, 2)
 k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, const WorkItem* __restrict__ items,
           const double* __restrict__ phi_buf, double* __restrict__ rho, double* __restrict__ gx,
           double* __restrict__ gy, double* __restrict__ gz, int* __restrict__ nonneg, int a_slot, int e_slot0,
-          int epi_prefetch) {
+          int epi_prefetch) {  // bit 0: L2 prefetch of the epilogue rows; bit 1 (development): epilogue of phi only
   // a_slot / e_slot0: tile slots of the A operand of the product and of the first epilogue component (0 / 0 for the density and
   // its gradient; the second derivatives of the density contract other slots of an 8-slot gradient plan, sxc_density_hessian_on_grid)
   using namespace dens;
@@ -150,7 +150,7 @@ k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, cons
   const int njt_all = (s8 + TJ - 1) / TJ;     // j-tiles of 64 of the block (= ceil(s_pad / 64), the host's count)
   const int jt_begin = item.begin, njt = item.end;  // this CTA's segment of them (normally all)
   const bool partial = jt_begin != 0 || njt != njt_all;
-  const int ncomp = gx ? 4 : 1;
+  const int ncomp = (gx && !(epi_prefetch & 2)) ? 4 : 1;
   int stage = 0, pass = 0;  // ring position; every warp walks the same chunk sequence
 
   if (warp == CWARPS) {
@@ -177,7 +177,7 @@ k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, cons
     // each, but the epilogue stages are consumed in a fraction of that and would run at HBM latency (16 stages per j-tile).  Their
     // rows are therefore pulled into L2 one component ahead with bulk prefetches (64 KB each, one instruction of one lane).
     auto prefetch_epi = [&](int jt, int comp, int nrg) {
-      if (epi_prefetch && lane == 0 && comp < ncomp)
+      if ((epi_prefetch & 1) && lane == 0 && comp < ncomp)
         bulk_prefetch_l2(tile + (e_slot0 + comp) * comp_stride + (size_t)(jt * TJ) * BP, (unsigned)(nrg * TK * BP * sizeof(double)));
     };
     for (int jt = jt_begin; jt < njt; ++jt) {

@@ -6,10 +6,11 @@
 // HBM phase (reads four tile components, writes one) followed by a pure DMMA phase, each leaving the other unit of the SM idle.
 // This kernel runs both phases of DIFFERENT blocks at the same time inside every persistent CTA:
 //
-//   warpgroups 0, 1 (8 warps)  DMMA warps of k_vmat_tma, unchanged: the rounds of block n
-//   warpgroup 2     (4 warps)  "G formers": pull the next work item from the device queue, form a, b and the block test of
-//                              block n + 1, stream its phi / grad-phi rows through a small TMA ring (4 stages of 2 rows x 4
-//                              components, no swizzle: a lane reads consecutive points) and store G into the tile's fifth slot
+//   warpgroup 0     (4 warps)  "G formers": pull the next work item from the device queue, form a, b and the block test of
+//                              block n + 1, stream its phi / grad-phi rows through private per-warp TMA rings (4 stages of 2 rows
+//                              x 32 points x 4 components, no swizzle: a lane reads consecutive points) and store G into the
+//                              tile's fifth slot
+//   warpgroups 1, 2 (8 warps)  DMMA warps of k_vmat_tma, unchanged: the rounds of block n
 //   warpgroup 3     warp 12 lane 0: the TMA producer of the operand ring (phi and G boxes of block n); the rest exits
 //
 // Registers are moved between the warpgroups with setmaxnreg: the kernel is launched at 64 registers per thread (2 CTAs of 512
@@ -28,14 +29,17 @@ constexpr int WARPS = 8;    // DMMA warps
 constexpr int HWARPS = 4;   // G formers
 constexpr int THREADS = 512;
 constexpr int PRODUCER_WARP = 12;
-constexpr int HROWS = 2;    // tile rows per stage of the formers' ring
+// every former warp owns 32 of the block's 128 points and a private TMA ring: a stage holds HROWS rows x 32 points of each of
+// the four tile components (2 KB); the warps never wait for each other inside a block
+constexpr int HROWS = 2;
 constexpr int HSTAGES = 4;
-constexpr int HPREFETCH = 12;  // stages (of 8 KB) the formers' L2 prefetch runs ahead of their TMA loads
-constexpr int H_STAGE_ELEMS = 4 * HROWS * BP;  // phi, dx, dy, dz rows
+constexpr int HPTS = 32;                            // points per former warp
+constexpr int H_STAGE_ELEMS = 4 * HROWS * HPTS;     // phi, dx, dy, dz rows of one warp's stage
+constexpr int H_WARP_ELEMS = HSTAGES * H_STAGE_ELEMS;
 using C = scat2::Cfg<8, 3>;
-constexpr int NBAR = 2 * C::STAGES + HSTAGES + 4;
+constexpr int NBAR = 2 * C::STAGES + HWARPS * HSTAGES + 4;
 constexpr size_t smem_bytes(int sig_cap) {
-  return (size_t)C::STAGES * C::STAGE_ELEMS * sizeof(double) + (size_t)HSTAGES * H_STAGE_ELEMS * sizeof(double) +
+  return (size_t)C::STAGES * C::STAGE_ELEMS * sizeof(double) + (size_t)HWARPS * H_WARP_ELEMS * sizeof(double) +
          NBAR * sizeof(uint64_t) + 16 * sizeof(double) + (size_t)sig_cap * sizeof(int) + 1024;
 }
 }  // namespace scat3
@@ -53,8 +57,13 @@ __device__ __forceinline__ void fence_global_to_async_proxy() {
   __threadfence();
   asm volatile("fence.proxy.async;\n" ::: "memory");
 }
+// Named barrier among `nthreads` threads.  bar.sync is the .aligned form: every thread of a warp must execute it together, and a
+// warp that reaches it in two pieces (lane 0 coming late out of an `if (ht == 0)` body with spin loops, which ptxas does not
+// always re-join before an opaque asm statement) is counted twice - the barrier then opens before the late lane has written what
+// the others are about to read.  So: re-converge the warp explicitly and use the form that counts threads, not warps.
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+  __syncwarp();
+  asm volatile("barrier.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 __global__ void __launch_bounds__(scat3::THREADS, 2)
@@ -69,10 +78,10 @@ k_vmat_fg(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUte
   double* stage_base = reinterpret_cast<double*>(
       smem_raw + ((1024u - (static_cast<unsigned>(__cvta_generic_to_shared(smem_raw)) & 1023u)) & 1023u));
   double* hring = stage_base + C::STAGES * C::STAGE_ELEMS;
-  uint64_t* full = reinterpret_cast<uint64_t*>(hring + HSTAGES * H_STAGE_ELEMS);
+  uint64_t* full = reinterpret_cast<uint64_t*>(hring + HWARPS * H_WARP_ELEMS);
   uint64_t* empty = full + C::STAGES;
-  uint64_t* hfull = empty + C::STAGES;
-  uint64_t* ready = hfull + HSTAGES;
+  uint64_t* hfull = empty + C::STAGES;  // [HWARPS][HSTAGES]
+  uint64_t* ready = hfull + HWARPS * HSTAGES;
   uint64_t* release = ready + 2;
   double* scratch = reinterpret_cast<double*>(release + 2);  // [8] partial sums of the block test
   int* s_item = reinterpret_cast<int*>(scratch + 8);         // [2] item index of the slot, [2] skip flag
@@ -85,7 +94,7 @@ k_vmat_fg(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUte
       mbar_init(full + i, 1);
       mbar_init(empty + i, WARPS);
     }
-    for (int i = 0; i < HSTAGES; ++i) mbar_init(hfull + i, 1);
+    for (int i = 0; i < HWARPS * HSTAGES; ++i) mbar_init(hfull + i, 1);
     for (int k = 0; k < 2; ++k) {
       mbar_init(ready + k, HWARPS * 32);  // every G former arrives after its own stores
       mbar_init(release + k, WARPS + 1);  // the DMMA warps and the operand producer
@@ -123,10 +132,12 @@ k_vmat_fg(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUte
       }
       mbar_arrive(release + k);
     }
-  } else if (warp >= WARPS) {
-    // ------------------------------------------------------------------------------------ warpgroup 2: G formers
+  } else if (warp < HWARPS) {
+    // ------------------------------------------------------------------------------------ warpgroup 0: G formers
+    // (the lowest warp ids of the CTA: when an FP64-pipe slot frees up they compete with DMMA warps that always have a tensor
+    // instruction ready; being the oldest warps of the CTA is the only lever the issue scheduler offers)
     setmaxnreg_dec<40>();
-    const int ht = tid - WARPS * 32;  // 0 .. 127: the point of the block this thread owns
+    const int ht = tid;  // 0 .. 127: the point of the block this thread owns
     int hs = 0, hpass = 0;            // ring position, carried from item to item
     for (int it = 0;; ++it) {
       const int k = it & 1;
@@ -162,7 +173,7 @@ k_vmat_fg(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUte
         }
         const double part = warp_sum(fabs(pa) + fabs(px) + fabs(py) + fabs(pz));
         double* sc = scratch + 4 * (kp & 1);  // alternate halves: one barrier per operator is enough
-        if (lane == 0) sc[warp - WARPS] = part;
+        if (lane == 0) sc[warp] = part;
         named_bar_sync(2, HWARPS * 32);
         const double total = ((sc[0] + sc[1]) + sc[2]) + sc[3];
         if (!(total / (double)n < block_ave_thr)) {
@@ -185,31 +196,45 @@ k_vmat_fg(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUte
         const int nst_all = ((dev_mode & 4) ? sp : ((s + 7) & ~7)) / HROWS;
         const int st0 = (int)((long)nst_all * item.seg / item.nseg);  // this item's piece of the rows (all of them: seg 0 of 1)
         const int nst = (dev_mode & 1) ? 0 : (int)((long)nst_all * (item.seg + 1) / item.nseg) - st0;
-        const int pf = (dev_mode & 2) ? 0 : HPREFETCH;
         double* __restrict__ gout = phi_buf + plan.phi_off[q] + (size_t)4 * sp * BP + (size_t)st0 * HROWS * BP + ht;
-        auto issue = [&](int i, int slot) {  // rows [i * HROWS, (i + 1) * HROWS) of every component into ring slot `slot`
-          mbar_arrive_expect_tx(hfull + slot, (unsigned)(ncomp * HROWS * BP * sizeof(double)));
+        const int hw = warp;  // this warp's quarter of the points and its private ring
+        double* wring = hring + hw * H_WARP_ELEMS;
+        uint64_t* wfull = hfull + hw * HSTAGES;
+        auto issue = [&](int i, int slot) {  // rows [i * HROWS, (i + 1) * HROWS) x 32 points of every component into `slot`
+          mbar_arrive_expect_tx(wfull + slot, (unsigned)(ncomp * HROWS * HPTS * sizeof(double)));
           for (int c = 0; c < ncomp; ++c)
-            tma_load_2d(hring + slot * H_STAGE_ELEMS + c * HROWS * BP, &tmap_rows, 0, row0 + c * sp + (st0 + i) * HROWS, hfull + slot);
-          if (i + pf < nst && pf > 0)  // the ring holds 24 KB in flight per CTA: too little for HBM latency; L2 latency it covers
-            for (int c = 0; c < ncomp; ++c) tma_prefetch_l2_2d(&tmap_rows, 0, row0 + c * sp + (st0 + i + pf) * HROWS);
+            tma_load_2d(wring + slot * H_STAGE_ELEMS + c * HROWS * HPTS, &tmap_rows, hw * HPTS, row0 + c * sp + (st0 + i) * HROWS,
+                        wfull + slot);
         };
-        if (ht == 0) {
-          for (int i = HSTAGES; i < min(pf, nst); ++i)
-            for (int c = 0; c < ncomp; ++c) tma_prefetch_l2_2d(&tmap_rows, 0, row0 + c * sp + (st0 + i) * HROWS);
-          for (int i = 0; i < min(HSTAGES, nst); ++i) issue(i, (hs + i) % HSTAGES);
+        // Each warp keeps 3 stages (6 KB) in flight: at HBM latency that is ~3 GB/s per warp, too little to stay ahead of the
+        // DMMA warps.  One lane of the CTA therefore pulls the rows 32..47 rows ahead into L2 (one bulk prefetch of 16 rows per
+        // component every 8 stages), so that the rings run at L2 latency.
+        const double* __restrict__ tile_rows = phi_buf + plan.phi_off[q];
+        auto prefetch_rows = [&](int r0) {  // rows [r0, r0 + 16) of this item's piece, every component
+          const int r1 = min(r0 + 16, nst * HROWS);
+          if (r1 > r0)
+            for (int c = 0; c < ncomp; ++c)
+              bulk_prefetch_l2(tile_rows + ((size_t)c * sp + (size_t)st0 * HROWS + r0) * BP, (unsigned)((r1 - r0) * BP * sizeof(double)));
+        };
+        const bool pf = ht == 0 && !(dev_mode & 2);
+        if (pf) {
+          prefetch_rows(HSTAGES * HROWS);
+          prefetch_rows(HSTAGES * HROWS + 16);
         }
+        if (lane == 0)
+          for (int i = 0; i < min(HSTAGES, nst); ++i) issue(i, (hs + i) % HSTAGES);
         for (int i = 0; i < nst; ++i) {
-          mbar_wait(hfull + hs, hpass & 1);
-          const double* st = hring + hs * H_STAGE_ELEMS + ht;
+          if (pf && (i & 7) == 0) prefetch_rows(i * HROWS + HSTAGES * HROWS + 32);
+          mbar_wait(wfull + hs, hpass & 1);
+          const double* st = wring + hs * H_STAGE_ELEMS + lane;
 #pragma unroll
           for (int r = 0; r < HROWS; ++r) {
-            double v = a * st[r * BP];
-            if (ncomp == 4) v += bx * st[(HROWS + r) * BP] + by * st[(2 * HROWS + r) * BP] + bz * st[(3 * HROWS + r) * BP];
+            double v = a * st[r * HPTS];
+            if (ncomp == 4) v += bx * st[(HROWS + r) * HPTS] + by * st[(2 * HROWS + r) * HPTS] + bz * st[(3 * HROWS + r) * HPTS];
             gout[(size_t)(i * HROWS + r) * BP] = v;
           }
-          named_bar_sync(2, HWARPS * 32);  // every former has read the slot
-          if (ht == 0 && i + HSTAGES < nst) issue(i + HSTAGES, hs);
+          __syncwarp();  // every lane has read the slot
+          if (lane == 0 && i + HSTAGES < nst) issue(i + HSTAGES, hs);
           if (++hs == HSTAGES) {
             hs = 0;
             ++hpass;
@@ -227,8 +252,9 @@ k_vmat_fg(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUte
       mbar_arrive(ready + k);
     }
   } else {
-    // ------------------------------------------------------------------------------------ warpgroups 0, 1: DMMA warps
+    // ------------------------------------------------------------------------------------ warpgroups 1, 2: DMMA warps
     setmaxnreg_inc<96>();
+    const int dwarp = warp - HWARPS, dtid = tid - HWARPS * 32;  // 0 .. 7, 0 .. 255
     int stage = 0, pass = 0;
     for (int it = 0;; ++it) {
       const int k = it & 1;
@@ -244,9 +270,9 @@ k_vmat_fg(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUte
         const ScatterRound2* __restrict__ rounds = tpl + tpl_off[sp >> 5] + item.begin;
         named_bar_sync(1, WARPS * 32);  // the epilogues of the previous item have read s_sig
         const int* __restrict__ sig_g = plan.sig_bf + (size_t)q * plan.nbf_pad;
-        for (int c = tid; c < sp; c += WARPS * 32) s_sig[c] = sig_g[c];
+        for (int c = dtid; c < sp; c += WARPS * 32) s_sig[c] = sig_g[c];
         named_bar_sync(1, WARPS * 32);
-        vmat2_consume_item<C>(rounds, item.end - item.begin, s, sp, nbf, s_sig, stage_base, full, empty, stage, pass, warp, lane, W);
+        vmat2_consume_item<C>(rounds, item.end - item.begin, s, sp, nbf, s_sig, stage_base, full, empty, stage, pass, dwarp, lane, W);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(release + k);

@@ -253,7 +253,8 @@ k_vmat_tma(const __grid_constant__ CUtensorMap tmap, PlanView plan, int nbf, con
       {  // compact -> function map of the block into shared memory (read by the RED epilogues of every round)
         const int* __restrict__ sig_g = plan.sig_bf + (size_t)q * plan.nbf_pad;
         for (int c = tid; c < sp; c += WARPS * 32) s_sig[c] = sig_g[c];
-        asm volatile("bar.sync 1, %0;\n" ::"n"(WARPS * 32) : "memory");
+        __syncwarp();
+        asm volatile("barrier.sync 1, %0;\n" ::"n"(WARPS * 32) : "memory");
       }
       vmat2_consume_item<C>(rounds, nr, s, sp, nbf, s_sig, stage_base, full, empty, stage, pass, warp, lane, W);
     }

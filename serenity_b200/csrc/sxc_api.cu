@@ -190,13 +190,16 @@ struct sxc_ctx {
   // 24 = k_vmat_fg (k_form_g fused behind the DMMA warps of the TKP = 8 kernel; chunks cut into segments fall back to 8)
   int vmat_variant = 24;
   int dens_variant = 0;  // 0 = k_density (cp.async producers; 1-3 % faster as measured), 1 = k_density_tma; SXC_DENS overrides
-  int dens_prefetch = 1;  // SXC_DPF: L2 prefetch of k_density's epilogue rows
+  int dens_prefetch = 0;  // SXC_DPF: bit 0 = L2 prefetch of k_density's epilogue rows (measured: no effect), bit 1 = development
+  int basis_variant = 0;  // SXC_BASIS: 1 = k_basis<1> (128 registers, one CTA per SM), 2 = k_basis<2> (64 registers, two CTAs), 0 = by size
+  int seg_waves = 6;  // SXC_SEG_WAVES: a shard with fewer blocks than 3 waves of resident CTAs is cut into items for this many waves
+  int fg_lead = 1;   // SXC_FG_LEAD: k_vmat_fg's queue opens with medium-sized blocks (get_plan)
   int fg_mode = 0;   // SXC_FG_MODE: development switches of k_vmat_fg
   int smem_pad = 0;  // SXC_SMEM_PAD: extra dynamic shared memory per DMMA CTA (development: forces one CTA per SM)
   int dseg = 1, vseg = 1;  // pieces per block of the k_density / k_vmat work items (SXC_DSEG / SXC_VSEG; 1 = only when a shard is small)
   CUtensorMap tmap_v8{}, tmap_v16{};  // tile workspace as [rows] x [128 points], boxes 32 x 8 (SWIZZLE_64B) and 32 x 16 (128B)
   CUtensorMap tmap_d16{};             // boxes of 16 rows x 16 points (SWIZZLE_128B) for k_density_tma
-  CUtensorMap tmap_rows{};            // boxes of scat3::HROWS whole rows (no swizzle) for the G formers of k_vmat_fg
+  CUtensorMap tmap_rows{};            // boxes of scat3::HROWS rows x 32 points (no swizzle) for the G formers of k_vmat_fg
   void* tmap_ptr = nullptr;
   size_t tmap_bytes = 0;
   DevMem phi;     // tile workspace (one chunk)
@@ -782,7 +785,7 @@ int ensure_tile_maps(sxc_ctx* ctx) {
   TRY(make_tile_map(ctx, ctx->phi, 8, 32, CU_TENSOR_MAP_SWIZZLE_64B, &ctx->tmap_v8));
   TRY(make_tile_map(ctx, ctx->phi, 16, 32, CU_TENSOR_MAP_SWIZZLE_128B, &ctx->tmap_v16));
   TRY(make_tile_map(ctx, ctx->phi, 16, 16, CU_TENSOR_MAP_SWIZZLE_128B, &ctx->tmap_d16));
-  TRY(make_tile_map(ctx, ctx->phi, BP, scat3::HROWS, CU_TENSOR_MAP_SWIZZLE_NONE, &ctx->tmap_rows));
+  TRY(make_tile_map(ctx, ctx->phi, scat3::HPTS, scat3::HROWS, CU_TENSOR_MAP_SWIZZLE_NONE, &ctx->tmap_rows));
   ctx->tmap_ptr = ctx->phi.p;
   ctx->tmap_bytes = ctx->phi.bytes;
   return SXC_OK;
@@ -909,7 +912,10 @@ int get_plan(sxc_ctx* ctx, int gh, int bh, Plan** out, int comps = TILE_COMPS) {
   // work items of the DMMA kernels: whole blocks, unless that leaves fewer than ~3 waves of the resident CTAs (strong
   // scaling of a small grid over many GPUs): then blocks are cut into segments of j-tiles / rounds
   std::vector<WorkItem> ditems, vitems;
+  // (threshold: fewer blocks than 3 waves of the resident CTAs; granularity: items for ~seg_waves waves - measured on rank 0 of an
+  // 8-rank tetracene run: 3 waves 0.892 ms per build, 4: 0.882, 6: 0.875; whole blocks: 1.07)
   const int target = 3 * 2 * ctx->num_sms;
+  const int seg_target = ctx->seg_waves * 2 * ctx->num_sms;
   for (Chunk& c : p.chunks) {
     long tot_jt = 0, tot_r = 0;
     for (int k = 0; k < c.nslots; ++k) {
@@ -919,9 +925,23 @@ int get_plan(sxc_ctx* ctx, int gh, int bh, Plan** out, int comps = TILE_COMPS) {
       tot_jt += (n32 + dens::NJW - 1) / dens::NJW;
       tot_r += tpl_off[n32 + 1] - tpl_off[n32];
     }
-    const int seg_jt = (int)std::max<long>(1, tot_jt / target), seg_r = (int)std::max<long>(1, tot_r / target);
+    const int seg_jt = (int)std::max<long>(1, tot_jt / seg_target), seg_r = (int)std::max<long>(1, tot_r / seg_target);
     c.ditem_off = (int)ditems.size();
     c.vitem_off = (int)vitems.size();
+    // k_vmat_fg forms the G of a CTA's next item while its DMMA warps contract the current one; only the FIRST item of every CTA
+    // is formed with the tensor pipe idle.  Largest-first would make those first items the most expensive ones to form (all
+    // formers start together and share HBM).  Instead the queue opens with the smallest blocks whose contraction still covers the
+    // forming of the largest block that follows (contraction ~ s^2, forming ~ s: s_first^2 >= ~100 s_max from the measured
+    // rates), as many as there are resident CTAs; everything else stays largest-first.
+    std::vector<int> vorder(order.begin() + c.slot0, order.begin() + c.slot0 + c.nslots);
+    if (p.vmat_variant == 24 && ctx->fg_lead && c.nslots > 0) {
+      const int G = 2 * ctx->num_sms;
+      const double smax = p.h_s_pad[vorder[0]];
+      const double s_first = std::sqrt(100.0 * smax);
+      int hi = 0;  // blocks [0, hi) have s_pad >= s_first (descending order)
+      while (hi < c.nslots && p.h_s_pad[vorder[hi]] >= s_first) ++hi;
+      if (hi >= 2 * G) std::rotate(vorder.begin(), vorder.begin() + (hi - G), vorder.begin() + hi);
+    }
     for (int k = 0; k < c.nslots; ++k) {
       const int q = order[c.slot0 + k];
       const int n32 = p.h_s_pad[q] / 32;
@@ -937,7 +957,11 @@ int get_plan(sxc_ctx* ctx, int gh, int bh, Plan** out, int comps = TILE_COMPS) {
         for (int sgi = 0; sgi < nseg; ++sgi)  // equal-sized segments
           ditems.push_back(WorkItem{q, (short)((long)njt * sgi / nseg), (short)((long)njt * (sgi + 1) / nseg), (short)sgi, (short)nseg});
       }
+    }
+    for (int k = 0; k < c.nslots; ++k) {
+      const int q = vorder[k];
       if (p.h_s[q] == 0) continue;
+      const int n32 = p.h_s_pad[q] / 32;
       const int nr = tpl_off[n32 + 1] - tpl_off[n32];
       const int want_v = ctx->vseg > 1 ? std::min(nr, ctx->vseg) : 1;
       if (want_v <= 1 && (nr <= seg_r || c.nslots >= target)) {
@@ -1014,8 +1038,15 @@ int phase_basis(sxc_ctx* ctx, const Grid& g, const Basis& b, const Plan& p, cons
   if (!buf) ctx->phi_owner = p.chunks.size() == 1 ? p.serial : 0;
   CU(phi.ensure(c.doubles * sizeof(double)));
   PhaseTimer t(ctx, SXC_T_BASIS);
-  k_basis<<<c.nslots, BASIS_GROUPS * BP, 0, ctx->stream>>>(g.view(), b.view(), p.view(), c.slot0,
-                                                            p.order.as<int>() + c.order_off, phi.as<double>());
+  // 64 registers / two CTAs per SM pay off when shells are small (def2-SVP: (H2O)64 0.90 -> 0.79 ms, peptide 2.21 -> 1.87 ms;
+  // def2-TZVP tetracene unchanged) and the chunk has enough blocks for two waves of them; a small shard is faster with one
+  const int variant = ctx->basis_variant ? ctx->basis_variant : (c.nslots >= 4 * ctx->num_sms ? 2 : 1);
+  if (variant == 2)
+    k_basis<2><<<c.nslots, BASIS_GROUPS * BP, 0, ctx->stream>>>(g.view(), b.view(), p.view(), c.slot0,
+                                                               p.order.as<int>() + c.order_off, phi.as<double>());
+  else
+    k_basis<1><<<c.nslots, BASIS_GROUPS * BP, 0, ctx->stream>>>(g.view(), b.view(), p.view(), c.slot0,
+                                                               p.order.as<int>() + c.order_off, phi.as<double>());
   LAUNCH_CHECK();
   return SXC_OK;
 }
@@ -1099,8 +1130,10 @@ int phase_scatter(sxc_ctx* ctx, const Grid& g, const Basis& b, const Plan& p, co
   const double* v_gy = gga ? pot4 + 2 * N : nullptr;
   const double* v_gz = gga ? pot4 + 3 * N : nullptr;
   const int grid = std::min(c.nvitems, 2 * ctx->num_sms);
-  if (p.vmat_variant == 24) {
-    // one launch: G of block n + 1 is formed by the helper warpgroup while the DMMA warps contract block n (scatter_fused.cuh)
+  if (p.vmat_variant == 24 && (c.vitems_whole || (ctx->fg_mode & 8))) {
+    // one launch: G of block n + 1 is formed by the helper warpgroup while the DMMA warps contract block n (scatter_fused.cuh).
+    // Shards cut into segments (few blocks per GPU) take the two-launch path below: there the formers of several CTAs share a
+    // block and the wait for the last piece costs more than k_form_g does (measured, profiles/r02_scatter_fused.md)
     if (c.nvitems == 0) return SXC_OK;
     int* counter = nullptr;
     TRY(next_counter(ctx, &counter));
@@ -1747,6 +1780,9 @@ int sxc_create(sxc_ctx** out, int device) {
   if (const char* v = std::getenv("SXC_DENS")) ctx->dens_variant = std::atoi(v) ? 1 : 0;
   if (const char* v = std::getenv("SXC_COPY_THREADS")) ctx->copy_threads = std::max(0, std::min(16, std::atoi(v)));
   if (const char* v = std::getenv("SXC_DPF")) ctx->dens_prefetch = std::atoi(v);
+  if (const char* v = std::getenv("SXC_BASIS")) ctx->basis_variant = std::max(0, std::min(2, std::atoi(v)));
+  if (const char* v = std::getenv("SXC_SEG_WAVES")) ctx->seg_waves = std::max(1, std::atoi(v));
+  if (const char* v = std::getenv("SXC_FG_LEAD")) ctx->fg_lead = std::atoi(v);
   if (const char* v = std::getenv("SXC_FG_MODE")) ctx->fg_mode = std::atoi(v);
   if (const char* v = std::getenv("SXC_SMEM_PAD")) ctx->smem_pad = std::max(0, std::atoi(v));
   if (const char* v = std::getenv("SXC_DSEG")) ctx->dseg = std::max(1, std::atoi(v));
@@ -2163,7 +2199,7 @@ int sxc_basis_on_grid(sxc_ctx* ctx, int grid, int basis, int block, double* val,
     if (q >= c.slot0 && q < c.slot0 + c.nslots) ch = &c;
   ctx->phi_owner = 0;  // the single block is evaluated into the workspace: cached tiles are gone
   CU(ctx->phi.ensure(ch->doubles * sizeof(double)));
-  k_basis<<<1, BASIS_GROUPS * BP, 0, ctx->stream>>>(g.view(), b.view(), p.view(), q, nullptr, ctx->phi.as<double>());
+  k_basis<1><<<1, BASIS_GROUPS * BP, 0, ctx->stream>>>(g.view(), b.view(), p.view(), q, nullptr, ctx->phi.as<double>());
   LAUNCH_CHECK();
   const int s = p.h_s[q], sp = p.h_s_pad[q];
   std::vector<double> tile((size_t)4 * sp * BP);
@@ -2191,6 +2227,53 @@ int sxc_basis_on_grid(sxc_ctx* ctx, int grid, int basis, int block, double* val,
       std::copy(src, src + n, outs[comp] + (size_t)sig[c] * n);
     }
   }
+  return SXC_OK;
+}
+
+// SupersystemDensityOnGridController::updateData (data/grid/SupersystemDensityOnGridController.cpp:95-193): the densities (and
+// gradients) of several subsystems, each in its own basis, summed on the common grid - the stage NAddFuncPotential uses for
+// rho_tot.  Subsystems are added in the order given, starting from zero, as the reference does; host outputs [N].
+int sxc_supersystem_density_on_grid(sxc_ctx* ctx, int grid, int ndens, const int* basis, const double* const* P, double* rho,
+                                    double* gx, double* gy, double* gz) {
+  if (!ctx || ndens < 1 || !basis || !P || !rho) return fail(ctx, SXC_ERR_INVALID, "sxc_supersystem_density_on_grid: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  Grid* gp = get_grid(ctx, grid);
+  if (!gp) return fail(ctx, SXC_ERR_INVALID, "invalid grid handle %d", grid);
+  Grid& g = *gp;
+  for (int i = 0; i < ndens; ++i) {
+    Plan* pp = nullptr;
+    if (!get_basis(ctx, basis[i]) || !P[i]) return fail(ctx, SXC_ERR_INVALID, "invalid basis handle or matrix of density %d", i);
+    TRY(get_plan(ctx, grid, basis[i], &pp));
+  }
+  TRY(ensure_point_arrays(ctx, g, true, 1));
+  const long N = g.npts;
+  g.env_valid = false;  // the accumulator is the frozen-environment cache of sxc_build_nadd
+  CU(cudaMemsetAsync(g.envsum.p, 0, (size_t)4 * N * sizeof(double), ctx->stream));
+  for (int i = 0; i < ndens; ++i) {
+    Basis& b = *get_basis(ctx, basis[i]);
+    Plan* pp = nullptr;
+    TRY(get_plan(ctx, grid, basis[i], &pp));
+    const size_t nb2 = (size_t)b.nbf * b.nbf;
+    CU(ctx->dP.ensure(nb2 * sizeof(double)));
+    CU(cudaMemcpyAsync(ctx->dP.p, P[i], nb2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));  // (dP is reused by the next subsystem; a diagnostic entry point)
+    for (const Chunk& c : pp->chunks) {
+      if (c.nslots == 0) continue;
+      TRY(phase_basis(ctx, g, b, *pp, c));
+      TRY(phase_density(ctx, g, b, *pp, c, ctx->dP.as<double>(), g.dens.as<double>(), gx != nullptr, nullptr));
+      k_add4<<<c.nslots, 128, 0, ctx->stream>>>(N, g.blocksize, gx ? 4 : 1, pp->block_id.as<int>() + c.slot0, g.envsum.as<double>(),
+                                                g.dens.as<double>(), g.envsum.as<double>());
+      LAUNCH_CHECK();
+    }
+  }
+  const double* d = g.envsum.as<double>();
+  CU(cudaMemcpyAsync(rho, d, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (gx) {
+    CU(cudaMemcpyAsync(gx, d + N, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(gy, d + 2 * N, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(gz, d + 3 * N, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
   return SXC_OK;
 }
 

@@ -33,6 +33,36 @@ def _spin_unpack(buf):
     return tuple(np.asfortranarray(buf[s].reshape(nb, nb, order="F")) for s in range(2))
 
 
+def _take_grid_points(lib, handle):
+    n = lib.sxc_grid_points_size(handle)
+    xyz = np.ctypeslib.as_array(C.cast(lib.sxc_grid_points_xyz(handle), C.POINTER(C.c_double)), shape=(n, 3)).copy()
+    w = np.ctypeslib.as_array(C.cast(lib.sxc_grid_points_weights(handle), C.POINTER(C.c_double)), shape=(n,)).copy()
+    lib.sxc_grid_points_free(handle)
+    return xyz, w
+
+
+def atom_grid(nuclear_charge: int, accuracy: int, radial: str = "AHLRICHS"):
+    """Row f-1 through the C ABI (sxc_atom_grid, host only): AtomGridFactory::produce - points relative to the nucleus [n, 3]
+    and weights [n] of one atom's pruned reference grid."""
+    lib = _lib.load()
+    h = C.c_void_p()
+    rc = lib.sxc_atom_grid(int(nuclear_charge), int(accuracy), {"AHLRICHS": 0, "BECKE": 1}[radial], C.byref(h))
+    if rc != 0:
+        raise _lib.SerenityError(lib.sxc_grid_last_error().decode())
+    return _take_grid_points(lib, h)
+
+
+def hilbert_rtree_order(xyz):
+    """sxc_hilbert_rtree_order (host only): the permutation HilbertRTreeSorting::sort applies."""
+    lib = _lib.load()
+    xyz = _f64(xyz).reshape(-1, 3)
+    order = np.zeros(xyz.shape[0], dtype=np.int64)
+    rc = lib.sxc_hilbert_rtree_order(xyz.shape[0], _ptr(xyz), _ptr(order))
+    if rc != 0:
+        raise _lib.SerenityError(lib.sxc_grid_last_error().decode())
+    return order
+
+
 def shell_table_from_file(path: str, basis_label: str, symbols, coords_bohr, spherical: bool = True):
     """Row f-2 through the C ABI (sxc_shell_table_from_file): BasisFunctionProvider + Shell + extended indices of the
     reference for a geometry and a Turbomole-format basis file.  Returns (ShellTable, atom_of_bf); host only."""
@@ -301,6 +331,17 @@ class XCContext:
         # library layout: n x nbf column-major (index mu*n + p)
         return [a.reshape(-1)[: n * nbf].reshape(nbf, n).T for a in arrs], neg, n
 
+    def supersystem_density_on_grid(self, grid, bases, Ps, npts: int, gradient: bool = True):
+        """SupersystemDensityOnGridController: sum of the subsystem densities (and gradients) on the common grid."""
+        Ps = [np.asfortranarray(P, dtype=np.float64) for P in Ps]
+        rho = np.zeros(npts)
+        g = [np.zeros(npts) for _ in range(3)] if gradient else [None, None, None]
+        barr = (C.c_int * len(bases))(*bases)
+        parr = (C.c_void_p * len(Ps))(*[P.ctypes.data for P in Ps])
+        self._check(self._lib.sxc_supersystem_density_on_grid(self._h, grid, len(bases), barr, parr, _ptr(rho), _ptr(g[0]),
+                                                              _ptr(g[1]), _ptr(g[2])))
+        return rho, g
+
     def basis_hessian_on_grid(self, grid, basis, block: int, nbf: int, blocksize: int = 128):
         """xx, xy, xz, yy, yz, zz second derivatives of every basis function on one block, each [n, nbf]."""
         arrs = [np.zeros((nbf, blocksize)) for _ in range(6)]
@@ -409,6 +450,20 @@ class XCContext:
                                                     None if a is None else _ptr(a), xyz.shape[0], _ptr(xyz), _ptr(parent),
                                                     _ptr(out)))
         return out, float(self._lib.sxc_last_partition_ms(self._h))
+
+    def molecular_grid(self, nuclear_charges, coords_bohr, accuracy: int = 4, flavour: str = "SSF", radial: str = "AHLRICHS",
+                       smoothing: int = 3, weight_threshold: float = 1e-14, hilbert_sort: bool = True):
+        """GridFactory::produce behind the C ABI (sxc_molecular_grid): atom grids, partition weights on the device, weight cut,
+        Hilbert R-tree order.  Returns (xyz [N, 3], w [N]) ready for set_grid."""
+        z = np.ascontiguousarray(nuclear_charges, dtype=np.int32)
+        coords = _f64(coords_bohr).reshape(-1, 3)
+        h = C.c_void_p()
+        rc = self._lib.sxc_molecular_grid(self._h, len(z), _ptr(z), _ptr(coords), int(accuracy),
+                                          {"BECKE": 0, "SSF": 1, "VORONOI": 2}[flavour], {"AHLRICHS": 0, "BECKE": 1}[radial],
+                                          int(smoothing), float(weight_threshold), 1 if hilbert_sort else 0, C.byref(h))
+        if rc != 0:
+            raise _lib.SerenityError(self._lib.sxc_grid_last_error().decode())
+        return _take_grid_points(self._lib, h)
 
     # ---- row f-4: LR-TDDFT kernel
     def kernel_create(self, grid: int, nspin: int = 1, gga: bool = True) -> int:

@@ -119,6 +119,35 @@ def test_hessians_vs_oracle_all_l(ctx, orc):
         assert np.allclose(h, r, rtol=1e-11, atol=1e-11)
 
 
+def test_supersystem_density_is_the_exact_sum(ctx, fixtures, small_mixed):
+    """SupersystemDensityOnGridController_test.cpp:43-90: a supersystem of twice the same subsystem has EXACTLY rho + rho and
+    grad rho + grad rho on every point (EXPECT_EQ in the reference: bit-for-bit), and a third copy adds once more."""
+    gold = load_golden("density_ref.json")
+    xyz, w = grid_arrays(fixtures, "TINY")
+    g = ctx.set_grid(xyz, w, gold["block_size"])
+    b = ctx.add_basis(small_mixed, 1e-300)
+    P = np.asarray(gold["P"])
+    rho, grad = ctx.density_on_grid(g, b, P, 4)
+    rho2, grad2 = ctx.supersystem_density_on_grid(g, [b, b], [P, P], 4)
+    assert np.array_equal(rho2, rho + rho)
+    for k in range(3):
+        assert np.array_equal(grad2[k], grad[k] + grad[k])
+    rho3, grad3 = ctx.supersystem_density_on_grid(g, [b, b, b], [P, P, P], 4)
+    assert np.array_equal(rho3, (rho + rho) + rho)
+    # two different subsystems on a molecular grid: the sum of the separately evaluated densities, in the order given
+    from serenity_b200.inputs import make_config
+    cfg = make_config("fde_dimer", 2)
+    act, env = cfg.subsystems
+    gg = ctx.set_grid(cfg.xyz, cfg.w, 128)
+    ba, be = ctx.add_basis(act.basis, 1e-9), ctx.add_basis(env.basis, 1e-9)
+    ra, ga = ctx.density_on_grid(gg, ba, act.P, cfg.npts)
+    re_, ge = ctx.density_on_grid(gg, be, env.P, cfg.npts)
+    rs, gs = ctx.supersystem_density_on_grid(gg, [ba, be], [act.P, env.P], cfg.npts)
+    assert np.array_equal(rs, ra + re_)
+    for k in range(3):
+        assert np.array_equal(gs[k], ga[k] + ge[k])
+
+
 def test_golden_scalar_to_matrix(ctx, fixtures, small_mixed):
     """ScalarOperatorToMatrixAdder_test.cpp:41-148 (55 elements, GGA variant, block size 3)."""
     gold = load_golden("scatter_ref.json")

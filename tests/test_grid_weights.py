@@ -170,3 +170,65 @@ def test_hilbert_rtree_sort_known_answer_of_the_reference():
     step_sorted = np.linalg.norm(np.diff(gx, axis=0), axis=1).mean()
     step_unsorted = np.linalg.norm(np.diff(gu, axis=0), axis=1).mean()
     assert step_sorted < 0.5 * step_unsorted
+
+
+# ------------------------------------------------------------------------------------------------ grid construction in C++ (f-1)
+@pytest.mark.parametrize("z,acc,radial", [(1, 4, "AHLRICHS"), (6, 4, "AHLRICHS"), (8, 6, "AHLRICHS"), (7, 2, "AHLRICHS"), (1, 1, "AHLRICHS"),
+                                          (6, 4, "BECKE"), (1, 3, "BECKE")])
+def test_cpp_atom_grid_matches_the_python_restatement(z, acc, radial):
+    """sxc_atom_grid (csrc/grid_builder.cpp: AtomGridFactory.cpp:78-255) against serenity_b200.inputs.grid.atom_grid, which meets
+    the property tests of AtomGridFactory_test.cpp:46-99: same point count and order, coordinates and weights to rounding."""
+    from serenity_b200.inputs.grid import atom_grid as py_atom_grid
+    from serenity_b200.xc import atom_grid
+    xyz, w = atom_grid(z, acc, radial)
+    pxyz, pw = py_atom_grid(z, acc, radial)
+    assert xyz.shape == pxyz.shape and w.shape == pw.shape
+    assert np.abs(xyz - pxyz).max() <= 1e-13 * np.abs(pxyz).max()
+    assert np.abs(w - pw).max() <= 1e-13 * np.abs(pw).max()
+    # the unit sphere integrates to its volume through every shell structure (Lebedev weights sum to 1 per shell)
+    r = np.linalg.norm(xyz, axis=1)
+    f = np.exp(-r * r)
+    assert abs(np.dot(w, f) - np.pi ** 1.5) < 2e-5 * np.pi ** 1.5
+
+
+def test_cpp_atom_grid_rejects_what_it_has_no_data_for():
+    from serenity_b200._lib import SerenityError
+    from serenity_b200.xc import atom_grid
+    with pytest.raises(SerenityError, match="H..Kr"):
+        atom_grid(40, 4)
+    with pytest.raises(SerenityError, match="Bragg-Slater"):
+        atom_grid(2, 4, "BECKE")
+
+
+def test_cpp_hilbert_rtree_order_reproduces_the_reference_known_answer():
+    """HilbertRTreeSorting_test.cpp:32-54 (the 2 x 2 x 2 cube) through sxc_hilbert_rtree_order, and the Python restatement on a
+    molecular point cloud."""
+    from serenity_b200.inputs.grid import hilbert_rtree_order as py_order
+    from serenity_b200.xc import hilbert_rtree_order
+    x = [+0.5, -0.5, +0.5, -0.5, -0.5, +0.5, +0.5, -0.5]  # (Eigen's comma initialiser fills the 3 x 8 matrix row by row)
+    y = [+0.5, -0.5, -0.5, +0.5, +0.5, -0.5, +0.5, -0.5]
+    z = [+0.5, -0.5, -0.5, +0.5, -0.5, +0.5, -0.5, +0.5]
+    assert list(hilbert_rtree_order(np.stack([x, y, z], axis=1))) == [3, 7, 1, 4, 6, 2, 5, 0]
+    rng = np.random.default_rng(5)
+    cloud = rng.normal(size=(20000, 3)) * np.array([3.0, 1.0, 2.0])
+    assert np.array_equal(hilbert_rtree_order(cloud), py_order(cloud))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flavour", ["SSF", "BECKE"])
+def test_cpp_molecular_grid_matches_the_python_pipeline(flavour):
+    """GridFactory::produce behind the C ABI (sxc_molecular_grid): same points in the same order as the Python pipeline with the
+    reference's sort, weights to rounding."""
+    from serenity_b200.inputs import geometry as geo
+    from serenity_b200.inputs.geometry import atomic_numbers
+    from serenity_b200.inputs.grid import molecular_grid
+    from serenity_b200.xc import XCContext
+    symbols, coords = geo.water_cluster(2)
+    ctx = XCContext(0)
+    try:
+        xyz, w = ctx.molecular_grid(atomic_numbers(symbols), coords, 3, flavour)
+        pxyz, pw = molecular_grid(symbols, coords, 3, flavour, sort="reference", device_ctx=ctx)
+        assert xyz.shape == pxyz.shape
+        assert np.abs(xyz - pxyz).max() <= 1e-12 and np.abs(w - pw).max() <= 1e-12 * np.abs(pw).max()
+    finally:
+        ctx.close()

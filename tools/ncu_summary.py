@@ -2,7 +2,7 @@
 """Summarise ncu outputs into small tracked files under profiles/.
 
   python tools/ncu_summary.py launches <launches.csv> <out.md>     per-kernel launch counts, device time and share
-  python tools/ncu_summary.py full <report.ncu-rep> <out.md> [traffic.json workload]
+  python tools/ncu_summary.py full <report.ncu-rep> <out.md> [traffic.json workload [n<ranks>]]
         per-kernel roofline-relevant counters of an `ncu --set full` capture (read with `ncu -i ... --page raw --csv`)
 """
 import collections
@@ -61,7 +61,7 @@ def launches(path, out):
                 "serialised - compare shares, not absolutes)\n")
 
 
-def full(rep, out, traffic_json=None, workload=None):
+def full(rep, out, traffic_json=None, workload=None, ranks="n1"):
     txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     h, units = rows[0], rows[1]
@@ -69,7 +69,7 @@ def full(rep, out, traffic_json=None, workload=None):
     seen, traffic = set(), {}
     with open(out, "w") as f:
         for r in rows[2:]:
-            name = r[col["Kernel Name"]].split("(")[0]
+            name = r[col["Kernel Name"]].split("(")[0].replace("void ", "")
             if name in seen:
                 continue
             seen.add(name)
@@ -82,13 +82,16 @@ def full(rep, out, traffic_json=None, workload=None):
             def byt(m):
                 v, u = float(r[col[m]].replace(",", "")), units[col[m]]
                 return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[u]
-            traffic[name.replace("sxc::", "")] = byt("dram__bytes_read.sum") + byt("dram__bytes_write.sum")
+            short = name.replace("sxc::", "").split("<")[0]
+            traffic[short] = byt("dram__bytes_read.sum") + byt("dram__bytes_write.sum")
+            if short in ("k_vmat_fg", "k_vmat_tma"):  # bench.py names the scatter contraction "k_vmat" whichever variant ran
+                traffic.setdefault("k_vmat", traffic[short])
     if traffic_json:
         try:
             d = json.load(open(traffic_json))
         except (OSError, ValueError):
             d = {}
-        d.setdefault(workload, {}).update(traffic)
+        d.setdefault(workload, {}).setdefault(ranks, {}).update(traffic)  # {workload: {"n<N>": {kernel: bytes per launch}}}
         json.dump(d, open(traffic_json, "w"), indent=1, sort_keys=True)
 
 
