@@ -33,6 +33,7 @@ struct NcclApi {
   int (*CommInitAll)(nccl_comm_t*, int, const int*) = nullptr;
   int (*CommDestroy)(nccl_comm_t) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
@@ -65,6 +66,7 @@ struct NcclApi {
     CommInitAll = reinterpret_cast<decltype(CommInitAll)>(sym("ncclCommInitAll"));
     CommDestroy = reinterpret_cast<decltype(CommDestroy)>(sym("ncclCommDestroy"));
     AllReduce = reinterpret_cast<decltype(AllReduce)>(sym("ncclAllReduce"));
+    AllGather = reinterpret_cast<decltype(AllGather)>(sym("ncclAllGather"));
     GroupStart = reinterpret_cast<decltype(GroupStart)>(sym("ncclGroupStart"));
     GroupEnd = reinterpret_cast<decltype(GroupEnd)>(sym("ncclGroupEnd"));
     GetErrorString = reinterpret_cast<decltype(GetErrorString)>(sym("ncclGetErrorString"));

@@ -16,8 +16,10 @@
 // Registers are moved between the warpgroups with setmaxnreg: the kernel is launched at 64 registers per thread (2 CTAs of 512
 // threads per SM), the DMMA warpgroups grow to 96, the G formers shrink to 40, warpgroup 3 to 24.  The G of a block travels
 // through HBM/L2 as before (the rounds of the schedule re-stage it), but the two CTAs of an SM and the two halves of a CTA keep
-// the HBM pipe and the DMMA pipe busy together.  Item slots are double-buffered in shared memory: `ready[k]` (G formers ->
-// consumers: item index, skip flag and G are valid) and `release[k]` (consumers -> G formers: the slot may be reused).
+// the HBM pipe and the DMMA pipe busy together.  The two sides are decoupled: the formers of all CTAs work through the block
+// queue from their own counter and publish a per-block flag in global memory (release), the operand producer of the CTA that
+// contracts a block waits for its flag (acquire) - the formers never wait for anybody, so they run as far ahead as their
+// throughput allows.  (FP64 FMAs and DMMA share one pipe, so the formers' arithmetic is not free: DESIGN.md section 3.)
 #pragma once
 
 #include "scatter_tma.cuh"
@@ -68,11 +70,16 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 __global__ void __launch_bounds__(scat3::THREADS, 2)
 k_vmat_fg(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_rows, GridView g, PlanView plan,
-          int nbf, const WorkItem* __restrict__ items, int nitems, int* __restrict__ counter,
-          const ScatterRound2* __restrict__ tpl, const int* __restrict__ tpl_off, int sig_cap, double block_ave_thr,
-          double a_scale, const double* __restrict__ v_rho, const double* __restrict__ v_gx, const double* __restrict__ v_gy,
-          const double* __restrict__ v_gz, int npot, size_t pot_stride, double* __restrict__ phi_buf, double* __restrict__ W,
-          int* __restrict__ gflag, int dev_mode) {  // dev_mode (development, SXC_FG_MODE): 1 = the formers skip the row loop (timing experiment: wrong G)
+          int nbf, const WorkItem* __restrict__ items, int nitems, const int* __restrict__ fblocks, int nfblocks,
+          int* __restrict__ counter, int* __restrict__ fcounter, const ScatterRound2* __restrict__ tpl,
+          const int* __restrict__ tpl_off, int sig_cap,
+          double block_ave_thr, double a_scale, const double* __restrict__ v_rho, const double* __restrict__ v_gx,
+          const double* __restrict__ v_gy, const double* __restrict__ v_gz, int npot, size_t pot_stride,
+          double* __restrict__ phi_buf, double* __restrict__ W, int* __restrict__ gflag, int dev_mode) {
+  // items: blocks, or segments of their rounds when a shard is small, in queue order; fblocks: the blocks themselves in the same
+  // order.  The formers of all CTAs form fblocks[0 .. nfblocks) from their own counter and publish gflag[q] = 1 (formed) or 2 (the
+  // block-average test failed); the contraction side pulls items from `counter` and waits for the flag of its block.
+  // dev_mode (development, SXC_FG_MODE): 1 = the formers skip the row loop (timing experiment: wrong G)
   using namespace scat3;
   extern __shared__ unsigned char smem_raw[];
   double* stage_base = reinterpret_cast<double*>(
@@ -84,8 +91,9 @@ k_vmat_fg(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUte
   uint64_t* ready = hfull + HWARPS * HSTAGES;
   uint64_t* release = ready + 2;
   double* scratch = reinterpret_cast<double*>(release + 2);  // [8] partial sums of the block test
-  int* s_item = reinterpret_cast<int*>(scratch + 8);         // [2] item index of the slot, [2] skip flag
+  int* s_item = reinterpret_cast<int*>(scratch + 8);         // [2] item index of the slot, [2] skip flag, [1] the formers' item
   int* s_skip = s_item + 2;
+  int* s_fitem = s_item + 4;
   int* s_sig = reinterpret_cast<int*>(scratch + 16);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -96,8 +104,8 @@ k_vmat_fg(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUte
     }
     for (int i = 0; i < HWARPS * HSTAGES; ++i) mbar_init(hfull + i, 1);
     for (int k = 0; k < 2; ++k) {
-      mbar_init(ready + k, HWARPS * 32);  // every G former arrives after its own stores
-      mbar_init(release + k, WARPS + 1);  // the DMMA warps and the operand producer
+      mbar_init(ready + k, 1);        // the operand producer publishes an item slot
+      mbar_init(release + k, WARPS);  // the DMMA warps are done with it
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmap);
@@ -112,25 +120,27 @@ k_vmat_fg(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUte
     int stage = 0, pass = 0;
     for (int it = 0;; ++it) {
       const int k = it & 1;
-      mbar_wait(ready + k, (it >> 1) & 1);
-      const int qi = s_item[k];
-      if (qi >= nitems) return;
-      const bool skip = s_skip[k] != 0;
+      if (it >= 2) mbar_wait(release + k, ((it >> 1) - 1) & 1);  // the DMMA warps have left the slot's previous item
+      const int qi = atomicAdd(counter, 1);
+      s_item[k] = qi;
+      if (qi >= nitems) {
+        mbar_arrive(ready + k);
+        return;
+      }
+      const WorkItem item = items[qi];
+      const int q = item.q;
+      int f;
+      while ((f = ld_acquire_gpu(gflag + q)) == 0) __nanosleep(100);
+      const int skip = f == 2;
+      asm volatile("fence.proxy.async;\n" ::: "memory");  // the formers' (generic-proxy) stores before this thread's TMA loads
+      s_skip[k] = skip;
+      mbar_arrive(ready + k);
       if (!skip) {
-        const WorkItem item = items[qi];
-        const int q = item.q;
         const int sp = plan.s_pad[q];
         const ScatterRound2* __restrict__ rounds = tpl + tpl_off[sp >> 5] + item.begin;
         const int row0 = (int)(plan.phi_off[q] / BP);
-        if (item.nseg > 1) {
-          // the block was cut into several work items (small shard): each item's formers made one piece of its G; wait for all
-          // of them (they run in CTAs that pulled their items earlier or at the same time and never wait themselves)
-          while (ld_acquire_gpu(gflag + q) < item.nseg) __nanosleep(200);
-          asm volatile("fence.proxy.async;\n" ::: "memory");
-        }
         vmat2_produce_item<C>(&tmap, rounds, item.end - item.begin, row0, row0 + 4 * sp, stage_base, full, empty, stage, pass);
       }
-      mbar_arrive(release + k);
     }
   } else if (warp < HWARPS) {
     // ------------------------------------------------------------------------------------ warpgroup 0: G formers
@@ -138,21 +148,13 @@ k_vmat_fg(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUte
     // instruction ready; being the oldest warps of the CTA is the only lever the issue scheduler offers)
     setmaxnreg_dec<40>();
     const int ht = tid;  // 0 .. 127: the point of the block this thread owns
-    int hs = 0, hpass = 0;            // ring position, carried from item to item
-    for (int it = 0;; ++it) {
-      const int k = it & 1;
-      if (ht == 0) {
-        if (it >= 2) mbar_wait(release + k, ((it >> 1) - 1) & 1);
-        s_item[k] = atomicAdd(counter, 1);
-      }
+    int hs = 0, hpass = 0;  // ring position, carried from item to item
+    for (;;) {
+      if (ht == 0) *s_fitem = atomicAdd(fcounter, 1);
       named_bar_sync(2, HWARPS * 32);
-      const int qi = s_item[k];
-      if (qi >= nitems) {
-        mbar_arrive(ready + k);
-        return;
-      }
-      const WorkItem item = items[qi];
-      const int q = item.q;
+      const int fi = *s_fitem;
+      if (fi >= nfblocks) return;
+      const int q = fblocks[fi];
       const long first = (long)plan.block_id[q] * g.blocksize;
       const int n = (int)min((long)g.blocksize, g.npts - first);
       // a = w v_rho, b = w g of the operators that pass their own block-average test (:253-268; npot > 1: summed scatter of
@@ -186,70 +188,48 @@ k_vmat_fg(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUte
       }
       const int s = plan.s[q];
       const bool skip = !any_pass || s == 0;
-      if (ht == 0) s_skip[k] = skip ? 1 : 0;
       if (!skip) {
         a *= a_scale;  // 1/2: the T + T^T trick of :281
         const int sp = plan.s_pad[q];
         const int row0 = (int)(plan.phi_off[q] / BP);
         const int ncomp = v_gx ? 4 : 1;
         // rows beyond s rounded up to 8 are never multiplied by the DMMA warps (vmat2_consume_item): G is formed for the others
-        const int nst_all = ((dev_mode & 4) ? sp : ((s + 7) & ~7)) / HROWS;
-        const int st0 = (int)((long)nst_all * item.seg / item.nseg);  // this item's piece of the rows (all of them: seg 0 of 1)
-        const int nst = (dev_mode & 1) ? 0 : (int)((long)nst_all * (item.seg + 1) / item.nseg) - st0;
-        double* __restrict__ gout = phi_buf + plan.phi_off[q] + (size_t)4 * sp * BP + (size_t)st0 * HROWS * BP + ht;
+        const int nst = (dev_mode & 1) ? 0 : ((s + 7) & ~7) / HROWS;
+        double* __restrict__ gout = phi_buf + plan.phi_off[q] + (size_t)4 * sp * BP + ht;
         const int hw = warp;  // this warp's quarter of the points and its private ring
         double* wring = hring + hw * H_WARP_ELEMS;
         uint64_t* wfull = hfull + hw * HSTAGES;
         auto issue = [&](int i, int slot) {  // rows [i * HROWS, (i + 1) * HROWS) x 32 points of every component into `slot`
           mbar_arrive_expect_tx(wfull + slot, (unsigned)(ncomp * HROWS * HPTS * sizeof(double)));
           for (int c = 0; c < ncomp; ++c)
-            tma_load_2d(wring + slot * H_STAGE_ELEMS + c * HROWS * HPTS, &tmap_rows, hw * HPTS, row0 + c * sp + (st0 + i) * HROWS,
-                        wfull + slot);
+            tma_load_2d(wring + slot * H_STAGE_ELEMS + c * HROWS * HPTS, &tmap_rows, hw * HPTS, row0 + c * sp + i * HROWS, wfull + slot);
         };
-        // Each warp keeps 3 stages (6 KB) in flight: at HBM latency that is ~3 GB/s per warp, too little to stay ahead of the
-        // DMMA warps.  One lane of the CTA therefore pulls the rows 32..47 rows ahead into L2 (one bulk prefetch of 16 rows per
-        // component every 8 stages), so that the rings run at L2 latency.
-        const double* __restrict__ tile_rows = phi_buf + plan.phi_off[q];
-        auto prefetch_rows = [&](int r0) {  // rows [r0, r0 + 16) of this item's piece, every component
-          const int r1 = min(r0 + 16, nst * HROWS);
-          if (r1 > r0)
-            for (int c = 0; c < ncomp; ++c)
-              bulk_prefetch_l2(tile_rows + ((size_t)c * sp + (size_t)st0 * HROWS + r0) * BP, (unsigned)((r1 - r0) * BP * sizeof(double)));
-        };
-        const bool pf = ht == 0 && !(dev_mode & 2);
-        if (pf) {
-          prefetch_rows(HSTAGES * HROWS);
-          prefetch_rows(HSTAGES * HROWS + 16);
-        }
-        if (lane == 0)
+        const bool no_loads = (dev_mode & 16) != 0, no_stores = (dev_mode & 32) != 0;  // development: which part interferes
+        if (lane == 0 && !no_loads)
           for (int i = 0; i < min(HSTAGES, nst); ++i) issue(i, (hs + i) % HSTAGES);
         for (int i = 0; i < nst; ++i) {
-          if (pf && (i & 7) == 0) prefetch_rows(i * HROWS + HSTAGES * HROWS + 32);
-          mbar_wait(wfull + hs, hpass & 1);
+          if (!no_loads) mbar_wait(wfull + hs, hpass & 1);
           const double* st = wring + hs * H_STAGE_ELEMS + lane;
 #pragma unroll
           for (int r = 0; r < HROWS; ++r) {
             double v = a * st[r * HPTS];
             if (ncomp == 4) v += bx * st[(HROWS + r) * HPTS] + by * st[(2 * HROWS + r) * HPTS] + bz * st[(3 * HROWS + r) * HPTS];
-            gout[(size_t)(i * HROWS + r) * BP] = v;
+            if (!no_stores || v == 1.2345678e300) gout[(size_t)(i * HROWS + r) * BP] = v;
           }
           __syncwarp();  // every lane has read the slot
-          if (lane == 0 && i + HSTAGES < nst) issue(i + HSTAGES, hs);
+          if (lane == 0 && i + HSTAGES < nst && !no_loads) issue(i + HSTAGES, hs);
           if (++hs == HSTAGES) {
             hs = 0;
             ++hpass;
           }
         }
-        fence_global_to_async_proxy();
-        if (item.nseg > 1) {  // publish this piece (every former's stores are fenced above; the barrier orders them before the count)
-          named_bar_sync(2, HWARPS * 32);
-          if (ht == 0) {
-            __threadfence();
-            atomicAdd(gflag + q, 1);
-          }
-        }
+        __threadfence();  // this thread's G stores are visible device-wide before the flag below
       }
-      mbar_arrive(ready + k);
+      named_bar_sync(2, HWARPS * 32);  // all formers have stored and fenced (and read s_fitem)
+      if (ht == 0) {
+        __threadfence();
+        atomicExch(gflag + q, skip ? 2 : 1);
+      }
     }
   } else {
     // ------------------------------------------------------------------------------------ warpgroups 1, 2: DMMA warps

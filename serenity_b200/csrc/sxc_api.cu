@@ -132,6 +132,7 @@ struct Chunk {
   int ditem_off = 0, nditems = 0;  // k_density work items
   int vitem_off = 0, nvitems = 0;  // k_vmat work items
   bool vitems_whole = true;        // every k_vmat work item is a whole block (k_vmat_fg can form G for it)
+  int fblock_off = 0, nfblocks = 0;  // k_vmat_fg: the chunk's blocks with s > 0 in queue order (what its formers walk through)
   bool dens_split = false;         // some block's j-tiles are spread over several CTAs (outputs accumulated)
 };
 
@@ -143,7 +144,8 @@ struct Plan {
   int s_pad_max = 0;
   int vmat_variant = 0;  // scatter kernel the round templates / work items were made for
   DevMem block_id, nsig_shell, s, sig_shell, sig_c0, sig_bf, s_pad, phi_off, order, tpl, tpl_off, skip, ditems, vitems;
-  DevMem gflag;  // [nown] k_vmat_fg: pieces of a block's G formed so far, when the block is cut into several work items
+  DevMem gflag;   // [nown] k_vmat_fg: 0 = G of the block not formed yet, 1 = formed, 2 = block-average test failed
+  DevMem vorder;  // plan slots of the blocks with s > 0 in k_vmat's queue order, chunk by chunk (the formers' list of k_vmat_fg)
   std::vector<int> h_s, h_s_pad;
   std::vector<Chunk> chunks;
   sxc_stats stats{};
@@ -193,7 +195,10 @@ struct sxc_ctx {
   int dens_prefetch = 0;  // SXC_DPF: bit 0 = L2 prefetch of k_density's epilogue rows (measured: no effect), bit 1 = development
   int basis_variant = 0;  // SXC_BASIS: 1 = k_basis<1> (128 registers, one CTA per SM), 2 = k_basis<2> (64 registers, two CTAs), 0 = by size
   int seg_waves = 6;  // SXC_SEG_WAVES: a shard with fewer blocks than 3 waves of resident CTAs is cut into items for this many waves
-  int fg_lead = 1;   // SXC_FG_LEAD: k_vmat_fg's queue opens with medium-sized blocks (get_plan)
+  int fg_lead = 0;   // SXC_FG_LEAD (development): k_vmat_fg's queue opens with medium-sized blocks (get_plan)
+  // SXC_FG_SEG = 1: k_vmat_fg also on shards whose blocks are cut into segments.  Measured on rank 0 of an 8- / 4-rank tetracene
+  // run: 0.918 / 1.704 ms per build against 0.873 / 1.665 ms with k_form_g + k_vmat_tma, so such shards take the two launches
+  int fg_segments = 0;
   int fg_mode = 0;   // SXC_FG_MODE: development switches of k_vmat_fg
   int smem_pad = 0;  // SXC_SMEM_PAD: extra dynamic shared memory per DMMA CTA (development: forces one CTA per SM)
   int dseg = 1, vseg = 1;  // pieces per block of the k_density / k_vmat work items (SXC_DSEG / SXC_VSEG; 1 = only when a shard is small)
@@ -320,6 +325,7 @@ int set_kernel_attrs(sxc_ctx* ctx) {
 }
 
 constexpr size_t STAGE_MIN_BYTES = (size_t)1 << 20;  // smaller transfers are left to the driver
+constexpr size_t P_SLACK_BYTES = 1024;  // room behind the density matrices in ctx->dP: an all-gather of ceil(n / world) doubles per rank
 constexpr size_t STAGE_CHUNK = (size_t)4 << 20;
 
 bool is_pageable(const void* p) {
@@ -400,8 +406,27 @@ int wait_p_ready(sxc_ctx* ctx) {
     for (const auto& u : ctx->pending) total += u.bytes;
     if (ctx->copy_threads > 0 && total >= STAGE_MIN_BYTES) TRY(ensure_staging(ctx, &ctx->h_up, &ctx->h_up_bytes, total));
     size_t off = 0;
+    // With a communicator every rank holds the SAME host matrix: each uploads 1 / world of it over its own PCIe link and the
+    // slices are all-gathered over NVLink (the matrix crosses PCIe once per build instead of once per rank; the decision
+    // depends on sizes only, so every rank takes it alike).  The gather writes ceil(n / world) doubles per rank: up to world - 1
+    // doubles of padding behind the matrix, which the next matrix's gather overwrites or P_SLACK_BYTES absorbs.
+    const int W = ctx->comm ? ctx->comm_world : 1;
+    const char* p0 = static_cast<const char*>(ctx->dP.p);
     for (const auto& u : ctx->pending) {
-      TRY(staged_h2d(ctx, u.dst, u.src, u.bytes, off, ctx->copy_stream));
+      const char* d0 = static_cast<const char*>(u.dst);
+      const bool in_dp = p0 && d0 >= p0 && d0 + u.bytes + P_SLACK_BYTES <= p0 + ctx->dP.bytes;
+      if (W > 1 && (size_t)W * sizeof(double) <= P_SLACK_BYTES && u.bytes >= STAGE_MIN_BYTES && u.bytes % sizeof(double) == 0 && in_dp) {
+        const size_t n = u.bytes / sizeof(double), cnt = (n + W - 1) / W;
+        const size_t lo = std::min(n, (size_t)ctx->comm_rank * cnt), hi = std::min(n, lo + cnt);
+        if (hi > lo)
+          TRY(staged_h2d(ctx, static_cast<double*>(u.dst) + lo, static_cast<const double*>(u.src) + lo, (hi - lo) * sizeof(double), off,
+                         ctx->copy_stream));
+        const int rc = nccl().AllGather(static_cast<double*>(u.dst) + (size_t)ctx->comm_rank * cnt, u.dst, cnt, NCCL_DOUBLE, ctx->comm,
+                                        ctx->copy_stream);
+        if (rc != NCCL_SUCCESS) return fail(ctx, SXC_ERR_CUDA, "ncclAllGather failed: %s", nccl().GetErrorString(rc));
+      } else {
+        TRY(staged_h2d(ctx, u.dst, u.src, u.bytes, off, ctx->copy_stream));
+      }
       off += u.bytes;
     }
     ctx->pending.clear();
@@ -912,6 +937,7 @@ int get_plan(sxc_ctx* ctx, int gh, int bh, Plan** out, int comps = TILE_COMPS) {
   // work items of the DMMA kernels: whole blocks, unless that leaves fewer than ~3 waves of the resident CTAs (strong
   // scaling of a small grid over many GPUs): then blocks are cut into segments of j-tiles / rounds
   std::vector<WorkItem> ditems, vitems;
+  std::vector<int> vq;  // plan slots of the blocks behind vitems, each once
   // (threshold: fewer blocks than 3 waves of the resident CTAs; granularity: items for ~seg_waves waves - measured on rank 0 of an
   // 8-rank tetracene run: 3 waves 0.892 ms per build, 4: 0.882, 6: 0.875; whole blocks: 1.07)
   const int target = 3 * 2 * ctx->num_sms;
@@ -928,6 +954,7 @@ int get_plan(sxc_ctx* ctx, int gh, int bh, Plan** out, int comps = TILE_COMPS) {
     const int seg_jt = (int)std::max<long>(1, tot_jt / seg_target), seg_r = (int)std::max<long>(1, tot_r / seg_target);
     c.ditem_off = (int)ditems.size();
     c.vitem_off = (int)vitems.size();
+    c.fblock_off = (int)vq.size();
     // k_vmat_fg forms the G of a CTA's next item while its DMMA warps contract the current one; only the FIRST item of every CTA
     // is formed with the tensor pipe idle.  Largest-first would make those first items the most expensive ones to form (all
     // formers start together and share HBM).  Instead the queue opens with the smallest blocks whose contraction still covers the
@@ -964,6 +991,7 @@ int get_plan(sxc_ctx* ctx, int gh, int bh, Plan** out, int comps = TILE_COMPS) {
       const int n32 = p.h_s_pad[q] / 32;
       const int nr = tpl_off[n32 + 1] - tpl_off[n32];
       const int want_v = ctx->vseg > 1 ? std::min(nr, ctx->vseg) : 1;
+      vq.push_back(q);
       if (want_v <= 1 && (nr <= seg_r || c.nslots >= target)) {
         vitems.push_back(WorkItem{q, 0, (short)nr, 0, 1});
       } else {
@@ -973,10 +1001,13 @@ int get_plan(sxc_ctx* ctx, int gh, int bh, Plan** out, int comps = TILE_COMPS) {
           vitems.push_back(WorkItem{q, (short)((long)nr * sgi / nseg), (short)((long)nr * (sgi + 1) / nseg), (short)sgi, (short)nseg});
       }
     }
+    c.nfblocks = (int)vq.size() - c.fblock_off;
     c.nditems = (int)ditems.size() - c.ditem_off;
     c.nvitems = (int)vitems.size() - c.vitem_off;
   }
   CU(p.gflag.ensure(std::max<size_t>(p.nown, 1) * sizeof(int)));
+  CU(p.vorder.ensure(std::max<size_t>(vq.size(), 1) * sizeof(int)));
+  if (!vq.empty()) CU(cudaMemcpyAsync(p.vorder.p, vq.data(), vq.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   CU(p.ditems.ensure(std::max<size_t>(ditems.size(), 1) * sizeof(WorkItem)));
   CU(p.vitems.ensure(std::max<size_t>(vitems.size(), 1) * sizeof(WorkItem)));
   if (!ditems.empty())
@@ -1130,21 +1161,20 @@ int phase_scatter(sxc_ctx* ctx, const Grid& g, const Basis& b, const Plan& p, co
   const double* v_gy = gga ? pot4 + 2 * N : nullptr;
   const double* v_gz = gga ? pot4 + 3 * N : nullptr;
   const int grid = std::min(c.nvitems, 2 * ctx->num_sms);
-  if (p.vmat_variant == 24 && (c.vitems_whole || (ctx->fg_mode & 8))) {
-    // one launch: G of block n + 1 is formed by the helper warpgroup while the DMMA warps contract block n (scatter_fused.cuh).
-    // Shards cut into segments (few blocks per GPU) take the two-launch path below: there the formers of several CTAs share a
-    // block and the wait for the last piece costs more than k_form_g does (measured, profiles/r02_scatter_fused.md)
+  if (p.vmat_variant == 24 && (c.vitems_whole || ctx->fg_segments)) {
+    // one launch: the helper warpgroups of all CTAs form G block by block in queue order while the DMMA warps contract the work
+    // items (blocks, or segments of their rounds on a small shard) whose G is ready (scatter_fused.cuh)
     if (c.nvitems == 0) return SXC_OK;
-    int* counter = nullptr;
+    int *counter = nullptr, *fcounter = nullptr;
     TRY(next_counter(ctx, &counter));
+    TRY(next_counter(ctx, &fcounter));
     TRY(ensure_tile_maps(ctx));
     PhaseTimer t(ctx, SXC_T_SCATTER);
-    if (!c.vitems_whole)  // blocks cut into several work items: their formers count the finished pieces here
-      CU(cudaMemsetAsync(p.gflag.as<int>() + c.slot0, 0, (size_t)c.nslots * sizeof(int), ctx->stream));
+    CU(cudaMemsetAsync(p.gflag.as<int>() + c.slot0, 0, (size_t)c.nslots * sizeof(int), ctx->stream));
     k_vmat_fg<<<grid, scat3::THREADS, scat3::smem_bytes(p.s_pad_max), ctx->stream>>>(
-        ctx->tmap_v8, ctx->tmap_rows, g.view(), p.view(), b.nbf, p.vitems.as<WorkItem>() + c.vitem_off, c.nvitems, counter,
-        p.tpl.as<ScatterRound2>(), p.tpl_off.as<int>(), p.s_pad_max, block_ave_thr, 0.5, pot4, v_gx, v_gy, v_gz, npot, pot_stride,
-        ctx->phi.as<double>(), dW, p.gflag.as<int>(), ctx->fg_mode);
+        ctx->tmap_v8, ctx->tmap_rows, g.view(), p.view(), b.nbf, p.vitems.as<WorkItem>() + c.vitem_off, c.nvitems,
+        p.vorder.as<int>() + c.fblock_off, c.nfblocks, counter, fcounter, p.tpl.as<ScatterRound2>(), p.tpl_off.as<int>(), p.s_pad_max,
+        block_ave_thr, 0.5, pot4, v_gx, v_gy, v_gz, npot, pot_stride, ctx->phi.as<double>(), dW, p.gflag.as<int>(), ctx->fg_mode);
     LAUNCH_CHECK();
     return SXC_OK;
   }
@@ -1783,6 +1813,7 @@ int sxc_create(sxc_ctx** out, int device) {
   if (const char* v = std::getenv("SXC_BASIS")) ctx->basis_variant = std::max(0, std::min(2, std::atoi(v)));
   if (const char* v = std::getenv("SXC_SEG_WAVES")) ctx->seg_waves = std::max(1, std::atoi(v));
   if (const char* v = std::getenv("SXC_FG_LEAD")) ctx->fg_lead = std::atoi(v);
+  if (const char* v = std::getenv("SXC_FG_SEG")) ctx->fg_segments = std::atoi(v);
   if (const char* v = std::getenv("SXC_FG_MODE")) ctx->fg_mode = std::atoi(v);
   if (const char* v = std::getenv("SXC_SMEM_PAD")) ctx->smem_pad = std::max(0, std::atoi(v));
   if (const char* v = std::getenv("SXC_DSEG")) ctx->dseg = std::max(1, std::atoi(v));
@@ -2070,7 +2101,7 @@ int sxc_build_xc(sxc_ctx* ctx, int grid, int basis, int func, int nspin, const d
   if (!b) return fail(ctx, SXC_ERR_INVALID, "invalid basis handle %d", basis);
   CU(cudaSetDevice(ctx->device));
   const size_t nv = (size_t)nspin * b->nbf * b->nbf;
-  CU(ctx->dP.ensure(nv * sizeof(double)));
+  CU(ctx->dP.ensure(nv * sizeof(double) + P_SLACK_BYTES));
   CU(ctx->dOut.ensure((nv + 2) * sizeof(double)));
   HostCall host_guard{ctx};
   TRY(upload_async(ctx, ctx->dP.p, P, nv * sizeof(double)));
@@ -2125,7 +2156,7 @@ int sxc_build_nadd_multi(sxc_ctx* ctx, int grid, int nfunc, const int* funcs, in
     offs[i] = total;
     total += (size_t)nspin * be->nbf * be->nbf;
   }
-  CU(ctx->dP.ensure(total * sizeof(double)));
+  CU(ctx->dP.ensure(total * sizeof(double) + P_SLACK_BYTES));
   CU(ctx->dOut.ensure((nV + nE) * sizeof(double)));
   HostCall host_guard{ctx};
   TRY(upload_async(ctx, ctx->dP.p, P_act, nvA * sizeof(double)));
@@ -2165,7 +2196,7 @@ int sxc_density_on_grid(sxc_ctx* ctx, int grid, int basis, const double* P, doub
   TRY(ensure_point_arrays(ctx, g, false, 1));
   const size_t nb2 = (size_t)b.nbf * b.nbf;
   const long N = g.npts;
-  CU(ctx->dP.ensure(nb2 * sizeof(double)));
+  CU(ctx->dP.ensure(nb2 * sizeof(double) + P_SLACK_BYTES));
   CU(cudaMemcpyAsync(ctx->dP.p, P, nb2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemsetAsync(g.dens.p, 0, (size_t)4 * N * sizeof(double), ctx->stream));
   for (const Chunk& c : pp->chunks) {
@@ -2254,7 +2285,7 @@ int sxc_supersystem_density_on_grid(sxc_ctx* ctx, int grid, int ndens, const int
     Plan* pp = nullptr;
     TRY(get_plan(ctx, grid, basis[i], &pp));
     const size_t nb2 = (size_t)b.nbf * b.nbf;
-    CU(ctx->dP.ensure(nb2 * sizeof(double)));
+    CU(ctx->dP.ensure(nb2 * sizeof(double) + P_SLACK_BYTES));
     CU(cudaMemcpyAsync(ctx->dP.p, P[i], nb2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));  // (dP is reused by the next subsystem; a diagnostic entry point)
     for (const Chunk& c : pp->chunks) {
@@ -2346,7 +2377,7 @@ int sxc_density_hessian_on_grid(sxc_ctx* ctx, int grid, int basis, const double*
   TRY(ensure_point_arrays(ctx, g, false, 2));  // two [4][N] outputs
   const size_t nb2 = (size_t)b.nbf * b.nbf;
   const long N = g.npts;
-  CU(ctx->dP.ensure(nb2 * sizeof(double)));
+  CU(ctx->dP.ensure(nb2 * sizeof(double) + P_SLACK_BYTES));
   CU(cudaMemcpyAsync(ctx->dP.p, P, nb2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   double* t1 = g.dens.as<double>();          // [4][N]: (unused), 2 sum (phi P) d_d d_c phi for c = x, y, z
   double* t2 = t1 + (size_t)4 * N;           // [4][N]: (unused), 2 sum (d_d phi P) d_c phi
@@ -2534,7 +2565,7 @@ int sxc_build_ab(sxc_ctx* ctx, int grid, int func, int nspin, int basis_a, int b
     offs[i] = total;
     total += (size_t)nspin * bc->nbf * bc->nbf;
   }
-  CU(ctx->dP.ensure(total * sizeof(double)));
+  CU(ctx->dP.ensure(total * sizeof(double) + P_SLACK_BYTES));
   CU(ctx->dOut.ensure((nab + 2) * sizeof(double)));
   std::vector<const double*> dpc(ndens);
   HostCall host_guard{ctx};
@@ -2573,7 +2604,7 @@ int sxc_build_ab_nadd(sxc_ctx* ctx, int grid, int func, int nspin, int basis_a, 
     offs[i] = total;
     total += (size_t)nspin * be->nbf * be->nbf;
   }
-  CU(ctx->dP.ensure(total * sizeof(double)));
+  CU(ctx->dP.ensure(total * sizeof(double) + P_SLACK_BYTES));
   CU(ctx->dOut.ensure((nab + 2) * sizeof(double)));
   HostCall host_guard{ctx};
   TRY(upload_async(ctx, ctx->dP.p, P_act, (size_t)nspin * bact->nbf * bact->nbf * sizeof(double)));
@@ -2623,7 +2654,7 @@ int sxc_xc_gradient(sxc_ctx* ctx, int grid, int basis, int func, int nspin, cons
     if (atom_of_bf[i] < 0 || atom_of_bf[i] >= natoms) return fail(ctx, SXC_ERR_INVALID, "atom_of_bf[%d] out of range", i);
   CU(cudaSetDevice(ctx->device));
   const size_t nv = (size_t)nspin * b->nbf * b->nbf;
-  CU(ctx->dP.ensure(nv * sizeof(double)));
+  CU(ctx->dP.ensure(nv * sizeof(double) + P_SLACK_BYTES));
   CU(ctx->dOut.ensure((size_t)b->nbf * 3 * sizeof(double)));
   HostCall host_guard{ctx};
   TRY(upload_async(ctx, ctx->dP.p, P, nv * sizeof(double)));
@@ -2729,7 +2760,7 @@ int sxc_nadd_gradient(sxc_ctx* ctx, int grid, int func, int nspin, int basis_act
     offs[i] = total;
     total += (size_t)nspin * be->nbf * be->nbf;
   }
-  CU(ctx->dP.ensure(total * sizeof(double)));
+  CU(ctx->dP.ensure(total * sizeof(double) + P_SLACK_BYTES));
   CU(ctx->dOut.ensure((size_t)b->nbf * 3 * sizeof(double)));
   HostCall host_guard{ctx};
   TRY(upload_async(ctx, ctx->dP.p, P_act, nvA * sizeof(double)));
@@ -2810,7 +2841,7 @@ int sxc_kernel_add(sxc_ctx* ctx, int kernel, int func, double sign, int ndens, c
     offs[i] = total;
     total += (size_t)nspin * bc->nbf * bc->nbf;
   }
-  CU(ctx->dP.ensure(total * sizeof(double)));
+  CU(ctx->dP.ensure(total * sizeof(double) + P_SLACK_BYTES));
   HostCall host_guard{ctx};
   for (int i = 0; i < ndens; ++i) {
     Basis* bc = get_basis(ctx, basis_c[i]);
