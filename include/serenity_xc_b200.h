@@ -117,6 +117,10 @@ int sxc_set_p_ready_event(sxc_ctx* ctx, void* cuda_event);
 /* per-kernel CUDA-event timing of the *_device builds (off by default: events cost a few microseconds each);
  * sxc_get_stats() then synchronises on the last build's events */
 int sxc_set_timing(sxc_ctx* ctx, int on);
+/* Several contexts of ONE process that write their (identical, all-reduced) result matrix into the same caller buffer: this
+ * context copies back only part `part` of `parts` of V in sxc_build_xc / sxc_build_nadd[_multi] (the matrix then crosses N PCIe
+ * links at once).  Set by sxc_group_create for its workers; default 0 of 1 = the whole matrix. */
+int sxc_set_output_slice(sxc_ctx* ctx, int part, int parts);
 
 /* Optional page-locked host memory (cudaHostAlloc) for the P / V buffers of the host-buffer builds: with it their copies are
  * asynchronous DMA; with ordinary (pageable) caller memory - what Eigen matrices in Serenity are - the driver stages them. */
@@ -146,8 +150,8 @@ int sxc_comm_info(sxc_ctx* ctx, int* rank, int* world, int64_t* collectives, int
 /* The reference calls getMatrix() from its single SCF driver thread; a single-process host gets the multi-GPU build through a
  * group (the form SURVEY.md section 8b sketches as sxc_create(ctx, ngpu, devices)): one context and one host worker thread per
  * GPU, communicators created inside (ncclCommInitRank from every worker), every call below handed to all workers.  Handles
- * returned by the group name the same object on every context.  A group build returns the all-reduced result through the
- * first context's copy-back; P / V are caller-owned host buffers as in sxc_build_xc.  ngpu = 1 works (no NCCL needed). */
+ * returned by the group name the same object on every context.  A group build returns the all-reduced result in the caller's
+ * buffer, every context copying back its 1 / ngpu of the matrix over its own PCIe link (sxc_set_output_slice); P / V are caller-owned host buffers as in sxc_build_xc.  ngpu = 1 works (no NCCL needed). */
 typedef struct sxc_group sxc_group;
 int sxc_group_create(sxc_group** group, int ngpu, const int* devices /* NULL: 0 .. ngpu-1 */);
 void sxc_group_destroy(sxc_group* group);

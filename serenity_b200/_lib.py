@@ -28,7 +28,7 @@ SYMBOLS = [
     "sxc_group_add_basis", "sxc_group_set_functional", "sxc_group_release_grid", "sxc_group_release_basis", "sxc_group_build_xc",
     "sxc_group_build_nadd_multi", "sxc_group_xc_gradient", "sxc_basis_hessian_on_grid", "sxc_density_hessian_on_grid",
     "sxc_supersystem_density_on_grid", "sxc_atom_grid", "sxc_molecular_grid", "sxc_hilbert_rtree_order", "sxc_grid_points_size",
-    "sxc_grid_points_xyz", "sxc_grid_points_weights", "sxc_grid_points_free", "sxc_grid_last_error",
+    "sxc_grid_points_xyz", "sxc_grid_points_weights", "sxc_grid_points_free", "sxc_grid_last_error", "sxc_set_output_slice",
 ]
 
 
@@ -74,6 +74,7 @@ def load():
     lib.sxc_set_stream.argtypes = [vp, vp]
     lib.sxc_set_workspace_limit.argtypes = [vp, i64]
     lib.sxc_set_timing.argtypes = [vp, i]
+    lib.sxc_set_output_slice.argtypes = [vp, i, i]
     lib.sxc_set_tile_cache.argtypes = [vp, i]
     lib.sxc_set_p_ready_event.argtypes = [vp, vp]
     lib.sxc_set_grid.argtypes = [vp, i64, vp, vp, i, ip]

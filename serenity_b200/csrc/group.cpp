@@ -103,7 +103,11 @@ int sxc_group_create(sxc_group** out, int ngpu, const int* devices) {
     unsigned char id[SXC_COMM_ID_BYTES];
     int rc = sxc_comm_unique_id(id);
     if (rc == SXC_OK)  // every rank joins from its own thread (ncclCommInitRank blocks until all have arrived)
-      rc = g->all([&](int r, sxc_ctx* c) { return sxc_comm_init_rank(c, r, ngpu, id); });
+      rc = g->all([&](int r, sxc_ctx* c) {
+        const int rr = sxc_comm_init_rank(c, r, ngpu, id);
+        // every rank ends a build with the same all-reduced matrix: each copies 1 / ngpu of it into the caller's buffer
+        return rr != SXC_OK ? rr : sxc_set_output_slice(c, r, ngpu);
+      });
     if (rc != SXC_OK) {
       sxc_group_destroy(g);
       return rc;
@@ -185,8 +189,8 @@ int sxc_group_build_xc(sxc_group* g, int grid, int basis, int func, int nspin, c
                        double* nelec) {
   if (!g || !P || !V || !E) return SXC_ERR_INVALID;
   std::vector<double> e(g->workers.size(), 0.0), n(g->workers.size(), 0.0);
-  const int rc = g->all([&](int r, sxc_ctx* c) {  // every rank ends with the all-reduced [V | E | N]; rank 0 alone copies V back
-    return sxc_build_xc(c, grid, basis, func, nspin, P, thr, r == 0 ? V : nullptr, &e[r], &n[r]);
+  const int rc = g->all([&](int r, sxc_ctx* c) {  // every rank ends with the all-reduced [V | E | N] and copies its part of V back
+    return sxc_build_xc(c, grid, basis, func, nspin, P, thr, V, &e[r], &n[r]);
   });
   if (rc != SXC_OK) return rc;
   *E = e[0];
@@ -202,7 +206,7 @@ int sxc_group_build_nadd_multi(sxc_group* g, int grid, int nfunc, const int* fun
   std::vector<std::vector<double>> e(g->workers.size(), std::vector<double>(ne, 0.0));
   const int rc = g->all([&](int r, sxc_ctx* c) {
     return sxc_build_nadd_multi(c, grid, nfunc, funcs, nspin, basis_act, P_act, nenv, basis_env, P_env, env_frozen, thr,
-                                sum_matrices, r == 0 ? V_act : nullptr, e[r].data());
+                                sum_matrices, V_act, e[r].data());
   });
   if (rc != SXC_OK) return rc;
   std::memcpy(E, e[0].data(), ne * sizeof(double));

@@ -247,6 +247,7 @@ struct sxc_ctx {
   size_t h_up_bytes = 0, h_down_bytes = 0;
   std::vector<cudaEvent_t> chunk_events;
   int copy_threads = 4;    // SXC_COPY_THREADS (0: leave pageable transfers to the driver)
+  int out_part = 0, out_parts = 1;  // sxc_set_output_slice: this context copies back part out_part of out_parts of a result matrix
   struct Stamp {
     int slot;
     cudaEvent_t a, b;
@@ -389,6 +390,14 @@ int staged_d2h(sxc_ctx* ctx, void* dst, const void* src, size_t bytes, cudaStrea
     CU(cudaEventSynchronize(ctx->chunk_events[c]));
     ctx->copier->copy(static_cast<char*>(dst) + off, st + off, n);
   }
+  return SXC_OK;
+}
+
+// result matrix -> the caller's buffer: all of it, or this context's part when several contexts of one process share the buffer
+// (sxc_set_output_slice: every GPU of a group then moves 1 / N of the matrix over its own PCIe link)
+int result_d2h(sxc_ctx* ctx, double* dst, const double* src, size_t n) {
+  const size_t lo = n * (size_t)ctx->out_part / (size_t)ctx->out_parts, hi = n * ((size_t)ctx->out_part + 1) / (size_t)ctx->out_parts;
+  if (hi > lo) TRY(staged_d2h(ctx, dst + lo, src + lo, (hi - lo) * sizeof(double), ctx->stream));
   return SXC_OK;
 }
 
@@ -2111,7 +2120,7 @@ int sxc_build_xc(sxc_ctx* ctx, int grid, int basis, int func, int nspin, const d
   if (rc != SXC_OK) return abort_build(ctx, rc);
   std::vector<double> tail(2);
   CU(cudaMemcpyAsync(tail.data(), ctx->dOut.as<double>() + nv, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  if (V) TRY(staged_d2h(ctx, V, ctx->dOut.p, nv * sizeof(double), ctx->stream));
+  if (V) TRY(result_d2h(ctx, V, ctx->dOut.as<double>(), nv));
   CU(cudaStreamSynchronize(ctx->stream));
   collect_timers(ctx);
   *E = tail[0];
@@ -2174,7 +2183,7 @@ int sxc_build_nadd_multi(sxc_ctx* ctx, int grid, int nfunc, const int* funcs, in
   ctx->timing = 0;
   if (rc != SXC_OK) return abort_build(ctx, rc);
   CU(cudaMemcpyAsync(E, ctx->dOut.as<double>() + nV, nE * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  if (V_act) TRY(staged_d2h(ctx, V_act, ctx->dOut.p, nV * sizeof(double), ctx->stream));
+  if (V_act) TRY(result_d2h(ctx, V_act, ctx->dOut.as<double>(), nV));
   CU(cudaStreamSynchronize(ctx->stream));
   collect_timers(ctx);
   return SXC_OK;
@@ -2635,6 +2644,13 @@ int sxc_set_tile_cache(sxc_ctx* ctx, int on) {
   if (!ctx) return SXC_ERR_INVALID;
   ctx->tile_cache = on != 0;
   if (!on) ctx->phi_owner = 0;
+  return SXC_OK;
+}
+
+int sxc_set_output_slice(sxc_ctx* ctx, int part, int parts) {
+  if (!ctx || parts < 1 || part < 0 || part >= parts) return SXC_ERR_INVALID;
+  ctx->out_part = part;
+  ctx->out_parts = parts;
   return SXC_OK;
 }
 

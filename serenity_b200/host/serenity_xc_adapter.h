@@ -32,6 +32,10 @@ class SerenityError : public std::runtime_error {
 
 namespace Options {
 enum class SCF_MODES { RESTRICTED = 0, UNRESTRICTED = 1 };
+// settings/EmbeddingOptions.h:42-52
+enum class KIN_EMBEDDING_MODES {
+  NONE = 0, NADD_FUNC = 1, LEVELSHIFT = 2, HUZINAGA = 3, HOFFMANN = 4, RECONSTRUCTION = 5, FERMI_SHIFTED_HUZINAGA = 6, LOEWDIN = 7, ALMO = 8
+};
 }
 
 // Column-major dense matrix with Eigen::MatrixXd's memory layout (data()[row + rows * col]).
@@ -825,9 +829,64 @@ class Kernel {
                                    pc.data()));
     }
   }
+  // Mixed exact / approximate embedding, Kernel::calculateDerivativesMixedEmbedding (Kernel.cpp:752-888): subsystems whose
+  // embedding mode is LEVELSHIFT or HUZINAGA are "exact" (their non-additive XC functional is naddXCExact and they carry no
+  // non-additive kinetic term), all others "approximate" (naddXCApprox + naddKinFunc).  Three kinds of store:
+  //   sub[I]  + func_I[rho_I]; exact: - naddXCExact[rho_I]; approximate: - naddXCApprox[rho_I] - naddKin[rho_I]      (:788-850)
+  //   tot     + naddXCApprox[rho_all] + naddKin[rho_all]                                                                 (:857-870)
+  //   exact   + naddXCExact[rho_ex] - naddXCApprox[rho_ex] - naddKin[rho_ex],  rho_ex = sum over the exact subsystems      (:871-887)
+  // (the `samedensity` list of the reference, which drops duplicate densities from the sums, is not mirrored)
+  Kernel(std::shared_ptr<B200::XCDevice> device, std::shared_ptr<GridController> grid,
+         std::vector<std::shared_ptr<DensityMatrixController<SCFMode>>> dMats, std::vector<Functional> funcs,
+         std::vector<Options::KIN_EMBEDDING_MODES> embeddingModes, Functional naddXCExact, Functional naddXCApprox,
+         Functional naddKinFunc, bool gga = true)
+    : _dev(std::move(device)), _grid(std::move(grid)), _dMats(std::move(dMats)), _gga(gga), _modes(std::move(embeddingModes)) {
+    if (_dMats.empty() || funcs.size() != _dMats.size() || _modes.size() != _dMats.size())
+      throw SerenityError("Kernel: one functional and one embedding mode per subsystem are needed");
+    const int g = _grid->handle(_dev);
+    const int nspin = detail::nspin<SCFMode>();
+    std::vector<int> bc, bex;
+    std::vector<const double*> pc, pex;
+    for (size_t I = 0; I < _dMats.size(); ++I) {
+      const auto m = _modes[I];
+      if (m == Options::KIN_EMBEDDING_MODES::FERMI_SHIFTED_HUZINAGA || m == Options::KIN_EMBEDDING_MODES::HOFFMANN ||
+          m == Options::KIN_EMBEDDING_MODES::RECONSTRUCTION)
+        throw SerenityError("Exact embedding mode not supported in list input yet!");  // Kernel.cpp:820-824
+      bc.push_back(_dMats[I]->getBasisController()->handle(_dev));
+      pc.push_back(_dMats[I]->getDensityMatrix().data());
+      if (isExact(I)) {
+        bex.push_back(bc.back());
+        pex.push_back(pc.back());
+      }
+    }
+    auto add = [&](int store, const Functional& f, double sign, int n, const int* b, const double* const* p) {
+      if (!f.basicFunctionals.empty() && n > 0)
+        _dev->check(sxc_kernel_add(_dev->get(), store, detail::functionalHandle(*_dev, f), sign, n, b, p));
+    };
+    for (size_t I = 0; I < _dMats.size(); ++I) {
+      int k = -1;
+      _dev->check(sxc_kernel_create(_dev->get(), g, nspin, _gga ? 1 : 0, &k));
+      _sub.push_back(k);
+      add(k, funcs[I], 1.0, 1, &bc[I], &pc[I]);
+      if (isExact(I)) {
+        add(k, naddXCExact, -1.0, 1, &bc[I], &pc[I]);
+      } else {
+        add(k, naddXCApprox, -1.0, 1, &bc[I], &pc[I]);
+        add(k, naddKinFunc, -1.0, 1, &bc[I], &pc[I]);
+      }
+    }
+    _dev->check(sxc_kernel_create(_dev->get(), g, nspin, _gga ? 1 : 0, &_tot));
+    add(_tot, naddXCApprox, 1.0, (int)bc.size(), bc.data(), pc.data());
+    add(_tot, naddKinFunc, 1.0, (int)bc.size(), bc.data(), pc.data());
+    _dev->check(sxc_kernel_create(_dev->get(), g, nspin, _gga ? 1 : 0, &_exact));
+    add(_exact, naddXCExact, 1.0, (int)bex.size(), bex.data(), pex.data());
+    add(_exact, naddXCApprox, -1.0, (int)bex.size(), bex.data(), pex.data());
+    add(_exact, naddKinFunc, -1.0, (int)bex.size(), bex.data(), pex.data());
+  }
   ~Kernel() {
     for (int k : _sub) sxc_kernel_destroy(_dev->get(), k);
     if (_tot >= 0) sxc_kernel_destroy(_dev->get(), _tot);
+    if (_exact >= 0) sxc_kernel_destroy(_dev->get(), _exact);
   }
   Kernel(const Kernel&) = delete;
   Kernel& operator=(const Kernel&) = delete;
@@ -839,9 +898,13 @@ class Kernel {
   std::vector<int> stores(unsigned I, unsigned J) const {
     std::vector<int> k;
     if (_tot >= 0) k.push_back(_tot);
+    // the store of the exactly embedded subsystems enters between two of them with the same mode (Kernel.cpp:182-189)
+    if (_exact >= 0 && _modes[I] == _modes[J] && isExact(I)) k.push_back(_exact);
     if (I == J) k.push_back(_sub[I]);
     return k;
   }
+  bool mixedEmbeddingUsed() const { return _exact >= 0; }
+  int exactStore() const { return _exact; }
   int totalStore() const { return _tot; }
   // Kernel::getPP(I, J, blockSize, iGridStart) (Kernel.cpp:170-230): first array(s) of the summed stores for one block
   std::vector<double> getPP(unsigned I, unsigned J, unsigned blockSize, unsigned iGridStart) const {
@@ -862,9 +925,14 @@ class Kernel {
   std::shared_ptr<B200::XCDevice> _dev;
   std::shared_ptr<GridController> _grid;
   std::vector<std::shared_ptr<DensityMatrixController<SCFMode>>> _dMats;
+  bool isExact(size_t I) const {
+    return !_modes.empty() &&
+           (_modes[I] == Options::KIN_EMBEDDING_MODES::LEVELSHIFT || _modes[I] == Options::KIN_EMBEDDING_MODES::HUZINAGA);
+  }
   bool _gga;
+  std::vector<Options::KIN_EMBEDDING_MODES> _modes;  // empty: not the mixed-embedding variant
   std::vector<int> _sub;
-  int _tot = -1;
+  int _tot = -1, _exact = -1;
 };
 
 // postHF/LRSCF/Sigmavectors/KernelSigmavector.h:40-123.  calcF(I, J, D) returns the Fock-like matrices of

@@ -210,6 +210,19 @@ int main(int argc, char** argv) {
         if (std::abs(p2->getEnergy(PA2) - pot->getEnergy(PA2)) > 1e-12) throw SerenityError("rebuilt grid gives another energy");
       }
     }
+    {
+      // mixed exact / approximate embedding (Kernel::calculateDerivativesMixedEmbedding, Kernel.cpp:752-888): subsystem A embedded
+      // exactly (LEVELSHIFT), B approximately; the three kinds of store and the rule that picks them for a pair (I, J)
+      using KM = Options::KIN_EMBEDDING_MODES;
+      Kernel<R::RESTRICTED> mixed(dev, grid, std::vector<std::shared_ptr<DMC>>{dA, dB}, std::vector<Functional>{xc, xc},
+                                  std::vector<KM>{KM::LEVELSHIFT, KM::NADD_FUNC}, /*naddXCExact*/ kin, /*naddXCApprox*/ xc, kin);
+      if (!mixed.mixedEmbeddingUsed() || mixed.stores(0, 0).size() != 3 || mixed.stores(0, 1).size() != 1 || mixed.stores(1, 1).size() != 2)
+        throw SerenityError("mixed-embedding kernel: wrong store selection");
+      for (auto ij : {std::make_pair(0u, 0u), std::make_pair(0u, 1u), std::make_pair(1u, 1u)}) {
+        std::vector<double> pp = mixed.getPP(ij.first, ij.second, 128, 256);
+        wr(out, pp.data(), 128);
+      }
+    }
     if (ngpu > 1) {
       // one process, ngpu GPUs: the same potential classes on a group device (sxc_group: one worker thread and context per GPU,
       // ncclAllReduce inside the library)

@@ -107,6 +107,7 @@ def test_cpp_potentials_match_oracle(tmp_path):
         lin = _r(f)
         V_comb, E_comb = _r(f, (nA, nA)), _r(f)
         F_sum, F_x, F_k, E_x, E_k = _r(f, (nA, nA)), _r(f, (nA, nA)), _r(f, (nA, nA)), _r(f), _r(f)
+        pp_mixed = [_r(f, (128,)) for _ in range(3)]
         if ngpu > 1:
             Vg, Eg, Fg, gradg, ng = _r(f, (nA, nA)), _r(f), _r(f, (nA, nA)), _r(f, (len(act.symbols), 3)), _r(f)
     og = orc.Grid(cfg.xyz, cfg.w, 128)
@@ -172,6 +173,15 @@ def test_cpp_potentials_match_oracle(tmp_path):
     assert np.abs(F_x - Vx_ref).max() <= 1e-8 and np.abs(F_k - Vk_ref).max() <= 1e-8
     assert abs(E_x - Ex_ref) <= 1e-9 and abs(E_k - Ek_ref) <= 1e-9
     assert np.abs(F_sum - (F_x + F_k)).max() <= 1e-14
+    # mixed exact / approximate embedding kernel (A exact with naddXCExact = kin, B approximate with naddXCApprox = xc, naddKin = kin):
+    #   tot = xc[rho_A + rho_B] + kin[rho_A + rho_B];  sub_A = xc[rho_A] - kin[rho_A];  sub_B = xc[rho_B] - xc[rho_B] - kin[rho_B];
+    #   exact = kin[rho_A] - xc[rho_A] - kin[rho_A];   getPP(0,0) = tot + exact + sub_A,  getPP(0,1) = tot,  getPP(1,1) = tot + sub_B
+    pp = lambda fn, r, g_: orc.kernel_store_r(fn, r, g_)[0, 256:384]
+    tot_pp = pp(fx, rt, gt) + pp(fk, rt, gt)
+    want_mixed = [tot_pp + (pp(fk, ra, ga) - pp(fx, ra, ga) - pp(fk, ra, ga)) + (pp(fx, ra, ga) - pp(fk, ra, ga)),
+                  tot_pp, tot_pp + (pp(fx, rb, gb) - pp(fx, rb, gb) - pp(fk, rb, gb))]
+    for got_pp, ref_pp in zip(pp_mixed, want_mixed):
+        assert np.abs(got_pp - ref_pp).max() <= 1e-6 * max(np.abs(ref_pp).max(), 1e-30)
     if ngpu > 1:
         assert ng == ngpu
         assert np.abs(Vg - want[3][0]).max() <= 1e-8 and abs(Eg - want[3][1]) <= 1e-9

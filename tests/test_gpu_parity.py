@@ -148,6 +148,21 @@ def test_supersystem_density_is_the_exact_sum(ctx, fixtures, small_mixed):
         assert np.array_equal(gs[k], ga[k] + ge[k])
 
 
+def test_density_is_bitwise_reproducible(ctx):
+    """k_density sums in a fixed order (its mbarrier-ordered cp.async ring is what compute-sanitizer's racecheck cannot follow,
+    profiles/r02_sanitizer.md): the same build twice gives the same bits, on a grid large enough for many CTAs per SM."""
+    cfg = _cfg("tetracene", 4)
+    assert (cfg.npts + 127) // 128 >= 900  # whole-block work items (a smaller shard is cut into segments that accumulate with atomics)
+    sub = cfg.subsystems[0]
+    g = ctx.set_grid(cfg.xyz, cfg.w, 128)
+    b = ctx.add_basis(sub.basis, 1e-9)
+    runs = [ctx.density_on_grid(g, b, sub.P, cfg.npts) for _ in range(3)]
+    for rho, grad in runs[1:]:
+        assert np.array_equal(rho, runs[0][0])
+        for k in range(3):
+            assert np.array_equal(grad[k], runs[0][1][k])
+
+
 def test_golden_scalar_to_matrix(ctx, fixtures, small_mixed):
     """ScalarOperatorToMatrixAdder_test.cpp:41-148 (55 elements, GGA variant, block size 3)."""
     gold = load_golden("scatter_ref.json")
