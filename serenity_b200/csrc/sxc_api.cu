@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -189,8 +190,10 @@ struct sxc_ctx {
   std::map<int, std::vector<ScatterRound>> scatter_tpl;  // round templates per s_pad / 32
   std::map<std::pair<int, int>, std::vector<ScatterRound2>> scatter_tpl2;  // v2 templates per (s_pad / 32, k-steps per chunk)
   // which scatter kernel runs: 0 = k_vmat (cp.async producers), 8 / 16 = k_vmat_tma<8 / 16> (TMA producer); SXC_VMAT overrides
-  // 24 = k_vmat_fg (k_form_g fused behind the DMMA warps of the TKP = 8 kernel; chunks cut into segments fall back to 8)
-  int vmat_variant = 24;
+  // 24 = k_vmat_fg (G formed by helper warpgroups inside the TKP = 8 kernel; chunks cut into segments fall back to 8).  Opt-in:
+  // measured against 16 on two kinds of box of the pool it is 3 % faster per build on one and equal (peptide: 1 % slower) on
+  // the other (profiles/r02_scatter_fused.md), and the two-launch form keeps the tensor kernel's time free of HBM work
+  int vmat_variant = 16;
   int dens_variant = 0;  // 0 = k_density (cp.async producers; 1-3 % faster as measured), 1 = k_density_tma; SXC_DENS overrides
   int dens_prefetch = 0;  // SXC_DPF: bit 0 = L2 prefetch of k_density's epilogue rows (measured: no effect), bit 1 = development
   int basis_variant = 0;  // SXC_BASIS: 1 = k_basis<1> (128 registers, one CTA per SM), 2 = k_basis<2> (64 registers, two CTAs), 0 = by size
@@ -2113,16 +2116,26 @@ int sxc_build_xc(sxc_ctx* ctx, int grid, int basis, int func, int nspin, const d
   CU(ctx->dP.ensure(nv * sizeof(double) + P_SLACK_BYTES));
   CU(ctx->dOut.ensure((nv + 2) * sizeof(double)));
   HostCall host_guard{ctx};
+  // SXC_TRACE=1 (development): host-side timeline of the call on stderr, microseconds since entry
+  static const bool trace = std::getenv("SXC_TRACE") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
+  auto us = [&] { return (long)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count(); };
   TRY(upload_async(ctx, ctx->dP.p, P, nv * sizeof(double)));
   TRY(upload_done(ctx));
   int rc = build_xc_device(ctx, grid, basis, func, nspin, ctx->dP.as<double>(), thr, ctx->dOut.as<double>(), true);
   ctx->timing = 0;
   if (rc != SXC_OK) return abort_build(ctx, rc);
+  const long t_launched = us();
   std::vector<double> tail(2);
   CU(cudaMemcpyAsync(tail.data(), ctx->dOut.as<double>() + nv, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  const long t_built = us();
   if (V) TRY(result_d2h(ctx, V, ctx->dOut.as<double>(), nv));
+  const long t_copied = us();
   CU(cudaStreamSynchronize(ctx->stream));
   collect_timers(ctx);
+  if (trace)
+    std::fprintf(stderr, "sxc_build_xc: launches issued %ld us, build done %ld us, V copied %ld us, return %ld us (device time %.1f us)\n",
+                 t_launched, t_built, t_copied, us(), 1e3 * ctx->stats.ms_total);
   *E = tail[0];
   if (nelec) *nelec = tail[1];
   return SXC_OK;

@@ -114,6 +114,31 @@ def test_config4_fde_water64_full_size_one_pass(ctx, orc, water64_grid):
     assert np.abs(V1 - Vs[1]).max() <= 1e-12 and np.abs(E1 - Es[1]).max() <= 1e-12
 
 
+def test_fused_scatter_variant_matches_oracle(orc, monkeypatch):
+    """SXC_VMAT=24 (opt-in): k_vmat_fg forms G inside the persistent scatter kernel (helper warpgroups, per-block flags).  Whole-block
+    work items need a shard of >= 3 waves of CTAs (tetracene at accuracy 4: 1083 blocks); a small grid takes its fallback."""
+    from serenity_b200.inputs import make_config
+    from serenity_b200.inputs.configs import FUNCTIONALS
+    from serenity_b200.xc import XCContext
+    monkeypatch.setenv("SXC_VMAT", "24")
+    c = XCContext(0)
+    try:
+        for name, acc, fn in (("tetracene", 4, "B3LYP"), ("water8", 3, "PBE"), ("h2o", 2, "LDA")):
+            cfg = make_config(name, acc)
+            sub = cfg.subsystems[0]
+            ids, mix = FUNCTIONALS[fn]
+            g = c.set_grid(cfg.xyz, cfg.w, 128)
+            b = c.add_basis(sub.basis, 1e-9)
+            f = c.set_functional(ids, mix)
+            for _ in range(2):  # (the second build reuses the plan and the per-block flags)
+                V, E, ne = c.build_xc(g, b, f, sub.P)
+            Vr, Er, ner, _ = orc.build_xc(orc.Basis(sub.basis), orc.Grid(cfg.xyz, cfg.w, 128), orc.Functional(ids, mix), sub.P)
+            assert abs(E - Er) <= 1e-9 and np.abs(V - Vr).max() <= 1e-8 and abs(ne - ner) <= 1e-10 * abs(ner), name
+            assert np.array_equal(V, V.T)
+    finally:
+        c.close()
+
+
 def test_config1_h2o_accuracy4(ctx, orc):
     """BASELINE configs[0]: H2O PBE/def2-SVP on the accuracy-4 grid (the reference's CPU-runnable case)."""
     from serenity_b200.inputs import make_config

@@ -46,7 +46,7 @@ def launches(path, out):
     for r in rows[hdr + 1:]:
         if len(r) <= vi or r[mi] != "gpu__time_duration.sum":
             continue
-        name = r[ki].split("(")[0]
+        name = r[ki].split("(")[0].replace("void ", "")
         a = agg.setdefault(name, [0, 0.0])
         a[0] += 1
         a[1] += float(r[vi].replace(",", ""))
