@@ -60,6 +60,12 @@ for name in names:
         out.append("| %s | %d | %.3f | %.3f | %.3f | %.3f | %.3f | %.3f | %.3f | %.3f | %.3f |" % (
             name, n, k["k_basis"], k["k_density"], k["k_functional"], k["k_form_g"], k["k_scatter"], k["finish"], k["allreduce"],
             sum(k.values()), s1 / n))
+fused = [(name, n) for name in names for n in sorted(table.get(name, {}))
+         if table[name][n]["kernels_ms_per_build"]["k_form_g"] == 0.0 and table[name][n]["kernels_ms_per_build"]["k_scatter"] > 0.0]
+if fused:
+    out += ["", "Lines with k_form_g = 0 (" + ", ".join("%s N = %d" % x for x in fused) + ") were measured while the fused scatter `k_vmat_fg` "
+            "(`SXC_VMAT=24`) was the default for whole-block shards: their scatter column contains the G phase.  On that pool of boxes "
+            "the fused and the two-launch build take the same time to within 1 % (profiles/r02_scatter_fused.md)."]
 clk = [(n, d.get("clocks", {})) for n, d in sorted(lines.items())]
 out += ["", "Clocks under load: " + "; ".join("N=%d %s MHz %s" % (n, c.get("sm_mhz"), c.get("reasons")) for n, c in clk), ""]
 open(os.path.join(ROOT, "profiles", "r02_scaling.md"), "w").write("\n".join(out))
