@@ -85,9 +85,19 @@ def build_jet_probe(force=False):
     return out
 
 
+def build_host_copy_test(force=False):
+    """csrc/host_copy.h (pageable <-> page-locked staging with worker threads) exercised without a GPU."""
+    src = os.path.join(ROOT, "tests", "cpp", "host_copy_test.cpp")
+    hdr = os.path.join(HERE, "csrc", "host_copy.h")
+    out = os.path.join(ROOT, "tests", "cpp", "host_copy_test")
+    if force or _newer(out, [src, hdr]):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-Wextra", "-pthread", "-o", out, src])
+    return out
+
+
 def build_all(force=False, verbose=False):
     return [build_cuda(force, verbose), build_inputs_helper(force), build_host_test(force), build_bridge_test(force),
-            build_jet_probe(force)]
+            build_jet_probe(force), build_host_copy_test(force)]
 
 
 if __name__ == "__main__":

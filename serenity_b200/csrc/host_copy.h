@@ -4,6 +4,9 @@
 // one thread (about 10 GB/s): 19 MB of P and V of a 1536-function system then cost more than 2 ms around a 5.8 ms build.  The
 // host-buffer entry points therefore stage large transfers themselves: a few persistent worker threads copy between the
 // caller's buffer and a page-locked staging buffer slice by slice while the DMA engine moves the slices that are ready.
+// Downloads are streamed: the job is opened once (one wake-up of the workers), the thread that owns the CUDA stream publishes how
+// many bytes of the staging buffer the DMA engine has delivered so far, and the workers copy every slice below that mark - the
+// memcpy of chunk c runs while chunk c + 1 is on the bus, with no per-chunk hand-shake.
 #pragma once
 
 #include <atomic>
@@ -37,16 +40,41 @@ class HostCopier {
       std::memcpy(dst, src, bytes);
       return;
     }
+    open(dst, src, bytes, bytes);
+    close();
+  }
+
+  // streamed form: open() hands the job to the workers with the first `avail` bytes of src valid, publish() raises that mark
+  // (monotonically, up to bytes), help() lets the caller copy slices that are ready without waiting, close() copies what is left
+  // and returns when every slice has landed.  With no workers the caller does all of it in help() / close().
+  void open(void* dst, const void* src, size_t bytes, size_t avail) {
     {
       std::lock_guard<std::mutex> lk(m_);
       dst_ = static_cast<char*>(dst);
       src_ = static_cast<const char*>(src);
       bytes_ = bytes;
+      avail_.store(avail, std::memory_order_release);
       next_.store(0);
       pending_ = (int)workers_.size();
       ++generation_;
     }
     cv_.notify_all();
+  }
+  void publish(size_t avail) { avail_.store(avail, std::memory_order_release); }
+  // copies at most one slice; false when the next unclaimed slice is not available yet (or none is left)
+  bool help() {
+    size_t off = next_.load(std::memory_order_relaxed);
+    for (;;) {
+      if (off >= bytes_) return false;
+      const size_t end = std::min(off + SLICE, bytes_);
+      if (avail_.load(std::memory_order_acquire) < end) return false;
+      if (next_.compare_exchange_weak(off, off + SLICE)) {
+        std::memcpy(dst_ + off, src_ + off, end - off);
+        return true;
+      }
+    }
+  }
+  void close() {
     work();
     std::unique_lock<std::mutex> lk(m_);
     done_cv_.wait(lk, [&] { return pending_ == 0; });
@@ -58,8 +86,17 @@ class HostCopier {
     for (;;) {
       const size_t off = next_.fetch_add(SLICE);
       if (off >= bytes_) break;
-      std::memcpy(dst_ + off, src_ + off, std::min(SLICE, bytes_ - off));
+      const size_t end = std::min(off + SLICE, bytes_);
+      while (avail_.load(std::memory_order_acquire) < end) cpu_relax();  // the DMA engine has not delivered this slice yet
+      std::memcpy(dst_ + off, src_ + off, end - off);
     }
+  }
+  static void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#else
+    std::this_thread::yield();
+#endif
   }
   void loop() {
     unsigned long seen = 0;
@@ -82,6 +119,7 @@ class HostCopier {
   const char* src_ = nullptr;
   size_t bytes_ = 0;
   std::atomic<size_t> next_{0};
+  std::atomic<size_t> avail_{0};
   int pending_ = 0;
   unsigned long generation_ = 0;
   bool stop_ = false;

@@ -249,7 +249,7 @@ struct sxc_ctx {
   void* h_down = nullptr;  // staging of the downloads (V)
   size_t h_up_bytes = 0, h_down_bytes = 0;
   std::vector<cudaEvent_t> chunk_events;
-  int copy_threads = 4;    // SXC_COPY_THREADS (0: leave pageable transfers to the driver)
+  int copy_threads = std::thread::hardware_concurrency() >= 16 ? 8 : 4;  // SXC_COPY_THREADS (0: leave pageable transfers to the driver)
   int out_part = 0, out_parts = 1;  // sxc_set_output_slice: this context copies back part out_part of out_parts of a result matrix
   struct Stamp {
     int slot;
@@ -368,7 +368,11 @@ int staged_h2d(sxc_ctx* ctx, void* dst, const void* src, size_t bytes, size_t st
   return SXC_OK;
 }
 
-// device -> caller memory, complete on return (the stream is synchronised up to the copy)
+// device -> caller memory, complete on return (the stream is synchronised up to the copy).  Pageable destinations of >= 1 MB:
+// the DMA engine delivers D2H_CHUNK pieces into the page-locked staging buffer, each followed by an event; the copier job is
+// opened when the first piece has arrived and the calling thread only raises the "delivered" mark event by event (copying slices
+// itself while the next event is pending), so the memcpy into the caller's pages overlaps with the rest of the transfer.
+constexpr size_t D2H_CHUNK = (size_t)512 << 10;
 int staged_d2h(sxc_ctx* ctx, void* dst, const void* src, size_t bytes, cudaStream_t stream) {
   if (ctx->copy_threads <= 0 || bytes < STAGE_MIN_BYTES || !is_pageable(dst)) {
     CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
@@ -376,7 +380,7 @@ int staged_d2h(sxc_ctx* ctx, void* dst, const void* src, size_t bytes, cudaStrea
     return SXC_OK;
   }
   TRY(ensure_staging(ctx, &ctx->h_down, &ctx->h_down_bytes, bytes));
-  const size_t nchunk = (bytes + STAGE_CHUNK - 1) / STAGE_CHUNK;
+  const size_t nchunk = (bytes + D2H_CHUNK - 1) / D2H_CHUNK;
   while (ctx->chunk_events.size() < nchunk) {
     cudaEvent_t e = nullptr;
     CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -384,15 +388,27 @@ int staged_d2h(sxc_ctx* ctx, void* dst, const void* src, size_t bytes, cudaStrea
   }
   char* st = static_cast<char*>(ctx->h_down);
   for (size_t c = 0; c < nchunk; ++c) {
-    const size_t off = c * STAGE_CHUNK, n = std::min(STAGE_CHUNK, bytes - off);
+    const size_t off = c * D2H_CHUNK, n = std::min(D2H_CHUNK, bytes - off);
     CU(cudaMemcpyAsync(st + off, static_cast<const char*>(src) + off, n, cudaMemcpyDeviceToHost, stream));
     CU(cudaEventRecord(ctx->chunk_events[c], stream));
   }
-  for (size_t c = 0; c < nchunk; ++c) {
-    const size_t off = c * STAGE_CHUNK, n = std::min(STAGE_CHUNK, bytes - off);
-    CU(cudaEventSynchronize(ctx->chunk_events[c]));
-    ctx->copier->copy(static_cast<char*>(dst) + off, st + off, n);
+  cudaError_t err = cudaEventSynchronize(ctx->chunk_events[0]);
+  if (err != cudaSuccess) return fail(ctx, SXC_ERR_CUDA, "staged_d2h: %s", cudaGetErrorString(err));
+  ctx->copier->open(dst, st, bytes, std::min(D2H_CHUNK, bytes));
+  for (size_t c = 1; c < nchunk && err == cudaSuccess; ++c) {
+    while ((err = cudaEventQuery(ctx->chunk_events[c])) == cudaErrorNotReady) {
+      cudaGetLastError();  // "not ready" is recorded like an error; it must not surface in a later check
+      if (!ctx->copier->help()) {  // nothing to copy: block until the piece is there
+        err = cudaEventSynchronize(ctx->chunk_events[c]);
+        break;
+      }
+    }
+    if (err == cudaSuccess) ctx->copier->publish(std::min((c + 1) * D2H_CHUNK, bytes));
   }
+  if (err != cudaSuccess) cudaGetLastError();
+  ctx->copier->publish(bytes);  // (on an error too: the job has to drain before the buffers can be reused)
+  ctx->copier->close();
+  if (err != cudaSuccess) return fail(ctx, SXC_ERR_CUDA, "staged_d2h: %s", cudaGetErrorString(err));
   return SXC_OK;
 }
 

@@ -26,6 +26,13 @@ def test_adapter_fails_loudly_without_device():
     assert r.returncode == 0 and "SerenityError" in r.stdout and "no CPU fallback" in r.stdout
 
 
+def test_host_copier_streams_every_byte_once():
+    """csrc/host_copy.h: the streamed download job of staged_d2h (open / publish / help / close) for 0...7 workers, ragged sizes."""
+    from serenity_b200 import build
+    r = subprocess.run([build.build_host_copy_test()], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "host_copy_test: ok" in r.stdout, r.stdout
+
+
 def test_resolve_functional_matches_the_python_table():
     """CompositeFunctionals::resolveFunctional of the adapter (host only) against serenity_b200.inputs.configs.FUNCTIONALS, both
     restating dft/functionals/functional_definitions.dat."""
