@@ -274,12 +274,19 @@ k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, cons
             ++pass;
           }
         }
-        // reduce over the 4 lanes of a fragment row; lane lc == 0 owns the (jw, point) slot of the CTA scratch
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          r[m] += __shfl_xor_sync(0xffffffffu, r[m], 1);
-          r[m] += __shfl_xor_sync(0xffffffffu, r[m], 2);
-          if (lc == 0) red[((size_t)jw * BP + pw * 32 + m * 8 + lr) * 4 + comp] += r[m];
+        // reduce over the 4 lanes of a fragment row.  FP64 vector instructions queue behind the DMMAs of the SM's other warps (a
+        // DADD / DFMA waits ~4x as long as a DMMA in the stall samples of profiles/r02_ncu_full_water64.md), so the four sums are
+        // reduced as a 4 x 4 transpose - lane lc ends up with the total of m = lc: 3 DADD + 3 shuffles and one update of the CTA
+        // scratch by every lane, instead of 8 + 8 and four predicated updates.  Same additions in the same order (pairs lc ^ 1,
+        // then lc ^ 2): bit-identical results.
+        {
+          const bool b0 = lc & 1, b1 = lc & 2;
+          const double k0 = b0 ? r[1] : r[0], k1 = b0 ? r[3] : r[2];
+          const double s0 = b0 ? r[0] : r[1], s1 = b0 ? r[2] : r[3];
+          const double a0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 1);  // m = b0,     lanes lc, lc ^ 1
+          const double a1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 1);  // m = 2 + b0
+          const double t = (b1 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, b1 ? a0 : a1, 2);  // m = lc, all four lanes
+          red[((size_t)jw * BP + pw * 32 + lc * 8 + lr) * 4 + comp] += t;
         }
       }
     }

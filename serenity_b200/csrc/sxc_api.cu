@@ -249,7 +249,8 @@ struct sxc_ctx {
   void* h_down = nullptr;  // staging of the downloads (V)
   size_t h_up_bytes = 0, h_down_bytes = 0;
   std::vector<cudaEvent_t> chunk_events;
-  int copy_threads = std::thread::hardware_concurrency() >= 16 ? 8 : 4;  // SXC_COPY_THREADS (0: leave pageable transfers to the driver)
+  int copy_threads = 4;    // SXC_COPY_THREADS (0: leave pageable transfers to the driver); measured on a 16-core box with the 18.9 MB
+                           // matrix of (H2O)64: 4 threads 6.08 ms end to end, 8: 6.66, 16: 6.97 - the DMA engine delivers what ~3 memcpy threads move
   int out_part = 0, out_parts = 1;  // sxc_set_output_slice: this context copies back part out_part of out_parts of a result matrix
   struct Stamp {
     int slot;
