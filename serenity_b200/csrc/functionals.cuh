@@ -317,12 +317,13 @@ __host__ inline bool functional_id_supported(int id) {
 //   out_v[0..3] (+)= sign * {dF/drho, dF/dgx, dF/dgy, dF/dgz};  e_part[lb] = sum_p w F;  n_part[lb] = sum_p w rho
 // lit_blocks == nullptr: block index = blockIdx.x.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(FUNC_BLOCK)
-k_functional(FuncView f, long npts, const int* __restrict__ lit_blocks, const double* __restrict__ w,
-             const double* __restrict__ rho, const double* __restrict__ gx, const double* __restrict__ gy,
-             const double* __restrict__ gz, double sign, int accumulate, double* __restrict__ epuv,
-             double* __restrict__ v_rho, double* __restrict__ v_gx, double* __restrict__ v_gy,
-             double* __restrict__ v_gz, double* __restrict__ e_part, double* __restrict__ n_part) {
+__device__ __forceinline__ void functional_block(const FuncView& f, long npts, const int* __restrict__ lit_blocks,
+                                                 const double* __restrict__ w, const double* __restrict__ rho,
+                                                 const double* __restrict__ gx, const double* __restrict__ gy,
+                                                 const double* __restrict__ gz, double sign, int accumulate,
+                                                 double* __restrict__ epuv, double* __restrict__ v_rho, double* __restrict__ v_gx,
+                                                 double* __restrict__ v_gy, double* __restrict__ v_gz, double* __restrict__ e_part,
+                                                 double* __restrict__ n_part) {
   __shared__ double scratch[32];
   const int lb = lit_blocks ? lit_blocks[blockIdx.x] : blockIdx.x;
   const long first = (long)lb * FUNC_BLOCK;
@@ -386,6 +387,27 @@ k_functional(FuncView f, long npts, const int* __restrict__ lit_blocks, const do
     if (e_part) e_part[lb] = e;
     if (n_part) n_part[lb] = ne;
   }
+}
+
+__global__ void __launch_bounds__(FUNC_BLOCK)
+k_functional(FuncView f, long npts, const int* __restrict__ lit_blocks, const double* __restrict__ w,
+             const double* __restrict__ rho, const double* __restrict__ gx, const double* __restrict__ gy,
+             const double* __restrict__ gz, double sign, int accumulate, double* __restrict__ epuv,
+             double* __restrict__ v_rho, double* __restrict__ v_gx, double* __restrict__ v_gy,
+             double* __restrict__ v_gz, double* __restrict__ e_part, double* __restrict__ n_part) {
+  functional_block(f, npts, lit_blocks, w, rho, gx, gy, gz, sign, accumulate, epuv, v_rho, v_gx, v_gy, v_gz, e_part, n_part);
+}
+
+// The same kernel compiled for MINB resident CTAs per SM (128 / 96 registers instead of 168, a few spilled doubles): the dependent
+// FP64 chains of a functional leave the pipe idle with 12 warps per SM; SXC_FUNC selects it (measured in profiles/README.md).
+template <int MINB>
+__global__ void __launch_bounds__(FUNC_BLOCK, MINB)
+k_functional_occ(FuncView f, long npts, const int* __restrict__ lit_blocks, const double* __restrict__ w,
+                 const double* __restrict__ rho, const double* __restrict__ gx, const double* __restrict__ gy,
+                 const double* __restrict__ gz, double sign, int accumulate, double* __restrict__ epuv,
+                 double* __restrict__ v_rho, double* __restrict__ v_gx, double* __restrict__ v_gy,
+                 double* __restrict__ v_gz, double* __restrict__ e_part, double* __restrict__ n_part) {
+  functional_block(f, npts, lit_blocks, w, rho, gx, gy, gz, sign, accumulate, epuv, v_rho, v_gx, v_gy, v_gz, e_part, n_part);
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -196,6 +196,8 @@ struct sxc_ctx {
   int vmat_variant = 16;
   int dens_variant = 0;  // 0 = k_density (cp.async producers; 1-3 % faster as measured), 1 = k_density_tma; SXC_DENS overrides
   int dens_prefetch = 0;  // SXC_DPF: bit 0 = L2 prefetch of k_density's epilogue rows (measured: no effect), bit 1 = development
+  int func_variant = 4;   // SXC_FUNC: 4 / 5 = k_functional_occ<4 / 5> (restricted functional kernel at 4 / 5 CTAs per SM), 0 = k_functional
+                          // (measured: peptide 0.416 / 0.373 / 0.363 ms, fde (H2O)64 0.412 / 0.372 / 0.369, tetracene 0.090 / 0.081 / 0.082)
   int basis_variant = 0;  // SXC_BASIS: 1 = k_basis<1> (128 registers, one CTA per SM), 2 = k_basis<2> (64 registers, two CTAs), 0 = by size
   int seg_waves = 6;  // SXC_SEG_WAVES: a shard with fewer blocks than 3 waves of resident CTAs is cut into items for this many waves
   int fg_lead = 0;   // SXC_FG_LEAD (development): k_vmat_fg's queue opens with medium-sized blocks (get_plan)
@@ -1157,10 +1159,10 @@ int phase_functional(sxc_ctx* ctx, const Grid& g, const Plan& p, const Chunk& c,
     k_functional_u<<<nb, FUNC_BLOCK, 0, ctx->stream>>>(f, N, list, gv.w, dens, sign, accumulate, nullptr, pot, e_part,
                                                        n_part);
   } else {
-    k_functional<<<nb, FUNC_BLOCK, 0, ctx->stream>>>(f, N, list, gv.w, dens, dens + N, dens + 2 * N, dens + 3 * N, sign,
-                                                     accumulate, nullptr, pot, f.gga ? pot + N : nullptr,
-                                                     f.gga ? pot + 2 * N : nullptr, f.gga ? pot + 3 * N : nullptr, e_part,
-                                                     n_part);
+    auto kern = ctx->func_variant == 4 ? k_functional_occ<4> : ctx->func_variant == 5 ? k_functional_occ<5> : k_functional;
+    kern<<<nb, FUNC_BLOCK, 0, ctx->stream>>>(f, N, list, gv.w, dens, dens + N, dens + 2 * N, dens + 3 * N, sign, accumulate, nullptr,
+                                             pot, f.gga ? pot + N : nullptr, f.gga ? pot + 2 * N : nullptr,
+                                             f.gga ? pot + 3 * N : nullptr, e_part, n_part);
   }
   LAUNCH_CHECK();
   return SXC_OK;
@@ -1839,6 +1841,7 @@ int sxc_create(sxc_ctx** out, int device) {
   if (const char* v = std::getenv("SXC_DENS")) ctx->dens_variant = std::atoi(v) ? 1 : 0;
   if (const char* v = std::getenv("SXC_COPY_THREADS")) ctx->copy_threads = std::max(0, std::min(16, std::atoi(v)));
   if (const char* v = std::getenv("SXC_DPF")) ctx->dens_prefetch = std::atoi(v);
+  if (const char* v = std::getenv("SXC_FUNC")) ctx->func_variant = std::atoi(v);
   if (const char* v = std::getenv("SXC_BASIS")) ctx->basis_variant = std::max(0, std::min(2, std::atoi(v)));
   if (const char* v = std::getenv("SXC_SEG_WAVES")) ctx->seg_waves = std::max(1, std::atoi(v));
   if (const char* v = std::getenv("SXC_FG_LEAD")) ctx->fg_lead = std::atoi(v);
