@@ -106,7 +106,7 @@ k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, cons
   using namespace dens;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* stage_base = reinterpret_cast<double*>(smem_raw);
-  double* red = stage_base + PSTAGES * PSTAGE_ELEMS;        // [NJW][128][4]
+  double* red = stage_base + PSTAGES * PSTAGE_ELEMS;        // [NJW][4][128]
   int* sig = reinterpret_cast<int*>(red + NJW * BP * 4);    // [s_pad + TJ]
 
   const WorkItem item = items[blockIdx.x];
@@ -286,7 +286,7 @@ k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, cons
           const double a0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 1);  // m = b0,     lanes lc, lc ^ 1
           const double a1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 1);  // m = 2 + b0
           const double t = (b1 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, b1 ? a0 : a1, 2);  // m = lc, all four lanes
-          red[((size_t)jw * BP + pw * 32 + lc * 8 + lr) * 4 + comp] += t;
+          red[(jw * 4 + comp) * BP + pw * 32 + lc * 8 + lr] += t;  // [jw][comp][point]: the 32 lanes hit 32 consecutive doubles
         }
       }
     }
@@ -296,11 +296,11 @@ k_density(GridView g, PlanView plan, int nbf, const double* __restrict__ P, cons
     double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
 #pragma unroll
     for (int jj = 0; jj < NJW; ++jj) {  // fixed order over the function-group warps
-      const double* a = red + ((size_t)jj * BP + tid) * 4;
+      const double* a = red + (size_t)jj * 4 * BP + tid;
       r0 += a[0];
-      r1 += a[1];
-      r2 += a[2];
-      r3 += a[3];
+      r1 += a[BP];
+      r2 += a[2 * BP];
+      r3 += a[3 * BP];
     }
     if (partial) {  // several CTAs share the block: the (pre-zeroed) outputs are accumulated
       atomicAdd(rho + first + tid, r0);
