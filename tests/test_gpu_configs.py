@@ -139,6 +139,35 @@ def test_fused_scatter_variant_matches_oracle(orc, monkeypatch):
         c.close()
 
 
+def test_functional_kernel_occupancy_variants_agree(monkeypatch):
+    """SXC_FUNC = 0 / 4 (default) / 5: k_functional compiled for 3 / 4 / 5 resident CTAs per SM (168 / 128 / 96 registers, the
+    smaller ones with a few spilled doubles).  Register allocation must not change E_xc, V_xc or the electron count beyond
+    rounding (B3LYP = four basic functionals; the scatter's red.global order is run-to-run noise at the 1e-15 level)."""
+    from serenity_b200.inputs import make_config
+    from serenity_b200.inputs.configs import FUNCTIONALS
+    from serenity_b200.xc import XCContext
+    cfg = make_config("water8", 3)
+    sub = cfg.subsystems[0]
+    out = {}
+    for variant in ("0", "4", "5"):
+        monkeypatch.setenv("SXC_FUNC", variant)
+        c = XCContext(0)
+        try:
+            g = c.set_grid(cfg.xyz, cfg.w, 128)
+            b = c.add_basis(sub.basis, 1e-9)
+            for fn in ("B3LYP", "PBE"):
+                f = c.set_functional(*FUNCTIONALS[fn])
+                out[variant, fn] = c.build_xc(g, b, f, sub.P)
+        finally:
+            c.close()
+    for fn in ("B3LYP", "PBE"):
+        V0, E0, n0 = out["0", fn]
+        for variant in ("4", "5"):
+            V, E, n = out[variant, fn]
+            assert abs(E - E0) <= 1e-11 and n == n0, (variant, fn, E - E0)
+            assert np.abs(V - V0).max() <= 1e-12, (variant, fn)
+
+
 def test_config1_h2o_accuracy4(ctx, orc):
     """BASELINE configs[0]: H2O PBE/def2-SVP on the accuracy-4 grid (the reference's CPU-runnable case)."""
     from serenity_b200.inputs import make_config
