@@ -123,7 +123,9 @@ int sxc_set_timing(sxc_ctx* ctx, int on);
 int sxc_set_output_slice(sxc_ctx* ctx, int part, int parts);
 
 /* Optional page-locked host memory (cudaHostAlloc) for the P / V buffers of the host-buffer builds: with it their copies are
- * asynchronous DMA; with ordinary (pageable) caller memory - what Eigen matrices in Serenity are - the driver stages them. */
+ * asynchronous DMA.  With ordinary (pageable) caller memory - what Eigen matrices in Serenity are - transfers of >= 1 MB are
+ * staged by the library through its own page-locked buffer with a few host threads (SXC_COPY_THREADS, default 4; uploads behind
+ * the basis kernel, downloads streamed in 512 KB pieces so that the memcpy overlaps the DMA); smaller ones are left to the driver. */
 void* sxc_host_alloc(size_t bytes);
 void sxc_host_free(void* p);
 
